@@ -1,0 +1,162 @@
+/* lds_b200.h — C ABI of liblds_b200.so: the B200 (sm_100a) hot path of LDS-GNN's outer step.
+ *
+ * The reference (andreas-grafberger/lds-gnn) is pure Python/PyTorch and has no FFI of its own; the
+ * boundary it offers for this path is its Python API. Every entry point below names
+ * the reference function(s) it replaces (paths relative to the reference repo). INTEGRATION.md shows
+ * the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless the comment says "host". The library never allocates or
+ *    frees caller-visible memory and keeps no pointer after a call returns. Scratch is passed in
+ *    (`workspace`, `workspace_bytes`) and sized by the matching `*_workspace_bytes` query.
+ *  - `stream` is a `cudaStream_t` passed as `void*`. Calls are asynchronous, never synchronise the
+ *    host, never allocate, and are CUDA-graph capturable.
+ *  - Return value: LDS_OK or an LDS_ERR_* code; `lds_last_error()` gives a thread-local message.
+ *    Nothing throws or aborts across the ABI.
+ *  - theta is stored as a full symmetric N x ld fp32 matrix (`ld = lds_padded_ld(N)`), unclamped like
+ *    the reference's `probs` (src/models/graph.py:60-61); the (T,) upper-triangle vector of the
+ *    reference is converted at the API edge (lds_theta_triu_to_full / lds_theta_full_to_triu).
+ *  - A_tilde is the sampled adjacency WITH self loops as bf16 {0,1}, N x ld. The normalisation
+ *    D^-1/2 A_tilde D^-1/2 (src/utils/graph.py:136-153) is carried as the fp32 vector r = deg^-1/2
+ *    and folded into the skinny operands:  A_hat P = r * (A_tilde (r * P)).
+ */
+#ifndef LDS_B200_H
+#define LDS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDS_OK               0
+#define LDS_ERR_ARG          1   /* bad shape / alignment / null pointer (mirrors the reference's asserts) */
+#define LDS_ERR_CUDA         2   /* a CUDA runtime/driver call failed; message holds the CUDA error string  */
+#define LDS_ERR_UNSUPPORTED  3   /* device is not sm_100 or a size is outside the compiled range             */
+#define LDS_ERR_WORKSPACE    4   /* workspace too small                                                       */
+
+/* K1 flags */
+#define LDS_K1_EXPLICIT_U    1u  /* read uniforms from `u_explicit` (parity mode) instead of Philox           */
+/* K2 flags */
+#define LDS_K2_SIMT          1u  /* CUDA-core validation kernel instead of the tcgen05 kernel (tests only)    */
+#define LDS_K2_SINGLE_BF16   2u  /* operand as one bf16 term instead of the hi+lo split                       */
+/* K3 flags */
+#define LDS_K3_DENSE_GRAD    1u  /* write dL/dA_tilde (dense, not symmetrised) instead of updating theta      */
+#define LDS_K3_ACCUMULATE    2u  /* with DENSE_GRAD: add into grad_out instead of overwriting                  */
+/* optimiser kinds (src/models/factory.py:66-69 uses SGD; Adam is the north-star's option)                   */
+#define LDS_OPT_SGD          0
+#define LDS_OPT_ADAM         1
+/* Philox streams */
+#define LDS_STREAM_EDGES     0u
+#define LDS_STREAM_DROP_X    1u
+#define LDS_STREAM_DROP_H    2u
+
+int32_t     lds_version(void);
+const char* lds_last_error(void);                 /* host; thread-local, never NULL                        */
+int32_t     lds_device_check(void);               /* LDS_OK iff the current device is compute capability 10.x */
+int64_t     lds_padded_ld(int32_t n);             /* row stride (elements) used for theta / A_tilde: round_up(n, 64) */
+
+/* Host-side restatement of the device draw, for the oracle: the uniform in [0,1) that element (i, j)
+ * of `stream` receives at (seed, step, sample). Edges are keyed on (min(i,j), max(i,j)). */
+float lds_philox_uniform(uint64_t seed, uint64_t step, uint32_t stream, uint32_t sample, uint32_t i, uint32_t j);
+
+/* ---- a1/a2: theta layouts. Replaces get_triu_values (src/utils/graph.py:41-45) and the scatter+mirror of
+ * triu_values_to_symmetric_matrix (src/utils/graph.py:166-181). `clamp01` applies that function's clamp. */
+int32_t lds_theta_triu_to_full(const float* triu, float* theta_full, int64_t ld, int32_t n, int32_t clamp01, void* stream);
+/* sym_sum = 0: out[idx(i,j)] = in[i][j];  sym_sum = 1: out[idx(i,j)] = in[i][j] + in[j][i] (i<j), in[i][i] (i=j)
+ * — the backward of the mirror (autograd of src/utils/graph.py:35-37 + 176). */
+int32_t lds_theta_full_to_triu(const float* full, int64_t ld, float* triu, int32_t n, int32_t sym_sum, void* stream);
+/* project_parameters -> ParameterClamper (src/models/graph.py:16-20, 63-64) on the full matrix. */
+int32_t lds_theta_clamp(float* theta_full, int64_t ld, int32_t n, void* stream);
+/* statistics() (src/models/graph.py:69-78): out4 (device, double[4]) = { sum of clamp(theta_full) over all N*N,
+ * sum of theta over the upper triangle incl. diagonal, min, max over that triangle }. */
+int32_t lds_theta_stats(const float* theta_full, int64_t ld, int32_t n, double* out4, void* stream);
+
+/* ---- K1 (a2,a3,a5,a6,a7): Bernoulli sample from the upper-triangle draw, mirror, self loops, row-sum
+ * degrees, r = deg^-1/2 in one pass over rows [row0, row0+rows) of theta. Replaces
+ * BernoulliGraphModel.forward + Sampler.sample/sample_graph (src/models/graph.py:29-32,66-67;
+ * src/models/sampling.py:47-85) + add_self_loops/normalize_adjacency_matrix (src/utils/graph.py:123-153).
+ * theta_full points at global row `row0` (row-block shard); row0 must be even.
+ * a_out   bf16 [rows][ld_a]  A_tilde (diag = 1), columns >= n zeroed.           (may be NULL)
+ * sample_out fp32 [rows][ld_s] the raw sample incl. the SAMPLED diagonal (what sample() returns). (may be NULL)
+ * deg_out, rsqrt_out fp32 [rows].
+ * u_explicit fp32 [n][ld_u] full matrix of uniforms (flag LDS_K1_EXPLICIT_U); element (i,j) uses
+ * u[min][max], exactly the reference's "upper-triangle draw wins" (src/models/sampling.py:76). */
+int32_t lds_k1_sample_normalize(const float* theta_full, int64_t ld_theta, int32_t n, int32_t row0, int32_t rows,
+                                uint64_t seed, uint64_t step, uint32_t sample,
+                                const float* u_explicit, int64_t ld_u,
+                                void* a_out, int64_t ld_a, float* sample_out, int64_t ld_s,
+                                float* deg_out, float* rsqrt_out, uint32_t flags, void* stream);
+
+/* ---- K2 (a8's torch.mm(dense_adj, .), src/models/layers.py:44, and its transposes in backward):
+ *   z_out[rows][width] = scale_out * ( A[rows][n] @ (scale_in * p[n][width]) )
+ * A bf16 (TMA -> tcgen05.mma, fp32 accumulation in TMEM), p split into bf16 hi+lo terms.
+ * scale_in [n] / scale_out [rows] may be NULL (= 1). width <= 128. */
+int64_t lds_k2_workspace_bytes(int32_t n, int32_t rows, int32_t width);
+int32_t lds_k2_propagate(const void* a, int64_t ld_a, int32_t n, int32_t rows,
+                         const float* p, int64_t ld_p, int32_t width,
+                         const float* scale_in, const float* scale_out,
+                         float* z_out, int64_t ld_z,
+                         void* workspace, int64_t workspace_bytes, uint32_t flags, void* stream);
+
+/* ---- K3+K4 (a10's theta part, a11): closed-form straight-through gradient + optimiser step + projection
+ * for rows [row0, row0+rows):   g_ij = fa_i.fb_j + fb_i.fa_j + c_i + c_j  (i != j),  0 on the diagonal,
+ * masked where theta is outside [0,1] (clamp backward), then
+ *   SGD : theta <- clamp(theta - lr g, 0, 1)                  (src/models/factory.py:66-69, outer.py:78-83)
+ *   Adam: torch.optim.Adam defaults on (m, v), step count t (1-based), then the same clamp.
+ * fa = r * (dZ1 | dZ2), fb = r * (P1 | P2), each [n][ld_f] fp32 with `d` used columns (d <= 512).
+ * With LDS_K3_DENSE_GRAD nothing is updated: grad_out[rows][ld_g] (+)= fa_i.fb_j + c_i (0 on the diagonal),
+ * i.e. dL/d(sample) of ONE propagate, for the composable autograd path. */
+int32_t lds_k3k4_theta_update(float* theta_full, int64_t ld_theta, int32_t n, int32_t row0, int32_t rows,
+                              const float* fa, const float* fb, int64_t ld_f, int32_t d, const float* cvec,
+                              float lr, int32_t opt_kind, float* adam_m, float* adam_v,
+                              float beta1, float beta2, float eps, int32_t t,
+                              float* grad_out, int64_t ld_g, uint32_t flags, void* stream);
+
+/* ---- fused direct outer step (a4..a11): one OuterProblemTrainer.train_step (src/trainers/outer.py:57-87)
+ * with gcn_predict_fct = InnerProblemTrainer.model_forward (src/trainers/inner.py:76-78) at fixed weights,
+ * regularize = False. Enqueues K1, the feature GEMM with fused dropout, 4 x K2 with their row epilogues
+ * (scaling, relu, dropout, second linear, log-softmax, NLL/accuracy, backward chain), K3+K4. */
+typedef struct lds_outer_step_args {
+  uint32_t struct_bytes;      /* sizeof(lds_outer_step_args), checked                                   */
+  int32_t  n, f, h, c;        /* nodes, features, hidden, classes                                       */
+  float*   theta_full;        /* [n][ld_theta] fp32, updated in place                                   */
+  int64_t  ld_theta;
+  const float*   x;           /* [n][ld_x] fp32, ld_x % 4 == 0                                          */
+  int64_t  ld_x;
+  const float*   w0;          /* [h][ld_w0] fp32 (layer_in.fc.weight), ld_w0 % 4 == 0                   */
+  int64_t  ld_w0;
+  const float*   b0;          /* [h]                                                                    */
+  const float*   w1;          /* [c][h] contiguous (layer_out.fc.weight)                                */
+  const float*   b1;          /* [c]                                                                    */
+  const int64_t* y;           /* [n] labels                                                             */
+  const uint8_t* mask;        /* [n] 0/1: rows in the outer objective (opt_mask)                        */
+  int32_t  mask_count;        /* number of ones in mask                                                 */
+  float    dropout_p;         /* 0 disables dropout (eval mode)                                         */
+  uint64_t seed, step;        /* Philox key / step counter                                              */
+  const float* u_explicit;    /* optional [n][ld_u] explicit edge uniforms (parity mode), else NULL     */
+  int64_t  ld_u;
+  const uint8_t* keep_x;      /* optional explicit dropout keep masks [n][f], [n][h] (parity mode)      */
+  const uint8_t* keep_h;
+  float    lr;                /* learning rate used by this step                                        */
+  int32_t  opt_kind;          /* LDS_OPT_*                                                              */
+  float*   adam_m; float* adam_v; float beta1, beta2, eps; int32_t adam_t;
+  int32_t  update;            /* 1: apply K3+K4; 0: forward + backward factors only                     */
+  float*   out_scalars;       /* [4] fp32: loss, accuracy, reserved, reserved                            */
+  float*   out_logp;          /* optional [n][c] log-probabilities, else NULL                           */
+  void*    workspace; int64_t workspace_bytes;
+  uint32_t k2_flags;          /* LDS_K2_* for the four propagations                                      */
+  uint32_t reserved;
+} lds_outer_step_args;
+
+int64_t lds_outer_step_workspace_bytes(int32_t n, int32_t f, int32_t h, int32_t c);
+int32_t lds_outer_step(const lds_outer_step_args* args, void* stream);
+/* Device pointers into a workspace laid out by lds_outer_step (for tests / the composable path):
+ * which: 0 A_tilde(bf16) 1 deg 2 rsqrt 3 P1 4 Z1 5 P2 6 Z2 7 dZ2 8 dP2 9 dZ1 10 dP1 11 fa 12 fb 13 cvec. */
+void*   lds_outer_step_buffer(void* workspace, int32_t n, int32_t f, int32_t h, int32_t c, int32_t which);
+int64_t lds_outer_step_factor_ld(int32_t h, int32_t c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDS_B200_H */

@@ -1,0 +1,116 @@
+"""ctypes binding of liblds_b200.so (C ABI declared in include/lds_b200.h).
+
+There is no CPU or PyTorch fallback: if the library is missing, or the device is not sm_100, every
+compute entry point raises. Loading the library and reading its symbols works without a GPU.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_int64, c_uint8, c_uint32, c_uint64, c_void_p
+
+from . import _build
+
+LDS_OK = 0
+K1_EXPLICIT_U = 1
+K2_SIMT, K2_SINGLE_BF16 = 1, 2
+K3_DENSE_GRAD, K3_ACCUMULATE = 1, 2
+OPT_SGD, OPT_ADAM = 0, 1
+STREAM_EDGES, STREAM_DROP_X, STREAM_DROP_H = 0, 1, 2
+
+# every symbol include/lds_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "lds_version": (c_int32, []),
+    "lds_last_error": (c_char_p, []),
+    "lds_device_check": (c_int32, []),
+    "lds_padded_ld": (c_int64, [c_int32]),
+    "lds_philox_uniform": (c_float, [c_uint64, c_uint64, c_uint32, c_uint32, c_uint32, c_uint32]),
+    "lds_theta_triu_to_full": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
+    "lds_theta_full_to_triu": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p]),
+    "lds_theta_clamp": (c_int32, [c_void_p, c_int64, c_int32, c_void_p]),
+    "lds_theta_stats": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
+    "lds_k1_sample_normalize": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_uint64, c_uint64, c_uint32,
+                                          c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
+                                          c_uint32, c_void_p]),
+    "lds_k2_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32]),
+    "lds_k2_propagate": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_void_p,
+                                   c_void_p, c_int64, c_void_p, c_int64, c_uint32, c_void_p]),
+    "lds_k3k4_theta_update": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_int32,
+                                        c_void_p, c_float, c_int32, c_void_p, c_void_p, c_float, c_float, c_float, c_int32,
+                                        c_void_p, c_int64, c_uint32, c_void_p]),
+    "lds_outer_step_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
+    "lds_outer_step": (c_int32, [c_void_p, c_void_p]),
+    "lds_outer_step_buffer": (c_void_p, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32]),
+    "lds_outer_step_factor_ld": (c_int64, [c_int32, c_int32]),
+}
+
+
+class OuterStepArgs(Structure):
+    """Mirror of `lds_outer_step_args` (include/lds_b200.h); `struct_bytes` is checked by the library."""
+    _fields_ = [
+        ("struct_bytes", c_uint32),
+        ("n", c_int32), ("f", c_int32), ("h", c_int32), ("c", c_int32),
+        ("theta_full", c_void_p), ("ld_theta", c_int64),
+        ("x", c_void_p), ("ld_x", c_int64),
+        ("w0", c_void_p), ("ld_w0", c_int64),
+        ("b0", c_void_p), ("w1", c_void_p), ("b1", c_void_p),
+        ("y", c_void_p), ("mask", c_void_p),
+        ("mask_count", c_int32), ("dropout_p", c_float),
+        ("seed", c_uint64), ("step", c_uint64),
+        ("u_explicit", c_void_p), ("ld_u", c_int64),
+        ("keep_x", c_void_p), ("keep_h", c_void_p),
+        ("lr", c_float), ("opt_kind", c_int32),
+        ("adam_m", c_void_p), ("adam_v", c_void_p),
+        ("beta1", c_float), ("beta2", c_float), ("eps", c_float), ("adam_t", c_int32),
+        ("update", c_int32),
+        ("out_scalars", c_void_p), ("out_logp", c_void_p),
+        ("workspace", c_void_p), ("workspace_bytes", c_int64),
+        ("k2_flags", c_uint32), ("reserved", c_uint32),
+    ]
+
+
+_lib = None
+
+
+def library_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Load liblds_b200.so and bind every declared symbol. Raises if the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback for the LDS hot path)")
+    lib = ctypes.CDLL(path)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header/library mismatch
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().lds_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what=""):
+    if rc != LDS_OK:
+        raise RuntimeError(f"liblds_b200 {what} failed (code {rc}): {last_error()}")
+
+
+_device_ok = False
+
+
+def require_device():
+    """Fail loudly unless a CUDA device of compute capability 10.x is current."""
+    global _device_ok
+    if _device_ok:
+        return
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("liblds_b200 needs a B200 (sm_100a) GPU: torch.cuda.is_available() is False and there is no CPU fallback")
+    check(load().lds_device_check(), "lds_device_check")
+    _device_ok = True

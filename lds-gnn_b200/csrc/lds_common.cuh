@@ -1,0 +1,42 @@
+// lds_common.cuh — shared helpers for liblds_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/lds_b200.h"
+
+namespace lds {
+
+// thread-local error slot behind lds_last_error()
+void set_error(const char* fmt, ...);
+int32_t cuda_fail(cudaError_t e, const char* what);
+
+#define LDS_CHECK_ARG(cond, ...)                      \
+  do { if (!(cond)) { lds::set_error(__VA_ARGS__); return LDS_ERR_ARG; } } while (0)
+#define LDS_CHECK_CUDA(expr)                          \
+  do { cudaError_t _e = (expr); if (_e != cudaSuccess) return lds::cuda_fail(_e, #expr); } while (0)
+#define LDS_CHECK_LAUNCH(name)                        \
+  do { cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) return lds::cuda_fail(_e, name); } while (0)
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+static inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
+
+constexpr int kLdAlign = 64;          // theta / A_tilde row stride multiple (elements)
+constexpr int kNumSMsB200 = 148;
+
+int num_sms();                        // cached cudaDevAttrMultiProcessorCount of the current device
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// bf16 hi/lo split of an fp32 value: x ~= hi + lo with |err| <= 2^-17 |x|
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+}  // namespace lds

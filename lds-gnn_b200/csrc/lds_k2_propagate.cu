@@ -1,0 +1,462 @@
+// lds_k2_propagate.cu — K2: Z[rows x w] = A_tilde[rows x n] (bf16 {0,1}) @ B[n x w] on the 5th-gen tensor cores.
+//
+// Replaces the dense `torch.mm(dense_adj, embeddings)` of MetaDenseGraphConvolution.forward
+// (reference src/models/layers.py:44) and its transposed products in autograd's backward. The
+// normalisation D^-1/2 A D^-1/2 (src/utils/graph.py:150-152, two N^3 SGEMMs in the reference) never
+// becomes a GEMM here: r = deg^-1/2 is folded into the skinny operand before and after the product.
+//
+// Shape of the problem: M = rows (<= N), K = N, "N" = w in {7..128}: arithmetic intensity = w flop/byte,
+// far below the B200 ridge (~214 flop/B) => the kernel is an HBM stream of A_tilde; the tensor core is
+// used because it is the only unit that consumes 16 KB tiles at stream rate without spending issue slots.
+//
+// Kernel: persistent stream-K, one CTA per SM slot.
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d of A (128 x 64, SWIZZLE_128B) and of the two
+//               bf16 terms of the operand (HP x 64, K-major) into a STAGES-deep mbarrier ring
+//   warp 1      tcgen05.mma issuer (one lane): D[tmem 128 x HP fp32] += A[smem] x Bhi[smem] (+ Blo), UMMA 128xHPx16,
+//               tcgen05.commit -> frees the smem stage / publishes the accumulator; owns the TMEM allocation
+//   warps 2-5   epilogue: tcgen05.ld 32x32b -> registers -> fp32 partial tile in global memory
+//   accumulators are double-buffered in TMEM so the next segment's MMAs overlap the epilogue.
+#include <cuda.h>
+#include "lds_k2.cuh"
+
+namespace lds {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a protocol bug becomes a trap (reported as a CUDA error) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  long long t0 = 0;
+  for (uint32_t spins = 0;; ++spins) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return;
+    if (spins == 64) t0 = clock64();
+    if (spins > 64 && (spins & 1023) == 0 && clock64() - t0 > 4000000000ll) {
+      printf("liblds_b200: mbarrier wait timed out (block %d thread %d smem 0x%x parity %u)\n", blockIdx.x, threadIdx.x, addr, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory operand descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (= 1, ignored for swizzled K-major) | [32,46) SBO >> 4 (8 rows x 128 B = 1024)
+//   [46,48) version = 1 (Blackwell) | [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b_format BF16 (1) @7/@10,
+// a/b K-major (0) @15/@16, N >> 3 @17, M >> 4 @24.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <int HP> struct K2Cfg {
+  static constexpr int STAGES = (HP == 64) ? 6 : 4;
+  static constexpr int A_BYTES = K2_BLOCK_M * K2_BLOCK_K * 2;        // 16 KB
+  static constexpr int B_BYTES = HP * K2_BLOCK_K * 2;                // one bf16 term
+  static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
+  static constexpr int TMEM_COLS = (2 * HP < 32) ? 32 : 2 * HP;      // two accumulators, power of two >= 32
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers + tmem slot*/;
+  static constexpr int CTAS_PER_SM = (SMEM_BYTES <= 110 * 1024) ? 2 : 1;
+};
+
+template <int HP>
+__global__ void __launch_bounds__(K2_THREADS, 1)
+k2_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_bhi,
+              const __grid_constant__ CUtensorMap tm_blo, float* __restrict__ partial, const K2Sched s, const int use_lo) {
+  using Cfg = K2Cfg<HP>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;      // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;          // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta = blockIdx.x;
+  const int lo = cta * s.per_cta;
+  const int hi = min(lo + s.per_cta, s.total);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_bhi); tma_prefetch_desc(&tm_blo);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      const uint32_t tx_bytes = Cfg::A_BYTES + Cfg::B_BYTES * (use_lo ? 2 : 1);
+      int stage = 0; uint32_t phase = 0;
+      for (int pos = lo; pos < hi;) {
+        const int p = pos / s.kblocks, kb0 = pos - p * s.kblocks;
+        const int cnt = min(s.kblocks - kb0, hi - pos);
+        for (int kb = kb0; kb < kb0 + cnt; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], tx_bytes);
+          tma_load_2d(st, &tm_a, &full_bar[stage], kb * K2_BLOCK_K, p * K2_BLOCK_M);
+          tma_load_2d(st + Cfg::A_BYTES, &tm_bhi, &full_bar[stage], kb * K2_BLOCK_K, 0);
+          if (use_lo) tma_load_2d(st + Cfg::A_BYTES + Cfg::B_BYTES, &tm_blo, &full_bar[stage], kb * K2_BLOCK_K, 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        pos += cnt;
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(K2_BLOCK_M, HP);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int pos = lo; pos < hi;) {
+        const int p = pos / s.kblocks, kb0 = pos - p * s.kblocks;
+        const int cnt = min(s.kblocks - kb0, hi - pos);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * HP);
+        for (int it = 0; it < cnt; ++it) {
+          mbar_wait(&full_bar[stage], phase);                // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t adesc = umma_desc_k_sw128(a_addr);
+          const uint64_t bhdesc = umma_desc_k_sw128(a_addr + Cfg::A_BYTES);
+          const uint64_t bldesc = umma_desc_k_sw128(a_addr + Cfg::A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < K2_BLOCK_K / 16; ++k)          // +32 B per UMMA_K inside the swizzle atom = +2 in the address field
+            tc_mma_bf16(d_tmem, adesc + 2 * k, bhdesc + 2 * k, idesc, (it | k) != 0);
+          if (use_lo) {
+#pragma unroll
+            for (int k = 0; k < K2_BLOCK_K / 16; ++k)
+              tc_mma_bf16(d_tmem, adesc + 2 * k, bldesc + 2 * k, idesc, 1u);
+          }
+          tc_commit(&empty_bar[stage]);                      // smem stage reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull_bar[acc]);                          // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        pos += cnt;
+        (void)p;
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> fp32 partial tile =====
+    const int quarter = warp & 3;                            // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0; int seg = 0;
+    for (int pos = lo; pos < hi; ++seg) {
+      const int p = pos / s.kblocks, kb0 = pos - p * s.kblocks;
+      const int cnt = min(s.kblocks - kb0, hi - pos);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      float* dst = partial + ((int64_t)(cta * s.max_seg + seg) * K2_BLOCK_M + row) * HP;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * HP);
+#pragma unroll
+      for (int c0 = 0; c0 < HP; c0 += 16) {
+        uint32_t v[16];
+        tc_ld16(taddr + c0, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(dst + c0 + 4 * q) =
+              make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      pos += cnt;
+      (void)p;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// operand preparation, partial reduction, validation kernel
+// ------------------------------------------------------------------------------------------------
+// Bt_hi/lo[c][i] = bf16 split of scale_in[i] * p[i][c]  (transposed: K-major operand), rows c >= width zero.
+__global__ void k2_prep_kernel(const float* __restrict__ p, int64_t ld_p, int n, int width, int hp, const float* __restrict__ scale_in,
+                               __nv_bfloat16* __restrict__ bt_hi, __nv_bfloat16* __restrict__ bt_lo, int64_t ldb) {
+  __shared__ float tile[32][33];
+  const int i0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 256 threads: ty in [0, 8)
+  for (int r = ty; r < 32; r += 8) {
+    const int i = i0 + r, c = c0 + tx;
+    float v = 0.f;
+    if (i < n && c < width) v = p[(int64_t)i * ld_p + c] * (scale_in ? scale_in[i] : 1.f);
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, i = i0 + tx;
+    if (c < hp && i < (int)ldb) {
+      __nv_bfloat16 h, l;
+      split_bf16(tile[tx][r], h, l);
+      bt_hi[(int64_t)c * ldb + i] = h;
+      bt_lo[(int64_t)c * ldb + i] = l;
+    }
+  }
+}
+
+__global__ void k2_reduce_kernel(const float* __restrict__ partial, const K2Sched s, int rows, int width,
+                                 const float* __restrict__ scale_out, float* __restrict__ z, int64_t ld_z) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = idx / s.hp, col = idx - row * s.hp;
+  if (row >= rows || col >= width) return;
+  const float v = k2_sum_partials(partial, s, row, col);
+  z[(int64_t)row * ld_z + col] = v * (scale_out ? scale_out[row] : 1.f);
+}
+
+// CUDA-core validation kernel (tests only): one warp per output row, fp32 FMA over bf16 A.
+__global__ void k2_simt_kernel(const __nv_bfloat16* __restrict__ a, int64_t ld_a, int n, int rows,
+                               const float* __restrict__ p, int64_t ld_p, int width,
+                               const float* __restrict__ scale_in, const float* __restrict__ scale_out,
+                               float* __restrict__ z, int64_t ld_z) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  for (int c0 = 0; c0 < width; c0 += 8) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j = lane; j < n; j += 32) {
+      const float av = __bfloat162float(a[(int64_t)row * ld_a + j]);
+      if (av != 0.f) {
+        const float sj = scale_in ? scale_in[j] : 1.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) if (c0 + e < width) acc[e] = fmaf(av, sj * p[(int64_t)j * ld_p + c0 + e], acc[e]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float v = warp_sum(acc[e]);
+      if (lane == 0 && c0 + e < width) z[(int64_t)row * ld_z + c0 + e] = v * (scale_out ? scale_out[row] : 1.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+int k2_padded_width(int width) {
+  if (width <= 0) return -1;
+  if (width <= 16) return 16;
+  if (width <= 32) return 32;
+  if (width <= 64) return 64;
+  if (width <= 128) return 128;
+  return -1;
+}
+
+static int k2_ctas_per_sm(int hp) {
+  switch (hp) {
+    case 16: return K2Cfg<16>::CTAS_PER_SM;
+    case 32: return K2Cfg<32>::CTAS_PER_SM;
+    case 64: return K2Cfg<64>::CTAS_PER_SM;
+    default: return K2Cfg<128>::CTAS_PER_SM;
+  }
+}
+
+K2Sched k2_make_schedule(int n, int rows, int hp) {
+  K2Sched s;
+  s.hp = hp;
+  s.panels = (int)ceil_div(rows, K2_BLOCK_M);
+  s.kblocks = (int)ceil_div(n, K2_BLOCK_K);
+  s.total = s.panels * s.kblocks;
+  const int grid_max = kNumSMsB200 * k2_ctas_per_sm(hp);     // a pure function of the shape: workspace sizing needs no device query
+  int per = (int)ceil_div(s.total, grid_max);
+  if (per < 4) per = 4;                                      // amortise the pipeline prologue
+  if (per > s.total) per = s.total;
+  s.per_cta = per;
+  s.grid = (int)ceil_div(s.total, per);
+  s.max_seg = (per - 1 + s.kblocks - 1) / s.kblocks + 1;
+  return s;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !sym) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(sym);
+  return fn;
+}
+
+// 2-D bf16 row-major tensor [rows][cols] with row stride ld (elements); box = box_rows x 64 columns, 128-byte swizzle.
+static int32_t make_tmap_bf16(CUtensorMap* out, const void* base, int64_t cols, int64_t rows, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return LDS_ERR_CUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)K2_BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (cols=%lld rows=%lld ld=%lld)", (int)r, (long long)cols, (long long)rows, (long long)ld); return LDS_ERR_CUDA; }
+  return LDS_OK;
+}
+
+template <int HP>
+static int32_t launch_mma_t(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tbl, float* partial, const K2Sched& s, bool use_lo, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    LDS_CHECK_CUDA(cudaFuncSetAttribute(k2_mma_kernel<HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2Cfg<HP>::SMEM_BYTES));
+    attr_set = true;
+  }
+  k2_mma_kernel<HP><<<s.grid, K2_THREADS, K2Cfg<HP>::SMEM_BYTES, stream>>>(ta, tbh, tbl, partial, s, use_lo ? 1 : 0);
+  LDS_CHECK_LAUNCH("k2_mma_kernel");
+  return LDS_OK;
+}
+
+int32_t k2_launch_mma(const void* a, int64_t ld_a, int n, int rows, const void* bt_hi, const void* bt_lo, int64_t ldb,
+                      float* partial, const K2Sched& s, bool use_lo, cudaStream_t stream) {
+  CUtensorMap ta, tbh, tbl;
+  int32_t rc;
+  if ((rc = make_tmap_bf16(&ta, a, n, rows, ld_a, K2_BLOCK_M)) != LDS_OK) return rc;
+  if ((rc = make_tmap_bf16(&tbh, bt_hi, n, s.hp, ldb, s.hp)) != LDS_OK) return rc;
+  if ((rc = make_tmap_bf16(&tbl, bt_lo, n, s.hp, ldb, s.hp)) != LDS_OK) return rc;
+  switch (s.hp) {
+    case 16: return launch_mma_t<16>(ta, tbh, tbl, partial, s, use_lo, stream);
+    case 32: return launch_mma_t<32>(ta, tbh, tbl, partial, s, use_lo, stream);
+    case 64: return launch_mma_t<64>(ta, tbh, tbl, partial, s, use_lo, stream);
+    case 128: return launch_mma_t<128>(ta, tbh, tbl, partial, s, use_lo, stream);
+  }
+  set_error("k2: unsupported padded width %d", s.hp);
+  return LDS_ERR_UNSUPPORTED;
+}
+
+int32_t k2_launch_simt(const void* a, int64_t ld_a, int n, int rows, const float* p, int64_t ld_p, int width,
+                       const float* scale_in, const float* scale_out, float* z, int64_t ld_z, cudaStream_t stream) {
+  const int warps = 8;
+  k2_simt_kernel<<<(int)ceil_div(rows, warps), warps * 32, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a), ld_a, n, rows, p, ld_p, width, scale_in, scale_out, z, ld_z);
+  LDS_CHECK_LAUNCH("k2_simt_kernel");
+  return LDS_OK;
+}
+
+int32_t k2_launch_prep(const float* p, int64_t ld_p, int n, int width, int hp, const float* scale_in,
+                       void* bt_hi, void* bt_lo, int64_t ldb, cudaStream_t stream) {
+  dim3 grid((unsigned)ceil_div(ldb, 32), (unsigned)ceil_div(hp, 32));
+  k2_prep_kernel<<<grid, 256, 0, stream>>>(p, ld_p, n, width, hp, scale_in, reinterpret_cast<__nv_bfloat16*>(bt_hi), reinterpret_cast<__nv_bfloat16*>(bt_lo), ldb);
+  LDS_CHECK_LAUNCH("k2_prep_kernel");
+  return LDS_OK;
+}
+
+}  // namespace lds
+
+using namespace lds;
+
+extern "C" int64_t lds_k2_workspace_bytes(int32_t n, int32_t rows, int32_t width) {
+  const int hp = k2_padded_width(width);
+  if (hp < 0 || n <= 0 || rows <= 0) return -1;
+  const K2Sched s = k2_make_schedule(n, rows, hp);
+  return round_up(2 * k2_operand_bytes(n, hp), 1024) + round_up(k2_partial_bytes(s), 1024) + 1024;
+}
+
+extern "C" int32_t lds_k2_propagate(const void* a, int64_t ld_a, int32_t n, int32_t rows,
+                                    const float* p, int64_t ld_p, int32_t width,
+                                    const float* scale_in, const float* scale_out,
+                                    float* z_out, int64_t ld_z,
+                                    void* workspace, int64_t workspace_bytes, uint32_t flags, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LDS_CHECK_ARG(a && p && z_out, "lds_k2_propagate: null pointer");
+  LDS_CHECK_ARG(n > 0 && rows > 0, "lds_k2_propagate: need n > 0 and rows > 0");
+  LDS_CHECK_ARG(ld_a >= n && ld_a % 8 == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0, "lds_k2_propagate: A must be 16-byte aligned with ld_a >= n, ld_a %% 8 == 0");
+  LDS_CHECK_ARG(ld_p >= width && ld_z >= width, "lds_k2_propagate: ld_p / ld_z smaller than width");
+  const int hp = k2_padded_width(width);
+  if (hp < 0) { set_error("lds_k2_propagate: width %d outside [1, 128]", width); return LDS_ERR_UNSUPPORTED; }
+  if (flags & LDS_K2_SIMT) return k2_launch_simt(a, ld_a, n, rows, p, ld_p, width, scale_in, scale_out, z_out, ld_z, stream);
+  const int64_t need = lds_k2_workspace_bytes(n, rows, width);
+  if (!workspace || workspace_bytes < need) { set_error("lds_k2_propagate: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need); return LDS_ERR_WORKSPACE; }
+  LDS_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "lds_k2_propagate: workspace must be 1024-byte aligned");
+  const K2Sched s = k2_make_schedule(n, rows, hp);
+  const int64_t ldb = k2_operand_ld(n);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  void* bt_hi = ws;
+  void* bt_lo = ws + k2_operand_bytes(n, hp);
+  float* partial = reinterpret_cast<float*>(ws + round_up(2 * k2_operand_bytes(n, hp), 1024));
+  int32_t rc;
+  if ((rc = k2_launch_prep(p, ld_p, n, width, hp, scale_in, bt_hi, bt_lo, ldb, stream)) != LDS_OK) return rc;
+  if ((rc = k2_launch_mma(a, ld_a, n, rows, bt_hi, bt_lo, ldb, partial, s, !(flags & LDS_K2_SINGLE_BF16), stream)) != LDS_OK) return rc;
+  const int threads = 256;
+  k2_reduce_kernel<<<(int)ceil_div((int64_t)rows * hp, threads), threads, 0, stream>>>(partial, s, rows, width, scale_out, z_out, ld_z);
+  LDS_CHECK_LAUNCH("k2_reduce_kernel");
+  return LDS_OK;
+}

@@ -1,0 +1,450 @@
+// lds_outer_step.cu — the fused direct outer step: one OuterProblemTrainer.train_step
+// (reference src/trainers/outer.py:57-87) with gcn_predict_fct = InnerProblemTrainer.model_forward
+// (src/trainers/inner.py:76-78) evaluated at fixed GCN weights, regularize=False.
+//
+// Launch sequence (all on the caller's stream, no host sync, graph-capturable):
+//   K1            theta -> A_tilde (bf16), deg, r                                   lds_k1_sample.cu
+//   feat_linear   P1 = dropout(X) W0^T + b0 (Philox dropout fused, X read once); operand (r*P1)^T     gcn.py:27-28, layers.py:43
+//   K2            A_tilde (r*P1)                                                    lds_k2_propagate.cu
+//   epi_layer1    Z1 = r*., H1 = relu, dropout, P2 = H1' W1^T + b1; operand (r*P2)^T                 gcn.py:28-30
+//   K2            A_tilde (r*P2)
+//   epi_layer2    Z2 = r*., log_softmax, masked NLL + accuracy, dZ2; operand (r*dZ2)^T              gcn.py:34, outer.py:65-67
+//   K2            A_tilde (r*dZ2)       (A_hat is symmetric: dP = A_hat dZ)
+//   epi_bwd2      dP2 = r*., dH1' = dP2 W1, dZ1 = dropout'/relu' ; operand (r*dZ1)^T
+//   K2            A_tilde (r*dZ1)
+//   epi_bwd1      dP1 = r*., rho, kappa, c = -(rho+kappa)/(2 deg); factors fa = r(dZ1|dZ2), fb = r(P1|P2); loss/acc finalised
+//   K3+K4         theta <- clamp(theta - lr * g(fa, fb, c))                         lds_k3_theta_update.cu
+// The outer step needs no weight gradients (the reference computes and discards them), so X is read once.
+#include "lds_k2.cuh"
+#include "lds_philox.cuh"
+
+namespace lds {
+
+constexpr int EPI_ROWS = 32;        // rows per CTA in the row epilogues
+constexpr int EPI_THREADS = 256;    // 8 warps x 4 rows
+constexpr int EPI_MAXW = 128;       // widest operand
+
+struct OuterLayout {
+  int n, f, h, c, hp1, hp2, hpmax, nblk;
+  int64_t lda, ldb, ldf;
+  K2Sched s1, s2;
+  int64_t off[20];
+  int64_t total;
+};
+enum { B_A = 0, B_DEG, B_RS, B_P1, B_Z1, B_P2, B_Z2, B_DZ2, B_DP2, B_DZ1, B_DP1, B_FA, B_FB, B_C, B_BTHI, B_BTLO, B_PARTIAL, B_LOSSP, B_CORRP, B_END };
+
+static bool make_layout(int n, int f, int h, int c, OuterLayout& L) {
+  L.n = n; L.f = f; L.h = h; L.c = c;
+  L.hp1 = k2_padded_width(h); L.hp2 = k2_padded_width(c);
+  if (n <= 0 || f <= 0 || L.hp1 < 0 || L.hp2 < 0) return false;
+  L.hpmax = L.hp1 > L.hp2 ? L.hp1 : L.hp2;
+  L.lda = round_up(n, kLdAlign); L.ldb = k2_operand_ld(n); L.ldf = round_up(h + c, 4);
+  L.s1 = k2_make_schedule(n, n, L.hp1); L.s2 = k2_make_schedule(n, n, L.hp2);
+  L.nblk = (int)ceil_div(n, EPI_ROWS);
+  int64_t bytes[B_END];
+  bytes[B_A] = (int64_t)n * L.lda * 2;
+  bytes[B_DEG] = bytes[B_RS] = bytes[B_C] = (int64_t)n * 4;
+  bytes[B_P1] = bytes[B_Z1] = bytes[B_DZ1] = bytes[B_DP1] = (int64_t)n * h * 4;
+  bytes[B_P2] = bytes[B_Z2] = bytes[B_DZ2] = bytes[B_DP2] = (int64_t)n * c * 4;
+  bytes[B_FA] = bytes[B_FB] = (int64_t)n * L.ldf * 4;
+  bytes[B_BTHI] = bytes[B_BTLO] = k2_operand_bytes(n, L.hpmax);
+  const int64_t p1 = k2_partial_bytes(L.s1), p2 = k2_partial_bytes(L.s2);
+  bytes[B_PARTIAL] = p1 > p2 ? p1 : p2;
+  bytes[B_LOSSP] = bytes[B_CORRP] = (int64_t)L.nblk * 4;
+  int64_t o = 0;
+  for (int b = 0; b < B_END; ++b) { L.off[b] = o; o += round_up(bytes[b], 1024); }
+  L.total = o;
+  return true;
+}
+
+struct DropCfg {           // dropout of one stream
+  float p, keep_thresh, scale;
+  const uint8_t* explicit_keep;   // [rows][cols] or nullptr
+  PhiloxKey key;
+};
+
+__device__ __forceinline__ bool drop_keep(const DropCfg& dc, int row, int col, int ncols) {
+  if (dc.p <= 0.f) return true;
+  if (dc.explicit_keep) return dc.explicit_keep[(int64_t)row * ncols + col] != 0;
+  uint32_t w[4];
+  philox4x32_10((uint32_t)(col >> 2), (uint32_t)row, dc.key, w);
+  return philox_to_uniform(w[col & 3]) < dc.keep_thresh;
+}
+
+// Transposed operand store: tile[c][r] (already scaled by r_i) -> bt_hi/lo[c][i0 + r], bf16 hi/lo split.
+__device__ __forceinline__ void store_operand_tile(const float (*tile)[EPI_ROWS + 1], int hp, int i0, int64_t ldb,
+                                                   __nv_bfloat16* __restrict__ bt_hi, __nv_bfloat16* __restrict__ bt_lo) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = i0 + lane;
+  if (i >= (int)ldb) return;
+  for (int c = warp; c < hp; c += EPI_THREADS / 32) {
+    __nv_bfloat16 hi, lo;
+    split_bf16(tile[c][lane], hi, lo);
+    bt_hi[(int64_t)c * ldb + i] = hi;
+    bt_lo[(int64_t)c * ldb + i] = lo;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// P1 = dropout(X) W0^T + b0, operand (r*P1)^T.  One warp = 4 rows; lanes stride over feature quads.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EPI_THREADS)
+feat_linear_kernel(const float* __restrict__ x, int64_t ldx, int n, int f, const float* __restrict__ w0, int64_t ldw, const float* __restrict__ b0, int h,
+                   DropCfg dc, const float* __restrict__ rs, float* __restrict__ p1,
+                   __nv_bfloat16* __restrict__ bt_hi, __nv_bfloat16* __restrict__ bt_lo, int64_t ldb, int hp) {
+  __shared__ float tile[EPI_MAXW][EPI_ROWS + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i0 = blockIdx.x * EPI_ROWS;
+  const int f4 = (f + 3) >> 2;
+  const int iters = (f4 + 31) >> 5;
+  for (int idx = threadIdx.x; idx < EPI_MAXW * (EPI_ROWS + 1); idx += EPI_THREADS) (&tile[0][0])[idx] = 0.f;
+  __syncthreads();
+
+  for (int oc = 0; oc < h; oc += 16) {
+    float acc[4][16];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int o = 0; o < 16; ++o) acc[r][o] = 0.f;
+    for (int it = 0; it < iters; ++it) {
+      const int q = it * 32 + lane;
+      const bool valid = q < f4;
+      float4 xv[4];
+      bool nz = false;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int i = i0 + 4 * warp + r;
+        xv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid && i < n) {
+          xv[r] = *reinterpret_cast<const float4*>(x + (int64_t)i * ldx + 4 * q);
+          if (dc.p > 0.f) {
+            float k[4];
+            if (dc.explicit_keep) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) k[e] = (4 * q + e < f && dc.explicit_keep[(int64_t)i * f + 4 * q + e]) ? dc.scale : 0.f;
+            } else {
+              uint32_t w[4];
+              philox4x32_10((uint32_t)q, (uint32_t)i, dc.key, w);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) k[e] = (philox_to_uniform(w[e]) < dc.keep_thresh) ? dc.scale : 0.f;
+            }
+            xv[r].x *= k[0]; xv[r].y *= k[1]; xv[r].z *= k[2]; xv[r].w *= k[3];
+          }
+          nz = nz || (xv[r].x != 0.f) || (xv[r].y != 0.f) || (xv[r].z != 0.f) || (xv[r].w != 0.f);
+        }
+      }
+      if (!__any_sync(0xffffffffu, nz)) continue;          // bag-of-words features are mostly zero
+      if (valid) {
+#pragma unroll
+        for (int o = 0; o < 16; ++o) {
+          if (oc + o < h) {
+            const float4 wv = *reinterpret_cast<const float4*>(w0 + (int64_t)(oc + o) * ldw + 4 * q);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+              acc[r][o] = fmaf(xv[r].x, wv.x, fmaf(xv[r].y, wv.y, fmaf(xv[r].z, wv.z, fmaf(xv[r].w, wv.w, acc[r][o]))));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int o = 0; o < 16; ++o) {
+        const float v = warp_sum(acc[r][o]);
+        if (lane == 0 && oc + o < h) tile[oc + o][4 * warp + r] = v + b0[oc + o];
+      }
+  }
+  __syncthreads();
+  // coalesced P1 rows, then the scaled transposed operand
+  for (int r = 0; r < 4; ++r) {
+    const int rr = 4 * warp + r, i = i0 + rr;
+    if (i < n) for (int c = lane; c < h; c += 32) p1[(int64_t)i * h + c] = tile[c][rr];
+  }
+  __syncthreads();
+  {
+    const int rr = threadIdx.x & 31;                         // scale column rr of the tile by r_i
+    const int i = i0 + rr;
+    const float ri = (i < n) ? rs[i] : 0.f;
+    for (int c = threadIdx.x >> 5; c < hp; c += EPI_THREADS / 32) tile[c][rr] *= ri;
+  }
+  __syncthreads();
+  store_operand_tile(tile, hp, i0, ldb, bt_hi, bt_lo);
+}
+
+// ------------------------------------------------------------------------------------------------
+// row epilogues
+// ------------------------------------------------------------------------------------------------
+struct EpiArgs {
+  int n, h, c, hp1, hp2;
+  K2Sched s1, s2;
+  const float* partial;
+  const float* deg; const float* rs;
+  float* p1; float* z1; float* p2; float* z2; float* dz2; float* dp2; float* dz1; float* dp1;
+  float* fa; float* fb; int64_t ldf; float* cvec;
+  const float* w1; const float* b1;
+  const int64_t* y; const uint8_t* mask; float inv_m;
+  DropCfg drop_h;
+  __nv_bfloat16* bt_hi; __nv_bfloat16* bt_lo; int64_t ldb;
+  float* loss_part; float* corr_part; int nblk;
+  float* out_scalars; float* out_logp;
+};
+
+__global__ void __launch_bounds__(EPI_THREADS) epi_layer1_kernel(const EpiArgs a) {
+  __shared__ float tile[EPI_MAXW][EPI_ROWS + 1];
+  __shared__ float rowbuf[EPI_THREADS / 32][EPI_MAXW];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i0 = blockIdx.x * EPI_ROWS;
+  for (int idx = threadIdx.x; idx < EPI_MAXW * (EPI_ROWS + 1); idx += EPI_THREADS) (&tile[0][0])[idx] = 0.f;
+  __syncthreads();
+  for (int r = 0; r < 4; ++r) {
+    const int rr = 4 * warp + r, i = i0 + rr;
+    if (i >= a.n) continue;                                   // warp-uniform
+    const float ri = a.rs[i];
+    for (int c = lane; c < a.h; c += 32) {
+      const float z = ri * k2_sum_partials(a.partial, a.s1, i, c);
+      a.z1[(int64_t)i * a.h + c] = z;
+      float hv = fmaxf(z, 0.f);                               // relu (gcn.py:28)
+      hv = drop_keep(a.drop_h, i, c, a.h) ? hv * (a.drop_h.p > 0.f ? a.drop_h.scale : 1.f) : 0.f;   // dropout (gcn.py:29)
+      rowbuf[warp][c] = hv;
+    }
+    __syncwarp();
+    for (int o = lane; o < a.c; o += 32) {                    // P2 = H1' W1^T + b1 (layers.py:43)
+      float acc = a.b1[o];
+      for (int k = 0; k < a.h; ++k) acc = fmaf(rowbuf[warp][k], a.w1[(int64_t)o * a.h + k], acc);
+      a.p2[(int64_t)i * a.c + o] = acc;
+      tile[o][rr] = ri * acc;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  store_operand_tile(tile, a.hp2, i0, a.ldb, a.bt_hi, a.bt_lo);
+}
+
+__global__ void __launch_bounds__(EPI_THREADS) epi_layer2_kernel(const EpiArgs a) {
+  __shared__ float tile[EPI_MAXW][EPI_ROWS + 1];
+  __shared__ float sh_loss[EPI_THREADS / 32], sh_corr[EPI_THREADS / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i0 = blockIdx.x * EPI_ROWS;
+  for (int idx = threadIdx.x; idx < EPI_MAXW * (EPI_ROWS + 1); idx += EPI_THREADS) (&tile[0][0])[idx] = 0.f;
+  __syncthreads();
+  float loss_w = 0.f, corr_w = 0.f;
+  for (int r = 0; r < 4; ++r) {
+    const int rr = 4 * warp + r, i = i0 + rr;
+    if (i >= a.n) continue;
+    const float ri = a.rs[i];
+    float z[4];
+    float mx = -3.4e38f; int best = 0x7fffffff; float bestv = -3.4e38f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int o = lane + 32 * t;
+      z[t] = -3.4e38f;
+      if (o < a.c) {
+        z[t] = ri * k2_sum_partials(a.partial, a.s2, i, o);
+        a.z2[(int64_t)i * a.c + o] = z[t];
+        if (z[t] > bestv) { bestv = z[t]; best = o; }           // ascending o: first maximum wins (torch.argmax)
+      }
+      mx = fmaxf(mx, z[t]);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+      const float ov = __shfl_xor_sync(0xffffffffu, bestv, s);
+      const int oi = __shfl_xor_sync(0xffffffffu, best, s);
+      if (ov > bestv || (ov == bestv && oi < best)) { bestv = ov; best = oi; }
+    }
+    float se = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) if (lane + 32 * t < a.c) se += expf(z[t] - mx);
+    se = warp_sum(se);
+    const float lse = mx + logf(se);                           // log_softmax (gcn.py:34)
+    const int yi = (int)a.y[i];
+    const bool mk = a.mask[i] != 0;
+    float li = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int o = lane + 32 * t;
+      if (o < a.c) {
+        const float lp = z[t] - lse;
+        if (a.out_logp) a.out_logp[(int64_t)i * a.c + o] = lp;
+        if (mk && o == yi) li = -lp;                           // nll_loss numerator (outer.py:66)
+        const float dz = mk ? (expf(lp) - (o == yi ? 1.f : 0.f)) * a.inv_m : 0.f;
+        a.dz2[(int64_t)i * a.c + o] = dz;
+        tile[o][rr] = ri * dz;
+      }
+    }
+    li = warp_sum(li);
+    loss_w += li;
+    corr_w += (mk && best == yi) ? 1.f : 0.f;                  // accuracy (utils/evaluation.py:15-22)
+  }
+  if (lane == 0) { sh_loss[warp] = loss_w; sh_corr[warp] = corr_w; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float l = 0.f, c = 0.f;
+    for (int k = 0; k < EPI_THREADS / 32; ++k) { l += sh_loss[k]; c += sh_corr[k]; }
+    a.loss_part[blockIdx.x] = l; a.corr_part[blockIdx.x] = c;
+  }
+  store_operand_tile(tile, a.hp2, i0, a.ldb, a.bt_hi, a.bt_lo);
+}
+
+__global__ void __launch_bounds__(EPI_THREADS) epi_bwd2_kernel(const EpiArgs a) {
+  __shared__ float tile[EPI_MAXW][EPI_ROWS + 1];
+  __shared__ float rowbuf[EPI_THREADS / 32][EPI_MAXW];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i0 = blockIdx.x * EPI_ROWS;
+  for (int idx = threadIdx.x; idx < EPI_MAXW * (EPI_ROWS + 1); idx += EPI_THREADS) (&tile[0][0])[idx] = 0.f;
+  __syncthreads();
+  for (int r = 0; r < 4; ++r) {
+    const int rr = 4 * warp + r, i = i0 + rr;
+    if (i >= a.n) continue;
+    const float ri = a.rs[i];
+    for (int o = lane; o < a.c; o += 32) {
+      const float dp = ri * k2_sum_partials(a.partial, a.s2, i, o);      // dP2 = A_hat dZ2
+      a.dp2[(int64_t)i * a.c + o] = dp;
+      rowbuf[warp][o] = dp;
+    }
+    __syncwarp();
+    for (int c = lane; c < a.h; c += 32) {
+      float acc = 0.f;                                                    // dH1' = dP2 W1
+      for (int o = 0; o < a.c; ++o) acc = fmaf(rowbuf[warp][o], a.w1[(int64_t)o * a.h + c], acc);
+      const bool keep = drop_keep(a.drop_h, i, c, a.h);
+      const float sc = a.drop_h.p > 0.f ? a.drop_h.scale : 1.f;
+      const float dz = (keep && a.z1[(int64_t)i * a.h + c] > 0.f) ? acc * sc : 0.f;   // dropout' then relu'
+      a.dz1[(int64_t)i * a.h + c] = dz;
+      tile[c][rr] = ri * dz;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  store_operand_tile(tile, a.hp1, i0, a.ldb, a.bt_hi, a.bt_lo);
+}
+
+__global__ void __launch_bounds__(EPI_THREADS) epi_bwd1_kernel(const EpiArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i0 = blockIdx.x * EPI_ROWS;
+  for (int r = 0; r < 4; ++r) {
+    const int i = i0 + 4 * warp + r;
+    if (i >= a.n) continue;
+    const float ri = a.rs[i];
+    float rho = 0.f, kappa = 0.f;
+    float* fa = a.fa + (int64_t)i * a.ldf;
+    float* fb = a.fb + (int64_t)i * a.ldf;
+    for (int c = lane; c < a.h; c += 32) {
+      const float dp1 = ri * k2_sum_partials(a.partial, a.s1, i, c);      // dP1 = A_hat dZ1
+      a.dp1[(int64_t)i * a.h + c] = dp1;
+      const float dz1 = a.dz1[(int64_t)i * a.h + c], p1 = a.p1[(int64_t)i * a.h + c];
+      rho = fmaf(dz1, a.z1[(int64_t)i * a.h + c], rho);
+      kappa = fmaf(p1, dp1, kappa);
+      fa[c] = ri * dz1; fb[c] = ri * p1;
+    }
+    for (int o = lane; o < a.c; o += 32) {
+      const float dz2 = a.dz2[(int64_t)i * a.c + o], p2 = a.p2[(int64_t)i * a.c + o];
+      rho = fmaf(dz2, a.z2[(int64_t)i * a.c + o], rho);
+      kappa = fmaf(p2, a.dp2[(int64_t)i * a.c + o], kappa);
+      fa[a.h + o] = ri * dz2; fb[a.h + o] = ri * p2;
+    }
+    for (int k = a.h + a.c + lane; k < (int)a.ldf; k += 32) { fa[k] = 0.f; fb[k] = 0.f; }
+    rho = warp_sum(rho); kappa = warp_sum(kappa);
+    if (lane == 0) a.cvec[i] = -(rho + kappa) / (2.f * a.deg[i]);          // both D^-1/2 factors depend on the row sum
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {                                // deterministic final reduction
+    float l = 0.f, c = 0.f;
+    for (int k = 0; k < a.nblk; ++k) { l += a.loss_part[k]; c += a.corr_part[k]; }
+    a.out_scalars[0] = l * a.inv_m;
+    a.out_scalars[1] = c * a.inv_m;
+  }
+}
+
+}  // namespace lds
+
+using namespace lds;
+
+extern "C" int64_t lds_outer_step_workspace_bytes(int32_t n, int32_t f, int32_t h, int32_t c) {
+  OuterLayout L;
+  if (!make_layout(n, f, h, c, L)) return -1;
+  return L.total;
+}
+
+extern "C" int64_t lds_outer_step_factor_ld(int32_t h, int32_t c) { return round_up(h + c, 4); }
+
+extern "C" void* lds_outer_step_buffer(void* workspace, int32_t n, int32_t f, int32_t h, int32_t c, int32_t which) {
+  OuterLayout L;
+  if (!workspace || !make_layout(n, f, h, c, L) || which < 0 || which > B_C) return nullptr;
+  return reinterpret_cast<uint8_t*>(workspace) + L.off[which];
+}
+
+extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LDS_CHECK_ARG(args != nullptr, "lds_outer_step: null args");
+  LDS_CHECK_ARG(args->struct_bytes == sizeof(lds_outer_step_args), "lds_outer_step: struct_bytes %u != %zu (header mismatch)", args->struct_bytes, sizeof(lds_outer_step_args));
+  const lds_outer_step_args& A = *args;
+  OuterLayout L;
+  if (!make_layout(A.n, A.f, A.h, A.c, L)) { set_error("lds_outer_step: unsupported shape n=%d f=%d h=%d c=%d (h, c must be in [1,128])", A.n, A.f, A.h, A.c); return LDS_ERR_UNSUPPORTED; }
+  LDS_CHECK_ARG(A.theta_full && A.x && A.w0 && A.b0 && A.w1 && A.b1 && A.y && A.mask && A.out_scalars, "lds_outer_step: null pointer");
+  LDS_CHECK_ARG(A.ld_theta >= A.n && A.ld_theta % 4 == 0, "lds_outer_step: ld_theta must be >= n and a multiple of 4");
+  LDS_CHECK_ARG(A.ld_x >= A.f && A.ld_x % 4 == 0 && A.ld_w0 >= A.f && A.ld_w0 % 4 == 0, "lds_outer_step: ld_x / ld_w0 must be >= f and multiples of 4 (zero padded)");
+  LDS_CHECK_ARG((reinterpret_cast<uintptr_t>(A.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(A.w0) & 15) == 0, "lds_outer_step: x and w0 must be 16-byte aligned");
+  LDS_CHECK_ARG(A.mask_count > 0, "lds_outer_step: mask_count must be positive");
+  LDS_CHECK_ARG(A.dropout_p >= 0.f && A.dropout_p < 1.f, "lds_outer_step: dropout_p must be in [0, 1)");
+  if (!A.workspace || A.workspace_bytes < L.total) { set_error("lds_outer_step: workspace too small (%lld < %lld)", (long long)A.workspace_bytes, (long long)L.total); return LDS_ERR_WORKSPACE; }
+  LDS_CHECK_ARG((reinterpret_cast<uintptr_t>(A.workspace) & 1023) == 0, "lds_outer_step: workspace must be 1024-byte aligned");
+  uint8_t* ws = reinterpret_cast<uint8_t*>(A.workspace);
+  auto buf = [&](int b) { return ws + L.off[b]; };
+  auto fbuf = [&](int b) { return reinterpret_cast<float*>(ws + L.off[b]); };
+
+  int32_t rc;
+  // K1
+  rc = lds_k1_sample_normalize(A.theta_full, A.ld_theta, A.n, 0, A.n, A.seed, A.step, 0, A.u_explicit, A.ld_u,
+                               buf(B_A), L.lda, nullptr, 0, fbuf(B_DEG), fbuf(B_RS), A.u_explicit ? LDS_K1_EXPLICIT_U : 0u, stream_);
+  if (rc != LDS_OK) return rc;
+
+  DropCfg dx, dh;
+  dx.p = dh.p = A.dropout_p;
+  dx.keep_thresh = dh.keep_thresh = (float)(1.0 - (double)A.dropout_p);
+  dx.scale = dh.scale = 1.0f / dx.keep_thresh;
+  dx.explicit_keep = A.keep_x; dh.explicit_keep = A.keep_h;
+  dx.key = philox_key(A.seed, A.step, LDS_STREAM_DROP_X, 0);
+  dh.key = philox_key(A.seed, A.step, LDS_STREAM_DROP_H, 0);
+
+  auto* bt_hi = reinterpret_cast<__nv_bfloat16*>(buf(B_BTHI));
+  auto* bt_lo = reinterpret_cast<__nv_bfloat16*>(buf(B_BTLO));
+  const bool use_lo = !(A.k2_flags & LDS_K2_SINGLE_BF16);
+  const dim3 egrid((unsigned)L.nblk);
+
+  feat_linear_kernel<<<egrid, EPI_THREADS, 0, stream>>>(A.x, A.ld_x, A.n, A.f, A.w0, A.ld_w0, A.b0, A.h, dx, fbuf(B_RS), fbuf(B_P1), bt_hi, bt_lo, L.ldb, L.hp1);
+  LDS_CHECK_LAUNCH("feat_linear_kernel");
+
+  EpiArgs E;
+  E.n = A.n; E.h = A.h; E.c = A.c; E.hp1 = L.hp1; E.hp2 = L.hp2; E.s1 = L.s1; E.s2 = L.s2;
+  E.partial = fbuf(B_PARTIAL); E.deg = fbuf(B_DEG); E.rs = fbuf(B_RS);
+  E.p1 = fbuf(B_P1); E.z1 = fbuf(B_Z1); E.p2 = fbuf(B_P2); E.z2 = fbuf(B_Z2); E.dz2 = fbuf(B_DZ2); E.dp2 = fbuf(B_DP2);
+  E.dz1 = fbuf(B_DZ1); E.dp1 = fbuf(B_DP1); E.fa = fbuf(B_FA); E.fb = fbuf(B_FB); E.ldf = L.ldf; E.cvec = fbuf(B_C);
+  E.w1 = A.w1; E.b1 = A.b1; E.y = A.y; E.mask = A.mask; E.inv_m = 1.0f / (float)A.mask_count;
+  E.drop_h = dh; E.bt_hi = bt_hi; E.bt_lo = bt_lo; E.ldb = L.ldb;
+  E.loss_part = fbuf(B_LOSSP); E.corr_part = fbuf(B_CORRP); E.nblk = L.nblk;
+  E.out_scalars = A.out_scalars; E.out_logp = A.out_logp;
+
+  auto propagate = [&](const K2Sched& s) -> int32_t {
+    if (A.k2_flags & LDS_K2_SIMT) { set_error("lds_outer_step: LDS_K2_SIMT is only available through lds_k2_propagate"); return LDS_ERR_ARG; }
+    return k2_launch_mma(buf(B_A), L.lda, A.n, A.n, bt_hi, bt_lo, L.ldb, fbuf(B_PARTIAL), s, use_lo, stream);
+  };
+
+  if ((rc = propagate(L.s1)) != LDS_OK) return rc;
+  epi_layer1_kernel<<<egrid, EPI_THREADS, 0, stream>>>(E);
+  LDS_CHECK_LAUNCH("epi_layer1_kernel");
+  if ((rc = propagate(L.s2)) != LDS_OK) return rc;
+  epi_layer2_kernel<<<egrid, EPI_THREADS, 0, stream>>>(E);
+  LDS_CHECK_LAUNCH("epi_layer2_kernel");
+  if ((rc = propagate(L.s2)) != LDS_OK) return rc;
+  epi_bwd2_kernel<<<egrid, EPI_THREADS, 0, stream>>>(E);
+  LDS_CHECK_LAUNCH("epi_bwd2_kernel");
+  if ((rc = propagate(L.s1)) != LDS_OK) return rc;
+  epi_bwd1_kernel<<<egrid, EPI_THREADS, 0, stream>>>(E);
+  LDS_CHECK_LAUNCH("epi_bwd1_kernel");
+
+  if (A.update) {
+    rc = lds_k3k4_theta_update(A.theta_full, A.ld_theta, A.n, 0, A.n, fbuf(B_FA), fbuf(B_FB), L.ldf, A.h + A.c, fbuf(B_C),
+                               A.lr, A.opt_kind, A.adam_m, A.adam_v, A.beta1, A.beta2, A.eps, A.adam_t, nullptr, 0, 0u, stream_);
+    if (rc != LDS_OK) return rc;
+  }
+  return LDS_OK;
+}

@@ -1,0 +1,254 @@
+"""Host-side wrappers of the C ABI on torch CUDA tensors (device memory, streams: plumbing only).
+
+Every function here enqueues hand-written sm_100a kernels from liblds_b200.so on torch's current
+stream. Nothing falls back to PyTorch arithmetic: without the library or a B200 these raise.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _f32(t, name):
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise TypeError(f"{name} must be a CUDA float32 tensor (got {t.dtype} on {t.device})")
+    return t
+
+
+def padded_ld(n):
+    return int(_lib.load().lds_padded_ld(int(n)))
+
+
+def num_nodes_from_triu_shape(t):
+    """Same formula as the reference (src/utils/graph.py:184-192)."""
+    from math import sqrt
+    return int(0.5 * sqrt((8 * t + 1) - 1))
+
+
+# ----------------------------------------------------------------------------- theta layouts (a1/a2)
+def theta_triu_to_full(triu, clamp=False, out=None):
+    """(T,) upper-triangle vector -> symmetric [n, ld] matrix (src/utils/graph.py:166-181)."""
+    _lib.require_device()
+    _f32(triu, "triu")
+    n = num_nodes_from_triu_shape(triu.numel())
+    if n * (n + 1) // 2 != triu.numel():
+        raise ValueError(f"{triu.numel()} is not a triangular number")
+    ld = padded_ld(n)
+    full = out if out is not None else torch.empty((n, ld), dtype=torch.float32, device=triu.device)
+    _lib.check(_lib.load().lds_theta_triu_to_full(_ptr(triu.contiguous()), _ptr(full), ld, n, int(bool(clamp)), _stream()),
+               "lds_theta_triu_to_full")
+    return full
+
+
+def theta_full_to_triu(full, n, sym_sum=False, ld=None):
+    _lib.require_device()
+    _f32(full, "full")
+    ld = full.stride(0) if ld is None else ld
+    triu = torch.empty(n * (n + 1) // 2, dtype=torch.float32, device=full.device)
+    _lib.check(_lib.load().lds_theta_full_to_triu(_ptr(full), ld, _ptr(triu), n, int(bool(sym_sum)), _stream()),
+               "lds_theta_full_to_triu")
+    return triu
+
+
+def theta_clamp_(full, n):
+    """project_parameters (src/models/graph.py:16-20, 63-64) on the full matrix, in place."""
+    _lib.require_device()
+    _lib.check(_lib.load().lds_theta_clamp(_ptr(_f32(full, "full")), full.stride(0), n, _stream()), "lds_theta_clamp")
+    return full
+
+
+def theta_stats(full, n):
+    """Device double[4]: sum(clamp(theta_full)), sum/min/max over the upper triangle (src/models/graph.py:69-78)."""
+    _lib.require_device()
+    out = torch.empty(4, dtype=torch.float64, device=full.device)
+    _lib.check(_lib.load().lds_theta_stats(_ptr(_f32(full, "full")), full.stride(0), n, _ptr(out), _stream()), "lds_theta_stats")
+    return out
+
+
+# ----------------------------------------------------------------------------- K1
+def k1_sample_normalize(theta_full, n, seed, step, sample=0, u=None, want_adj=True, want_sample=False,
+                        row0=0, rows=None):
+    """Fused sample / mirror / self-loop / degree / rsqrt pass. Returns (A_tilde bf16 [rows, ld] or None,
+    raw sample fp32 [rows, n] or None, deg [rows], rsqrt [rows])."""
+    _lib.require_device()
+    _f32(theta_full, "theta_full")
+    rows = n - row0 if rows is None else rows
+    dev = theta_full.device
+    ld = padded_ld(n)
+    adj = torch.empty((rows, ld), dtype=BF16, device=dev) if want_adj else None
+    smp = torch.empty((rows, n), dtype=torch.float32, device=dev) if want_sample else None
+    deg = torch.empty(rows, dtype=torch.float32, device=dev)
+    rs = torch.empty(rows, dtype=torch.float32, device=dev)
+    flags = 0
+    if u is not None:
+        _f32(u, "u")
+        flags |= _lib.K1_EXPLICIT_U
+    _lib.check(_lib.load().lds_k1_sample_normalize(
+        _ptr(theta_full), theta_full.stride(0), n, row0, rows, int(seed), int(step), int(sample),
+        _ptr(u), 0 if u is None else u.stride(0), _ptr(adj), ld, _ptr(smp), n, _ptr(deg), _ptr(rs), flags, _stream()),
+        "lds_k1_sample_normalize")
+    return adj, smp, deg, rs
+
+
+# ----------------------------------------------------------------------------- K2
+_ws_cache = {}
+
+
+def _workspace(nbytes, device, tag):
+    key = (tag, str(device))
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    off = (-buf.data_ptr()) % 1024
+    return buf[off:off + nbytes]
+
+
+def k2_propagate(adj, n, p, scale_in=None, scale_out=None, flags=0, out=None):
+    """z = scale_out * (A_tilde[rows, n] @ (scale_in * p[n, w])) on the tcgen05 tensor cores."""
+    _lib.require_device()
+    if adj.dtype != BF16 or not adj.is_cuda:
+        raise TypeError("adj must be a CUDA bfloat16 tensor")
+    _f32(p, "p")
+    rows, width = adj.shape[0], p.shape[1]
+    if p.shape[0] != n:
+        raise ValueError(f"p has {p.shape[0]} rows, expected {n}")
+    p = p if p.stride(1) == 1 else p.contiguous()
+    z = out if out is not None else torch.empty((rows, width), dtype=torch.float32, device=adj.device)
+    need = int(_lib.load().lds_k2_workspace_bytes(n, rows, width))
+    if need < 0:
+        raise ValueError(f"unsupported propagate shape n={n} rows={rows} width={width}")
+    ws = _workspace(need, adj.device, "k2")
+    _lib.check(_lib.load().lds_k2_propagate(
+        _ptr(adj), adj.stride(0), n, rows, _ptr(p), p.stride(0), width, _ptr(scale_in), _ptr(scale_out),
+        _ptr(z), z.stride(0), _ptr(ws), need, int(flags), _stream()), "lds_k2_propagate")
+    return z
+
+
+# ----------------------------------------------------------------------------- K3 + K4
+def k3k4_theta_update_(theta_full, n, fa, fb, cvec, lr, d=None, opt_kind=_lib.OPT_SGD, adam_m=None, adam_v=None,
+                       betas=(0.9, 0.999), eps=1e-8, t=1, row0=0, rows=None):
+    _lib.require_device()
+    rows = n - row0 if rows is None else rows
+    d = fa.shape[1] if d is None else d
+    _lib.check(_lib.load().lds_k3k4_theta_update(
+        _ptr(_f32(theta_full, "theta_full")), theta_full.stride(0), n, row0, rows, _ptr(_f32(fa, "fa")), _ptr(_f32(fb, "fb")),
+        fa.stride(0), d, _ptr(_f32(cvec, "cvec")), float(lr), int(opt_kind), _ptr(adam_m), _ptr(adam_v),
+        float(betas[0]), float(betas[1]), float(eps), int(t), None, 0, 0, _stream()), "lds_k3k4_theta_update")
+    return theta_full
+
+
+def k3_dense_grad(n, fa, fb, cvec, d=None, out=None, accumulate=False, row0=0, rows=None):
+    """grad[i][j] (+)= fa_i . fb_j + c_i (0 on the diagonal): dL/d(sample) of one propagate (composable path)."""
+    _lib.require_device()
+    rows = n - row0 if rows is None else rows
+    d = fa.shape[1] if d is None else d
+    g = out if out is not None else torch.empty((rows, n), dtype=torch.float32, device=fa.device)
+    flags = _lib.K3_DENSE_GRAD | (_lib.K3_ACCUMULATE if accumulate else 0)
+    _lib.check(_lib.load().lds_k3k4_theta_update(
+        None, 0, n, row0, rows, _ptr(_f32(fa, "fa")), _ptr(_f32(fb, "fb")), fa.stride(0), d, _ptr(_f32(cvec, "cvec")),
+        0.0, 0, None, None, 0.0, 0.0, 0.0, 1, _ptr(g), g.stride(0), flags, _stream()), "lds_k3k4_theta_update(dense)")
+    return g
+
+
+# ----------------------------------------------------------------------------- fused direct outer step
+class OuterStep:
+    """Resident state + workspace of the fused outer step (lds_outer_step). One instance per (theta, dataset)."""
+
+    BUFFERS = {"adj": 0, "deg": 1, "rsqrt": 2, "p1": 3, "z1": 4, "p2": 5, "z2": 6, "dz2": 7, "dp2": 8, "dz1": 9,
+               "dp1": 10, "fa": 11, "fb": 12, "cvec": 13}
+
+    def __init__(self, n, x, y, mask, hidden, classes):
+        _lib.require_device()
+        self.lib = _lib.load()
+        self.n, self.f, self.h, self.c = int(n), int(x.shape[1]), int(hidden), int(classes)
+        dev = x.device
+        self.device = dev
+        self.ld_x = (self.f + 3) // 4 * 4
+        self.x = torch.zeros((self.n, self.ld_x), dtype=torch.float32, device=dev)       # zero-padded copy, 16-byte rows
+        self.x[:, :self.f] = x
+        self.y = y.to(device=dev, dtype=torch.int64).contiguous()
+        self.set_mask(mask)
+        self.w0 = torch.zeros((self.h, self.ld_x), dtype=torch.float32, device=dev)       # staging, zero-padded
+        self.b0 = torch.zeros(self.h, dtype=torch.float32, device=dev)
+        self.w1 = torch.zeros((self.c, self.h), dtype=torch.float32, device=dev)
+        self.b1 = torch.zeros(self.c, dtype=torch.float32, device=dev)
+        nbytes = int(self.lib.lds_outer_step_workspace_bytes(self.n, self.f, self.h, self.c))
+        if nbytes < 0:
+            raise ValueError(f"unsupported shape n={n} f={self.f} h={hidden} c={classes}")
+        self._ws_raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        off = (-self._ws_raw.data_ptr()) % 1024
+        self.ws = self._ws_raw[off:off + nbytes]
+        self.ws_bytes = nbytes
+        self.scalars = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.args = _lib.OuterStepArgs()
+
+    def set_mask(self, mask):
+        m = mask.to(device=self.device)
+        self.mask = m.to(torch.uint8).contiguous()
+        self.mask_count = int(m.sum().item())
+
+    def set_weights(self, w0, b0, w1, b1):
+        """Copy the current GCN (fast) weights into the fixed, padded staging buffers."""
+        self.w0[:, :self.f].copy_(w0.detach())
+        self.b0.copy_(b0.detach())
+        self.w1.copy_(w1.detach())
+        self.b1.copy_(b1.detach())
+
+    def buffer(self, name):
+        """View of an intermediate buffer of the last step (tests / composable path)."""
+        which = self.BUFFERS[name]
+        ptr = self.lib.lds_outer_step_buffer(_ptr(self.ws), self.n, self.f, self.h, self.c, which)
+        off = ptr - self.ws.data_ptr()
+        n, h, c = self.n, self.h, self.c
+        ldf = int(self.lib.lds_outer_step_factor_ld(h, c))
+        shapes = {"adj": (n, padded_ld(n)), "deg": (n,), "rsqrt": (n,), "p1": (n, h), "z1": (n, h), "p2": (n, c), "z2": (n, c),
+                  "dz2": (n, c), "dp2": (n, c), "dz1": (n, h), "dp1": (n, h), "fa": (n, ldf), "fb": (n, ldf), "cvec": (n,)}
+        shape = shapes[name]
+        if name == "adj":
+            numel = shape[0] * shape[1]
+            return self.ws[off:off + 2 * numel].view(BF16).view(shape)
+        numel = 1
+        for s in shape:
+            numel *= s
+        return self.ws[off:off + 4 * numel].view(torch.float32).view(shape)
+
+    def run(self, theta_full, lr, seed, step, dropout_p=0.0, update=True, u=None, keep_x=None, keep_h=None,
+            opt_kind=_lib.OPT_SGD, adam_m=None, adam_v=None, betas=(0.9, 0.999), eps=1e-8, adam_t=1,
+            out_logp=None, k2_flags=0):
+        """Enqueue one fused outer step on the current stream. Results: self.scalars[0:2] = (loss, acc)."""
+        a = self.args
+        a.struct_bytes = ctypes.sizeof(_lib.OuterStepArgs)
+        a.n, a.f, a.h, a.c = self.n, self.f, self.h, self.c
+        a.theta_full, a.ld_theta = theta_full.data_ptr(), theta_full.stride(0)
+        a.x, a.ld_x = self.x.data_ptr(), self.ld_x
+        a.w0, a.ld_w0 = self.w0.data_ptr(), self.ld_x
+        a.b0, a.w1, a.b1 = self.b0.data_ptr(), self.w1.data_ptr(), self.b1.data_ptr()
+        a.y, a.mask, a.mask_count = self.y.data_ptr(), self.mask.data_ptr(), self.mask_count
+        a.dropout_p = float(dropout_p)
+        a.seed, a.step = int(seed), int(step)
+        a.u_explicit, a.ld_u = (None, 0) if u is None else (u.data_ptr(), u.stride(0))
+        a.keep_x = None if keep_x is None else keep_x.data_ptr()
+        a.keep_h = None if keep_h is None else keep_h.data_ptr()
+        a.lr, a.opt_kind = float(lr), int(opt_kind)
+        a.adam_m = None if adam_m is None else adam_m.data_ptr()
+        a.adam_v = None if adam_v is None else adam_v.data_ptr()
+        a.beta1, a.beta2, a.eps, a.adam_t = float(betas[0]), float(betas[1]), float(eps), int(adam_t)
+        a.update = int(bool(update))
+        a.out_scalars = self.scalars.data_ptr()
+        a.out_logp = None if out_logp is None else out_logp.data_ptr()
+        a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws_bytes
+        a.k2_flags, a.reserved = int(k2_flags), 0
+        _lib.check(self.lib.lds_outer_step(ctypes.byref(a), _stream()), "lds_outer_step")
+        return self.scalars

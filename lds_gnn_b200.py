@@ -1,0 +1,12 @@
+"""Import alias. The package directory is `lds-gnn_b200/` (the layout the build contract names); a hyphen
+is not importable, so this one-file shim loads that directory as the package `lds_gnn_b200`."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lds-gnn_b200")
+_spec = importlib.util.spec_from_file_location(__name__, os.path.join(_dir, "__init__.py"),
+                                               submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)

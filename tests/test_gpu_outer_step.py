@@ -1,0 +1,160 @@
+"""-m gpu parity tests of the fused direct outer step (lds_outer_step through the C ABI).
+
+Checked against (1) the committed golden vectors produced by the LIVE reference
+(`OuterProblemTrainer.train_step`, src/trainers/outer.py:57-87; oracle/make_golden.py) and
+(2) the numpy restatement on fresh seeded inputs, including the Philox path where the oracle
+regenerates the device's uniforms on the CPU. Tolerances are the north-star's: mask bit-exact,
+logits and dL/dtheta rel <= 1e-3 (inf-norm relative), loss within 1e-4.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import philox as PH
+from oracle import restatement as R
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def rel_inf(x, ref):
+    ref = np.asarray(ref, dtype=np.float64)
+    return float(np.abs(np.asarray(x, dtype=np.float64) - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def grad_from_factors(eng, n, theta_triu):
+    """Rebuild dL/dtheta_triu in fp64 from the device factor matrices (what K3 consumes)."""
+    fa = eng.buffer("fa").double().cpu().numpy()
+    fb = eng.buffer("fb").double().cpu().numpy()
+    c = eng.buffer("cvec").double().cpu().numpy()
+    g = fa @ fb.T + fb @ fa.T + c[:, None] + c[None, :]
+    np.fill_diagonal(g, 0.0)
+    gt = g[np.triu_indices(n)]
+    return gt * ((theta_triu >= 0) & (theta_triu <= 1))
+
+
+def make_engine(g):
+    from lds_gnn_b200 import kernels as K
+    n = int(g["n"])
+    eng = K.OuterStep(n, dev(g["x"]), dev(g["y"]), dev(g["mask"]), hidden=int(g["h"]), classes=int(g["c"]))
+    eng.set_weights(dev(g["w0"]), dev(g["b0"]), dev(g["w1"]), dev(g["b1"]))
+    return K, eng, n
+
+
+def test_golden_outer_step(golden):
+    g = golden
+    K, eng, n = make_engine(g)
+    p = float(g["p"])
+    theta = g["theta_triu"].astype(np.float32)
+    for s in range(int(g["steps"])):
+        full = K.theta_triu_to_full(dev(theta))
+        logp = torch.empty((n, int(g["c"])), dtype=torch.float32, device="cuda")
+        kx = dev(g[f"keep_x{s}"].astype(np.uint8)) if p > 0 else None
+        kh = dev(g[f"keep_h{s}"].astype(np.uint8)) if p > 0 else None
+        lr = float(g[f"lr_used{s}_f64"])
+        sc = eng.run(full, lr=lr, seed=0, step=s, dropout_p=p, update=True, u=dev(g[f"U{s}"]), keep_x=kx, keep_h=kh,
+                     out_logp=logp)
+        torch.cuda.synchronize()
+        # sampled mask: bit exact (the reference's sample keeps the sampled diagonal; A_tilde sets it to 1)
+        sample = g[f"sample{s}"].astype(np.float32)
+        a_ref = sample.copy(); np.fill_diagonal(a_ref, 1.0)
+        assert np.array_equal(eng.buffer("adj")[:, :n].float().cpu().numpy(), a_ref), "sampled mask differs"
+        assert np.array_equal(eng.buffer("deg").cpu().numpy(), a_ref.sum(1))
+        # forward
+        assert rel_inf(logp.cpu().numpy(), g[f"logp{s}_f64"]) < 1e-3
+        loss, acc = float(sc[0].item()), float(sc[1].item())
+        assert abs(loss - float(g[f"loss{s}_f64"])) < 1e-4 * max(1.0, abs(float(g[f"loss{s}_f64"])))
+        assert abs(acc - float(g[f"acc{s}_f64"])) < 1e-6
+        # hypergradient (factor form) and projected update
+        gt = grad_from_factors(eng, n, theta)
+        ref_g = g[f"grad_triu{s}_f64"]
+        assert rel_inf(gt, ref_g) < 1e-3, f"dL/dtheta rel err {rel_inf(gt, ref_g)}"
+        new = K.theta_full_to_triu(full, n).cpu().numpy()
+        ref_new = g[f"theta_new{s}_f64"]
+        tol = 1e-3 * lr * max(np.abs(ref_g).max(), 1e-12) + 2e-7
+        assert np.abs(new - ref_new).max() <= tol
+        sym = full[:, :n].cpu().numpy()
+        assert np.array_equal(sym, sym.T)
+        theta = g[f"theta_new{s}_f32"].astype(np.float32)          # continue from the reference's own state
+    # statistics() of the final state (src/models/graph.py:69-78)
+    st = K.theta_stats(K.theta_triu_to_full(dev(theta)), n).cpu().numpy()
+    assert abs(st[0] - float(g["stat_expected_num_edges_f64"])) <= 1e-4 * max(1.0, float(g["stat_expected_num_edges_f64"]))
+    assert abs(st[1] / len(theta) - float(g["stat_mean_prob_f64"])) < 1e-5
+
+
+@pytest.mark.parametrize("n,f,h,c,p", [(50, 30, 16, 7, 0.0), (301, 120, 16, 7, 0.5), (700, 64, 64, 7, 0.5),
+                                       (1200, 200, 32, 10, 0.0), (2708, 1433, 16, 7, 0.5)])
+def test_philox_outer_step_matches_oracle(n, f, h, c, p):
+    """Philox mode end to end: the oracle regenerates the edge uniforms and both dropout masks on the CPU."""
+    from oracle.make_golden import make_inputs
+    from lds_gnn_b200 import kernels as K
+    inp = make_inputs(seed=n, n=n, f=f, h=h, c=c, theta_kind="mixed" if n < 2000 else "sparse", p=p, mask_frac=0.2)
+    seed, step, lr = 0xABCDEF0123, 11, 0.3
+    eng = K.OuterStep(n, dev(inp["x"]), dev(inp["y"]), dev(inp["mask"]), hidden=h, classes=c)
+    eng.set_weights(dev(inp["w0"]), dev(inp["b0"]), dev(inp["w1"]), dev(inp["b1"]))
+    full = K.theta_triu_to_full(dev(inp["theta_triu"]))
+    logp = torch.empty((n, c), dtype=torch.float32, device="cuda")
+    sc = eng.run(full, lr=lr, seed=seed, step=step, dropout_p=p, update=True, out_logp=logp)
+    torch.cuda.synchronize()
+    u = PH.edge_uniforms(n, seed, step)
+    kx = PH.dropout_keep_mask(n, f, p, seed, step, PH.STREAM_DROP_X) if p > 0 else None
+    kh = PH.dropout_keep_mask(n, h, p, seed, step, PH.STREAM_DROP_H) if p > 0 else None
+    o = R.outer_step(inp["theta_triu"], u, inp["x"], inp["w0"], inp["b0"], inp["w1"], inp["b1"], inp["y"], inp["mask"],
+                     lr=lr, p=p, keep_x=kx, keep_h=kh)
+    assert np.array_equal(eng.buffer("adj")[:, :n].float().cpu().numpy(), o["a_tilde"].astype(np.float32))
+    assert rel_inf(eng.buffer("p1").cpu().numpy(), o["p1"]) < 1e-4
+    assert rel_inf(eng.buffer("z1").cpu().numpy(), o["z1"]) < 1e-3
+    assert rel_inf(logp.cpu().numpy(), o["logp"]) < 1e-3
+    assert abs(float(sc[0].item()) - o["loss"]) < 1e-4 * max(1.0, abs(o["loss"]))
+    assert abs(float(sc[1].item()) - o["acc"]) < 1e-6
+    for name in ("dz2", "dp2", "dz1", "dp1"):
+        assert rel_inf(eng.buffer(name).cpu().numpy(), o[name]) < 1e-3, name
+    assert rel_inf(eng.buffer("cvec").cpu().numpy(), o["c"]) < 1e-3
+    gt = grad_from_factors(eng, n, inp["theta_triu"])
+    assert rel_inf(gt, o["d_theta_triu"]) < 1e-3
+    new = K.theta_full_to_triu(full, n).cpu().numpy()
+    assert np.abs(new - o["theta_new"]).max() <= 1e-3 * lr * np.abs(o["d_theta_triu"]).max() + 2e-7
+
+
+def test_outer_step_update_flag_and_determinism():
+    from oracle.make_golden import make_inputs
+    from lds_gnn_b200 import kernels as K
+    n, f, h, c = 400, 60, 16, 7
+    inp = make_inputs(seed=9, n=n, f=f, h=h, c=c, theta_kind="uniform", p=0.5)
+    eng = K.OuterStep(n, dev(inp["x"]), dev(inp["y"]), dev(inp["mask"]), hidden=h, classes=c)
+    eng.set_weights(dev(inp["w0"]), dev(inp["b0"]), dev(inp["w1"]), dev(inp["b1"]))
+    full = K.theta_triu_to_full(dev(inp["theta_triu"]))
+    before = full.clone()
+    eng.run(full, lr=0.5, seed=3, step=0, dropout_p=0.5, update=False)
+    assert torch.equal(full, before)                                     # update=0 leaves theta untouched
+    outs = []
+    for _ in range(2):
+        t = before.clone()
+        sc = eng.run(t, lr=0.5, seed=3, step=0, dropout_p=0.5, update=True).clone()
+        outs.append((t.clone(), sc))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])   # bitwise reproducible
+    t2 = before.clone()
+    eng.run(t2, lr=0.5, seed=3, step=1, dropout_p=0.5, update=True)
+    assert not torch.equal(t2, outs[0][0])                               # a new step draws a new graph
+
+
+def test_error_paths_do_not_abort():
+    from lds_gnn_b200 import _lib, kernels as K
+    lib = _lib.load()
+    full = torch.zeros((8, 64), device="cuda")
+    with pytest.raises(RuntimeError, match="row0 must be even"):
+        K.k1_sample_normalize(full, 8, 0, 0, row0=1, rows=2)
+    with pytest.raises(RuntimeError, match="outside"):
+        K.k1_sample_normalize(full, 8, 0, 0, row0=6, rows=4)
+    assert lib.lds_k2_workspace_bytes(100, 100, 300) == -1
+    args = _lib.OuterStepArgs()
+    args.struct_bytes = 8
+    import ctypes
+    assert lib.lds_outer_step(ctypes.byref(args), None) != 0
+    assert "struct_bytes" in _lib.last_error()
