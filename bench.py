@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — LDS outer steps/s on B200 (BASELINE.json metric), one JSON line on stdout.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload citeseer|cora|tiny] [--impl ours|reference]
+
+A "step" is one direct outer step (OuterProblemTrainer.train_step with model_forward at fixed GCN weights,
+SGD, one sample, dropout 0.5; reference src/trainers/outer.py:57-87) on synthetic data of the named shape.
+  value     device-resident throughput: K calls of the fused C entry point `lds_outer_step`, theta / X / weights
+            already in HBM, each step timed with CUDA events on the launching stream, L2 flushed between steps.
+  e2e       the same metric through the reference-facing API `OuterProblemTrainer.train_step(inner.model_forward)`:
+            every step copies that step's GCN weights from pinned host memory to the device and reads Metrics
+            (loss, acc) back to the host; wall clock between two device synchronisations.
+  roofline  the dominant kernel of the step (by device time, per-kernel CUDA events recorded inside the library
+            on the launching stream): algorithmic bytes per launch / its mean duration vs the measured HBM peak.
+  cpu_baseline  the oracle's torch/CPU port of the reference's own op sequence, timed on this box's host cores
+            (rank 0, N=1 only), a bounded sample of the same workload.
+--impl reference times that CPU port for K steps and prints the same line with "impl": "reference".
+N > 1 (torchrun): replicas only this round — every rank runs the same single-GPU workload on its own theta
+(no data-path collective), value = sum of units / max-over-ranks time, "scaling": "weak".
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "lds_outer_steps_per_sec"
+UNIT = "steps/s"
+KERNEL_NAMES = {0: "k1_sample_normalize", 1: "feat_linear", 2: "k2_mma_tcgen05", 3: "epi_layer1", 4: "epi_layer2",
+                5: "epi_bwd2", 6: "epi_bwd1", 7: "k3k4_theta_update"}
+LAUNCHES_PER_STEP = 11      # K1, feature GEMM, 4 x K2, 4 row epilogues, K3+K4 (csrc/lds_outer_step.cu)
+HYPER = dict(lr=0.1, lr_decay=0.99, dropout=0.5)            # configs/seml/final/lds.yaml:18-110
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="citeseer")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_peaks_json():
+    return peaks()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.file, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.file.flush()
+        self.file.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.file.read().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.file.name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def make_workload(name, seed=0):
+    from lds_gnn_b200.data import SHAPES, make_dataset
+    n, f, c, h, _, _ = SHAPES[name]
+    data = make_dataset(name, seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    lim0, lim1 = np.sqrt(6.0 / (f + h)), np.sqrt(6.0 / (h + c))          # xavier-uniform, zero bias (layers.py:38-40)
+    weights = dict(w0=torch.as_tensor(rng.uniform(-lim0, lim0, (h, f)).astype(np.float32)), b0=torch.zeros(h),
+                   w1=torch.as_tensor(rng.uniform(-lim1, lim1, (c, h)).astype(np.float32)), b1=torch.zeros(c))
+    # outer objective mask = half of the validation nodes (src/scripts/bilevel.py:77)
+    val_idx = data.val_mask.nonzero().flatten()
+    opt_mask = torch.zeros_like(data.val_mask)
+    opt_mask[val_idx[len(val_idx) // 2:]] = True
+    return data, weights, opt_mask, dict(n=n, f=f, c=c, h=h)
+
+
+def algorithmic_bytes(shape):
+    n, f = shape["n"], shape["f"]
+    per_kernel = {0: 6 * n * n, 2: 2 * n * n, 7: 8 * n * n, 1: 4 * n * f}
+    step = 6 * n * n + 4 * 2 * n * n + 8 * n * n + 4 * n * f            # the outer step reads X once (no dW)
+    return per_kernel, step
+
+
+# ------------------------------------------------------------------------------------------------ ours
+def run_ours(args, rank, world, device):
+    import torch.distributed as dist
+    from lds_gnn_b200 import _lib, kernels as K
+    from lds_gnn_b200.models.gcn import MetaDenseGCN
+    from lds_gnn_b200.models.graph import BernoulliGraphModel
+    from lds_gnn_b200.trainers.inner import InnerProblemTrainer
+    from lds_gnn_b200.trainers.outer import OuterProblemTrainer
+
+    data, weights, opt_mask, shape = make_workload(args.workload, seed=rank)
+    n, f, h, c = shape["n"], shape["f"], shape["h"], shape["c"]
+    data = data.to(device)
+    opt_mask = opt_mask.to(device)
+    lib = _lib.load()
+
+    # ---- device-resident arm: the fused C entry point ------------------------------------------------
+    eng = K.OuterStep(n, data.x, data.y, opt_mask, hidden=h, classes=c)
+    eng.set_weights(*(weights[k].to(device) for k in ("w0", "b0", "w1", "b1")))
+    theta = K.theta_triu_to_full(data.dense_adj[torch.triu_indices(n, n)[0], torch.triu_indices(n, n)[1]].contiguous())
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)        # > 126 MB L2
+    lr = HYPER["lr"]
+    seed = 1234 + rank
+
+    def one(step_idx, lr_now):
+        eng.run(theta, lr=lr_now, seed=seed, step=step_idx, dropout_p=HYPER["dropout"], update=True)
+
+    for w in range(args.warmup):
+        one(w, lr); lr *= HYPER["lr_decay"]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(torch.cuda.current_device())
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)                       # evict theta / A_tilde / X from L2 between timed steps
+        starts[k].record()
+        one(args.warmup + k, lr); lr *= HYPER["lr_decay"]
+        ends[k].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    loss_after = float(eng.scalars[0].item())
+
+    # warm-L2 figure (back-to-back, no flush) for context
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for k in range(args.steps):
+        one(10_000 + k, lr)
+    t1.record()
+    torch.cuda.synchronize()
+    warm_ms = t0.elapsed_time(t1)
+
+    # ---- per-kernel durations (CUDA events inside the library, on the launching stream) ---------------
+    per_kernel = {}
+    ms_buf = (ctypes.c_float * 64)()
+    id_buf = (ctypes.c_int32 * 64)()
+    reps = min(args.steps, 20)
+    for k in range(reps):
+        flush.fill_(k & 0xFF)
+        lib.lds_profile_begin()
+        one(20_000 + k, lr)
+        cnt = lib.lds_profile_end(ms_buf, id_buf, 64)
+        for i in range(max(cnt, 0)):
+            per_kernel.setdefault(int(id_buf[i]), []).append(float(ms_buf[i]))
+    clock_info = clocks.stop()
+
+    # ---- e2e arm: the reference-facing API with host buffers ------------------------------------------
+    gcn = MetaDenseGCN(f, h, c, dropout=HYPER["dropout"]).to(device)
+    inner = InnerProblemTrainer(gcn, data)
+    model = BernoulliGraphModel(data.dense_adj).to(device)
+    opt = torch.optim.SGD(model.parameters(), lr=HYPER["lr"])
+    outer = OuterProblemTrainer(optimizer=opt, data=data, opt_mask=opt_mask, model=model, smoothness_factor=0.0,
+                                disconnection_factor=0.0, sparsity_factor=0.0, regularize=False,
+                                lr_decay=HYPER["lr_decay"], pretrain=False)
+    host_w = {k: v.clone().pin_memory() for k, v in weights.items()}
+    names = {"w0": "layer_in.fc.weight", "b0": "layer_in.fc.bias", "w1": "layer_out.fc.weight", "b1": "layer_out.fc.bias"}
+    h2d_bytes = sum(v.numel() * 4 for v in host_w.values())
+
+    def api_step():
+        for k, pname in names.items():                     # this step's fast weights: pinned host -> device
+            inner.model_params[pname].data.copy_(host_w[k], non_blocking=True)
+        return outer.train_step(inner.model_forward)       # returns host floats (device -> host read inside)
+
+    for _ in range(args.warmup):
+        api_step()
+    assert outer.last_route == "fused", "bench e2e must exercise the fused CUDA path"
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_start = time.perf_counter()
+    for _ in range(args.steps):
+        m = api_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t_start
+    if world > 1:
+        dist.barrier()
+
+    # ---- reduce over ranks -----------------------------------------------------------------------------
+    times = torch.tensor([dev_ms, e2e_s * 1e3, warm_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, warm_ms = times.tolist()
+    total_steps = args.steps * world
+    value = total_steps / (dev_ms / 1e3)
+    per_kernel_bytes, step_bytes = algorithmic_bytes(shape)
+    hbm_peak, peak_src = peaks()
+    kernel_summary = {}
+    for kid, vals in per_kernel.items():
+        launches = len(vals) / reps
+        kernel_summary[KERNEL_NAMES.get(kid, str(kid))] = {"launches_per_step": launches, "mean_us": 1e3 * sum(vals) / len(vals),
+                                                            "step_share_us": 1e3 * sum(vals) / reps}
+    dominant_id = max(per_kernel, key=lambda k: sum(per_kernel[k])) if per_kernel else None
+    roofline = None
+    if dominant_id is not None:
+        mean_s = sum(per_kernel[dominant_id]) / len(per_kernel[dominant_id]) / 1e3
+        alg = per_kernel_bytes.get(dominant_id)
+        if alg is not None:
+            achieved = alg / mean_s / 1e9
+            roofline = {"kernel": KERNEL_NAMES[dominant_id], "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak,
+                        "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": None,
+                        "algorithmic_bytes_per_launch": alg, "mean_launch_us": round(mean_s * 1e6, 2), "peak_source": peak_src,
+                        "note": "working set fits the 126 MB L2 at this shape: DRAM traffic can be below algorithmic bytes"}
+        else:
+            roofline = {"kernel": KERNEL_NAMES.get(dominant_id), "bound": "latency", "achieved": None, "peak": hbm_peak,
+                        "unit": "GB/s", "frac": None, "traffic": None}
+    step_frac = (step_bytes / (dev_ms / 1e3 / args.steps)) / 1e9 / hbm_peak
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(dev_ms / args.steps, 5), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16 adjacency x (bf16 hi+lo) operands, fp32 accumulate; fp32 theta",
+        "data": "synthetic",
+        "config": {"workload": f"LDS-GCN direct outer step, {args.workload} shape (N={n}, F={f}, C={c}, hidden={h}), SGD lr 0.1 decay 0.99, "
+                               f"dropout 0.5, 1 sample/step", "parallelism": "single GPU" if world == 1 else f"{world} independent replicas",
+                   "l2": "flushed between timed steps (256 MiB write)", "theta_init": "synthetic SBM adjacency"},
+        "clocks": clock_info,
+        "e2e": {"value": round(total_steps / (e2e_ms / 1e3), 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
+                "api": "OuterProblemTrainer.train_step(InnerProblemTrainer.model_forward)", "l2": "not flushed"},
+        "gpu_launches": LAUNCHES_PER_STEP * args.steps,
+        "roofline": roofline,
+        "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "frac_of_hbm_peak": round(step_frac, 4)},
+        "warm_l2": {"value": round(total_steps / (warm_ms / 1e3), 2), "unit": UNIT, "ms_per_step": round(warm_ms / args.steps, 5)},
+        "kernels": kernel_summary,
+        "final_loss": loss_after, "e2e_last_metrics": {"loss": m.loss, "acc": m.acc},
+    }
+    return line
+
+
+# ------------------------------------------------------------------------------------------------ reference / CPU baseline
+def time_cpu_port(workload, steps, warmup):
+    """The oracle's op-for-op torch/CPU port of the reference outer step on this box's host cores."""
+    from oracle.reference_port import ReferenceOuterStep
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    data, weights, opt_mask, shape = make_workload(workload, seed=0)
+    n = shape["n"]
+    iu = torch.triu_indices(n, n)
+    theta = data.dense_adj[iu[0], iu[1]].clone()
+    ref = ReferenceOuterStep(theta, data.x, data.y, opt_mask, weights["w0"], weights["b0"], weights["w1"], weights["b1"],
+                             lr=HYPER["lr"], lr_decay=HYPER["lr_decay"], dropout=HYPER["dropout"])
+    for _ in range(warmup):
+        ref.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss, acc = ref.step()
+    dt = time.perf_counter() - t0
+    return steps / dt, dt / steps * 1e3, torch.get_num_threads(), shape, loss
+
+
+def run_reference(args):
+    rate, ms, threads, shape, loss = time_cpu_port(args.workload, args.steps, max(1, min(args.warmup, 2)))
+    cpu = {"value": round(rate, 4), "unit": UNIT, "cores": threads, "kind": "port",
+           "sample": f"{args.steps} full outer steps of the same workload (oracle/reference_port.py, torch CPU, {threads} threads)"}
+    return {"impl": "reference", "metric": METRIC, "value": round(rate, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": max(1, min(args.warmup, 2)), "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"LDS-GCN direct outer step, {args.workload} shape (N={shape['n']}, F={shape['f']}, C={shape['c']}, "
+                                   f"hidden={shape['h']}), SGD lr 0.1 decay 0.99, dropout 0.5, 1 sample/step", "parallelism": "host CPU"},
+            "cpu_baseline": cpu, "e2e": {"value": round(rate, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "final_loss": loss}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps(run_reference(args)), flush=True)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: no CUDA device visible (there is no CPU fallback; use --impl reference for the CPU port)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    line = run_ours(args, rank, world, device)
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            rate, ms, threads, _, _ = time_cpu_port(args.workload, args.cpu_steps, 1)
+            line["cpu_baseline"] = {"value": round(rate, 4), "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{args.cpu_steps} full outer steps of the same workload after 1 warm-up "
+                                              f"(oracle/reference_port.py: the reference's torch op sequence on CPU)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

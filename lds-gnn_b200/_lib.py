@@ -40,6 +40,8 @@ SIGNATURES = {
     "lds_outer_step": (c_int32, [c_void_p, c_void_p]),
     "lds_outer_step_buffer": (c_void_p, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32]),
     "lds_outer_step_factor_ld": (c_int64, [c_int32, c_int32]),
+    "lds_profile_begin": (c_int32, []),
+    "lds_profile_end": (c_int32, [c_void_p, c_void_p, c_int32]),
 }
 
 

@@ -30,7 +30,44 @@ int num_sms() {
   return cached;
 }
 
+constexpr int kMaxMarks = 64;
+static bool g_profiling = false;
+static int g_marks = 0;
+static cudaEvent_t g_events[kMaxMarks];
+static int g_ids[kMaxMarks];
+static bool g_events_created = false;
+
+void profile_mark(cudaStream_t stream, int id) {
+  if (!g_profiling || g_marks >= kMaxMarks) return;
+  cudaEventRecord(g_events[g_marks], stream);
+  g_ids[g_marks++] = id;
+}
+
 }  // namespace lds
+
+extern "C" int32_t lds_profile_begin(void) {
+  if (!lds::g_events_created) {
+    for (int i = 0; i < lds::kMaxMarks; ++i) LDS_CHECK_CUDA(cudaEventCreate(&lds::g_events[i]));
+    lds::g_events_created = true;
+  }
+  lds::g_marks = 0;
+  lds::g_profiling = true;
+  return LDS_OK;
+}
+
+extern "C" int32_t lds_profile_end(float* ms_out, int32_t* ids_out, int32_t cap) {
+  lds::g_profiling = false;
+  if (lds::g_marks == 0) return 0;
+  if (cudaEventSynchronize(lds::g_events[lds::g_marks - 1]) != cudaSuccess) { (void)cudaGetLastError(); return -1; }
+  int n = 0;
+  for (int i = 1; i < lds::g_marks && n < cap; ++i, ++n) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, lds::g_events[i - 1], lds::g_events[i]);
+    ms_out[n] = ms;
+    ids_out[n] = lds::g_ids[i];
+  }
+  return n;
+}
 
 extern "C" int32_t lds_version(void) { return 100; }   // 0.1.0
 

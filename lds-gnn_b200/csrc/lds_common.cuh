@@ -27,6 +27,9 @@ constexpr int kNumSMsB200 = 148;
 
 int num_sms();                        // cached cudaDevAttrMultiProcessorCount of the current device
 
+// Per-kernel timing of lds_outer_step for bench.py (lds_profile_begin/end): records a CUDA event after each launch.
+void profile_mark(cudaStream_t stream, int id);
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

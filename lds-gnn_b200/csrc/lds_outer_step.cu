@@ -392,10 +392,12 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   auto fbuf = [&](int b) { return reinterpret_cast<float*>(ws + L.off[b]); };
 
   int32_t rc;
+  profile_mark(stream, -1);
   // K1
   rc = lds_k1_sample_normalize(A.theta_full, A.ld_theta, A.n, 0, A.n, A.seed, A.step, 0, A.u_explicit, A.ld_u,
                                buf(B_A), L.lda, nullptr, 0, fbuf(B_DEG), fbuf(B_RS), A.u_explicit ? LDS_K1_EXPLICIT_U : 0u, stream_);
   if (rc != LDS_OK) return rc;
+  profile_mark(stream, 0);
 
   DropCfg dx, dh;
   dx.p = dh.p = A.dropout_p;
@@ -412,6 +414,7 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
 
   feat_linear_kernel<<<egrid, EPI_THREADS, 0, stream>>>(A.x, A.ld_x, A.n, A.f, A.w0, A.ld_w0, A.b0, A.h, dx, fbuf(B_RS), fbuf(B_P1), bt_hi, bt_lo, L.ldb, L.hp1);
   LDS_CHECK_LAUNCH("feat_linear_kernel");
+  profile_mark(stream, 1);
 
   EpiArgs E;
   E.n = A.n; E.h = A.h; E.c = A.c; E.hp1 = L.hp1; E.hp2 = L.hp2; E.s1 = L.s1; E.s2 = L.s2;
@@ -425,26 +428,33 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
 
   auto propagate = [&](const K2Sched& s) -> int32_t {
     if (A.k2_flags & LDS_K2_SIMT) { set_error("lds_outer_step: LDS_K2_SIMT is only available through lds_k2_propagate"); return LDS_ERR_ARG; }
-    return k2_launch_mma(buf(B_A), L.lda, A.n, A.n, bt_hi, bt_lo, L.ldb, fbuf(B_PARTIAL), s, use_lo, stream);
+    const int32_t r = k2_launch_mma(buf(B_A), L.lda, A.n, A.n, bt_hi, bt_lo, L.ldb, fbuf(B_PARTIAL), s, use_lo, stream);
+    profile_mark(stream, 2);
+    return r;
   };
 
   if ((rc = propagate(L.s1)) != LDS_OK) return rc;
   epi_layer1_kernel<<<egrid, EPI_THREADS, 0, stream>>>(E);
   LDS_CHECK_LAUNCH("epi_layer1_kernel");
+  profile_mark(stream, 3);
   if ((rc = propagate(L.s2)) != LDS_OK) return rc;
   epi_layer2_kernel<<<egrid, EPI_THREADS, 0, stream>>>(E);
   LDS_CHECK_LAUNCH("epi_layer2_kernel");
+  profile_mark(stream, 4);
   if ((rc = propagate(L.s2)) != LDS_OK) return rc;
   epi_bwd2_kernel<<<egrid, EPI_THREADS, 0, stream>>>(E);
   LDS_CHECK_LAUNCH("epi_bwd2_kernel");
+  profile_mark(stream, 5);
   if ((rc = propagate(L.s1)) != LDS_OK) return rc;
   epi_bwd1_kernel<<<egrid, EPI_THREADS, 0, stream>>>(E);
   LDS_CHECK_LAUNCH("epi_bwd1_kernel");
+  profile_mark(stream, 6);
 
   if (A.update) {
     rc = lds_k3k4_theta_update(A.theta_full, A.ld_theta, A.n, 0, A.n, fbuf(B_FA), fbuf(B_FB), L.ldf, A.h + A.c, fbuf(B_C),
                                A.lr, A.opt_kind, A.adam_m, A.adam_v, A.beta1, A.beta2, A.eps, A.adam_t, nullptr, 0, 0u, stream_);
     if (rc != LDS_OK) return rc;
+    profile_mark(stream, 7);
   }
   return LDS_OK;
 }

@@ -1,0 +1,146 @@
+"""Graph generative models with the reference's API (src/models/graph.py:16-78): `GraphGenerativeModel`,
+`ParameterClamper`, `BernoulliGraphModel` (LDS: one Bernoulli parameter per potential edge).
+
+State compatibility: `probs` is an `nn.Parameter` with the reference's shape — the (T,) row-major upper
+triangle incl. diagonal for the undirected model, (N, N) for `directed=True` — and `state_dict()` has the
+single key `probs`, so the in-memory checkpoints of the bilevel loop (src/trainers/bilevel.py:96-98,131-132)
+round-trip. The kernels work on a full symmetric N x ld fp32 copy (`theta_full()`): coalesced rows for both
+triangles and a natural row-block sharding. The two views are kept consistent lazily:
+  * anything that touches `probs` through the Module API (attribute access, parameters(), state_dict(),
+    optimizers holding the Parameter) sees fresh values — a fused step only marks `probs` stale and the
+    conversion kernel runs on the next access;
+  * `theta_full()` re-expands `probs` when the Parameter was modified since the last sync (tensor version
+    counter / storage pointer).
+"""
+from abc import ABC, abstractmethod
+from typing import Dict
+
+import torch
+from torch import Tensor, nn
+from torch.nn import Parameter
+
+from ..utils.graph import get_triu_values, is_square_matrix, triu_values_to_symmetric_matrix
+from ..utils.tracking import setup_basic_logger
+from .sampling import Sampler
+
+logger = setup_basic_logger()
+
+
+class ParameterClamper(object):
+    """Clamp every parameter of a module to [0, 1] in place (src/models/graph.py:16-20)."""
+
+    def __call__(self, module):
+        for param in module.parameters():
+            param.data.clamp_(0.0, 1.0)
+
+
+class GraphGenerativeModel(nn.Module, ABC):
+
+    def __init__(self, sample_undirected: bool = True, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.sample_undirected = sample_undirected
+
+    def sample(self, *args, **kwargs) -> Tensor:
+        return Sampler.sample(self.forward())
+
+    def project_parameters(self):
+        pass
+
+    def refine(self):
+        logger.warning("Model called to refine current parameters but method is not implemented. Ignore...")
+
+    @abstractmethod
+    def statistics(self) -> Dict[str, float]:
+        pass
+
+
+class BernoulliGraphModel(GraphGenerativeModel):
+
+    def __init__(self, init_matrix: Tensor, directed: bool = False):
+        """init_matrix: square matrix of initial edge probabilities (the adjacency for LDS, factory.py:60-62)."""
+        super().__init__()
+        assert is_square_matrix(init_matrix)
+        self.directed = directed
+        self.orig_matrix = init_matrix
+        self._n = init_matrix.size(0)
+        self._full = None            # [n, ld] fp32 device copy (unclamped, symmetric)
+        self._full_key = None        # (data_ptr, version) of `probs` when `_full` was built from it
+        self._probs_stale = False    # `_full` is newer than `probs` (after fused steps)
+        values = init_matrix if directed else get_triu_values(init_matrix)
+        self.probs = Parameter(values, requires_grad=True)
+
+    # ---- lazy consistency between the (T,) Parameter and the full device matrix ------------------
+    def _probs_param(self) -> Parameter:
+        return self._parameters["probs"]
+
+    def _sync_probs(self):
+        if self._probs_stale:
+            from .. import kernels
+            p = self._probs_param()
+            with torch.no_grad():
+                p.data.copy_(kernels.theta_full_to_triu(self._full, self._n))
+            self._probs_stale = False
+            self._full_key = (p.data_ptr(), p._version)
+
+    def __getattr__(self, name):
+        if name == "probs" and "_parameters" in self.__dict__:
+            self._sync_probs()
+        return super().__getattr__(name)
+
+    def named_parameters(self, *args, **kwargs):
+        self._sync_probs()
+        return super().named_parameters(*args, **kwargs)
+
+    def state_dict(self, *args, **kwargs):
+        self._sync_probs()
+        return super().state_dict(*args, **kwargs)
+
+    def load_state_dict(self, state_dict, *args, **kwargs):
+        self._probs_stale = False    # the loaded values win over a newer device copy
+        return super().load_state_dict(state_dict, *args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._sync_probs()
+        self._full, self._full_key = None, None
+        return super()._apply(fn, *args, **kwargs)
+
+    def theta_full(self) -> Tensor:
+        """Full symmetric [n, ld] fp32 device matrix of the current probabilities (undirected model)."""
+        if self.directed:
+            raise NotImplementedError("theta_full() is defined for the undirected LDS model")
+        p = self._probs_param()
+        if not p.is_cuda:
+            raise RuntimeError("BernoulliGraphModel: the B200 path needs the model on a CUDA device (model.to('cuda')); no CPU fallback")
+        key = (p.data_ptr(), p._version)
+        if self._full is None or (not self._probs_stale and key != self._full_key):
+            from .. import kernels
+            self._full = kernels.theta_triu_to_full(p.detach(), clamp=False, out=self._full)
+            self._full_key = key
+        return self._full
+
+    def mark_full_updated(self):
+        """Called by the fused outer step after it updated `theta_full()` in place."""
+        self._probs_stale = True
+
+    # ---- reference API ---------------------------------------------------------------------------
+    def project_parameters(self):
+        self.apply(ParameterClamper())
+
+    def forward(self, *args, **kwargs) -> Tensor:
+        return self.probs if self.directed else triu_values_to_symmetric_matrix(self.probs)  # type: ignore
+
+    def statistics(self) -> Dict[str, float]:
+        """Same keys and definitions as the reference (src/models/graph.py:69-78); one reduction kernel and
+        a single device->host copy instead of a rebuild of the N x N matrix plus five `.item()` syncs."""
+        if self.directed or not self._probs_param().is_cuda:
+            sample = self.forward()
+            probs = self.probs
+            total = sample.sum().item()
+            return {"expected_num_edges": total, "percentage_edges_expected": total / sample.size(0) ** 2,
+                    "mean_prob": torch.mean(probs).item(), "min_prob": torch.min(probs).item(),
+                    "max_prob": torch.max(probs).item()}
+        from .. import kernels
+        s = kernels.theta_stats(self.theta_full(), self._n).tolist()
+        t = self._n * (self._n + 1) // 2
+        return {"expected_num_edges": s[0], "percentage_edges_expected": s[0] / (self._n ** 2),
+                "mean_prob": s[1] / t, "min_prob": s[2], "max_prob": s[3]}

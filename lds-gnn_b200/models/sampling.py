@@ -1,0 +1,149 @@
+"""Graph sampling with the reference's API (src/models/sampling.py): `sample_graph`, `Sampler.sample`,
+`straight_through_estimator`, `SPARSIFICATION`.
+
+The LDS path (undirected=True, sparsification NONE, dense=False — the only combination any LDS config
+uses, configs/sacred/lds/config.json, configs/seml/final/lds.yaml) runs K1: one fused CUDA pass that draws
+counter-based Philox uniforms for the upper triangle only, mirrors, and at the same time produces the
+bf16 self-looped adjacency, the degrees and deg^-1/2 that the GCN needs next. The returned tensor is the
+dense {0,1} sample (sampled diagonal kept, like the reference) with a straight-through gradient to the
+probabilities; the by-products ride along as `graph._lds_handle`.
+
+KNN / EPS sparsification and `dense=True` belong to the GAE/GRCN model families (out of scope, SURVEY.md
+§2 row 2) and raise NotImplementedError.
+"""
+from enum import Enum
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from ..config import Ingredient
+from ..utils.graph import is_square_matrix, to_undirected
+
+
+class SPARSIFICATION(Enum):
+    NONE = 1
+    KNN = 2
+    EPS = 3
+
+
+class PhiloxState:
+    """Seed + step counter of the device RNG. The seed is drawn from torch's global generator on first use,
+    so `torch.manual_seed` (what sacred's seeding does) makes runs reproducible."""
+
+    def __init__(self):
+        self.seed = None
+        self.step = 0
+
+    def manual_seed(self, seed: int):
+        self.seed = int(seed) & ((1 << 64) - 1)
+        self.step = 0
+
+    def next_step(self):
+        if self.seed is None:
+            self.seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        step = self.step
+        self.step += 1
+        return self.seed, step
+
+
+PHILOX = PhiloxState()
+
+
+class SampleHandle:
+    """By-products of K1 for one sampled graph."""
+
+    def __init__(self, n, adj, deg, rsqrt, seed, step):
+        self.n, self.adj, self.deg, self.rsqrt, self.seed, self.step = n, adj, deg, rsqrt, seed, step
+
+
+_LAST_HANDLE = {}
+
+
+class _SampleSTE(torch.autograd.Function):
+    """value = Bernoulli sample (upper-triangle draw mirrored); d value / d edge_probs = identity for EVERY entry —
+    the reference applies the estimator to the matrix it was handed (src/models/sampling.py:77-78, 82-85)."""
+
+    @staticmethod
+    def forward(ctx, edge_probs, kernel_input, seed, step, explicit_uniforms):
+        from .. import kernels
+        n = kernel_input.shape[0]
+        ld = kernels.padded_ld(n)
+        src = kernel_input.detach()
+        if not (src.stride(1) == 1 and src.stride(0) == ld and src.data_ptr() % 16 == 0):
+            padded = torch.zeros((n, ld), dtype=torch.float32, device=src.device)
+            padded[:, :n] = src
+            src = padded
+        adj, sample, deg, rs = kernels.k1_sample_normalize(src, n, seed, step, u=explicit_uniforms, want_sample=True)
+        _LAST_HANDLE["handle"] = SampleHandle(n, adj, deg, rs, seed, step)     # picked up by sample_graph
+        return sample
+
+    @staticmethod
+    def backward(ctx, grad):
+        return grad, None, None, None, None
+
+
+def straight_through_estimator(sample: Tensor, parameters: Tensor) -> Tensor:
+    """(sample - parameters).detach() + parameters (src/models/sampling.py:82-85)."""
+    assert sample.size() == parameters.size()
+    return (sample - parameters).detach() + parameters
+
+
+def sample_graph(edge_probs: Tensor,
+                 undirected: bool,
+                 embeddings: Optional[Tensor] = None,
+                 dense: bool = False,
+                 k: Optional[int] = None,
+                 sparsification: SPARSIFICATION = SPARSIFICATION.NONE,
+                 force_straight_through_estimator: bool = False,
+                 eps: Optional[float] = None,
+                 knn_metric: str = "cosine",
+                 uniforms: Optional[Tensor] = None) -> Tensor:
+    """Same signature as the reference plus `uniforms` (explicit draws, parity tests)."""
+    assert is_square_matrix(edge_probs)
+    assert embeddings is None or edge_probs.size(0) == embeddings.size(0)
+    if dense or sparsification != SPARSIFICATION.NONE or not undirected:
+        raise NotImplementedError(
+            "lds_gnn_b200 implements the LDS sampling path (undirected=True, sparsification NONE, dense=False); "
+            "KNN/EPS sparsification, dense=True and directed sampling belong to the GAE/GRCN variants")
+    if not edge_probs.is_cuda:
+        raise RuntimeError("sample_graph runs on the B200 CUDA path only (edge_probs must be a CUDA tensor); there is no CPU fallback")
+    kernel_input = edge_probs.detach()
+    if not getattr(edge_probs, "_lds_symmetric", False):
+        kernel_input = to_undirected(kernel_input, from_triu_only=True)   # only the upper triangle defines the draw
+    seed, step = PHILOX.next_step()
+    graph = _SampleSTE.apply(edge_probs, kernel_input, seed, step, uniforms)
+    graph._lds_handle = _LAST_HANDLE.pop("handle")
+    return graph
+
+
+class Sampler:
+    _ingredient = Ingredient("sampler")
+    INGREDIENTS = {"sampler": _ingredient}
+
+    @staticmethod
+    @_ingredient.config
+    def config():
+        undirected: bool = True          # noqa: F841
+        k: int = 20                      # noqa: F841
+        eps: float = 0.9                 # noqa: F841
+        sparsification: str = "NONE"     # noqa: F841
+        dense: bool = False              # noqa: F841
+        knn_metric: str = "cosine"       # noqa: F841
+
+    @staticmethod
+    @_ingredient.capture
+    def sample(edge_probs: Tensor,
+               undirected: bool,
+               sparsification: str,
+               k: int,
+               eps: float,
+               embeddings: Tensor = None,
+               dense: bool = False,
+               knn_metric: str = "cosine") -> Tensor:
+        """Square matrix of Bernoulli parameters -> sampled adjacency with a straight-through gradient
+        (src/models/sampling.py:104-138)."""
+        assert sparsification in SPARSIFICATION.__members__
+        return sample_graph(edge_probs=edge_probs, embeddings=embeddings, undirected=undirected,
+                            sparsification=SPARSIFICATION[sparsification], dense=dense, k=k, eps=eps,
+                            knn_metric=knn_metric)

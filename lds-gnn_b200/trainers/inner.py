@@ -1,0 +1,88 @@
+"""Inner (GCN weights) trainer with the reference's API (src/trainers/inner.py:15-125).
+
+On the outer-step hot path only `model_forward` matters: it is the `gcn_predict_fct` the outer trainer
+receives, and the fused outer step recognises it to read the fast weights. `train_step` — the unrolled
+inner step the hypergradient later flows back through — is the "next" row of the scope table
+(SURVEY.md §8f #2): it is functional here, with sampling on the K1 kernel and the GCN forward written
+in differentiable torch ops (O(N^2) elementwise normalisation, no N^3 products) because that forward must
+support double backward; its optimiser is `diffopt.DifferentiableAdam` (numeric parity with `higher` unpinned).
+"""
+from collections import OrderedDict
+from typing import Dict, List
+
+import torch
+import torch.nn.functional as F
+from torch.optim import Adam
+
+from ..models.gcn import MetaDenseGCN, double_backward_path
+from ..utils.evaluation import accuracy
+from ..utils.graph import DenseData, is_square_matrix
+from . import Metrics
+from .diffopt import DifferentiableAdam
+
+
+def copy_detach_parameter_dict(parameters: OrderedDict) -> OrderedDict:
+    return OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in parameters.items())
+
+
+class InnerProblemTrainer:
+    def __init__(self, model: MetaDenseGCN, data: DenseData, lr: float = 0.01, weight_decay: float = 1e-4):
+        self.model = model
+        self.lr = lr
+        self.weight_decay = weight_decay
+        self.model_params: OrderedDict = OrderedDict(model.named_parameters())
+        self.optimizer: DifferentiableAdam = None
+        self.data = data
+        self.reset_optimizer()
+
+    def reset_weights(self):
+        self.model.reset_weights()
+        self.model_params = OrderedDict(self.model.named_parameters())
+
+    def reset_optimizer(self) -> None:
+        """Adam with weight decay on the first layer only (inner.py:42-50)."""
+        optimizer = Adam([{"params": self.model.layer_in.parameters(), "weight_decay": self.weight_decay},
+                          {"params": self.model.layer_out.parameters()}], lr=self.lr)
+        self.optimizer = DifferentiableAdam(optimizer, self.model.parameters())
+
+    def copy_model_params(self) -> Dict:
+        return copy_detach_parameter_dict(self.model_params)
+
+    def train_step(self, graph: torch.Tensor, mask: torch.Tensor = None) -> Metrics:
+        """One differentiable optimiser step on the training nodes (inner.py:55-74)."""
+        assert is_square_matrix(graph)
+        with double_backward_path():
+            predictions = self.model_forward(graph, is_train=True)
+        mask = mask or self.data.train_mask
+        loss = F.nll_loss(predictions[mask], self.data.y[mask])
+        acc = accuracy(predictions[mask], self.data.y[mask])
+        new_params = self.optimizer.step(loss, params=self.model_params.values())
+        self._update_model_params(list(new_params))
+        return Metrics(loss=loss.item(), acc=acc)
+
+    def model_forward(self, graph, is_train: bool = True) -> torch.Tensor:
+        """The `gcn_predict_fct` of the outer step (inner.py:76-78): sets train/eval mode, runs the GCN at the
+        current fast weights."""
+        self.model.train(mode=is_train)
+        return self.model(self.data.x, graph, params=self.model_params)
+
+    def evaluate(self, graph: torch.Tensor, mask: torch.Tensor = None) -> Metrics:
+        self.model.eval()
+        with torch.no_grad():
+            predictions = self.model_forward(graph, is_train=False)
+            mask = mask or self.data.val_mask
+            loss = F.nll_loss(predictions[mask], self.data.y[mask])
+            acc = accuracy(predictions[mask], self.data.y[mask])
+        return Metrics(loss=loss.item(), acc=acc)
+
+    def detach(self) -> None:
+        """Truncate the unroll: fast weights and optimiser state become leaves again (inner.py:98-125)."""
+        self.model_params = copy_detach_parameter_dict(self.model_params)
+        self.detach_optimizer()
+
+    def _update_model_params(self, new_model_params: List[torch.Tensor]) -> None:
+        for name, value in zip(list(self.model_params.keys()), new_model_params):
+            self.model_params[name] = value
+
+    def detach_optimizer(self):
+        self.optimizer.detach_()

@@ -1,0 +1,335 @@
+"""-m gpu tests of the reference-facing Python API (the drop-in boundary).
+
+They read like the reference's own tests for the path (tst/models/test_bernoulli_model.py,
+tst/models/test_sampling.py, tst/utils/test_graph.py, tst/models/test_gcn.py,
+tst/trainers/test_outer_trainer.py) re-pointed at `lds_gnn_b200` on a CUDA device, plus parity of the
+two `train_step` routes with each other and with the live-reference golden vectors.
+"""
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+CUDA = "cuda"
+
+
+@pytest.fixture(autouse=True)
+def _fresh_config():
+    from lds_gnn_b200.models.sampling import PHILOX, Sampler
+    saved = dict(Sampler._ingredient.values)
+    PHILOX.manual_seed(1234)
+    yield
+    Sampler._ingredient.values.update(saved)
+
+
+def t(a, dtype=None):
+    x = torch.as_tensor(np.ascontiguousarray(a))
+    return (x if dtype is None else x.to(dtype)).to(CUDA)
+
+
+# ------------------------------------------------------------------ BernoulliGraphModel (test_bernoulli_model.py)
+@pytest.mark.parametrize("directed", [True, False])
+def test_bernoulli_model_returns_square_matrix(directed):
+    from lds_gnn_b200.models.graph import BernoulliGraphModel
+    from lds_gnn_b200.utils.graph import is_square_matrix
+    model = BernoulliGraphModel(init_matrix=torch.eye(10, device=CUDA), directed=directed)
+    assert is_square_matrix(model.forward())
+
+
+def test_undirected_bernoulli_model_returns_symmetric_matrix():          # test_bernoulli_model.py:56-64
+    from lds_gnn_b200.models.graph import BernoulliGraphModel
+    from lds_gnn_b200.utils.graph import to_undirected
+    adj = torch.eye(10, device=CUDA)
+    adj[1, :] = 1.0
+    adj = to_undirected(adj)
+    model = BernoulliGraphModel(init_matrix=adj, directed=False)
+    assert torch.equal(model.forward(), torch.clamp(adj + adj.t(), 0.0, 1.0))
+    assert list(model.state_dict().keys()) == ["probs"] and model.probs.shape == (55,)
+
+
+def test_directed_bernoulli_model_returns_asymmetric_matrix():           # test_bernoulli_model.py:113-120
+    from lds_gnn_b200.models.graph import BernoulliGraphModel
+    adj = torch.eye(10, device=CUDA)
+    adj[1, :] = 1.0
+    assert torch.equal(BernoulliGraphModel(init_matrix=adj, directed=True).forward(), adj)
+
+
+@pytest.mark.parametrize("directed", [True, False])
+def test_bernoulli_model_gradients_flow_through_forward(directed):      # test_bernoulli_model.py:67-88
+    from lds_gnn_b200.models.graph import BernoulliGraphModel
+    adj = torch.eye(10, device=CUDA)
+    adj[1, :] = 1.0
+    model = BernoulliGraphModel(init_matrix=adj, directed=directed)
+    assert model.probs.grad is None
+    model.forward().sum().backward()
+    assert model.probs.grad is not None and (model.probs.grad > 0).all()
+
+
+def test_parameters_are_projected_correctly():                           # test_bernoulli_model.py:123-128
+    from lds_gnn_b200.models.graph import BernoulliGraphModel
+    model = BernoulliGraphModel(init_matrix=torch.eye(10, device=CUDA) * 2, directed=False)
+    assert (model.probs > 1.0).any()
+    model.project_parameters()
+    assert not (model.probs > 1.0).any()
+    assert not (model.forward() > 1.0).any()
+
+
+def test_statistics_keys_and_values():
+    from lds_gnn_b200.models.graph import BernoulliGraphModel
+    adj = (torch.rand(30, 30, device=CUDA) < 0.2).float()
+    adj = torch.max(adj, adj.t())
+    s = BernoulliGraphModel(adj).statistics()
+    assert set(s) == {"expected_num_edges", "percentage_edges_expected", "mean_prob", "min_prob", "max_prob"}
+    assert abs(s["expected_num_edges"] - adj.sum().item()) < 1e-6
+    assert abs(s["percentage_edges_expected"] - adj.sum().item() / 900) < 1e-9
+    assert s["min_prob"] == 0.0 and s["max_prob"] == 1.0
+
+
+# ------------------------------------------------------------------ sampling (test_sampling.py)
+def test_undirected_sample_known_answer_and_dense_ste_gradient():        # test_sampling.py:156-160, 89-116
+    from lds_gnn_b200.models.sampling import SPARSIFICATION, sample_graph
+    probs = torch.ones(10, 10, device=CUDA).triu(1).requires_grad_(True)
+    sample = sample_graph(probs, undirected=True, sparsification=SPARSIFICATION.NONE)
+    assert torch.equal(sample, torch.ones(10, 10, device=CUDA) - torch.eye(10, device=CUDA))
+    sample.sum().backward()
+    assert probs.grad is not None and sample.grad is None                # test_sampling.py:247-253
+    assert (probs.grad != 0).sum().item() == 100                          # straight-through: dense gradient
+
+
+def test_sampler_uses_ingredient_defaults_and_rejects_out_of_scope_modes():
+    from lds_gnn_b200.models.sampling import Sampler
+    probs = torch.rand(16, 16, device=CUDA)
+    g = Sampler.sample(probs)
+    assert g.shape == (16, 16) and torch.equal(g, g.t()) and set(g.unique().tolist()) <= {0.0, 1.0}
+    assert hasattr(g, "_lds_handle") and g._lds_handle.adj.dtype == torch.bfloat16
+    with pytest.raises(NotImplementedError):
+        Sampler.sample(probs, sparsification="KNN")
+    with pytest.raises(NotImplementedError):
+        Sampler.sample(probs, dense=True)
+
+
+def test_sampling_is_reproducible_under_manual_seed():
+    from lds_gnn_b200.models.sampling import PHILOX, Sampler
+    probs = torch.rand(64, 64, device=CUDA)
+    torch.manual_seed(7); PHILOX.seed = None; PHILOX.step = 0
+    a = [Sampler.sample(probs).clone() for _ in range(2)]
+    torch.manual_seed(7); PHILOX.seed = None; PHILOX.step = 0
+    b = [Sampler.sample(probs).clone() for _ in range(2)]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and not torch.equal(a[0], a[1])
+
+
+# ------------------------------------------------------------------ graph utils (test_graph.py, test_gradients.py)
+def test_triu_values_to_symmetric_matrix_known_answer_and_gradient():    # test_graph.py:213-229
+    from lds_gnn_b200.utils.graph import triu_values_to_symmetric_matrix
+    triu = torch.tensor([1.0, 2.0, 3.0, 4.0, 5.0, 6.0], device=CUDA, requires_grad=True) / 10
+    triu.retain_grad()
+    out = triu_values_to_symmetric_matrix(triu)
+    expected = torch.tensor([[1, 2, 3], [2, 4, 5], [3, 5, 6]], device=CUDA) / 10.0
+    assert torch.equal(out, expected)
+    out.sum().backward()
+    assert torch.equal(triu.grad, torch.tensor([1.0, 2, 2, 1, 2, 1], device=CUDA))
+
+
+def test_add_self_loops_gives_zero_gradient_on_the_diagonal():           # test_graph.py:169-178
+    from lds_gnn_b200.utils.graph import add_self_loops
+    adj = torch.rand(5, 5, device=CUDA, requires_grad=True)
+    add_self_loops(adj).sum().backward()
+    assert (adj.grad.diag() == 0).all() and (adj.grad - torch.diag(adj.grad.diag()) != 0).sum() == 20
+
+
+def test_normalize_adjacency_matrix_dense_matches_gcn_formula():
+    from lds_gnn_b200.utils.graph import normalize_adjacency_matrix
+    a = (torch.rand(40, 40, device=CUDA) < 0.2).float()
+    a = torch.max(a, a.t())
+    at = a.clone(); at.fill_diagonal_(1.0)
+    d = torch.diag(1.0 / at.sum(1).sqrt())
+    assert torch.allclose(normalize_adjacency_matrix(a), d @ at @ d, atol=1e-6)      # reference formula (graph.py:148-152)
+
+
+# ------------------------------------------------------------------ GCN (test_gcn.py, test_layers.py)
+def _gcn(f=12, h=8, c=3, dropout=0.0):
+    from lds_gnn_b200.models.gcn import MetaDenseGCN
+    torch.manual_seed(0)
+    return MetaDenseGCN(f, h, c, dropout=dropout).to(CUDA)
+
+
+def test_gcn_factored_path_matches_dense_path_forward_and_backward():
+    from lds_gnn_b200.models.sampling import Sampler
+    from lds_gnn_b200.utils.graph import normalize_adjacency_matrix
+    gcn = _gcn()
+    x = torch.rand(50, 12, device=CUDA)
+    probs = torch.rand(50, 50, device=CUDA)
+    probs = torch.max(probs, probs.t()).requires_grad_(True)
+    graph = Sampler.sample(probs)
+    out_fast = gcn(x, graph)
+    (out_fast[:, 0].sum() + (out_fast ** 2).sum()).backward()
+    g_fast, w_fast = probs.grad.clone(), gcn.layer_in.fc.weight.grad.clone()
+    probs.grad = None; gcn.zero_grad()
+    dense = graph.detach().clone().requires_grad_(True)                                # no handle: generic dense path
+    a_hat = normalize_adjacency_matrix(dense)
+    hid = F.relu(torch.mm(a_hat, F.linear(x, gcn.layer_in.fc.weight, gcn.layer_in.fc.bias)))
+    out_ref = F.log_softmax(torch.mm(a_hat, F.linear(hid, gcn.layer_out.fc.weight, gcn.layer_out.fc.bias)), dim=1)
+    (out_ref[:, 0].sum() + (out_ref ** 2).sum()).backward()
+    assert torch.allclose(out_fast, out_ref, rtol=1e-4, atol=1e-5)
+    assert (g_fast - dense.grad).abs().max() <= 1e-3 * dense.grad.abs().max()
+    assert (w_fast - gcn.layer_in.fc.weight.grad).abs().max() <= 1e-3 * w_fast.abs().max()
+
+
+def test_gcn_params_override_routes_gradients():                         # test_gcn.py:75-109
+    from lds_gnn_b200.models.sampling import Sampler
+    gcn = _gcn()
+    x = torch.rand(30, 12, device=CUDA)
+    graph = Sampler.sample(torch.rand(30, 30, device=CUDA))
+    override = OrderedDict((k, (v.detach() * 2).requires_grad_(True)) for k, v in gcn.named_parameters())
+    assert list(override) == ["layer_in.fc.weight", "layer_in.fc.bias", "layer_out.fc.weight", "layer_out.fc.bias"]
+    out_own, out_over = gcn(x, graph), gcn(x, graph, params=override)
+    assert not torch.allclose(out_own, out_over)
+    out_over.sum().backward()
+    assert all(p.grad is None for p in gcn.parameters()) and all(p.grad is not None for p in override.values())
+
+
+def test_normalize_adj_flag_calls_or_skips_normalisation(monkeypatch):   # test_gcn.py:51-72
+    import lds_gnn_b200.models.gcn as gcn_mod
+    calls = []
+    real = gcn_mod.normalize_adjacency_matrix
+    monkeypatch.setattr(gcn_mod, "normalize_adjacency_matrix", lambda *a, **k: calls.append(1) or real(*a, **k))
+    x, adj = torch.rand(10, 12, device=CUDA), torch.eye(10, device=CUDA)
+    gcn_mod.MetaDenseGCN(12, 4, 3, 0.0, normalize_adj=True).to(CUDA)(x, adj)
+    assert len(calls) == 1
+    gcn_mod.MetaDenseGCN(12, 4, 3, 0.0, normalize_adj=False).to(CUDA)(x, adj)
+    assert len(calls) == 1
+
+
+# ------------------------------------------------------------------ outer trainer (test_outer_trainer.py + parity)
+def _setup(g, lr, lr_decay, dropout=0.0, optimizer="SGD", **opt_kwargs):
+    from lds_gnn_b200.models.gcn import MetaDenseGCN
+    from lds_gnn_b200.models.graph import BernoulliGraphModel
+    from lds_gnn_b200.trainers.inner import InnerProblemTrainer
+    from lds_gnn_b200.trainers.outer import OuterProblemTrainer
+    from lds_gnn_b200.utils.graph import DenseData
+    n = int(g["n"])
+    full = np.zeros((n, n), np.float32)
+    full[np.triu_indices(n)] = g["theta_triu"]
+    full = np.triu(full, 1) + np.triu(full, 1).T + np.diag(np.diag(full))
+    data = DenseData(x=t(g["x"]), y=t(g["y"]), train_mask=t(g["mask"]), val_mask=t(g["mask"]), test_mask=t(g["mask"]),
+                     dense_adj=t(full), num_classes=int(g["c"]))
+    gcn = MetaDenseGCN(int(g["f"]), int(g["h"]), int(g["c"]), dropout=dropout).to(CUDA)
+    with torch.no_grad():
+        gcn.layer_in.fc.weight.copy_(t(g["w0"])); gcn.layer_in.fc.bias.copy_(t(g["b0"]))
+        gcn.layer_out.fc.weight.copy_(t(g["w1"])); gcn.layer_out.fc.bias.copy_(t(g["b1"]))
+    inner = InnerProblemTrainer(gcn, data)
+    model = BernoulliGraphModel(data.dense_adj).to(CUDA)
+    opt = (torch.optim.SGD if optimizer == "SGD" else torch.optim.Adam)(model.parameters(), lr=lr, **opt_kwargs)
+    outer = OuterProblemTrainer(optimizer=opt, data=data, opt_mask=t(g["mask"]), model=model, smoothness_factor=0.0,
+                                disconnection_factor=0.0, sparsity_factor=0.0, regularize=False, lr_decay=lr_decay, pretrain=False)
+    return data, gcn, inner, model, outer
+
+
+def test_train_step_fused_route_matches_live_reference_golden():
+    """theta in {0,1} makes the sample deterministic (factory.py:62), so the API result must
+    equal the reference's own train_step output stored in tests/golden/n96_binary.npz."""
+    g = load_golden("n96_binary")
+    data, gcn, inner, model, outer = _setup(g, lr=float(g["lr"]), lr_decay=float(g["lr_decay"]))
+    m = outer.train_step(inner.model_forward)
+    assert outer.last_route == "fused"
+    assert abs(m.loss - float(g["loss0_f64"])) < 1e-4 and abs(m.acc - float(g["acc0_f64"])) < 1e-6
+    ref_new, ref_g = g["theta_new0_f64"], g["grad_triu0_f64"]
+    assert np.abs(model.probs.detach().cpu().numpy() - ref_new).max() <= 1e-3 * float(g["lr"]) * np.abs(ref_g).max() + 2e-7
+    assert outer.get_learning_rates() == [float(g["lr"]) * float(g["lr_decay"])]
+
+
+def test_train_step_composable_route_matches_live_reference_golden():
+    g = load_golden("n96_binary")
+    data, gcn, inner, model, outer = _setup(g, lr=float(g["lr"]), lr_decay=float(g["lr_decay"]))
+    outer.fused_enabled = False
+    m = outer.train_step(inner.model_forward, retain_graph=False)
+    assert outer.last_route == "composable"
+    assert abs(m.loss - float(g["loss0_f64"])) < 1e-4 and abs(m.acc - float(g["acc0_f64"])) < 1e-6
+    ref_g = g["grad_triu0_f64"]
+    got = model.probs.grad.cpu().numpy()
+    assert np.abs(got - ref_g).max() <= 1e-3 * np.abs(ref_g).max()
+    assert np.abs(model.probs.detach().cpu().numpy() - g["theta_new0_f64"]).max() <= 1e-3 * float(g["lr"]) * np.abs(ref_g).max() + 2e-7
+
+
+@pytest.mark.parametrize("name,optimizer", [("n33_twostep", "SGD"), ("n257_h64", "SGD"), ("n130_sparse", "Adam")])
+def test_fused_and_composable_routes_agree_over_several_steps(name, optimizer):
+    from lds_gnn_b200.models.sampling import PHILOX
+    g = load_golden(name)
+    results = {}
+    for route in ("fused", "composable"):
+        # Adam's update lr * m / (sqrt(v) + eps) is sign-like where |g| ~ eps: a larger eps keeps the comparison of
+        # two numerically different (but equally valid) gradient evaluations well conditioned
+        kw = dict(eps=1e-3) if optimizer == "Adam" else {}
+        data, gcn, inner, model, outer = _setup(g, lr=0.05 if optimizer == "Adam" else 0.5, lr_decay=0.9, optimizer=optimizer, **kw)
+        outer.fused_enabled = route == "fused"
+        PHILOX.manual_seed(99)
+        metrics = [outer.train_step(inner.model_forward, retain_graph=False) for _ in range(3)]
+        assert outer.last_route == route
+        results[route] = (metrics, model.probs.detach().clone(), outer.get_learning_rates())
+    mf, pf, lf = results["fused"]
+    mc, pc, lc = results["composable"]
+    assert lf == lc
+    for a, b in zip(mf, mc):
+        assert abs(a.loss - b.loss) < 1e-4 and abs(a.acc - b.acc) < 1e-6
+    assert (pf - pc).abs().max().item() < 2e-5
+
+
+def test_train_step_contract():                                          # test_outer_trainer.py:92-171
+    g = load_golden("n64_dropout")
+    data, gcn, inner, model, outer = _setup(g, lr=0.1, lr_decay=0.99, dropout=0.5)
+    before = model.probs.detach().clone()
+    m = outer.train_step(inner.model_forward)
+    assert isinstance(m.loss, float) and isinstance(m.acc, float) and outer.last_route == "fused"
+    after = model.probs.detach()
+    assert not torch.equal(before, after)                                 # parameters updated
+    assert after.min() >= 0 and after.max() <= 1                          # projected
+    assert gcn.training and model.training
+    outer.detach()
+    # a custom predict function cannot be fused: same API, composable route
+    m2 = outer.train_step(lambda graph: gcn(data.x, graph))
+    assert outer.last_route == "composable" and np.isfinite(m2.loss)
+    # fast weights with unrolled history keep the exact (autograd) route unless first_order is requested
+    graph = outer.sample()
+    inner.train_step(graph)
+    assert any(p.grad_fn is not None for p in inner.model_params.values())
+    outer.train_step(inner.model_forward)
+    assert outer.last_route == "composable"
+    inner.detach()
+    outer.train_step(inner.model_forward)
+    assert outer.last_route == "fused"
+
+
+def test_hypergradient_reaches_first_graph_through_unrolled_inner_steps():   # test_inner_trainer.py:44-70
+    g = load_golden("n33_twostep")
+    data, gcn, inner, model, outer = _setup(g, lr=0.5, lr_decay=None)
+    first = outer.sample()
+    first.retain_grad()
+    inner.train_step(first)
+    for _ in range(2):
+        inner.train_step(outer.sample())
+    pred = inner.model_forward(outer.sample())
+    F.nll_loss(pred[data.val_mask], data.y[data.val_mask]).backward()
+    assert first.grad is not None and first.grad.abs().sum() > 0
+    inner.detach()                                                        # truncation cuts the path to earlier graphs
+    first.grad = None
+    pred = inner.model_forward(outer.sample())
+    F.nll_loss(pred[data.val_mask], data.y[data.val_mask]).backward()
+    assert first.grad is None
+
+
+def test_empirical_mean_loss_and_bilevel_runner_smoke():
+    from lds_gnn_b200.trainers.bilevel import BilevelProblemRunner
+    from lds_gnn_b200.utils.evaluation import empirical_mean_loss
+    g = load_golden("n130_sparse")
+    data, gcn, inner, model, outer = _setup(g, lr=0.1, lr_decay=0.99, dropout=0.5)
+    val, test = empirical_mean_loss(gcn, model, n_samples=4, data=data, model_parameters=inner.model_params)
+    assert np.isfinite(val.loss) and 0 <= val.acc <= 1 and np.isfinite(test.loss)
+    runner = BilevelProblemRunner(inner, outer, data, n_samples_empirical_mean=2)
+    runner.train(patience=1, hyper_gradient_interval=2, inner_loop_max_epochs=3, outer_loop_max_epochs=1)
+    out = runner.evaluate()
+    assert set(out) == {"loss.val.final", "acc.val.final", "loss.test.final", "acc.test.final"}
