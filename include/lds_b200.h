@@ -122,8 +122,12 @@ typedef struct lds_outer_step_args {
   int32_t  n, f, h, c;        /* nodes, features, hidden, classes                                       */
   float*   theta_full;        /* [n][ld_theta] fp32, updated in place                                   */
   int64_t  ld_theta;
-  const float*   x;           /* [n][ld_x] fp32, ld_x % 4 == 0                                          */
+  const float*   x;           /* [n][ld_x] fp32, ld_x % 4 == 0 (dense features; may be NULL if x_crow given) */
   int64_t  ld_x;
+  const int32_t* x_crow;      /* optional CSR copy of x: [n+1] row offsets, [nnz] columns, [nnz] values.      */
+  const int32_t* x_col;       /* Bag-of-words features are ~1% dense; with CSR the feature GEMM gathers rows  */
+  const float*   x_val;       /* of w0t instead of streaming N x F zeros. Same result for any x.              */
+  const float*   w0t;         /* [f][h] contiguous = w0 transposed; required when x_crow is given             */
   const float*   w0;          /* [h][ld_w0] fp32 (layer_in.fc.weight), ld_w0 % 4 == 0                   */
   int64_t  ld_w0;
   const float*   b0;          /* [h]                                                                    */

@@ -27,15 +27,25 @@ static inline int64_t k2_operand_ld(int n) { return round_up(n, K2_BLOCK_K); }
 static inline int64_t k2_operand_bytes(int n, int hp) { return (int64_t)hp * k2_operand_ld(n) * 2; }            // one bf16 term
 static inline int64_t k2_partial_bytes(const K2Sched& s) { return (int64_t)s.grid * s.max_seg * K2_BLOCK_M * s.hp * 4; }
 
-// Sum of the partial tiles covering (row, col): fixed CTA order.
+// Sum of the partial tiles covering (row, col) in a fixed CTA order (deterministic). Loads are issued four at a
+// time before any is consumed: the consumers are latency-bound row epilogues.
 __device__ __forceinline__ float k2_sum_partials(const float* __restrict__ partial, const K2Sched& s, int row, int col) {
   const int p = row >> 7, rin = row & 127;
   const int c_first = (p * s.kblocks) / s.per_cta;
   const int c_last = ((p + 1) * s.kblocks - 1) / s.per_cta;
+  const int64_t tile = (int64_t)K2_BLOCK_M * s.hp;
+  const float* base = partial + (int64_t)rin * s.hp + col;
   float acc = 0.f;
-  for (int c = c_first; c <= c_last; ++c) {
-    const int seg = p - (c * s.per_cta) / s.kblocks;
-    acc += partial[((int64_t)(c * s.max_seg + seg) * K2_BLOCK_M + rin) * s.hp + col];
+  for (int c = c_first; c <= c_last; c += 4) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int cc = c + u;
+      const int seg = p - (cc * s.per_cta) / s.kblocks;
+      v[u] = (cc <= c_last) ? base[(int64_t)(cc * s.max_seg + seg) * tile] : 0.f;
+    }
+    acc = ((acc + v[0]) + v[1]) + v[2];
+    acc += v[3];
   }
   return acc;
 }

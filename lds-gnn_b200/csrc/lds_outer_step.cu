@@ -21,7 +21,8 @@
 namespace lds {
 
 constexpr int EPI_ROWS = 32;        // rows per CTA in the row epilogues
-constexpr int EPI_THREADS = 256;    // 8 warps x 4 rows
+constexpr int EPI_THREADS = 1024;   // 32 warps, one row each: the epilogues are latency-bound, so maximise rows in flight
+constexpr int FEAT_THREADS = 256;   // dense feature GEMM: 8 warps x 4 rows
 constexpr int EPI_MAXW = 128;       // widest operand
 
 struct OuterLayout {
@@ -77,7 +78,7 @@ __device__ __forceinline__ void store_operand_tile(const float (*tile)[EPI_ROWS 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = i0 + lane;
   if (i >= (int)ldb) return;
-  for (int c = warp; c < hp; c += EPI_THREADS / 32) {
+  for (int c = warp; c < hp; c += (int)(blockDim.x >> 5)) {
     __nv_bfloat16 hi, lo;
     split_bf16(tile[c][lane], hi, lo);
     bt_hi[(int64_t)c * ldb + i] = hi;
@@ -88,7 +89,7 @@ __device__ __forceinline__ void store_operand_tile(const float (*tile)[EPI_ROWS 
 // ------------------------------------------------------------------------------------------------
 // P1 = dropout(X) W0^T + b0, operand (r*P1)^T.  One warp = 4 rows; lanes stride over feature quads.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(EPI_THREADS)
+__global__ void __launch_bounds__(FEAT_THREADS)
 feat_linear_kernel(const float* __restrict__ x, int64_t ldx, int n, int f, const float* __restrict__ w0, int64_t ldw, const float* __restrict__ b0, int h,
                    DropCfg dc, const float* __restrict__ rs, float* __restrict__ p1,
                    __nv_bfloat16* __restrict__ bt_hi, __nv_bfloat16* __restrict__ bt_lo, int64_t ldb, int hp) {
@@ -97,7 +98,7 @@ feat_linear_kernel(const float* __restrict__ x, int64_t ldx, int n, int f, const
   const int i0 = blockIdx.x * EPI_ROWS;
   const int f4 = (f + 3) >> 2;
   const int iters = (f4 + 31) >> 5;
-  for (int idx = threadIdx.x; idx < EPI_MAXW * (EPI_ROWS + 1); idx += EPI_THREADS) (&tile[0][0])[idx] = 0.f;
+  for (int idx = threadIdx.x; idx < EPI_MAXW * (EPI_ROWS + 1); idx += FEAT_THREADS) (&tile[0][0])[idx] = 0.f;
   __syncthreads();
 
   for (int oc = 0; oc < h; oc += 16) {
@@ -165,7 +166,57 @@ feat_linear_kernel(const float* __restrict__ x, int64_t ldx, int n, int f, const
     const int rr = threadIdx.x & 31;                         // scale column rr of the tile by r_i
     const int i = i0 + rr;
     const float ri = (i < n) ? rs[i] : 0.f;
-    for (int c = threadIdx.x >> 5; c < hp; c += EPI_THREADS / 32) tile[c][rr] *= ri;
+    for (int c = threadIdx.x >> 5; c < hp; c += FEAT_THREADS / 32) tile[c][rr] *= ri;
+  }
+  __syncthreads();
+  store_operand_tile(tile, hp, i0, ldb, bt_hi, bt_lo);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sparse variant of the feature GEMM: x given as CSR (bag-of-words features are ~1% dense). One warp per row:
+// lanes load up to 32 non-zeros (+ their dropout draw, keyed on (row, col) exactly like the dense kernel), then
+// every non-zero is broadcast and the lanes FMA one contiguous row of w0t = W0^T each. Same result as the dense
+// kernel up to fp32 summation order.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EPI_THREADS)
+feat_sparse_kernel(const int32_t* __restrict__ crow, const int32_t* __restrict__ xcol, const float* __restrict__ xval, int n, int f,
+                   const float* __restrict__ w0t, const float* __restrict__ b0, int h,
+                   DropCfg dc, const float* __restrict__ rs, float* __restrict__ p1,
+                   __nv_bfloat16* __restrict__ bt_hi, __nv_bfloat16* __restrict__ bt_lo, int64_t ldb, int hp) {
+  __shared__ float tile[EPI_MAXW][EPI_ROWS + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i0 = blockIdx.x * EPI_ROWS;
+  for (int idx = threadIdx.x; idx < EPI_MAXW * (EPI_ROWS + 1); idx += EPI_THREADS) (&tile[0][0])[idx] = 0.f;
+  __syncthreads();
+  for (int rr = warp; rr < EPI_ROWS; rr += EPI_THREADS / 32) {
+    const int i = i0 + rr;
+    if (i >= n) continue;
+    const int beg = crow[i], end = crow[i + 1];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int base = beg; base < end; base += 32) {
+      const int idx = base + lane;
+      int col = 0; float v = 0.f;
+      if (idx < end) {
+        col = xcol[idx]; v = xval[idx];
+        if (dc.p > 0.f) v = drop_keep(dc, i, col, f) ? v * dc.scale : 0.f;
+      }
+      const int cnt = min(32, end - base);
+      for (int j = 0; j < cnt; ++j) {
+        const float vj = __shfl_sync(0xffffffffu, v, j);
+        const int cj = __shfl_sync(0xffffffffu, col, j);
+        if (vj != 0.f) {                                        // warp-uniform
+          const float* wrow = w0t + (int64_t)cj * h;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) { const int o = lane + 32 * t; if (o < h) acc[t] = fmaf(vj, wrow[o], acc[t]); }
+        }
+      }
+    }
+    const float ri = rs[i];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int o = lane + 32 * t;
+      if (o < h) { const float pv = acc[t] + b0[o]; p1[(int64_t)i * h + o] = pv; tile[o][rr] = ri * pv; }
+    }
   }
   __syncthreads();
   store_operand_tile(tile, hp, i0, ldb, bt_hi, bt_lo);
@@ -196,8 +247,8 @@ __global__ void __launch_bounds__(EPI_THREADS) epi_layer1_kernel(const EpiArgs a
   const int i0 = blockIdx.x * EPI_ROWS;
   for (int idx = threadIdx.x; idx < EPI_MAXW * (EPI_ROWS + 1); idx += EPI_THREADS) (&tile[0][0])[idx] = 0.f;
   __syncthreads();
-  for (int r = 0; r < 4; ++r) {
-    const int rr = 4 * warp + r, i = i0 + rr;
+  for (int rr = warp; rr < EPI_ROWS; rr += EPI_THREADS / 32) {    // one row per warp
+    const int i = i0 + rr;
     if (i >= a.n) continue;                                   // warp-uniform
     const float ri = a.rs[i];
     for (int c = lane; c < a.h; c += 32) {
@@ -228,8 +279,8 @@ __global__ void __launch_bounds__(EPI_THREADS) epi_layer2_kernel(const EpiArgs a
   for (int idx = threadIdx.x; idx < EPI_MAXW * (EPI_ROWS + 1); idx += EPI_THREADS) (&tile[0][0])[idx] = 0.f;
   __syncthreads();
   float loss_w = 0.f, corr_w = 0.f;
-  for (int r = 0; r < 4; ++r) {
-    const int rr = 4 * warp + r, i = i0 + rr;
+  for (int rr = warp; rr < EPI_ROWS; rr += EPI_THREADS / 32) {    // one row per warp
+    const int i = i0 + rr;
     if (i >= a.n) continue;
     const float ri = a.rs[i];
     float z[4];
@@ -293,8 +344,8 @@ __global__ void __launch_bounds__(EPI_THREADS) epi_bwd2_kernel(const EpiArgs a) 
   const int i0 = blockIdx.x * EPI_ROWS;
   for (int idx = threadIdx.x; idx < EPI_MAXW * (EPI_ROWS + 1); idx += EPI_THREADS) (&tile[0][0])[idx] = 0.f;
   __syncthreads();
-  for (int r = 0; r < 4; ++r) {
-    const int rr = 4 * warp + r, i = i0 + rr;
+  for (int rr = warp; rr < EPI_ROWS; rr += EPI_THREADS / 32) {    // one row per warp
+    const int i = i0 + rr;
     if (i >= a.n) continue;
     const float ri = a.rs[i];
     for (int o = lane; o < a.c; o += 32) {
@@ -321,8 +372,8 @@ __global__ void __launch_bounds__(EPI_THREADS) epi_bwd2_kernel(const EpiArgs a) 
 __global__ void __launch_bounds__(EPI_THREADS) epi_bwd1_kernel(const EpiArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * EPI_ROWS;
-  for (int r = 0; r < 4; ++r) {
-    const int i = i0 + 4 * warp + r;
+  for (int rr = warp; rr < EPI_ROWS; rr += EPI_THREADS / 32) {    // one row per warp
+    const int i = i0 + rr;
     if (i >= a.n) continue;
     const float ri = a.rs[i];
     float rho = 0.f, kappa = 0.f;
@@ -379,10 +430,16 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   const lds_outer_step_args& A = *args;
   OuterLayout L;
   if (!make_layout(A.n, A.f, A.h, A.c, L)) { set_error("lds_outer_step: unsupported shape n=%d f=%d h=%d c=%d (h, c must be in [1,128])", A.n, A.f, A.h, A.c); return LDS_ERR_UNSUPPORTED; }
-  LDS_CHECK_ARG(A.theta_full && A.x && A.w0 && A.b0 && A.w1 && A.b1 && A.y && A.mask && A.out_scalars, "lds_outer_step: null pointer");
+  LDS_CHECK_ARG(A.theta_full && A.b0 && A.w1 && A.b1 && A.y && A.mask && A.out_scalars, "lds_outer_step: null pointer");
   LDS_CHECK_ARG(A.ld_theta >= A.n && A.ld_theta % 4 == 0, "lds_outer_step: ld_theta must be >= n and a multiple of 4");
-  LDS_CHECK_ARG(A.ld_x >= A.f && A.ld_x % 4 == 0 && A.ld_w0 >= A.f && A.ld_w0 % 4 == 0, "lds_outer_step: ld_x / ld_w0 must be >= f and multiples of 4 (zero padded)");
-  LDS_CHECK_ARG((reinterpret_cast<uintptr_t>(A.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(A.w0) & 15) == 0, "lds_outer_step: x and w0 must be 16-byte aligned");
+  const bool sparse_x = A.x_crow != nullptr;
+  if (sparse_x) {
+    LDS_CHECK_ARG(A.x_col && A.x_val && A.w0t, "lds_outer_step: the CSR feature path needs x_col, x_val and w0t");
+  } else {
+    LDS_CHECK_ARG(A.x && A.w0, "lds_outer_step: null pointer (x / w0)");
+    LDS_CHECK_ARG(A.ld_x >= A.f && A.ld_x % 4 == 0 && A.ld_w0 >= A.f && A.ld_w0 % 4 == 0, "lds_outer_step: ld_x / ld_w0 must be >= f and multiples of 4 (zero padded)");
+    LDS_CHECK_ARG((reinterpret_cast<uintptr_t>(A.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(A.w0) & 15) == 0, "lds_outer_step: x and w0 must be 16-byte aligned");
+  }
   LDS_CHECK_ARG(A.mask_count > 0, "lds_outer_step: mask_count must be positive");
   LDS_CHECK_ARG(A.dropout_p >= 0.f && A.dropout_p < 1.f, "lds_outer_step: dropout_p must be in [0, 1)");
   if (!A.workspace || A.workspace_bytes < L.total) { set_error("lds_outer_step: workspace too small (%lld < %lld)", (long long)A.workspace_bytes, (long long)L.total); return LDS_ERR_WORKSPACE; }
@@ -412,8 +469,13 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   const bool use_lo = !(A.k2_flags & LDS_K2_SINGLE_BF16);
   const dim3 egrid((unsigned)L.nblk);
 
-  feat_linear_kernel<<<egrid, EPI_THREADS, 0, stream>>>(A.x, A.ld_x, A.n, A.f, A.w0, A.ld_w0, A.b0, A.h, dx, fbuf(B_RS), fbuf(B_P1), bt_hi, bt_lo, L.ldb, L.hp1);
-  LDS_CHECK_LAUNCH("feat_linear_kernel");
+  if (sparse_x) {
+    feat_sparse_kernel<<<egrid, EPI_THREADS, 0, stream>>>(A.x_crow, A.x_col, A.x_val, A.n, A.f, A.w0t, A.b0, A.h, dx, fbuf(B_RS), fbuf(B_P1), bt_hi, bt_lo, L.ldb, L.hp1);
+    LDS_CHECK_LAUNCH("feat_sparse_kernel");
+  } else {
+    feat_linear_kernel<<<egrid, FEAT_THREADS, 0, stream>>>(A.x, A.ld_x, A.n, A.f, A.w0, A.ld_w0, A.b0, A.h, dx, fbuf(B_RS), fbuf(B_P1), bt_hi, bt_lo, L.ldb, L.hp1);
+    LDS_CHECK_LAUNCH("feat_linear_kernel");
+  }
   profile_mark(stream, 1);
 
   EpiArgs E;

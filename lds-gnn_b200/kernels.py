@@ -169,7 +169,9 @@ class OuterStep:
     BUFFERS = {"adj": 0, "deg": 1, "rsqrt": 2, "p1": 3, "z1": 4, "p2": 5, "z2": 6, "dz2": 7, "dp2": 8, "dz1": 9,
                "dp1": 10, "fa": 11, "fb": 12, "cvec": 13}
 
-    def __init__(self, n, x, y, mask, hidden, classes):
+    SPARSE_DENSITY = 0.25          # below this share of non-zeros the feature GEMM runs from a CSR copy of x
+
+    def __init__(self, n, x, y, mask, hidden, classes, sparse_features=None):
         _lib.require_device()
         self.lib = _lib.load()
         self.n, self.f, self.h, self.c = int(n), int(x.shape[1]), int(hidden), int(classes)
@@ -178,6 +180,15 @@ class OuterStep:
         self.ld_x = (self.f + 3) // 4 * 4
         self.x = torch.zeros((self.n, self.ld_x), dtype=torch.float32, device=dev)       # zero-padded copy, 16-byte rows
         self.x[:, :self.f] = x
+        nnz = int((x != 0).sum().item())
+        self.sparse = (nnz < self.SPARSE_DENSITY * x.numel()) if sparse_features is None else bool(sparse_features)
+        self.x_crow = self.x_col = self.x_val = self.w0t = None
+        if self.sparse:                                     # one-off layout conversion of static data (setup, not hot path)
+            csr = x.detach().to(torch.float32).to_sparse_csr()
+            self.x_crow = csr.crow_indices().to(torch.int32).contiguous()
+            self.x_col = csr.col_indices().to(torch.int32).contiguous()
+            self.x_val = csr.values().to(torch.float32).contiguous()
+            self.w0t = torch.zeros((self.f, int(hidden)), dtype=torch.float32, device=dev)
         self.y = y.to(device=dev, dtype=torch.int64).contiguous()
         self.set_mask(mask)
         self.w0 = torch.zeros((self.h, self.ld_x), dtype=torch.float32, device=dev)       # staging, zero-padded
@@ -201,7 +212,10 @@ class OuterStep:
 
     def set_weights(self, w0, b0, w1, b1):
         """Copy the current GCN (fast) weights into the fixed, padded staging buffers."""
-        self.w0[:, :self.f].copy_(w0.detach())
+        if self.sparse:
+            self.w0t.copy_(w0.detach().t())
+        else:
+            self.w0[:, :self.f].copy_(w0.detach())
         self.b0.copy_(b0.detach())
         self.w1.copy_(w1.detach())
         self.b1.copy_(b1.detach())
@@ -233,6 +247,11 @@ class OuterStep:
         a.n, a.f, a.h, a.c = self.n, self.f, self.h, self.c
         a.theta_full, a.ld_theta = theta_full.data_ptr(), theta_full.stride(0)
         a.x, a.ld_x = self.x.data_ptr(), self.ld_x
+        if self.sparse:
+            a.x_crow, a.x_col, a.x_val, a.w0t = (self.x_crow.data_ptr(), self.x_col.data_ptr(), self.x_val.data_ptr(),
+                                                 self.w0t.data_ptr())
+        else:
+            a.x_crow = a.x_col = a.x_val = a.w0t = None
         a.w0, a.ld_w0 = self.w0.data_ptr(), self.ld_x
         a.b0, a.w1, a.b1 = self.b0.data_ptr(), self.w1.data_ptr(), self.b1.data_ptr()
         a.y, a.mask, a.mask_count = self.y.data_ptr(), self.mask.data_ptr(), self.mask_count

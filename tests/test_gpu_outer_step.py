@@ -39,17 +39,18 @@ def grad_from_factors(eng, n, theta_triu):
     return gt * ((theta_triu >= 0) & (theta_triu <= 1))
 
 
-def make_engine(g):
+def make_engine(g, sparse):
     from lds_gnn_b200 import kernels as K
     n = int(g["n"])
-    eng = K.OuterStep(n, dev(g["x"]), dev(g["y"]), dev(g["mask"]), hidden=int(g["h"]), classes=int(g["c"]))
+    eng = K.OuterStep(n, dev(g["x"]), dev(g["y"]), dev(g["mask"]), hidden=int(g["h"]), classes=int(g["c"]), sparse_features=sparse)
     eng.set_weights(dev(g["w0"]), dev(g["b0"]), dev(g["w1"]), dev(g["b1"]))
     return K, eng, n
 
 
-def test_golden_outer_step(golden):
+@pytest.mark.parametrize("sparse", [False, True], ids=["dense_x", "csr_x"])
+def test_golden_outer_step(golden, sparse):
     g = golden
-    K, eng, n = make_engine(g)
+    K, eng, n = make_engine(g, sparse)
     p = float(g["p"])
     theta = g["theta_triu"].astype(np.float32)
     for s in range(int(g["steps"])):
@@ -88,15 +89,16 @@ def test_golden_outer_step(golden):
     assert abs(st[1] / len(theta) - float(g["stat_mean_prob_f64"])) < 1e-5
 
 
+@pytest.mark.parametrize("sparse", [False, True], ids=["dense_x", "csr_x"])
 @pytest.mark.parametrize("n,f,h,c,p", [(50, 30, 16, 7, 0.0), (301, 120, 16, 7, 0.5), (700, 64, 64, 7, 0.5),
                                        (1200, 200, 32, 10, 0.0), (2708, 1433, 16, 7, 0.5)])
-def test_philox_outer_step_matches_oracle(n, f, h, c, p):
+def test_philox_outer_step_matches_oracle(n, f, h, c, p, sparse):
     """Philox mode end to end: the oracle regenerates the edge uniforms and both dropout masks on the CPU."""
     from oracle.make_golden import make_inputs
     from lds_gnn_b200 import kernels as K
     inp = make_inputs(seed=n, n=n, f=f, h=h, c=c, theta_kind="mixed" if n < 2000 else "sparse", p=p, mask_frac=0.2)
     seed, step, lr = 0xABCDEF0123, 11, 0.3
-    eng = K.OuterStep(n, dev(inp["x"]), dev(inp["y"]), dev(inp["mask"]), hidden=h, classes=c)
+    eng = K.OuterStep(n, dev(inp["x"]), dev(inp["y"]), dev(inp["mask"]), hidden=h, classes=c, sparse_features=sparse)
     eng.set_weights(dev(inp["w0"]), dev(inp["b0"]), dev(inp["w1"]), dev(inp["b1"]))
     full = K.theta_triu_to_full(dev(inp["theta_triu"]))
     logp = torch.empty((n, c), dtype=torch.float32, device="cuda")
