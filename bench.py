@@ -134,6 +134,15 @@ def algorithmic_bytes(shape):
     return per_kernel, step
 
 
+def reduce_rank_times(values_ms, device, world):
+    """Max over ranks of each timing (the job is as slow as its slowest rank)."""
+    t = torch.tensor(list(values_ms), dtype=torch.float64, device=device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
 # ------------------------------------------------------------------------------------------------ ours
 def run_ours(args, rank, world, device):
     import torch.distributed as dist
@@ -236,10 +245,7 @@ def run_ours(args, rank, world, device):
         dist.barrier()
 
     # ---- reduce over ranks -----------------------------------------------------------------------------
-    times = torch.tensor([dev_ms, e2e_s * 1e3, warm_ms], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, warm_ms = times.tolist()
+    dev_ms, e2e_ms, warm_ms = reduce_rank_times([dev_ms, e2e_s * 1e3, warm_ms], device, world)
     total_steps = args.steps * world
     value = total_steps / (dev_ms / 1e3)
     per_kernel_bytes, step_bytes = algorithmic_bytes(shape)

@@ -1,0 +1,324 @@
+"""CPU tests (no GPU, no compute calls): the C-ABI library loads and exports every symbol the header declares,
+the ctypes mirror of the argument struct matches the C layout, the host-side logic of the drop-in (config
+ingredients + loaders, early stopping, differentiable Adam, model state handling) behaves like the reference's,
+and the product path refuses to run without a B200 instead of falling back."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "lds_b200.h")
+REFERENCE = "/root/reference"
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from lds_gnn_b200 import _build, _lib
+    if _build.is_stale():
+        _build.build()
+    return _lib.load()
+
+
+# ------------------------------------------------------------------------------------------- C ABI
+def header_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lds_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from lds_gnn_b200 import _lib
+    declared = header_functions()
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/lds_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == declared, "ctypes SIGNATURES and the header disagree"
+
+
+def test_struct_layout_matches_header(lib):
+    """Compile the header as plain C and compare sizeof / offsets with the ctypes mirror."""
+    from lds_gnn_b200 import _lib
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "lds_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n", ' \
+          'sizeof(lds_outer_step_args), offsetof(lds_outer_step_args, theta_full), offsetof(lds_outer_step_args, seed), ' \
+          'offsetof(lds_outer_step_args, out_scalars), offsetof(lds_outer_step_args, k2_flags)); return 0;}\n'
+    with tempfile.TemporaryDirectory() as tmp:
+        c = os.path.join(tmp, "t.c")
+        open(c, "w").write(src)
+        exe = os.path.join(tmp, "t")
+        subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
+    S = _lib.OuterStepArgs
+    assert [int(v) for v in out] == [ctypes.sizeof(S), S.theta_full.offset, S.seed.offset, S.out_scalars.offset, S.k2_flags.offset]
+
+
+def test_host_only_entry_points(lib):
+    from oracle import philox as PH
+    assert lib.lds_version() >= 100
+    assert lib.lds_padded_ld(2708) == 2752 and lib.lds_padded_ld(64) == 64 and lib.lds_padded_ld(1) == 64
+    assert lib.lds_k2_workspace_bytes(2708, 2708, 16) > 0 and lib.lds_k2_workspace_bytes(10, 10, 129) == -1
+    assert lib.lds_outer_step_workspace_bytes(3327, 3703, 16, 6) > 3327 * 3328 * 2
+    assert lib.lds_outer_step_factor_ld(16, 7) == 24
+    u = PH.edge_uniforms(40, seed=99, step=5, sample=2)
+    for i, j in [(0, 0), (3, 17), (17, 3), (39, 39), (38, 39)]:
+        assert np.float32(lib.lds_philox_uniform(99, 5, 0, 2, i, j)) == u[i, j]
+    d = PH.dropout_uniforms(8, 20, seed=99, step=5, stream=PH.STREAM_DROP_H)
+    assert np.float32(lib.lds_philox_uniform(99, 5, 2, 0, 6, 13)) == d[6, 13]
+
+
+def test_errors_are_reported_not_thrown(lib):
+    from lds_gnn_b200 import _lib
+    rc = lib.lds_outer_step(None, None)
+    assert rc != 0 and "null args" in _lib.last_error()
+    rc = lib.lds_k1_sample_normalize(None, 0, 4, 0, 4, 0, 0, 0, None, 0, None, 0, None, 0, None, None, 0, None)
+    assert rc != 0 and "null pointer" in _lib.last_error()
+
+
+def test_no_cpu_fallback():
+    """Without a GPU every compute path raises loudly (the driver checks that nothing silently falls back)."""
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from lds_gnn_b200 import kernels
+    from lds_gnn_b200.models.graph import BernoulliGraphModel
+    from lds_gnn_b200.models.sampling import Sampler
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        kernels.theta_triu_to_full(torch.zeros(6))
+    model = BernoulliGraphModel(torch.eye(5))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model.forward()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Sampler.sample(torch.rand(5, 5))
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        model.theta_full()
+
+
+def test_product_code_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "lds-gnn_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(base, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{f} imports oracle/"
+
+
+# ------------------------------------------------------------------------------------------- config
+def test_ingredient_config_and_capture():
+    from lds_gnn_b200.config import Ingredient
+    ing = Ingredient("unit-test-ingredient")
+
+    @ing.config
+    def cfg():
+        alpha = 3            # noqa: F841
+        beta = "x"           # noqa: F841
+
+    @ing.capture
+    def fn(a, alpha, beta="default", gamma=7):
+        return a, alpha, beta, gamma
+
+    assert fn(1) == (1, 3, "x", 7)
+    assert fn(1, alpha=9) == (1, 9, "x", 7) and fn(1, 2, "y") == (1, 2, "y", 7)
+    ing.update({"alpha": 5})
+    assert fn(0)[1] == 5
+    with pytest.raises(KeyError):
+        ing.update({"nope": 1})
+
+
+def test_reference_defaults_are_preserved():
+    from lds_gnn_b200.config import current_config
+    import lds_gnn_b200.models.factory  # noqa: F401
+    import lds_gnn_b200.trainers.outer  # noqa: F401
+    cfg = current_config()
+    assert cfg["sampler"] == {"undirected": True, "k": 20, "eps": 0.9, "sparsification": "NONE", "dense": False,
+                              "knn_metric": "cosine"}                                   # src/models/sampling.py:93-102
+    assert cfg["lds"]["directed"] is False and cfg["lds"]["lr"] == 1.0                  # src/models/factory.py:52-56
+    ot = cfg["outer-trainer"]                                                           # src/trainers/outer.py:118-129
+    assert (ot["lr_decay"], ot["lr_decay_step_size"], ot["pretrain"], ot["regularize"]) == (1.0, 1, True, False)
+
+
+def test_seml_yaml_expansion(tmp_path):
+    from lds_gnn_b200.config import expand_seml, load_seml_yaml
+    p = tmp_path / "cfg.yaml"
+    p.write_text("""
+seml: {db_collection: x}
+slurm: {name: y}
+fixed:
+  device: cuda
+  hidden_sizes: 16
+grid:
+  hyper_gradient_interval: {type: choice, options: [5, 10]}
+  lds:
+    type: parameter_collection
+    params:
+      lr: {type: choice, options: [0.1, 1.0]}
+sub-a:
+  fixed:
+    data: {type: parameter_collection, params: {shuffle_splits: false}}
+  grid:
+    data: {type: parameter_collection, params: {dataset: {type: choice, options: [cora, citeseer]}}}
+  random:
+    samples: 2
+    seed: 1
+    data: {type: parameter_collection, params: {split_seed: {type: randint, min: 1, max: 100}}}
+""")
+    doc = load_seml_yaml(str(p))
+    cfgs = expand_seml(doc, "sub-a")
+    assert len(cfgs) == 2 * 2 * 2 * 2
+    assert {c["lds"]["lr"] for c in cfgs} == {0.1, 1.0} and {c["data"]["dataset"] for c in cfgs} == {"cora", "citeseer"}
+    assert all(c["device"] == "cuda" and c["data"]["shuffle_splits"] is False and 1 <= c["data"]["split_seed"] < 100 for c in cfgs)
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference configs only exist in the build container")
+def test_reference_lds_config_files_parse():
+    from lds_gnn_b200.config import apply_config, current_config, expand_seml, load_sacred_json, load_seml_yaml
+    import lds_gnn_b200.models.factory  # noqa: F401
+    import lds_gnn_b200.trainers.outer  # noqa: F401
+    cfg = load_sacred_json(f"{REFERENCE}/configs/sacred/lds/config.json")
+    assert cfg["graph_model"] == "lds" and cfg["lds"] == {"directed": False, "lr": 1.0}
+    final = load_seml_yaml(f"{REFERENCE}/configs/seml/final/lds.yaml")
+    runs = expand_seml(final, "graph-datasets-planetoid")
+    assert len(runs) == 20 and runs[0]["lds"]["lr"] == 0.1 and runs[0]["outer-trainer"]["lr_decay"] == 0.99
+    assert runs[0]["hyper_gradient_interval"] == 5 and runs[0]["n_samples_empirical_mean"] == 16
+    grid = expand_seml(load_seml_yaml(f"{REFERENCE}/configs/seml/grid/lds_grid.yaml"), "graph-datasets")
+    assert len(grid) > 50 and all(g["graph_model"] == "lds" for g in grid)
+    saved = current_config()
+    try:
+        rest = apply_config({k: v for k, v in runs[0].items() if k in ("lds", "outer-trainer", "hidden_sizes", "dropout")})
+        assert rest == {"hidden_sizes": 16, "dropout": 0.5}
+        assert current_config()["lds"]["lr"] == 0.1 and current_config()["outer-trainer"]["lr_decay"] == 0.99
+    finally:
+        from lds_gnn_b200.config import REGISTRY
+        for k, v in saved.items():
+            REGISTRY[k].values.update(v)
+
+
+# ------------------------------------------------------------------------------------------- host logic
+def test_early_stopping_indices():                       # tst/utils/test_early_stopping.py
+    from lds_gnn_b200.utils.early_stopping import EarlyStopping
+
+    def run(stopper, values):
+        for v in values:
+            stopper.update(v)
+            if stopper.abort:
+                return stopper.curr_step
+    assert run(EarlyStopping(patience=1, max_epochs=100), (-a for a in range(1000))) == 101
+    assert run(EarlyStopping(patience=20, max_epochs=100), (42.0 + a for a in range(1000))) == 22
+    assert run(EarlyStopping(patience=34, max_epochs=1000), (42.0 - a if a < 500 else 42.0 + a for a in range(1000))) == 501
+
+
+def test_differentiable_adam_tracks_torch_adam_and_is_differentiable():
+    from lds_gnn_b200.trainers.diffopt import DifferentiableAdam
+    torch.manual_seed(0)
+    w = [torch.randn(4, 3), torch.randn(4)]
+    ref = [p.clone().requires_grad_(True) for p in w]
+    opt = torch.optim.Adam([{"params": [ref[0]], "weight_decay": 5e-4}, {"params": [ref[1]]}], lr=0.01)
+    fast = [p.clone().requires_grad_(True) for p in w]
+    dopt = DifferentiableAdam(torch.optim.Adam([{"params": [fast[0]], "weight_decay": 5e-4}, {"params": [fast[1]]}], lr=0.01), fast)
+    x = torch.randn(8, 3)
+    scale = torch.tensor(1.5, requires_grad=True)            # a "hyper-parameter" the inner loss depends on
+    cur = fast
+    for _ in range(5):
+        opt.zero_grad()
+        ((x @ ref[0].t() + ref[1]) ** 2).mean().mul(1.5).backward()
+        opt.step()
+        cur = dopt.step(((x @ cur[0].t() + cur[1]) ** 2).mean() * scale, cur)
+    for a, b in zip(cur, ref):
+        assert torch.allclose(a, b, atol=1e-5)               # eps placement differs from modern torch Adam: immaterial here
+    (cur[0].sum()).backward()
+    assert scale.grad is not None and scale.grad.abs() > 0   # hypergradient flows through the unrolled updates
+    dopt.detach_()
+    assert all(not v.requires_grad for st in dopt.state for s in st.values() for v in s.values() if torch.is_tensor(v))
+
+
+def test_directed_model_and_state_dict_on_cpu():         # tst/models/test_bernoulli_model.py:113-128
+    from lds_gnn_b200.models.graph import BernoulliGraphModel
+    adj = torch.eye(10); adj[1, :] = 1.0
+    model = BernoulliGraphModel(init_matrix=adj, directed=True)
+    assert torch.equal(model.forward(), adj)
+    model.forward().sum().backward()
+    assert (model.probs.grad > 0).all()
+    und = BernoulliGraphModel(init_matrix=adj * 2, directed=False)
+    assert und.probs.shape == (55,) and list(und.state_dict()) == ["probs"]
+    und.project_parameters()
+    assert und.probs.max() <= 1.0
+    clone = BernoulliGraphModel(init_matrix=torch.zeros(10, 10))
+    clone.load_state_dict(und.state_dict())
+    assert torch.equal(clone.probs, und.probs)
+    assert [n for n, _ in und.named_parameters()] == ["probs"]
+
+
+def test_gcn_module_structure_and_param_override_on_cpu():   # tst/models/test_gcn.py:75-109, test_layers.py
+    from collections import OrderedDict
+    from lds_gnn_b200.models.gcn import MetaDenseGCN
+    torch.manual_seed(0)
+    gcn = MetaDenseGCN(6, 4, 3, dropout=0.0)
+    names = [n for n, _ in gcn.named_parameters()]
+    assert names == ["layer_in.fc.weight", "layer_in.fc.bias", "layer_out.fc.weight", "layer_out.fc.bias"]
+    assert (gcn.layer_in.fc.bias == 0).all()
+    x, adj = torch.rand(5, 6), torch.eye(5)
+    out = gcn(x, adj)                                         # dense adjacency without a sample handle: generic torch path
+    assert out.shape == (5, 3) and torch.allclose(out.exp().sum(1), torch.ones(5), atol=1e-6)
+    override = OrderedDict((k, (v.detach() + 1).requires_grad_(True)) for k, v in gcn.named_parameters())
+    out2 = gcn(x, adj, params=override)
+    assert not torch.allclose(out, out2)
+    out2.sum().backward()
+    assert all(p.grad is None for p in gcn.parameters()) and all(v.grad is not None for v in override.values())
+    before = gcn.layer_in.fc.weight.clone()
+    gcn.reset_weights()
+    assert not torch.equal(before, gcn.layer_in.fc.weight)
+
+
+def test_normalisation_matches_reference_formula_on_cpu():
+    from lds_gnn_b200.utils.graph import add_self_loops, get_triu_values, normalize_adjacency_matrix, split_mask, to_undirected
+    a = (torch.rand(30, 30) < 0.2).float()
+    a = to_undirected(a)
+    at = add_self_loops(a)
+    d = torch.diag(1.0 / at.sum(1).sqrt())
+    assert torch.allclose(normalize_adjacency_matrix(a), d @ at @ d, atol=1e-6)          # src/utils/graph.py:148-152
+    assert get_triu_values(a).numel() == 30 * 31 // 2
+    m = torch.zeros(30, dtype=torch.bool); m[:20] = True
+    first, second = split_mask(m, 0.5)
+    assert first.sum() == 10 and second.sum() == 10 and not (first & second).any() and torch.equal(first | second, m)
+
+
+def test_synthetic_dataset_shapes():
+    from lds_gnn_b200.data import make_dataset
+    d = make_dataset("tiny", seed=3)
+    assert d.x.shape == (300, 64) and d.dense_adj.shape == (300, 300) and torch.equal(d.dense_adj, d.dense_adj.t())
+    assert torch.allclose(d.x.sum(1), torch.ones(300), atol=1e-5)
+    assert d.train_mask.sum() == 80 and not (d.train_mask & d.val_mask).any() and not (d.val_mask & d.test_mask).any()
+
+
+# ------------------------------------------------------------------------------------------- N > 1 (gloo, world size 2)
+WORKER = r"""
+import os, sys, json
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+from bench import reduce_rank_times
+ms = [10.0, 30.0] if dist.get_rank() == 0 else [20.0, 5.0]
+out = reduce_rank_times(ms, torch.device("cpu"), world=2)
+if dist.get_rank() == 0:
+    print(json.dumps(out))
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_multi_rank_timing_is_max_over_ranks(tmp_path):
+    """The N>1 bench path (independent replicas, no data-path collective) reports max-over-ranks times."""
+    import json
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=180) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert json.loads(outs[0][0].strip().splitlines()[-1]) == [20.0, 30.0]
