@@ -43,6 +43,7 @@ extern "C" {
 /* K3 flags */
 #define LDS_K3_DENSE_GRAD    1u  /* write dL/dA_tilde (dense, not symmetrised) instead of updating theta      */
 #define LDS_K3_ACCUMULATE    2u  /* with DENSE_GRAD: add into grad_out instead of overwriting                  */
+#define LDS_K3_SIMT          4u  /* lds_outer_step: use the CUDA-core update kernel instead of the tcgen05 one   */
 /* optimiser kinds (src/models/factory.py:66-69 uses SGD; Adam is the north-star's option)                   */
 #define LDS_OPT_SGD          0
 #define LDS_OPT_ADAM         1
@@ -113,6 +114,14 @@ int32_t lds_k3k4_theta_update(float* theta_full, int64_t ld_theta, int32_t n, in
                               float beta1, float beta2, float eps, int32_t t,
                               float* grad_out, int64_t ld_g, uint32_t flags, void* stream);
 
+/* Tensor-core variant of the SGD update (the one lds_outer_step uses): the rank-2d term runs as a bf16 hi/lo-split
+ * GEMM on tcgen05 (fp32 accumulation in TMEM) with theta streamed through shared memory by TMA; same result as
+ * the CUDA-core kernel within ~1e-6 relative, and exactly symmetric. workspace: lds_k3_workspace_bytes(n, d). */
+int64_t lds_k3_workspace_bytes(int32_t n, int32_t d);
+int32_t lds_k3k4_theta_update_tc(float* theta_full, int64_t ld_theta, int32_t n, int32_t row0, int32_t rows,
+                                 const float* fa, const float* fb, int64_t ld_f, int32_t d, const float* cvec,
+                                 float lr, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- fused direct outer step (a4..a11): one OuterProblemTrainer.train_step (src/trainers/outer.py:57-87)
  * with gcn_predict_fct = InnerProblemTrainer.model_forward (src/trainers/inner.py:76-78) at fixed weights,
  * regularize = False. Enqueues K1, the feature GEMM with fused dropout, 4 x K2 with their row epilogues
@@ -150,7 +159,7 @@ typedef struct lds_outer_step_args {
   float*   out_logp;          /* optional [n][c] log-probabilities, else NULL                           */
   void*    workspace; int64_t workspace_bytes;
   uint32_t k2_flags;          /* LDS_K2_* for the four propagations                                      */
-  uint32_t reserved;
+  uint32_t k3_flags;          /* LDS_K3_SIMT or 0                                                        */
 } lds_outer_step_args;
 
 int64_t lds_outer_step_workspace_bytes(int32_t n, int32_t f, int32_t h, int32_t c);

@@ -12,7 +12,7 @@ from . import _build
 LDS_OK = 0
 K1_EXPLICIT_U = 1
 K2_SIMT, K2_SINGLE_BF16 = 1, 2
-K3_DENSE_GRAD, K3_ACCUMULATE = 1, 2
+K3_DENSE_GRAD, K3_ACCUMULATE, K3_SIMT = 1, 2, 4
 OPT_SGD, OPT_ADAM = 0, 1
 STREAM_EDGES, STREAM_DROP_X, STREAM_DROP_H = 0, 1, 2
 
@@ -36,6 +36,9 @@ SIGNATURES = {
     "lds_k3k4_theta_update": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_int32,
                                         c_void_p, c_float, c_int32, c_void_p, c_void_p, c_float, c_float, c_float, c_int32,
                                         c_void_p, c_int64, c_uint32, c_void_p]),
+    "lds_k3_workspace_bytes": (c_int64, [c_int32, c_int32]),
+    "lds_k3k4_theta_update_tc": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_int32,
+                                           c_void_p, c_float, c_void_p, c_int64, c_void_p]),
     "lds_outer_step_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
     "lds_outer_step": (c_int32, [c_void_p, c_void_p]),
     "lds_outer_step_buffer": (c_void_p, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32]),
@@ -66,7 +69,7 @@ class OuterStepArgs(Structure):
         ("update", c_int32),
         ("out_scalars", c_void_p), ("out_logp", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_int64),
-        ("k2_flags", c_uint32), ("reserved", c_uint32),
+        ("k2_flags", c_uint32), ("k3_flags", c_uint32),
     ]
 
 

@@ -14,7 +14,8 @@
 // with sequential FMAs in k order; element (j,i) computes the same two chains swapped, and fp32 add/mul/fma are
 // commutative in their multiplicands, so theta_ij == theta_ji bit for bit (the row-block shards of a multi-GPU
 // run therefore stay consistent without any exchange).
-#include "lds_common.cuh"
+#include "lds_k3.cuh"
+#include "lds_tc.cuh"
 
 namespace lds {
 
@@ -137,6 +138,222 @@ k3_update_kernel(float* __restrict__ theta, int64_t ldt, int n, int row0, int ro
   }
 }
 
+// ================================================================================================
+// Tensor-core variant (SGD): the rank-2d term is a GEMM, so at large d (h = 64 => d = 71, 142 FMA per element
+// on CUDA cores) it must run on tcgen05 or the update stops being an HBM stream. Operands are the bf16
+// hi/lo-split factor matrices laid out K-major:
+//     Pm = [fa_hi | fa_hi | fa_lo | 0],  Qm = [fb_hi | fb_lo | fb_hi | 0]          ([n][Kp] bf16, Kp = round_up(3d, 64))
+//     D1 = Pm_i Qm_j^T ~= fa_i.fb_j,    D2 = Qm_i Pm_j^T ~= fb_i.fa_j               (fp32 accumulation in TMEM)
+// D1(i,j) and D2(j,i) are the same products accumulated in the same k order, so g_ij == g_ji bit for bit
+// (bf16 x bf16 products are exact in fp32; fp32 addition is commutative) — asserted by the tests.
+// One persistent CTA per SM walks 128 x 128 tiles:
+//   warp 0   TMA producer: theta slabs (128 rows x 32 fp32, SWIZZLE_128B) into an 8-slab ring = two tiles in
+//            flight, and per k-block the four 128 x 64 operand blocks
+//   warp 1   tcgen05.mma issuer, two double-buffered accumulator pairs in TMEM (512 columns)
+//   warps 2-9 epilogue: tcgen05.ld D1/D2, theta from smem, g = (D1 + D2) + (c_i + c_j), SGD step + clamp written
+//            back into the same smem slab, then one TMA store per slab (coalesced, asynchronous)
+// ================================================================================================
+constexpr int K3T_TILE = 128;
+constexpr int K3T_KB = 64;
+constexpr int K3T_SLAB_COLS = 32;
+constexpr int K3T_RING = 8;
+constexpr int K3T_OP_BYTES = K3T_TILE * K3T_KB * 2;          // 16 KB
+constexpr int K3T_STAGE_BYTES = 4 * K3T_OP_BYTES;            // Pm_i, Qm_i, Qm_j, Pm_j
+constexpr int K3T_SLAB_BYTES = K3T_TILE * K3T_SLAB_COLS * 4; // 16 KB
+constexpr int K3T_THREADS = 320;
+constexpr int K3T_SMEM = K3T_STAGE_BYTES + K3T_RING * K3T_SLAB_BYTES + 1024 + 512;
+
+__global__ void __launch_bounds__(K3T_THREADS, 1)
+k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant__ CUtensorMap tm_pm,
+             const __grid_constant__ CUtensorMap tm_qm, const float* __restrict__ cvec,
+             int n, int row0, int rows, int kblocks, int ksteps, float lr) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ops = smem;                                        // one operand stage
+  uint8_t* slabs = smem + K3T_STAGE_BYTES;                    // theta ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slabs + K3T_RING * K3T_SLAB_BYTES);
+  uint64_t* ofull = bars;            // [1]
+  uint64_t* oempty = bars + 1;       // [1]
+  uint64_t* tfull = bars + 2;        // [2]
+  uint64_t* tempty = bars + 4;       // [2]
+  uint64_t* thfull = bars + 6;       // [RING]
+  uint64_t* thempty = bars + 6 + K3T_RING;   // [RING]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * K3T_RING);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_j = (n + K3T_TILE - 1) / K3T_TILE;
+  const int tiles_i = (rows + K3T_TILE - 1) / K3T_TILE;
+  const int num_tiles = tiles_i * tiles_j;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_theta); tma_prefetch_desc(&tm_pm); tma_prefetch_desc(&tm_qm); }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(ofull, 1); mbar_init(oempty, 1);
+      for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+      for (int i = 0; i < K3T_RING; ++i) { mbar_init(&thfull[i], 1); mbar_init(&thempty[i], 1); }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int tt = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tt) {
+        const int bi = t / tiles_j, bj = t - bi * tiles_j;
+        const int li0 = bi * K3T_TILE, gi0 = row0 + li0, j0 = bj * K3T_TILE;
+        for (int s = 0; s < 4; ++s) {                         // theta first: deepest HBM prefetch
+          const int q = tt * 4 + s, slot = q % K3T_RING;
+          mbar_wait(&thempty[slot], ((q / K3T_RING) & 1) ^ 1);
+          mbar_expect_tx(&thfull[slot], K3T_SLAB_BYTES);
+          tma_load_2d(slabs + slot * K3T_SLAB_BYTES, &tm_theta, &thfull[slot], j0 + s * K3T_SLAB_COLS, li0);
+        }
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const int oq = tt * kblocks + kb;
+          mbar_wait(oempty, (oq & 1) ^ 1);
+          mbar_expect_tx(ofull, K3T_STAGE_BYTES);
+          tma_load_2d(ops + 0 * K3T_OP_BYTES, &tm_pm, ofull, kb * K3T_KB, gi0);   // A1 = Pm_i
+          tma_load_2d(ops + 1 * K3T_OP_BYTES, &tm_qm, ofull, kb * K3T_KB, gi0);   // A2 = Qm_i
+          tma_load_2d(ops + 2 * K3T_OP_BYTES, &tm_qm, ofull, kb * K3T_KB, j0);    // B1 = Qm_j
+          tma_load_2d(ops + 3 * K3T_OP_BYTES, &tm_pm, ofull, kb * K3T_KB, j0);    // B2 = Pm_j
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(K3T_TILE, K3T_TILE);
+      const uint32_t base = smem_u32(ops);
+      const uint64_t a1 = umma_desc_k_sw128(base), a2 = umma_desc_k_sw128(base + K3T_OP_BYTES);
+      const uint64_t b1 = umma_desc_k_sw128(base + 2 * K3T_OP_BYTES), b2 = umma_desc_k_sw128(base + 3 * K3T_OP_BYTES);
+      int tt = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tt) {
+        const int acc = tt & 1;
+        mbar_wait(&tempty[acc], ((tt >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d1 = tmem_base + (uint32_t)(acc * 256), d2 = d1 + 128;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const int oq = tt * kblocks + kb;
+          mbar_wait(ofull, oq & 1);
+          tc_fence_after();
+          const int steps = min(4, ksteps - 4 * kb);
+          for (int k = 0; k < steps; ++k) tc_mma_bf16(d1, a1 + 2 * k, b1 + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < steps; ++k) tc_mma_bf16(d2, a2 + 2 * k, b2 + 2 * k, idesc, (kb | k) != 0);
+          tc_commit(oempty);
+        }
+        tc_commit(&tfull[acc]);
+      }
+    }
+  } else {
+    // ===== epilogue =====
+    const int e = warp - 2;
+    const int quarter = warp & 3;                    // TMEM lane quarter this warp may access (warp id mod 4)
+    const int hf = e >> 2;                           // which pair of slabs (column half of the tile)
+    const int row = quarter * 32 + lane;
+    const bool storer = ((e & 3) == 0) && (lane == 0);
+    int pending = -1;
+    int tt = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tt) {
+      const int bi = t / tiles_j, bj = t - bi * tiles_j;
+      const int li0 = bi * K3T_TILE, gi0 = row0 + li0, j0 = bj * K3T_TILE;
+      const int acc = tt & 1;
+      const int gi = gi0 + row;
+      const float ci = (gi < n) ? cvec[gi] : 0.f;
+      mbar_wait(&tfull[acc], (tt >> 1) & 1);
+      tc_fence_after();
+      for (int sl = 0; sl < 2; ++sl) {
+        const int s = 2 * hf + sl;
+        const int q = tt * 4 + s, slot = q % K3T_RING;
+        uint32_t d1[32], d2[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + s * K3T_SLAB_COLS);
+        {
+          uint32_t (&lo1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&d1[0]);
+          uint32_t (&hi1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&d1[16]);
+          uint32_t (&lo2)[16] = *reinterpret_cast<uint32_t (*)[16]>(&d2[0]);
+          uint32_t (&hi2)[16] = *reinterpret_cast<uint32_t (*)[16]>(&d2[16]);
+          tc_ld16(taddr, lo1); tc_ld16(taddr + 16, hi1);
+          tc_ld16(taddr + 128, lo2); tc_ld16(taddr + 128 + 16, hi2);
+        }
+        mbar_wait(&thfull[slot], (q / K3T_RING) & 1);
+        tc_wait_ld();
+        uint8_t* slab = slabs + slot * K3T_SLAB_BYTES + row * 128;
+        const int jb = j0 + s * K3T_SLAB_COLS;
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          float4* cell = reinterpret_cast<float4*>(slab + ((c4 ^ (row & 7)) << 4));
+          float4 th = *cell;
+          const int gj = jb + 4 * c4;
+          float cj[4];
+          if (gj + 3 < n) { const float4 cv = *reinterpret_cast<const float4*>(cvec + gj); cj[0] = cv.x; cj[1] = cv.y; cj[2] = cv.z; cj[3] = cv.w; }
+          else { for (int b = 0; b < 4; ++b) cj[b] = (gj + b < n) ? cvec[gj + b] : 0.f; }
+          float tv[4] = {th.x, th.y, th.z, th.w};
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            float g = (__uint_as_float(d1[4 * c4 + b]) + __uint_as_float(d2[4 * c4 + b])) + (ci + cj[b]);
+            if (gi == gj + b) g = 0.f;
+            if (tv[b] < 0.f || tv[b] > 1.f) g = 0.f;
+            const float nv = fminf(fmaxf(fmaf(-lr, g, tv[b]), 0.f), 1.f);
+            if (gj + b < n) tv[b] = nv;               // the TMA store clips at 16-byte granularity: leave padding as loaded
+          }
+          *cell = make_float4(tv[0], tv[1], tv[2], tv[3]);
+        }
+        fence_proxy_async_smem();                      // generic-proxy writes -> visible to the TMA store
+        named_bar_sync(1 + hf, 128);                   // the four warps that own this slab
+        if (storer) {
+          if (pending >= 0) { tma_store_wait_read(); mbar_arrive(&thempty[pending]); }
+          tma_store_2d(slabs + slot * K3T_SLAB_BYTES, &tm_theta, jb, li0);
+          tma_store_commit();
+          pending = slot;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+    if (storer) {
+      if (pending >= 0) { tma_store_wait_read(); mbar_arrive(&thempty[pending]); }
+      tma_store_wait_all();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// fa, fb fp32 [n][ldf] -> Pm, Qm bf16 [n][kp]
+__global__ void k3_pack_kernel(const float* __restrict__ fa, const float* __restrict__ fb, int64_t ldf, int n, int d, int kp,
+                               __nv_bfloat16* __restrict__ pm, __nv_bfloat16* __restrict__ qm) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)n * kp) return;
+  const int i = (int)(idx / kp), k = (int)(idx - (int64_t)i * kp);
+  k3_pack_element(fa + (int64_t)i * ldf, fb + (int64_t)i * ldf, d, k, pm[idx], qm[idx]);
+}
+
+int32_t k3_launch_tc(float* theta, int64_t ldt, int n, int row0, int rows, const void* pm, const void* qm, int kp, int d,
+                     const float* cvec, float lr, cudaStream_t stream) {
+  CUtensorMap tth, tpm, tqm;
+  int32_t rc;
+  if ((rc = make_tmap_2d(&tth, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, theta, n, rows, ldt, K3T_SLAB_COLS, K3T_TILE)) != LDS_OK) return rc;
+  if ((rc = make_tmap_2d(&tpm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pm, kp, n, kp, K3T_KB, K3T_TILE)) != LDS_OK) return rc;
+  if ((rc = make_tmap_2d(&tqm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qm, kp, n, kp, K3T_KB, K3T_TILE)) != LDS_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LDS_CHECK_CUDA(cudaFuncSetAttribute(k3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K3T_SMEM));
+    attr_set = true;
+  }
+  const int tiles = (int)(ceil_div(rows, K3T_TILE) * ceil_div(n, K3T_TILE));
+  const int grid = tiles < kNumSMsB200 ? tiles : kNumSMsB200;
+  k3_tc_kernel<<<grid, K3T_THREADS, K3T_SMEM, stream>>>(tth, tpm, tqm, cvec, n, row0, rows, kp / K3T_KB, (int)ceil_div(3 * d, 16), lr);
+  LDS_CHECK_LAUNCH("k3_tc_kernel");
+  return LDS_OK;
+}
+
 }  // namespace lds
 
 using namespace lds;
@@ -171,4 +388,31 @@ extern "C" int32_t lds_k3k4_theta_update(float* theta_full, int64_t ld_theta, in
                                                            adam_m, adam_v, beta1, beta2, eps, bc1, bc2, nullptr, 0, 0);
   LDS_CHECK_LAUNCH("k3_update_kernel");
   return LDS_OK;
+}
+
+extern "C" int64_t lds_k3_workspace_bytes(int32_t n, int32_t d) {
+  if (n <= 0 || d <= 0) return -1;
+  return 2 * round_up((int64_t)n * k3_padded_k(d) * 2, 1024);
+}
+
+extern "C" int32_t lds_k3k4_theta_update_tc(float* theta_full, int64_t ld_theta, int32_t n, int32_t row0, int32_t rows,
+                                            const float* fa, const float* fb, int64_t ld_f, int32_t d, const float* cvec,
+                                            float lr, void* workspace, int64_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LDS_CHECK_ARG(theta_full && fa && fb && cvec, "lds_k3k4_theta_update_tc: null pointer");
+  LDS_CHECK_ARG(n > 0 && rows > 0 && row0 >= 0 && row0 + rows <= n, "lds_k3k4_theta_update_tc: rows [%d, %d) outside [0, %d)", row0, row0 + rows, n);
+  LDS_CHECK_ARG(d > 0 && ld_f >= d, "lds_k3k4_theta_update_tc: need d > 0 and ld_f >= d");
+  LDS_CHECK_ARG((reinterpret_cast<uintptr_t>(cvec) & 15) == 0, "lds_k3k4_theta_update_tc: cvec must be 16-byte aligned");
+  LDS_CHECK_ARG(ld_theta >= n && ld_theta % 4 == 0 && (reinterpret_cast<uintptr_t>(theta_full) & 15) == 0,
+                "lds_k3k4_theta_update_tc: theta must be 16-byte aligned with ld_theta >= n, ld_theta %% 4 == 0");
+  const int64_t need = lds_k3_workspace_bytes(n, d);
+  if (!workspace || workspace_bytes < need) { set_error("lds_k3k4_theta_update_tc: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need); return LDS_ERR_WORKSPACE; }
+  LDS_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "lds_k3k4_theta_update_tc: workspace must be 1024-byte aligned");
+  const int kp = k3_padded_k(d);
+  auto* pm = reinterpret_cast<__nv_bfloat16*>(workspace);
+  auto* qm = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + need / 2);
+  const int64_t total = (int64_t)n * kp;
+  k3_pack_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(fa, fb, ld_f, n, d, kp, pm, qm);
+  LDS_CHECK_LAUNCH("k3_pack_kernel");
+  return k3_launch_tc(theta_full, ld_theta, n, row0, rows, pm, qm, kp, d, cvec, lr, stream);
 }

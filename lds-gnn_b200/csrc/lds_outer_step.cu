@@ -16,6 +16,7 @@
 //   K3+K4         theta <- clamp(theta - lr * g(fa, fb, c))                         lds_k3_theta_update.cu
 // The outer step needs no weight gradients (the reference computes and discards them), so X is read once.
 #include "lds_k2.cuh"
+#include "lds_k3.cuh"
 #include "lds_philox.cuh"
 
 namespace lds {
@@ -25,14 +26,14 @@ constexpr int EPI_THREADS = 1024;   // 32 warps, one row each: the epilogues are
 constexpr int FEAT_THREADS = 256;   // dense feature GEMM: 8 warps x 4 rows
 constexpr int EPI_MAXW = 128;       // widest operand
 
+enum { B_A = 0, B_DEG, B_RS, B_P1, B_Z1, B_P2, B_Z2, B_DZ2, B_DP2, B_DZ1, B_DP1, B_FA, B_FB, B_C, B_BTHI, B_BTLO, B_PARTIAL, B_LOSSP, B_CORRP, B_PM, B_QM, B_END };
 struct OuterLayout {
-  int n, f, h, c, hp1, hp2, hpmax, nblk;
+  int n, f, h, c, hp1, hp2, hpmax, nblk, kp;
   int64_t lda, ldb, ldf;
   K2Sched s1, s2;
-  int64_t off[20];
+  int64_t off[B_END];
   int64_t total;
 };
-enum { B_A = 0, B_DEG, B_RS, B_P1, B_Z1, B_P2, B_Z2, B_DZ2, B_DP2, B_DZ1, B_DP1, B_FA, B_FB, B_C, B_BTHI, B_BTLO, B_PARTIAL, B_LOSSP, B_CORRP, B_END };
 
 static bool make_layout(int n, int f, int h, int c, OuterLayout& L) {
   L.n = n; L.f = f; L.h = h; L.c = c;
@@ -52,6 +53,8 @@ static bool make_layout(int n, int f, int h, int c, OuterLayout& L) {
   const int64_t p1 = k2_partial_bytes(L.s1), p2 = k2_partial_bytes(L.s2);
   bytes[B_PARTIAL] = p1 > p2 ? p1 : p2;
   bytes[B_LOSSP] = bytes[B_CORRP] = (int64_t)L.nblk * 4;
+  L.kp = k3_padded_k(h + c);
+  bytes[B_PM] = bytes[B_QM] = (int64_t)n * L.kp * 2;
   int64_t o = 0;
   for (int b = 0; b < B_END; ++b) { L.off[b] = o; o += round_up(bytes[b], 1024); }
   L.total = o;
@@ -232,6 +235,7 @@ struct EpiArgs {
   const float* deg; const float* rs;
   float* p1; float* z1; float* p2; float* z2; float* dz2; float* dp2; float* dz1; float* dp1;
   float* fa; float* fb; int64_t ldf; float* cvec;
+  __nv_bfloat16* pm; __nv_bfloat16* qm; int kp;
   const float* w1; const float* b1;
   const int64_t* y; const uint8_t* mask; float inv_m;
   DropCfg drop_h;
@@ -394,6 +398,11 @@ __global__ void __launch_bounds__(EPI_THREADS) epi_bwd1_kernel(const EpiArgs a) 
       fa[a.h + o] = ri * dz2; fb[a.h + o] = ri * p2;
     }
     for (int k = a.h + a.c + lane; k < (int)a.ldf; k += 32) { fa[k] = 0.f; fb[k] = 0.f; }
+    __threadfence_block();
+    __syncwarp();                                             // the row's factors are complete and visible to the warp
+    for (int k = lane; k < a.kp; k += 32)                     // bf16 hi/lo operands of the tensor-core theta update
+      k3_pack_element(const_cast<const volatile float*>(fa), const_cast<const volatile float*>(fb), a.h + a.c, k,
+                      a.pm[(int64_t)i * a.kp + k], a.qm[(int64_t)i * a.kp + k]);
     rho = warp_sum(rho); kappa = warp_sum(kappa);
     if (lane == 0) a.cvec[i] = -(rho + kappa) / (2.f * a.deg[i]);          // both D^-1/2 factors depend on the row sum
   }
@@ -483,6 +492,7 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   E.partial = fbuf(B_PARTIAL); E.deg = fbuf(B_DEG); E.rs = fbuf(B_RS);
   E.p1 = fbuf(B_P1); E.z1 = fbuf(B_Z1); E.p2 = fbuf(B_P2); E.z2 = fbuf(B_Z2); E.dz2 = fbuf(B_DZ2); E.dp2 = fbuf(B_DP2);
   E.dz1 = fbuf(B_DZ1); E.dp1 = fbuf(B_DP1); E.fa = fbuf(B_FA); E.fb = fbuf(B_FB); E.ldf = L.ldf; E.cvec = fbuf(B_C);
+  E.pm = reinterpret_cast<__nv_bfloat16*>(buf(B_PM)); E.qm = reinterpret_cast<__nv_bfloat16*>(buf(B_QM)); E.kp = L.kp;
   E.w1 = A.w1; E.b1 = A.b1; E.y = A.y; E.mask = A.mask; E.inv_m = 1.0f / (float)A.mask_count;
   E.drop_h = dh; E.bt_hi = bt_hi; E.bt_lo = bt_lo; E.ldb = L.ldb;
   E.loss_part = fbuf(B_LOSSP); E.corr_part = fbuf(B_CORRP); E.nblk = L.nblk;
@@ -513,8 +523,11 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   profile_mark(stream, 6);
 
   if (A.update) {
-    rc = lds_k3k4_theta_update(A.theta_full, A.ld_theta, A.n, 0, A.n, fbuf(B_FA), fbuf(B_FB), L.ldf, A.h + A.c, fbuf(B_C),
-                               A.lr, A.opt_kind, A.adam_m, A.adam_v, A.beta1, A.beta2, A.eps, A.adam_t, nullptr, 0, 0u, stream_);
+    if (A.opt_kind == LDS_OPT_SGD && !(A.k3_flags & LDS_K3_SIMT))
+      rc = k3_launch_tc(A.theta_full, A.ld_theta, A.n, 0, A.n, buf(B_PM), buf(B_QM), L.kp, A.h + A.c, fbuf(B_C), A.lr, stream);
+    else
+      rc = lds_k3k4_theta_update(A.theta_full, A.ld_theta, A.n, 0, A.n, fbuf(B_FA), fbuf(B_FB), L.ldf, A.h + A.c, fbuf(B_C),
+                                 A.lr, A.opt_kind, A.adam_m, A.adam_v, A.beta1, A.beta2, A.eps, A.adam_t, nullptr, 0, 0u, stream_);
     if (rc != LDS_OK) return rc;
     profile_mark(stream, 7);
   }

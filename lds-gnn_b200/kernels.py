@@ -149,6 +149,19 @@ def k3k4_theta_update_(theta_full, n, fa, fb, cvec, lr, d=None, opt_kind=_lib.OP
     return theta_full
 
 
+def k3k4_theta_update_tc_(theta_full, n, fa, fb, cvec, lr, d=None, row0=0, rows=None):
+    """SGD update on the tcgen05 kernel (bf16 hi/lo-split factors, fp32 accumulation, TMA-streamed theta)."""
+    _lib.require_device()
+    rows = n - row0 if rows is None else rows
+    d = fa.shape[1] if d is None else d
+    need = int(_lib.load().lds_k3_workspace_bytes(n, d))
+    ws = _workspace(need, theta_full.device, "k3")
+    _lib.check(_lib.load().lds_k3k4_theta_update_tc(
+        _ptr(_f32(theta_full, "theta_full")), theta_full.stride(0), n, row0, rows, _ptr(_f32(fa, "fa")), _ptr(_f32(fb, "fb")),
+        fa.stride(0), d, _ptr(_f32(cvec, "cvec")), float(lr), _ptr(ws), need, _stream()), "lds_k3k4_theta_update_tc")
+    return theta_full
+
+
 def k3_dense_grad(n, fa, fb, cvec, d=None, out=None, accumulate=False, row0=0, rows=None):
     """grad[i][j] (+)= fa_i . fb_j + c_i (0 on the diagonal): dL/d(sample) of one propagate (composable path)."""
     _lib.require_device()
@@ -240,7 +253,7 @@ class OuterStep:
 
     def run(self, theta_full, lr, seed, step, dropout_p=0.0, update=True, u=None, keep_x=None, keep_h=None,
             opt_kind=_lib.OPT_SGD, adam_m=None, adam_v=None, betas=(0.9, 0.999), eps=1e-8, adam_t=1,
-            out_logp=None, k2_flags=0):
+            out_logp=None, k2_flags=0, k3_flags=0):
         """Enqueue one fused outer step on the current stream. Results: self.scalars[0:2] = (loss, acc)."""
         a = self.args
         a.struct_bytes = ctypes.sizeof(_lib.OuterStepArgs)
@@ -268,6 +281,6 @@ class OuterStep:
         a.out_scalars = self.scalars.data_ptr()
         a.out_logp = None if out_logp is None else out_logp.data_ptr()
         a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws_bytes
-        a.k2_flags, a.reserved = int(k2_flags), 0
+        a.k2_flags, a.k3_flags = int(k2_flags), int(k3_flags)
         _lib.check(self.lib.lds_outer_step(ctypes.byref(a), _stream()), "lds_outer_step")
         return self.scalars

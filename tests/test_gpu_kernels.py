@@ -212,6 +212,45 @@ def test_k3k4_sgd_update_matches_closed_form_and_stays_symmetric(K, n, d):
     assert np.abs(out - ref).max() < 1e-5
 
 
+@pytest.mark.parametrize("n,d,rows0", [(64, 23, None), (130, 23, None), (257, 71, None), (1000, 22, None), (2708, 23, None),
+                                       (700, 5, None), (1000, 22, (256, 384))])
+def test_k3k4_tensor_core_update_matches_closed_form_and_is_exactly_symmetric(K, n, d, rows0):
+    rng = np.random.default_rng(n * 13 + d)
+    th = random_theta(rng, n, "outside" if n == 130 else "mixed")
+    fa = (rng.standard_normal((n, d)) * 0.1).astype(np.float32)
+    fb = (rng.standard_normal((n, d)) * 0.1).astype(np.float32)
+    cv = (rng.standard_normal(n) * 0.01).astype(np.float32)
+    lr = 0.7
+    full = K.theta_triu_to_full(dev(th))
+    before = full.clone()
+    fa64, fb64, c64 = fa.astype(np.float64), fb.astype(np.float64), cv.astype(np.float64)
+    g = fa64 @ fb64.T + fb64 @ fa64.T + c64[:, None] + c64[None, :]
+    np.fill_diagonal(g, 0.0)
+    th_full = before[:, :n].double().cpu().numpy()
+    g = g * ((th_full >= 0) & (th_full <= 1))
+    ref = np.clip(th_full - lr * g, 0, 1)
+    if rows0 is None:
+        K.k3k4_theta_update_tc_(full, n, dev(fa), dev(fb), dev(cv), lr)
+        out = full[:, :n].cpu().numpy()
+        assert np.array_equal(out, out.T), "tensor-core update must keep theta exactly symmetric"
+        assert np.abs(out - ref).max() < 2e-6 + 1e-5 * lr * np.abs(g).max()
+        assert torch.equal(full[:, n:], before[:, n:])                     # padding untouched
+        # agrees with the CUDA-core kernel
+        simt = before.clone()
+        K.k3k4_theta_update_(simt, n, dev(fa), dev(fb), dev(cv), lr)
+        assert (simt[:, :n] - full[:, :n]).abs().max().item() < 2e-6
+    else:                                                                  # a row-block shard (multi-GPU layout)
+        r0, r = rows0
+        shard = full[r0:r0 + r]
+        K.k3k4_theta_update_tc_(shard, n, dev(fa), dev(fb), dev(cv), lr, row0=r0, rows=r)
+        out = full[:, :n].cpu().numpy()
+        assert np.abs(out[r0:r0 + r] - ref[r0:r0 + r]).max() < 2e-6 + 1e-5 * lr * np.abs(g).max()
+        assert np.array_equal(out[:r0], th_full[:r0].astype(np.float32)) and np.array_equal(out[r0 + r:], th_full[r0 + r:].astype(np.float32))
+        whole = before.clone()
+        K.k3k4_theta_update_tc_(whole, n, dev(fa), dev(fb), dev(cv), lr)
+        assert torch.equal(whole[r0:r0 + r], full[r0:r0 + r])              # shard result == the same rows of the full update, bitwise
+
+
 def test_k3_dense_grad_mode(K):
     n, d = 130, 23
     rng = np.random.default_rng(1)
