@@ -38,8 +38,8 @@ import torch
 METRIC = "lds_outer_steps_per_sec"
 UNIT = "steps/s"
 KERNEL_NAMES = {0: "k1_sample_normalize", 1: "feat_linear", 2: "k2_mma_tcgen05", 3: "epi_layer1", 4: "epi_layer2",
-                5: "epi_bwd2", 6: "epi_bwd1", 7: "k3k4_theta_update"}
-LAUNCHES_PER_STEP = 11      # K1, feature GEMM, 4 x K2, 4 row epilogues, K3+K4 (csrc/lds_outer_step.cu)
+                5: "epi_bwd2", 6: "epi_bwd1", 7: "k3k4_theta_update", 8: "stage_w0"}
+LAUNCHES_PER_STEP = 12      # weight staging, K1, feature GEMM, 4 x K2, 4 row epilogues, K3+K4 (csrc/lds_outer_step.cu)
 HYPER = dict(lr=0.1, lr_decay=0.99, dropout=0.5)            # configs/seml/final/lds.yaml:18-110
 
 
@@ -221,13 +221,22 @@ def run_ours(args, rank, world, device):
     outer = OuterProblemTrainer(optimizer=opt, data=data, opt_mask=opt_mask, model=model, smoothness_factor=0.0,
                                 disconnection_factor=0.0, sparsity_factor=0.0, regularize=False,
                                 lr_decay=HYPER["lr_decay"], pretrain=False)
-    host_w = {k: v.clone().pin_memory() for k, v in weights.items()}
     names = {"w0": "layer_in.fc.weight", "b0": "layer_in.fc.bias", "w1": "layer_out.fc.weight", "b1": "layer_out.fc.bias"}
-    h2d_bytes = sum(v.numel() * 4 for v in host_w.values())
+    # The step's inputs are the current GCN (fast) weights: one flat pinned host buffer, one flat device buffer whose
+    # slices ARE the fast-weight tensors handed to the trainer, one host->device copy per step.
+    total = sum(v.numel() for v in weights.values())
+    host_flat = torch.empty(total, dtype=torch.float32).pin_memory()
+    dev_flat = torch.empty(total, dtype=torch.float32, device=device)
+    off = 0
+    for k, pname in names.items():
+        cnt = weights[k].numel()
+        host_flat[off:off + cnt].copy_(weights[k].reshape(-1))
+        inner.model_params[pname] = dev_flat[off:off + cnt].view(weights[k].shape)
+        off += cnt
+    h2d_bytes = total * 4
 
     def api_step():
-        for k, pname in names.items():                     # this step's fast weights: pinned host -> device
-            inner.model_params[pname].data.copy_(host_w[k], non_blocking=True)
+        dev_flat.copy_(host_flat, non_blocking=True)       # this step's fast weights: pinned host -> device
         return outer.train_step(inner.model_forward)       # returns host floats (device -> host read inside)
 
     for _ in range(args.warmup):

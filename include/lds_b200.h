@@ -136,9 +136,9 @@ typedef struct lds_outer_step_args {
   const int32_t* x_crow;      /* optional CSR copy of x: [n+1] row offsets, [nnz] columns, [nnz] values.      */
   const int32_t* x_col;       /* Bag-of-words features are ~1% dense; with CSR the feature GEMM gathers rows  */
   const float*   x_val;       /* of w0t instead of streaming N x F zeros. Same result for any x.              */
-  const float*   w0t;         /* [f][h] contiguous = w0 transposed; required when x_crow is given             */
-  const float*   w0;          /* [h][ld_w0] fp32 (layer_in.fc.weight), ld_w0 % 4 == 0                   */
-  int64_t  ld_w0;
+  const float*   reserved_ptr; /* must be NULL                                                                */
+  const float*   w0;          /* [h][ld_w0] fp32 (layer_in.fc.weight), any ld_w0 >= f: staged (padded or      */
+  int64_t  ld_w0;             /* transposed) into the workspace by the first kernel of the step               */
   const float*   b0;          /* [h]                                                                    */
   const float*   w1;          /* [c][h] contiguous (layer_out.fc.weight)                                */
   const float*   b1;          /* [c]                                                                    */
@@ -173,7 +173,7 @@ int64_t lds_outer_step_factor_ld(int32_t h, int32_t c);
  * lds_outer_step records a CUDA event on its stream after every kernel launch. lds_profile_end synchronises on
  * the last event and returns the number of intervals written: ms_out[i] = device time of the launch whose id is
  * ids_out[i] (host, both arrays of capacity `cap`). ids: 0 K1, 1 feature GEMM, 2 K2 (tcgen05), 3 epi_layer1,
- * 4 epi_layer2, 5 epi_bwd2, 6 epi_bwd1, 7 K3+K4. Not graph-capturable while active. */
+ * 4 epi_layer2, 5 epi_bwd2, 6 epi_bwd1, 7 K3+K4, 8 weight staging. Not graph-capturable while active. */
 int32_t lds_profile_begin(void);
 int32_t lds_profile_end(float* ms_out, int32_t* ids_out, int32_t cap);
 

@@ -55,7 +55,7 @@ class OuterStepArgs(Structure):
         ("n", c_int32), ("f", c_int32), ("h", c_int32), ("c", c_int32),
         ("theta_full", c_void_p), ("ld_theta", c_int64),
         ("x", c_void_p), ("ld_x", c_int64),
-        ("x_crow", c_void_p), ("x_col", c_void_p), ("x_val", c_void_p), ("w0t", c_void_p),
+        ("x_crow", c_void_p), ("x_col", c_void_p), ("x_val", c_void_p), ("reserved_ptr", c_void_p),
         ("w0", c_void_p), ("ld_w0", c_int64),
         ("b0", c_void_p), ("w1", c_void_p), ("b1", c_void_p),
         ("y", c_void_p), ("mask", c_void_p),

@@ -100,8 +100,74 @@ __global__ void stats_kernel(const float* __restrict__ full, int64_t ld, int n, 
 // K1
 // ------------------------------------------------------------------------------------------------
 constexpr int K1_THREADS = 256;
+constexpr int K1_UNROLL = 4;      // column quads per thread per trip: 8 x 16-byte loads in flight per thread
+
+// Processes one column quad (4 columns) of the row pair (2p, 2p+1): draws, compares, self loops, A_tilde store.
+template <bool EXPLICIT_U>
+__device__ __forceinline__ void k1_quad(int j0, const float (&th0)[4], const float (&th1)[4], int p, int gi0, int gi1, int li0, int li1,
+                                        bool has1, int n, const PhiloxKey& key, const float* __restrict__ U, int64_t ldu,
+                                        __nv_bfloat16* __restrict__ A, int64_t lda, float* __restrict__ S, int64_t lds_,
+                                        float& sum0, float& sum1) {
+  float u0[4], u1[4];
+  if (EXPLICIT_U) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = j0 + e;
+      u0[e] = 2.f; u1[e] = 2.f;
+      if (j < n) {
+        u0[e] = (gi0 <= j) ? U[(int64_t)gi0 * ldu + j] : U[(int64_t)j * ldu + gi0];
+        if (has1) u1[e] = (gi1 <= j) ? U[(int64_t)gi1 * ldu + j] : U[(int64_t)j * ldu + gi1];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {                     // two 2x2 blocks: column blocks q = j0/2 + b
+      const int q = (j0 >> 1) + b;
+      const bool upper = p <= q;                      // canonical block = (min, max): counter (c0 = max block, c1 = min block)
+      uint32_t w[4];
+      philox4x32_10((uint32_t)(upper ? q : p), (uint32_t)(upper ? p : q), key, w);
+      // word = 2*(a%2) + (b%2) of the canonical pair (a, b) = (min, max): [di][dj] for rows (2p, 2p+1) x cols (2q, 2q+1)
+      const uint32_t w01 = (p < q) ? w[1] : ((p > q) ? w[2] : w[1]);
+      const uint32_t w10 = (p < q) ? w[2] : ((p > q) ? w[1] : w[1]);
+      u0[2 * b] = philox_to_uniform(w[0]); u0[2 * b + 1] = philox_to_uniform(w01);
+      u1[2 * b] = philox_to_uniform(w10);  u1[2 * b + 1] = philox_to_uniform(w[3]);
+    }
+  }
+  float s0[4], s1[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const bool in = (j0 + e) < n;
+    s0[e] = (in && u0[e] < fminf(fmaxf(th0[e], 0.f), 1.f)) ? 1.f : 0.f;
+    s1[e] = (in && has1 && u1[e] < fminf(fmaxf(th1[e], 0.f), 1.f)) ? 1.f : 0.f;
+  }
+  if (S != nullptr) {                               // raw sample incl. the sampled diagonal
+#pragma unroll
+    for (int e = 0; e < 4; ++e) if (j0 + e < n) {
+      S[(int64_t)li0 * lds_ + j0 + e] = s0[e];
+      if (has1) S[(int64_t)li1 * lds_ + j0 + e] = s1[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {                     // self loops: diag := 1 (src/utils/graph.py:131-132)
+    if (j0 + e == gi0) s0[e] = 1.f;
+    if (j0 + e == gi1 && has1) s1[e] = 1.f;
+    sum0 += s0[e]; sum1 += s1[e];
+  }
+  if (A != nullptr) {
+    __nv_bfloat162 a01 = __floats2bfloat162_rn(s0[0], s0[1]), a23 = __floats2bfloat162_rn(s0[2], s0[3]);
+    uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&a01); pk.y = *reinterpret_cast<uint32_t*>(&a23);
+    *reinterpret_cast<uint2*>(A + (int64_t)li0 * lda + j0) = pk;
+    if (has1) {
+      __nv_bfloat162 b01 = __floats2bfloat162_rn(s1[0], s1[1]), b23 = __floats2bfloat162_rn(s1[2], s1[3]);
+      uint2 pk1; pk1.x = *reinterpret_cast<uint32_t*>(&b01); pk1.y = *reinterpret_cast<uint32_t*>(&b23);
+      *reinterpret_cast<uint2*>(A + (int64_t)li1 * lda + j0) = pk1;
+    }
+  }
+}
 
 // One CTA per global row pair (2p, 2p+1). A thread owns column quads; each quad = two 2x2 Philox blocks.
+// All of a trip's 128-bit loads are issued before the first is consumed: the kernel is bound by memory-level
+// parallelism (each quad costs ~200 ALU instructions after its load), not by issue slots.
 template <bool EXPLICIT_U>
 __global__ void __launch_bounds__(K1_THREADS)
 k1_sample_kernel(const float* __restrict__ theta, int64_t ldt, int n, int row0, int rows,
@@ -117,73 +183,28 @@ k1_sample_kernel(const float* __restrict__ theta, int64_t ldt, int n, int row0, 
   const int ncols = (A != nullptr) ? (int)lda : ((n + 3) & ~3);      // cover A's padding so it is zeroed
   float sum0 = 0.f, sum1 = 0.f;
 
-  for (int j0 = 4 * threadIdx.x; j0 < ncols; j0 += 4 * K1_THREADS) {
-    float th0[4] = {0.f, 0.f, 0.f, 0.f}, th1[4] = {0.f, 0.f, 0.f, 0.f};
-    if (j0 + 3 < n) {
-      const float4 v0 = *reinterpret_cast<const float4*>(t0 + j0);
-      th0[0] = v0.x; th0[1] = v0.y; th0[2] = v0.z; th0[3] = v0.w;
-      if (has1) { const float4 v1 = *reinterpret_cast<const float4*>(t1 + j0);
-                  th1[0] = v1.x; th1[1] = v1.y; th1[2] = v1.z; th1[3] = v1.w; }
-    } else {
+  for (int base = 4 * threadIdx.x; base < ncols; base += 4 * K1_THREADS * K1_UNROLL) {
+    float th0[K1_UNROLL][4], th1[K1_UNROLL][4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) if (j0 + e < n) { th0[e] = t0[j0 + e]; if (has1) th1[e] = t1[j0 + e]; }
-    }
-    float u0[4], u1[4];
-    if (EXPLICIT_U) {
+    for (int u = 0; u < K1_UNROLL; ++u) {
+      const int j0 = base + u * 4 * K1_THREADS;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int j = j0 + e;
-        u0[e] = 2.f; u1[e] = 2.f;
-        if (j < n) {
-          u0[e] = (gi0 <= j) ? U[(int64_t)gi0 * ldu + j] : U[(int64_t)j * ldu + gi0];
-          if (has1) u1[e] = (gi1 <= j) ? U[(int64_t)gi1 * ldu + j] : U[(int64_t)j * ldu + gi1];
-        }
-      }
-    } else {
+      for (int e = 0; e < 4; ++e) { th0[u][e] = 0.f; th1[u][e] = 0.f; }
+      if (j0 + 3 < n) {
+        const float4 v0 = *reinterpret_cast<const float4*>(t0 + j0);
+        th0[u][0] = v0.x; th0[u][1] = v0.y; th0[u][2] = v0.z; th0[u][3] = v0.w;
+        if (has1) { const float4 v1 = *reinterpret_cast<const float4*>(t1 + j0);
+                    th1[u][0] = v1.x; th1[u][1] = v1.y; th1[u][2] = v1.z; th1[u][3] = v1.w; }
+      } else if (j0 < n) {
 #pragma unroll
-      for (int b = 0; b < 2; ++b) {                   // two column blocks q = j0/2 + b
-        const int q = (j0 >> 1) + b;
-        uint32_t w[4];
-        if (p <= q) philox4x32_10((uint32_t)q, (uint32_t)p, key, w);     // canonical block (p, q): word = 2*di + dj
-        else        philox4x32_10((uint32_t)p, (uint32_t)q, key, w);     // mirrored block (q, p): word = 2*dj + di
-        uint32_t w00, w01, w10, w11;                  // [di][dj] for rows (2p, 2p+1) x cols (2q, 2q+1)
-        if (p < q)      { w00 = w[0]; w01 = w[1]; w10 = w[2]; w11 = w[3]; }
-        else if (p > q) { w00 = w[0]; w01 = w[2]; w10 = w[1]; w11 = w[3]; }
-        else            { w00 = w[0]; w01 = w[1]; w10 = w[1]; w11 = w[3]; }
-        u0[2 * b] = philox_to_uniform(w00); u0[2 * b + 1] = philox_to_uniform(w01);
-        u1[2 * b] = philox_to_uniform(w10); u1[2 * b + 1] = philox_to_uniform(w11);
-      }
-    }
-    float s0[4], s1[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int j = j0 + e;
-      const bool in = j < n;
-      s0[e] = (in && u0[e] < fminf(fmaxf(th0[e], 0.f), 1.f)) ? 1.f : 0.f;
-      s1[e] = (in && has1 && u1[e] < fminf(fmaxf(th1[e], 0.f), 1.f)) ? 1.f : 0.f;
-    }
-    if (S != nullptr) {                               // raw sample incl. the sampled diagonal
-#pragma unroll
-      for (int e = 0; e < 4; ++e) if (j0 + e < n) {
-        S[(int64_t)li0 * lds_ + j0 + e] = s0[e];
-        if (has1) S[(int64_t)li1 * lds_ + j0 + e] = s1[e];
+        for (int e = 0; e < 4; ++e) if (j0 + e < n) { th0[u][e] = t0[j0 + e]; if (has1) th1[u][e] = t1[j0 + e]; }
       }
     }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {                     // self loops: diag := 1 (src/utils/graph.py:131-132)
-      if (j0 + e == gi0) s0[e] = 1.f;
-      if (j0 + e == gi1 && has1) s1[e] = 1.f;
-      sum0 += s0[e]; sum1 += s1[e];
-    }
-    if (A != nullptr && j0 < (int)lda) {
-      __nv_bfloat162 a01 = __floats2bfloat162_rn(s0[0], s0[1]), a23 = __floats2bfloat162_rn(s0[2], s0[3]);
-      uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&a01); pk.y = *reinterpret_cast<uint32_t*>(&a23);
-      *reinterpret_cast<uint2*>(A + (int64_t)li0 * lda + j0) = pk;
-      if (has1) {
-        __nv_bfloat162 b01 = __floats2bfloat162_rn(s1[0], s1[1]), b23 = __floats2bfloat162_rn(s1[2], s1[3]);
-        uint2 pk1; pk1.x = *reinterpret_cast<uint32_t*>(&b01); pk1.y = *reinterpret_cast<uint32_t*>(&b23);
-        *reinterpret_cast<uint2*>(A + (int64_t)li1 * lda + j0) = pk1;
-      }
+    for (int u = 0; u < K1_UNROLL; ++u) {
+      const int j0 = base + u * 4 * K1_THREADS;
+      if (j0 < ncols)
+        k1_quad<EXPLICIT_U>(j0, th0[u], th1[u], p, gi0, gi1, li0, li1, has1, n, key, U, ldu, A, lda, S, lds_, sum0, sum1);
     }
   }
   // block reduction of the two row sums (integers in fp32: exact, order-independent for N < 2^24)

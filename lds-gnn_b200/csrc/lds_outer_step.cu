@@ -26,7 +26,7 @@ constexpr int EPI_THREADS = 1024;   // 32 warps, one row each: the epilogues are
 constexpr int FEAT_THREADS = 256;   // dense feature GEMM: 8 warps x 4 rows
 constexpr int EPI_MAXW = 128;       // widest operand
 
-enum { B_A = 0, B_DEG, B_RS, B_P1, B_Z1, B_P2, B_Z2, B_DZ2, B_DP2, B_DZ1, B_DP1, B_FA, B_FB, B_C, B_BTHI, B_BTLO, B_PARTIAL, B_LOSSP, B_CORRP, B_PM, B_QM, B_END };
+enum { B_A = 0, B_DEG, B_RS, B_P1, B_Z1, B_P2, B_Z2, B_DZ2, B_DP2, B_DZ1, B_DP1, B_FA, B_FB, B_C, B_BTHI, B_BTLO, B_PARTIAL, B_LOSSP, B_CORRP, B_PM, B_QM, B_W0S, B_END };
 struct OuterLayout {
   int n, f, h, c, hp1, hp2, hpmax, nblk, kp;
   int64_t lda, ldb, ldf;
@@ -55,6 +55,7 @@ static bool make_layout(int n, int f, int h, int c, OuterLayout& L) {
   bytes[B_LOSSP] = bytes[B_CORRP] = (int64_t)L.nblk * 4;
   L.kp = k3_padded_k(h + c);
   bytes[B_PM] = bytes[B_QM] = (int64_t)n * L.kp * 2;
+  bytes[B_W0S] = (int64_t)h * round_up(f, 4) * 4;          // staged layer_in weight: transposed [f][h] (CSR path) or padded [h][ldx]
   int64_t o = 0;
   for (int b = 0; b < B_END; ++b) { L.off[b] = o; o += round_up(bytes[b], 1024); }
   L.total = o;
@@ -86,6 +87,30 @@ __device__ __forceinline__ void store_operand_tile(const float (*tile)[EPI_ROWS 
     split_bf16(tile[c][lane], hi, lo);
     bt_hi[(int64_t)c * ldb + i] = hi;
     bt_lo[(int64_t)c * ldb + i] = lo;
+  }
+}
+
+// Stage layer_in.fc.weight [h][ldw] for the feature kernels: transposed [f][h] (CSR path: one contiguous row per
+// non-zero) or zero-padded [h][ldp] with 16-byte rows (dense path). Tiled through shared memory, coalesced both ways.
+__global__ void stage_w0_kernel(const float* __restrict__ w0, int64_t ldw, int h, int f, float* __restrict__ out, int64_t ldp, int transpose) {
+  __shared__ float tile[32][33];
+  const int f0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 256 threads
+  for (int r = ty; r < 32; r += 8) {
+    const int o = o0 + r, ff = f0 + tx;
+    tile[r][tx] = (o < h && ff < f) ? w0[(int64_t)o * ldw + ff] : 0.f;
+  }
+  __syncthreads();
+  if (transpose) {
+    for (int r = ty; r < 32; r += 8) {
+      const int ff = f0 + r, o = o0 + tx;
+      if (ff < f && o < h) out[(int64_t)ff * h + o] = tile[tx][r];
+    }
+  } else {
+    for (int r = ty; r < 32; r += 8) {
+      const int o = o0 + r, ff = f0 + tx;
+      if (o < h && ff < (int)ldp) out[(int64_t)o * ldp + ff] = tile[r][tx];
+    }
   }
 }
 
@@ -204,14 +229,24 @@ feat_sparse_kernel(const int32_t* __restrict__ crow, const int32_t* __restrict__
         if (dc.p > 0.f) v = drop_keep(dc, i, col, f) ? v * dc.scale : 0.f;
       }
       const int cnt = min(32, end - base);
-      for (int j = 0; j < cnt; ++j) {
-        const float vj = __shfl_sync(0xffffffffu, v, j);
-        const int cj = __shfl_sync(0xffffffffu, col, j);
-        if (vj != 0.f) {                                        // warp-uniform
-          const float* wrow = w0t + (int64_t)cj * h;
+      for (int j = 0; j < cnt; j += 8) {                        // 8 non-zeros per trip: their w0t rows are loaded together
+        float vj[8], wv[8][4];
+        int cj[8];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) { const int o = lane + 32 * t; if (o < h) acc[t] = fmaf(vj, wrow[o], acc[t]); }
+        for (int u = 0; u < 8; ++u) {                           // lanes past `cnt` hold v = 0, col = 0: harmless
+          vj[u] = __shfl_sync(0xffffffffu, v, (j + u) & 31);
+          cj[u] = __shfl_sync(0xffffffffu, col, (j + u) & 31);
         }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float* wrow = w0t + (int64_t)cj[u] * h;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) { const int o = lane + 32 * t; wv[u][t] = (o < h && j + u < cnt) ? wrow[o] : 0.f; }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int t = 0; t < 4; ++t) acc[t] = fmaf(vj[u], wv[u][t], acc[t]);
       }
     }
     const float ri = rs[i];
@@ -439,15 +474,16 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   const lds_outer_step_args& A = *args;
   OuterLayout L;
   if (!make_layout(A.n, A.f, A.h, A.c, L)) { set_error("lds_outer_step: unsupported shape n=%d f=%d h=%d c=%d (h, c must be in [1,128])", A.n, A.f, A.h, A.c); return LDS_ERR_UNSUPPORTED; }
-  LDS_CHECK_ARG(A.theta_full && A.b0 && A.w1 && A.b1 && A.y && A.mask && A.out_scalars, "lds_outer_step: null pointer");
+  LDS_CHECK_ARG(A.theta_full && A.w0 && A.b0 && A.w1 && A.b1 && A.y && A.mask && A.out_scalars, "lds_outer_step: null pointer");
+  LDS_CHECK_ARG(A.ld_w0 >= A.f, "lds_outer_step: ld_w0 must be >= f");
   LDS_CHECK_ARG(A.ld_theta >= A.n && A.ld_theta % 4 == 0, "lds_outer_step: ld_theta must be >= n and a multiple of 4");
   const bool sparse_x = A.x_crow != nullptr;
   if (sparse_x) {
-    LDS_CHECK_ARG(A.x_col && A.x_val && A.w0t, "lds_outer_step: the CSR feature path needs x_col, x_val and w0t");
+    LDS_CHECK_ARG(A.x_col && A.x_val, "lds_outer_step: the CSR feature path needs x_col and x_val");
   } else {
-    LDS_CHECK_ARG(A.x && A.w0, "lds_outer_step: null pointer (x / w0)");
-    LDS_CHECK_ARG(A.ld_x >= A.f && A.ld_x % 4 == 0 && A.ld_w0 >= A.f && A.ld_w0 % 4 == 0, "lds_outer_step: ld_x / ld_w0 must be >= f and multiples of 4 (zero padded)");
-    LDS_CHECK_ARG((reinterpret_cast<uintptr_t>(A.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(A.w0) & 15) == 0, "lds_outer_step: x and w0 must be 16-byte aligned");
+    LDS_CHECK_ARG(A.x, "lds_outer_step: null pointer (x)");
+    LDS_CHECK_ARG(A.ld_x == round_up(A.f, 4), "lds_outer_step: dense x must be zero padded to ld_x == round_up(f, 4)");
+    LDS_CHECK_ARG((reinterpret_cast<uintptr_t>(A.x) & 15) == 0, "lds_outer_step: x must be 16-byte aligned");
   }
   LDS_CHECK_ARG(A.mask_count > 0, "lds_outer_step: mask_count must be positive");
   LDS_CHECK_ARG(A.dropout_p >= 0.f && A.dropout_p < 1.f, "lds_outer_step: dropout_p must be in [0, 1)");
@@ -459,6 +495,13 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
 
   int32_t rc;
   profile_mark(stream, -1);
+  {   // stage the layer_in weight (tiny; independent of K1)
+    const int64_t ldp = round_up(A.f, 4);
+    dim3 sgrid((unsigned)ceil_div(ldp, 32), (unsigned)ceil_div(A.h, 32));
+    stage_w0_kernel<<<sgrid, 256, 0, stream>>>(A.w0, A.ld_w0, A.h, A.f, fbuf(B_W0S), ldp, sparse_x ? 1 : 0);
+    LDS_CHECK_LAUNCH("stage_w0_kernel");
+    profile_mark(stream, 8);
+  }
   // K1
   rc = lds_k1_sample_normalize(A.theta_full, A.ld_theta, A.n, 0, A.n, A.seed, A.step, 0, A.u_explicit, A.ld_u,
                                buf(B_A), L.lda, nullptr, 0, fbuf(B_DEG), fbuf(B_RS), A.u_explicit ? LDS_K1_EXPLICIT_U : 0u, stream_);
@@ -479,10 +522,10 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   const dim3 egrid((unsigned)L.nblk);
 
   if (sparse_x) {
-    feat_sparse_kernel<<<egrid, EPI_THREADS, 0, stream>>>(A.x_crow, A.x_col, A.x_val, A.n, A.f, A.w0t, A.b0, A.h, dx, fbuf(B_RS), fbuf(B_P1), bt_hi, bt_lo, L.ldb, L.hp1);
+    feat_sparse_kernel<<<egrid, EPI_THREADS, 0, stream>>>(A.x_crow, A.x_col, A.x_val, A.n, A.f, fbuf(B_W0S), A.b0, A.h, dx, fbuf(B_RS), fbuf(B_P1), bt_hi, bt_lo, L.ldb, L.hp1);
     LDS_CHECK_LAUNCH("feat_sparse_kernel");
   } else {
-    feat_linear_kernel<<<egrid, FEAT_THREADS, 0, stream>>>(A.x, A.ld_x, A.n, A.f, A.w0, A.ld_w0, A.b0, A.h, dx, fbuf(B_RS), fbuf(B_P1), bt_hi, bt_lo, L.ldb, L.hp1);
+    feat_linear_kernel<<<egrid, FEAT_THREADS, 0, stream>>>(A.x, A.ld_x, A.n, A.f, fbuf(B_W0S), round_up(A.f, 4), A.b0, A.h, dx, fbuf(B_RS), fbuf(B_P1), bt_hi, bt_lo, L.ldb, L.hp1);
     LDS_CHECK_LAUNCH("feat_linear_kernel");
   }
   profile_mark(stream, 1);

@@ -195,19 +195,15 @@ class OuterStep:
         self.x[:, :self.f] = x
         nnz = int((x != 0).sum().item())
         self.sparse = (nnz < self.SPARSE_DENSITY * x.numel()) if sparse_features is None else bool(sparse_features)
-        self.x_crow = self.x_col = self.x_val = self.w0t = None
+        self.x_crow = self.x_col = self.x_val = None
         if self.sparse:                                     # one-off layout conversion of static data (setup, not hot path)
             csr = x.detach().to(torch.float32).to_sparse_csr()
             self.x_crow = csr.crow_indices().to(torch.int32).contiguous()
             self.x_col = csr.col_indices().to(torch.int32).contiguous()
             self.x_val = csr.values().to(torch.float32).contiguous()
-            self.w0t = torch.zeros((self.f, int(hidden)), dtype=torch.float32, device=dev)
         self.y = y.to(device=dev, dtype=torch.int64).contiguous()
         self.set_mask(mask)
-        self.w0 = torch.zeros((self.h, self.ld_x), dtype=torch.float32, device=dev)       # staging, zero-padded
-        self.b0 = torch.zeros(self.h, dtype=torch.float32, device=dev)
-        self.w1 = torch.zeros((self.c, self.h), dtype=torch.float32, device=dev)
-        self.b1 = torch.zeros(self.c, dtype=torch.float32, device=dev)
+        self.w0 = self.b0 = self.w1 = self.b1 = None         # references to the caller's current GCN weights
         nbytes = int(self.lib.lds_outer_step_workspace_bytes(self.n, self.f, self.h, self.c))
         if nbytes < 0:
             raise ValueError(f"unsupported shape n={n} f={self.f} h={hidden} c={classes}")
@@ -224,14 +220,15 @@ class OuterStep:
         self.mask_count = int(m.sum().item())
 
     def set_weights(self, w0, b0, w1, b1):
-        """Copy the current GCN (fast) weights into the fixed, padded staging buffers."""
-        if self.sparse:
-            self.w0t.copy_(w0.detach().t())
-        else:
-            self.w0[:, :self.f].copy_(w0.detach())
-        self.b0.copy_(b0.detach())
-        self.w1.copy_(w1.detach())
-        self.b1.copy_(b1.detach())
+        """Use these GCN (fast) weights for the next steps. No copies: the step's first kernel stages the layer_in
+        weight (padded / transposed) inside the workspace; the other three are read in place."""
+        def prep(t, shape):
+            t = t.detach()
+            if t.dtype != torch.float32 or not t.is_cuda or tuple(t.shape) != shape:
+                raise TypeError(f"GCN weight of shape {tuple(t.shape)} / {t.dtype}: expected CUDA float32 {shape}")
+            return t if t.is_contiguous() else t.contiguous()
+        self.w0, self.b0 = prep(w0, (self.h, self.f)), prep(b0, (self.h,))
+        self.w1, self.b1 = prep(w1, (self.c, self.h)), prep(b1, (self.c,))
 
     def buffer(self, name):
         """View of an intermediate buffer of the last step (tests / composable path)."""
@@ -261,11 +258,11 @@ class OuterStep:
         a.theta_full, a.ld_theta = theta_full.data_ptr(), theta_full.stride(0)
         a.x, a.ld_x = self.x.data_ptr(), self.ld_x
         if self.sparse:
-            a.x_crow, a.x_col, a.x_val, a.w0t = (self.x_crow.data_ptr(), self.x_col.data_ptr(), self.x_val.data_ptr(),
-                                                 self.w0t.data_ptr())
+            a.x_crow, a.x_col, a.x_val = self.x_crow.data_ptr(), self.x_col.data_ptr(), self.x_val.data_ptr()
         else:
-            a.x_crow = a.x_col = a.x_val = a.w0t = None
-        a.w0, a.ld_w0 = self.w0.data_ptr(), self.ld_x
+            a.x_crow = a.x_col = a.x_val = None
+        a.reserved_ptr = None
+        a.w0, a.ld_w0 = self.w0.data_ptr(), self.f
         a.b0, a.w1, a.b1 = self.b0.data_ptr(), self.w1.data_ptr(), self.b1.data_ptr()
         a.y, a.mask, a.mask_count = self.y.data_ptr(), self.mask.data_ptr(), self.mask_count
         a.dropout_p = float(dropout_p)
