@@ -37,9 +37,10 @@ import torch
 
 METRIC = "lds_outer_steps_per_sec"
 UNIT = "steps/s"
-KERNEL_NAMES = {0: "k1_sample_normalize", 1: "feat_linear", 2: "k2_mma_tcgen05", 3: "epi_layer1", 4: "epi_layer2",
-                5: "epi_bwd2", 6: "epi_bwd1", 7: "k3k4_theta_update", 8: "stage_w0"}
-LAUNCHES_PER_STEP = 12      # weight staging, K1, feature GEMM, 4 x K2, 4 row epilogues, K3+K4 (csrc/lds_outer_step.cu)
+KERNEL_NAMES = {0: "k1_sample_normalize", 1: "feat_linear", 3: "k2_layer1", 4: "k2_layer2", 5: "k2_bwd2", 6: "k2_bwd1",
+                7: "k3k4_theta_update", 8: "stage_w0"}
+K2_IDS = (3, 4, 5, 6)       # the four tcgen05 propagations (each with its fused row epilogue)
+LAUNCHES_PER_STEP = 8       # weight staging, K1, feature GEMM, 4 x K2 (+ fused row epilogue), K3+K4 (csrc/lds_outer_step.cu)
 HYPER = dict(lr=0.1, lr_decay=0.99, dropout=0.5)            # configs/seml/final/lds.yaml:18-110
 
 
@@ -129,7 +130,7 @@ def make_workload(name, seed=0):
 
 def algorithmic_bytes(shape):
     n, f = shape["n"], shape["f"]
-    per_kernel = {0: 6 * n * n, 2: 2 * n * n, 7: 8 * n * n, 1: 4 * n * f}
+    per_kernel = {0: 6 * n * n, 3: 2 * n * n, 4: 2 * n * n, 5: 2 * n * n, 6: 2 * n * n, 7: 8 * n * n}
     step = 6 * n * n + 4 * 2 * n * n + 8 * n * n + 4 * n * f            # the outer step reads X once (no dW)
     return per_kernel, step
 

@@ -172,8 +172,8 @@ int64_t lds_outer_step_factor_ld(int32_t h, int32_t c);
 /* ---- measurement hook for bench.py (not part of the reference-facing surface). Between begin and end,
  * lds_outer_step records a CUDA event on its stream after every kernel launch. lds_profile_end synchronises on
  * the last event and returns the number of intervals written: ms_out[i] = device time of the launch whose id is
- * ids_out[i] (host, both arrays of capacity `cap`). ids: 0 K1, 1 feature GEMM, 2 K2 (tcgen05), 3 epi_layer1,
- * 4 epi_layer2, 5 epi_bwd2, 6 epi_bwd1, 7 K3+K4, 8 weight staging. Not graph-capturable while active. */
+ * ids_out[i] (host, both arrays of capacity `cap`). ids: 0 K1, 1 feature GEMM, 3/4/5/6 the four K2 propagations
+ * (layer 1, layer 2, backward 2, backward 1, each with its fused row epilogue), 7 K3+K4, 8 weight staging. Not graph-capturable while active. */
 int32_t lds_profile_begin(void);
 int32_t lds_profile_end(float* ms_out, int32_t* ids_out, int32_t cap);
 

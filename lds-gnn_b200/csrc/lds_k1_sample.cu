@@ -102,6 +102,34 @@ __global__ void stats_kernel(const float* __restrict__ full, int64_t ld, int n, 
 constexpr int K1_THREADS = 256;
 constexpr int K1_UNROLL = 4;      // column quads per thread per trip: 8 x 16-byte loads in flight per thread
 
+// Fast path of a quad: all four columns in range, no diagonal element, Philox mode, only A_tilde wanted.
+// `u < clamp(theta, 0, 1)` with u = (w >> 8) * 2^-24 is evaluated exactly in integers: (w >> 8) < ceil(theta * 2^24)
+// (the saturating round-up conversion gives 0 for theta <= 0 or NaN and > 2^24 for theta > 1, which is the clamp).
+__device__ __forceinline__ void k1_quad_fast(int j0, const float (&th0)[4], const float (&th1)[4], int p, const PhiloxRounds& R,
+                                             __nv_bfloat16* __restrict__ a0, __nv_bfloat16* __restrict__ a1,
+                                             uint32_t& cnt0, uint32_t& cnt1) {
+  uint32_t b0[4], b1[4];
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {
+    const int q = (j0 >> 1) + b;
+    const bool upper = p < q;                       // p == q cannot happen here (no diagonal element in the quad)
+    uint32_t w[4];
+    philox4x32_10_rk((uint32_t)(upper ? q : p), (uint32_t)(upper ? p : q), R, w);
+    const uint32_t w01 = upper ? w[1] : w[2], w10 = upper ? w[2] : w[1];
+    b0[2 * b]     = ((w[0] >> 8) < __float2uint_ru(th0[2 * b] * 16777216.f)) ? 1u : 0u;
+    b0[2 * b + 1] = ((w01 >> 8)  < __float2uint_ru(th0[2 * b + 1] * 16777216.f)) ? 1u : 0u;
+    b1[2 * b]     = ((w10 >> 8)  < __float2uint_ru(th1[2 * b] * 16777216.f)) ? 1u : 0u;
+    b1[2 * b + 1] = ((w[3] >> 8) < __float2uint_ru(th1[2 * b + 1] * 16777216.f)) ? 1u : 0u;
+  }
+  cnt0 += b0[0] + b0[1] + b0[2] + b0[3];
+  cnt1 += b1[0] + b1[1] + b1[2] + b1[3];
+  uint2 r0, r1;                                       // bf16 1.0 = 0x3F80
+  r0.x = b0[0] * 0x3F80u + b0[1] * 0x3F800000u; r0.y = b0[2] * 0x3F80u + b0[3] * 0x3F800000u;
+  r1.x = b1[0] * 0x3F80u + b1[1] * 0x3F800000u; r1.y = b1[2] * 0x3F80u + b1[3] * 0x3F800000u;
+  *reinterpret_cast<uint2*>(a0) = r0;
+  *reinterpret_cast<uint2*>(a1) = r1;
+}
+
 // Processes one column quad (4 columns) of the row pair (2p, 2p+1): draws, compares, self loops, A_tilde store.
 template <bool EXPLICIT_U>
 __device__ __forceinline__ void k1_quad(int j0, const float (&th0)[4], const float (&th1)[4], int p, int gi0, int gi1, int li0, int li1,
@@ -169,9 +197,9 @@ __device__ __forceinline__ void k1_quad(int j0, const float (&th0)[4], const flo
 // All of a trip's 128-bit loads are issued before the first is consumed: the kernel is bound by memory-level
 // parallelism (each quad costs ~200 ALU instructions after its load), not by issue slots.
 template <bool EXPLICIT_U>
-__global__ void __launch_bounds__(K1_THREADS)
+__global__ void __launch_bounds__(K1_THREADS, 3)
 k1_sample_kernel(const float* __restrict__ theta, int64_t ldt, int n, int row0, int rows,
-                 PhiloxKey key, const float* __restrict__ U, int64_t ldu,
+                 const PhiloxKey key, const __grid_constant__ PhiloxRounds rounds, const float* __restrict__ U, int64_t ldu,
                  __nv_bfloat16* __restrict__ A, int64_t lda, float* __restrict__ S, int64_t lds_,
                  float* __restrict__ deg, float* __restrict__ rs) {
   const int p = (row0 >> 1) + blockIdx.x;             // global row-pair index
@@ -182,6 +210,7 @@ k1_sample_kernel(const float* __restrict__ theta, int64_t ldt, int n, int row0, 
   const float* t1 = theta + (int64_t)li1 * ldt;
   const int ncols = (A != nullptr) ? (int)lda : ((n + 3) & ~3);      // cover A's padding so it is zeroed
   float sum0 = 0.f, sum1 = 0.f;
+  uint32_t cnt0 = 0, cnt1 = 0;
 
   for (int base = 4 * threadIdx.x; base < ncols; base += 4 * K1_THREADS * K1_UNROLL) {
     float th0[K1_UNROLL][4], th1[K1_UNROLL][4];
@@ -203,12 +232,15 @@ k1_sample_kernel(const float* __restrict__ theta, int64_t ldt, int n, int row0, 
 #pragma unroll
     for (int u = 0; u < K1_UNROLL; ++u) {
       const int j0 = base + u * 4 * K1_THREADS;
-      if (j0 < ncols)
-        k1_quad<EXPLICIT_U>(j0, th0[u], th1[u], p, gi0, gi1, li0, li1, has1, n, key, U, ldu, A, lda, S, lds_, sum0, sum1);
+      if (j0 >= ncols) continue;
+      const bool fast = !EXPLICIT_U && has1 && S == nullptr && A != nullptr && (j0 + 3 < n) && (gi1 < j0 || gi0 > j0 + 3);
+      if (fast) k1_quad_fast(j0, th0[u], th1[u], p, rounds, A + (int64_t)li0 * lda + j0, A + (int64_t)li1 * lda + j0, cnt0, cnt1);
+      else k1_quad<EXPLICIT_U>(j0, th0[u], th1[u], p, gi0, gi1, li0, li1, has1, n, key, U, ldu, A, lda, S, lds_, sum0, sum1);
     }
   }
   // block reduction of the two row sums (integers in fp32: exact, order-independent for N < 2^24)
   __shared__ float sh0[K1_THREADS / 32], sh1[K1_THREADS / 32];
+  sum0 += (float)cnt0; sum1 += (float)cnt1;          // per-thread counts are far below 2^24: exact
   sum0 = warp_sum(sum0); sum1 = warp_sum(sum1);
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   if (l == 0) { sh0[w] = sum0; sh1[w] = sum1; }
@@ -280,12 +312,13 @@ extern "C" int32_t lds_k1_sample_normalize(const float* theta_full, int64_t ld_t
   const bool explicit_u = (flags & LDS_K1_EXPLICIT_U) != 0;
   if (explicit_u) LDS_CHECK_ARG(u_explicit && ld_u >= n, "lds_k1_sample_normalize: LDS_K1_EXPLICIT_U needs u_explicit with ld_u >= n");
   const PhiloxKey key = philox_key(seed, step, LDS_STREAM_EDGES, sample);
+  const PhiloxRounds rounds = philox_rounds(key);
   const int pairs = (rows + 1) / 2;
   auto* A = reinterpret_cast<__nv_bfloat16*>(a_out);
   if (explicit_u)
-    k1_sample_kernel<true><<<pairs, K1_THREADS, 0, (cudaStream_t)stream>>>(theta_full, ld_theta, n, row0, rows, key, u_explicit, ld_u, A, ld_a, sample_out, ld_s, deg_out, rsqrt_out);
+    k1_sample_kernel<true><<<pairs, K1_THREADS, 0, (cudaStream_t)stream>>>(theta_full, ld_theta, n, row0, rows, key, rounds, u_explicit, ld_u, A, ld_a, sample_out, ld_s, deg_out, rsqrt_out);
   else
-    k1_sample_kernel<false><<<pairs, K1_THREADS, 0, (cudaStream_t)stream>>>(theta_full, ld_theta, n, row0, rows, key, nullptr, 0, A, ld_a, sample_out, ld_s, deg_out, rsqrt_out);
+    k1_sample_kernel<false><<<pairs, K1_THREADS, 0, (cudaStream_t)stream>>>(theta_full, ld_theta, n, row0, rows, key, rounds, nullptr, 0, A, ld_a, sample_out, ld_s, deg_out, rsqrt_out);
   LDS_CHECK_LAUNCH("k1_sample_kernel");
   return LDS_OK;
 }

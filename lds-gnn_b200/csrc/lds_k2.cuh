@@ -10,7 +10,7 @@ constexpr int K2_THREADS = 192;      // warp 0 TMA producer, warp 1 MMA issuer +
 
 // Stream-K schedule: the (panel, k-block) space is linearised (panel-major) and cut into equal contiguous
 // ranges, one per CTA. A CTA writes one fp32 partial tile (128 x HP) per panel its range touches into
-// slot (cta * max_seg + segment); consumers sum the slots of a row in a fixed order (deterministic).
+// slot (cta * max_seg + segment); the last CTA to finish a panel sums its slots in a fixed order (deterministic).
 struct K2Sched {
   int hp;          // padded operand width (16/32/64/128)
   int panels;      // ceil(rows / 128)
@@ -27,35 +27,15 @@ static inline int64_t k2_operand_ld(int n) { return round_up(n, K2_BLOCK_K); }
 static inline int64_t k2_operand_bytes(int n, int hp) { return (int64_t)hp * k2_operand_ld(n) * 2; }            // one bf16 term
 static inline int64_t k2_partial_bytes(const K2Sched& s) { return (int64_t)s.grid * s.max_seg * K2_BLOCK_M * s.hp * 4; }
 
-// Sum of the partial tiles covering (row, col) in a fixed CTA order (deterministic). Loads are issued four at a
-// time before any is consumed: the consumers are latency-bound row epilogues.
-__device__ __forceinline__ float k2_sum_partials(const float* __restrict__ partial, const K2Sched& s, int row, int col) {
-  const int p = row >> 7, rin = row & 127;
-  const int c_first = (p * s.kblocks) / s.per_cta;
-  const int c_last = ((p + 1) * s.kblocks - 1) / s.per_cta;
-  const int64_t tile = (int64_t)K2_BLOCK_M * s.hp;
-  const float* base = partial + (int64_t)rin * s.hp + col;
-  float acc = 0.f;
-  for (int c = c_first; c <= c_last; c += 4) {
-    float v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int cc = c + u;
-      const int seg = p - (cc * s.per_cta) / s.kblocks;
-      v[u] = (cc <= c_last) ? base[(int64_t)(cc * s.max_seg + seg) * tile] : 0.f;
-    }
-    acc = ((acc + v[0]) + v[1]) + v[2];
-    acc += v[3];
-  }
-  return acc;
-}
+struct EpiArgs;   // lds_epilogue.cuh
 
-// Enqueue the tcgen05 kernel: partial <- A[rows][n] (bf16, ld_a) x Bt (bf16 hi/lo terms, [hp][ldb], K-major).
+// Enqueue the tcgen05 kernel: A[rows][n] (bf16, ld_a) x Bt (bf16 hi/lo terms, [hp][ldb], K-major), then the row
+// epilogue `epi` (K2Epi) on every completed 128-row panel. `counters`: one zero-initialised int per panel.
 int32_t k2_launch_mma(const void* a, int64_t ld_a, int n, int rows, const void* bt_hi, const void* bt_lo, int64_t ldb,
-                      float* partial, const K2Sched& s, bool use_lo, cudaStream_t stream);
-// Operand preparation: bt_hi/lo[c][i] = bf16 split of scale_in[i] * p[i][c] (transposed, K-major), c < hp.
+                      float* partial, int* counters, const K2Sched& s, bool use_lo, int epi, const EpiArgs& ea, cudaStream_t stream);
+// Operand preparation: bt_hi/lo[c][i] = bf16 split of scale_in[i] * p[i][c] (transposed, K-major), c < hp; zeroes the counters.
 int32_t k2_launch_prep(const float* p, int64_t ld_p, int n, int width, int hp, const float* scale_in,
-                       void* bt_hi, void* bt_lo, int64_t ldb, cudaStream_t stream);
+                       void* bt_hi, void* bt_lo, int64_t ldb, int* counters, int num_counters, cudaStream_t stream);
 // CUDA-core validation kernel producing the same partial layout (slot 0 of each panel's first CTA only is NOT used:
 // it writes complete sums into z directly). Tests only.
 int32_t k2_launch_simt(const void* a, int64_t ld_a, int n, int rows, const float* p, int64_t ld_p, int width,

@@ -16,7 +16,8 @@
 //               tcgen05.commit -> frees the smem stage / publishes the accumulator; owns the TMEM allocation
 //   warps 2-5   epilogue: tcgen05.ld 32x32b -> registers -> fp32 partial tile in global memory
 //   accumulators are double-buffered in TMEM so the next segment's MMAs overlap the epilogue.
-#include "lds_k2.cuh"
+#include <string.h>
+#include "lds_epilogue.cuh"
 #include "lds_tc.cuh"
 
 namespace lds {
@@ -25,19 +26,22 @@ namespace lds {
 // the kernel
 // ------------------------------------------------------------------------------------------------
 template <int HP> struct K2Cfg {
-  static constexpr int STAGES = (HP == 64) ? 6 : 4;
+  static constexpr int STAGES = (HP == 16) ? 8 : (HP == 32) ? 7 : (HP == 64) ? 6 : 4;   // ~160-200 KB of tiles in flight per SM
   static constexpr int A_BYTES = K2_BLOCK_M * K2_BLOCK_K * 2;        // 16 KB
   static constexpr int B_BYTES = HP * K2_BLOCK_K * 2;                // one bf16 term
   static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
   static constexpr int TMEM_COLS = (2 * HP < 32) ? 32 : 2 * HP;      // two accumulators, power of two >= 32
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers + tmem slot*/;
-  static constexpr int CTAS_PER_SM = (SMEM_BYTES <= 110 * 1024) ? 2 : 1;
+  static constexpr int CTAS_PER_SM = 1;
 };
 
-template <int HP>
+template <int HP, int EPI>
 __global__ void __launch_bounds__(K2_THREADS, 1)
 k2_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_bhi,
-              const __grid_constant__ CUtensorMap tm_blo, float* __restrict__ partial, const K2Sched s, const int use_lo) {
+              const __grid_constant__ CUtensorMap tm_blo, float* __restrict__ partial, int* __restrict__ counters,
+              const K2Sched s, const int use_lo, const __grid_constant__ EpiArgs ea) {
+  __shared__ int sh_last;
+  __shared__ float sh_red[4][2];
   using Cfg = K2Cfg<HP>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -127,33 +131,100 @@ k2_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
       }
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> fp32 partial tile =====
+    // ===== epilogue: TMEM -> registers; split panels go through fp32 partial tiles and the LAST CTA to arrive
+    // reduces them in a fixed order (deterministic) and runs the row epilogue; a CTA that covered a whole panel
+    // runs it straight from registers =====
     const int quarter = warp & 3;                            // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
+    const int etid = (warp - 2) * 32 + lane;                 // 0..127
+    if (EPI == K2_EPI_BWD2 && cta == 0 && etid == 0) {       // the layer-2 launch is complete: finalise loss / accuracy
+      float l = 0.f, c = 0.f;
+      for (int k = 0; k < ea.nblk; ++k) { l += ea.loss_part[k]; c += ea.corr_part[k]; }
+      ea.out_scalars[0] = l * ea.inv_m;
+      ea.out_scalars[1] = c * ea.inv_m;
+    }
     int acc = 0; uint32_t acc_phase = 0; int seg = 0;
     for (int pos = lo; pos < hi; ++seg) {
       const int p = pos / s.kblocks, kb0 = pos - p * s.kblocks;
       const int cnt = min(s.kblocks - kb0, hi - pos);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      float* dst = partial + ((int64_t)(cta * s.max_seg + seg) * K2_BLOCK_M + row) * HP;
+      float v[HP];
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * HP);
 #pragma unroll
       for (int c0 = 0; c0 < HP; c0 += 16) {
-        uint32_t v[16];
-        tc_ld16(taddr + c0, v);
+        uint32_t t16[16];
+        tc_ld16(taddr + c0, t16);
         tc_wait_ld();
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<float4*>(dst + c0 + 4 * q) =
-              make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+        for (int q = 0; q < 16; ++q) v[c0 + q] = __uint_as_float(t16[q]);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);          // accumulator drained: the next segment's MMAs may start
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       pos += cnt;
-      (void)p;
+
+      bool run_epilogue = (kb0 == 0 && cnt == s.kblocks);    // this CTA covered the whole panel
+      if (!run_epilogue) {
+        float* dst = partial + ((int64_t)(cta * s.max_seg + seg) * K2_BLOCK_M + row) * HP;
+#pragma unroll
+        for (int c0 = 0; c0 < HP; c0 += 4) *reinterpret_cast<float4*>(dst + c0) = make_float4(v[c0], v[c0 + 1], v[c0 + 2], v[c0 + 3]);
+        __threadfence();                                     // publish the partial tile before counting this CTA in
+        named_bar_sync(1, 128);
+        const int c_first = (p * s.kblocks) / s.per_cta;
+        const int c_last = ((p + 1) * s.kblocks - 1) / s.per_cta;
+        if (etid == 0) {
+          const int old = atomicAdd(&counters[p], 1);
+          const int last = (old == c_last - c_first) ? 1 : 0;
+          if (last) counters[p] = 0;                         // everyone has arrived: re-arm for the next launch
+          sh_last = last;
+        }
+        named_bar_sync(1, 128);
+        run_epilogue = sh_last != 0;
+        if (run_epilogue) {
+          __threadfence();
+#pragma unroll
+          for (int c0 = 0; c0 < HP; ++c0) v[c0] = 0.f;
+          // fixed order => bitwise reproducible; two contributors' tiles are in flight before either is added
+          const int64_t tile_elems = (int64_t)K2_BLOCK_M * HP;
+          const float* rowbase = partial + (int64_t)row * HP;
+          for (int c = c_first; c <= c_last; c += 2) {
+            const int sg0 = p - (c * s.per_cta) / s.kblocks;
+            const bool two = (c + 1 <= c_last);
+            const int sg1 = two ? p - ((c + 1) * s.per_cta) / s.kblocks : 0;
+            const float4* src0 = reinterpret_cast<const float4*>(rowbase + (int64_t)(c * s.max_seg + sg0) * tile_elems);
+            const float4* src1 = reinterpret_cast<const float4*>(rowbase + (int64_t)((two ? c + 1 : c) * s.max_seg + sg1) * tile_elems);
+            float4 t0[HP / 4], t1[HP / 4];
+#pragma unroll
+            for (int c0 = 0; c0 < HP / 4; ++c0) { t0[c0] = __ldcg(src0 + c0); t1[c0] = __ldcg(src1 + c0); }
+#pragma unroll
+            for (int c0 = 0; c0 < HP / 4; ++c0) {
+              v[4 * c0] += t0[c0].x; v[4 * c0 + 1] += t0[c0].y; v[4 * c0 + 2] += t0[c0].z; v[4 * c0 + 3] += t0[c0].w;
+              if (two) { v[4 * c0] += t1[c0].x; v[4 * c0 + 1] += t1[c0].y; v[4 * c0 + 2] += t1[c0].z; v[4 * c0 + 3] += t1[c0].w; }
+            }
+          }
+        }
+      }
+      if (run_epilogue) {                                    // uniform over the 128 epilogue threads
+        const int i = p * K2_BLOCK_M + row;
+        if (EPI == K2_EPI_PLAIN) epi_plain<HP>(ea, i, v);
+        else if (EPI == K2_EPI_LAYER1) epi_layer1<HP>(ea, i, v);
+        else if (EPI == K2_EPI_BWD2) epi_bwd2<HP>(ea, i, v);
+        else if (EPI == K2_EPI_BWD1) epi_bwd1<HP>(ea, i, v);
+        else if (EPI == K2_EPI_LAYER2) {
+          float li, ci;
+          epi_layer2<HP>(ea, i, v, li, ci);
+          li = warp_sum(li); ci = warp_sum(ci);
+          if (lane == 0) { sh_red[warp - 2][0] = li; sh_red[warp - 2][1] = ci; }
+          named_bar_sync(1, 128);
+          if (etid == 0) {
+            ea.loss_part[p] = ((sh_red[0][0] + sh_red[1][0]) + sh_red[2][0]) + sh_red[3][0];
+            ea.corr_part[p] = ((sh_red[0][1] + sh_red[1][1]) + sh_red[2][1]) + sh_red[3][1];
+          }
+          named_bar_sync(1, 128);
+        }
+      }
     }
   }
 
@@ -170,8 +241,11 @@ k2_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 // Bt_hi/lo[c][i] = bf16 split of scale_in[i] * p[i][c]  (transposed: K-major operand), rows c >= width zero.
 __global__ void k2_prep_kernel(const float* __restrict__ p, int64_t ld_p, int n, int width, int hp, const float* __restrict__ scale_in,
-                               __nv_bfloat16* __restrict__ bt_hi, __nv_bfloat16* __restrict__ bt_lo, int64_t ldb) {
+                               __nv_bfloat16* __restrict__ bt_hi, __nv_bfloat16* __restrict__ bt_lo, int64_t ldb,
+                               int* __restrict__ counters, int num_counters) {
   __shared__ float tile[32][33];
+  if (blockIdx.x == 0 && blockIdx.y == 0)
+    for (int k = threadIdx.x; k < num_counters; k += blockDim.x) counters[k] = 0;
   const int i0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 256 threads: ty in [0, 8)
   for (int r = ty; r < 32; r += 8) {
@@ -190,15 +264,6 @@ __global__ void k2_prep_kernel(const float* __restrict__ p, int64_t ld_p, int n,
       bt_lo[(int64_t)c * ldb + i] = l;
     }
   }
-}
-
-__global__ void k2_reduce_kernel(const float* __restrict__ partial, const K2Sched s, int rows, int width,
-                                 const float* __restrict__ scale_out, float* __restrict__ z, int64_t ld_z) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int row = idx / s.hp, col = idx - row * s.hp;
-  if (row >= rows || col >= width) return;
-  const float v = k2_sum_partials(partial, s, row, col);
-  z[(int64_t)row * ld_z + col] = v * (scale_out ? scale_out[row] : 1.f);
 }
 
 // CUDA-core validation kernel (tests only): one warp per output row, fp32 FMA over bf16 A.
@@ -301,30 +366,45 @@ static int32_t make_tmap_bf16(CUtensorMap* out, const void* base, int64_t cols, 
   return make_tmap_2d(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, cols, rows, ld, K2_BLOCK_K, box_rows);
 }
 
-template <int HP>
-static int32_t launch_mma_t(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tbl, float* partial, const K2Sched& s, bool use_lo, cudaStream_t stream) {
+template <int HP, int EPI>
+static int32_t launch_mma_t(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tbl, float* partial, int* counters,
+                            const K2Sched& s, bool use_lo, const EpiArgs& ea, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    LDS_CHECK_CUDA(cudaFuncSetAttribute(k2_mma_kernel<HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2Cfg<HP>::SMEM_BYTES));
+    LDS_CHECK_CUDA(cudaFuncSetAttribute(k2_mma_kernel<HP, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2Cfg<HP>::SMEM_BYTES));
     attr_set = true;
   }
-  k2_mma_kernel<HP><<<s.grid, K2_THREADS, K2Cfg<HP>::SMEM_BYTES, stream>>>(ta, tbh, tbl, partial, s, use_lo ? 1 : 0);
+  k2_mma_kernel<HP, EPI><<<s.grid, K2_THREADS, K2Cfg<HP>::SMEM_BYTES, stream>>>(ta, tbh, tbl, partial, counters, s, use_lo ? 1 : 0, ea);
   LDS_CHECK_LAUNCH("k2_mma_kernel");
   return LDS_OK;
 }
 
+template <int HP>
+static int32_t launch_mma_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tbl, float* partial, int* counters,
+                              const K2Sched& s, bool use_lo, const EpiArgs& ea, cudaStream_t stream) {
+  switch (epi) {
+    case K2_EPI_PLAIN:  return launch_mma_t<HP, K2_EPI_PLAIN>(ta, tbh, tbl, partial, counters, s, use_lo, ea, stream);
+    case K2_EPI_LAYER1: return launch_mma_t<HP, K2_EPI_LAYER1>(ta, tbh, tbl, partial, counters, s, use_lo, ea, stream);
+    case K2_EPI_LAYER2: return launch_mma_t<HP, K2_EPI_LAYER2>(ta, tbh, tbl, partial, counters, s, use_lo, ea, stream);
+    case K2_EPI_BWD2:   return launch_mma_t<HP, K2_EPI_BWD2>(ta, tbh, tbl, partial, counters, s, use_lo, ea, stream);
+    case K2_EPI_BWD1:   return launch_mma_t<HP, K2_EPI_BWD1>(ta, tbh, tbl, partial, counters, s, use_lo, ea, stream);
+  }
+  set_error("k2: unknown epilogue %d", epi);
+  return LDS_ERR_ARG;
+}
+
 int32_t k2_launch_mma(const void* a, int64_t ld_a, int n, int rows, const void* bt_hi, const void* bt_lo, int64_t ldb,
-                      float* partial, const K2Sched& s, bool use_lo, cudaStream_t stream) {
+                      float* partial, int* counters, const K2Sched& s, bool use_lo, int epi, const EpiArgs& ea, cudaStream_t stream) {
   CUtensorMap ta, tbh, tbl;
   int32_t rc;
   if ((rc = make_tmap_bf16(&ta, a, n, rows, ld_a, K2_BLOCK_M)) != LDS_OK) return rc;
   if ((rc = make_tmap_bf16(&tbh, bt_hi, n, s.hp, ldb, s.hp)) != LDS_OK) return rc;
   if ((rc = make_tmap_bf16(&tbl, bt_lo, n, s.hp, ldb, s.hp)) != LDS_OK) return rc;
   switch (s.hp) {
-    case 16: return launch_mma_t<16>(ta, tbh, tbl, partial, s, use_lo, stream);
-    case 32: return launch_mma_t<32>(ta, tbh, tbl, partial, s, use_lo, stream);
-    case 64: return launch_mma_t<64>(ta, tbh, tbl, partial, s, use_lo, stream);
-    case 128: return launch_mma_t<128>(ta, tbh, tbl, partial, s, use_lo, stream);
+    case 16: return launch_mma_epi<16>(epi, ta, tbh, tbl, partial, counters, s, use_lo, ea, stream);
+    case 32: return launch_mma_epi<32>(epi, ta, tbh, tbl, partial, counters, s, use_lo, ea, stream);
+    case 64: return launch_mma_epi<64>(epi, ta, tbh, tbl, partial, counters, s, use_lo, ea, stream);
+    case 128: return launch_mma_epi<128>(epi, ta, tbh, tbl, partial, counters, s, use_lo, ea, stream);
   }
   set_error("k2: unsupported padded width %d", s.hp);
   return LDS_ERR_UNSUPPORTED;
@@ -339,9 +419,9 @@ int32_t k2_launch_simt(const void* a, int64_t ld_a, int n, int rows, const float
 }
 
 int32_t k2_launch_prep(const float* p, int64_t ld_p, int n, int width, int hp, const float* scale_in,
-                       void* bt_hi, void* bt_lo, int64_t ldb, cudaStream_t stream) {
+                       void* bt_hi, void* bt_lo, int64_t ldb, int* counters, int num_counters, cudaStream_t stream) {
   dim3 grid((unsigned)ceil_div(ldb, 32), (unsigned)ceil_div(hp, 32));
-  k2_prep_kernel<<<grid, 256, 0, stream>>>(p, ld_p, n, width, hp, scale_in, reinterpret_cast<__nv_bfloat16*>(bt_hi), reinterpret_cast<__nv_bfloat16*>(bt_lo), ldb);
+  k2_prep_kernel<<<grid, 256, 0, stream>>>(p, ld_p, n, width, hp, scale_in, reinterpret_cast<__nv_bfloat16*>(bt_hi), reinterpret_cast<__nv_bfloat16*>(bt_lo), ldb, counters, num_counters);
   LDS_CHECK_LAUNCH("k2_prep_kernel");
   return LDS_OK;
 }
@@ -354,7 +434,7 @@ extern "C" int64_t lds_k2_workspace_bytes(int32_t n, int32_t rows, int32_t width
   const int hp = k2_padded_width(width);
   if (hp < 0 || n <= 0 || rows <= 0) return -1;
   const K2Sched s = k2_make_schedule(n, rows, hp);
-  return round_up(2 * k2_operand_bytes(n, hp), 1024) + round_up(k2_partial_bytes(s), 1024) + 1024;
+  return round_up(2 * k2_operand_bytes(n, hp), 1024) + round_up(k2_partial_bytes(s), 1024) + round_up((int64_t)s.panels * 4, 1024) + 1024;
 }
 
 extern "C" int32_t lds_k2_propagate(const void* a, int64_t ld_a, int32_t n, int32_t rows,
@@ -379,11 +459,11 @@ extern "C" int32_t lds_k2_propagate(const void* a, int64_t ld_a, int32_t n, int3
   void* bt_hi = ws;
   void* bt_lo = ws + k2_operand_bytes(n, hp);
   float* partial = reinterpret_cast<float*>(ws + round_up(2 * k2_operand_bytes(n, hp), 1024));
+  int* counters = reinterpret_cast<int*>(ws + round_up(2 * k2_operand_bytes(n, hp), 1024) + round_up(k2_partial_bytes(s), 1024));
   int32_t rc;
-  if ((rc = k2_launch_prep(p, ld_p, n, width, hp, scale_in, bt_hi, bt_lo, ldb, stream)) != LDS_OK) return rc;
-  if ((rc = k2_launch_mma(a, ld_a, n, rows, bt_hi, bt_lo, ldb, partial, s, !(flags & LDS_K2_SINGLE_BF16), stream)) != LDS_OK) return rc;
-  const int threads = 256;
-  k2_reduce_kernel<<<(int)ceil_div((int64_t)rows * hp, threads), threads, 0, stream>>>(partial, s, rows, width, scale_out, z_out, ld_z);
-  LDS_CHECK_LAUNCH("k2_reduce_kernel");
-  return LDS_OK;
+  if ((rc = k2_launch_prep(p, ld_p, n, width, hp, scale_in, bt_hi, bt_lo, ldb, counters, s.panels, stream)) != LDS_OK) return rc;
+  EpiArgs ea;
+  memset(&ea, 0, sizeof(ea));
+  ea.z_out = z_out; ea.ld_z = ld_z; ea.scale_out = scale_out; ea.rows = rows; ea.width = width;
+  return k2_launch_mma(a, ld_a, n, rows, bt_hi, bt_lo, ldb, partial, counters, s, !(flags & LDS_K2_SINGLE_BF16), K2_EPI_PLAIN, ea, stream);
 }

@@ -22,6 +22,9 @@ __device__ __forceinline__ void k3_pack_element(FloatPtr fa_row, FloatPtr fb_row
   qm = (seg == 1) ? bl : bh;
 }
 
+// fa, fb fp32 [n][ldf] -> packed bf16 operands Pm, Qm [n][kp] (coalesced, one thread per element).
+int32_t k3_launch_pack(const float* fa, const float* fb, int64_t ldf, int n, int d, int kp, void* pm, void* qm, cudaStream_t stream);
+
 // Tensor-core SGD update of rows [row0, row0+rows): theta <- clamp(theta - lr g), g from the packed operands.
 int32_t k3_launch_tc(float* theta, int64_t ldt, int n, int row0, int rows, const void* pm, const void* qm, int kp, int d,
                      const float* cvec, float lr, cudaStream_t stream);

@@ -335,6 +335,14 @@ __global__ void k3_pack_kernel(const float* __restrict__ fa, const float* __rest
   k3_pack_element(fa + (int64_t)i * ldf, fb + (int64_t)i * ldf, d, k, pm[idx], qm[idx]);
 }
 
+int32_t k3_launch_pack(const float* fa, const float* fb, int64_t ldf, int n, int d, int kp, void* pm, void* qm, cudaStream_t stream) {
+  const int64_t total = (int64_t)n * kp;
+  k3_pack_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(fa, fb, ldf, n, d, kp, reinterpret_cast<__nv_bfloat16*>(pm),
+                                                                    reinterpret_cast<__nv_bfloat16*>(qm));
+  LDS_CHECK_LAUNCH("k3_pack_kernel");
+  return LDS_OK;
+}
+
 int32_t k3_launch_tc(float* theta, int64_t ldt, int n, int row0, int rows, const void* pm, const void* qm, int kp, int d,
                      const float* cvec, float lr, cudaStream_t stream) {
   CUtensorMap tth, tpm, tqm;
@@ -411,8 +419,7 @@ extern "C" int32_t lds_k3k4_theta_update_tc(float* theta_full, int64_t ld_theta,
   const int kp = k3_padded_k(d);
   auto* pm = reinterpret_cast<__nv_bfloat16*>(workspace);
   auto* qm = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + need / 2);
-  const int64_t total = (int64_t)n * kp;
-  k3_pack_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(fa, fb, ld_f, n, d, kp, pm, qm);
-  LDS_CHECK_LAUNCH("k3_pack_kernel");
+  int32_t rc = k3_launch_pack(fa, fb, ld_f, n, d, kp, pm, qm, stream);
+  if (rc != LDS_OK) return rc;
   return k3_launch_tc(theta_full, ld_theta, n, row0, rows, pm, qm, kp, d, cvec, lr, stream);
 }

@@ -15,9 +15,8 @@
 //   epi_bwd1      dP1 = r*., rho, kappa, c = -(rho+kappa)/(2 deg); factors fa = r(dZ1|dZ2), fb = r(P1|P2); loss/acc finalised
 //   K3+K4         theta <- clamp(theta - lr * g(fa, fb, c))                         lds_k3_theta_update.cu
 // The outer step needs no weight gradients (the reference computes and discards them), so X is read once.
-#include "lds_k2.cuh"
-#include "lds_k3.cuh"
-#include "lds_philox.cuh"
+#include <string.h>
+#include "lds_epilogue.cuh"
 
 namespace lds {
 
@@ -26,9 +25,9 @@ constexpr int EPI_THREADS = 1024;   // 32 warps, one row each: the epilogues are
 constexpr int FEAT_THREADS = 256;   // dense feature GEMM: 8 warps x 4 rows
 constexpr int EPI_MAXW = 128;       // widest operand
 
-enum { B_A = 0, B_DEG, B_RS, B_P1, B_Z1, B_P2, B_Z2, B_DZ2, B_DP2, B_DZ1, B_DP1, B_FA, B_FB, B_C, B_BTHI, B_BTLO, B_PARTIAL, B_LOSSP, B_CORRP, B_PM, B_QM, B_W0S, B_END };
+enum { B_A = 0, B_DEG, B_RS, B_P1, B_Z1, B_P2, B_Z2, B_DZ2, B_DP2, B_DZ1, B_DP1, B_FA, B_FB, B_C, B_BTHI, B_BTLO, B_PARTIAL, B_LOSSP, B_CORRP, B_PM, B_QM, B_W0S, B_CNT, B_END };
 struct OuterLayout {
-  int n, f, h, c, hp1, hp2, hpmax, nblk, kp;
+  int n, f, h, c, hp1, hp2, hpmax, nblk, kp, panels;
   int64_t lda, ldb, ldf;
   K2Sched s1, s2;
   int64_t off[B_END];
@@ -43,6 +42,7 @@ static bool make_layout(int n, int f, int h, int c, OuterLayout& L) {
   L.lda = round_up(n, kLdAlign); L.ldb = k2_operand_ld(n); L.ldf = round_up(h + c, 4);
   L.s1 = k2_make_schedule(n, n, L.hp1); L.s2 = k2_make_schedule(n, n, L.hp2);
   L.nblk = (int)ceil_div(n, EPI_ROWS);
+  L.panels = (int)ceil_div(n, K2_BLOCK_M);
   int64_t bytes[B_END];
   bytes[B_A] = (int64_t)n * L.lda * 2;
   bytes[B_DEG] = bytes[B_RS] = bytes[B_C] = (int64_t)n * 4;
@@ -52,28 +52,15 @@ static bool make_layout(int n, int f, int h, int c, OuterLayout& L) {
   bytes[B_BTHI] = bytes[B_BTLO] = k2_operand_bytes(n, L.hpmax);
   const int64_t p1 = k2_partial_bytes(L.s1), p2 = k2_partial_bytes(L.s2);
   bytes[B_PARTIAL] = p1 > p2 ? p1 : p2;
-  bytes[B_LOSSP] = bytes[B_CORRP] = (int64_t)L.nblk * 4;
+  bytes[B_LOSSP] = bytes[B_CORRP] = (int64_t)ceil_div(n, K2_BLOCK_M) * 4;
   L.kp = k3_padded_k(h + c);
   bytes[B_PM] = bytes[B_QM] = (int64_t)n * L.kp * 2;
+  bytes[B_CNT] = (int64_t)ceil_div(n, K2_BLOCK_M) * 4;     // per-panel arrival counters of the stream-K reduction
   bytes[B_W0S] = (int64_t)h * round_up(f, 4) * 4;          // staged layer_in weight: transposed [f][h] (CSR path) or padded [h][ldx]
   int64_t o = 0;
   for (int b = 0; b < B_END; ++b) { L.off[b] = o; o += round_up(bytes[b], 1024); }
   L.total = o;
   return true;
-}
-
-struct DropCfg {           // dropout of one stream
-  float p, keep_thresh, scale;
-  const uint8_t* explicit_keep;   // [rows][cols] or nullptr
-  PhiloxKey key;
-};
-
-__device__ __forceinline__ bool drop_keep(const DropCfg& dc, int row, int col, int ncols) {
-  if (dc.p <= 0.f) return true;
-  if (dc.explicit_keep) return dc.explicit_keep[(int64_t)row * ncols + col] != 0;
-  uint32_t w[4];
-  philox4x32_10((uint32_t)(col >> 2), (uint32_t)row, dc.key, w);
-  return philox_to_uniform(w[col & 3]) < dc.keep_thresh;
 }
 
 // Transposed operand store: tile[c][r] (already scaled by r_i) -> bt_hi/lo[c][i0 + r], bf16 hi/lo split.
@@ -92,8 +79,11 @@ __device__ __forceinline__ void store_operand_tile(const float (*tile)[EPI_ROWS 
 
 // Stage layer_in.fc.weight [h][ldw] for the feature kernels: transposed [f][h] (CSR path: one contiguous row per
 // non-zero) or zero-padded [h][ldp] with 16-byte rows (dense path). Tiled through shared memory, coalesced both ways.
-__global__ void stage_w0_kernel(const float* __restrict__ w0, int64_t ldw, int h, int f, float* __restrict__ out, int64_t ldp, int transpose) {
+__global__ void stage_w0_kernel(const float* __restrict__ w0, int64_t ldw, int h, int f, float* __restrict__ out, int64_t ldp, int transpose,
+                                int* __restrict__ counters, int num_counters) {
   __shared__ float tile[32][33];
+  if (blockIdx.x == 0 && blockIdx.y == 0)
+    for (int k = threadIdx.x; k < num_counters; k += blockDim.x) counters[k] = 0;      // re-arm the stream-K panel counters
   const int f0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 256 threads
   for (int r = ty; r < 32; r += 8) {
@@ -260,195 +250,6 @@ feat_sparse_kernel(const int32_t* __restrict__ crow, const int32_t* __restrict__
   store_operand_tile(tile, hp, i0, ldb, bt_hi, bt_lo);
 }
 
-// ------------------------------------------------------------------------------------------------
-// row epilogues
-// ------------------------------------------------------------------------------------------------
-struct EpiArgs {
-  int n, h, c, hp1, hp2;
-  K2Sched s1, s2;
-  const float* partial;
-  const float* deg; const float* rs;
-  float* p1; float* z1; float* p2; float* z2; float* dz2; float* dp2; float* dz1; float* dp1;
-  float* fa; float* fb; int64_t ldf; float* cvec;
-  __nv_bfloat16* pm; __nv_bfloat16* qm; int kp;
-  const float* w1; const float* b1;
-  const int64_t* y; const uint8_t* mask; float inv_m;
-  DropCfg drop_h;
-  __nv_bfloat16* bt_hi; __nv_bfloat16* bt_lo; int64_t ldb;
-  float* loss_part; float* corr_part; int nblk;
-  float* out_scalars; float* out_logp;
-};
-
-__global__ void __launch_bounds__(EPI_THREADS) epi_layer1_kernel(const EpiArgs a) {
-  __shared__ float tile[EPI_MAXW][EPI_ROWS + 1];
-  __shared__ float rowbuf[EPI_THREADS / 32][EPI_MAXW];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i0 = blockIdx.x * EPI_ROWS;
-  for (int idx = threadIdx.x; idx < EPI_MAXW * (EPI_ROWS + 1); idx += EPI_THREADS) (&tile[0][0])[idx] = 0.f;
-  __syncthreads();
-  for (int rr = warp; rr < EPI_ROWS; rr += EPI_THREADS / 32) {    // one row per warp
-    const int i = i0 + rr;
-    if (i >= a.n) continue;                                   // warp-uniform
-    const float ri = a.rs[i];
-    for (int c = lane; c < a.h; c += 32) {
-      const float z = ri * k2_sum_partials(a.partial, a.s1, i, c);
-      a.z1[(int64_t)i * a.h + c] = z;
-      float hv = fmaxf(z, 0.f);                               // relu (gcn.py:28)
-      hv = drop_keep(a.drop_h, i, c, a.h) ? hv * (a.drop_h.p > 0.f ? a.drop_h.scale : 1.f) : 0.f;   // dropout (gcn.py:29)
-      rowbuf[warp][c] = hv;
-    }
-    __syncwarp();
-    for (int o = lane; o < a.c; o += 32) {                    // P2 = H1' W1^T + b1 (layers.py:43)
-      float acc = a.b1[o];
-      for (int k = 0; k < a.h; ++k) acc = fmaf(rowbuf[warp][k], a.w1[(int64_t)o * a.h + k], acc);
-      a.p2[(int64_t)i * a.c + o] = acc;
-      tile[o][rr] = ri * acc;
-    }
-    __syncwarp();
-  }
-  __syncthreads();
-  store_operand_tile(tile, a.hp2, i0, a.ldb, a.bt_hi, a.bt_lo);
-}
-
-__global__ void __launch_bounds__(EPI_THREADS) epi_layer2_kernel(const EpiArgs a) {
-  __shared__ float tile[EPI_MAXW][EPI_ROWS + 1];
-  __shared__ float sh_loss[EPI_THREADS / 32], sh_corr[EPI_THREADS / 32];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i0 = blockIdx.x * EPI_ROWS;
-  for (int idx = threadIdx.x; idx < EPI_MAXW * (EPI_ROWS + 1); idx += EPI_THREADS) (&tile[0][0])[idx] = 0.f;
-  __syncthreads();
-  float loss_w = 0.f, corr_w = 0.f;
-  for (int rr = warp; rr < EPI_ROWS; rr += EPI_THREADS / 32) {    // one row per warp
-    const int i = i0 + rr;
-    if (i >= a.n) continue;
-    const float ri = a.rs[i];
-    float z[4];
-    float mx = -3.4e38f; int best = 0x7fffffff; float bestv = -3.4e38f;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int o = lane + 32 * t;
-      z[t] = -3.4e38f;
-      if (o < a.c) {
-        z[t] = ri * k2_sum_partials(a.partial, a.s2, i, o);
-        a.z2[(int64_t)i * a.c + o] = z[t];
-        if (z[t] > bestv) { bestv = z[t]; best = o; }           // ascending o: first maximum wins (torch.argmax)
-      }
-      mx = fmaxf(mx, z[t]);
-    }
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) {
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
-      const float ov = __shfl_xor_sync(0xffffffffu, bestv, s);
-      const int oi = __shfl_xor_sync(0xffffffffu, best, s);
-      if (ov > bestv || (ov == bestv && oi < best)) { bestv = ov; best = oi; }
-    }
-    float se = 0.f;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) if (lane + 32 * t < a.c) se += expf(z[t] - mx);
-    se = warp_sum(se);
-    const float lse = mx + logf(se);                           // log_softmax (gcn.py:34)
-    const int yi = (int)a.y[i];
-    const bool mk = a.mask[i] != 0;
-    float li = 0.f;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int o = lane + 32 * t;
-      if (o < a.c) {
-        const float lp = z[t] - lse;
-        if (a.out_logp) a.out_logp[(int64_t)i * a.c + o] = lp;
-        if (mk && o == yi) li = -lp;                           // nll_loss numerator (outer.py:66)
-        const float dz = mk ? (expf(lp) - (o == yi ? 1.f : 0.f)) * a.inv_m : 0.f;
-        a.dz2[(int64_t)i * a.c + o] = dz;
-        tile[o][rr] = ri * dz;
-      }
-    }
-    li = warp_sum(li);
-    loss_w += li;
-    corr_w += (mk && best == yi) ? 1.f : 0.f;                  // accuracy (utils/evaluation.py:15-22)
-  }
-  if (lane == 0) { sh_loss[warp] = loss_w; sh_corr[warp] = corr_w; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float l = 0.f, c = 0.f;
-    for (int k = 0; k < EPI_THREADS / 32; ++k) { l += sh_loss[k]; c += sh_corr[k]; }
-    a.loss_part[blockIdx.x] = l; a.corr_part[blockIdx.x] = c;
-  }
-  store_operand_tile(tile, a.hp2, i0, a.ldb, a.bt_hi, a.bt_lo);
-}
-
-__global__ void __launch_bounds__(EPI_THREADS) epi_bwd2_kernel(const EpiArgs a) {
-  __shared__ float tile[EPI_MAXW][EPI_ROWS + 1];
-  __shared__ float rowbuf[EPI_THREADS / 32][EPI_MAXW];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i0 = blockIdx.x * EPI_ROWS;
-  for (int idx = threadIdx.x; idx < EPI_MAXW * (EPI_ROWS + 1); idx += EPI_THREADS) (&tile[0][0])[idx] = 0.f;
-  __syncthreads();
-  for (int rr = warp; rr < EPI_ROWS; rr += EPI_THREADS / 32) {    // one row per warp
-    const int i = i0 + rr;
-    if (i >= a.n) continue;
-    const float ri = a.rs[i];
-    for (int o = lane; o < a.c; o += 32) {
-      const float dp = ri * k2_sum_partials(a.partial, a.s2, i, o);      // dP2 = A_hat dZ2
-      a.dp2[(int64_t)i * a.c + o] = dp;
-      rowbuf[warp][o] = dp;
-    }
-    __syncwarp();
-    for (int c = lane; c < a.h; c += 32) {
-      float acc = 0.f;                                                    // dH1' = dP2 W1
-      for (int o = 0; o < a.c; ++o) acc = fmaf(rowbuf[warp][o], a.w1[(int64_t)o * a.h + c], acc);
-      const bool keep = drop_keep(a.drop_h, i, c, a.h);
-      const float sc = a.drop_h.p > 0.f ? a.drop_h.scale : 1.f;
-      const float dz = (keep && a.z1[(int64_t)i * a.h + c] > 0.f) ? acc * sc : 0.f;   // dropout' then relu'
-      a.dz1[(int64_t)i * a.h + c] = dz;
-      tile[c][rr] = ri * dz;
-    }
-    __syncwarp();
-  }
-  __syncthreads();
-  store_operand_tile(tile, a.hp1, i0, a.ldb, a.bt_hi, a.bt_lo);
-}
-
-__global__ void __launch_bounds__(EPI_THREADS) epi_bwd1_kernel(const EpiArgs a) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i0 = blockIdx.x * EPI_ROWS;
-  for (int rr = warp; rr < EPI_ROWS; rr += EPI_THREADS / 32) {    // one row per warp
-    const int i = i0 + rr;
-    if (i >= a.n) continue;
-    const float ri = a.rs[i];
-    float rho = 0.f, kappa = 0.f;
-    float* fa = a.fa + (int64_t)i * a.ldf;
-    float* fb = a.fb + (int64_t)i * a.ldf;
-    for (int c = lane; c < a.h; c += 32) {
-      const float dp1 = ri * k2_sum_partials(a.partial, a.s1, i, c);      // dP1 = A_hat dZ1
-      a.dp1[(int64_t)i * a.h + c] = dp1;
-      const float dz1 = a.dz1[(int64_t)i * a.h + c], p1 = a.p1[(int64_t)i * a.h + c];
-      rho = fmaf(dz1, a.z1[(int64_t)i * a.h + c], rho);
-      kappa = fmaf(p1, dp1, kappa);
-      fa[c] = ri * dz1; fb[c] = ri * p1;
-    }
-    for (int o = lane; o < a.c; o += 32) {
-      const float dz2 = a.dz2[(int64_t)i * a.c + o], p2 = a.p2[(int64_t)i * a.c + o];
-      rho = fmaf(dz2, a.z2[(int64_t)i * a.c + o], rho);
-      kappa = fmaf(p2, a.dp2[(int64_t)i * a.c + o], kappa);
-      fa[a.h + o] = ri * dz2; fb[a.h + o] = ri * p2;
-    }
-    for (int k = a.h + a.c + lane; k < (int)a.ldf; k += 32) { fa[k] = 0.f; fb[k] = 0.f; }
-    __threadfence_block();
-    __syncwarp();                                             // the row's factors are complete and visible to the warp
-    for (int k = lane; k < a.kp; k += 32)                     // bf16 hi/lo operands of the tensor-core theta update
-      k3_pack_element(const_cast<const volatile float*>(fa), const_cast<const volatile float*>(fb), a.h + a.c, k,
-                      a.pm[(int64_t)i * a.kp + k], a.qm[(int64_t)i * a.kp + k]);
-    rho = warp_sum(rho); kappa = warp_sum(kappa);
-    if (lane == 0) a.cvec[i] = -(rho + kappa) / (2.f * a.deg[i]);          // both D^-1/2 factors depend on the row sum
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {                                // deterministic final reduction
-    float l = 0.f, c = 0.f;
-    for (int k = 0; k < a.nblk; ++k) { l += a.loss_part[k]; c += a.corr_part[k]; }
-    a.out_scalars[0] = l * a.inv_m;
-    a.out_scalars[1] = c * a.inv_m;
-  }
-}
-
 }  // namespace lds
 
 using namespace lds;
@@ -498,7 +299,8 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   {   // stage the layer_in weight (tiny; independent of K1)
     const int64_t ldp = round_up(A.f, 4);
     dim3 sgrid((unsigned)ceil_div(ldp, 32), (unsigned)ceil_div(A.h, 32));
-    stage_w0_kernel<<<sgrid, 256, 0, stream>>>(A.w0, A.ld_w0, A.h, A.f, fbuf(B_W0S), ldp, sparse_x ? 1 : 0);
+    stage_w0_kernel<<<sgrid, 256, 0, stream>>>(A.w0, A.ld_w0, A.h, A.f, fbuf(B_W0S), ldp, sparse_x ? 1 : 0,
+                                               reinterpret_cast<int*>(buf(B_CNT)), L.panels);
     LDS_CHECK_LAUNCH("stage_w0_kernel");
     profile_mark(stream, 8);
   }
@@ -531,44 +333,35 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   profile_mark(stream, 1);
 
   EpiArgs E;
-  E.n = A.n; E.h = A.h; E.c = A.c; E.hp1 = L.hp1; E.hp2 = L.hp2; E.s1 = L.s1; E.s2 = L.s2;
-  E.partial = fbuf(B_PARTIAL); E.deg = fbuf(B_DEG); E.rs = fbuf(B_RS);
+  memset(&E, 0, sizeof(E));
+  E.n = A.n; E.h = A.h; E.c = A.c; E.hp1 = L.hp1; E.hp2 = L.hp2;
+  E.deg = fbuf(B_DEG); E.rs = fbuf(B_RS);
   E.p1 = fbuf(B_P1); E.z1 = fbuf(B_Z1); E.p2 = fbuf(B_P2); E.z2 = fbuf(B_Z2); E.dz2 = fbuf(B_DZ2); E.dp2 = fbuf(B_DP2);
   E.dz1 = fbuf(B_DZ1); E.dp1 = fbuf(B_DP1); E.fa = fbuf(B_FA); E.fb = fbuf(B_FB); E.ldf = L.ldf; E.cvec = fbuf(B_C);
   E.pm = reinterpret_cast<__nv_bfloat16*>(buf(B_PM)); E.qm = reinterpret_cast<__nv_bfloat16*>(buf(B_QM)); E.kp = L.kp;
   E.w1 = A.w1; E.b1 = A.b1; E.y = A.y; E.mask = A.mask; E.inv_m = 1.0f / (float)A.mask_count;
   E.drop_h = dh; E.bt_hi = bt_hi; E.bt_lo = bt_lo; E.ldb = L.ldb;
-  E.loss_part = fbuf(B_LOSSP); E.corr_part = fbuf(B_CORRP); E.nblk = L.nblk;
+  E.loss_part = fbuf(B_LOSSP); E.corr_part = fbuf(B_CORRP); E.nblk = L.panels;
   E.out_scalars = A.out_scalars; E.out_logp = A.out_logp;
 
-  auto propagate = [&](const K2Sched& s) -> int32_t {
-    if (A.k2_flags & LDS_K2_SIMT) { set_error("lds_outer_step: LDS_K2_SIMT is only available through lds_k2_propagate"); return LDS_ERR_ARG; }
-    const int32_t r = k2_launch_mma(buf(B_A), L.lda, A.n, A.n, bt_hi, bt_lo, L.ldb, fbuf(B_PARTIAL), s, use_lo, stream);
-    profile_mark(stream, 2);
+  if (A.k2_flags & LDS_K2_SIMT) { set_error("lds_outer_step: LDS_K2_SIMT is only available through lds_k2_propagate"); return LDS_ERR_ARG; }
+  int* counters = reinterpret_cast<int*>(buf(B_CNT));
+  auto propagate = [&](const K2Sched& s, int epi, int mark) -> int32_t {
+    const int32_t r = k2_launch_mma(buf(B_A), L.lda, A.n, A.n, bt_hi, bt_lo, L.ldb, fbuf(B_PARTIAL), counters, s, use_lo, epi, E, stream);
+    profile_mark(stream, mark);
     return r;
   };
-
-  if ((rc = propagate(L.s1)) != LDS_OK) return rc;
-  epi_layer1_kernel<<<egrid, EPI_THREADS, 0, stream>>>(E);
-  LDS_CHECK_LAUNCH("epi_layer1_kernel");
-  profile_mark(stream, 3);
-  if ((rc = propagate(L.s2)) != LDS_OK) return rc;
-  epi_layer2_kernel<<<egrid, EPI_THREADS, 0, stream>>>(E);
-  LDS_CHECK_LAUNCH("epi_layer2_kernel");
-  profile_mark(stream, 4);
-  if ((rc = propagate(L.s2)) != LDS_OK) return rc;
-  epi_bwd2_kernel<<<egrid, EPI_THREADS, 0, stream>>>(E);
-  LDS_CHECK_LAUNCH("epi_bwd2_kernel");
-  profile_mark(stream, 5);
-  if ((rc = propagate(L.s1)) != LDS_OK) return rc;
-  epi_bwd1_kernel<<<egrid, EPI_THREADS, 0, stream>>>(E);
-  LDS_CHECK_LAUNCH("epi_bwd1_kernel");
-  profile_mark(stream, 6);
+  if ((rc = propagate(L.s1, K2_EPI_LAYER1, 3)) != LDS_OK) return rc;   // Z1, H1, P2, operand (r P2)^T
+  if ((rc = propagate(L.s2, K2_EPI_LAYER2, 4)) != LDS_OK) return rc;   // Z2, log-softmax, loss, dZ2, operand (r dZ2)^T
+  if ((rc = propagate(L.s2, K2_EPI_BWD2, 5)) != LDS_OK) return rc;     // dP2, dZ1, operand (r dZ1)^T; loss/acc finalised
+  if ((rc = propagate(L.s1, K2_EPI_BWD1, 6)) != LDS_OK) return rc;     // dP1, c, factor matrices
 
   if (A.update) {
-    if (A.opt_kind == LDS_OPT_SGD && !(A.k3_flags & LDS_K3_SIMT))
-      rc = k3_launch_tc(A.theta_full, A.ld_theta, A.n, 0, A.n, buf(B_PM), buf(B_QM), L.kp, A.h + A.c, fbuf(B_C), A.lr, stream);
-    else
+    if (A.opt_kind == LDS_OPT_SGD && !(A.k3_flags & LDS_K3_SIMT)) {
+      rc = k3_launch_pack(fbuf(B_FA), fbuf(B_FB), L.ldf, A.n, A.h + A.c, L.kp, buf(B_PM), buf(B_QM), stream);
+      profile_mark(stream, 9);
+      if (rc == LDS_OK) rc = k3_launch_tc(A.theta_full, A.ld_theta, A.n, 0, A.n, buf(B_PM), buf(B_QM), L.kp, A.h + A.c, fbuf(B_C), A.lr, stream);
+    } else
       rc = lds_k3k4_theta_update(A.theta_full, A.ld_theta, A.n, 0, A.n, fbuf(B_FA), fbuf(B_FB), L.ldf, A.h + A.c, fbuf(B_C),
                                  A.lr, A.opt_kind, A.adam_m, A.adam_v, A.beta1, A.beta2, A.eps, A.adam_t, nullptr, 0, 0u, stream_);
     if (rc != LDS_OK) return rc;
