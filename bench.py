@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--workload", default="citeseer")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicas", action="store_true", help="N > 1: independent single-GPU replicas instead of the sharded N=65536 config")
     ap.add_argument("--cpu-steps", type=int, default=3)
     return ap.parse_args()
 
@@ -301,6 +302,156 @@ def run_ours(args, rank, world, device):
     return line
 
 
+# ------------------------------------------------------------------------------------------------ large-N / sharded arm
+def hashed_theta(n, ld, row0, rows, device, seed):
+    """Dense symmetric theta ~ U[0,1), generated row block by row block on the device from a
+    hash of the canonical pair (min(i,j), max(i,j)): every rank builds its own rows, theta_ij == theta_ji across ranks."""
+    out = torch.zeros((rows, ld), dtype=torch.float32, device=device)
+    cols = torch.arange(n, device=device, dtype=torch.int64)[None, :]
+    m35, m32 = (1 << 35) - 1, (1 << 32) - 1
+    for r in range(0, rows, 1024):
+        i = torch.arange(row0 + r, row0 + min(r + 1024, rows), device=device, dtype=torch.int64)[:, None]
+        key = (torch.minimum(i, cols) * n + torch.maximum(i, cols) + seed) * -7046029254386353131       # 0x9E3779B97F4A7C15
+        key = (key ^ ((key >> 29) & m35)) * -4658895280553007687                                        # 0xBF58476D1CE4E5B9
+        key = key ^ ((key >> 32) & m32)
+        out[r:r + i.shape[0], :n] = ((key >> 40) & 0xFFFFFF).to(torch.float32) * (1.0 / 16777216.0)
+    return out
+
+
+def make_large_rows(name, device, row0, rows, seed=0):
+    """Row block [row0, row0+rows) of the synthetic large-N workload: theta, sparse bag-of-words X, labels, objective mask."""
+    from lds_gnn_b200.data import SHAPES
+    n, f, c, h, rho, _ = SHAPES[name]
+    ld = (n + 63) // 64 * 64
+    theta = hashed_theta(n, ld, row0, rows, device, seed)
+    g = torch.Generator(device=device); g.manual_seed(1000 + seed * 977 + row0)
+    x = (torch.rand((rows, f), device=device, generator=g) < rho).to(torch.float32)
+    x[torch.arange(rows, device=device), torch.randint(0, f, (rows,), device=device, generator=g)] = 1.0
+    x /= x.sum(1, keepdim=True)
+    gl = torch.Generator(device="cpu"); gl.manual_seed(seed)
+    y_all = torch.randint(0, c, (n,), generator=gl)
+    mask_all = torch.zeros(n, dtype=torch.bool)
+    mask_all[torch.randperm(n, generator=gl)[:250]] = True
+    return dict(n=n, f=f, c=c, h=h, theta=theta, x=x, y=y_all[row0:row0 + rows].to(device), mask=mask_all[row0:row0 + rows].to(device),
+                mask_count=250)
+
+
+def run_large(args, rank, world, device, workload):
+    """N = 20 000 / 65 536 on one GPU, or N = 65 536 row-block sharded over `world` GPUs with NCCL all-gathers of the
+    N x h operand (lds_gnn_b200/sharded.py). Inputs are far larger than L2, so no flush between timed steps."""
+    import torch.distributed as dist
+    from lds_gnn_b200 import _lib, kernels as K, sharded as S
+    from lds_gnn_b200.data import SHAPES
+    n, f, c, h, _, _ = SHAPES[workload]
+    lo, cnt = S.shard_bounds(n, world, rank) if world > 1 else (0, n)
+    d = make_large_rows(workload, device, lo, cnt, seed=0)
+    rng = np.random.default_rng(1)
+    lim0, lim1 = np.sqrt(6.0 / (f + h)), np.sqrt(6.0 / (h + c))
+    host_w = [torch.as_tensor(rng.uniform(-lim0, lim0, (h, f)).astype(np.float32)), torch.zeros(h),
+              torch.as_tensor(rng.uniform(-lim1, lim1, (c, h)).astype(np.float32)), torch.zeros(c)]
+    total = sum(w.numel() for w in host_w)
+    host_flat = torch.cat([w.reshape(-1) for w in host_w]).pin_memory()
+    dev_flat = host_flat.to(device)
+    views, off = [], 0
+    for w in host_w:
+        views.append(dev_flat[off:off + w.numel()].view(w.shape)); off += w.numel()
+    theta = d["theta"]
+    lib = _lib.load()
+    if world > 1:
+        eng = S.ShardedOuterStep(n, lo, cnt, d["x"], d["y"], d["mask"], d["mask_count"], h, c)
+        comm = S.DistComm(n)
+        eng.set_weights(*views)
+        step_fn = lambda k, lr_now: eng.run(theta, comm, lr=lr_now, seed=1234, step=k, dropout_p=HYPER["dropout"], update=True)
+        scal = lambda: None
+    else:
+        eng = K.OuterStep(n, d["x"], d["y"], d["mask"], hidden=h, classes=c)
+        eng.set_weights(*views)
+        step_fn = lambda k, lr_now: eng.run(theta, lr=lr_now, seed=1234, step=k, dropout_p=HYPER["dropout"], update=True)
+    lr = HYPER["lr"]
+    for w in range(args.warmup):
+        step_fn(w, lr); lr *= HYPER["lr_decay"]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(torch.cuda.current_device())
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0.record()
+    for k in range(args.steps):
+        out = step_fn(args.warmup + k, lr); lr *= HYPER["lr_decay"]
+    t1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dev_ms = t0.elapsed_time(t1)
+    # per-kernel breakdown (rank-local)
+    per_kernel = {}
+    ms_buf = (ctypes.c_float * 64)(); id_buf = (ctypes.c_int32 * 64)()
+    reps = min(args.steps, 5)
+    for k in range(reps):
+        lib.lds_profile_begin()
+        step_fn(20_000 + k, lr)
+        cntm = lib.lds_profile_end(ms_buf, id_buf, 64)
+        for i in range(max(cntm, 0)):
+            per_kernel.setdefault(int(id_buf[i]), []).append(float(ms_buf[i]))
+    clock_info = clocks.stop()
+    # e2e: the step's weights from pinned host memory, (loss, acc) back to the host, every step
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ts = time.perf_counter()
+    for k in range(args.steps):
+        dev_flat.copy_(host_flat, non_blocking=True)
+        out = step_fn(30_000 + k, lr)
+        loss_acc = (out if world > 1 else eng.scalars)[:2].tolist()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - ts) * 1e3
+    dev_ms, e2e_ms = reduce_rank_times([dev_ms, e2e_ms], device, world)
+    value = args.steps / (dev_ms / 1e3)
+    hbm_peak, peak_src = peaks()
+    rows_local = cnt
+    alg = {0: 6 * rows_local * n, 3: 2 * rows_local * n, 4: 2 * rows_local * n, 5: 2 * rows_local * n, 6: 2 * rows_local * n,
+           7: 8 * rows_local * n}
+    kernel_summary = {}
+    for kid, vals in per_kernel.items():
+        if kid < 0:
+            kernel_summary["exchange_and_host_gaps"] = {"step_share_us": 1e3 * sum(vals) / reps}
+            continue
+        entry = {"mean_us": 1e3 * sum(vals) / len(vals), "step_share_us": 1e3 * sum(vals) / reps}
+        if kid in alg:
+            entry["algorithmic_GBps"] = round(alg[kid] / (sum(vals) / len(vals) / 1e3) / 1e9, 1)
+            entry["frac_of_hbm_peak"] = round(entry["algorithmic_GBps"] / hbm_peak, 4)
+        kernel_summary[KERNEL_NAMES.get(kid, str(kid))] = entry
+    cand = {k: v for k, v in per_kernel.items() if k in alg}
+    dom = max(cand, key=lambda k: sum(cand[k]))
+    mean_s = sum(cand[dom]) / len(cand[dom]) / 1e3
+    achieved = alg[dom] / mean_s / 1e9
+    step_bytes = 22 * rows_local * n
+    line = {
+        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+        "vs_baseline": None, "dtype": "bf16 adjacency x (bf16 hi+lo) operands, fp32 accumulate; fp32 theta", "data": "synthetic",
+        "config": {"workload": f"LDS-GCN direct outer step, synthetic N={n} dense theta ~ U(0,1), F={f}, hidden={h}, C={c}, SGD lr 0.1 decay 0.99, "
+                               f"dropout 0.5, 1 sample/step", "parallelism": "single GPU" if world == 1 else
+                               f"theta / A_tilde row-block sharded over {world} GPUs, NCCL all-gather of the N x h operand (4 per step) + factors",
+                   "l2": "not flushed: per-GPU theta rows are %.1f GB, far larger than the 126 MB L2" % (rows_local * n * 4 / 1e9)},
+        "clocks": clock_info,
+        "e2e": {"value": round(args.steps / (e2e_ms / 1e3), 3), "unit": UNIT, "h2d_bytes_per_step": total * 4, "d2h_bytes_per_step": 8,
+                "api": "lds_gnn_b200.sharded.ShardedOuterStep.run" if world > 1 else "lds_gnn_b200.kernels.OuterStep.run"},
+        "gpu_launches": (LAUNCHES_PER_STEP + (4 if world > 1 else 0)) * args.steps,
+        "roofline": {"kernel": KERNEL_NAMES[dom], "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
+                     "frac": round(achieved / hbm_peak, 4), "traffic": None, "algorithmic_bytes_per_launch": alg[dom],
+                     "mean_launch_us": round(mean_s * 1e6, 1), "peak_source": peak_src, "scope": "per GPU (rank 0)"},
+        "step_roofline": {"algorithmic_bytes_per_step_per_gpu": step_bytes,
+                          "frac_of_hbm_peak": round(step_bytes / (dev_ms / 1e3 / args.steps) / 1e9 / hbm_peak, 4)},
+        "kernels": kernel_summary, "last_metrics": {"loss": loss_acc[0], "acc": loss_acc[1]},
+        "cpu_baseline": {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"not runnable: the reference keeps ~25 dense N x N fp32 tensors ({25 * n * n * 4 / 1e9:.0f} GB) and does "
+                                   f"6 N^3 SGEMMs per step at N={n}; see --impl reference for the extrapolated figure"},
+    }
+    return line
+
+
 # ------------------------------------------------------------------------------------------------ reference / CPU baseline
 def time_cpu_port(workload, steps, warmup):
     """The oracle's op-for-op torch/CPU port of the reference outer step on this box's host cores."""
@@ -322,7 +473,32 @@ def time_cpu_port(workload, steps, warmup):
     return steps / dt, dt / steps * 1e3, torch.get_num_threads(), shape, loss
 
 
+def run_reference_large(args, workload):
+    """The reference cannot run N >= 20 000 (25 dense N x N fp32 temporaries, 6 N^3 SGEMMs per step). Bounded sample: the
+    port's step on a Cora-shape sub-problem, extrapolated with its measured O(N^3) normalisation cost."""
+    from lds_gnn_b200.data import SHAPES
+    n = SHAPES[workload][0]
+    steps = max(2, min(args.steps, 3))
+    rate, ms, threads, shape, loss = time_cpu_port("cora", steps, 1)
+    scale = (shape["n"] / n) ** 3
+    value = rate * scale
+    cpu = {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+           "sample": f"{steps} outer steps of the port at Cora shape (N={shape['n']}: {ms:.0f} ms/step) x (N_s/N)^3 — EXTRAPOLATED, "
+                     f"the reference cannot hold N={n} in memory"}
+    return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": 1,
+            "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": f"LDS-GCN direct outer step, synthetic N={n} (extrapolated from N={shape['n']})",
+                                            "parallelism": "host CPU"},
+            "cpu_baseline": cpu, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "extrapolated": True}
+
+
 def run_reference(args):
+    workload = args.workload
+    if args.gpus > 1 and workload in ("citeseer", "cora", "tiny") and not args.replicas:
+        workload = "n65k"
+    if workload in ("n20k", "n65k"):
+        return run_reference_large(args, workload)
     rate, ms, threads, shape, loss = time_cpu_port(args.workload, args.steps, max(1, min(args.warmup, 2)))
     cpu = {"value": round(rate, 4), "unit": UNIT, "cores": threads, "kind": "port",
            "sample": f"{args.steps} full outer steps of the same workload (oracle/reference_port.py, torch CPU, {threads} threads)"}
@@ -354,9 +530,15 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
-    line = run_ours(args, rank, world, device)
+    workload = args.workload
+    if world > 1 and workload in ("citeseer", "cora", "tiny") and not args.replicas:
+        workload = "n65k"                        # the multi-GPU config of BASELINE.json: N = 65 536 row-block sharded
+    if workload in ("n20k", "n65k"):
+        line = run_large(args, rank, world, device, workload)
+    else:
+        line = run_ours(args, rank, world, device)
     if rank == 0:
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and "cpu_baseline" not in line:
             rate, ms, threads, _, _ = time_cpu_port(args.workload, args.cpu_steps, 1)
             line["cpu_baseline"] = {"value": round(rate, 4), "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{args.cpu_steps} full outer steps of the same workload after 1 warm-up "

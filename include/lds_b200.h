@@ -40,6 +40,7 @@ extern "C" {
 /* K2 flags */
 #define LDS_K2_SIMT          1u  /* CUDA-core validation kernel instead of the tcgen05 kernel (tests only)    */
 #define LDS_K2_SINGLE_BF16   2u  /* operand as one bf16 term instead of the hi+lo split                       */
+#define LDS_K2_FORCE_STREAMK 4u  /* split panels across CTAs (stream-K) even when every panel could own a CTA   */
 /* K3 flags */
 #define LDS_K3_DENSE_GRAD    1u  /* write dL/dA_tilde (dense, not symmetrised) instead of updating theta      */
 #define LDS_K3_ACCUMULATE    2u  /* with DENSE_GRAD: add into grad_out instead of overwriting                  */
@@ -160,13 +161,40 @@ typedef struct lds_outer_step_args {
   void*    workspace; int64_t workspace_bytes;
   uint32_t k2_flags;          /* LDS_K2_* for the four propagations                                      */
   uint32_t k3_flags;          /* LDS_K3_SIMT or 0                                                        */
+  /* ---- row-block sharding (multi-GPU). rows == 0: the whole matrix, all phases, fields below ignored.
+   * With rows > 0 this rank owns global rows [row0, row0+rows): theta_full, x (or its CSR), y, mask, keep_x/keep_h and
+   * out_logp are the LOCAL row blocks; every row-local buffer of the workspace holds `rows` rows. A step is run as
+   * phases with one exchange between them (the caller all-gathers, e.g. with NCCL):
+   *   PHASE_SAMPLE   K1 + feature GEMM            -> local operand rows  (buffer 14, [rows][h]  fp32 = r * P1)
+   *   PHASE_LAYER1   needs opnd_full [n][h]       -> local operand rows  (buffer 14, [rows][c]  = r * P2)
+   *   PHASE_LAYER2   needs opnd_full [n][c]       -> local operand rows  ([rows][c] = r * dZ2), out_scalars = LOCAL sums / mask_count
+   *   PHASE_BWD2     needs opnd_full [n][c]       -> local operand rows  ([rows][h] = r * dZ1)
+   *   PHASE_BWD1     needs opnd_full [n][h]       -> local factor rows   (buffers 11, 12, 13)
+   *   PHASE_UPDATE   needs fa_full, fb_full [n][ld_f], c_full [n]        -> theta rows updated in place
+   * mask_count is the GLOBAL number of masked rows; seed/step must agree on all ranks. No theta / A_tilde traffic. */
+  int32_t  row0, rows;
+  uint32_t phases;            /* bitmask of LDS_PHASE_*                                                  */
+  uint32_t reserved2;
+  const float* opnd_full;
+  const float* fa_full; const float* fb_full; const float* c_full;
 } lds_outer_step_args;
 
+#define LDS_PHASE_SAMPLE   1u
+#define LDS_PHASE_LAYER1   2u
+#define LDS_PHASE_LAYER2   4u
+#define LDS_PHASE_BWD2     8u
+#define LDS_PHASE_BWD1    16u
+#define LDS_PHASE_UPDATE  32u
+#define LDS_PHASE_ALL     63u
+
 int64_t lds_outer_step_workspace_bytes(int32_t n, int32_t f, int32_t h, int32_t c);
+int64_t lds_outer_step_shard_workspace_bytes(int32_t n, int32_t rows, int32_t f, int32_t h, int32_t c);
 int32_t lds_outer_step(const lds_outer_step_args* args, void* stream);
-/* Device pointers into a workspace laid out by lds_outer_step (for tests / the composable path):
- * which: 0 A_tilde(bf16) 1 deg 2 rsqrt 3 P1 4 Z1 5 P2 6 Z2 7 dZ2 8 dP2 9 dZ1 10 dP1 11 fa 12 fb 13 cvec. */
+/* Device pointers into a workspace laid out by lds_outer_step (for tests / the composable path / the sharded exchange):
+ * which: 0 A_tilde(bf16) 1 deg 2 rsqrt 3 P1 4 Z1 5 P2 6 Z2 7 dZ2 8 dP2 9 dZ1 10 dP1 11 fa 12 fb 13 cvec 14 operand rows.
+ * `rows` = n for the unsharded layout. */
 void*   lds_outer_step_buffer(void* workspace, int32_t n, int32_t f, int32_t h, int32_t c, int32_t which);
+void*   lds_outer_step_shard_buffer(void* workspace, int32_t n, int32_t rows, int32_t f, int32_t h, int32_t c, int32_t which);
 int64_t lds_outer_step_factor_ld(int32_t h, int32_t c);
 
 /* ---- measurement hook for bench.py (not part of the reference-facing surface). Between begin and end,

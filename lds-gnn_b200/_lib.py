@@ -11,10 +11,11 @@ from . import _build
 
 LDS_OK = 0
 K1_EXPLICIT_U = 1
-K2_SIMT, K2_SINGLE_BF16 = 1, 2
+K2_SIMT, K2_SINGLE_BF16, K2_FORCE_STREAMK = 1, 2, 4
 K3_DENSE_GRAD, K3_ACCUMULATE, K3_SIMT = 1, 2, 4
 OPT_SGD, OPT_ADAM = 0, 1
 STREAM_EDGES, STREAM_DROP_X, STREAM_DROP_H = 0, 1, 2
+PHASE_SAMPLE, PHASE_LAYER1, PHASE_LAYER2, PHASE_BWD2, PHASE_BWD1, PHASE_UPDATE, PHASE_ALL = 1, 2, 4, 8, 16, 32, 63
 
 # every symbol include/lds_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
@@ -41,6 +42,8 @@ SIGNATURES = {
                                            c_void_p, c_float, c_void_p, c_int64, c_void_p]),
     "lds_outer_step_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
     "lds_outer_step": (c_int32, [c_void_p, c_void_p]),
+    "lds_outer_step_shard_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32, c_int32, c_int32]),
+    "lds_outer_step_shard_buffer": (c_void_p, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32]),
     "lds_outer_step_buffer": (c_void_p, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32]),
     "lds_outer_step_factor_ld": (c_int64, [c_int32, c_int32]),
     "lds_profile_begin": (c_int32, []),
@@ -70,6 +73,8 @@ class OuterStepArgs(Structure):
         ("out_scalars", c_void_p), ("out_logp", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_int64),
         ("k2_flags", c_uint32), ("k3_flags", c_uint32),
+        ("row0", c_int32), ("rows", c_int32), ("phases", c_uint32), ("reserved2", c_uint32),
+        ("opnd_full", c_void_p), ("fa_full", c_void_p), ("fb_full", c_void_p), ("c_full", c_void_p),
     ]
 
 

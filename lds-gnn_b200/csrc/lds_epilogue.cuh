@@ -20,16 +20,17 @@ struct DropCfg {           // dropout of one stream
   PhiloxKey key;
 };
 
-__device__ __forceinline__ bool drop_keep(const DropCfg& dc, int row, int col, int ncols) {
+__device__ __forceinline__ bool drop_keep(const DropCfg& dc, int row, int key_row, int col, int ncols) {
   if (dc.p <= 0.f) return true;
   if (dc.explicit_keep) return dc.explicit_keep[(int64_t)row * ncols + col] != 0;
   uint32_t w[4];
-  philox4x32_10((uint32_t)(col >> 2), (uint32_t)row, dc.key, w);
+  philox4x32_10((uint32_t)(col >> 2), (uint32_t)key_row, dc.key, w);
   return philox_to_uniform(w[col & 3]) < dc.keep_thresh;
 }
 
 // keep flags (as multipliers: scale or 0) of columns 4q .. 4q+3 of `row`: one Philox call
-__device__ __forceinline__ void drop_quad(const DropCfg& dc, int row, int q, int ncols, float (&k)[4]) {
+// (`row` indexes the explicit mask — local rows of a shard; `key_row` = global row keys the Philox draw)
+__device__ __forceinline__ void drop_quad(const DropCfg& dc, int row, int key_row, int q, int ncols, float (&k)[4]) {
   if (dc.p <= 0.f) { k[0] = k[1] = k[2] = k[3] = 1.f; return; }
   if (dc.explicit_keep) {
 #pragma unroll
@@ -37,13 +38,15 @@ __device__ __forceinline__ void drop_quad(const DropCfg& dc, int row, int q, int
     return;
   }
   uint32_t w[4];
-  philox4x32_10((uint32_t)q, (uint32_t)row, dc.key, w);
+  philox4x32_10((uint32_t)q, (uint32_t)key_row, dc.key, w);
 #pragma unroll
   for (int e = 0; e < 4; ++e) k[e] = (philox_to_uniform(w[e]) < dc.keep_thresh) ? dc.scale : 0.f;
 }
 
 struct EpiArgs {
-  int n, h, c, hp1, hp2;
+  int n, h, c, hp1, hp2;       // n = number of (local) rows the epilogue owns
+  int row0;                    // global index of local row 0 (row-block shard), keys the dropout draws
+  float* opnd; int64_t ld_opnd; // sharded: write the next operand's rows as fp32 [n][ld_opnd] (all-gathered by the caller)
   const float* deg; const float* rs;
   float* p1; float* z1; float* p2; float* z2; float* dz2; float* dp2; float* dz1; float* dp1;
   float* fa; float* fb; int64_t ldf; float* cvec;
@@ -59,6 +62,7 @@ struct EpiArgs {
 };
 
 __device__ __forceinline__ void store_operand(const EpiArgs& a, int c, int i, float v) {
+  if (a.opnd) { a.opnd[(int64_t)i * a.ld_opnd + c] = v; return; }
   __nv_bfloat16 hi, lo;
   split_bf16(v, hi, lo);
   a.bt_hi[(int64_t)c * a.ldb + i] = hi;
@@ -83,7 +87,7 @@ __device__ __forceinline__ void epi_layer1(const EpiArgs& a, int i, float (&v)[H
   for (int q = 0; q < HP / 4; ++q) {
     if (4 * q < a.h) {
       float k[4];
-      drop_quad(a.drop_h, i, q, a.h, k);
+      drop_quad(a.drop_h, i, a.row0 + i, q, a.h, k);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int c = 4 * q + e;
@@ -150,7 +154,7 @@ __device__ __forceinline__ void epi_bwd2(const EpiArgs& a, int i, float (&v)[HP]
   }
   for (int q = 0; 4 * q < a.h; ++q) {
     float k[4];
-    drop_quad(a.drop_h, i, q, a.h, k);
+    drop_quad(a.drop_h, i, a.row0 + i, q, a.h, k);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int c = 4 * q + e;

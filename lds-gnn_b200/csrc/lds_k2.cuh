@@ -22,7 +22,7 @@ struct K2Sched {
 };
 
 int k2_padded_width(int width);                        // 16/32/64/128, or -1
-K2Sched k2_make_schedule(int n, int rows, int hp);
+K2Sched k2_make_schedule(int n, int rows, int hp, bool force_streamk = false);
 static inline int64_t k2_operand_ld(int n) { return round_up(n, K2_BLOCK_K); }
 static inline int64_t k2_operand_bytes(int n, int hp) { return (int64_t)hp * k2_operand_ld(n) * 2; }            // one bf16 term
 static inline int64_t k2_partial_bytes(const K2Sched& s) { return (int64_t)s.grid * s.max_seg * K2_BLOCK_M * s.hp * 4; }

@@ -26,7 +26,7 @@ namespace lds {
 // the kernel
 // ------------------------------------------------------------------------------------------------
 template <int HP> struct K2Cfg {
-  static constexpr int STAGES = (HP == 16) ? 8 : (HP == 32) ? 7 : (HP == 64) ? 6 : 4;   // ~160-200 KB of tiles in flight per SM
+  static constexpr int STAGES = (HP == 16) ? 8 : (HP == 32) ? 7 : (HP == 64) ? 6 : 4;
   static constexpr int A_BYTES = K2_BLOCK_M * K2_BLOCK_K * 2;        // 16 KB
   static constexpr int B_BYTES = HP * K2_BLOCK_K * 2;                // one bf16 term
   static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
@@ -313,15 +313,18 @@ static int k2_ctas_per_sm(int hp) {
   }
 }
 
-K2Sched k2_make_schedule(int n, int rows, int hp) {
+K2Sched k2_make_schedule(int n, int rows, int hp, bool force_streamk) {
   K2Sched s;
   s.hp = hp;
   s.panels = (int)ceil_div(rows, K2_BLOCK_M);
   s.kblocks = (int)ceil_div(n, K2_BLOCK_K);
   s.total = s.panels * s.kblocks;
   const int grid_max = kNumSMsB200 * k2_ctas_per_sm(hp);     // a pure function of the shape: workspace sizing needs no device query
+  // Stream-K over the linearised (panel, k-block) space. Measured on B200 (Citeseer shape, 26 panels): one CTA per
+  // panel streams at only ~35 GB/s per SM (33 us per propagate) — every SM has to pull on the TMA path, so panels are
+  // split even when they could each own a CTA (20 us). `force_streamk` is kept for tests of larger splits.
   int per = (int)ceil_div(s.total, grid_max);
-  if (per < 4) per = 4;                                      // amortise the pipeline prologue
+  if (per < (force_streamk ? 2 : 4)) per = force_streamk ? 2 : 4;
   if (per > s.total) per = s.total;
   s.per_cta = per;
   s.grid = (int)ceil_div(s.total, per);
@@ -433,7 +436,7 @@ using namespace lds;
 extern "C" int64_t lds_k2_workspace_bytes(int32_t n, int32_t rows, int32_t width) {
   const int hp = k2_padded_width(width);
   if (hp < 0 || n <= 0 || rows <= 0) return -1;
-  const K2Sched s = k2_make_schedule(n, rows, hp);
+  const K2Sched s = k2_make_schedule(n, rows, hp, true);      // sized for the stream-K schedule (the larger one)
   return round_up(2 * k2_operand_bytes(n, hp), 1024) + round_up(k2_partial_bytes(s), 1024) + round_up((int64_t)s.panels * 4, 1024) + 1024;
 }
 
@@ -453,13 +456,14 @@ extern "C" int32_t lds_k2_propagate(const void* a, int64_t ld_a, int32_t n, int3
   const int64_t need = lds_k2_workspace_bytes(n, rows, width);
   if (!workspace || workspace_bytes < need) { set_error("lds_k2_propagate: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need); return LDS_ERR_WORKSPACE; }
   LDS_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "lds_k2_propagate: workspace must be 1024-byte aligned");
-  const K2Sched s = k2_make_schedule(n, rows, hp);
+  const K2Sched s_max = k2_make_schedule(n, rows, hp, true);
+  const K2Sched s = k2_make_schedule(n, rows, hp, (flags & LDS_K2_FORCE_STREAMK) != 0);
   const int64_t ldb = k2_operand_ld(n);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   void* bt_hi = ws;
   void* bt_lo = ws + k2_operand_bytes(n, hp);
   float* partial = reinterpret_cast<float*>(ws + round_up(2 * k2_operand_bytes(n, hp), 1024));
-  int* counters = reinterpret_cast<int*>(ws + round_up(2 * k2_operand_bytes(n, hp), 1024) + round_up(k2_partial_bytes(s), 1024));
+  int* counters = reinterpret_cast<int*>(ws + round_up(2 * k2_operand_bytes(n, hp), 1024) + round_up(k2_partial_bytes(s_max), 1024));
   int32_t rc;
   if ((rc = k2_launch_prep(p, ld_p, n, width, hp, scale_in, bt_hi, bt_lo, ldb, counters, s.panels, stream)) != LDS_OK) return rc;
   EpiArgs ea;

@@ -284,24 +284,43 @@ k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant
         tc_wait_ld();
         uint8_t* slab = slabs + slot * K3T_SLAB_BYTES + row * 128;
         const int jb = j0 + s * K3T_SLAB_COLS;
+        const bool interior = (gi0 + K3T_TILE <= j0 || j0 + K3T_TILE <= gi0) && (j0 + K3T_TILE <= n);   // no diagonal element, every column in range
+        if (interior) {
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          float4* cell = reinterpret_cast<float4*>(slab + ((c4 ^ (row & 7)) << 4));
-          float4 th = *cell;
-          const int gj = jb + 4 * c4;
-          float cj[4];
-          if (gj + 3 < n) { const float4 cv = *reinterpret_cast<const float4*>(cvec + gj); cj[0] = cv.x; cj[1] = cv.y; cj[2] = cv.z; cj[3] = cv.w; }
-          else { for (int b = 0; b < 4; ++b) cj[b] = (gj + b < n) ? cvec[gj + b] : 0.f; }
-          float tv[4] = {th.x, th.y, th.z, th.w};
+          for (int c4 = 0; c4 < 8; ++c4) {
+            float4* cell = reinterpret_cast<float4*>(slab + ((c4 ^ (row & 7)) << 4));
+            const float4 th = *cell;
+            const float4 cv = *reinterpret_cast<const float4*>(cvec + jb + 4 * c4);
+            const float tv[4] = {th.x, th.y, th.z, th.w}, cj[4] = {cv.x, cv.y, cv.z, cv.w};
+            float nv[4];
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            float g = (__uint_as_float(d1[4 * c4 + b]) + __uint_as_float(d2[4 * c4 + b])) + (ci + cj[b]);
-            if (gi == gj + b) g = 0.f;
-            if (tv[b] < 0.f || tv[b] > 1.f) g = 0.f;
-            const float nv = fminf(fmaxf(fmaf(-lr, g, tv[b]), 0.f), 1.f);
-            if (gj + b < n) tv[b] = nv;               // the TMA store clips at 16-byte granularity: leave padding as loaded
+            for (int b = 0; b < 4; ++b) {
+              float g = (__uint_as_float(d1[4 * c4 + b]) + __uint_as_float(d2[4 * c4 + b])) + (ci + cj[b]);
+              if (tv[b] < 0.f || tv[b] > 1.f) g = 0.f;                 // clamp backward
+              nv[b] = fminf(fmaxf(fmaf(-lr, g, tv[b]), 0.f), 1.f);
+            }
+            *cell = make_float4(nv[0], nv[1], nv[2], nv[3]);
           }
-          *cell = make_float4(tv[0], tv[1], tv[2], tv[3]);
+        } else {
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            float4* cell = reinterpret_cast<float4*>(slab + ((c4 ^ (row & 7)) << 4));
+            float4 th = *cell;
+            const int gj = jb + 4 * c4;
+            float cj[4];
+            if (gj + 3 < n) { const float4 cv = *reinterpret_cast<const float4*>(cvec + gj); cj[0] = cv.x; cj[1] = cv.y; cj[2] = cv.z; cj[3] = cv.w; }
+            else { for (int b = 0; b < 4; ++b) cj[b] = (gj + b < n) ? cvec[gj + b] : 0.f; }
+            float tv[4] = {th.x, th.y, th.z, th.w};
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              float g = (__uint_as_float(d1[4 * c4 + b]) + __uint_as_float(d2[4 * c4 + b])) + (ci + cj[b]);
+              if (gi == gj + b) g = 0.f;
+              if (tv[b] < 0.f || tv[b] > 1.f) g = 0.f;
+              const float nv = fminf(fmaxf(fmaf(-lr, g, tv[b]), 0.f), 1.f);
+              if (gj + b < n) tv[b] = nv;               // the TMA store clips at 16-byte granularity: leave padding as loaded
+            }
+            *cell = make_float4(tv[0], tv[1], tv[2], tv[3]);
+          }
         }
         fence_proxy_async_smem();                      // generic-proxy writes -> visible to the TMA store
         named_bar_sync(1 + hf, 128);                   // the four warps that own this slab

@@ -25,37 +25,39 @@ constexpr int EPI_THREADS = 1024;   // 32 warps, one row each: the epilogues are
 constexpr int FEAT_THREADS = 256;   // dense feature GEMM: 8 warps x 4 rows
 constexpr int EPI_MAXW = 128;       // widest operand
 
-enum { B_A = 0, B_DEG, B_RS, B_P1, B_Z1, B_P2, B_Z2, B_DZ2, B_DP2, B_DZ1, B_DP1, B_FA, B_FB, B_C, B_BTHI, B_BTLO, B_PARTIAL, B_LOSSP, B_CORRP, B_PM, B_QM, B_W0S, B_CNT, B_END };
+enum { B_A = 0, B_DEG, B_RS, B_P1, B_Z1, B_P2, B_Z2, B_DZ2, B_DP2, B_DZ1, B_DP1, B_FA, B_FB, B_C, B_BTHI, B_BTLO, B_PARTIAL, B_LOSSP, B_CORRP, B_PM, B_QM, B_W0S, B_CNT, B_OPND, B_END };
 struct OuterLayout {
-  int n, f, h, c, hp1, hp2, hpmax, nblk, kp, panels;
+  int n, rows, f, h, c, hp1, hp2, hpmax, nblk, kp, panels;
   int64_t lda, ldb, ldf;
   K2Sched s1, s2;
   int64_t off[B_END];
   int64_t total;
 };
 
-static bool make_layout(int n, int f, int h, int c, OuterLayout& L) {
-  L.n = n; L.f = f; L.h = h; L.c = c;
+static bool make_layout(int n, int rows, int f, int h, int c, OuterLayout& L, bool streamk = false) {
+  L.n = n; L.rows = rows; L.f = f; L.h = h; L.c = c;
   L.hp1 = k2_padded_width(h); L.hp2 = k2_padded_width(c);
-  if (n <= 0 || f <= 0 || L.hp1 < 0 || L.hp2 < 0) return false;
+  if (n <= 0 || rows <= 0 || rows > n || f <= 0 || L.hp1 < 0 || L.hp2 < 0) return false;
   L.hpmax = L.hp1 > L.hp2 ? L.hp1 : L.hp2;
   L.lda = round_up(n, kLdAlign); L.ldb = k2_operand_ld(n); L.ldf = round_up(h + c, 4);
-  L.s1 = k2_make_schedule(n, n, L.hp1); L.s2 = k2_make_schedule(n, n, L.hp2);
-  L.nblk = (int)ceil_div(n, EPI_ROWS);
-  L.panels = (int)ceil_div(n, K2_BLOCK_M);
+  L.s1 = k2_make_schedule(n, rows, L.hp1, streamk); L.s2 = k2_make_schedule(n, rows, L.hp2, streamk);
+  L.nblk = (int)ceil_div(rows, EPI_ROWS);
+  L.panels = (int)ceil_div(rows, K2_BLOCK_M);
   int64_t bytes[B_END];
-  bytes[B_A] = (int64_t)n * L.lda * 2;
-  bytes[B_DEG] = bytes[B_RS] = bytes[B_C] = (int64_t)n * 4;
-  bytes[B_P1] = bytes[B_Z1] = bytes[B_DZ1] = bytes[B_DP1] = (int64_t)n * h * 4;
-  bytes[B_P2] = bytes[B_Z2] = bytes[B_DZ2] = bytes[B_DP2] = (int64_t)n * c * 4;
-  bytes[B_FA] = bytes[B_FB] = (int64_t)n * L.ldf * 4;
+  bytes[B_A] = (int64_t)rows * L.lda * 2;
+  bytes[B_DEG] = bytes[B_RS] = bytes[B_C] = (int64_t)rows * 4;
+  bytes[B_P1] = bytes[B_Z1] = bytes[B_DZ1] = bytes[B_DP1] = (int64_t)rows * h * 4;
+  bytes[B_P2] = bytes[B_Z2] = bytes[B_DZ2] = bytes[B_DP2] = (int64_t)rows * c * 4;
+  bytes[B_FA] = bytes[B_FB] = (int64_t)rows * L.ldf * 4;
+  bytes[B_OPND] = (rows < n) ? (int64_t)rows * (h > c ? h : c) * 4 : 0;        // sharded: operand rows for the all-gather
   bytes[B_BTHI] = bytes[B_BTLO] = k2_operand_bytes(n, L.hpmax);
-  const int64_t p1 = k2_partial_bytes(L.s1), p2 = k2_partial_bytes(L.s2);
+  // partial tiles are sized for the stream-K schedule whichever schedule runs (workspace size must not depend on flags)
+  const int64_t p1 = k2_partial_bytes(k2_make_schedule(n, rows, L.hp1, true)), p2 = k2_partial_bytes(k2_make_schedule(n, rows, L.hp2, true));
   bytes[B_PARTIAL] = p1 > p2 ? p1 : p2;
-  bytes[B_LOSSP] = bytes[B_CORRP] = (int64_t)ceil_div(n, K2_BLOCK_M) * 4;
+  bytes[B_LOSSP] = bytes[B_CORRP] = (int64_t)ceil_div(rows, K2_BLOCK_M) * 4;
   L.kp = k3_padded_k(h + c);
   bytes[B_PM] = bytes[B_QM] = (int64_t)n * L.kp * 2;
-  bytes[B_CNT] = (int64_t)ceil_div(n, K2_BLOCK_M) * 4;     // per-panel arrival counters of the stream-K reduction
+  bytes[B_CNT] = (int64_t)ceil_div(rows, K2_BLOCK_M) * 4;     // per-panel arrival counters of the stream-K reduction
   bytes[B_W0S] = (int64_t)h * round_up(f, 4) * 4;          // staged layer_in weight: transposed [f][h] (CSR path) or padded [h][ldx]
   int64_t o = 0;
   for (int b = 0; b < B_END; ++b) { L.off[b] = o; o += round_up(bytes[b], 1024); }
@@ -110,7 +112,8 @@ __global__ void stage_w0_kernel(const float* __restrict__ w0, int64_t ldw, int h
 __global__ void __launch_bounds__(FEAT_THREADS)
 feat_linear_kernel(const float* __restrict__ x, int64_t ldx, int n, int f, const float* __restrict__ w0, int64_t ldw, const float* __restrict__ b0, int h,
                    DropCfg dc, const float* __restrict__ rs, float* __restrict__ p1,
-                   __nv_bfloat16* __restrict__ bt_hi, __nv_bfloat16* __restrict__ bt_lo, int64_t ldb, int hp) {
+                   __nv_bfloat16* __restrict__ bt_hi, __nv_bfloat16* __restrict__ bt_lo, int64_t ldb, int hp,
+                   int row0, float* __restrict__ opnd, int64_t ld_opnd) {
   __shared__ float tile[EPI_MAXW][EPI_ROWS + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * EPI_ROWS;
@@ -143,7 +146,7 @@ feat_linear_kernel(const float* __restrict__ x, int64_t ldx, int n, int f, const
               for (int e = 0; e < 4; ++e) k[e] = (4 * q + e < f && dc.explicit_keep[(int64_t)i * f + 4 * q + e]) ? dc.scale : 0.f;
             } else {
               uint32_t w[4];
-              philox4x32_10((uint32_t)q, (uint32_t)i, dc.key, w);
+              philox4x32_10((uint32_t)q, (uint32_t)(row0 + i), dc.key, w);
 #pragma unroll
               for (int e = 0; e < 4; ++e) k[e] = (philox_to_uniform(w[e]) < dc.keep_thresh) ? dc.scale : 0.f;
             }
@@ -187,6 +190,13 @@ feat_linear_kernel(const float* __restrict__ x, int64_t ldx, int n, int f, const
     for (int c = threadIdx.x >> 5; c < hp; c += FEAT_THREADS / 32) tile[c][rr] *= ri;
   }
   __syncthreads();
+  if (opnd) {                                                 // sharded: fp32 operand rows for the all-gather
+    for (int r = 0; r < 4; ++r) {
+      const int rr = 4 * warp + r, i = i0 + rr;
+      if (i < n) for (int c = lane; c < h; c += 32) opnd[(int64_t)i * ld_opnd + c] = tile[c][rr];
+    }
+    return;
+  }
   store_operand_tile(tile, hp, i0, ldb, bt_hi, bt_lo);
 }
 
@@ -200,7 +210,8 @@ __global__ void __launch_bounds__(EPI_THREADS)
 feat_sparse_kernel(const int32_t* __restrict__ crow, const int32_t* __restrict__ xcol, const float* __restrict__ xval, int n, int f,
                    const float* __restrict__ w0t, const float* __restrict__ b0, int h,
                    DropCfg dc, const float* __restrict__ rs, float* __restrict__ p1,
-                   __nv_bfloat16* __restrict__ bt_hi, __nv_bfloat16* __restrict__ bt_lo, int64_t ldb, int hp) {
+                   __nv_bfloat16* __restrict__ bt_hi, __nv_bfloat16* __restrict__ bt_lo, int64_t ldb, int hp,
+                   int row0, float* __restrict__ opnd, int64_t ld_opnd) {
   __shared__ float tile[EPI_MAXW][EPI_ROWS + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * EPI_ROWS;
@@ -216,7 +227,7 @@ feat_sparse_kernel(const int32_t* __restrict__ crow, const int32_t* __restrict__
       int col = 0; float v = 0.f;
       if (idx < end) {
         col = xcol[idx]; v = xval[idx];
-        if (dc.p > 0.f) v = drop_keep(dc, i, col, f) ? v * dc.scale : 0.f;
+        if (dc.p > 0.f) v = drop_keep(dc, i, row0 + i, col, f) ? v * dc.scale : 0.f;
       }
       const int cnt = min(32, end - base);
       for (int j = 0; j < cnt; j += 8) {                        // 8 non-zeros per trip: their w0t rows are loaded together
@@ -243,9 +254,14 @@ feat_sparse_kernel(const int32_t* __restrict__ crow, const int32_t* __restrict__
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const int o = lane + 32 * t;
-      if (o < h) { const float pv = acc[t] + b0[o]; p1[(int64_t)i * h + o] = pv; tile[o][rr] = ri * pv; }
+      if (o < h) {
+        const float pv = acc[t] + b0[o];
+        p1[(int64_t)i * h + o] = pv;
+        if (opnd) opnd[(int64_t)i * ld_opnd + o] = ri * pv; else tile[o][rr] = ri * pv;
+      }
     }
   }
+  if (opnd) return;
   __syncthreads();
   store_operand_tile(tile, hp, i0, ldb, bt_hi, bt_lo);
 }
@@ -256,16 +272,27 @@ using namespace lds;
 
 extern "C" int64_t lds_outer_step_workspace_bytes(int32_t n, int32_t f, int32_t h, int32_t c) {
   OuterLayout L;
-  if (!make_layout(n, f, h, c, L)) return -1;
+  if (!make_layout(n, n, f, h, c, L)) return -1;
+  return L.total;
+}
+
+extern "C" int64_t lds_outer_step_shard_workspace_bytes(int32_t n, int32_t rows, int32_t f, int32_t h, int32_t c) {
+  OuterLayout L;
+  if (!make_layout(n, rows, f, h, c, L)) return -1;
   return L.total;
 }
 
 extern "C" int64_t lds_outer_step_factor_ld(int32_t h, int32_t c) { return round_up(h + c, 4); }
 
-extern "C" void* lds_outer_step_buffer(void* workspace, int32_t n, int32_t f, int32_t h, int32_t c, int32_t which) {
+extern "C" void* lds_outer_step_shard_buffer(void* workspace, int32_t n, int32_t rows, int32_t f, int32_t h, int32_t c, int32_t which) {
   OuterLayout L;
-  if (!workspace || !make_layout(n, f, h, c, L) || which < 0 || which > B_C) return nullptr;
-  return reinterpret_cast<uint8_t*>(workspace) + L.off[which];
+  if (!workspace || !make_layout(n, rows, f, h, c, L) || which < 0 || which > 14) return nullptr;
+  const int b = (which == 14) ? B_OPND : which;
+  return reinterpret_cast<uint8_t*>(workspace) + L.off[b];
+}
+
+extern "C" void* lds_outer_step_buffer(void* workspace, int32_t n, int32_t f, int32_t h, int32_t c, int32_t which) {
+  return lds_outer_step_shard_buffer(workspace, n, n, f, h, c, which);
 }
 
 extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_) {
@@ -273,11 +300,22 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   LDS_CHECK_ARG(args != nullptr, "lds_outer_step: null args");
   LDS_CHECK_ARG(args->struct_bytes == sizeof(lds_outer_step_args), "lds_outer_step: struct_bytes %u != %zu (header mismatch)", args->struct_bytes, sizeof(lds_outer_step_args));
   const lds_outer_step_args& A = *args;
+  const bool sharded = A.rows > 0 && A.rows < A.n;
+  const int rows = sharded ? A.rows : A.n;
+  const int row0 = sharded ? A.row0 : 0;
+  const uint32_t phases = sharded ? A.phases : LDS_PHASE_ALL;
   OuterLayout L;
-  if (!make_layout(A.n, A.f, A.h, A.c, L)) { set_error("lds_outer_step: unsupported shape n=%d f=%d h=%d c=%d (h, c must be in [1,128])", A.n, A.f, A.h, A.c); return LDS_ERR_UNSUPPORTED; }
+  if (!make_layout(A.n, rows, A.f, A.h, A.c, L, (A.k2_flags & LDS_K2_FORCE_STREAMK) != 0)) { set_error("lds_outer_step: unsupported shape n=%d rows=%d f=%d h=%d c=%d (h, c must be in [1,128])", A.n, rows, A.f, A.h, A.c); return LDS_ERR_UNSUPPORTED; }
   LDS_CHECK_ARG(A.theta_full && A.w0 && A.b0 && A.w1 && A.b1 && A.y && A.mask && A.out_scalars, "lds_outer_step: null pointer");
   LDS_CHECK_ARG(A.ld_w0 >= A.f, "lds_outer_step: ld_w0 must be >= f");
   LDS_CHECK_ARG(A.ld_theta >= A.n && A.ld_theta % 4 == 0, "lds_outer_step: ld_theta must be >= n and a multiple of 4");
+  if (sharded) {
+    LDS_CHECK_ARG(row0 >= 0 && row0 + rows <= A.n && (row0 & 1) == 0, "lds_outer_step: shard rows [%d, %d) invalid (row0 must be even)", row0, row0 + rows);
+    LDS_CHECK_ARG(phases != 0 && (phases & ~LDS_PHASE_ALL) == 0, "lds_outer_step: sharded calls need a phase mask");
+    if (phases & (LDS_PHASE_LAYER1 | LDS_PHASE_LAYER2 | LDS_PHASE_BWD2 | LDS_PHASE_BWD1))
+      LDS_CHECK_ARG(A.opnd_full && (phases & (phases - 1)) == 0, "lds_outer_step: a sharded propagation phase runs alone and needs opnd_full");
+    if (phases & LDS_PHASE_UPDATE) LDS_CHECK_ARG(A.fa_full && A.fb_full && A.c_full, "lds_outer_step: PHASE_UPDATE needs the gathered factors");
+  }
   const bool sparse_x = A.x_crow != nullptr;
   if (sparse_x) {
     LDS_CHECK_ARG(A.x_col && A.x_val, "lds_outer_step: the CSR feature path needs x_col and x_val");
@@ -293,22 +331,12 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   uint8_t* ws = reinterpret_cast<uint8_t*>(A.workspace);
   auto buf = [&](int b) { return ws + L.off[b]; };
   auto fbuf = [&](int b) { return reinterpret_cast<float*>(ws + L.off[b]); };
-
-  int32_t rc;
-  profile_mark(stream, -1);
-  {   // stage the layer_in weight (tiny; independent of K1)
-    const int64_t ldp = round_up(A.f, 4);
-    dim3 sgrid((unsigned)ceil_div(ldp, 32), (unsigned)ceil_div(A.h, 32));
-    stage_w0_kernel<<<sgrid, 256, 0, stream>>>(A.w0, A.ld_w0, A.h, A.f, fbuf(B_W0S), ldp, sparse_x ? 1 : 0,
-                                               reinterpret_cast<int*>(buf(B_CNT)), L.panels);
-    LDS_CHECK_LAUNCH("stage_w0_kernel");
-    profile_mark(stream, 8);
-  }
-  // K1
-  rc = lds_k1_sample_normalize(A.theta_full, A.ld_theta, A.n, 0, A.n, A.seed, A.step, 0, A.u_explicit, A.ld_u,
-                               buf(B_A), L.lda, nullptr, 0, fbuf(B_DEG), fbuf(B_RS), A.u_explicit ? LDS_K1_EXPLICIT_U : 0u, stream_);
-  if (rc != LDS_OK) return rc;
-  profile_mark(stream, 0);
+  float* opnd = sharded ? fbuf(B_OPND) : nullptr;            // sharded: operand rows go out as fp32 for the all-gather
+  const int64_t ld_opnd = A.h > A.c ? A.h : A.c;
+  int* counters = reinterpret_cast<int*>(buf(B_CNT));
+  auto* bt_hi = reinterpret_cast<__nv_bfloat16*>(buf(B_BTHI));
+  auto* bt_lo = reinterpret_cast<__nv_bfloat16*>(buf(B_BTLO));
+  const bool use_lo = !(A.k2_flags & LDS_K2_SINGLE_BF16);
 
   DropCfg dx, dh;
   dx.p = dh.p = A.dropout_p;
@@ -318,23 +346,37 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   dx.key = philox_key(A.seed, A.step, LDS_STREAM_DROP_X, 0);
   dh.key = philox_key(A.seed, A.step, LDS_STREAM_DROP_H, 0);
 
-  auto* bt_hi = reinterpret_cast<__nv_bfloat16*>(buf(B_BTHI));
-  auto* bt_lo = reinterpret_cast<__nv_bfloat16*>(buf(B_BTLO));
-  const bool use_lo = !(A.k2_flags & LDS_K2_SINGLE_BF16);
-  const dim3 egrid((unsigned)L.nblk);
-
-  if (sparse_x) {
-    feat_sparse_kernel<<<egrid, EPI_THREADS, 0, stream>>>(A.x_crow, A.x_col, A.x_val, A.n, A.f, fbuf(B_W0S), A.b0, A.h, dx, fbuf(B_RS), fbuf(B_P1), bt_hi, bt_lo, L.ldb, L.hp1);
-    LDS_CHECK_LAUNCH("feat_sparse_kernel");
-  } else {
-    feat_linear_kernel<<<egrid, FEAT_THREADS, 0, stream>>>(A.x, A.ld_x, A.n, A.f, fbuf(B_W0S), round_up(A.f, 4), A.b0, A.h, dx, fbuf(B_RS), fbuf(B_P1), bt_hi, bt_lo, L.ldb, L.hp1);
-    LDS_CHECK_LAUNCH("feat_linear_kernel");
+  int32_t rc;
+  profile_mark(stream, -1);
+  if (phases & LDS_PHASE_SAMPLE) {
+    {   // stage the layer_in weight (tiny; independent of K1) and re-arm the stream-K counters
+      const int64_t ldp = round_up(A.f, 4);
+      dim3 sgrid((unsigned)ceil_div(ldp, 32), (unsigned)ceil_div(A.h, 32));
+      stage_w0_kernel<<<sgrid, 256, 0, stream>>>(A.w0, A.ld_w0, A.h, A.f, fbuf(B_W0S), ldp, sparse_x ? 1 : 0, counters, L.panels);
+      LDS_CHECK_LAUNCH("stage_w0_kernel");
+      profile_mark(stream, 8);
+    }
+    rc = lds_k1_sample_normalize(A.theta_full, A.ld_theta, A.n, row0, rows, A.seed, A.step, 0, A.u_explicit, A.ld_u,
+                                 buf(B_A), L.lda, nullptr, 0, fbuf(B_DEG), fbuf(B_RS), A.u_explicit ? LDS_K1_EXPLICIT_U : 0u, stream_);
+    if (rc != LDS_OK) return rc;
+    profile_mark(stream, 0);
+    const dim3 egrid((unsigned)L.nblk);
+    if (sparse_x) {
+      feat_sparse_kernel<<<egrid, EPI_THREADS, 0, stream>>>(A.x_crow, A.x_col, A.x_val, rows, A.f, fbuf(B_W0S), A.b0, A.h, dx, fbuf(B_RS), fbuf(B_P1),
+                                                            bt_hi, bt_lo, L.ldb, L.hp1, row0, opnd, ld_opnd);
+      LDS_CHECK_LAUNCH("feat_sparse_kernel");
+    } else {
+      feat_linear_kernel<<<egrid, FEAT_THREADS, 0, stream>>>(A.x, A.ld_x, rows, A.f, fbuf(B_W0S), round_up(A.f, 4), A.b0, A.h, dx, fbuf(B_RS), fbuf(B_P1),
+                                                             bt_hi, bt_lo, L.ldb, L.hp1, row0, opnd, ld_opnd);
+      LDS_CHECK_LAUNCH("feat_linear_kernel");
+    }
+    profile_mark(stream, 1);
   }
-  profile_mark(stream, 1);
 
   EpiArgs E;
   memset(&E, 0, sizeof(E));
-  E.n = A.n; E.h = A.h; E.c = A.c; E.hp1 = L.hp1; E.hp2 = L.hp2;
+  E.n = rows; E.h = A.h; E.c = A.c; E.hp1 = L.hp1; E.hp2 = L.hp2; E.row0 = row0;
+  E.opnd = opnd; E.ld_opnd = ld_opnd;
   E.deg = fbuf(B_DEG); E.rs = fbuf(B_RS);
   E.p1 = fbuf(B_P1); E.z1 = fbuf(B_Z1); E.p2 = fbuf(B_P2); E.z2 = fbuf(B_Z2); E.dz2 = fbuf(B_DZ2); E.dp2 = fbuf(B_DP2);
   E.dz1 = fbuf(B_DZ1); E.dp1 = fbuf(B_DP1); E.fa = fbuf(B_FA); E.fb = fbuf(B_FB); E.ldf = L.ldf; E.cvec = fbuf(B_C);
@@ -344,26 +386,37 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   E.loss_part = fbuf(B_LOSSP); E.corr_part = fbuf(B_CORRP); E.nblk = L.panels;
   E.out_scalars = A.out_scalars; E.out_logp = A.out_logp;
 
-  if (A.k2_flags & LDS_K2_SIMT) { set_error("lds_outer_step: LDS_K2_SIMT is only available through lds_k2_propagate"); return LDS_ERR_ARG; }
-  int* counters = reinterpret_cast<int*>(buf(B_CNT));
-  auto propagate = [&](const K2Sched& s, int epi, int mark) -> int32_t {
-    const int32_t r = k2_launch_mma(buf(B_A), L.lda, A.n, A.n, bt_hi, bt_lo, L.ldb, fbuf(B_PARTIAL), counters, s, use_lo, epi, E, stream);
+  if ((A.k2_flags & LDS_K2_SIMT) && (phases & (LDS_PHASE_LAYER1 | LDS_PHASE_LAYER2 | LDS_PHASE_BWD2 | LDS_PHASE_BWD1))) {
+    set_error("lds_outer_step: LDS_K2_SIMT is only available through lds_k2_propagate"); return LDS_ERR_ARG;
+  }
+  auto propagate = [&](uint32_t phase, const K2Sched& s, int width, int epi, int mark) -> int32_t {
+    if (!(phases & phase)) return LDS_OK;
+    if (sharded) {   // the gathered operand [n][width] fp32 -> K-major bf16 hi/lo terms
+      const int32_t r0 = k2_launch_prep(A.opnd_full, ld_opnd, A.n, width, s.hp, nullptr, bt_hi, bt_lo, L.ldb, counters, 0, stream);
+      if (r0 != LDS_OK) return r0;
+    }
+    const int32_t r = k2_launch_mma(buf(B_A), L.lda, A.n, rows, bt_hi, bt_lo, L.ldb, fbuf(B_PARTIAL), counters, s, use_lo, epi, E, stream);
     profile_mark(stream, mark);
     return r;
   };
-  if ((rc = propagate(L.s1, K2_EPI_LAYER1, 3)) != LDS_OK) return rc;   // Z1, H1, P2, operand (r P2)^T
-  if ((rc = propagate(L.s2, K2_EPI_LAYER2, 4)) != LDS_OK) return rc;   // Z2, log-softmax, loss, dZ2, operand (r dZ2)^T
-  if ((rc = propagate(L.s2, K2_EPI_BWD2, 5)) != LDS_OK) return rc;     // dP2, dZ1, operand (r dZ1)^T; loss/acc finalised
-  if ((rc = propagate(L.s1, K2_EPI_BWD1, 6)) != LDS_OK) return rc;     // dP1, c, factor matrices
+  if ((rc = propagate(LDS_PHASE_LAYER1, L.s1, A.h, K2_EPI_LAYER1, 3)) != LDS_OK) return rc;   // Z1, H1, P2, operand (r P2)^T
+  if ((rc = propagate(LDS_PHASE_LAYER2, L.s2, A.c, K2_EPI_LAYER2, 4)) != LDS_OK) return rc;   // Z2, log-softmax, loss, dZ2, operand (r dZ2)^T
+  if ((rc = propagate(LDS_PHASE_BWD2, L.s2, A.c, K2_EPI_BWD2, 5)) != LDS_OK) return rc;       // dP2, dZ1, operand (r dZ1)^T; loss/acc finalised
+  if ((rc = propagate(LDS_PHASE_BWD1, L.s1, A.h, K2_EPI_BWD1, 6)) != LDS_OK) return rc;       // dP1, c, factor matrices
 
-  if (A.update) {
+  if ((phases & LDS_PHASE_UPDATE) && A.update) {
+    const float* fa = sharded ? A.fa_full : fbuf(B_FA);
+    const float* fb = sharded ? A.fb_full : fbuf(B_FB);
+    const float* cv = sharded ? A.c_full : fbuf(B_C);
     if (A.opt_kind == LDS_OPT_SGD && !(A.k3_flags & LDS_K3_SIMT)) {
-      rc = k3_launch_pack(fbuf(B_FA), fbuf(B_FB), L.ldf, A.n, A.h + A.c, L.kp, buf(B_PM), buf(B_QM), stream);
+      LDS_CHECK_ARG((reinterpret_cast<uintptr_t>(cv) & 15) == 0, "lds_outer_step: c_full must be 16-byte aligned");
+      rc = k3_launch_pack(fa, fb, L.ldf, A.n, A.h + A.c, L.kp, buf(B_PM), buf(B_QM), stream);
       profile_mark(stream, 9);
-      if (rc == LDS_OK) rc = k3_launch_tc(A.theta_full, A.ld_theta, A.n, 0, A.n, buf(B_PM), buf(B_QM), L.kp, A.h + A.c, fbuf(B_C), A.lr, stream);
-    } else
-      rc = lds_k3k4_theta_update(A.theta_full, A.ld_theta, A.n, 0, A.n, fbuf(B_FA), fbuf(B_FB), L.ldf, A.h + A.c, fbuf(B_C),
+      if (rc == LDS_OK) rc = k3_launch_tc(A.theta_full, A.ld_theta, A.n, row0, rows, buf(B_PM), buf(B_QM), L.kp, A.h + A.c, cv, A.lr, stream);
+    } else {
+      rc = lds_k3k4_theta_update(A.theta_full, A.ld_theta, A.n, row0, rows, fa, fb, L.ldf, A.h + A.c, cv,
                                  A.lr, A.opt_kind, A.adam_m, A.adam_v, A.beta1, A.beta2, A.eps, A.adam_t, nullptr, 0, 0u, stream_);
+    }
     if (rc != LDS_OK) return rc;
     profile_mark(stream, 7);
   }

@@ -180,18 +180,26 @@ class OuterStep:
     """Resident state + workspace of the fused outer step (lds_outer_step). One instance per (theta, dataset)."""
 
     BUFFERS = {"adj": 0, "deg": 1, "rsqrt": 2, "p1": 3, "z1": 4, "p2": 5, "z2": 6, "dz2": 7, "dp2": 8, "dz1": 9,
-               "dp1": 10, "fa": 11, "fb": 12, "cvec": 13}
+               "dp1": 10, "fa": 11, "fb": 12, "cvec": 13, "operand": 14}
 
     SPARSE_DENSITY = 0.25          # below this share of non-zeros the feature GEMM runs from a CSR copy of x
 
-    def __init__(self, n, x, y, mask, hidden, classes, sparse_features=None):
+    def __init__(self, n, x, y, mask, hidden, classes, sparse_features=None, row0=0, rows=None, mask_count=None):
+        """x, y, mask hold this engine's rows: all n rows, or — for a row-block shard — global rows [row0, row0+rows)
+        (then `mask_count` is the GLOBAL number of masked rows and the step is run phase by phase, see sharded.py)."""
         _lib.require_device()
         self.lib = _lib.load()
         self.n, self.f, self.h, self.c = int(n), int(x.shape[1]), int(hidden), int(classes)
+        self.row0 = int(row0)
+        self.rows = self.n if rows is None else int(rows)
+        self.sharded = self.rows < self.n
+        if x.shape[0] != self.rows:
+            raise ValueError(f"x has {x.shape[0]} rows, expected {self.rows}")
+        self._mask_count_override = mask_count
         dev = x.device
         self.device = dev
         self.ld_x = (self.f + 3) // 4 * 4
-        self.x = torch.zeros((self.n, self.ld_x), dtype=torch.float32, device=dev)       # zero-padded copy, 16-byte rows
+        self.x = torch.zeros((self.rows, self.ld_x), dtype=torch.float32, device=dev)    # zero-padded copy, 16-byte rows
         self.x[:, :self.f] = x
         nnz = int((x != 0).sum().item())
         self.sparse = (nnz < self.SPARSE_DENSITY * x.numel()) if sparse_features is None else bool(sparse_features)
@@ -204,7 +212,7 @@ class OuterStep:
         self.y = y.to(device=dev, dtype=torch.int64).contiguous()
         self.set_mask(mask)
         self.w0 = self.b0 = self.w1 = self.b1 = None         # references to the caller's current GCN weights
-        nbytes = int(self.lib.lds_outer_step_workspace_bytes(self.n, self.f, self.h, self.c))
+        nbytes = int(self.lib.lds_outer_step_shard_workspace_bytes(self.n, self.rows, self.f, self.h, self.c))
         if nbytes < 0:
             raise ValueError(f"unsupported shape n={n} f={self.f} h={hidden} c={classes}")
         self._ws_raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
@@ -217,7 +225,7 @@ class OuterStep:
     def set_mask(self, mask):
         m = mask.to(device=self.device)
         self.mask = m.to(torch.uint8).contiguous()
-        self.mask_count = int(m.sum().item())
+        self.mask_count = int(m.sum().item()) if self._mask_count_override is None else int(self._mask_count_override)
 
     def set_weights(self, w0, b0, w1, b1):
         """Use these GCN (fast) weights for the next steps. No copies: the step's first kernel stages the layer_in
@@ -233,12 +241,13 @@ class OuterStep:
     def buffer(self, name):
         """View of an intermediate buffer of the last step (tests / composable path)."""
         which = self.BUFFERS[name]
-        ptr = self.lib.lds_outer_step_buffer(_ptr(self.ws), self.n, self.f, self.h, self.c, which)
+        ptr = self.lib.lds_outer_step_shard_buffer(_ptr(self.ws), self.n, self.rows, self.f, self.h, self.c, which)
         off = ptr - self.ws.data_ptr()
-        n, h, c = self.n, self.h, self.c
+        n, h, c = self.rows, self.h, self.c
         ldf = int(self.lib.lds_outer_step_factor_ld(h, c))
-        shapes = {"adj": (n, padded_ld(n)), "deg": (n,), "rsqrt": (n,), "p1": (n, h), "z1": (n, h), "p2": (n, c), "z2": (n, c),
-                  "dz2": (n, c), "dp2": (n, c), "dz1": (n, h), "dp1": (n, h), "fa": (n, ldf), "fb": (n, ldf), "cvec": (n,)}
+        shapes = {"adj": (n, padded_ld(self.n)), "deg": (n,), "rsqrt": (n,), "p1": (n, h), "z1": (n, h), "p2": (n, c), "z2": (n, c),
+                  "dz2": (n, c), "dp2": (n, c), "dz1": (n, h), "dp1": (n, h), "fa": (n, ldf), "fb": (n, ldf), "cvec": (n,),
+                  "operand": (n, max(h, c))}
         shape = shapes[name]
         if name == "adj":
             numel = shape[0] * shape[1]
@@ -250,7 +259,7 @@ class OuterStep:
 
     def run(self, theta_full, lr, seed, step, dropout_p=0.0, update=True, u=None, keep_x=None, keep_h=None,
             opt_kind=_lib.OPT_SGD, adam_m=None, adam_v=None, betas=(0.9, 0.999), eps=1e-8, adam_t=1,
-            out_logp=None, k2_flags=0, k3_flags=0):
+            out_logp=None, k2_flags=0, k3_flags=0, phases=None, opnd_full=None, fa_full=None, fb_full=None, c_full=None):
         """Enqueue one fused outer step on the current stream. Results: self.scalars[0:2] = (loss, acc)."""
         a = self.args
         a.struct_bytes = ctypes.sizeof(_lib.OuterStepArgs)
@@ -279,5 +288,15 @@ class OuterStep:
         a.out_logp = None if out_logp is None else out_logp.data_ptr()
         a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws_bytes
         a.k2_flags, a.k3_flags = int(k2_flags), int(k3_flags)
+        if self.sharded:
+            if phases is None:
+                raise ValueError("a row-block shard runs phase by phase (lds_gnn_b200.sharded.ShardedOuterStep)")
+            a.row0, a.rows, a.phases, a.reserved2 = self.row0, self.rows, int(phases), 0
+        else:
+            a.row0, a.rows, a.phases, a.reserved2 = 0, 0, 0, 0
+        a.opnd_full = None if opnd_full is None else opnd_full.data_ptr()
+        a.fa_full = None if fa_full is None else fa_full.data_ptr()
+        a.fb_full = None if fb_full is None else fb_full.data_ptr()
+        a.c_full = None if c_full is None else c_full.data_ptr()
         _lib.check(self.lib.lds_outer_step(ctypes.byref(a), _stream()), "lds_outer_step")
         return self.scalars

@@ -1,0 +1,120 @@
+"""Row-block sharded direct outer step: theta, A_tilde and every row-local buffer are partitioned
+by contiguous row blocks over the ranks of one box. theta / A_tilde never move:
+
+  * sampling needs no exchange — the Philox draw of edge (i, j) is keyed on (min, max), so the owners of row i and of
+    row j regenerate the same bit, and the K3 update is symmetric bit for bit (csrc/lds_k3_theta_update.cu);
+  * each of the four propagations Z_rows = r_rows * (A_tilde_rows @ (r * P)) needs the scaled N x w operand of ALL
+    rows: one all-gather of [rows, w] fp32 blocks (16.8 MB at N = 65 536, w = 64) — the only data-path collective;
+  * the closed-form theta update needs the gathered factor matrices fa, fb [N, d] and c [N];
+  * loss / accuracy: one all-reduce of two floats.
+
+`ShardedOuterStep` drives one rank through the phases of `lds_outer_step` (include/lds_b200.h, LDS_PHASE_*);
+the exchange object is either `DistComm` (torch.distributed: NCCL over NVLink on GPUs) or, for single-GPU tests,
+`run_local_group`, which steps several shards of one matrix through the same phases and gathers by concatenation.
+"""
+import torch
+
+from . import _lib
+from . import kernels as K
+
+PHASES = (_lib.PHASE_LAYER1, _lib.PHASE_LAYER2, _lib.PHASE_BWD2, _lib.PHASE_BWD1)
+
+
+def shard_bounds(n, world, rank):
+    """Contiguous row block of `rank`; block starts are multiples of 128 (K2 row panels, even for K1's row pairs)."""
+    per = -(-n // world)
+    per = -(-per // 128) * 128
+    lo = min(n, rank * per)
+    hi = min(n, lo + per)
+    return lo, hi - lo
+
+
+class DistComm:
+    """Exchange over torch.distributed (backend nccl on GPUs, gloo in CPU tests). Shards may be ragged."""
+
+    def __init__(self, n, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.bounds = [shard_bounds(n, self.world, r) for r in range(self.world)]
+        self.equal = len({b[1] for b in self.bounds}) == 1
+
+    def all_gather_rows(self, local, out):
+        """local [rows_r, w] -> out [n, w] (row blocks in rank order)."""
+        if self.equal:
+            self.dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
+            return out
+        per = max(cnt for _, cnt in self.bounds)           # ragged last block: pad to the common block size
+        padded = local.new_zeros((per,) + tuple(local.shape[1:]))
+        padded[:local.shape[0]] = local
+        gathered = local.new_empty((self.world * per,) + tuple(local.shape[1:]))
+        self.dist.all_gather_into_tensor(gathered, padded, group=self.group)
+        for r, (lo, cnt) in enumerate(self.bounds):
+            out[lo:lo + cnt] = gathered[r * per:r * per + cnt]
+        return out
+
+    def all_reduce_sum(self, t):
+        self.dist.all_reduce(t, group=self.group)
+        return t
+
+
+class ShardedOuterStep:
+    def __init__(self, n, row0, rows, x_local, y_local, mask_local, mask_count, hidden, classes, sparse_features=None):
+        self.n, self.row0, self.rows = int(n), int(row0), int(rows)
+        self.h, self.c = int(hidden), int(classes)
+        self.eng = K.OuterStep(n, x_local, y_local, mask_local, hidden, classes, sparse_features=sparse_features,
+                               row0=row0, rows=rows, mask_count=mask_count)
+        dev = x_local.device
+        w = max(self.h, self.c)
+        self.ldf = int(_lib.load().lds_outer_step_factor_ld(self.h, self.c))
+        self.opnd_full = torch.empty((self.n, w), dtype=torch.float32, device=dev)
+        self.fa_full = torch.empty((self.n, self.ldf), dtype=torch.float32, device=dev)
+        self.fb_full = torch.empty((self.n, self.ldf), dtype=torch.float32, device=dev)
+        self.c_full = torch.empty(self.n, dtype=torch.float32, device=dev)
+
+    def set_weights(self, *w):
+        self.eng.set_weights(*w)
+
+    def phase(self, theta_local, phases, **kw):
+        return self.eng.run(theta_local, phases=phases, opnd_full=self.opnd_full, fa_full=self.fa_full, fb_full=self.fb_full,
+                            c_full=self.c_full, **kw)
+
+    def run(self, theta_local, comm, lr, seed, step, dropout_p=0.0, update=True, **kw):
+        """One sharded outer step on this rank. Returns a device tensor (loss, acc) of the WHOLE graph."""
+        kw = dict(lr=lr, seed=seed, step=step, dropout_p=dropout_p, update=update, **kw)
+        self.phase(theta_local, _lib.PHASE_SAMPLE, **kw)
+        for ph in PHASES:
+            comm.all_gather_rows(self.eng.buffer("operand"), self.opnd_full)
+            self.phase(theta_local, ph, **kw)
+        scalars = comm.all_reduce_sum(self.eng.scalars[:2].clone())
+        comm.all_gather_rows(self.eng.buffer("fa"), self.fa_full)
+        comm.all_gather_rows(self.eng.buffer("fb"), self.fb_full)
+        comm.all_gather_rows(self.eng.buffer("cvec").view(-1, 1), self.c_full.view(-1, 1))
+        self.phase(theta_local, _lib.PHASE_UPDATE, **kw)
+        return scalars
+
+
+def run_local_group(shards, thetas, lr, seed, step, dropout_p=0.0, update=True, **kw):
+    """Single-GPU emulation of the multi-rank step (tests): every shard goes through the same phases, the exchange is a
+    concatenation. `shards`: ShardedOuterStep objects covering [0, n) in order; `thetas`: their local theta row blocks."""
+    kw = dict(lr=lr, seed=seed, step=step, dropout_p=dropout_p, update=update, **kw)
+
+    def gather(name, attr, view=None):
+        parts = [s.eng.buffer(name) for s in shards]
+        full = torch.cat([p if view is None else p.view(*view) for p in parts], dim=0)
+        for s in shards:
+            getattr(s, attr).view(full.shape).copy_(full)
+
+    for s, t in zip(shards, thetas):
+        s.phase(t, _lib.PHASE_SAMPLE, **kw)
+    for ph in PHASES:
+        gather("operand", "opnd_full")
+        for s, t in zip(shards, thetas):
+            s.phase(t, ph, **kw)
+    scalars = sum(s.eng.scalars[:2].clone() for s in shards)
+    gather("fa", "fa_full")
+    gather("fb", "fb_full")
+    gather("cvec", "c_full", view=(-1,))
+    for s, t in zip(shards, thetas):
+        s.phase(t, _lib.PHASE_UPDATE, **kw)
+    return scalars

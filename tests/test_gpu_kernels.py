@@ -169,8 +169,10 @@ def test_k2_simt_validation_kernel(K, n, w):
 @pytest.mark.parametrize("n,w,rows", [(64, 16, None), (128, 16, None), (257, 7, None), (1000, 16, None), (2708, 16, None),
                                       (3327, 6, None), (1000, 64, None), (515, 33, None), (300, 128, None),
                                       (2708, 16, 512), (700, 32, 130)])
-def test_k2_tcgen05_matches_fp64(K, n, w, rows):
-    z, ref = _k2_case(K, n, w, rows=rows, seed=n + w)
+@pytest.mark.parametrize("streamk", [False, True], ids=["panel_per_cta", "stream_k"])
+def test_k2_tcgen05_matches_fp64(K, n, w, rows, streamk):
+    from lds_gnn_b200 import _lib
+    z, ref = _k2_case(K, n, w, rows=rows, seed=n + w, flags=_lib.K2_FORCE_STREAMK if streamk else 0)
     err = rel_inf(z, ref)
     assert err < 2e-5, f"tcgen05 propagate rel err {err}"
 
@@ -183,9 +185,12 @@ def test_k2_single_bf16_term_is_within_north_star_tolerance(K):
     assert rel_inf(z2, ref) < rel_inf(z, ref)
 
 
-def test_k2_is_deterministic(K):
-    z1, _ = _k2_case(K, 2708, 16, seed=5)
-    z2, _ = _k2_case(K, 2708, 16, seed=5)
+@pytest.mark.parametrize("streamk", [False, True], ids=["panel_per_cta", "stream_k"])
+def test_k2_is_deterministic(K, streamk):
+    from lds_gnn_b200 import _lib
+    fl = _lib.K2_FORCE_STREAMK if streamk else 0
+    z1, _ = _k2_case(K, 2708, 16, seed=5, flags=fl)
+    z2, _ = _k2_case(K, 2708, 16, seed=5, flags=fl)
     assert np.array_equal(z1, z2)
 
 

@@ -124,6 +124,27 @@ def test_philox_outer_step_matches_oracle(n, f, h, c, p, sparse):
     assert np.abs(new - o["theta_new"]).max() <= 1e-3 * lr * np.abs(o["d_theta_triu"]).max() + 2e-7
 
 
+@pytest.mark.parametrize("n,f,h,c", [(301, 120, 16, 7), (2708, 1433, 16, 7), (700, 64, 64, 7)])
+def test_stream_k_schedule_gives_the_same_step(n, f, h, c):
+    """Large graphs (> 148 row panels) split panels across CTAs; force that schedule at test sizes and compare."""
+    from oracle.make_golden import make_inputs
+    from lds_gnn_b200 import _lib, kernels as K
+    inp = make_inputs(seed=n + 1, n=n, f=f, h=h, c=c, theta_kind="mixed", p=0.5, mask_frac=0.2)
+    eng = K.OuterStep(n, dev(inp["x"]), dev(inp["y"]), dev(inp["mask"]), hidden=h, classes=c)
+    eng.set_weights(dev(inp["w0"]), dev(inp["b0"]), dev(inp["w1"]), dev(inp["b1"]))
+    full = K.theta_triu_to_full(dev(inp["theta_triu"]))
+    outs = []
+    for flags in (0, _lib.K2_FORCE_STREAMK, _lib.K2_FORCE_STREAMK):
+        t = full.clone()
+        lp = torch.empty((n, c), device="cuda")
+        sc = eng.run(t, lr=0.3, seed=5, step=2, dropout_p=0.5, update=True, out_logp=lp, k2_flags=flags).clone()
+        outs.append((t, lp, sc))
+    assert torch.equal(outs[1][0], outs[2][0]) and torch.equal(outs[1][1], outs[2][1])          # stream-K is bitwise reproducible
+    assert (outs[0][1] - outs[1][1]).abs().max().item() <= 1e-5 * outs[0][1].abs().max().item()  # same logits up to summation order
+    assert (outs[0][0] - outs[1][0]).abs().max().item() < 1e-6
+    assert abs(outs[0][2][0].item() - outs[1][2][0].item()) < 1e-5
+
+
 def test_outer_step_update_flag_and_determinism():
     from oracle.make_golden import make_inputs
     from lds_gnn_b200 import kernels as K
@@ -160,3 +181,46 @@ def test_error_paths_do_not_abort():
     import ctypes
     assert lib.lds_outer_step(ctypes.byref(args), None) != 0
     assert "struct_bytes" in _lib.last_error()
+
+
+@pytest.mark.parametrize("n,f,h,c,p,world", [(700, 64, 16, 7, 0.5, 3), (1500, 200, 32, 10, 0.0, 4), (2708, 1433, 16, 7, 0.5, 2),
+                                             (600, 40, 64, 7, 0.5, 5)])
+def test_row_block_sharded_step_matches_single_device(n, f, h, c, p, world):
+    """the oracle of the sharded run is the single-device result. All `world` ranks are emulated on one GPU
+    (same kernels, same phases, exchange = concatenation); the sampled mask must be identical bit for bit (no exchange
+    of random bits), the rest equal up to fp32 summation order."""
+    from oracle.make_golden import make_inputs
+    from lds_gnn_b200 import kernels as K, sharded as S
+    inp = make_inputs(seed=n + world, n=n, f=f, h=h, c=c, theta_kind="mixed", p=p, mask_frac=0.2)
+    w = [dev(inp[k]) for k in ("w0", "b0", "w1", "b1")]
+    x, y, mask = dev(inp["x"]), dev(inp["y"]), dev(inp["mask"])
+    full = K.theta_triu_to_full(dev(inp["theta_triu"]))
+    seed, step, lr = 4242, 7, 0.4
+    # single device
+    eng = K.OuterStep(n, x, y, mask, hidden=h, classes=c)
+    eng.set_weights(*w)
+    ref_theta = full.clone()
+    ref_sc = eng.run(ref_theta, lr=lr, seed=seed, step=step, dropout_p=p, update=True).clone()
+    # `world` row-block shards
+    bounds = [S.shard_bounds(n, world, r) for r in range(world)]
+    bounds = [b for b in bounds if b[1] > 0]
+    assert sum(b[1] for b in bounds) == n
+    shards, thetas = [], []
+    for lo, cnt in bounds:
+        sh = S.ShardedOuterStep(n, lo, cnt, x[lo:lo + cnt], y[lo:lo + cnt], mask[lo:lo + cnt], int(mask.sum().item()), h, c)
+        sh.set_weights(*w)
+        shards.append(sh)
+        thetas.append(full[lo:lo + cnt].clone())
+    sc = S.run_local_group(shards, thetas, lr=lr, seed=seed, step=step, dropout_p=p, update=True)
+    torch.cuda.synchronize()
+    adj = torch.cat([s.eng.buffer("adj") for s in shards], dim=0)
+    assert torch.equal(adj, eng.buffer("adj")), "sharded sampling must reproduce the same graph without any exchange"
+    assert torch.equal(torch.cat([s.eng.buffer("deg") for s in shards]), eng.buffer("deg"))
+    for name in ("z1", "z2", "dz1", "dp1", "cvec"):
+        got = torch.cat([s.eng.buffer(name) for s in shards], dim=0)
+        ref = eng.buffer(name)
+        assert (got - ref).abs().max().item() <= 2e-5 * max(ref.abs().max().item(), 1e-30), name
+    assert abs(sc[0].item() - ref_sc[0].item()) < 1e-5 and abs(sc[1].item() - ref_sc[1].item()) < 1e-6
+    new = torch.cat(thetas, dim=0)
+    assert (new - ref_theta).abs().max().item() < 5e-6       # fp32 summation order of the split propagations differs
+    assert torch.equal(new[:, :n], new[:, :n].t())            # shards stay mutually consistent (exact symmetry)

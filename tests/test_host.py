@@ -322,3 +322,46 @@ def test_multi_rank_timing_is_max_over_ranks(tmp_path):
     outs = [p.communicate(timeout=180) for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert json.loads(outs[0][0].strip().splitlines()[-1]) == [20.0, 30.0]
+
+
+SHARD_WORKER = r"""
+import sys
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+from lds_gnn_b200.sharded import DistComm, shard_bounds
+n = 300                                   # ragged: 256 + 44 rows
+comm = DistComm(n)
+lo, cnt = shard_bounds(n, 2, dist.get_rank())
+local = torch.arange(lo, lo + cnt, dtype=torch.float32).view(-1, 1).repeat(1, 3)
+out = torch.empty(n, 3)
+comm.all_gather_rows(local, out)
+assert torch.equal(out[:, 0], torch.arange(n, dtype=torch.float32)), out[:, 0]
+t = comm.all_reduce_sum(torch.tensor([1.0 + dist.get_rank(), 2.0]))
+assert t.tolist() == [3.0, 4.0]
+n2 = 512                                  # equal blocks: the all_gather_into_tensor path
+comm2 = DistComm(n2)
+lo, cnt = shard_bounds(n2, 2, dist.get_rank())
+out2 = torch.empty(n2, 2)
+comm2.all_gather_rows(torch.full((cnt, 2), float(dist.get_rank())), out2)
+assert comm2.equal and out2[:256].sum() == 0 and out2[256:].sum() == 512
+dist.barrier()
+dist.destroy_process_group()
+print("ok")
+"""
+
+
+def test_sharded_exchange_world_size_2_gloo(tmp_path):
+    """Host logic of the multi-GPU path on CPU: row-block bounds, ragged and equal all-gather, all-reduce."""
+    import socket
+    from lds_gnn_b200.sharded import shard_bounds
+    assert [shard_bounds(65536, 8, r) for r in range(8)] == [(r * 8192, 8192) for r in range(8)]
+    assert [shard_bounds(3327, 4, r) for r in range(4)] == [(0, 896), (896, 896), (1792, 896), (2688, 639)]
+    assert shard_bounds(100, 4, 3) == (100, 0)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "shard_worker.py"
+    script.write_text(SHARD_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=180) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
