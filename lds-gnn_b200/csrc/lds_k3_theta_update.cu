@@ -147,8 +147,8 @@ k3_update_kernel(float* __restrict__ theta, int64_t ldt, int n, int row0, int ro
 // D1(i,j) and D2(j,i) are the same products accumulated in the same k order, so g_ij == g_ji bit for bit
 // (bf16 x bf16 products are exact in fp32; fp32 addition is commutative) — asserted by the tests.
 // One persistent CTA per SM walks 128 x 128 tiles:
-//   warp 0   TMA producer: theta slabs (128 rows x 32 fp32, SWIZZLE_128B) into an 8-slab ring = two tiles in
-//            flight, and per k-block the four 128 x 64 operand blocks
+//   warp 0   TMA producer: theta slabs (128 rows x 32 fp32, SWIZZLE_128B) into a 6-slab ring = 1.5 tiles in
+//            flight, and per k-block the four 128 x 64 operand blocks (two stages)
 //   warp 1   tcgen05.mma issuer, two double-buffered accumulator pairs in TMEM (512 columns)
 //   warps 2-9 epilogue: tcgen05.ld D1/D2, theta from smem, g = (D1 + D2) + (c_i + c_j), SGD step + clamp written
 //            back into the same smem slab, then one TMA store per slab (coalesced, asynchronous)
@@ -156,12 +156,13 @@ k3_update_kernel(float* __restrict__ theta, int64_t ldt, int n, int row0, int ro
 constexpr int K3T_TILE = 128;
 constexpr int K3T_KB = 64;
 constexpr int K3T_SLAB_COLS = 32;
-constexpr int K3T_RING = 8;
+constexpr int K3T_RING = 6;                                  // theta slabs in flight (1.5 tiles)
+constexpr int K3T_OSTAGES = 2;                               // operand stages: the next k-block loads while this one multiplies
 constexpr int K3T_OP_BYTES = K3T_TILE * K3T_KB * 2;          // 16 KB
 constexpr int K3T_STAGE_BYTES = 4 * K3T_OP_BYTES;            // Pm_i, Qm_i, Qm_j, Pm_j
 constexpr int K3T_SLAB_BYTES = K3T_TILE * K3T_SLAB_COLS * 4; // 16 KB
 constexpr int K3T_THREADS = 320;
-constexpr int K3T_SMEM = K3T_STAGE_BYTES + K3T_RING * K3T_SLAB_BYTES + 1024 + 512;
+constexpr int K3T_SMEM = K3T_OSTAGES * K3T_STAGE_BYTES + K3T_RING * K3T_SLAB_BYTES + 1024 + 512;
 
 __global__ void __launch_bounds__(K3T_THREADS, 1)
 k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant__ CUtensorMap tm_pm,
@@ -169,16 +170,16 @@ k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant
              int n, int row0, int rows, int kblocks, int ksteps, float lr) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* ops = smem;                                        // one operand stage
-  uint8_t* slabs = smem + K3T_STAGE_BYTES;                    // theta ring
+  uint8_t* ops = smem;                                        // operand stages
+  uint8_t* slabs = smem + K3T_OSTAGES * K3T_STAGE_BYTES;      // theta ring
   uint64_t* bars = reinterpret_cast<uint64_t*>(slabs + K3T_RING * K3T_SLAB_BYTES);
-  uint64_t* ofull = bars;            // [1]
-  uint64_t* oempty = bars + 1;       // [1]
-  uint64_t* tfull = bars + 2;        // [2]
-  uint64_t* tempty = bars + 4;       // [2]
-  uint64_t* thfull = bars + 6;       // [RING]
-  uint64_t* thempty = bars + 6 + K3T_RING;   // [RING]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * K3T_RING);
+  uint64_t* ofull = bars;            // [OSTAGES]
+  uint64_t* oempty = bars + K3T_OSTAGES;       // [OSTAGES]
+  uint64_t* tfull = bars + 2 * K3T_OSTAGES;    // [2]
+  uint64_t* tempty = tfull + 2;      // [2]
+  uint64_t* thfull = tempty + 2;     // [RING]
+  uint64_t* thempty = thfull + K3T_RING;       // [RING]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(thempty + K3T_RING);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_j = (n + K3T_TILE - 1) / K3T_TILE;
@@ -188,7 +189,7 @@ k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_theta); tma_prefetch_desc(&tm_pm); tma_prefetch_desc(&tm_qm); }
   if (warp == 1) {
     if (lane == 0) {
-      mbar_init(ofull, 1); mbar_init(oempty, 1);
+      for (int i = 0; i < K3T_OSTAGES; ++i) { mbar_init(&ofull[i], 1); mbar_init(&oempty[i], 1); }
       for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
       for (int i = 0; i < K3T_RING; ++i) { mbar_init(&thfull[i], 1); mbar_init(&thempty[i], 1); }
       mbar_fence_init();
@@ -208,20 +209,23 @@ k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tt) {
         const int bi = t / tiles_j, bj = t - bi * tiles_j;
         const int li0 = bi * K3T_TILE, gi0 = row0 + li0, j0 = bj * K3T_TILE;
-        for (int s = 0; s < 4; ++s) {                         // theta first: deepest HBM prefetch
+        // Operands first: the MMA of this tile must never wait on a theta slot, because slots are released by the
+        // epilogue of EARLIER tiles only (a theta-first order deadlocks once the ring is shorter than two tiles).
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const int oq = tt * kblocks + kb, os = oq % K3T_OSTAGES;
+          uint8_t* st = ops + os * K3T_STAGE_BYTES;
+          mbar_wait(&oempty[os], ((oq / K3T_OSTAGES) & 1) ^ 1);
+          mbar_expect_tx(&ofull[os], K3T_STAGE_BYTES);
+          tma_load_2d(st + 0 * K3T_OP_BYTES, &tm_pm, &ofull[os], kb * K3T_KB, gi0);   // A1 = Pm_i
+          tma_load_2d(st + 1 * K3T_OP_BYTES, &tm_qm, &ofull[os], kb * K3T_KB, gi0);   // A2 = Qm_i
+          tma_load_2d(st + 2 * K3T_OP_BYTES, &tm_qm, &ofull[os], kb * K3T_KB, j0);    // B1 = Qm_j
+          tma_load_2d(st + 3 * K3T_OP_BYTES, &tm_pm, &ofull[os], kb * K3T_KB, j0);    // B2 = Pm_j
+        }
+        for (int s = 0; s < 4; ++s) {
           const int q = tt * 4 + s, slot = q % K3T_RING;
           mbar_wait(&thempty[slot], ((q / K3T_RING) & 1) ^ 1);
           mbar_expect_tx(&thfull[slot], K3T_SLAB_BYTES);
           tma_load_2d(slabs + slot * K3T_SLAB_BYTES, &tm_theta, &thfull[slot], j0 + s * K3T_SLAB_COLS, li0);
-        }
-        for (int kb = 0; kb < kblocks; ++kb) {
-          const int oq = tt * kblocks + kb;
-          mbar_wait(oempty, (oq & 1) ^ 1);
-          mbar_expect_tx(ofull, K3T_STAGE_BYTES);
-          tma_load_2d(ops + 0 * K3T_OP_BYTES, &tm_pm, ofull, kb * K3T_KB, gi0);   // A1 = Pm_i
-          tma_load_2d(ops + 1 * K3T_OP_BYTES, &tm_qm, ofull, kb * K3T_KB, gi0);   // A2 = Qm_i
-          tma_load_2d(ops + 2 * K3T_OP_BYTES, &tm_qm, ofull, kb * K3T_KB, j0);    // B1 = Qm_j
-          tma_load_2d(ops + 3 * K3T_OP_BYTES, &tm_pm, ofull, kb * K3T_KB, j0);    // B2 = Pm_j
         }
       }
     }
@@ -229,9 +233,6 @@ k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(K3T_TILE, K3T_TILE);
-      const uint32_t base = smem_u32(ops);
-      const uint64_t a1 = umma_desc_k_sw128(base), a2 = umma_desc_k_sw128(base + K3T_OP_BYTES);
-      const uint64_t b1 = umma_desc_k_sw128(base + 2 * K3T_OP_BYTES), b2 = umma_desc_k_sw128(base + 3 * K3T_OP_BYTES);
       int tt = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tt) {
         const int acc = tt & 1;
@@ -239,13 +240,16 @@ k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant
         tc_fence_after();
         const uint32_t d1 = tmem_base + (uint32_t)(acc * 256), d2 = d1 + 128;
         for (int kb = 0; kb < kblocks; ++kb) {
-          const int oq = tt * kblocks + kb;
-          mbar_wait(ofull, oq & 1);
+          const int oq = tt * kblocks + kb, os = oq % K3T_OSTAGES;
+          mbar_wait(&ofull[os], (oq / K3T_OSTAGES) & 1);
           tc_fence_after();
+          const uint32_t base = smem_u32(ops + os * K3T_STAGE_BYTES);
+          const uint64_t a1 = umma_desc_k_sw128(base), a2 = umma_desc_k_sw128(base + K3T_OP_BYTES);
+          const uint64_t b1 = umma_desc_k_sw128(base + 2 * K3T_OP_BYTES), b2 = umma_desc_k_sw128(base + 3 * K3T_OP_BYTES);
           const int steps = min(4, ksteps - 4 * kb);
           for (int k = 0; k < steps; ++k) tc_mma_bf16(d1, a1 + 2 * k, b1 + 2 * k, idesc, (kb | k) != 0);
           for (int k = 0; k < steps; ++k) tc_mma_bf16(d2, a2 + 2 * k, b2 + 2 * k, idesc, (kb | k) != 0);
-          tc_commit(oempty);
+          tc_commit(&oempty[os]);
         }
         tc_commit(&tfull[acc]);
       }
@@ -334,11 +338,13 @@ k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (storer && pending >= 0) {                    // nothing of this tile stays pending: a slot's release never
+        tma_store_wait_read();                         // depends on work of a later tile
+        mbar_arrive(&thempty[pending]);
+        pending = -1;
+      }
     }
-    if (storer) {
-      if (pending >= 0) { tma_store_wait_read(); mbar_arrive(&thempty[pending]); }
-      tma_store_wait_all();
-    }
+    if (storer) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
