@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--workload", default="citeseer")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scale-ref", action="store_true", help="N > 1: skip the single-GPU run of the same workload on rank 0")
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent single-GPU replicas instead of the sharded N=65536 config")
     ap.add_argument("--cpu-steps", type=int, default=3)
     return ap.parse_args()
@@ -72,7 +73,9 @@ def load_peaks_json():
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi sampling in the background (started early: it needs a few hundred ms to come up); `stop(t0, t1)` keeps
+    the samples whose timestamp falls inside the wall-clock window [t0, t1] of the loaded region."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
@@ -80,12 +83,13 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.file, stderr=subprocess.DEVNULL)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.file, stderr=subprocess.DEVNULL)
         except OSError:
             pass
 
-    def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+    def stop(self, t0=None, t1=None):
+        import datetime
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -98,13 +102,17 @@ class ClockSampler:
         sm, mx, reasons = [], [], set()
         for line in self.file.read().splitlines():
             parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                clk, clk_max = float(parts[1]), float(parts[2])
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.05):
+                continue
+            sm.append(clk); mx.append(clk_max)
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         os.unlink(self.file.name)
@@ -154,6 +162,7 @@ def run_ours(args, rank, world, device):
     from lds_gnn_b200.trainers.inner import InnerProblemTrainer
     from lds_gnn_b200.trainers.outer import OuterProblemTrainer
 
+    clocks = ClockSampler(torch.cuda.current_device())
     data, weights, opt_mask, shape = make_workload(args.workload, seed=rank)
     n, f, h, c = shape["n"], shape["f"], shape["h"], shape["c"]
     data = data.to(device)
@@ -176,7 +185,7 @@ def run_ours(args, rank, world, device):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks = ClockSampler(torch.cuda.current_device())
+    wall0 = time.time()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     torch.cuda.synchronize()
@@ -191,15 +200,21 @@ def run_ours(args, rank, world, device):
     dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
     loss_after = float(eng.scalars[0].item())
 
-    # warm-L2 figure (back-to-back, no flush) for context
+    # warm-L2 figure (back-to-back, no flush) for context; run for >= 0.6 s so the clock sampler sees the loaded GPU
     torch.cuda.synchronize()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    warm_steps = 0
+    wall_sustained = time.time()
     t0.record()
-    for k in range(args.steps):
-        one(10_000 + k, lr)
+    while True:
+        for k in range(args.steps):
+            one(10_000 + warm_steps + k, lr)
+        warm_steps += args.steps
+        if time.time() - wall_sustained > 0.6 or warm_steps > 200_000:
+            break
     t1.record()
     torch.cuda.synchronize()
-    warm_ms = t0.elapsed_time(t1)
+    warm_ms = t0.elapsed_time(t1) * args.steps / warm_steps
 
     # ---- per-kernel durations (CUDA events inside the library, on the launching stream) ---------------
     per_kernel = {}
@@ -213,7 +228,7 @@ def run_ours(args, rank, world, device):
         cnt = lib.lds_profile_end(ms_buf, id_buf, 64)
         for i in range(max(cnt, 0)):
             per_kernel.setdefault(int(id_buf[i]), []).append(float(ms_buf[i]))
-    clock_info = clocks.stop()
+    clock_info = clocks.stop(wall0, time.time())
 
     # ---- e2e arm: the reference-facing API with host buffers ------------------------------------------
     gcn = MetaDenseGCN(f, h, c, dropout=HYPER["dropout"]).to(device)
@@ -343,6 +358,7 @@ def run_large(args, rank, world, device, workload):
     from lds_gnn_b200 import _lib, kernels as K, sharded as S
     from lds_gnn_b200.data import SHAPES
     n, f, c, h, _, _ = SHAPES[workload]
+    clocks = ClockSampler(torch.cuda.current_device())
     lo, cnt = S.shard_bounds(n, world, rank) if world > 1 else (0, n)
     d = make_large_rows(workload, device, lo, cnt, seed=0)
     rng = np.random.default_rng(1)
@@ -373,7 +389,7 @@ def run_large(args, rank, world, device, workload):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks = ClockSampler(torch.cuda.current_device())
+    wall0 = time.time()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t0.record()
@@ -394,7 +410,6 @@ def run_large(args, rank, world, device, workload):
         cntm = lib.lds_profile_end(ms_buf, id_buf, 64)
         for i in range(max(cntm, 0)):
             per_kernel.setdefault(int(id_buf[i]), []).append(float(ms_buf[i]))
-    clock_info = clocks.stop()
     # e2e: the step's weights from pinned host memory, (loss, acc) back to the host, every step
     torch.cuda.synchronize()
     if world > 1:
@@ -406,8 +421,34 @@ def run_large(args, rank, world, device, workload):
         loss_acc = (out if world > 1 else eng.scalars)[:2].tolist()
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - ts) * 1e3
+    clock_info = clocks.stop(wall0, time.time())
     dev_ms, e2e_ms = reduce_rank_times([dev_ms, e2e_ms], device, world)
     value = args.steps / (dev_ms / 1e3)
+    # strong-scaling reference: the SAME workload on one GPU (rank 0), so the sharded number can be read against it
+    scaling_reference = None
+    if world > 1 and not args.no_scale_ref:
+        if rank == 0:
+            d1 = make_large_rows(workload, device, 0, n, seed=0)
+            eng1 = K.OuterStep(n, d1["x"], d1["y"], d1["mask"], hidden=h, classes=c)
+            eng1.set_weights(*views)
+            th1 = d1["theta"]
+            for k in range(2):
+                eng1.run(th1, lr=0.1, seed=1234, step=k, dropout_p=HYPER["dropout"], update=True)
+            torch.cuda.synchronize()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            ref_steps = 4
+            for k in range(ref_steps):
+                eng1.run(th1, lr=0.1, seed=1234, step=10 + k, dropout_p=HYPER["dropout"], update=True)
+            r1.record()
+            torch.cuda.synchronize()
+            ref_ms = r0.elapsed_time(r1) / ref_steps
+            scaling_reference = {"n_gpus": 1, "workload": f"same N={n} step on one GPU (rank 0, unsharded)", "value": round(1e3 / ref_ms, 3),
+                                 "unit": UNIT, "ms_per_step": round(ref_ms, 4), "steps": ref_steps,
+                                 "speedup": round(value / (1e3 / ref_ms), 3), "efficiency": round(value / (1e3 / ref_ms) / world, 4)}
+            del eng1, d1, th1
+            torch.cuda.empty_cache()
+        dist.barrier()
     hbm_peak, peak_src = peaks()
     rows_local = cnt
     alg = {0: 6 * rows_local * n, 3: 2 * rows_local * n, 4: 2 * rows_local * n, 5: 2 * rows_local * n, 6: 2 * rows_local * n,
@@ -445,6 +486,7 @@ def run_large(args, rank, world, device, workload):
         "step_roofline": {"algorithmic_bytes_per_step_per_gpu": step_bytes,
                           "frac_of_hbm_peak": round(step_bytes / (dev_ms / 1e3 / args.steps) / 1e9 / hbm_peak, 4)},
         "kernels": kernel_summary, "last_metrics": {"loss": loss_acc[0], "acc": loss_acc[1]},
+        "scaling_reference": scaling_reference,
         "cpu_baseline": {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                          "sample": f"not runnable: the reference keeps ~25 dense N x N fp32 tensors ({25 * n * n * 4 / 1e9:.0f} GB) and does "
                                    f"6 N^3 SGEMMs per step at N={n}; see --impl reference for the extrapolated figure"},
@@ -529,6 +571,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"               # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=device)
     workload = args.workload
     if world > 1 and workload in ("citeseer", "cora", "tiny") and not args.replicas:
