@@ -177,6 +177,7 @@ typedef struct lds_outer_step_args {
   uint32_t reserved2;
   const float* opnd_full;
   const float* fa_full; const float* fb_full; const float* c_full;
+  unsigned long long* k2_timeline;   /* optional debug buffer [4][512][8] of %globaltimer stamps, else NULL            */
 } lds_outer_step_args;
 
 #define LDS_PHASE_SAMPLE   1u

@@ -75,6 +75,7 @@ class OuterStepArgs(Structure):
         ("k2_flags", c_uint32), ("k3_flags", c_uint32),
         ("row0", c_int32), ("rows", c_int32), ("phases", c_uint32), ("reserved2", c_uint32),
         ("opnd_full", c_void_p), ("fa_full", c_void_p), ("fb_full", c_void_p), ("c_full", c_void_p),
+        ("k2_timeline", c_void_p),
     ]
 
 

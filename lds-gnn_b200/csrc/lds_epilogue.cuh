@@ -57,6 +57,7 @@ struct EpiArgs {
   __nv_bfloat16* bt_hi; __nv_bfloat16* bt_lo; int64_t ldb;
   float* loss_part; float* corr_part; int nblk;       // one partial per 128-row panel
   float* out_scalars; float* out_logp;
+  unsigned long long* timeline;   // optional debug: [grid][8] globaltimer stamps per CTA (scripts/k2_timeline.py), else NULL
   // K2_EPI_PLAIN (standalone lds_k2_propagate)
   float* z_out; int64_t ld_z; const float* scale_out; int rows; int width;
 };
@@ -174,27 +175,44 @@ template <int HP>
 __device__ __forceinline__ void epi_bwd1(const EpiArgs& a, int i, float (&v)[HP]) {
   if (i >= a.n) return;
   const float ri = a.rs[i];
+  const float di = a.deg[i];
   const int d = a.h + a.c;
-  float rho = 0.f, kappa = 0.f;
   float* fa = a.fa + (int64_t)i * a.ldf;
   float* fb = a.fb + (int64_t)i * a.ldf;
+  float dz1[HP], p1[HP], z1[HP];
+#pragma unroll
+  for (int c = 0; c < HP; ++c) {                               // every load of the row in flight before the first use
+    const bool in = c < a.h;
+    dz1[c] = in ? a.dz1[(int64_t)i * a.h + c] : 0.f;
+    p1[c] = in ? a.p1[(int64_t)i * a.h + c] : 0.f;
+    z1[c] = in ? a.z1[(int64_t)i * a.h + c] : 0.f;
+  }
+  float rho = 0.f, kappa = 0.f;
+  for (int o0 = 0; o0 < a.c; o0 += 8) {
+    float dz2[8], p2[8], z2[8], dp2[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const bool in = o0 + u < a.c;
+      const int64_t idx = (int64_t)i * a.c + o0 + u;
+      dz2[u] = in ? a.dz2[idx] : 0.f; p2[u] = in ? a.p2[idx] : 0.f; z2[u] = in ? a.z2[idx] : 0.f; dp2[u] = in ? a.dp2[idx] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) if (o0 + u < a.c) {
+      rho = fmaf(dz2[u], z2[u], rho);
+      kappa = fmaf(p2[u], dp2[u], kappa);
+      fa[a.h + o0 + u] = ri * dz2[u]; fb[a.h + o0 + u] = ri * p2[u];
+    }
+  }
 #pragma unroll
   for (int c = 0; c < HP; ++c) if (c < a.h) {
     const float dp1 = ri * v[c];
+    rho = fmaf(dz1[c], z1[c], rho);
+    kappa = fmaf(p1[c], dp1, kappa);
     a.dp1[(int64_t)i * a.h + c] = dp1;
-    const float dz1 = a.dz1[(int64_t)i * a.h + c], p1 = a.p1[(int64_t)i * a.h + c];
-    rho = fmaf(dz1, a.z1[(int64_t)i * a.h + c], rho);
-    kappa = fmaf(p1, dp1, kappa);
-    fa[c] = ri * dz1; fb[c] = ri * p1;
-  }
-  for (int o = 0; o < a.c; ++o) {
-    const float dz2 = a.dz2[(int64_t)i * a.c + o], p2 = a.p2[(int64_t)i * a.c + o];
-    rho = fmaf(dz2, a.z2[(int64_t)i * a.c + o], rho);
-    kappa = fmaf(p2, a.dp2[(int64_t)i * a.c + o], kappa);
-    fa[a.h + o] = ri * dz2; fb[a.h + o] = ri * p2;
+    fa[c] = ri * dz1[c]; fb[c] = ri * p1[c];
   }
   for (int k = d; k < (int)a.ldf; ++k) { fa[k] = 0.f; fb[k] = 0.f; }
-  a.cvec[i] = -(rho + kappa) / (2.f * a.deg[i]);               // both D^-1/2 factors depend on the row sum
+  a.cvec[i] = -(rho + kappa) / (2.f * di);                     // both D^-1/2 factors depend on the row sum
 }
 
 }  // namespace lds

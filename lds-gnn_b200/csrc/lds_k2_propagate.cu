@@ -16,6 +16,7 @@
 //               tcgen05.commit -> frees the smem stage / publishes the accumulator; owns the TMEM allocation
 //   warps 2-5   epilogue: tcgen05.ld 32x32b -> registers -> fp32 partial tile in global memory
 //   accumulators are double-buffered in TMEM so the next segment's MMAs overlap the epilogue.
+#include <stdlib.h>
 #include <string.h>
 #include "lds_epilogue.cuh"
 #include "lds_tc.cuh"
@@ -32,7 +33,7 @@ template <int HP> struct K2Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
   static constexpr int TMEM_COLS = (2 * HP < 32) ? 32 : 2 * HP;      // two accumulators, power of two >= 32
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers + tmem slot*/;
-  static constexpr int CTAS_PER_SM = 1;
+  static constexpr int CTAS_PER_SM = (SMEM_BYTES <= 113 * 1024) ? 2 : 1;
 };
 
 template <int HP, int EPI>
@@ -137,6 +138,14 @@ k2_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
     const int quarter = warp & 3;                            // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const int etid = (warp - 2) * 32 + lane;                 // 0..127
+    auto stamp = [&](int k) {
+      if (ea.timeline != nullptr && etid == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        ea.timeline[(size_t)cta * 8 + k] = t;
+      }
+    };
+    stamp(0);                                                // epilogue warps past the setup barrier
     if (EPI == K2_EPI_BWD2 && cta == 0 && etid == 0) {       // the layer-2 launch is complete: finalise loss / accuracy
       float l = 0.f, c = 0.f;
       for (int k = 0; k < ea.nblk; ++k) { l += ea.loss_part[k]; c += ea.corr_part[k]; }
@@ -149,6 +158,7 @@ k2_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
       const int cnt = min(s.kblocks - kb0, hi - pos);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      stamp(1);                                              // accumulator of this segment complete (all MMAs retired)
       float v[HP];
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * HP);
 #pragma unroll
@@ -170,6 +180,7 @@ k2_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
         float* dst = partial + ((int64_t)(cta * s.max_seg + seg) * K2_BLOCK_M + row) * HP;
 #pragma unroll
         for (int c0 = 0; c0 < HP; c0 += 4) *reinterpret_cast<float4*>(dst + c0) = make_float4(v[c0], v[c0 + 1], v[c0 + 2], v[c0 + 3]);
+        stamp(2);                                            // partial tile written
         __threadfence();                                     // publish the partial tile before counting this CTA in
         named_bar_sync(1, 128);
         const int c_first = (p * s.kblocks) / s.per_cta;
@@ -182,31 +193,39 @@ k2_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
         }
         named_bar_sync(1, 128);
         run_epilogue = sh_last != 0;
+        stamp(3);                                            // fence + counter round trip done
         if (run_epilogue) {
           __threadfence();
 #pragma unroll
           for (int c0 = 0; c0 < HP; ++c0) v[c0] = 0.f;
-          // fixed order => bitwise reproducible; two contributors' tiles are in flight before either is added
+          // fixed order => bitwise reproducible; RB contributors' tiles are in flight before any is added
+          constexpr int RB = (HP <= 16) ? 8 : (HP <= 32) ? 4 : (HP <= 64) ? 2 : 1;
           const int64_t tile_elems = (int64_t)K2_BLOCK_M * HP;
           const float* rowbase = partial + (int64_t)row * HP;
-          for (int c = c_first; c <= c_last; c += 2) {
-            const int sg0 = p - (c * s.per_cta) / s.kblocks;
-            const bool two = (c + 1 <= c_last);
-            const int sg1 = two ? p - ((c + 1) * s.per_cta) / s.kblocks : 0;
-            const float4* src0 = reinterpret_cast<const float4*>(rowbase + (int64_t)(c * s.max_seg + sg0) * tile_elems);
-            const float4* src1 = reinterpret_cast<const float4*>(rowbase + (int64_t)((two ? c + 1 : c) * s.max_seg + sg1) * tile_elems);
-            float4 t0[HP / 4], t1[HP / 4];
+          for (int c = c_first; c <= c_last; c += RB) {
+            float4 t[RB][HP / 4];
 #pragma unroll
-            for (int c0 = 0; c0 < HP / 4; ++c0) { t0[c0] = __ldcg(src0 + c0); t1[c0] = __ldcg(src1 + c0); }
+            for (int u = 0; u < RB; ++u) {
+              const int cc = min(c + u, c_last);
+              const int sg = p - (cc * s.per_cta) / s.kblocks;
+              const float4* src = reinterpret_cast<const float4*>(rowbase + (int64_t)(cc * s.max_seg + sg) * tile_elems);
 #pragma unroll
-            for (int c0 = 0; c0 < HP / 4; ++c0) {
-              v[4 * c0] += t0[c0].x; v[4 * c0 + 1] += t0[c0].y; v[4 * c0 + 2] += t0[c0].z; v[4 * c0 + 3] += t0[c0].w;
-              if (two) { v[4 * c0] += t1[c0].x; v[4 * c0 + 1] += t1[c0].y; v[4 * c0 + 2] += t1[c0].z; v[4 * c0 + 3] += t1[c0].w; }
+              for (int c0 = 0; c0 < HP / 4; ++c0) t[u][c0] = __ldcg(src + c0);
+            }
+#pragma unroll
+            for (int u = 0; u < RB; ++u) {
+              if (c + u <= c_last) {
+#pragma unroll
+                for (int c0 = 0; c0 < HP / 4; ++c0) {
+                  v[4 * c0] += t[u][c0].x; v[4 * c0 + 1] += t[u][c0].y; v[4 * c0 + 2] += t[u][c0].z; v[4 * c0 + 3] += t[u][c0].w;
+                }
+              }
             }
           }
         }
       }
       if (run_epilogue) {                                    // uniform over the 128 epilogue threads
+        stamp(4);                                            // partial tiles reduced
         const int i = p * K2_BLOCK_M + row;
         if (EPI == K2_EPI_PLAIN) epi_plain<HP>(ea, i, v);
         else if (EPI == K2_EPI_LAYER1) epi_layer1<HP>(ea, i, v);
@@ -224,8 +243,10 @@ k2_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
           }
           named_bar_sync(1, 128);
         }
+        stamp(5);                                            // row epilogue done
       }
     }
+    stamp(6);
   }
 
   tc_fence_before();
@@ -319,7 +340,8 @@ K2Sched k2_make_schedule(int n, int rows, int hp, bool force_streamk) {
   s.panels = (int)ceil_div(rows, K2_BLOCK_M);
   s.kblocks = (int)ceil_div(n, K2_BLOCK_K);
   s.total = s.panels * s.kblocks;
-  const int grid_max = kNumSMsB200 * k2_ctas_per_sm(hp);     // a pure function of the shape: workspace sizing needs no device query
+  int grid_max = kNumSMsB200 * k2_ctas_per_sm(hp);           // a pure function of the shape: workspace sizing needs no device query
+  if (const char* e = getenv("LDS_K2_GRID_MAX")) { const int v = atoi(e); if (v > 0 && v <= grid_max) grid_max = v; }   // tuning knob
   // Stream-K over the linearised (panel, k-block) space. Measured on B200 (Citeseer shape, 26 panels): one CTA per
   // panel streams at only ~35 GB/s per SM (33 us per propagate) — every SM has to pull on the TMA path, so panels are
   // split even when they could each own a CTA (20 us). `force_streamk` is kept for tests of larger splits.

@@ -395,6 +395,7 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
       const int32_t r0 = k2_launch_prep(A.opnd_full, ld_opnd, A.n, width, s.hp, nullptr, bt_hi, bt_lo, L.ldb, counters, 0, stream);
       if (r0 != LDS_OK) return r0;
     }
+    E.timeline = A.k2_timeline ? A.k2_timeline + (size_t)(mark - 3) * 512 * 8 : nullptr;
     const int32_t r = k2_launch_mma(buf(B_A), L.lda, A.n, rows, bt_hi, bt_lo, L.ldb, fbuf(B_PARTIAL), counters, s, use_lo, epi, E, stream);
     profile_mark(stream, mark);
     return r;

@@ -259,7 +259,8 @@ class OuterStep:
 
     def run(self, theta_full, lr, seed, step, dropout_p=0.0, update=True, u=None, keep_x=None, keep_h=None,
             opt_kind=_lib.OPT_SGD, adam_m=None, adam_v=None, betas=(0.9, 0.999), eps=1e-8, adam_t=1,
-            out_logp=None, k2_flags=0, k3_flags=0, phases=None, opnd_full=None, fa_full=None, fb_full=None, c_full=None):
+            out_logp=None, k2_flags=0, k3_flags=0, phases=None, opnd_full=None, fa_full=None, fb_full=None, c_full=None,
+            k2_timeline=None):
         """Enqueue one fused outer step on the current stream. Results: self.scalars[0:2] = (loss, acc)."""
         a = self.args
         a.struct_bytes = ctypes.sizeof(_lib.OuterStepArgs)
@@ -298,5 +299,6 @@ class OuterStep:
         a.fa_full = None if fa_full is None else fa_full.data_ptr()
         a.fb_full = None if fb_full is None else fb_full.data_ptr()
         a.c_full = None if c_full is None else c_full.data_ptr()
+        a.k2_timeline = None if k2_timeline is None else k2_timeline.data_ptr()
         _lib.check(self.lib.lds_outer_step(ctypes.byref(a), _stream()), "lds_outer_step")
         return self.scalars
