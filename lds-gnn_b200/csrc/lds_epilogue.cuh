@@ -50,7 +50,6 @@ struct EpiArgs {
   const float* deg; const float* rs;
   float* p1; float* z1; float* p2; float* z2; float* dz2; float* dp2; float* dz1; float* dp1;
   float* fa; float* fb; int64_t ldf; float* cvec;
-  __nv_bfloat16* pm; __nv_bfloat16* qm; int kp;
   const float* w1; const float* b1;
   const int64_t* y; const uint8_t* mask; float inv_m;
   DropCfg drop_h;

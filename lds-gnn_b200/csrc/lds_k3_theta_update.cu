@@ -140,44 +140,96 @@ k3_update_kernel(float* __restrict__ theta, int64_t ldt, int n, int row0, int ro
 
 // ================================================================================================
 // Tensor-core variant (SGD): the rank-2d term is a GEMM, so at large d (h = 64 => d = 71, 142 FMA per element
-// on CUDA cores) it must run on tcgen05 or the update stops being an HBM stream. Operands are the bf16
-// hi/lo-split factor matrices laid out K-major:
-//     Pm = [fa_hi | fa_hi | fa_lo | 0],  Qm = [fb_hi | fb_lo | fb_hi | 0]          ([n][Kp] bf16, Kp = round_up(3d, 64))
-//     D1 = Pm_i Qm_j^T ~= fa_i.fb_j,    D2 = Qm_i Pm_j^T ~= fb_i.fa_j               (fp32 accumulation in TMEM)
-// D1(i,j) and D2(j,i) are the same products accumulated in the same k order, so g_ij == g_ji bit for bit
-// (bf16 x bf16 products are exact in fp32; fp32 addition is commutative) — asserted by the tests.
-// One persistent CTA per SM walks 128 x 128 tiles:
-//   warp 0   TMA producer: theta slabs (128 rows x 32 fp32, SWIZZLE_128B) into a 6-slab ring = 1.5 tiles in
-//            flight, and per k-block the four 128 x 64 operand blocks (two stages)
-//   warp 1   tcgen05.mma issuer, two double-buffered accumulator pairs in TMEM (512 columns)
+// on CUDA cores) it must run on tcgen05 or the update stops being an HBM stream. Operands: the bf16 hi/lo split
+// of the factor rows, packed K-major and INTERLEAVED per 16-column step so that one 128-byte swizzle atom holds
+// everything a k-step needs:
+//     F[i][64 q + 16 t + k] = block_t(i)[16 q + k],   blocks t = 0 a_hi, 1 a_lo, 2 b_hi, 3 b_lo   (a = fa, b = fb)
+//     ([n][kf] bf16, kf = 4 * round_up(d, 16); 8 B per factor element instead of the 12 B of a K-concatenated
+//      [hi|hi|lo] x [hi|lo|hi] packing — the operand re-reads from L2, not HBM, were the bound at d = 71)
+// Per k-step q the issuer runs six 128x128x16 MMAs on the two boxes F_i[q], F_j[q]:
+//     D1 += a_hi b_hi' + a_hi b_lo' + a_lo b_hi'        D2 += b_hi a_hi' + b_lo a_hi' + b_hi a_lo'
+// D1(i,j) and D2(j,i) are the same exact bf16 products accumulated in the same order, so g_ij == g_ji bit for
+// bit (fp32 addition is commutative) — asserted by the tests; row-block shards stay consistent with no exchange.
+// One persistent CTA per SM walks a contiguous range of 128 x 128 tiles:
+//   warp 0    TMA producer of the operand boxes (128 x 64 bf16, SWIZZLE_128B), K3T_OSTAGES stages of (F_i[q], F_j[q])
+//   warp 1    tcgen05.mma issuer, two double-buffered accumulator pairs in TMEM (512 columns)
 //   warps 2-9 epilogue: tcgen05.ld D1/D2, theta from smem, g = (D1 + D2) + (c_i + c_j), SGD step + clamp written
-//            back into the same smem slab, then one TMA store per slab (coalesced, asynchronous)
+//             back into the same smem slab, then one TMA store per slab (coalesced, asynchronous)
+//   warp 10   TMA producer of the theta slabs (128 rows x 32 fp32, SWIZZLE_128B) into a K3T_RING-slab ring. The ring
+//             depth is what hides HBM latency: measured at N = 20 000, 4 / 6 / 8 slabs in flight = 875 / 705 / 630 us.
 // ================================================================================================
 constexpr int K3T_TILE = 128;
-constexpr int K3T_KB = 64;
+constexpr int K3T_KB = 64;                                   // packed columns per k-step = one 128-byte swizzle atom
 constexpr int K3T_SLAB_COLS = 32;
-constexpr int K3T_RING = 6;                                  // theta slabs in flight (1.5 tiles)
-constexpr int K3T_OSTAGES = 2;                               // operand stages: the next k-block loads while this one multiplies
+constexpr int K3T_RING = 8;                                  // theta slabs in flight (2 tiles)
+constexpr int K3T_OSTAGES = 3;                               // operand stages
 constexpr int K3T_OP_BYTES = K3T_TILE * K3T_KB * 2;          // 16 KB
-constexpr int K3T_STAGE_BYTES = 4 * K3T_OP_BYTES;            // Pm_i, Qm_i, Qm_j, Pm_j
+constexpr int K3T_STAGE_BYTES = 2 * K3T_OP_BYTES;            // F_i[q], F_j[q]
 constexpr int K3T_SLAB_BYTES = K3T_TILE * K3T_SLAB_COLS * 4; // 16 KB
-constexpr int K3T_THREADS = 320;
+constexpr int K3T_THREADS = 352;
 constexpr int K3T_SMEM = K3T_OSTAGES * K3T_STAGE_BYTES + K3T_RING * K3T_SLAB_BYTES + 1024 + 512;
 
+// One thread's row of one theta slab (32 columns, 128-byte swizzled in smem): g = (D1 + D2) + (c_i + c_j) with the
+// diagonal and clamp-backward masks, SGD step + projection written back in place (src/models/factory.py:66-69,
+// src/trainers/outer.py:78-83, src/models/graph.py:16-20).
+// `cpre` holds c_j of the slab's 32 columns for interior tiles: loaded BEFORE the wait on the theta slab, because the
+// 224 KB shared-memory carve-out leaves almost no L1 and a cvec load issued per cell cost an L2 round trip each
+// (45 % of the kernel's stall samples at N = 20 000).
+__device__ __forceinline__ void k3_update_slab_row(uint8_t* slab, int row, const uint32_t (&d1)[32], const uint32_t (&d2)[32],
+                                                   const float* __restrict__ cvec, const float4 (&cpre)[8], bool interior,
+                                                   float ci, int gi, int jb, int n, float lr) {
+  if (interior) {
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+      float4* cell = reinterpret_cast<float4*>(slab + ((c4 ^ (row & 7)) << 4));
+      const float4 th = *cell;
+      const float4 cv = cpre[c4];
+      const float tv[4] = {th.x, th.y, th.z, th.w}, cj[4] = {cv.x, cv.y, cv.z, cv.w};
+      float nv[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        float g = (__uint_as_float(d1[4 * c4 + b]) + __uint_as_float(d2[4 * c4 + b])) + (ci + cj[b]);
+        if (tv[b] < 0.f || tv[b] > 1.f) g = 0.f;                 // clamp backward
+        nv[b] = fminf(fmaxf(fmaf(-lr, g, tv[b]), 0.f), 1.f);
+      }
+      *cell = make_float4(nv[0], nv[1], nv[2], nv[3]);
+    }
+  } else {
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+      float4* cell = reinterpret_cast<float4*>(slab + ((c4 ^ (row & 7)) << 4));
+      float4 th = *cell;
+      const int gj = jb + 4 * c4;
+      float cj[4];
+      if (gj + 3 < n) { const float4 cv = *reinterpret_cast<const float4*>(cvec + gj); cj[0] = cv.x; cj[1] = cv.y; cj[2] = cv.z; cj[3] = cv.w; }
+      else { for (int b = 0; b < 4; ++b) cj[b] = (gj + b < n) ? cvec[gj + b] : 0.f; }
+      float tv[4] = {th.x, th.y, th.z, th.w};
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        float g = (__uint_as_float(d1[4 * c4 + b]) + __uint_as_float(d2[4 * c4 + b])) + (ci + cj[b]);
+        if (gi == gj + b) g = 0.f;
+        if (tv[b] < 0.f || tv[b] > 1.f) g = 0.f;
+        const float nv = fminf(fmaxf(fmaf(-lr, g, tv[b]), 0.f), 1.f);
+        if (gj + b < n) tv[b] = nv;               // the TMA store clips at 16-byte granularity: leave padding as loaded
+      }
+      *cell = make_float4(tv[0], tv[1], tv[2], tv[3]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(K3T_THREADS, 1)
-k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant__ CUtensorMap tm_pm,
-             const __grid_constant__ CUtensorMap tm_qm, const float* __restrict__ cvec,
-             int n, int row0, int rows, int kblocks, int ksteps, float lr) {
+k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant__ CUtensorMap tm_f,
+             const float* __restrict__ cvec, int n, int row0, int rows, int ksteps, float lr) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* ops = smem;                                        // operand stages
   uint8_t* slabs = smem + K3T_OSTAGES * K3T_STAGE_BYTES;      // theta ring
   uint64_t* bars = reinterpret_cast<uint64_t*>(slabs + K3T_RING * K3T_SLAB_BYTES);
-  uint64_t* ofull = bars;            // [OSTAGES]
+  uint64_t* ofull = bars;                      // [OSTAGES]
   uint64_t* oempty = bars + K3T_OSTAGES;       // [OSTAGES]
   uint64_t* tfull = bars + 2 * K3T_OSTAGES;    // [2]
-  uint64_t* tempty = tfull + 2;      // [2]
-  uint64_t* thfull = tempty + 2;     // [RING]
+  uint64_t* tempty = tfull + 2;                // [2]
+  uint64_t* thfull = tempty + 2;               // [RING]
   uint64_t* thempty = thfull + K3T_RING;       // [RING]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(thempty + K3T_RING);
 
@@ -185,8 +237,10 @@ k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant
   const int tiles_j = (n + K3T_TILE - 1) / K3T_TILE;
   const int tiles_i = (rows + K3T_TILE - 1) / K3T_TILE;
   const int num_tiles = tiles_i * tiles_j;
+  const int t_lo = (int)(((int64_t)blockIdx.x * num_tiles) / gridDim.x);          // contiguous range: F_i stays hot in L2/L1
+  const int t_hi = (int)(((int64_t)(blockIdx.x + 1) * num_tiles) / gridDim.x);
 
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_theta); tma_prefetch_desc(&tm_pm); tma_prefetch_desc(&tm_qm); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_theta); tma_prefetch_desc(&tm_f); }
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < K3T_OSTAGES; ++i) { mbar_init(&ofull[i], 1); mbar_init(&oempty[i], 1); }
@@ -203,29 +257,32 @@ k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer: operand boxes =====
     if (lane == 0) {
-      int tt = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tt) {
+      int oq = 0;
+      for (int t = t_lo; t < t_hi; ++t) {
         const int bi = t / tiles_j, bj = t - bi * tiles_j;
-        const int li0 = bi * K3T_TILE, gi0 = row0 + li0, j0 = bj * K3T_TILE;
-        // Operands first: the MMA of this tile must never wait on a theta slot, because slots are released by the
-        // epilogue of EARLIER tiles only (a theta-first order deadlocks once the ring is shorter than two tiles).
-        for (int kb = 0; kb < kblocks; ++kb) {
-          const int oq = tt * kblocks + kb, os = oq % K3T_OSTAGES;
+        for (int q = 0; q < ksteps; ++q, ++oq) {
+          const int os = oq % K3T_OSTAGES;
           uint8_t* st = ops + os * K3T_STAGE_BYTES;
-          mbar_wait(&oempty[os], ((oq / K3T_OSTAGES) & 1) ^ 1);
+          mbar_wait(&oempty[os], (uint32_t)(((oq / K3T_OSTAGES) & 1) ^ 1));
           mbar_expect_tx(&ofull[os], K3T_STAGE_BYTES);
-          tma_load_2d(st + 0 * K3T_OP_BYTES, &tm_pm, &ofull[os], kb * K3T_KB, gi0);   // A1 = Pm_i
-          tma_load_2d(st + 1 * K3T_OP_BYTES, &tm_qm, &ofull[os], kb * K3T_KB, gi0);   // A2 = Qm_i
-          tma_load_2d(st + 2 * K3T_OP_BYTES, &tm_qm, &ofull[os], kb * K3T_KB, j0);    // B1 = Qm_j
-          tma_load_2d(st + 3 * K3T_OP_BYTES, &tm_pm, &ofull[os], kb * K3T_KB, j0);    // B2 = Pm_j
+          tma_load_2d(st, &tm_f, &ofull[os], q * K3T_KB, row0 + bi * K3T_TILE);          // F_i[q]
+          tma_load_2d(st + K3T_OP_BYTES, &tm_f, &ofull[os], q * K3T_KB, bj * K3T_TILE);   // F_j[q]
         }
-        for (int s = 0; s < 4; ++s) {
-          const int q = tt * 4 + s, slot = q % K3T_RING;
-          mbar_wait(&thempty[slot], ((q / K3T_RING) & 1) ^ 1);
+      }
+    }
+  } else if (warp == 10) {
+    // ===== TMA producer: theta slabs (never blocked by an operand wait) =====
+    if (lane == 0) {
+      int q = 0;
+      for (int t = t_lo; t < t_hi; ++t) {
+        const int bi = t / tiles_j, bj = t - bi * tiles_j;
+        for (int s = 0; s < 4; ++s, ++q) {
+          const int slot = q % K3T_RING;
+          mbar_wait(&thempty[slot], (uint32_t)(((q / K3T_RING) & 1) ^ 1));
           mbar_expect_tx(&thfull[slot], K3T_SLAB_BYTES);
-          tma_load_2d(slabs + slot * K3T_SLAB_BYTES, &tm_theta, &thfull[slot], j0 + s * K3T_SLAB_COLS, li0);
+          tma_load_2d(slabs + slot * K3T_SLAB_BYTES, &tm_theta, &thfull[slot], bj * K3T_TILE + s * K3T_SLAB_COLS, bi * K3T_TILE);
         }
       }
     }
@@ -233,22 +290,28 @@ k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(K3T_TILE, K3T_TILE);
-      int tt = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tt) {
+      int oq = 0, tt = 0;
+      for (int t = t_lo; t < t_hi; ++t, ++tt) {
         const int acc = tt & 1;
-        mbar_wait(&tempty[acc], ((tt >> 1) & 1) ^ 1);
+        mbar_wait(&tempty[acc], (uint32_t)(((tt >> 1) & 1) ^ 1));
         tc_fence_after();
         const uint32_t d1 = tmem_base + (uint32_t)(acc * 256), d2 = d1 + 128;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          const int oq = tt * kblocks + kb, os = oq % K3T_OSTAGES;
-          mbar_wait(&ofull[os], (oq / K3T_OSTAGES) & 1);
+        for (int q = 0; q < ksteps; ++q, ++oq) {
+          const int os = oq % K3T_OSTAGES;
+          mbar_wait(&ofull[os], (uint32_t)((oq / K3T_OSTAGES) & 1));
           tc_fence_after();
           const uint32_t base = smem_u32(ops + os * K3T_STAGE_BYTES);
-          const uint64_t a1 = umma_desc_k_sw128(base), a2 = umma_desc_k_sw128(base + K3T_OP_BYTES);
-          const uint64_t b1 = umma_desc_k_sw128(base + 2 * K3T_OP_BYTES), b2 = umma_desc_k_sw128(base + 3 * K3T_OP_BYTES);
-          const int steps = min(4, ksteps - 4 * kb);
-          for (int k = 0; k < steps; ++k) tc_mma_bf16(d1, a1 + 2 * k, b1 + 2 * k, idesc, (kb | k) != 0);
-          for (int k = 0; k < steps; ++k) tc_mma_bf16(d2, a2 + 2 * k, b2 + 2 * k, idesc, (kb | k) != 0);
+          const uint64_t fi = umma_desc_k_sw128(base), fj = umma_desc_k_sw128(base + K3T_OP_BYTES);
+          // 16-column block t of the atom sits at +32 t bytes = +2 t in the descriptor's address field
+          const uint64_t i_ah = fi, i_al = fi + 2, i_bh = fi + 4, i_bl = fi + 6;
+          const uint64_t j_ah = fj, j_al = fj + 2, j_bh = fj + 4, j_bl = fj + 6;
+          const uint32_t accum = q != 0;
+          tc_mma_bf16(d1, i_ah, j_bh, idesc, accum);
+          tc_mma_bf16(d1, i_ah, j_bl, idesc, 1u);
+          tc_mma_bf16(d1, i_al, j_bh, idesc, 1u);
+          tc_mma_bf16(d2, i_bh, j_ah, idesc, accum);
+          tc_mma_bf16(d2, i_bl, j_ah, idesc, 1u);
+          tc_mma_bf16(d2, i_bh, j_al, idesc, 1u);
           tc_commit(&oempty[os]);
         }
         tc_commit(&tfull[acc]);
@@ -263,13 +326,14 @@ k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant
     const bool storer = ((e & 3) == 0) && (lane == 0);
     int pending = -1;
     int tt = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tt) {
+    for (int t = t_lo; t < t_hi; ++t, ++tt) {
       const int bi = t / tiles_j, bj = t - bi * tiles_j;
       const int li0 = bi * K3T_TILE, gi0 = row0 + li0, j0 = bj * K3T_TILE;
       const int acc = tt & 1;
       const int gi = gi0 + row;
       const float ci = (gi < n) ? cvec[gi] : 0.f;
-      mbar_wait(&tfull[acc], (tt >> 1) & 1);
+      const bool interior = (gi0 + K3T_TILE <= j0 || j0 + K3T_TILE <= gi0) && (j0 + K3T_TILE <= n);   // no diagonal element, every column in range
+      mbar_wait(&tfull[acc], (uint32_t)((tt >> 1) & 1));
       tc_fence_after();
       for (int sl = 0; sl < 2; ++sl) {
         const int s = 2 * hf + sl;
@@ -284,48 +348,15 @@ k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant
           tc_ld16(taddr, lo1); tc_ld16(taddr + 16, hi1);
           tc_ld16(taddr + 128, lo2); tc_ld16(taddr + 128 + 16, hi2);
         }
-        mbar_wait(&thfull[slot], (q / K3T_RING) & 1);
-        tc_wait_ld();
-        uint8_t* slab = slabs + slot * K3T_SLAB_BYTES + row * 128;
         const int jb = j0 + s * K3T_SLAB_COLS;
-        const bool interior = (gi0 + K3T_TILE <= j0 || j0 + K3T_TILE <= gi0) && (j0 + K3T_TILE <= n);   // no diagonal element, every column in range
+        float4 cpre[8];
         if (interior) {
 #pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {
-            float4* cell = reinterpret_cast<float4*>(slab + ((c4 ^ (row & 7)) << 4));
-            const float4 th = *cell;
-            const float4 cv = *reinterpret_cast<const float4*>(cvec + jb + 4 * c4);
-            const float tv[4] = {th.x, th.y, th.z, th.w}, cj[4] = {cv.x, cv.y, cv.z, cv.w};
-            float nv[4];
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              float g = (__uint_as_float(d1[4 * c4 + b]) + __uint_as_float(d2[4 * c4 + b])) + (ci + cj[b]);
-              if (tv[b] < 0.f || tv[b] > 1.f) g = 0.f;                 // clamp backward
-              nv[b] = fminf(fmaxf(fmaf(-lr, g, tv[b]), 0.f), 1.f);
-            }
-            *cell = make_float4(nv[0], nv[1], nv[2], nv[3]);
-          }
-        } else {
-#pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {
-            float4* cell = reinterpret_cast<float4*>(slab + ((c4 ^ (row & 7)) << 4));
-            float4 th = *cell;
-            const int gj = jb + 4 * c4;
-            float cj[4];
-            if (gj + 3 < n) { const float4 cv = *reinterpret_cast<const float4*>(cvec + gj); cj[0] = cv.x; cj[1] = cv.y; cj[2] = cv.z; cj[3] = cv.w; }
-            else { for (int b = 0; b < 4; ++b) cj[b] = (gj + b < n) ? cvec[gj + b] : 0.f; }
-            float tv[4] = {th.x, th.y, th.z, th.w};
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              float g = (__uint_as_float(d1[4 * c4 + b]) + __uint_as_float(d2[4 * c4 + b])) + (ci + cj[b]);
-              if (gi == gj + b) g = 0.f;
-              if (tv[b] < 0.f || tv[b] > 1.f) g = 0.f;
-              const float nv = fminf(fmaxf(fmaf(-lr, g, tv[b]), 0.f), 1.f);
-              if (gj + b < n) tv[b] = nv;               // the TMA store clips at 16-byte granularity: leave padding as loaded
-            }
-            *cell = make_float4(tv[0], tv[1], tv[2], tv[3]);
-          }
+          for (int c4 = 0; c4 < 8; ++c4) cpre[c4] = __ldg(reinterpret_cast<const float4*>(cvec + jb) + c4);
         }
+        mbar_wait(&thfull[slot], (uint32_t)((q / K3T_RING) & 1));
+        tc_wait_ld();
+        k3_update_slab_row(slabs + slot * K3T_SLAB_BYTES + row * 128, row, d1, d2, cvec, cpre, interior, ci, gi, jb, n, lr);
         fence_proxy_async_smem();                      // generic-proxy writes -> visible to the TMA store
         named_bar_sync(1 + hf, 128);                   // the four warps that own this slab
         if (storer) {
@@ -338,43 +369,41 @@ k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
-      if (storer && pending >= 0) {                    // nothing of this tile stays pending: a slot's release never
-        tma_store_wait_read();                         // depends on work of a later tile
-        mbar_arrive(&thempty[pending]);
-        pending = -1;
-      }
     }
-    if (storer) tma_store_wait_all();
+    if (storer) {
+      if (pending >= 0) { tma_store_wait_read(); mbar_arrive(&thempty[pending]); }
+      tma_store_wait_all();
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-// fa, fb fp32 [n][ldf] -> Pm, Qm bf16 [n][kp]
-__global__ void k3_pack_kernel(const float* __restrict__ fa, const float* __restrict__ fb, int64_t ldf, int n, int d, int kp,
-                               __nv_bfloat16* __restrict__ pm, __nv_bfloat16* __restrict__ qm) {
+// fa, fb fp32 [n][ldf] -> F bf16 [n][kf], F[i][64 q + 16 t + k] = block_t(i)[16 q + k] (t: a_hi, a_lo, b_hi, b_lo)
+__global__ void k3_pack_kernel(const float* __restrict__ fa, const float* __restrict__ fb, int64_t ldf, int n, int d, int kf,
+                               __nv_bfloat16* __restrict__ f) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)n * kp) return;
-  const int i = (int)(idx / kp), k = (int)(idx - (int64_t)i * kp);
-  k3_pack_element(fa + (int64_t)i * ldf, fb + (int64_t)i * ldf, d, k, pm[idx], qm[idx]);
+  if (idx >= (int64_t)n * kf) return;
+  const int i = (int)(idx / kf), k = (int)(idx - (int64_t)i * kf);
+  f[idx] = k3_pack_element(fa + (int64_t)i * ldf, fb + (int64_t)i * ldf, d, k);
 }
 
-int32_t k3_launch_pack(const float* fa, const float* fb, int64_t ldf, int n, int d, int kp, void* pm, void* qm, cudaStream_t stream) {
-  const int64_t total = (int64_t)n * kp;
-  k3_pack_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(fa, fb, ldf, n, d, kp, reinterpret_cast<__nv_bfloat16*>(pm),
-                                                                    reinterpret_cast<__nv_bfloat16*>(qm));
+int32_t k3_launch_pack(const float* fa, const float* fb, int64_t ldf, int n, int d, void* f, cudaStream_t stream) {
+  const int kf = k3_packed_k(d);
+  const int64_t total = (int64_t)n * kf;
+  k3_pack_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(fa, fb, ldf, n, d, kf, reinterpret_cast<__nv_bfloat16*>(f));
   LDS_CHECK_LAUNCH("k3_pack_kernel");
   return LDS_OK;
 }
 
-int32_t k3_launch_tc(float* theta, int64_t ldt, int n, int row0, int rows, const void* pm, const void* qm, int kp, int d,
+int32_t k3_launch_tc(float* theta, int64_t ldt, int n, int row0, int rows, const void* f, int d,
                      const float* cvec, float lr, cudaStream_t stream) {
-  CUtensorMap tth, tpm, tqm;
+  CUtensorMap tth, tf;
   int32_t rc;
+  const int kf = k3_packed_k(d);
   if ((rc = make_tmap_2d(&tth, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, theta, n, rows, ldt, K3T_SLAB_COLS, K3T_TILE)) != LDS_OK) return rc;
-  if ((rc = make_tmap_2d(&tpm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pm, kp, n, kp, K3T_KB, K3T_TILE)) != LDS_OK) return rc;
-  if ((rc = make_tmap_2d(&tqm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qm, kp, n, kp, K3T_KB, K3T_TILE)) != LDS_OK) return rc;
+  if ((rc = make_tmap_2d(&tf, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, f, kf, n, kf, K3T_KB, K3T_TILE)) != LDS_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     LDS_CHECK_CUDA(cudaFuncSetAttribute(k3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K3T_SMEM));
@@ -382,7 +411,7 @@ int32_t k3_launch_tc(float* theta, int64_t ldt, int n, int row0, int rows, const
   }
   const int tiles = (int)(ceil_div(rows, K3T_TILE) * ceil_div(n, K3T_TILE));
   const int grid = tiles < kNumSMsB200 ? tiles : kNumSMsB200;
-  k3_tc_kernel<<<grid, K3T_THREADS, K3T_SMEM, stream>>>(tth, tpm, tqm, cvec, n, row0, rows, kp / K3T_KB, (int)ceil_div(3 * d, 16), lr);
+  k3_tc_kernel<<<grid, K3T_THREADS, K3T_SMEM, stream>>>(tth, tf, cvec, n, row0, rows, kf / K3T_KB, lr);
   LDS_CHECK_LAUNCH("k3_tc_kernel");
   return LDS_OK;
 }
@@ -425,7 +454,7 @@ extern "C" int32_t lds_k3k4_theta_update(float* theta_full, int64_t ld_theta, in
 
 extern "C" int64_t lds_k3_workspace_bytes(int32_t n, int32_t d) {
   if (n <= 0 || d <= 0) return -1;
-  return 2 * round_up((int64_t)n * k3_padded_k(d) * 2, 1024);
+  return round_up((int64_t)n * k3_packed_k(d) * 2, 1024);
 }
 
 extern "C" int32_t lds_k3k4_theta_update_tc(float* theta_full, int64_t ld_theta, int32_t n, int32_t row0, int32_t rows,
@@ -441,10 +470,7 @@ extern "C" int32_t lds_k3k4_theta_update_tc(float* theta_full, int64_t ld_theta,
   const int64_t need = lds_k3_workspace_bytes(n, d);
   if (!workspace || workspace_bytes < need) { set_error("lds_k3k4_theta_update_tc: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need); return LDS_ERR_WORKSPACE; }
   LDS_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "lds_k3k4_theta_update_tc: workspace must be 1024-byte aligned");
-  const int kp = k3_padded_k(d);
-  auto* pm = reinterpret_cast<__nv_bfloat16*>(workspace);
-  auto* qm = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) + need / 2);
-  int32_t rc = k3_launch_pack(fa, fb, ld_f, n, d, kp, pm, qm, stream);
+  int32_t rc = k3_launch_pack(fa, fb, ld_f, n, d, workspace, stream);
   if (rc != LDS_OK) return rc;
-  return k3_launch_tc(theta_full, ld_theta, n, row0, rows, pm, qm, kp, d, cvec, lr, stream);
+  return k3_launch_tc(theta_full, ld_theta, n, row0, rows, workspace, d, cvec, lr, stream);
 }

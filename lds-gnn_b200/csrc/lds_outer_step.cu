@@ -25,9 +25,9 @@ constexpr int EPI_THREADS = 1024;   // 32 warps, one row each: the epilogues are
 constexpr int FEAT_THREADS = 256;   // dense feature GEMM: 8 warps x 4 rows
 constexpr int EPI_MAXW = 128;       // widest operand
 
-enum { B_A = 0, B_DEG, B_RS, B_P1, B_Z1, B_P2, B_Z2, B_DZ2, B_DP2, B_DZ1, B_DP1, B_FA, B_FB, B_C, B_BTHI, B_BTLO, B_PARTIAL, B_LOSSP, B_CORRP, B_PM, B_QM, B_W0S, B_CNT, B_OPND, B_END };
+enum { B_A = 0, B_DEG, B_RS, B_P1, B_Z1, B_P2, B_Z2, B_DZ2, B_DP2, B_DZ1, B_DP1, B_FA, B_FB, B_C, B_BTHI, B_BTLO, B_PARTIAL, B_LOSSP, B_CORRP, B_F, B_W0S, B_CNT, B_OPND, B_END };
 struct OuterLayout {
-  int n, rows, f, h, c, hp1, hp2, hpmax, nblk, kp, panels;
+  int n, rows, f, h, c, hp1, hp2, hpmax, nblk, panels;
   int64_t lda, ldb, ldf;
   K2Sched s1, s2;
   int64_t off[B_END];
@@ -55,8 +55,7 @@ static bool make_layout(int n, int rows, int f, int h, int c, OuterLayout& L, bo
   const int64_t p1 = k2_partial_bytes(k2_make_schedule(n, rows, L.hp1, true)), p2 = k2_partial_bytes(k2_make_schedule(n, rows, L.hp2, true));
   bytes[B_PARTIAL] = p1 > p2 ? p1 : p2;
   bytes[B_LOSSP] = bytes[B_CORRP] = (int64_t)ceil_div(rows, K2_BLOCK_M) * 4;
-  L.kp = k3_padded_k(h + c);
-  bytes[B_PM] = bytes[B_QM] = (int64_t)n * L.kp * 2;
+  bytes[B_F] = (int64_t)n * k3_packed_k(h + c) * 2;        // packed bf16 factor rows of the tensor-core update
   bytes[B_CNT] = (int64_t)ceil_div(rows, K2_BLOCK_M) * 4;     // per-panel arrival counters of the stream-K reduction
   bytes[B_W0S] = (int64_t)h * round_up(f, 4) * 4;          // staged layer_in weight: transposed [f][h] (CSR path) or padded [h][ldx]
   int64_t o = 0;
@@ -380,7 +379,6 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   E.deg = fbuf(B_DEG); E.rs = fbuf(B_RS);
   E.p1 = fbuf(B_P1); E.z1 = fbuf(B_Z1); E.p2 = fbuf(B_P2); E.z2 = fbuf(B_Z2); E.dz2 = fbuf(B_DZ2); E.dp2 = fbuf(B_DP2);
   E.dz1 = fbuf(B_DZ1); E.dp1 = fbuf(B_DP1); E.fa = fbuf(B_FA); E.fb = fbuf(B_FB); E.ldf = L.ldf; E.cvec = fbuf(B_C);
-  E.pm = reinterpret_cast<__nv_bfloat16*>(buf(B_PM)); E.qm = reinterpret_cast<__nv_bfloat16*>(buf(B_QM)); E.kp = L.kp;
   E.w1 = A.w1; E.b1 = A.b1; E.y = A.y; E.mask = A.mask; E.inv_m = 1.0f / (float)A.mask_count;
   E.drop_h = dh; E.bt_hi = bt_hi; E.bt_lo = bt_lo; E.ldb = L.ldb;
   E.loss_part = fbuf(B_LOSSP); E.corr_part = fbuf(B_CORRP); E.nblk = L.panels;
@@ -411,9 +409,9 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
     const float* cv = sharded ? A.c_full : fbuf(B_C);
     if (A.opt_kind == LDS_OPT_SGD && !(A.k3_flags & LDS_K3_SIMT)) {
       LDS_CHECK_ARG((reinterpret_cast<uintptr_t>(cv) & 15) == 0, "lds_outer_step: c_full must be 16-byte aligned");
-      rc = k3_launch_pack(fa, fb, L.ldf, A.n, A.h + A.c, L.kp, buf(B_PM), buf(B_QM), stream);
+      rc = k3_launch_pack(fa, fb, L.ldf, A.n, A.h + A.c, buf(B_F), stream);
       profile_mark(stream, 9);
-      if (rc == LDS_OK) rc = k3_launch_tc(A.theta_full, A.ld_theta, A.n, row0, rows, buf(B_PM), buf(B_QM), L.kp, A.h + A.c, cv, A.lr, stream);
+      if (rc == LDS_OK) rc = k3_launch_tc(A.theta_full, A.ld_theta, A.n, row0, rows, buf(B_F), A.h + A.c, cv, A.lr, stream);
     } else {
       rc = lds_k3k4_theta_update(A.theta_full, A.ld_theta, A.n, row0, rows, fa, fb, L.ldf, A.h + A.c, cv,
                                  A.lr, A.opt_kind, A.adam_m, A.adam_v, A.beta1, A.beta2, A.eps, A.adam_t, nullptr, 0, 0u, stream_);

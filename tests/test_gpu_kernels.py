@@ -218,7 +218,11 @@ def test_k3k4_sgd_update_matches_closed_form_and_stays_symmetric(K, n, d):
 
 
 @pytest.mark.parametrize("n,d,rows0", [(64, 23, None), (130, 23, None), (257, 71, None), (1000, 22, None), (2708, 23, None),
-                                       (700, 5, None), (1000, 22, (256, 384))])
+                                       (700, 5, None), (1000, 22, (256, 384)),
+                                       # compact-operand kernel: 1..5 boxes of packed factors, ring wrap-around over many tiles
+                                       # per CTA, row-block changes inside a CTA's tile range; d > 80 = the k-block kernel
+                                       (300, 12, None), (520, 40, None), (520, 60, None), (900, 80, None), (4100, 71, None),
+                                       (520, 100, None), (4100, 71, (1024, 1000)), (900, 80, (128, 300))])
 def test_k3k4_tensor_core_update_matches_closed_form_and_is_exactly_symmetric(K, n, d, rows0):
     rng = np.random.default_rng(n * 13 + d)
     th = random_theta(rng, n, "outside" if n == 130 else "mixed")
@@ -243,7 +247,7 @@ def test_k3k4_tensor_core_update_matches_closed_form_and_is_exactly_symmetric(K,
         # agrees with the CUDA-core kernel
         simt = before.clone()
         K.k3k4_theta_update_(simt, n, dev(fa), dev(fb), dev(cv), lr)
-        assert (simt[:, :n] - full[:, :n]).abs().max().item() < 2e-6
+        assert (simt[:, :n] - full[:, :n]).abs().max().item() < 2e-6 + 1e-5 * lr * np.abs(g).max()   # both within the oracle bound
     else:                                                                  # a row-block shard (multi-GPU layout)
         r0, r = rows0
         shard = full[r0:r0 + r]
