@@ -172,18 +172,16 @@ constexpr int K3T_SMEM = K3T_OSTAGES * K3T_STAGE_BYTES + K3T_RING * K3T_SLAB_BYT
 // One thread's row of one theta slab (32 columns, 128-byte swizzled in smem): g = (D1 + D2) + (c_i + c_j) with the
 // diagonal and clamp-backward masks, SGD step + projection written back in place (src/models/factory.py:66-69,
 // src/trainers/outer.py:78-83, src/models/graph.py:16-20).
-// `cpre` holds c_j of the slab's 32 columns for interior tiles: loaded BEFORE the wait on the theta slab, because the
-// 224 KB shared-memory carve-out leaves almost no L1 and a cvec load issued per cell cost an L2 round trip each
-// (45 % of the kernel's stall samples at N = 20 000).
+// `cj` = c_j of the slab's 32 columns (zero past n), staged through shared memory once per tile: the 224 KB carve-out
+// leaves almost no L1, and a cvec load issued per cell cost an L2 round trip each (45 % of the stall samples at N = 20 000).
 __device__ __forceinline__ void k3_update_slab_row(uint8_t* slab, int row, const uint32_t (&d1)[32], const uint32_t (&d2)[32],
-                                                   const float* __restrict__ cvec, const float4 (&cpre)[8], bool interior,
-                                                   float ci, int gi, int jb, int n, float lr) {
+                                                   const float* cj_s, bool interior, float ci, int gi, int jb, int n, float lr) {
   if (interior) {
 #pragma unroll
     for (int c4 = 0; c4 < 8; ++c4) {
       float4* cell = reinterpret_cast<float4*>(slab + ((c4 ^ (row & 7)) << 4));
       const float4 th = *cell;
-      const float4 cv = cpre[c4];
+      const float4 cv = *reinterpret_cast<const float4*>(cj_s + 4 * c4);
       const float tv[4] = {th.x, th.y, th.z, th.w}, cj[4] = {cv.x, cv.y, cv.z, cv.w};
       float nv[4];
 #pragma unroll
@@ -200,9 +198,8 @@ __device__ __forceinline__ void k3_update_slab_row(uint8_t* slab, int row, const
       float4* cell = reinterpret_cast<float4*>(slab + ((c4 ^ (row & 7)) << 4));
       float4 th = *cell;
       const int gj = jb + 4 * c4;
-      float cj[4];
-      if (gj + 3 < n) { const float4 cv = *reinterpret_cast<const float4*>(cvec + gj); cj[0] = cv.x; cj[1] = cv.y; cj[2] = cv.z; cj[3] = cv.w; }
-      else { for (int b = 0; b < 4; ++b) cj[b] = (gj + b < n) ? cvec[gj + b] : 0.f; }
+      const float4 cv = *reinterpret_cast<const float4*>(cj_s + 4 * c4);
+      const float cj[4] = {cv.x, cv.y, cv.z, cv.w};
       float tv[4] = {th.x, th.y, th.z, th.w};
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
@@ -220,6 +217,7 @@ __device__ __forceinline__ void k3_update_slab_row(uint8_t* slab, int row, const
 __global__ void __launch_bounds__(K3T_THREADS, 1)
 k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant__ CUtensorMap tm_f,
              const float* __restrict__ cvec, int n, int row0, int rows, int ksteps, float lr) {
+  __shared__ __align__(16) float cj_stage[2][64];            // c_j of the tile's columns, one half per epilogue warp group
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* ops = smem;                                        // operand stages
@@ -332,9 +330,14 @@ k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant
       const int acc = tt & 1;
       const int gi = gi0 + row;
       const float ci = (gi < n) ? cvec[gi] : 0.f;
+      const int gt = (e & 3) * 32 + lane;            // 0..127 inside this warp group
+      const int cjcol = j0 + 64 * hf + gt;
+      const float cj_mine = (gt < 64 && cjcol < n) ? cvec[cjcol] : 0.f;                // in flight across the accumulator wait
       const bool interior = (gi0 + K3T_TILE <= j0 || j0 + K3T_TILE <= gi0) && (j0 + K3T_TILE <= n);   // no diagonal element, every column in range
       mbar_wait(&tfull[acc], (uint32_t)((tt >> 1) & 1));
       tc_fence_after();
+      if (gt < 64) cj_stage[hf][gt] = cj_mine;       // the group's reads of the previous tile ended before its last named barrier
+      named_bar_sync(1 + hf, 128);
       for (int sl = 0; sl < 2; ++sl) {
         const int s = 2 * hf + sl;
         const int q = tt * 4 + s, slot = q % K3T_RING;
@@ -349,14 +352,9 @@ k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant
           tc_ld16(taddr + 128, lo2); tc_ld16(taddr + 128 + 16, hi2);
         }
         const int jb = j0 + s * K3T_SLAB_COLS;
-        float4 cpre[8];
-        if (interior) {
-#pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) cpre[c4] = __ldg(reinterpret_cast<const float4*>(cvec + jb) + c4);
-        }
         mbar_wait(&thfull[slot], (uint32_t)((q / K3T_RING) & 1));
         tc_wait_ld();
-        k3_update_slab_row(slabs + slot * K3T_SLAB_BYTES + row * 128, row, d1, d2, cvec, cpre, interior, ci, gi, jb, n, lr);
+        k3_update_slab_row(slabs + slot * K3T_SLAB_BYTES + row * 128, row, d1, d2, &cj_stage[hf][32 * sl], interior, ci, gi, jb, n, lr);
         fence_proxy_async_smem();                      // generic-proxy writes -> visible to the TMA store
         named_bar_sync(1 + hf, 128);                   // the four warps that own this slab
         if (storer) {
