@@ -169,14 +169,17 @@ typedef struct lds_outer_step_args {
    *   PHASE_LAYER1   needs opnd_full [n][h]       -> local operand rows  (buffer 14, [rows][c]  = r * P2)
    *   PHASE_LAYER2   needs opnd_full [n][c]       -> local operand rows  ([rows][c] = r * dZ2), out_scalars = LOCAL sums / mask_count
    *   PHASE_BWD2     needs opnd_full [n][c]       -> local operand rows  ([rows][h] = r * dZ1)
-   *   PHASE_BWD1     needs opnd_full [n][h]       -> local factor rows   (buffers 11, 12, 13)
-   *   PHASE_UPDATE   needs fa_full, fb_full [n][ld_f], c_full [n]        -> theta rows updated in place
+   *   PHASE_BWD1     needs opnd_full [n][h]       -> local factor rows: packed bf16 rows [row0, row0+rows) of buffer 15 and c
+   *                                                  (13) for the tensor-core SGD update, else fp32 rows (buffers 11, 12, 13)
+   *   PHASE_UPDATE   needs c_full [n] and f_full [n][lds_outer_step_packed_k(h, c)] bf16 (tensor-core SGD update) or
+   *                  fa_full, fb_full [n][ld_f] fp32 (Adam / LDS_K3_SIMT)    -> theta rows updated in place
    * mask_count is the GLOBAL number of masked rows; seed/step must agree on all ranks. No theta / A_tilde traffic. */
   int32_t  row0, rows;
   uint32_t phases;            /* bitmask of LDS_PHASE_*                                                  */
   uint32_t reserved2;
   const float* opnd_full;
   const float* fa_full; const float* fb_full; const float* c_full;
+  const void*  f_full;        /* gathered packed factor rows (bf16), see PHASE_UPDATE                    */
   unsigned long long* k2_timeline;   /* optional debug buffer [4][512][8] of %globaltimer stamps, else NULL            */
 } lds_outer_step_args;
 
@@ -192,11 +195,16 @@ int64_t lds_outer_step_workspace_bytes(int32_t n, int32_t f, int32_t h, int32_t 
 int64_t lds_outer_step_shard_workspace_bytes(int32_t n, int32_t rows, int32_t f, int32_t h, int32_t c);
 int32_t lds_outer_step(const lds_outer_step_args* args, void* stream);
 /* Device pointers into a workspace laid out by lds_outer_step (for tests / the composable path / the sharded exchange):
- * which: 0 A_tilde(bf16) 1 deg 2 rsqrt 3 P1 4 Z1 5 P2 6 Z2 7 dZ2 8 dP2 9 dZ1 10 dP1 11 fa 12 fb 13 cvec 14 operand rows.
+ * which: 0 A_tilde(bf16) 1 deg 2 rsqrt 3 P1 4 Z1 5 P2 6 Z2 7 dZ2 8 dP2 9 dZ1 10 dP1 11 fa 12 fb 13 cvec 14 operand rows
+ * 15 packed factor rows (bf16 [n][lds_outer_step_packed_k], this rank's rows at row0).
+ * The row-local state 3..10 is stored TRANSPOSED, [width][lds_outer_step_state_ld(rows)] fp32 (coalesced for the
+ * thread-per-row epilogues); 11/12 are written only when the CUDA-core update runs (Adam or LDS_K3_SIMT).
  * `rows` = n for the unsharded layout. */
 void*   lds_outer_step_buffer(void* workspace, int32_t n, int32_t f, int32_t h, int32_t c, int32_t which);
 void*   lds_outer_step_shard_buffer(void* workspace, int32_t n, int32_t rows, int32_t f, int32_t h, int32_t c, int32_t which);
 int64_t lds_outer_step_factor_ld(int32_t h, int32_t c);
+int64_t lds_outer_step_packed_k(int32_t h, int32_t c);   /* columns of a packed bf16 factor row            */
+int64_t lds_outer_step_state_ld(int32_t rows);           /* row stride of the transposed row-local state    */
 
 /* ---- measurement hook for bench.py (not part of the reference-facing surface). Between begin and end,
  * lds_outer_step records a CUDA event on its stream after every kernel launch. lds_profile_end synchronises on

@@ -46,6 +46,8 @@ SIGNATURES = {
     "lds_outer_step_shard_buffer": (c_void_p, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32]),
     "lds_outer_step_buffer": (c_void_p, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32]),
     "lds_outer_step_factor_ld": (c_int64, [c_int32, c_int32]),
+    "lds_outer_step_packed_k": (c_int64, [c_int32, c_int32]),
+    "lds_outer_step_state_ld": (c_int64, [c_int32]),
     "lds_profile_begin": (c_int32, []),
     "lds_profile_end": (c_int32, [c_void_p, c_void_p, c_int32]),
 }
@@ -75,7 +77,7 @@ class OuterStepArgs(Structure):
         ("k2_flags", c_uint32), ("k3_flags", c_uint32),
         ("row0", c_int32), ("rows", c_int32), ("phases", c_uint32), ("reserved2", c_uint32),
         ("opnd_full", c_void_p), ("fa_full", c_void_p), ("fb_full", c_void_p), ("c_full", c_void_p),
-        ("k2_timeline", c_void_p),
+        ("f_full", c_void_p), ("k2_timeline", c_void_p),
     ]
 
 

@@ -5,6 +5,11 @@
 // width in registers and finishes the layer for that row — scaling by r_i, relu, dropout, the tiny second
 // linear, log-softmax + NLL, the backward chain — and emits the NEXT propagation's operand (r * .)^T as bf16
 // hi/lo terms (bt[c][i]: consecutive lanes = consecutive i, coalesced). Reference semantics per function below.
+//
+// Layout of the row-local state (P1, Z1, dZ1, dP1 [h][ldr]; P2, Z2, dZ2, dP2 [c][ldr]): TRANSPOSED, column-major in
+// the row index, so that a warp (lane = row) touches one 128-byte line per access. With row-major [n][h] arrays every
+// load/store instruction of the thread-per-row epilogue hit 32 different lines; the LSU serialises those, which made
+// the epilogue of one 128-row panel cost 4-8 us at h = 16 and > 20 us at h = 64 (the tail of every K2 launch).
 #pragma once
 #include "lds_k2.cuh"
 #include "lds_k3.cuh"
@@ -48,8 +53,11 @@ struct EpiArgs {
   int row0;                    // global index of local row 0 (row-block shard), keys the dropout draws
   float* opnd; int64_t ld_opnd; // sharded: write the next operand's rows as fp32 [n][ld_opnd] (all-gathered by the caller)
   const float* deg; const float* rs;
-  float* p1; float* z1; float* p2; float* z2; float* dz2; float* dp2; float* dz1; float* dp1;
-  float* fa; float* fb; int64_t ldf; float* cvec;
+  float* p1; float* z1; float* p2; float* z2; float* dz2; float* dp2; float* dz1; float* dp1;   // transposed: [w][ldr]
+  int64_t ldr;                 // row stride of the transposed state arrays (>= n)
+  float* fa; float* fb; int64_t ldf;   // optional row-major fp32 factor rows [n][ldf] (CUDA-core / Adam update), else NULL
+  __nv_bfloat16* fpack; int kf;        // optional packed bf16 factor rows [n][kf] of the tensor-core update (lds_k3.cuh), else NULL
+  float* cvec;
   const float* w1; const float* b1;
   const int64_t* y; const uint8_t* mask; float inv_m;
   DropCfg drop_h;
@@ -93,7 +101,7 @@ __device__ __forceinline__ void epi_layer1(const EpiArgs& a, int i, float (&v)[H
         const int c = 4 * q + e;
         if (c < a.h) {
           const float z = ri * v[c];
-          a.z1[(int64_t)i * a.h + c] = z;
+          a.z1[(int64_t)c * a.ldr + i] = z;
           v[c] = fmaxf(z, 0.f) * k[e];
         } else v[c] = 0.f;
       }
@@ -104,7 +112,7 @@ __device__ __forceinline__ void epi_layer1(const EpiArgs& a, int i, float (&v)[H
     const float* wrow = a.w1 + (int64_t)o * a.h;
 #pragma unroll
     for (int c = 0; c < HP; ++c) if (c < a.h) acc = fmaf(v[c], wrow[c], acc);
-    a.p2[(int64_t)i * a.c + o] = acc;
+    a.p2[(int64_t)o * a.ldr + i] = acc;
     store_operand(a, o, i, ri * acc);
   }
   // operand rows >= C are left as they are: column c of the product depends on operand row c only, and no epilogue
@@ -122,7 +130,7 @@ __device__ __forceinline__ void epi_layer2(const EpiArgs& a, int i, float (&v)[H
 #pragma unroll
   for (int o = 0; o < HP; ++o) if (o < a.c) {
     v[o] = ri * v[o];
-    a.z2[(int64_t)i * a.c + o] = v[o];
+    a.z2[(int64_t)o * a.ldr + i] = v[o];
     if (v[o] > mx) { mx = v[o]; best = o; }                    // ascending o: first maximum wins (torch.argmax)
   }
   float se = 0.f;
@@ -137,7 +145,7 @@ __device__ __forceinline__ void epi_layer2(const EpiArgs& a, int i, float (&v)[H
     if (a.out_logp) a.out_logp[(int64_t)i * a.c + o] = lp;
     if (mk && o == yi) loss_i = -lp;
     const float dz = mk ? (expf(lp) - (o == yi ? 1.f : 0.f)) * a.inv_m : 0.f;
-    a.dz2[(int64_t)i * a.c + o] = dz;
+    a.dz2[(int64_t)o * a.ldr + i] = dz;
     store_operand(a, o, i, ri * dz);
   }
   corr_i = (mk && best == yi) ? 1.f : 0.f;
@@ -150,7 +158,7 @@ __device__ __forceinline__ void epi_bwd2(const EpiArgs& a, int i, float (&v)[HP]
   const float ri = a.rs[i];
 #pragma unroll
   for (int o = 0; o < HP; ++o) {
-    if (o < a.c) { v[o] = ri * v[o]; a.dp2[(int64_t)i * a.c + o] = v[o]; } else v[o] = 0.f;
+    if (o < a.c) { v[o] = ri * v[o]; a.dp2[(int64_t)o * a.ldr + i] = v[o]; } else v[o] = 0.f;
   }
   for (int q = 0; 4 * q < a.h; ++q) {
     float k[4];
@@ -162,55 +170,89 @@ __device__ __forceinline__ void epi_bwd2(const EpiArgs& a, int i, float (&v)[HP]
       float acc = 0.f;
 #pragma unroll
       for (int o = 0; o < HP; ++o) if (o < a.c) acc = fmaf(v[o], a.w1[(int64_t)o * a.h + c], acc);
-      const float dz = (a.z1[(int64_t)i * a.h + c] > 0.f) ? acc * k[e] : 0.f;
-      a.dz1[(int64_t)i * a.h + c] = dz;
+      const float dz = (a.z1[(int64_t)c * a.ldr + i] > 0.f) ? acc * k[e] : 0.f;
+      a.dz1[(int64_t)c * a.ldr + i] = dz;
       store_operand(a, c, i, ri * dz);
     }
   }
 }
 
 // ---- backward 1: dP1 = r * sum, rho, kappa, c = -(rho+kappa)/(2 deg), factor rows fa = r(dZ1|dZ2), fb = r(P1|P2)
+// The factor rows leave as the packed bf16 operand row of the tensor-core update (16 columns per step: a_hi, a_lo,
+// b_hi, b_lo; the h-part padded to a multiple of 16 so that a step never straddles dZ1|dZ2 — zero columns add
+// nothing to fa.fb) and / or as row-major fp32 rows for the CUDA-core update.
+__device__ __forceinline__ void pack_step16(const float (&av)[16], const float (&bv)[16], __nv_bfloat16* dst) {
+  // dst: 64 bf16 = [a_hi(16) | a_lo(16) | b_hi(16) | b_lo(16)], 16-byte aligned
+  uint32_t w[32];
+#pragma unroll
+  for (int k = 0; k < 16; k += 2) {
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(av[k], h0, l0); split_bf16(av[k + 1], h1, l1);
+    w[k >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    w[8 + (k >> 1)] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    split_bf16(bv[k], h0, l0); split_bf16(bv[k + 1], h1, l1);
+    w[16 + (k >> 1)] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    w[24 + (k >> 1)] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  uint4* out = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) out[u] = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
+}
+
 template <int HP>
 __device__ __forceinline__ void epi_bwd1(const EpiArgs& a, int i, float (&v)[HP]) {
   if (i >= a.n) return;
   const float ri = a.rs[i];
   const float di = a.deg[i];
-  const int d = a.h + a.c;
-  float* fa = a.fa + (int64_t)i * a.ldf;
-  float* fb = a.fb + (int64_t)i * a.ldf;
-  float dz1[HP], p1[HP], z1[HP];
-#pragma unroll
-  for (int c = 0; c < HP; ++c) {                               // every load of the row in flight before the first use
-    const bool in = c < a.h;
-    dz1[c] = in ? a.dz1[(int64_t)i * a.h + c] : 0.f;
-    p1[c] = in ? a.p1[(int64_t)i * a.h + c] : 0.f;
-    z1[c] = in ? a.z1[(int64_t)i * a.h + c] : 0.f;
-  }
+  const int h16 = (a.h + 15) & ~15;
+  float* fa = a.fa ? a.fa + (int64_t)i * a.ldf : nullptr;
+  float* fb = a.fb ? a.fb + (int64_t)i * a.ldf : nullptr;
+  __nv_bfloat16* fp = a.fpack ? a.fpack + (int64_t)i * a.kf : nullptr;
   float rho = 0.f, kappa = 0.f;
-  for (int o0 = 0; o0 < a.c; o0 += 8) {
-    float dz2[8], p2[8], z2[8], dp2[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const bool in = o0 + u < a.c;
-      const int64_t idx = (int64_t)i * a.c + o0 + u;
-      dz2[u] = in ? a.dz2[idx] : 0.f; p2[u] = in ? a.p2[idx] : 0.f; z2[u] = in ? a.z2[idx] : 0.f; dp2[u] = in ? a.dp2[idx] : 0.f;
-    }
+  for (int g = 0; g < HP / 16; ++g) {                          // hidden part, one packed step (16 columns) per trip
+    if (16 * g < a.h) {
+      float dz1[16], p1[16], z1[16];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) if (o0 + u < a.c) {
-      rho = fmaf(dz2[u], z2[u], rho);
-      kappa = fmaf(p2[u], dp2[u], kappa);
-      fa[a.h + o0 + u] = ri * dz2[u]; fb[a.h + o0 + u] = ri * p2[u];
+      for (int k = 0; k < 16; ++k) {                           // coalesced: lane = row, one line per column
+        const int c = 16 * g + k;
+        const bool in = c < a.h;
+        dz1[k] = in ? a.dz1[(int64_t)c * a.ldr + i] : 0.f;
+        p1[k] = in ? a.p1[(int64_t)c * a.ldr + i] : 0.f;
+        z1[k] = in ? a.z1[(int64_t)c * a.ldr + i] : 0.f;
+      }
+      float av[16], bv[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int c = 16 * g + k;
+        const float dp1 = ri * v[c];
+        rho = fmaf(dz1[k], z1[k], rho);
+        kappa = fmaf(p1[k], dp1, kappa);
+        av[k] = ri * dz1[k]; bv[k] = ri * p1[k];
+        if (c < a.h) {
+          a.dp1[(int64_t)c * a.ldr + i] = dp1;
+          if (fa) { fa[c] = av[k]; fb[c] = bv[k]; }
+        }
+      }
+      if (fp) pack_step16(av, bv, fp + 64 * g);
     }
   }
+  for (int o0 = 0; o0 < a.c; o0 += 16) {                       // class part
+    float av[16], bv[16];
 #pragma unroll
-  for (int c = 0; c < HP; ++c) if (c < a.h) {
-    const float dp1 = ri * v[c];
-    rho = fmaf(dz1[c], z1[c], rho);
-    kappa = fmaf(p1[c], dp1, kappa);
-    a.dp1[(int64_t)i * a.h + c] = dp1;
-    fa[c] = ri * dz1[c]; fb[c] = ri * p1[c];
+    for (int k = 0; k < 16; ++k) {
+      const int o = o0 + k;
+      const bool in = o < a.c;
+      const int64_t idx = (int64_t)o * a.ldr + i;
+      const float dz2 = in ? a.dz2[idx] : 0.f, p2 = in ? a.p2[idx] : 0.f, z2 = in ? a.z2[idx] : 0.f, dp2 = in ? a.dp2[idx] : 0.f;
+      rho = fmaf(dz2, z2, rho);
+      kappa = fmaf(p2, dp2, kappa);
+      av[k] = ri * dz2; bv[k] = ri * p2;
+      if (in && fa) { fa[a.h + o] = av[k]; fb[a.h + o] = bv[k]; }
+    }
+    if (fp) pack_step16(av, bv, fp + 4 * h16 + 4 * o0);
   }
-  for (int k = d; k < (int)a.ldf; ++k) { fa[k] = 0.f; fb[k] = 0.f; }
+  if (fa) for (int k = a.h + a.c; k < (int)a.ldf; ++k) { fa[k] = 0.f; fb[k] = 0.f; }
   a.cvec[i] = -(rho + kappa) / (2.f * di);                     // both D^-1/2 factors depend on the row sum
 }
 

@@ -378,28 +378,27 @@ k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-// fa, fb fp32 [n][ldf] -> F bf16 [n][kf], F[i][64 q + 16 t + k] = block_t(i)[16 q + k] (t: a_hi, a_lo, b_hi, b_lo)
-__global__ void k3_pack_kernel(const float* __restrict__ fa, const float* __restrict__ fb, int64_t ldf, int n, int d, int kf,
+// fa, fb fp32 [n][ldf] -> packed rows F bf16 [n][kf] (layout: lds_k3.cuh)
+__global__ void k3_pack_kernel(const float* __restrict__ fa, const float* __restrict__ fb, int64_t ldf, int n, int h, int c, int kf,
                                __nv_bfloat16* __restrict__ f) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)n * kf) return;
   const int i = (int)(idx / kf), k = (int)(idx - (int64_t)i * kf);
-  f[idx] = k3_pack_element(fa + (int64_t)i * ldf, fb + (int64_t)i * ldf, d, k);
+  f[idx] = k3_pack_element(fa + (int64_t)i * ldf, fb + (int64_t)i * ldf, h, c, k);
 }
 
-int32_t k3_launch_pack(const float* fa, const float* fb, int64_t ldf, int n, int d, void* f, cudaStream_t stream) {
-  const int kf = k3_packed_k(d);
+int32_t k3_launch_pack(const float* fa, const float* fb, int64_t ldf, int n, int h, int c, void* f, cudaStream_t stream) {
+  const int kf = k3_packed_k(h, c);
   const int64_t total = (int64_t)n * kf;
-  k3_pack_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(fa, fb, ldf, n, d, kf, reinterpret_cast<__nv_bfloat16*>(f));
+  k3_pack_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(fa, fb, ldf, n, h, c, kf, reinterpret_cast<__nv_bfloat16*>(f));
   LDS_CHECK_LAUNCH("k3_pack_kernel");
   return LDS_OK;
 }
 
-int32_t k3_launch_tc(float* theta, int64_t ldt, int n, int row0, int rows, const void* f, int d,
+int32_t k3_launch_tc(float* theta, int64_t ldt, int n, int row0, int rows, const void* f, int kf,
                      const float* cvec, float lr, cudaStream_t stream) {
   CUtensorMap tth, tf;
   int32_t rc;
-  const int kf = k3_packed_k(d);
   if ((rc = make_tmap_2d(&tth, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, theta, n, rows, ldt, K3T_SLAB_COLS, K3T_TILE)) != LDS_OK) return rc;
   if ((rc = make_tmap_2d(&tf, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, f, kf, n, kf, K3T_KB, K3T_TILE)) != LDS_OK) return rc;
   static bool attr_set = false;
@@ -452,7 +451,7 @@ extern "C" int32_t lds_k3k4_theta_update(float* theta_full, int64_t ld_theta, in
 
 extern "C" int64_t lds_k3_workspace_bytes(int32_t n, int32_t d) {
   if (n <= 0 || d <= 0) return -1;
-  return round_up((int64_t)n * k3_packed_k(d) * 2, 1024);
+  return round_up((int64_t)n * k3_packed_k(d, 0) * 2, 1024);
 }
 
 extern "C" int32_t lds_k3k4_theta_update_tc(float* theta_full, int64_t ld_theta, int32_t n, int32_t row0, int32_t rows,
@@ -468,7 +467,7 @@ extern "C" int32_t lds_k3k4_theta_update_tc(float* theta_full, int64_t ld_theta,
   const int64_t need = lds_k3_workspace_bytes(n, d);
   if (!workspace || workspace_bytes < need) { set_error("lds_k3k4_theta_update_tc: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need); return LDS_ERR_WORKSPACE; }
   LDS_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "lds_k3k4_theta_update_tc: workspace must be 1024-byte aligned");
-  int32_t rc = k3_launch_pack(fa, fb, ld_f, n, d, workspace, stream);
+  int32_t rc = k3_launch_pack(fa, fb, ld_f, n, d, 0, workspace, stream);
   if (rc != LDS_OK) return rc;
-  return k3_launch_tc(theta_full, ld_theta, n, row0, rows, workspace, d, cvec, lr, stream);
+  return k3_launch_tc(theta_full, ld_theta, n, row0, rows, workspace, k3_packed_k(d, 0), cvec, lr, stream);
 }

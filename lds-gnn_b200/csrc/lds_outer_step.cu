@@ -28,7 +28,8 @@ constexpr int EPI_MAXW = 128;       // widest operand
 enum { B_A = 0, B_DEG, B_RS, B_P1, B_Z1, B_P2, B_Z2, B_DZ2, B_DP2, B_DZ1, B_DP1, B_FA, B_FB, B_C, B_BTHI, B_BTLO, B_PARTIAL, B_LOSSP, B_CORRP, B_F, B_W0S, B_CNT, B_OPND, B_END };
 struct OuterLayout {
   int n, rows, f, h, c, hp1, hp2, hpmax, nblk, panels;
-  int64_t lda, ldb, ldf;
+  int64_t lda, ldb, ldf, ldr;
+  int kf;
   K2Sched s1, s2;
   int64_t off[B_END];
   int64_t total;
@@ -40,14 +41,16 @@ static bool make_layout(int n, int rows, int f, int h, int c, OuterLayout& L, bo
   if (n <= 0 || rows <= 0 || rows > n || f <= 0 || L.hp1 < 0 || L.hp2 < 0) return false;
   L.hpmax = L.hp1 > L.hp2 ? L.hp1 : L.hp2;
   L.lda = round_up(n, kLdAlign); L.ldb = k2_operand_ld(n); L.ldf = round_up(h + c, 4);
+  L.ldr = round_up(rows, 32);                               // row stride of the transposed row-local state ([w][ldr])
+  L.kf = k3_packed_k(h, c);
   L.s1 = k2_make_schedule(n, rows, L.hp1, streamk); L.s2 = k2_make_schedule(n, rows, L.hp2, streamk);
   L.nblk = (int)ceil_div(rows, EPI_ROWS);
   L.panels = (int)ceil_div(rows, K2_BLOCK_M);
   int64_t bytes[B_END];
   bytes[B_A] = (int64_t)rows * L.lda * 2;
   bytes[B_DEG] = bytes[B_RS] = bytes[B_C] = (int64_t)rows * 4;
-  bytes[B_P1] = bytes[B_Z1] = bytes[B_DZ1] = bytes[B_DP1] = (int64_t)rows * h * 4;
-  bytes[B_P2] = bytes[B_Z2] = bytes[B_DZ2] = bytes[B_DP2] = (int64_t)rows * c * 4;
+  bytes[B_P1] = bytes[B_Z1] = bytes[B_DZ1] = bytes[B_DP1] = L.ldr * h * 4;
+  bytes[B_P2] = bytes[B_Z2] = bytes[B_DZ2] = bytes[B_DP2] = L.ldr * c * 4;
   bytes[B_FA] = bytes[B_FB] = (int64_t)rows * L.ldf * 4;
   bytes[B_OPND] = (rows < n) ? (int64_t)rows * (h > c ? h : c) * 4 : 0;        // sharded: operand rows for the all-gather
   bytes[B_BTHI] = bytes[B_BTLO] = k2_operand_bytes(n, L.hpmax);
@@ -55,7 +58,7 @@ static bool make_layout(int n, int rows, int f, int h, int c, OuterLayout& L, bo
   const int64_t p1 = k2_partial_bytes(k2_make_schedule(n, rows, L.hp1, true)), p2 = k2_partial_bytes(k2_make_schedule(n, rows, L.hp2, true));
   bytes[B_PARTIAL] = p1 > p2 ? p1 : p2;
   bytes[B_LOSSP] = bytes[B_CORRP] = (int64_t)ceil_div(rows, K2_BLOCK_M) * 4;
-  bytes[B_F] = (int64_t)n * k3_packed_k(h + c) * 2;        // packed bf16 factor rows of the tensor-core update
+  bytes[B_F] = (int64_t)n * L.kf * 2;                       // packed bf16 factor rows of the tensor-core update (all n rows: K3 needs F_j of every column)
   bytes[B_CNT] = (int64_t)ceil_div(rows, K2_BLOCK_M) * 4;     // per-panel arrival counters of the stream-K reduction
   bytes[B_W0S] = (int64_t)h * round_up(f, 4) * 4;          // staged layer_in weight: transposed [f][h] (CSR path) or padded [h][ldx]
   int64_t o = 0;
@@ -110,7 +113,7 @@ __global__ void stage_w0_kernel(const float* __restrict__ w0, int64_t ldw, int h
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(FEAT_THREADS)
 feat_linear_kernel(const float* __restrict__ x, int64_t ldx, int n, int f, const float* __restrict__ w0, int64_t ldw, const float* __restrict__ b0, int h,
-                   DropCfg dc, const float* __restrict__ rs, float* __restrict__ p1,
+                   DropCfg dc, const float* __restrict__ rs, float* __restrict__ p1, int64_t ldr,
                    __nv_bfloat16* __restrict__ bt_hi, __nv_bfloat16* __restrict__ bt_lo, int64_t ldb, int hp,
                    int row0, float* __restrict__ opnd, int64_t ld_opnd) {
   __shared__ float tile[EPI_MAXW][EPI_ROWS + 1];
@@ -176,11 +179,8 @@ feat_linear_kernel(const float* __restrict__ x, int64_t ldx, int n, int f, const
       }
   }
   __syncthreads();
-  // coalesced P1 rows, then the scaled transposed operand
-  for (int r = 0; r < 4; ++r) {
-    const int rr = 4 * warp + r, i = i0 + rr;
-    if (i < n) for (int c = lane; c < h; c += 32) p1[(int64_t)i * h + c] = tile[c][rr];
-  }
+  // P1 (transposed [h][ldr]: lanes = consecutive rows), then the scaled transposed operand
+  if (i0 + lane < n) for (int c = warp; c < h; c += FEAT_THREADS / 32) p1[(int64_t)c * ldr + i0 + lane] = tile[c][lane];
   __syncthreads();
   {
     const int rr = threadIdx.x & 31;                         // scale column rr of the tile by r_i
@@ -208,7 +208,7 @@ feat_linear_kernel(const float* __restrict__ x, int64_t ldx, int n, int f, const
 __global__ void __launch_bounds__(EPI_THREADS)
 feat_sparse_kernel(const int32_t* __restrict__ crow, const int32_t* __restrict__ xcol, const float* __restrict__ xval, int n, int f,
                    const float* __restrict__ w0t, const float* __restrict__ b0, int h,
-                   DropCfg dc, const float* __restrict__ rs, float* __restrict__ p1,
+                   DropCfg dc, const float* __restrict__ rs, float* __restrict__ p1, int64_t ldr,
                    __nv_bfloat16* __restrict__ bt_hi, __nv_bfloat16* __restrict__ bt_lo, int64_t ldb, int hp,
                    int row0, float* __restrict__ opnd, int64_t ld_opnd) {
   __shared__ float tile[EPI_MAXW][EPI_ROWS + 1];
@@ -255,10 +255,18 @@ feat_sparse_kernel(const int32_t* __restrict__ crow, const int32_t* __restrict__
       const int o = lane + 32 * t;
       if (o < h) {
         const float pv = acc[t] + b0[o];
-        p1[(int64_t)i * h + o] = pv;
-        if (opnd) opnd[(int64_t)i * ld_opnd + o] = ri * pv; else tile[o][rr] = ri * pv;
+        tile[o][rr] = pv;
+        if (opnd) opnd[(int64_t)i * ld_opnd + o] = ri * pv;
       }
     }
+  }
+  __syncthreads();
+  // P1 (transposed [h][ldr]: lanes = consecutive rows); then scale the tile by r_i for the operand
+  const float rl = (i0 + lane < n) ? rs[i0 + lane] : 0.f;
+  for (int c = warp; c < h; c += EPI_THREADS / 32) {
+    const float pv = tile[c][lane];
+    if (i0 + lane < n) p1[(int64_t)c * ldr + i0 + lane] = pv;
+    tile[c][lane] = rl * pv;
   }
   if (opnd) return;
   __syncthreads();
@@ -282,11 +290,13 @@ extern "C" int64_t lds_outer_step_shard_workspace_bytes(int32_t n, int32_t rows,
 }
 
 extern "C" int64_t lds_outer_step_factor_ld(int32_t h, int32_t c) { return round_up(h + c, 4); }
+extern "C" int64_t lds_outer_step_packed_k(int32_t h, int32_t c) { return k3_packed_k(h, c); }
+extern "C" int64_t lds_outer_step_state_ld(int32_t rows) { return round_up(rows, 32); }
 
 extern "C" void* lds_outer_step_shard_buffer(void* workspace, int32_t n, int32_t rows, int32_t f, int32_t h, int32_t c, int32_t which) {
   OuterLayout L;
-  if (!workspace || !make_layout(n, rows, f, h, c, L) || which < 0 || which > 14) return nullptr;
-  const int b = (which == 14) ? B_OPND : which;
+  if (!workspace || !make_layout(n, rows, f, h, c, L) || which < 0 || which > 15) return nullptr;
+  const int b = (which == 14) ? B_OPND : (which == 15) ? B_F : which;
   return reinterpret_cast<uint8_t*>(workspace) + L.off[b];
 }
 
@@ -313,7 +323,10 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
     LDS_CHECK_ARG(phases != 0 && (phases & ~LDS_PHASE_ALL) == 0, "lds_outer_step: sharded calls need a phase mask");
     if (phases & (LDS_PHASE_LAYER1 | LDS_PHASE_LAYER2 | LDS_PHASE_BWD2 | LDS_PHASE_BWD1))
       LDS_CHECK_ARG(A.opnd_full && (phases & (phases - 1)) == 0, "lds_outer_step: a sharded propagation phase runs alone and needs opnd_full");
-    if (phases & LDS_PHASE_UPDATE) LDS_CHECK_ARG(A.fa_full && A.fb_full && A.c_full, "lds_outer_step: PHASE_UPDATE needs the gathered factors");
+    if (phases & LDS_PHASE_UPDATE) {
+      const bool tc = A.opt_kind == LDS_OPT_SGD && !(A.k3_flags & LDS_K3_SIMT);
+      LDS_CHECK_ARG(A.c_full && (tc ? A.f_full != nullptr : (A.fa_full && A.fb_full)), "lds_outer_step: PHASE_UPDATE needs the gathered factors (f_full for the tensor-core SGD update, fa_full/fb_full otherwise) and c_full");
+    }
   }
   const bool sparse_x = A.x_crow != nullptr;
   if (sparse_x) {
@@ -361,11 +374,11 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
     profile_mark(stream, 0);
     const dim3 egrid((unsigned)L.nblk);
     if (sparse_x) {
-      feat_sparse_kernel<<<egrid, EPI_THREADS, 0, stream>>>(A.x_crow, A.x_col, A.x_val, rows, A.f, fbuf(B_W0S), A.b0, A.h, dx, fbuf(B_RS), fbuf(B_P1),
+      feat_sparse_kernel<<<egrid, EPI_THREADS, 0, stream>>>(A.x_crow, A.x_col, A.x_val, rows, A.f, fbuf(B_W0S), A.b0, A.h, dx, fbuf(B_RS), fbuf(B_P1), L.ldr,
                                                             bt_hi, bt_lo, L.ldb, L.hp1, row0, opnd, ld_opnd);
       LDS_CHECK_LAUNCH("feat_sparse_kernel");
     } else {
-      feat_linear_kernel<<<egrid, FEAT_THREADS, 0, stream>>>(A.x, A.ld_x, rows, A.f, fbuf(B_W0S), round_up(A.f, 4), A.b0, A.h, dx, fbuf(B_RS), fbuf(B_P1),
+      feat_linear_kernel<<<egrid, FEAT_THREADS, 0, stream>>>(A.x, A.ld_x, rows, A.f, fbuf(B_W0S), round_up(A.f, 4), A.b0, A.h, dx, fbuf(B_RS), fbuf(B_P1), L.ldr,
                                                              bt_hi, bt_lo, L.ldb, L.hp1, row0, opnd, ld_opnd);
       LDS_CHECK_LAUNCH("feat_linear_kernel");
     }
@@ -378,7 +391,12 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   E.opnd = opnd; E.ld_opnd = ld_opnd;
   E.deg = fbuf(B_DEG); E.rs = fbuf(B_RS);
   E.p1 = fbuf(B_P1); E.z1 = fbuf(B_Z1); E.p2 = fbuf(B_P2); E.z2 = fbuf(B_Z2); E.dz2 = fbuf(B_DZ2); E.dp2 = fbuf(B_DP2);
-  E.dz1 = fbuf(B_DZ1); E.dp1 = fbuf(B_DP1); E.fa = fbuf(B_FA); E.fb = fbuf(B_FB); E.ldf = L.ldf; E.cvec = fbuf(B_C);
+  E.dz1 = fbuf(B_DZ1); E.dp1 = fbuf(B_DP1); E.ldr = L.ldr; E.cvec = fbuf(B_C);
+  // factor rows: packed bf16 for the tensor-core update (own rows inside the n-row F buffer), row-major fp32 for the CUDA-core one
+  const bool tc_update = A.opt_kind == LDS_OPT_SGD && !(A.k3_flags & LDS_K3_SIMT);
+  E.ldf = L.ldf; E.kf = L.kf;
+  if (tc_update) E.fpack = reinterpret_cast<__nv_bfloat16*>(buf(B_F)) + (int64_t)row0 * L.kf;
+  else { E.fa = fbuf(B_FA); E.fb = fbuf(B_FB); }
   E.w1 = A.w1; E.b1 = A.b1; E.y = A.y; E.mask = A.mask; E.inv_m = 1.0f / (float)A.mask_count;
   E.drop_h = dh; E.bt_hi = bt_hi; E.bt_lo = bt_lo; E.ldb = L.ldb;
   E.loss_part = fbuf(B_LOSSP); E.corr_part = fbuf(B_CORRP); E.nblk = L.panels;
@@ -404,15 +422,14 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   if ((rc = propagate(LDS_PHASE_BWD1, L.s1, A.h, K2_EPI_BWD1, 6)) != LDS_OK) return rc;       // dP1, c, factor matrices
 
   if ((phases & LDS_PHASE_UPDATE) && A.update) {
-    const float* fa = sharded ? A.fa_full : fbuf(B_FA);
-    const float* fb = sharded ? A.fb_full : fbuf(B_FB);
     const float* cv = sharded ? A.c_full : fbuf(B_C);
-    if (A.opt_kind == LDS_OPT_SGD && !(A.k3_flags & LDS_K3_SIMT)) {
-      LDS_CHECK_ARG((reinterpret_cast<uintptr_t>(cv) & 15) == 0, "lds_outer_step: c_full must be 16-byte aligned");
-      rc = k3_launch_pack(fa, fb, L.ldf, A.n, A.h + A.c, buf(B_F), stream);
-      profile_mark(stream, 9);
-      if (rc == LDS_OK) rc = k3_launch_tc(A.theta_full, A.ld_theta, A.n, row0, rows, buf(B_F), A.h + A.c, cv, A.lr, stream);
+    if (tc_update) {
+      const void* f = sharded ? A.f_full : buf(B_F);
+      LDS_CHECK_ARG((reinterpret_cast<uintptr_t>(cv) & 15) == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0, "lds_outer_step: c_full / f_full must be 16-byte aligned");
+      rc = k3_launch_tc(A.theta_full, A.ld_theta, A.n, row0, rows, f, L.kf, cv, A.lr, stream);
     } else {
+      const float* fa = sharded ? A.fa_full : fbuf(B_FA);
+      const float* fb = sharded ? A.fb_full : fbuf(B_FB);
       rc = lds_k3k4_theta_update(A.theta_full, A.ld_theta, A.n, row0, rows, fa, fb, L.ldf, A.h + A.c, cv,
                                  A.lr, A.opt_kind, A.adam_m, A.adam_v, A.beta1, A.beta2, A.eps, A.adam_t, nullptr, 0, 0u, stream_);
     }

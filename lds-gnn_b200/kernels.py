@@ -180,7 +180,8 @@ class OuterStep:
     """Resident state + workspace of the fused outer step (lds_outer_step). One instance per (theta, dataset)."""
 
     BUFFERS = {"adj": 0, "deg": 1, "rsqrt": 2, "p1": 3, "z1": 4, "p2": 5, "z2": 6, "dz2": 7, "dp2": 8, "dz1": 9,
-               "dp1": 10, "fa": 11, "fb": 12, "cvec": 13, "operand": 14}
+               "dp1": 10, "fa": 11, "fb": 12, "cvec": 13, "operand": 14, "fpack": 15}
+    TRANSPOSED = ("p1", "z1", "p2", "z2", "dz2", "dp2", "dz1", "dp1")     # stored [width][state_ld] (coalesced row epilogues)
 
     SPARSE_DENSITY = 0.25          # below this share of non-zeros the feature GEMM runs from a CSR copy of x
 
@@ -221,6 +222,7 @@ class OuterStep:
         self.ws_bytes = nbytes
         self.scalars = torch.zeros(4, dtype=torch.float32, device=dev)
         self.args = _lib.OuterStepArgs()
+        self._f32_factors = False
 
     def set_mask(self, mask):
         m = mask.to(device=self.device)
@@ -239,19 +241,35 @@ class OuterStep:
         self.w1, self.b1 = prep(w1, (self.c, self.h)), prep(b1, (self.c,))
 
     def buffer(self, name):
-        """View of an intermediate buffer of the last step (tests / composable path)."""
+        """View of an intermediate buffer of the last step (tests / composable path / the sharded exchange), logical shape
+        [rows, width]. The row-local state is stored transposed in the workspace, so those views are non-contiguous.
+        "fa" / "fb" (fp32 factor rows r*(dZ1|dZ2), r*(P1|P2)) are materialised by the library only for the CUDA-core
+        update; otherwise they are rebuilt here from the state they are defined by."""
+        n, h, c = self.rows, self.h, self.c
+        ldf = int(self.lib.lds_outer_step_factor_ld(h, c))
+        if name in ("fa", "fb") and not self._f32_factors:
+            rs = self.buffer("rsqrt")[:, None]
+            parts = (self.buffer("dz1"), self.buffer("dz2")) if name == "fa" else (self.buffer("p1"), self.buffer("p2"))
+            out = torch.zeros((n, ldf), dtype=torch.float32, device=self.device)
+            out[:, :h] = rs * parts[0]
+            out[:, h:h + c] = rs * parts[1]
+            return out
         which = self.BUFFERS[name]
         ptr = self.lib.lds_outer_step_shard_buffer(_ptr(self.ws), self.n, self.rows, self.f, self.h, self.c, which)
         off = ptr - self.ws.data_ptr()
-        n, h, c = self.rows, self.h, self.c
-        ldf = int(self.lib.lds_outer_step_factor_ld(h, c))
-        shapes = {"adj": (n, padded_ld(self.n)), "deg": (n,), "rsqrt": (n,), "p1": (n, h), "z1": (n, h), "p2": (n, c), "z2": (n, c),
-                  "dz2": (n, c), "dp2": (n, c), "dz1": (n, h), "dp1": (n, h), "fa": (n, ldf), "fb": (n, ldf), "cvec": (n,),
-                  "operand": (n, max(h, c))}
-        shape = shapes[name]
         if name == "adj":
-            numel = shape[0] * shape[1]
-            return self.ws[off:off + 2 * numel].view(BF16).view(shape)
+            shape = (n, padded_ld(self.n))
+            return self.ws[off:off + 2 * shape[0] * shape[1]].view(BF16).view(shape)
+        if name == "fpack":                                  # this rank's rows of the packed bf16 factor matrix
+            kf = int(self.lib.lds_outer_step_packed_k(h, c))
+            off += 2 * kf * self.row0
+            return self.ws[off:off + 2 * n * kf].view(BF16).view(n, kf)
+        if name in self.TRANSPOSED:
+            w = h if name in ("p1", "z1", "dz1", "dp1") else c
+            ldr = int(self.lib.lds_outer_step_state_ld(n))
+            return self.ws[off:off + 4 * w * ldr].view(torch.float32).view(w, ldr)[:, :n].t()
+        shapes = {"deg": (n,), "rsqrt": (n,), "fa": (n, ldf), "fb": (n, ldf), "cvec": (n,), "operand": (n, max(h, c))}
+        shape = shapes[name]
         numel = 1
         for s in shape:
             numel *= s
@@ -260,7 +278,7 @@ class OuterStep:
     def run(self, theta_full, lr, seed, step, dropout_p=0.0, update=True, u=None, keep_x=None, keep_h=None,
             opt_kind=_lib.OPT_SGD, adam_m=None, adam_v=None, betas=(0.9, 0.999), eps=1e-8, adam_t=1,
             out_logp=None, k2_flags=0, k3_flags=0, phases=None, opnd_full=None, fa_full=None, fb_full=None, c_full=None,
-            k2_timeline=None):
+            f_full=None, k2_timeline=None):
         """Enqueue one fused outer step on the current stream. Results: self.scalars[0:2] = (loss, acc)."""
         a = self.args
         a.struct_bytes = ctypes.sizeof(_lib.OuterStepArgs)
@@ -299,6 +317,8 @@ class OuterStep:
         a.fa_full = None if fa_full is None else fa_full.data_ptr()
         a.fb_full = None if fb_full is None else fb_full.data_ptr()
         a.c_full = None if c_full is None else c_full.data_ptr()
+        a.f_full = None if f_full is None else f_full.data_ptr()
+        self._f32_factors = not (opt_kind == _lib.OPT_SGD and not (k3_flags & _lib.K3_SIMT))
         a.k2_timeline = None if k2_timeline is None else k2_timeline.data_ptr()
         _lib.check(self.lib.lds_outer_step(ctypes.byref(a), _stream()), "lds_outer_step")
         return self.scalars

@@ -5,7 +5,9 @@ by contiguous row blocks over the ranks of one box. theta / A_tilde never move:
     row j regenerate the same bit, and the K3 update is symmetric bit for bit (csrc/lds_k3_theta_update.cu);
   * each of the four propagations Z_rows = r_rows * (A_tilde_rows @ (r * P)) needs the scaled N x w operand of ALL
     rows: one all-gather of [rows, w] fp32 blocks (16.8 MB at N = 65 536, w = 64) — the only data-path collective;
-  * the closed-form theta update needs the gathered factor matrices fa, fb [N, d] and c [N];
+  * the closed-form theta update needs the factor rows of ALL nodes and c [N]: for the tensor-core SGD update these
+    are the packed bf16 rows the BWD1 epilogue writes (8 B per factor element, lds_k3.cuh), gathered as they are;
+    for the CUDA-core update (Adam) the fp32 rows fa, fb [N, d];
   * loss / accuracy: one all-reduce of two floats.
 
 `ShardedOuterStep` drives one rank through the phases of `lds_outer_step` (include/lds_b200.h, LDS_PHASE_*);
@@ -68,8 +70,9 @@ class ShardedOuterStep:
         w = max(self.h, self.c)
         self.ldf = int(_lib.load().lds_outer_step_factor_ld(self.h, self.c))
         self.opnd_full = torch.empty((self.n, w), dtype=torch.float32, device=dev)
-        self.fa_full = torch.empty((self.n, self.ldf), dtype=torch.float32, device=dev)
-        self.fb_full = torch.empty((self.n, self.ldf), dtype=torch.float32, device=dev)
+        self.fa_full = self.fb_full = None                   # fp32 factor rows: only for the CUDA-core update (allocated on first use)
+        self.kf = int(_lib.load().lds_outer_step_packed_k(self.h, self.c))
+        self.f_full = torch.empty((self.n, self.kf), dtype=K.BF16, device=dev)
         self.c_full = torch.empty(self.n, dtype=torch.float32, device=dev)
 
     def set_weights(self, *w):
@@ -77,7 +80,21 @@ class ShardedOuterStep:
 
     def phase(self, theta_local, phases, **kw):
         return self.eng.run(theta_local, phases=phases, opnd_full=self.opnd_full, fa_full=self.fa_full, fb_full=self.fb_full,
-                            c_full=self.c_full, **kw)
+                            c_full=self.c_full, f_full=self.f_full, **kw)
+
+    @staticmethod
+    def tensor_core_update(kw):
+        return kw.get("opt_kind", _lib.OPT_SGD) == _lib.OPT_SGD and not (kw.get("k3_flags", 0) & _lib.K3_SIMT)
+
+    def factor_buffers(self, kw):
+        """(workspace buffer name, gathered tensor) pairs PHASE_UPDATE needs besides c."""
+        if self.tensor_core_update(kw):
+            return [("fpack", self.f_full)]
+        if self.fa_full is None:
+            dev = self.opnd_full.device
+            self.fa_full = torch.empty((self.n, self.ldf), dtype=torch.float32, device=dev)
+            self.fb_full = torch.empty((self.n, self.ldf), dtype=torch.float32, device=dev)
+        return [("fa", self.fa_full), ("fb", self.fb_full)]
 
     def run(self, theta_local, comm, lr, seed, step, dropout_p=0.0, update=True, **kw):
         """One sharded outer step on this rank. Returns a device tensor (loss, acc) of the WHOLE graph."""
@@ -87,8 +104,8 @@ class ShardedOuterStep:
             comm.all_gather_rows(self.eng.buffer("operand"), self.opnd_full)
             self.phase(theta_local, ph, **kw)
         scalars = comm.all_reduce_sum(self.eng.scalars[:2].clone())
-        comm.all_gather_rows(self.eng.buffer("fa"), self.fa_full)
-        comm.all_gather_rows(self.eng.buffer("fb"), self.fb_full)
+        for name, full in self.factor_buffers(kw):
+            comm.all_gather_rows(self.eng.buffer(name), full)
         comm.all_gather_rows(self.eng.buffer("cvec").view(-1, 1), self.c_full.view(-1, 1))
         self.phase(theta_local, _lib.PHASE_UPDATE, **kw)
         return scalars
@@ -105,6 +122,9 @@ def run_local_group(shards, thetas, lr, seed, step, dropout_p=0.0, update=True, 
         for s in shards:
             getattr(s, attr).view(full.shape).copy_(full)
 
+    for s in shards:
+        s.factor_buffers(kw)                                 # allocate the fp32 factor buffers if this step needs them
+
     for s, t in zip(shards, thetas):
         s.phase(t, _lib.PHASE_SAMPLE, **kw)
     for ph in PHASES:
@@ -112,8 +132,11 @@ def run_local_group(shards, thetas, lr, seed, step, dropout_p=0.0, update=True, 
         for s, t in zip(shards, thetas):
             s.phase(t, ph, **kw)
     scalars = sum(s.eng.scalars[:2].clone() for s in shards)
-    gather("fa", "fa_full")
-    gather("fb", "fb_full")
+    if shards[0].tensor_core_update(kw):
+        gather("fpack", "f_full")
+    else:
+        gather("fa", "fa_full")
+        gather("fb", "fb_full")
     gather("cvec", "c_full", view=(-1,))
     for s, t in zip(shards, thetas):
         s.phase(t, _lib.PHASE_UPDATE, **kw)
