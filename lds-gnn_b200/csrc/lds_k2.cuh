@@ -6,7 +6,7 @@ namespace lds {
 
 constexpr int K2_BLOCK_M = 128;      // rows of A_tilde per output tile (= UMMA M, cta_group::1)
 constexpr int K2_BLOCK_K = 64;       // bf16 elements per k-block = one 128-byte swizzle atom
-constexpr int K2_THREADS = 192;      // warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue
+constexpr int K2_THREADS = 576;      // warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-17 epilogue (2-5 drain TMEM)
 
 // Stream-K schedule: the (panel, k-block) space is linearised (panel-major) and cut into equal contiguous
 // ranges, one per CTA. A CTA writes one fp32 partial tile (128 x HP) per panel its range touches into
