@@ -13,7 +13,7 @@ BF16 = torch.bfloat16
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
 
 
 def _ptr(t):
@@ -222,12 +222,16 @@ class OuterStep:
         self.ws_bytes = nbytes
         self.scalars = torch.zeros(4, dtype=torch.float32, device=dev)
         self.args = _lib.OuterStepArgs()
+        self._args_ref = ctypes.byref(self.args)
         self._f32_factors = False
+        self._init_static_args()
 
     def set_mask(self, mask):
         m = mask.to(device=self.device)
         self.mask = m.to(torch.uint8).contiguous()
         self.mask_count = int(m.sum().item()) if self._mask_count_override is None else int(self._mask_count_override)
+        if getattr(self, "args", None) is not None:
+            self.args.mask, self.args.mask_count = self.mask.data_ptr(), self.mask_count
 
     def set_weights(self, w0, b0, w1, b1):
         """Use these GCN (fast) weights for the next steps. No copies: the step's first kernel stages the layer_in
@@ -275,50 +279,74 @@ class OuterStep:
             numel *= s
         return self.ws[off:off + 4 * numel].view(torch.float32).view(shape)
 
-    def run(self, theta_full, lr, seed, step, dropout_p=0.0, update=True, u=None, keep_x=None, keep_h=None,
-            opt_kind=_lib.OPT_SGD, adam_m=None, adam_v=None, betas=(0.9, 0.999), eps=1e-8, adam_t=1,
-            out_logp=None, k2_flags=0, k3_flags=0, phases=None, opnd_full=None, fa_full=None, fb_full=None, c_full=None,
-            f_full=None, k2_timeline=None):
-        """Enqueue one fused outer step on the current stream. Results: self.scalars[0:2] = (loss, acc)."""
+    def _init_static_args(self):
+        """Fields of the argument block that do not change between steps (set once; `run` touches the rest)."""
         a = self.args
         a.struct_bytes = ctypes.sizeof(_lib.OuterStepArgs)
         a.n, a.f, a.h, a.c = self.n, self.f, self.h, self.c
-        a.theta_full, a.ld_theta = theta_full.data_ptr(), theta_full.stride(0)
         a.x, a.ld_x = self.x.data_ptr(), self.ld_x
         if self.sparse:
             a.x_crow, a.x_col, a.x_val = self.x_crow.data_ptr(), self.x_col.data_ptr(), self.x_val.data_ptr()
         else:
             a.x_crow = a.x_col = a.x_val = None
         a.reserved_ptr = None
-        a.w0, a.ld_w0 = self.w0.data_ptr(), self.f
-        a.b0, a.w1, a.b1 = self.b0.data_ptr(), self.w1.data_ptr(), self.b1.data_ptr()
+        a.ld_w0 = self.f
         a.y, a.mask, a.mask_count = self.y.data_ptr(), self.mask.data_ptr(), self.mask_count
+        a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws_bytes
+        a.row0, a.rows, a.phases, a.reserved2 = (self.row0, self.rows, 0, 0) if self.sharded else (0, 0, 0, 0)
+        self._clear_optional_args()
+
+    def _clear_optional_args(self):
+        a = self.args
+        a.u_explicit, a.ld_u, a.keep_x, a.keep_h = None, 0, None, None
+        a.adam_m = a.adam_v = None
+        a.beta1, a.beta2, a.eps, a.adam_t = 0.9, 0.999, 1e-8, 1
+        a.out_logp = None
+        a.k2_flags = a.k3_flags = 0
+        a.opnd_full = a.fa_full = a.fb_full = a.c_full = a.f_full = a.k2_timeline = None
+        a.out_scalars = self.scalars.data_ptr()
+        self._optional_set = False
+
+    def run(self, theta_full, lr, seed, step, dropout_p=0.0, update=True, u=None, keep_x=None, keep_h=None,
+            opt_kind=_lib.OPT_SGD, adam_m=None, adam_v=None, betas=(0.9, 0.999), eps=1e-8, adam_t=1,
+            out_logp=None, k2_flags=0, k3_flags=0, phases=None, opnd_full=None, fa_full=None, fb_full=None, c_full=None,
+            f_full=None, k2_timeline=None, scalars_out=None):
+        """Enqueue one fused outer step on the current stream. Results: (loss, acc) in `scalars_out[0:2]` (any fp32
+        buffer the device can write, e.g. pinned host memory) or, by default, in self.scalars."""
+        a = self.args
+        a.theta_full, a.ld_theta = theta_full.data_ptr(), theta_full.stride(0)
+        a.w0, a.b0, a.w1, a.b1 = self.w0.data_ptr(), self.b0.data_ptr(), self.w1.data_ptr(), self.b1.data_ptr()
         a.dropout_p = float(dropout_p)
         a.seed, a.step = int(seed), int(step)
-        a.u_explicit, a.ld_u = (None, 0) if u is None else (u.data_ptr(), u.stride(0))
-        a.keep_x = None if keep_x is None else keep_x.data_ptr()
-        a.keep_h = None if keep_h is None else keep_h.data_ptr()
         a.lr, a.opt_kind = float(lr), int(opt_kind)
-        a.adam_m = None if adam_m is None else adam_m.data_ptr()
-        a.adam_v = None if adam_v is None else adam_v.data_ptr()
-        a.beta1, a.beta2, a.eps, a.adam_t = float(betas[0]), float(betas[1]), float(eps), int(adam_t)
         a.update = int(bool(update))
-        a.out_scalars = self.scalars.data_ptr()
-        a.out_logp = None if out_logp is None else out_logp.data_ptr()
-        a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws_bytes
-        a.k2_flags, a.k3_flags = int(k2_flags), int(k3_flags)
+        plain = (u is None and keep_x is None and keep_h is None and adam_m is None and out_logp is None and not k2_flags
+                 and not k3_flags and opnd_full is None and fa_full is None and c_full is None and f_full is None
+                 and k2_timeline is None and scalars_out is None)
+        if not plain or self._optional_set:
+            if plain:
+                self._clear_optional_args()
+            else:
+                a.u_explicit, a.ld_u = (None, 0) if u is None else (u.data_ptr(), u.stride(0))
+                a.keep_x = None if keep_x is None else keep_x.data_ptr()
+                a.keep_h = None if keep_h is None else keep_h.data_ptr()
+                a.adam_m = None if adam_m is None else adam_m.data_ptr()
+                a.adam_v = None if adam_v is None else adam_v.data_ptr()
+                a.beta1, a.beta2, a.eps, a.adam_t = float(betas[0]), float(betas[1]), float(eps), int(adam_t)
+                a.out_scalars = self.scalars.data_ptr() if scalars_out is None else scalars_out.data_ptr()
+                a.out_logp = None if out_logp is None else out_logp.data_ptr()
+                a.k2_flags, a.k3_flags = int(k2_flags), int(k3_flags)
+                a.opnd_full = None if opnd_full is None else opnd_full.data_ptr()
+                a.fa_full = None if fa_full is None else fa_full.data_ptr()
+                a.fb_full = None if fb_full is None else fb_full.data_ptr()
+                a.c_full = None if c_full is None else c_full.data_ptr()
+                a.f_full = None if f_full is None else f_full.data_ptr()
+                a.k2_timeline = None if k2_timeline is None else k2_timeline.data_ptr()
+                self._optional_set = True
         if self.sharded:
             if phases is None:
                 raise ValueError("a row-block shard runs phase by phase (lds_gnn_b200.sharded.ShardedOuterStep)")
-            a.row0, a.rows, a.phases, a.reserved2 = self.row0, self.rows, int(phases), 0
-        else:
-            a.row0, a.rows, a.phases, a.reserved2 = 0, 0, 0, 0
-        a.opnd_full = None if opnd_full is None else opnd_full.data_ptr()
-        a.fa_full = None if fa_full is None else fa_full.data_ptr()
-        a.fb_full = None if fb_full is None else fb_full.data_ptr()
-        a.c_full = None if c_full is None else c_full.data_ptr()
-        a.f_full = None if f_full is None else f_full.data_ptr()
+            a.phases = int(phases)
         self._f32_factors = not (opt_kind == _lib.OPT_SGD and not (k3_flags & _lib.K3_SIMT))
-        a.k2_timeline = None if k2_timeline is None else k2_timeline.data_ptr()
-        _lib.check(self.lib.lds_outer_step(ctypes.byref(a), _stream()), "lds_outer_step")
-        return self.scalars
+        _lib.check(self.lib.lds_outer_step(self._args_ref, _stream()), "lds_outer_step")
+        return self.scalars if scalars_out is None else scalars_out

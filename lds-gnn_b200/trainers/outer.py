@@ -76,6 +76,7 @@ class OuterProblemTrainer:
         self.last_route = None             # "fused" | "composable" (observability / tests)
         self._engine = None
         self._adam_state = None
+        self._host_scalars = None
         if pretrain:
             self.pretrain_model()
 
@@ -172,8 +173,10 @@ class OuterProblemTrainer:
     def _train_step_fused(self, inner, opt) -> Metrics:
         self.last_route = "fused"
         model, gcn = self.model, inner.model
-        model.train()
-        gcn.train(True)                                   # side effect of model_forward(graph, is_train=True)
+        if not model.training:
+            model.train()
+        if not gcn.training:
+            gcn.train(True)                               # side effect of model_forward(graph, is_train=True)
         eng = self._get_engine(gcn)
         params = inner.model_params
         eng.set_weights(params["layer_in.fc.weight"], params["layer_in.fc.bias"],
@@ -188,13 +191,18 @@ class OuterProblemTrainer:
             st["t"] += 1
             extra = dict(adam_m=st["m"], adam_v=st["v"], betas=group["betas"], eps=group["eps"], adam_t=st["t"])
         seed, step = PHILOX.next_step()
-        scalars = eng.run(theta, lr=group["lr"], seed=seed, step=step, dropout_p=float(gcn.dropout),
-                          update=True, opt_kind=kind, **extra)
+        # (loss, acc) land in pinned host memory, written by the step's own kernel: the step's one device->host
+        # transfer is those 8 bytes, and the host only waits for the stream.
+        if self._host_scalars is None:
+            self._host_scalars = torch.zeros(4, dtype=torch.float32).pin_memory()
+        eng.run(theta, lr=group["lr"], seed=seed, step=step, dropout_p=float(gcn.dropout),
+                update=True, opt_kind=kind, scalars_out=self._host_scalars, **extra)
         model.mark_full_updated()
         if self.lr_decayer is not None:
             self.optimizer._opt_called = True             # the update ran in the kernel; keeps StepLR's order check quiet
             self.lr_decayer.step()
-        loss, acc = scalars[:2].tolist()                  # the step's one device->host read
+        torch.cuda.current_stream().synchronize()
+        loss, acc = self._host_scalars[:2].tolist()
         return Metrics(loss=loss, acc=acc)
 
     # ------------------------------------------------------------------------------------------ rest of the API
