@@ -71,6 +71,18 @@ def load_peaks_json():
     return peaks()
 
 
+def ncu_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture of
+    this workload (profiles/ncu_traffic.json, written by scripts/ncu_traffic.py from the .ncu-rep), or (None, None)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as fh:
+            entry = json.load(fh)[workload][kernel]
+        return int(entry["dram_bytes"]), entry["source"]
+    except (OSError, KeyError, ValueError):
+        return None, None
+
+
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     """nvidia-smi sampling in the background (started early: it needs a few hundred ms to come up); `stop(t0, t1)` keeps
@@ -288,8 +300,9 @@ def run_ours(args, rank, world, device):
         alg = per_kernel_bytes.get(dominant_id)
         if alg is not None:
             achieved = alg / mean_s / 1e9
+            traffic, traffic_src = ncu_traffic(args.workload, KERNEL_NAMES[dominant_id])
             roofline = {"kernel": KERNEL_NAMES[dominant_id], "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak,
-                        "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": None,
+                        "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                         "algorithmic_bytes_per_launch": alg, "mean_launch_us": round(mean_s * 1e6, 2), "peak_source": peak_src,
                         "note": "working set fits the 126 MB L2 at this shape: DRAM traffic can be below algorithmic bytes"}
         else:
@@ -481,7 +494,8 @@ def run_large(args, rank, world, device, workload):
                 "api": "lds_gnn_b200.sharded.ShardedOuterStep.run" if world > 1 else "lds_gnn_b200.kernels.OuterStep.run"},
         "gpu_launches": (LAUNCHES_PER_STEP + (4 if world > 1 else 0)) * args.steps,
         "roofline": {"kernel": KERNEL_NAMES[dom], "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
-                     "frac": round(achieved / hbm_peak, 4), "traffic": None, "algorithmic_bytes_per_launch": alg[dom],
+                     "frac": round(achieved / hbm_peak, 4), "traffic": ncu_traffic(workload if world == 1 else None, KERNEL_NAMES[dom])[0],
+                     "traffic_source": ncu_traffic(workload if world == 1 else None, KERNEL_NAMES[dom])[1], "algorithmic_bytes_per_launch": alg[dom],
                      "mean_launch_us": round(mean_s * 1e6, 1), "peak_source": peak_src, "scope": "per GPU (rank 0)"},
         "step_roofline": {"algorithmic_bytes_per_step_per_gpu": step_bytes,
                           "frac_of_hbm_peak": round(step_bytes / (dev_ms / 1e3 / args.steps) / 1e9 / hbm_peak, 4)},
