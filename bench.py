@@ -585,7 +585,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"               # keep stdout to the single JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the single JSON line only
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("WARN", "VERSION"):
+            os.environ.pop("NCCL_DEBUG")                # WARN / VERSION print "NCCL version ..." on stdout
         dist.init_process_group("nccl", device_id=device)
     workload = args.workload
     if world > 1 and workload in ("citeseer", "cora", "tiny") and not args.replicas:
