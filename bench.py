@@ -38,7 +38,7 @@ import torch
 METRIC = "lds_outer_steps_per_sec"
 UNIT = "steps/s"
 KERNEL_NAMES = {0: "k1_sample_normalize", 1: "feat_linear", 3: "k2_layer1", 4: "k2_layer2", 5: "k2_bwd2", 6: "k2_bwd1",
-                7: "k3k4_theta_update", 8: "stage_w0"}
+                7: "k3k4_theta_update", 8: "stage_w0", 10: "fused_k1_feat_k2x4"}
 K2_IDS = (3, 4, 5, 6)       # the four tcgen05 propagations (each with its fused row epilogue)
 LAUNCHES_PER_STEP = 8       # weight staging, K1, feature GEMM, 4 x K2 (+ fused row epilogue), K3+K4 (csrc/lds_outer_step.cu)
 HYPER = dict(lr=0.1, lr_decay=0.99, dropout=0.5)            # configs/seml/final/lds.yaml:18-110
@@ -151,7 +151,9 @@ def make_workload(name, seed=0):
 
 def algorithmic_bytes(shape):
     n, f = shape["n"], shape["f"]
-    per_kernel = {0: 6 * n * n, 3: 2 * n * n, 4: 2 * n * n, 5: 2 * n * n, 6: 2 * n * n, 7: 8 * n * n}
+    # per-unit figures of SURVEY.md 8(d): K1 6 N^2, each propagation 2 N^2, K3+K4 8 N^2. The fused small-graph kernel (id 10)
+    # covers K1 + the four propagations = 14 N^2 algorithmic bytes; its DRAM traffic is far lower (A_tilde stays in smem).
+    per_kernel = {0: 6 * n * n, 3: 2 * n * n, 4: 2 * n * n, 5: 2 * n * n, 6: 2 * n * n, 7: 8 * n * n, 10: 14 * n * n}
     step = 6 * n * n + 4 * 2 * n * n + 8 * n * n + 4 * n * f            # the outer step reads X once (no dW)
     return per_kernel, step
 
@@ -190,7 +192,7 @@ def run_ours(args, rank, world, device):
     seed = 1234 + rank
 
     def one(step_idx, lr_now):
-        eng.run(theta, lr=lr_now, seed=seed, step=step_idx, dropout_p=HYPER["dropout"], update=True)
+        eng.run(theta, lr=lr_now, seed=seed, step=step_idx, dropout_p=HYPER["dropout"], update=True, want_adj=False)
 
     for w in range(args.warmup):
         one(w, lr); lr *= HYPER["lr_decay"]
@@ -320,7 +322,7 @@ def run_ours(args, rank, world, device):
         "clocks": clock_info,
         "e2e": {"value": round(total_steps / (e2e_ms / 1e3), 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
                 "api": "OuterProblemTrainer.train_step(InnerProblemTrainer.model_forward)", "l2": "not flushed"},
-        "gpu_launches": LAUNCHES_PER_STEP * args.steps,
+        "gpu_launches": (2 if 10 in per_kernel else LAUNCHES_PER_STEP) * args.steps,      # fused small-graph kernel + K3K4, else 8
         "roofline": roofline,
         "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "frac_of_hbm_peak": round(step_frac, 4)},
         "warm_l2": {"value": round(total_steps / (warm_ms / 1e3), 2), "unit": UNIT, "ms_per_step": round(warm_ms / args.steps, 5)},
@@ -395,7 +397,7 @@ def run_large(args, rank, world, device, workload):
     else:
         eng = K.OuterStep(n, d["x"], d["y"], d["mask"], hidden=h, classes=c)
         eng.set_weights(*views)
-        step_fn = lambda k, lr_now: eng.run(theta, lr=lr_now, seed=1234, step=k, dropout_p=HYPER["dropout"], update=True)
+        step_fn = lambda k, lr_now: eng.run(theta, lr=lr_now, seed=1234, step=k, dropout_p=HYPER["dropout"], update=True, want_adj=False)
     lr = HYPER["lr"]
     for w in range(args.warmup):
         step_fn(w, lr); lr *= HYPER["lr_decay"]

@@ -41,6 +41,8 @@ extern "C" {
 #define LDS_K2_SIMT          1u  /* CUDA-core validation kernel instead of the tcgen05 kernel (tests only)    */
 #define LDS_K2_SINGLE_BF16   2u  /* operand as one bf16 term instead of the hi+lo split                       */
 #define LDS_K2_FORCE_STREAMK 4u  /* split panels across CTAs (stream-K) even when every panel could own a CTA   */
+#define LDS_K2_NO_FUSE       8u  /* lds_outer_step: never take the fused small-graph kernel (one launch per stage)   */
+#define LDS_K2_DUMP_ADJ     16u  /* lds_outer_step: the fused small-graph kernel also writes A_tilde to the workspace */
 /* K3 flags */
 #define LDS_K3_DENSE_GRAD    1u  /* write dL/dA_tilde (dense, not symmetrised) instead of updating theta      */
 #define LDS_K3_ACCUMULATE    2u  /* with DENSE_GRAD: add into grad_out instead of overwriting                  */
@@ -126,7 +128,10 @@ int32_t lds_k3k4_theta_update_tc(float* theta_full, int64_t ld_theta, int32_t n,
 /* ---- fused direct outer step (a4..a11): one OuterProblemTrainer.train_step (src/trainers/outer.py:57-87)
  * with gcn_predict_fct = InnerProblemTrainer.model_forward (src/trainers/inner.py:76-78) at fixed weights,
  * regularize = False. Enqueues K1, the feature GEMM with fused dropout, 4 x K2 with their row epilogues
- * (scaling, relu, dropout, second linear, log-softmax, NLL/accuracy, backward chain), K3+K4. */
+ * (scaling, relu, dropout, second linear, log-softmax, NLL/accuracy, backward chain), K3+K4.
+ * Small graphs (h, c <= 16, CSR features, A_tilde <= ~23 MB, e.g. Cora / Citeseer shape) run everything up to the
+ * update as ONE cooperative kernel that keeps A_tilde in shared memory (it never touches HBM), then K3+K4.
+ * The workspace must be zero-filled before its FIRST use (the library leaves its counters re-armed after every call). */
 typedef struct lds_outer_step_args {
   uint32_t struct_bytes;      /* sizeof(lds_outer_step_args), checked                                   */
   int32_t  n, f, h, c;        /* nodes, features, hidden, classes                                       */
@@ -210,7 +215,8 @@ int64_t lds_outer_step_state_ld(int32_t rows);           /* row stride of the tr
  * lds_outer_step records a CUDA event on its stream after every kernel launch. lds_profile_end synchronises on
  * the last event and returns the number of intervals written: ms_out[i] = device time of the launch whose id is
  * ids_out[i] (host, both arrays of capacity `cap`). ids: 0 K1, 1 feature GEMM, 3/4/5/6 the four K2 propagations
- * (layer 1, layer 2, backward 2, backward 1, each with its fused row epilogue), 7 K3+K4, 8 weight staging. Not graph-capturable while active. */
+ * (layer 1, layer 2, backward 2, backward 1, each with its fused row epilogue), 7 K3+K4, 8 weight staging, 10 the fused
+ * small-graph kernel (replaces 8, 0, 1, 3-6). Not graph-capturable while active. */
 int32_t lds_profile_begin(void);
 int32_t lds_profile_end(float* ms_out, int32_t* ids_out, int32_t cap);
 

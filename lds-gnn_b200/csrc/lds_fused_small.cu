@@ -1,0 +1,356 @@
+// lds_fused_small.cu — small-graph path of the outer step: K1 + feature GEMM + the four propagations as ONE
+// persistent cooperative kernel with A_tilde resident in shared memory.
+//
+// At Cora / Citeseer shape (N = 2708 / 3327) the sampled adjacency (2 N^2 bytes: 14.7 / 22.1 MB) fits the combined
+// shared memory of the 148 SMs (33 MB). The multi-kernel path writes A_tilde to HBM once and streams it back four
+// times (10 N^2 of the step's 22 N^2 bytes) through five launches whose fixed costs (launch, TMEM / barrier setup,
+// pipeline fill, tail) dominate at this size. Here every CTA owns the same contiguous range of (row panel, k-block)
+// tiles for the whole kernel (the stream-K schedule of lds_k2.cuh, at most FS_MAX_TILES tiles of 128 x 64):
+//
+//   P0  sample its tiles straight into shared memory in the UMMA K-major SWIZZLE_128B layout (Philox keyed on the
+//       canonical (min,max) 2x2 block, integer compare, self loops — bit-identical to k1_sample_kernel), write the
+//       per-tile row sums; transpose its slice of layer_in.weight                                   — grid barrier
+//   P1  deg = sum of the row sums, r = deg^-1/2; P1 = dropout(X) W0^T + b0 for its rows (CSR X, one warp per
+//       row), operand (r P1)^T as bf16 hi/lo                                                         — grid barrier
+//   P2  four times: TMA-load the operand k-blocks of its range, tcgen05.mma against the RESIDENT A tiles, drain /
+//       count in / last-arriver reduction + row epilogue exactly as the K2 kernel (lds_k2_device.cuh) — grid barrier
+//
+// The theta update (K3+K4) stays its own launch. Reference semantics: see lds_k1_sample.cu, lds_outer_step.cu and
+// lds_epilogue.cuh (src/models/sampling.py:47-85, src/utils/graph.py:123-153, src/models/gcn.py:23-34).
+#include <string.h>
+#include "lds_fused_small.cuh"
+#include "lds_k2_device.cuh"
+
+namespace lds {
+
+constexpr int FS_A_BYTES = K2_BLOCK_M * K2_BLOCK_K * 2;      // 16 KB: one resident A tile
+constexpr int FS_B_BYTES = FS_HP * K2_BLOCK_K * 2;           // 2 KB: one bf16 term of one operand k-block
+constexpr int FS_SMEM = FS_MAX_TILES * (FS_A_BYTES + 2 * FS_B_BYTES) + 1024 + 256;
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const unsigned* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Sense-reversing grid barrier over `bar` = {arrival count, generation}. All CTAs are co-resident (cooperative launch).
+// The count returns to zero after every barrier; the generation only grows, and every CTA reads its value at kernel
+// start (`base`) before it can change, so nothing has to be reset between launches. Bounded spin: a protocol bug traps.
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned base, unsigned& k, unsigned nctas) {
+  __syncthreads();                                           // the CTA's writes happen-before thread 0's cumulative release below
+  if (threadIdx.x == 0) {
+    const unsigned want = base + k + 1;
+    unsigned old;
+    asm volatile("fence.proxy.async;" ::: "memory");         // generic-proxy writes -> TMA (async proxy) reads of other CTAs
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(bar) : "memory");
+    if (old == nctas - 1) {                                  // last to arrive: re-arm the count, then release the generation
+      asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(bar), "r"(0u) : "memory");
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(want) : "memory");
+    } else {
+      long long t0 = 0;
+      for (unsigned spins = 0; ld_acquire_u32(&bar[1]) != want; ++spins) {
+        if (spins == 64) t0 = clock64();
+        if (spins > 64 && (spins & 255) == 0 && clock64() - t0 > 4000000000ll) {
+          printf("liblds_b200: grid barrier timed out (block %d, barrier %u)\n", blockIdx.x, k);
+          __trap();
+        }
+      }
+    }
+  }
+  __syncthreads();
+  ++k;
+}
+
+__global__ void __launch_bounds__(K2_THREADS, 1)
+fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo,
+                   const __grid_constant__ FusedSmallArgs fa) {
+  __shared__ K2EpiShared sh_epi;
+  __shared__ unsigned sh_base;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sa = smem;                                        // resident A tiles
+  uint8_t* sb = smem + FS_MAX_TILES * FS_A_BYTES;            // operand k-blocks of the current propagation: [tile][hi, lo]
+  uint64_t* bfull = reinterpret_cast<uint64_t*>(sb + FS_MAX_TILES * 2 * FS_B_BYTES);
+  uint64_t* tfull_bar = bfull + 1;                           // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;                      // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const K2Sched& s = fa.s;
+  const EpiArgs& ea = fa.ea;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cta = blockIdx.x;
+  const int lo = cta * s.per_cta;                              // panel-aligned schedule: [lo, hi) lies inside ONE panel of the
+  const int hi = lo + s.per_cta;                               // virtual (padded) k-range; k-blocks >= kb_real do not exist
+  const int n = fa.n;
+  const int my_p = lo / s.kblocks, my_kb0 = lo - my_p * s.kblocks;
+  const int nt = min(s.per_cta, fa.kb_real - my_kb0);         // real tiles of this CTA (>= 1)
+
+  if (tid == 0) sh_base = ld_acquire_u32(&fa.gridbar[1]);
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_bhi); tma_prefetch_desc(&tm_blo); }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(bfull, 1);
+      for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 64);                                // two accumulators of [hi | lo] products: 2 x 32 columns
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const unsigned gbase = sh_base;
+  unsigned gk = 0;
+  auto stamp = [&](int k) {
+    if (fa.timeline != nullptr && tid == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      fa.timeline[(size_t)cta * 16 + k] = t;
+    }
+  };
+  stamp(0);
+
+  // ================= P0: weight staging, panel counters, sampling into shared memory =================
+  for (int idx = cta * K2_THREADS + tid; idx < fa.f * ea.h; idx += gridDim.x * K2_THREADS) {
+    const int ff = idx / ea.h, o = idx - ff * ea.h;
+    fa.w0t[idx] = fa.w0[(int64_t)o * fa.ldw + ff];
+  }
+  if (cta == 0) for (int k = tid; k < s.panels; k += K2_THREADS) fa.counters[k] = 0;
+  if (warp < 16) {
+    const int rp = tid >> 3, c8 = tid & 7;                   // item = (row pair, 8-column chunk) of a 128 x 64 tile
+    const int gi0 = my_p * K2_BLOCK_M + 2 * rp, gi1 = gi0 + 1;
+    const int pblk = gi0 >> 1;
+    const float* row0p = fa.theta + (int64_t)gi0 * fa.ldt + 8 * c8;
+    const float* row1p = fa.theta + (int64_t)gi1 * fa.ldt + 8 * c8;
+    // theta rows are padded to ld >= round_up(n, 64): the 8 columns are always inside the row. The NEXT tile's theta is
+    // in flight while this tile's draws are computed (one item per thread per tile: the loop is latency-bound otherwise).
+    float4 nx[4];
+    auto load_theta = [&](int kb) {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      nx[0] = nx[1] = nx[2] = nx[3] = z;
+      if (gi0 < n) { const float4* r = reinterpret_cast<const float4*>(row0p + kb * K2_BLOCK_K); nx[0] = r[0]; nx[1] = r[1]; }
+      if (gi1 < n) { const float4* r = reinterpret_cast<const float4*>(row1p + kb * K2_BLOCK_K); nx[2] = r[0]; nx[3] = r[1]; }
+    };
+    // pull every theta tile of this CTA towards L2 right away (no registers needed): the loop below then runs at L2 latency
+    for (int j = 1; j < nt; ++j) {
+      if (gi0 < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(row0p + (my_kb0 + j) * K2_BLOCK_K));
+      if (gi1 < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(row1p + (my_kb0 + j) * K2_BLOCK_K));
+    }
+    load_theta(my_kb0);
+    for (int j = 0; j < nt; ++j) {
+      const int kb = my_kb0 + j;
+      const int gj0 = kb * K2_BLOCK_K + 8 * c8;
+      const float th0[8] = {nx[0].x, nx[0].y, nx[0].z, nx[0].w, nx[1].x, nx[1].y, nx[1].z, nx[1].w};
+      const float th1[8] = {nx[2].x, nx[2].y, nx[2].z, nx[2].w, nx[3].x, nx[3].y, nx[3].z, nx[3].w};
+      if (j + 1 < nt) load_theta(kb + 1);
+      uint32_t b0[8], b1[8];
+      if (fa.u_explicit != nullptr) {                        // parity mode: element (i,j) uses U[min][max] (src/models/sampling.py:76)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int gj = gj0 + e;
+          b0[e] = 0u; b1[e] = 0u;
+          if (gj < n) {
+            if (gi0 < n) { const float u = (gi0 <= gj) ? fa.u_explicit[(int64_t)gi0 * fa.ldu + gj] : fa.u_explicit[(int64_t)gj * fa.ldu + gi0];
+                           b0[e] = (u < fminf(fmaxf(th0[e], 0.f), 1.f)) ? 1u : 0u; }
+            if (gi1 < n) { const float u = (gi1 <= gj) ? fa.u_explicit[(int64_t)gi1 * fa.ldu + gj] : fa.u_explicit[(int64_t)gj * fa.ldu + gi1];
+                           b1[e] = (u < fminf(fmaxf(th1[e], 0.f), 1.f)) ? 1u : 0u; }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {                        // four 2x2 Philox blocks: column blocks q
+          const int q = (gj0 >> 1) + b;
+          const bool upper = pblk < q;
+          uint32_t w[4];
+          philox4x32_10_rk((uint32_t)(upper ? q : pblk), (uint32_t)(upper ? pblk : q), fa.rounds, w);
+          // word = 2*(a%2) + (b%2) of the canonical pair (a, b) = (min, max); the diagonal block uses w[1] for both off-diagonal cells
+          const uint32_t w01 = (pblk <= q) ? w[1] : w[2], w10 = upper ? w[2] : w[1];
+          b0[2 * b]     = ((w[0] >> 8) < __float2uint_ru(th0[2 * b] * 16777216.f)) ? 1u : 0u;
+          b0[2 * b + 1] = ((w01 >> 8)  < __float2uint_ru(th0[2 * b + 1] * 16777216.f)) ? 1u : 0u;
+          b1[2 * b]     = ((w10 >> 8)  < __float2uint_ru(th1[2 * b] * 16777216.f)) ? 1u : 0u;
+          b1[2 * b + 1] = ((w[3] >> 8) < __float2uint_ru(th1[2 * b + 1] * 16777216.f)) ? 1u : 0u;
+        }
+      }
+      uint32_t s0 = 0, s1 = 0;
+      // only the two k-blocks that cross the panel's diagonal and the last k-block / last panel need the per-cell checks
+      const bool edge = (kb >> 1) == my_p || (kb + 1) * K2_BLOCK_K > n || (my_p + 1) * K2_BLOCK_M > n;
+      if (edge) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int gj = gj0 + e;
+          if (gj == gi0) b0[e] = 1u;                         // self loops: diag := 1 (src/utils/graph.py:131-132)
+          if (gj == gi1) b1[e] = 1u;
+          if (gj >= n || gi0 >= n) b0[e] = 0u;
+          if (gj >= n || gi1 >= n) b1[e] = 0u;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s0 += b0[e]; s1 += b1[e]; }
+      uint4 v0, v1;                                          // bf16 1.0 = 0x3F80
+      v0.x = b0[0] * 0x3F80u + b0[1] * 0x3F800000u; v0.y = b0[2] * 0x3F80u + b0[3] * 0x3F800000u;
+      v0.z = b0[4] * 0x3F80u + b0[5] * 0x3F800000u; v0.w = b0[6] * 0x3F80u + b0[7] * 0x3F800000u;
+      v1.x = b1[0] * 0x3F80u + b1[1] * 0x3F800000u; v1.y = b1[2] * 0x3F80u + b1[3] * 0x3F800000u;
+      v1.z = b1[4] * 0x3F80u + b1[5] * 0x3F800000u; v1.w = b1[6] * 0x3F80u + b1[7] * 0x3F800000u;
+      uint8_t* tile = sa + j * FS_A_BYTES;                   // K-major SWIZZLE_128B: 16-byte chunk c of row r sits at chunk c ^ (r & 7)
+      const int ra = 2 * rp, rb = 2 * rp + 1;
+      *reinterpret_cast<uint4*>(tile + ra * 128 + ((c8 ^ (ra & 7)) << 4)) = v0;
+      *reinterpret_cast<uint4*>(tile + rb * 128 + ((c8 ^ (rb & 7)) << 4)) = v1;
+      if (fa.a_dump != nullptr) {                            // tests: the sampled A_tilde as the multi-kernel path stores it
+        if (gi0 < n) *reinterpret_cast<uint4*>(fa.a_dump + (int64_t)gi0 * fa.lda + gj0) = v0;
+        if (gi1 < n) *reinterpret_cast<uint4*>(fa.a_dump + (int64_t)gi1 * fa.lda + gj0) = v1;
+      }
+#pragma unroll
+      for (int sh = 1; sh <= 4; sh <<= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, sh); s1 += __shfl_xor_sync(0xffffffffu, s1, sh); }
+      if (c8 == 0) {                                         // row sums of this tile (integers in fp32: exact)
+        if (gi0 < n) fa.deg_part[(int64_t)kb * ea.ldr + gi0] = (float)s0;
+        if (gi1 < n) fa.deg_part[(int64_t)kb * ea.ldr + gi1] = (float)s1;
+      }
+    }
+  }
+  fence_proxy_async_smem();                                  // generic-proxy smem writes -> visible to tcgen05.mma
+  stamp(1);
+  grid_barrier(fa.gridbar, gbase, gk, gridDim.x);
+  stamp(2);
+
+  // ================= P1: degrees, r, feature rows, first operand =================
+  // Two rows per warp: h <= 16, so a half-warp owns a row (lane16 = output column; 16 non-zeros per trip).
+  {
+    const int lane16 = lane & 15, half = lane >> 4;
+    const int r_lo = cta * fa.rows_per_cta, r_hi = min(n, r_lo + fa.rows_per_cta);
+    for (int ib = r_lo + 2 * warp; ib < r_hi; ib += 2 * (K2_THREADS / 32)) {
+      const int i = ib + half;
+      const bool live = i < r_hi;
+      const int il = live ? i : r_hi - 1;
+      float d = 0.f;
+      for (int kb = lane16; kb < fa.kb_real; kb += 16) d += fa.deg_part[(int64_t)kb * ea.ldr + il];
+#pragma unroll
+      for (int sh = 8; sh > 0; sh >>= 1) d += __shfl_xor_sync(0xffffffffu, d, sh);      // integer-valued: exact in any order
+      const float ri = 1.0f / sqrtf(d);
+      if (live && lane16 == 0) { fa.deg[i] = d; fa.rs[i] = ri; }
+      const int beg = fa.crow[il], end = live ? fa.crow[il + 1] : beg;
+      const int trips = (max(__shfl_sync(0xffffffffu, end - beg, 0), __shfl_sync(0xffffffffu, end - beg, 16)) + 15) >> 4;
+      float acc = 0.f;
+      for (int tr = 0; tr < trips; ++tr) {                     // both halves run the same number of trips (shuffles are warp-wide)
+        const int base = beg + 16 * tr;
+        const int idx = base + lane16;
+        int col = 0; float v = 0.f;
+        if (idx < end) {
+          col = fa.xcol[idx]; v = fa.xval[idx];
+          if (fa.dx.p > 0.f) v = drop_keep(fa.dx, il, il, col, fa.f) ? v * fa.dx.scale : 0.f;
+        }
+        const int cnt = max(0, min(16, end - base));
+#pragma unroll
+        for (int j = 0; j < 16; j += 8) {                      // 8 non-zeros per trip: their w0t rows are loaded together
+          float vj[8], wv[8];
+          int cj[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { vj[u] = __shfl_sync(0xffffffffu, v, j + u, 16); cj[u] = __shfl_sync(0xffffffffu, col, j + u, 16); }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) wv[u] = (lane16 < ea.h && j + u < cnt) ? fa.w0t[(int64_t)cj[u] * ea.h + lane16] : 0.f;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) if (j + u < cnt) acc = fmaf(vj[u], wv[u], acc);
+        }
+      }
+      if (live && lane16 < ea.h) {
+        const float pv = acc + fa.b0[lane16];
+        ea.p1[(int64_t)lane16 * ea.ldr + i] = pv;
+        __nv_bfloat16 bh, bl;
+        split_bf16(ri * pv, bh, bl);
+        ea.bt_hi[(int64_t)lane16 * ea.ldb + i] = bh;
+        ea.bt_lo[(int64_t)lane16 * ea.ldb + i] = bl;
+      }
+    }
+  }
+  stamp(3);
+  grid_barrier(fa.gridbar, gbase, gk, gridDim.x);
+  stamp(4);
+
+  // ================= P2: the four propagations from the resident tiles =================
+  int acc_m = 0; uint32_t acc_phase_m = 0;                   // accumulator ring state of the MMA issuer
+  int acc_e = 0; uint32_t acc_phase_e = 0;                   // ... and of the epilogue warps
+  for (int ph = 0; ph < 4; ++ph) {
+    if (warp == 0) {
+      if (lane == 0) {                                       // the operand k-blocks of this CTA's range (all fit: no ring)
+        asm volatile("fence.proxy.async;" ::: "memory");     // the operand was written with generic stores before the grid barrier
+        mbar_expect_tx(bfull, (uint32_t)(nt * FS_B_BYTES * (fa.use_lo ? 2 : 1)));
+        for (int j = 0; j < nt; ++j) {
+          tma_load_2d(sb + j * 2 * FS_B_BYTES, &tm_bhi, bfull, (my_kb0 + j) * K2_BLOCK_K, 0);
+          if (fa.use_lo) tma_load_2d(sb + j * 2 * FS_B_BYTES + FS_B_BYTES, &tm_blo, bfull, (my_kb0 + j) * K2_BLOCK_K, 0);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        // one MMA of width 32 against the stacked operand [hi(16 rows); lo(16 rows)] (contiguous in smem): the hi and lo
+        // products land in columns 0-15 / 16-31 of the accumulator and are added by the drain
+        const uint32_t idesc = fa.use_lo ? umma_idesc_bf16(K2_BLOCK_M, 2 * FS_HP) : umma_idesc_bf16(K2_BLOCK_M, FS_HP);
+        mbar_wait(bfull, (uint32_t)(ph & 1));
+        mbar_wait(&tempty_bar[acc_m], acc_phase_m ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc_m * 2 * FS_HP);
+        for (int j = 0; j < nt; ++j) {
+          const uint64_t adesc = umma_desc_k_sw128(smem_u32(sa + j * FS_A_BYTES));
+          const uint64_t bdesc = umma_desc_k_sw128(smem_u32(sb + j * 2 * FS_B_BYTES));
+#pragma unroll
+          for (int k = 0; k < K2_BLOCK_K / 16; ++k) tc_mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (j | k) != 0);
+        }
+        tc_commit(&tfull_bar[acc_m]);
+        if (++acc_m == 2) { acc_m = 0; acc_phase_m ^= 1; }
+      }
+    } else {
+      if (ph == 0) k2_epilogue_loop<FS_HP, K2_EPI_LAYER1, true>(s, ea, fa.partial, fa.counters, cta, lo, hi, tmem_base, tfull_bar, tempty_bar, acc_e, acc_phase_e, sh_epi, fa.use_lo != 0);
+      else if (ph == 1) k2_epilogue_loop<FS_HP, K2_EPI_LAYER2, true>(s, ea, fa.partial, fa.counters, cta, lo, hi, tmem_base, tfull_bar, tempty_bar, acc_e, acc_phase_e, sh_epi, fa.use_lo != 0);
+      else if (ph == 2) k2_epilogue_loop<FS_HP, K2_EPI_BWD2, true>(s, ea, fa.partial, fa.counters, cta, lo, hi, tmem_base, tfull_bar, tempty_bar, acc_e, acc_phase_e, sh_epi, fa.use_lo != 0);
+      else k2_epilogue_loop<FS_HP, K2_EPI_BWD1, true>(s, ea, fa.partial, fa.counters, cta, lo, hi, tmem_base, tfull_bar, tempty_bar, acc_e, acc_phase_e, sh_epi, fa.use_lo != 0);
+    }
+    if (tid == 64) {                                           // first epilogue thread: its loop is done
+      unsigned long long t;
+      if (fa.timeline != nullptr) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); fa.timeline[(size_t)cta * 16 + 5 + 2 * ph] = t; }
+    }
+    if (ph < 3) grid_barrier(fa.gridbar, gbase, gk, gridDim.x);
+    stamp(6 + 2 * ph);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
+}
+
+bool fused_small_schedule(int n, int hp1, int hp2, K2Sched& s, int& kb_real) {
+  if (hp1 != FS_HP || hp2 != FS_HP || n < 2) return false;
+  const int panels = (int)ceil_div(n, K2_BLOCK_M);
+  kb_real = (int)ceil_div(n, K2_BLOCK_K);
+  if (panels > kNumSMsB200) return false;
+  int parts = kNumSMsB200 / panels;
+  if (parts > kb_real) parts = kb_real;
+  const int per = (int)ceil_div(kb_real, parts);
+  if (per > FS_MAX_TILES) return false;
+  parts = (int)ceil_div(kb_real, per);                       // drop parts that would own no real k-block
+  s.hp = FS_HP; s.panels = panels; s.kblocks = parts * per; s.total = panels * s.kblocks;
+  s.per_cta = per; s.grid = panels * parts; s.max_seg = 1;
+  return true;
+}
+
+int32_t fused_small_launch(const FusedSmallArgs& fa, cudaStream_t stream) {
+  static int coop = -1;
+  if (coop < 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess) v = 0;
+    if (v && num_sms() < fa.s.grid) v = 0;
+    if (v) {
+      if (cudaFuncSetAttribute(fused_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM) != cudaSuccess) v = 0;
+    }
+    (void)cudaGetLastError();
+    coop = v;
+  }
+  if (!coop) return LDS_ERR_UNSUPPORTED;                     // the caller falls back to the multi-kernel path
+  CUtensorMap tbh, tbl;
+  int32_t rc;
+  if ((rc = make_tmap_2d(&tbh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, fa.ea.bt_hi, fa.n, FS_HP, fa.ea.ldb, K2_BLOCK_K, FS_HP)) != LDS_OK) return rc;
+  if ((rc = make_tmap_2d(&tbl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, fa.ea.bt_lo, fa.n, FS_HP, fa.ea.ldb, K2_BLOCK_K, FS_HP)) != LDS_OK) return rc;
+  void* params[] = {(void*)&tbh, (void*)&tbl, (void*)&fa};
+  LDS_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)fused_small_kernel, dim3((unsigned)fa.s.grid), dim3(K2_THREADS), params, FS_SMEM, stream));
+  return LDS_OK;
+}
+
+}  // namespace lds

@@ -1,0 +1,37 @@
+// lds_fused_small.cuh — interface of the small-graph fused kernel (lds_fused_small.cu), used by lds_outer_step.cu.
+#pragma once
+#include "lds_epilogue.cuh"
+
+namespace lds {
+
+constexpr int FS_MAX_TILES = 11;     // resident 128 x 64 A tiles per CTA (176 KB of shared memory)
+constexpr int FS_HP = 16;            // padded operand width of all four propagations (h <= 16 and C <= 16)
+
+struct FusedSmallArgs {
+  // sampling (K1)
+  const float* theta; int64_t ldt; int n;
+  PhiloxRounds rounds;                         // edge stream of this (seed, step)
+  const float* u_explicit; int64_t ldu;        // parity mode, else NULL
+  __nv_bfloat16* a_dump; int64_t lda;          // optional copy of A_tilde in global memory (tests), else NULL
+  float* deg_part;                             // [kblocks][ldr] per-tile row sums
+  float* deg; float* rs;
+  // feature GEMM
+  const int32_t* crow; const int32_t* xcol; const float* xval; int f;
+  const float* w0; int64_t ldw; float* w0t; const float* b0; DropCfg dx;
+  int rows_per_cta;
+  // propagations
+  K2Sched s;                                   // panel-aligned: s.kblocks is the PADDED k-range (parts * per_cta), max_seg = 1
+  int kb_real;                                 // ceil(n / 64): k-blocks that exist
+  float* partial; int* counters; int use_lo;
+  unsigned* gridbar;                           // {arrival count (zero between launches), generation}
+  unsigned long long* timeline;                // optional debug: [grid][16] %globaltimer stamps per CTA, else NULL
+  EpiArgs ea;
+};
+
+// Panel-aligned schedule of the fused kernel: every CTA owns `per_cta` consecutive k-blocks of ONE 128-row panel.
+// Returns false when the graph does not fit (more than FS_MAX_TILES tiles per CTA on 148 SMs) or h, c > 16.
+bool fused_small_schedule(int n, int hp1, int hp2, K2Sched& s, int& kb_real);
+// LDS_ERR_UNSUPPORTED when the device cannot run the cooperative launch: the caller uses the multi-kernel path.
+int32_t fused_small_launch(const FusedSmallArgs& fa, cudaStream_t stream);
+
+}  // namespace lds

@@ -18,10 +18,12 @@ struct K2EpiShared {           // static shared memory of the epilogue loop
 // accumulator segment to an fp32 partial tile in global memory (L2) and count the CTA in on the panel; the LAST
 // CTA to arrive sums the panel's tiles in a fixed order (deterministic) and runs the row epilogue with all 16
 // warps, four threads per row (lds_epilogue.cuh). A panel covered by one CTA takes the same path. =====
-template <int HP, int EPI>
+// STACKED: the accumulator holds the hi-term and the lo-term products side by side (one MMA of width 2 HP against the
+// stacked operand [hi; lo]); the drain adds the two halves (`add_lo`) while it moves them out.
+template <int HP, int EPI, bool STACKED = false>
 __device__ __forceinline__ void k2_epilogue_loop(const K2Sched& s, const EpiArgs& ea, float* __restrict__ partial, int* __restrict__ counters,
                                                  int cta, int lo, int hi, uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
-                                                 int& acc, uint32_t& acc_phase, K2EpiShared& sh) {
+                                                 int& acc, uint32_t& acc_phase, K2EpiShared& sh, bool add_lo = false) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   {
     constexpr int Q = HP / 4;
@@ -55,12 +57,22 @@ __device__ __forceinline__ void k2_epilogue_loop(const K2Sched& s, const EpiArgs
         stamp(1);                                            // accumulator of this segment complete (all MMAs retired)
         const int row = quarter * 32 + lane;
         float* dst = partial + ((int64_t)(cta * s.max_seg + seg) * K2_BLOCK_M + row) * HP;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * HP);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * (STACKED ? 2 * HP : HP));
 #pragma unroll
         for (int c0 = 0; c0 < HP; c0 += 16) {
           uint32_t t16[16];
           tc_ld16(taddr + c0, t16);
-          tc_wait_ld();
+          if (STACKED) {
+            uint32_t u16[16];
+            tc_ld16(taddr + HP + c0, u16);
+            tc_wait_ld();
+            if (add_lo) {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) t16[q] = __float_as_uint(__uint_as_float(t16[q]) + __uint_as_float(u16[q]));
+            }
+          } else {
+            tc_wait_ld();
+          }
 #pragma unroll
           for (int q = 0; q < 16; q += 4)
             *reinterpret_cast<uint4*>(dst + c0 + q) = make_uint4(t16[q], t16[q + 1], t16[q + 2], t16[q + 3]);
@@ -70,10 +82,10 @@ __device__ __forceinline__ void k2_epilogue_loop(const K2Sched& s, const EpiArgs
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);        // accumulator drained: the next segment's MMAs may start
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         stamp(2);                                            // partial tile written
-        __threadfence();                                     // publish the partial tile before counting this CTA in
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 128);                              // the four drain warps' stores happen-before the release below
         if (etid == 0) {
-          const int old = atomicAdd(&counters[p], 1);
+          int old;                                           // release: publishes the CTA's partial tile; acquire: the last
+          asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(old) : "l"(counters + p) : "memory");   // arriver sees all of them
           const int last = (old == c_last - c_first) ? 1 : 0;
           if (last) counters[p] = 0;                         // everyone has arrived: re-arm for the next launch
           sh.last[seg & 1] = last;
@@ -81,8 +93,7 @@ __device__ __forceinline__ void k2_epilogue_loop(const K2Sched& s, const EpiArgs
       }
       named_bar_sync(2, 512);                                // the drain warps' verdict reaches all 16 warps
       stamp(3);                                              // fence + counter round trip done
-      if (sh.last[seg & 1] != 0) {                           // uniform over the 512 epilogue threads
-        __threadfence();
+      if (sh.last[seg & 1] != 0) {                           // uniform over the 512 epilogue threads (partials are read with ld.cg: L2)
         const int row = etid >> 2, g = etid & 3;             // four threads per row, a quarter of the columns each
         float v[Q];
 #pragma unroll

@@ -17,6 +17,7 @@
 // The outer step needs no weight gradients (the reference computes and discards them), so X is read once.
 #include <string.h>
 #include "lds_epilogue.cuh"
+#include "lds_fused_small.cuh"
 
 namespace lds {
 
@@ -25,12 +26,13 @@ constexpr int EPI_THREADS = 1024;   // 32 warps, one row each: the epilogues are
 constexpr int FEAT_THREADS = 256;   // dense feature GEMM: 8 warps x 4 rows
 constexpr int EPI_MAXW = 128;       // widest operand
 
-enum { B_A = 0, B_DEG, B_RS, B_P1, B_Z1, B_P2, B_Z2, B_DZ2, B_DP2, B_DZ1, B_DP1, B_FA, B_FB, B_C, B_BTHI, B_BTLO, B_PARTIAL, B_LOSSP, B_CORRP, B_F, B_W0S, B_CNT, B_OPND, B_END };
+enum { B_A = 0, B_DEG, B_RS, B_P1, B_Z1, B_P2, B_Z2, B_DZ2, B_DP2, B_DZ1, B_DP1, B_FA, B_FB, B_C, B_BTHI, B_BTLO, B_PARTIAL, B_LOSSP, B_CORRP, B_F, B_W0S, B_CNT, B_OPND, B_DEGP, B_GBAR, B_END };
 struct OuterLayout {
   int n, rows, f, h, c, hp1, hp2, hpmax, nblk, panels;
   int64_t lda, ldb, ldf, ldr;
   int kf;
-  K2Sched s1, s2;
+  K2Sched s1, s2, sf;       // sf: panel-aligned schedule of the fused small-graph kernel
+  bool fused; int kb_real;
   int64_t off[B_END];
   int64_t total;
 };
@@ -57,9 +59,13 @@ static bool make_layout(int n, int rows, int f, int h, int c, OuterLayout& L, bo
   // partial tiles are sized for the stream-K schedule whichever schedule runs (workspace size must not depend on flags)
   const int64_t p1 = k2_partial_bytes(k2_make_schedule(n, rows, L.hp1, true)), p2 = k2_partial_bytes(k2_make_schedule(n, rows, L.hp2, true));
   bytes[B_PARTIAL] = p1 > p2 ? p1 : p2;
+  L.fused = (rows == n) && fused_small_schedule(n, L.hp1, L.hp2, L.sf, L.kb_real);
+  if (L.fused && k2_partial_bytes(L.sf) > bytes[B_PARTIAL]) bytes[B_PARTIAL] = k2_partial_bytes(L.sf);
   bytes[B_LOSSP] = bytes[B_CORRP] = (int64_t)ceil_div(rows, K2_BLOCK_M) * 4;
   bytes[B_F] = (int64_t)n * L.kf * 2;                       // packed bf16 factor rows of the tensor-core update (all n rows: K3 needs F_j of every column)
   bytes[B_CNT] = (int64_t)ceil_div(rows, K2_BLOCK_M) * 4;     // per-panel arrival counters of the stream-K reduction
+  bytes[B_DEGP] = L.fused ? (int64_t)L.kb_real * L.ldr * 4 : 0;   // fused small-graph path: per-tile row sums
+  bytes[B_GBAR] = 16;                                       // grid barrier of the fused small-graph kernel {count, generation}
   bytes[B_W0S] = (int64_t)h * round_up(f, 4) * 4;          // staged layer_in weight: transposed [f][h] (CSR path) or padded [h][ldx]
   int64_t o = 0;
   for (int b = 0; b < B_END; ++b) { L.off[b] = o; o += round_up(bytes[b], 1024); }
@@ -360,7 +366,43 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
 
   int32_t rc;
   profile_mark(stream, -1);
-  if (phases & LDS_PHASE_SAMPLE) {
+
+  // ---- small graphs: K1 + feature GEMM + the four propagations in one cooperative kernel (lds_fused_small.cu) ----
+  bool fused_done = false;
+  const bool tc_update = A.opt_kind == LDS_OPT_SGD && !(A.k3_flags & LDS_K3_SIMT);
+  if (!sharded && sparse_x && !(A.k2_flags & (LDS_K2_NO_FUSE | LDS_K2_FORCE_STREAMK | LDS_K2_SIMT)) &&
+      L.fused) {
+    FusedSmallArgs F;
+    memset(&F, 0, sizeof(F));
+    F.theta = A.theta_full; F.ldt = A.ld_theta; F.n = A.n;
+    F.rounds = philox_rounds(philox_key(A.seed, A.step, LDS_STREAM_EDGES, 0));
+    F.u_explicit = A.u_explicit; F.ldu = A.ld_u;
+    F.a_dump = (A.k2_flags & LDS_K2_DUMP_ADJ) ? reinterpret_cast<__nv_bfloat16*>(buf(B_A)) : nullptr; F.lda = L.lda;
+    F.deg_part = fbuf(B_DEGP); F.deg = fbuf(B_DEG); F.rs = fbuf(B_RS);
+    F.crow = A.x_crow; F.xcol = A.x_col; F.xval = A.x_val; F.f = A.f;
+    F.w0 = A.w0; F.ldw = A.ld_w0; F.w0t = fbuf(B_W0S); F.b0 = A.b0; F.dx = dx;
+    F.rows_per_cta = (int)ceil_div(A.n, L.sf.grid);
+    F.s = L.sf; F.kb_real = L.kb_real; F.partial = fbuf(B_PARTIAL); F.counters = counters; F.use_lo = use_lo ? 1 : 0;
+    F.gridbar = reinterpret_cast<unsigned*>(buf(B_GBAR));
+    F.timeline = A.k2_timeline;
+    EpiArgs& E = F.ea;
+    E.n = rows; E.h = A.h; E.c = A.c; E.hp1 = L.hp1; E.hp2 = L.hp2; E.row0 = 0;
+    E.deg = fbuf(B_DEG); E.rs = fbuf(B_RS);
+    E.p1 = fbuf(B_P1); E.z1 = fbuf(B_Z1); E.p2 = fbuf(B_P2); E.z2 = fbuf(B_Z2); E.dz2 = fbuf(B_DZ2); E.dp2 = fbuf(B_DP2);
+    E.dz1 = fbuf(B_DZ1); E.dp1 = fbuf(B_DP1); E.ldr = L.ldr; E.cvec = fbuf(B_C);
+    E.ldf = L.ldf; E.kf = L.kf;
+    if (tc_update) E.fpack = reinterpret_cast<__nv_bfloat16*>(buf(B_F));
+    else { E.fa = fbuf(B_FA); E.fb = fbuf(B_FB); }
+    E.w1 = A.w1; E.b1 = A.b1; E.y = A.y; E.mask = A.mask; E.inv_m = 1.0f / (float)A.mask_count;
+    E.drop_h = dh; E.bt_hi = bt_hi; E.bt_lo = bt_lo; E.ldb = L.ldb;
+    E.loss_part = fbuf(B_LOSSP); E.corr_part = fbuf(B_CORRP); E.nblk = L.panels;
+    E.out_scalars = A.out_scalars; E.out_logp = A.out_logp;
+    rc = fused_small_launch(F, stream);
+    if (rc == LDS_OK) { fused_done = true; profile_mark(stream, 10); }
+    else if (rc != LDS_ERR_UNSUPPORTED) return rc;
+  }
+
+  if (!fused_done && (phases & LDS_PHASE_SAMPLE)) {
     {   // stage the layer_in weight (tiny; independent of K1) and re-arm the stream-K counters
       const int64_t ldp = round_up(A.f, 4);
       dim3 sgrid((unsigned)ceil_div(ldp, 32), (unsigned)ceil_div(A.h, 32));
@@ -393,7 +435,6 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   E.p1 = fbuf(B_P1); E.z1 = fbuf(B_Z1); E.p2 = fbuf(B_P2); E.z2 = fbuf(B_Z2); E.dz2 = fbuf(B_DZ2); E.dp2 = fbuf(B_DP2);
   E.dz1 = fbuf(B_DZ1); E.dp1 = fbuf(B_DP1); E.ldr = L.ldr; E.cvec = fbuf(B_C);
   // factor rows: packed bf16 for the tensor-core update (own rows inside the n-row F buffer), row-major fp32 for the CUDA-core one
-  const bool tc_update = A.opt_kind == LDS_OPT_SGD && !(A.k3_flags & LDS_K3_SIMT);
   E.ldf = L.ldf; E.kf = L.kf;
   if (tc_update) E.fpack = reinterpret_cast<__nv_bfloat16*>(buf(B_F)) + (int64_t)row0 * L.kf;
   else { E.fa = fbuf(B_FA); E.fb = fbuf(B_FB); }
@@ -406,7 +447,7 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
     set_error("lds_outer_step: LDS_K2_SIMT is only available through lds_k2_propagate"); return LDS_ERR_ARG;
   }
   auto propagate = [&](uint32_t phase, const K2Sched& s, int width, int epi, int mark) -> int32_t {
-    if (!(phases & phase)) return LDS_OK;
+    if (fused_done || !(phases & phase)) return LDS_OK;
     if (sharded) {   // the gathered operand [n][width] fp32 -> K-major bf16 hi/lo terms
       const int32_t r0 = k2_launch_prep(A.opnd_full, ld_opnd, A.n, width, s.hp, nullptr, bt_hi, bt_lo, L.ldb, counters, 0, stream);
       if (r0 != LDS_OK) return r0;

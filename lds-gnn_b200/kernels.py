@@ -216,7 +216,7 @@ class OuterStep:
         nbytes = int(self.lib.lds_outer_step_shard_workspace_bytes(self.n, self.rows, self.f, self.h, self.c))
         if nbytes < 0:
             raise ValueError(f"unsupported shape n={n} f={self.f} h={hidden} c={classes}")
-        self._ws_raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        self._ws_raw = torch.zeros(nbytes + 1024, dtype=torch.uint8, device=dev)     # zero-filled once: the library keeps its counters re-armed
         off = (-self._ws_raw.data_ptr()) % 1024
         self.ws = self._ws_raw[off:off + nbytes]
         self.ws_bytes = nbytes
@@ -310,9 +310,11 @@ class OuterStep:
     def run(self, theta_full, lr, seed, step, dropout_p=0.0, update=True, u=None, keep_x=None, keep_h=None,
             opt_kind=_lib.OPT_SGD, adam_m=None, adam_v=None, betas=(0.9, 0.999), eps=1e-8, adam_t=1,
             out_logp=None, k2_flags=0, k3_flags=0, phases=None, opnd_full=None, fa_full=None, fb_full=None, c_full=None,
-            f_full=None, k2_timeline=None, scalars_out=None):
+            f_full=None, k2_timeline=None, scalars_out=None, want_adj=True):
         """Enqueue one fused outer step on the current stream. Results: (loss, acc) in `scalars_out[0:2]` (any fp32
-        buffer the device can write, e.g. pinned host memory) or, by default, in self.scalars."""
+        buffer the device can write, e.g. pinned host memory) or, by default, in self.scalars.
+        `want_adj`: keep the sampled A_tilde readable through buffer("adj") — small graphs run a fused kernel whose A_tilde
+        lives in shared memory only; hot callers (trainer, bench) pass False."""
         a = self.args
         a.theta_full, a.ld_theta = theta_full.data_ptr(), theta_full.stride(0)
         a.w0, a.b0, a.w1, a.b1 = self.w0.data_ptr(), self.b0.data_ptr(), self.w1.data_ptr(), self.b1.data_ptr()
@@ -320,6 +322,8 @@ class OuterStep:
         a.seed, a.step = int(seed), int(step)
         a.lr, a.opt_kind = float(lr), int(opt_kind)
         a.update = int(bool(update))
+        if want_adj:
+            k2_flags = int(k2_flags) | _lib.K2_DUMP_ADJ
         plain = (u is None and keep_x is None and keep_h is None and adam_m is None and out_logp is None and not k2_flags
                  and not k3_flags and opnd_full is None and fa_full is None and c_full is None and f_full is None
                  and k2_timeline is None and scalars_out is None)

@@ -196,7 +196,7 @@ class OuterProblemTrainer:
         if self._host_scalars is None:
             self._host_scalars = torch.zeros(4, dtype=torch.float32).pin_memory()
         eng.run(theta, lr=group["lr"], seed=seed, step=step, dropout_p=float(gcn.dropout),
-                update=True, opt_kind=kind, scalars_out=self._host_scalars, **extra)
+                update=True, opt_kind=kind, scalars_out=self._host_scalars, want_adj=False, **extra)
         model.mark_full_updated()
         if self.lr_decayer is not None:
             self.optimizer._opt_called = True             # the update ran in the kernel; keeps StepLR's order check quiet

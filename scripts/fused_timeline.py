@@ -1,0 +1,27 @@
+"""Device-side timeline of the fused small-graph kernel (debug aid): %globaltimer stamps per CTA and phase."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bench
+from lds_gnn_b200 import kernels as K
+data, weights, opt_mask, shape = bench.make_workload(sys.argv[1] if len(sys.argv) > 1 else "citeseer", 0)
+dev = torch.device("cuda")
+data = data.to(dev); opt_mask = opt_mask.to(dev)
+n, f, h, c = shape["n"], shape["f"], shape["h"], shape["c"]
+eng = K.OuterStep(n, data.x, data.y, opt_mask, hidden=h, classes=c)
+eng.set_weights(*(weights[k].to(dev) for k in ("w0", "b0", "w1", "b1")))
+iu = torch.triu_indices(n, n)
+theta = K.theta_triu_to_full(data.dense_adj[iu[0], iu[1]].contiguous().to(dev))
+for i in range(5): eng.run(theta, lr=0.1, seed=1, step=i, dropout_p=0.5, want_adj=False)
+tl = torch.zeros((4, 512, 8), dtype=torch.int64, device=dev)
+eng.run(theta, lr=0.1, seed=1, step=99, dropout_p=0.5, k2_timeline=tl, want_adj=False)
+torch.cuda.synchronize()
+t = tl.cpu().numpy().astype(np.float64).reshape(-1)[:148 * 16].reshape(148, 16)
+act = t[:, 0] > 0
+t = t[act]
+t0 = t[:, 0].min()
+names = ["start", "sampled", "barrier1", "feat_done", "barrier2", "epi0_done", "after0", "epi1_done", "after1", "epi2_done", "after2", "epi3_done", "end"]
+print(f"{act.sum()} CTAs")
+for j, nm in enumerate(names):
+    col = t[:, j]; col = col[col > 0]
+    if len(col): print(f"   {nm:12s} n={len(col):4d}  min {(col.min()-t0)/1e3:7.2f} us  median {(np.median(col)-t0)/1e3:7.2f}  max {(col.max()-t0)/1e3:7.2f}")
