@@ -134,10 +134,19 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ workload
+KNN_WORKLOADS = {"cora_knn16": ("cora", 10, 16)}      # BASELINE.json config 3: kNN theta_0 (k = 10, cosine), 16 samples per outer step
+
+
 def make_workload(name, seed=0):
     from lds_gnn_b200.data import SHAPES, make_dataset
+    knn = KNN_WORKLOADS.get(name)
+    if knn is not None:
+        name = knn[0]
     n, f, c, h, _, _ = SHAPES[name]
     data = make_dataset(name, seed=seed)
+    if knn is not None:                                  # theta_0 = symmetrised kNN graph of the features (data/transforms.py:15-37)
+        from lds_gnn_b200.data.knn import knn_init_adjacency
+        data.dense_adj = knn_init_adjacency(data.x, k=knn[1], metric="cosine", loop=False)
     rng = np.random.default_rng(seed + 1)
     lim0, lim1 = np.sqrt(6.0 / (f + h)), np.sqrt(6.0 / (h + c))          # xavier-uniform, zero bias (layers.py:38-40)
     weights = dict(w0=torch.as_tensor(rng.uniform(-lim0, lim0, (h, f)).astype(np.float32)), b0=torch.zeros(h),
@@ -191,8 +200,13 @@ def run_ours(args, rank, world, device):
     lr = HYPER["lr"]
     seed = 1234 + rank
 
+    samples = KNN_WORKLOADS[args.workload][2] if args.workload in KNN_WORKLOADS else 1
+
     def one(step_idx, lr_now):
-        eng.run(theta, lr=lr_now, seed=seed, step=step_idx, dropout_p=HYPER["dropout"], update=True, want_adj=False)
+        if samples > 1:
+            eng.run_multi(theta, samples, lr=lr_now, seed=seed, step=step_idx, dropout_p=HYPER["dropout"], update=True, want_adj=False)
+        else:
+            eng.run(theta, lr=lr_now, seed=seed, step=step_idx, dropout_p=HYPER["dropout"], update=True, want_adj=False)
 
     for w in range(args.warmup):
         one(w, lr); lr *= HYPER["lr_decay"]
@@ -252,6 +266,7 @@ def run_ours(args, rank, world, device):
     outer = OuterProblemTrainer(optimizer=opt, data=data, opt_mask=opt_mask, model=model, smoothness_factor=0.0,
                                 disconnection_factor=0.0, sparsity_factor=0.0, regularize=False,
                                 lr_decay=HYPER["lr_decay"], pretrain=False)
+    outer.n_samples = samples
     names = {"w0": "layer_in.fc.weight", "b0": "layer_in.fc.bias", "w1": "layer_out.fc.weight", "b1": "layer_out.fc.bias"}
     # The step's inputs are the current GCN (fast) weights: one flat pinned host buffer, one flat device buffer whose
     # slices ARE the fast-weight tensors handed to the trainer, one host->device copy per step.
@@ -293,7 +308,7 @@ def run_ours(args, rank, world, device):
     kernel_summary = {}
     for kid, vals in per_kernel.items():
         launches = len(vals) / reps
-        kernel_summary[KERNEL_NAMES.get(kid, str(kid))] = {"launches_per_step": launches, "mean_us": 1e3 * sum(vals) / len(vals),
+        kernel_summary[KERNEL_NAMES.get(kid, "gap_between_calls" if kid < 0 else str(kid))] = {"launches_per_step": launches, "mean_us": 1e3 * sum(vals) / len(vals),
                                                             "step_share_us": 1e3 * sum(vals) / reps}
     dominant_id = max(per_kernel, key=lambda k: sum(per_kernel[k])) if per_kernel else None
     roofline = None
@@ -317,12 +332,15 @@ def run_ours(args, rank, world, device):
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16 adjacency x (bf16 hi+lo) operands, fp32 accumulate; fp32 theta",
         "data": "synthetic",
         "config": {"workload": f"LDS-GCN direct outer step, {args.workload} shape (N={n}, F={f}, C={c}, hidden={h}), SGD lr 0.1 decay 0.99, "
-                               f"dropout 0.5, 1 sample/step", "parallelism": "single GPU" if world == 1 else f"{world} independent replicas",
-                   "l2": "flushed between timed steps (256 MiB write)", "theta_init": "synthetic SBM adjacency"},
+                               f"dropout 0.5, {samples} sample(s)/step" + (", theta_0 = kNN graph (k=10, cosine)" if samples > 1 else ""),
+                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas",
+                   "l2": "flushed between timed steps (256 MiB write)",
+                   "theta_init": "kNN graph of the synthetic features" if samples > 1 else "synthetic SBM adjacency"},
         "clocks": clock_info,
         "e2e": {"value": round(total_steps / (e2e_ms / 1e3), 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
                 "api": "OuterProblemTrainer.train_step(InnerProblemTrainer.model_forward)", "l2": "not flushed"},
-        "gpu_launches": (2 if 10 in per_kernel else LAUNCHES_PER_STEP) * args.steps,      # fused small-graph kernel + K3K4, else 8
+        # fused small-graph kernel + K3K4 (S samples: S fused launches + one K3K4), else 8 launches per step
+        "gpu_launches": ((samples + 1) if 10 in per_kernel else LAUNCHES_PER_STEP * samples) * args.steps,
         "roofline": roofline,
         "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "frac_of_hbm_peak": round(step_frac, 4)},
         "warm_l2": {"value": round(total_steps / (warm_ms / 1e3), 2), "unit": UNIT, "ms_per_step": round(warm_ms / args.steps, 5)},
@@ -601,9 +619,13 @@ def main():
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline and "cpu_baseline" not in line:
             rate, ms, threads, _, _ = time_cpu_port(args.workload, args.cpu_steps, 1)
+            note = ""
+            if args.workload in KNN_WORKLOADS:           # the port runs single-sample steps; an S-sample step is S of them
+                rate /= KNN_WORKLOADS[args.workload][2]
+                note = f"; single-sample steps timed, rate divided by {KNN_WORKLOADS[args.workload][2]} samples per outer step"
             line["cpu_baseline"] = {"value": round(rate, 4), "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{args.cpu_steps} full outer steps of the same workload after 1 warm-up "
-                                              f"(oracle/reference_port.py: the reference's torch op sequence on CPU)"}
+                                              f"(oracle/reference_port.py: the reference's torch op sequence on CPU){note}"}
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist

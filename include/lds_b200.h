@@ -186,6 +186,14 @@ typedef struct lds_outer_step_args {
   const float* fa_full; const float* fb_full; const float* c_full;
   const void*  f_full;        /* gathered packed factor rows (bf16), see PHASE_UPDATE                    */
   unsigned long long* k2_timeline;   /* optional debug buffer [4][512][8] of %globaltimer stamps, else NULL            */
+  /* ---- multi-sample estimator (BASELINE config 3: S Bernoulli samples per outer step). num_samples <= 1: one sample.
+   * Otherwise the caller makes S calls with sample_index = 0 .. S-1 and the same (seed, step): each call draws its own graph
+   * and dropout masks (Philox sample = sample_index), runs forward + backward and leaves its packed factor rows in column
+   * block sample_index of fpack_multi [n][S * lds_outer_step_packed_k(h, c)] bf16 (caller-allocated, 16-byte aligned);
+   * c and (loss, acc) are accumulated; the LAST call applies theta <- clamp(theta - lr * mean_s g_s) in ONE update pass
+   * (the S rank-2d gradients are concatenated along K of the update GEMM). Tensor-core SGD update, unsharded only. */
+  int32_t  num_samples, sample_index;
+  void*    fpack_multi;
 } lds_outer_step_args;
 
 #define LDS_PHASE_SAMPLE   1u

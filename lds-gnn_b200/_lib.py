@@ -78,6 +78,7 @@ class OuterStepArgs(Structure):
         ("row0", c_int32), ("rows", c_int32), ("phases", c_uint32), ("reserved2", c_uint32),
         ("opnd_full", c_void_p), ("fa_full", c_void_p), ("fb_full", c_void_p), ("c_full", c_void_p),
         ("f_full", c_void_p), ("k2_timeline", c_void_p),
+        ("num_samples", c_int32), ("sample_index", c_int32), ("fpack_multi", c_void_p),
     ]
 
 

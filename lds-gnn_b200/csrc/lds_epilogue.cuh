@@ -59,7 +59,10 @@ struct EpiArgs {
   float* p1; float* z1; float* p2; float* z2; float* dz2; float* dp2; float* dz1; float* dp1;   // transposed: [w][ldr]
   int64_t ldr;                 // row stride of the transposed state arrays (>= n)
   float* fa; float* fb; int64_t ldf;   // optional row-major fp32 factor rows [n][ldf] (CUDA-core / Adam update), else NULL
-  __nv_bfloat16* fpack; int kf;        // optional packed bf16 factor rows [n][kf] of the tensor-core update (lds_k3.cuh), else NULL
+  __nv_bfloat16* fpack; int kf;        // optional packed bf16 factor rows of the tensor-core update (lds_k3.cuh), else NULL:
+  int64_t ld_fpack;                    // row i at fpack + i * ld_fpack, kf columns (multi-sample: column block s of [n][S * kf])
+  int c_accumulate;                    // multi-sample: cvec += instead of =
+  float scal_scale; int scal_accumulate;   // (loss, acc) *= scal_scale, added to out_scalars instead of stored (multi-sample mean)
   float* cvec;
   const float* w1; const float* b1;
   const int64_t* y; const uint8_t* mask; float inv_m;
@@ -275,7 +278,7 @@ __device__ __forceinline__ void epi_bwd1(const EpiArgs& a, int i, int g, float (
   const int h16 = (a.h + 15) & ~15;
   float* fa = (a.fa && live) ? a.fa + (int64_t)i * a.ldf : nullptr;
   float* fb = (a.fb && live) ? a.fb + (int64_t)i * a.ldf : nullptr;
-  __nv_bfloat16* fp = (a.fpack && live) ? a.fpack + (int64_t)i * a.kf : nullptr;
+  __nv_bfloat16* fp = (a.fpack && live) ? a.fpack + (int64_t)i * a.ld_fpack : nullptr;
   float rho = 0.f, kappa = 0.f;
 #pragma unroll
   for (int u = 0; u < Q / NC; ++u) {                           // hidden part: this thread's columns, NC at a time
@@ -324,7 +327,8 @@ __device__ __forceinline__ void epi_bwd1(const EpiArgs& a, int i, int g, float (
   rho = quad_sum(rho); kappa = quad_sum(kappa);
   if (g == 0 && live) {
     if (fa) for (int k = a.h + a.c; k < (int)a.ldf; ++k) { fa[k] = 0.f; fb[k] = 0.f; }
-    a.cvec[i] = -(rho + kappa) / (2.f * di);                   // both D^-1/2 factors depend on the row sum
+    const float cv = -(rho + kappa) / (2.f * di);              // both D^-1/2 factors depend on the row sum
+    a.cvec[i] = a.c_accumulate ? a.cvec[i] + cv : cv;
   }
 }
 

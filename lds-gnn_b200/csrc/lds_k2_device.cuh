@@ -41,8 +41,9 @@ __device__ __forceinline__ void k2_epilogue_loop(const K2Sched& s, const EpiArgs
     if (EPI == K2_EPI_BWD2 && cta == 0 && etid == 0) {       // the layer-2 launch is complete: finalise loss / accuracy
       float l = 0.f, c = 0.f;
       for (int k = 0; k < ea.nblk; ++k) { l += ea.loss_part[k]; c += ea.corr_part[k]; }
-      ea.out_scalars[0] = l * ea.inv_m;
-      ea.out_scalars[1] = c * ea.inv_m;
+      const float ls = l * ea.inv_m * ea.scal_scale, cs = c * ea.inv_m * ea.scal_scale;
+      ea.out_scalars[0] = ea.scal_accumulate ? ea.out_scalars[0] + ls : ls;
+      ea.out_scalars[1] = ea.scal_accumulate ? ea.out_scalars[1] + cs : cs;
     }
     int seg = 0;
     for (int pos = lo; pos < hi; ++seg) {

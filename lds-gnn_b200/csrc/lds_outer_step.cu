@@ -361,8 +361,15 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   dx.keep_thresh = dh.keep_thresh = (float)(1.0 - (double)A.dropout_p);
   dx.scale = dh.scale = 1.0f / dx.keep_thresh;
   dx.explicit_keep = A.keep_x; dh.explicit_keep = A.keep_h;
-  dx.key = philox_key(A.seed, A.step, LDS_STREAM_DROP_X, 0);
-  dh.key = philox_key(A.seed, A.step, LDS_STREAM_DROP_H, 0);
+  const int S = A.num_samples > 1 ? A.num_samples : 1;
+  const uint32_t smp = S > 1 ? (uint32_t)A.sample_index : (uint32_t)(A.sample_index > 0 ? A.sample_index : 0);
+  if (S > 1) {
+    LDS_CHECK_ARG(A.sample_index >= 0 && A.sample_index < S, "lds_outer_step: sample_index %d outside [0, %d)", A.sample_index, S);
+    LDS_CHECK_ARG(A.fpack_multi != nullptr && (reinterpret_cast<uintptr_t>(A.fpack_multi) & 15) == 0, "lds_outer_step: num_samples > 1 needs a 16-byte aligned fpack_multi");
+    if (sharded || A.opt_kind != LDS_OPT_SGD || (A.k3_flags & LDS_K3_SIMT)) { set_error("lds_outer_step: the multi-sample estimator runs unsharded with the tensor-core SGD update"); return LDS_ERR_UNSUPPORTED; }
+  }
+  dx.key = philox_key(A.seed, A.step, LDS_STREAM_DROP_X, smp);
+  dh.key = philox_key(A.seed, A.step, LDS_STREAM_DROP_H, smp);
 
   int32_t rc;
   profile_mark(stream, -1);
@@ -375,7 +382,7 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
     FusedSmallArgs F;
     memset(&F, 0, sizeof(F));
     F.theta = A.theta_full; F.ldt = A.ld_theta; F.n = A.n;
-    F.rounds = philox_rounds(philox_key(A.seed, A.step, LDS_STREAM_EDGES, 0));
+    F.rounds = philox_rounds(philox_key(A.seed, A.step, LDS_STREAM_EDGES, smp));
     F.u_explicit = A.u_explicit; F.ldu = A.ld_u;
     F.a_dump = (A.k2_flags & LDS_K2_DUMP_ADJ) ? reinterpret_cast<__nv_bfloat16*>(buf(B_A)) : nullptr; F.lda = L.lda;
     F.deg_part = fbuf(B_DEGP); F.deg = fbuf(B_DEG); F.rs = fbuf(B_RS);
@@ -391,8 +398,10 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
     E.p1 = fbuf(B_P1); E.z1 = fbuf(B_Z1); E.p2 = fbuf(B_P2); E.z2 = fbuf(B_Z2); E.dz2 = fbuf(B_DZ2); E.dp2 = fbuf(B_DP2);
     E.dz1 = fbuf(B_DZ1); E.dp1 = fbuf(B_DP1); E.ldr = L.ldr; E.cvec = fbuf(B_C);
     E.ldf = L.ldf; E.kf = L.kf;
-    if (tc_update) E.fpack = reinterpret_cast<__nv_bfloat16*>(buf(B_F));
+    if (tc_update) { E.fpack = reinterpret_cast<__nv_bfloat16*>(buf(B_F)); E.ld_fpack = L.kf; }
     else { E.fa = fbuf(B_FA); E.fb = fbuf(B_FB); }
+    if (S > 1) { E.fpack = reinterpret_cast<__nv_bfloat16*>(A.fpack_multi) + (int64_t)smp * L.kf; E.ld_fpack = (int64_t)S * L.kf; }
+    E.c_accumulate = (S > 1 && smp > 0) ? 1 : 0; E.scal_scale = 1.0f / (float)S; E.scal_accumulate = E.c_accumulate;
     E.w1 = A.w1; E.b1 = A.b1; E.y = A.y; E.mask = A.mask; E.inv_m = 1.0f / (float)A.mask_count;
     E.drop_h = dh; E.bt_hi = bt_hi; E.bt_lo = bt_lo; E.ldb = L.ldb;
     E.loss_part = fbuf(B_LOSSP); E.corr_part = fbuf(B_CORRP); E.nblk = L.panels;
@@ -410,7 +419,7 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
       LDS_CHECK_LAUNCH("stage_w0_kernel");
       profile_mark(stream, 8);
     }
-    rc = lds_k1_sample_normalize(A.theta_full, A.ld_theta, A.n, row0, rows, A.seed, A.step, 0, A.u_explicit, A.ld_u,
+    rc = lds_k1_sample_normalize(A.theta_full, A.ld_theta, A.n, row0, rows, A.seed, A.step, smp, A.u_explicit, A.ld_u,
                                  buf(B_A), L.lda, nullptr, 0, fbuf(B_DEG), fbuf(B_RS), A.u_explicit ? LDS_K1_EXPLICIT_U : 0u, stream_);
     if (rc != LDS_OK) return rc;
     profile_mark(stream, 0);
@@ -436,8 +445,10 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   E.dz1 = fbuf(B_DZ1); E.dp1 = fbuf(B_DP1); E.ldr = L.ldr; E.cvec = fbuf(B_C);
   // factor rows: packed bf16 for the tensor-core update (own rows inside the n-row F buffer), row-major fp32 for the CUDA-core one
   E.ldf = L.ldf; E.kf = L.kf;
-  if (tc_update) E.fpack = reinterpret_cast<__nv_bfloat16*>(buf(B_F)) + (int64_t)row0 * L.kf;
+  if (tc_update) { E.fpack = reinterpret_cast<__nv_bfloat16*>(buf(B_F)) + (int64_t)row0 * L.kf; E.ld_fpack = L.kf; }
   else { E.fa = fbuf(B_FA); E.fb = fbuf(B_FB); }
+  if (S > 1) { E.fpack = reinterpret_cast<__nv_bfloat16*>(A.fpack_multi) + (int64_t)smp * L.kf; E.ld_fpack = (int64_t)S * L.kf; }
+  E.c_accumulate = (S > 1 && smp > 0) ? 1 : 0; E.scal_scale = 1.0f / (float)S; E.scal_accumulate = E.c_accumulate;
   E.w1 = A.w1; E.b1 = A.b1; E.y = A.y; E.mask = A.mask; E.inv_m = 1.0f / (float)A.mask_count;
   E.drop_h = dh; E.bt_hi = bt_hi; E.bt_lo = bt_lo; E.ldb = L.ldb;
   E.loss_part = fbuf(B_LOSSP); E.corr_part = fbuf(B_CORRP); E.nblk = L.panels;
@@ -462,9 +473,11 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   if ((rc = propagate(LDS_PHASE_BWD2, L.s2, A.c, K2_EPI_BWD2, 5)) != LDS_OK) return rc;       // dP2, dZ1, operand (r dZ1)^T; loss/acc finalised
   if ((rc = propagate(LDS_PHASE_BWD1, L.s1, A.h, K2_EPI_BWD1, 6)) != LDS_OK) return rc;       // dP1, c, factor matrices
 
-  if ((phases & LDS_PHASE_UPDATE) && A.update) {
+  if ((phases & LDS_PHASE_UPDATE) && A.update && (S == 1 || (int)smp == S - 1)) {
     const float* cv = sharded ? A.c_full : fbuf(B_C);
-    if (tc_update) {
+    if (S > 1) {                                              // mean of the S single-sample gradients: one pass, K = S * kf
+      rc = k3_launch_tc(A.theta_full, A.ld_theta, A.n, 0, rows, A.fpack_multi, S * L.kf, cv, A.lr / (float)S, stream);
+    } else if (tc_update) {
       const void* f = sharded ? A.f_full : buf(B_F);
       LDS_CHECK_ARG((reinterpret_cast<uintptr_t>(cv) & 15) == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0, "lds_outer_step: c_full / f_full must be 16-byte aligned");
       rc = k3_launch_tc(A.theta_full, A.ld_theta, A.n, row0, rows, f, L.kf, cv, A.lr, stream);

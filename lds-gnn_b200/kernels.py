@@ -224,6 +224,7 @@ class OuterStep:
         self.args = _lib.OuterStepArgs()
         self._args_ref = ctypes.byref(self.args)
         self._f32_factors = False
+        self._fpack_multi = None
         self._init_static_args()
 
     def set_mask(self, mask):
@@ -296,6 +297,20 @@ class OuterStep:
         a.row0, a.rows, a.phases, a.reserved2 = (self.row0, self.rows, 0, 0) if self.sharded else (0, 0, 0, 0)
         self._clear_optional_args()
 
+    def run_multi(self, theta_full, num_samples, lr, seed, step, **kw):
+        """Multi-sample straight-through estimator: `num_samples` graphs (Philox sample index s) with their own dropout
+        masks, theta <- clamp(theta - lr * mean_s dL_s/dtheta) applied once; (loss, acc) are the sample means."""
+        s_total = int(num_samples)
+        if s_total <= 1:
+            return self.run(theta_full, lr=lr, seed=seed, step=step, **kw)
+        kf = int(self.lib.lds_outer_step_packed_k(self.h, self.c))
+        if self._fpack_multi is None or self._fpack_multi.shape != (self.n, s_total * kf):
+            self._fpack_multi = torch.zeros((self.n, s_total * kf), dtype=BF16, device=self.device)
+        out = None
+        for s in range(s_total):
+            out = self.run(theta_full, lr=lr, seed=seed, step=step, sample=s, num_samples=s_total, fpack_multi=self._fpack_multi, **kw)
+        return out
+
     def _clear_optional_args(self):
         a = self.args
         a.u_explicit, a.ld_u, a.keep_x, a.keep_h = None, 0, None, None
@@ -310,7 +325,7 @@ class OuterStep:
     def run(self, theta_full, lr, seed, step, dropout_p=0.0, update=True, u=None, keep_x=None, keep_h=None,
             opt_kind=_lib.OPT_SGD, adam_m=None, adam_v=None, betas=(0.9, 0.999), eps=1e-8, adam_t=1,
             out_logp=None, k2_flags=0, k3_flags=0, phases=None, opnd_full=None, fa_full=None, fb_full=None, c_full=None,
-            f_full=None, k2_timeline=None, scalars_out=None, want_adj=True):
+            f_full=None, k2_timeline=None, scalars_out=None, want_adj=True, sample=0, num_samples=1, fpack_multi=None):
         """Enqueue one fused outer step on the current stream. Results: (loss, acc) in `scalars_out[0:2]` (any fp32
         buffer the device can write, e.g. pinned host memory) or, by default, in self.scalars.
         `want_adj`: keep the sampled A_tilde readable through buffer("adj") — small graphs run a fused kernel whose A_tilde
@@ -324,6 +339,8 @@ class OuterStep:
         a.update = int(bool(update))
         if want_adj:
             k2_flags = int(k2_flags) | _lib.K2_DUMP_ADJ
+        a.num_samples, a.sample_index = int(num_samples), int(sample)
+        a.fpack_multi = None if fpack_multi is None else fpack_multi.data_ptr()
         plain = (u is None and keep_x is None and keep_h is None and adam_m is None and out_logp is None and not k2_flags
                  and not k3_flags and opnd_full is None and fa_full is None and c_full is None and f_full is None
                  and k2_timeline is None and scalars_out is None)

@@ -73,6 +73,7 @@ class OuterProblemTrainer:
         self.refine_embeddings = refine_embeddings
         self.fused_enabled = True          # set False to force the composable route
         self.first_order = False           # True: drop the hypergradient terms through unrolled inner steps (always fused)
+        self.n_samples = 1                 # fused route: Bernoulli samples per outer step (mean of the straight-through gradients)
         self.last_route = None             # "fused" | "composable" (observability / tests)
         self._engine = None
         self._adam_state = None
@@ -195,8 +196,14 @@ class OuterProblemTrainer:
         # transfer is those 8 bytes, and the host only waits for the stream.
         if self._host_scalars is None:
             self._host_scalars = torch.zeros(4, dtype=torch.float32).pin_memory()
-        eng.run(theta, lr=group["lr"], seed=seed, step=step, dropout_p=float(gcn.dropout),
-                update=True, opt_kind=kind, scalars_out=self._host_scalars, want_adj=False, **extra)
+        if self.n_samples > 1:
+            if kind != _lib.OPT_SGD:
+                raise NotImplementedError("n_samples > 1 is implemented for the SGD outer optimiser (models/factory.py:66-69)")
+            eng.run_multi(theta, self.n_samples, lr=group["lr"], seed=seed, step=step, dropout_p=float(gcn.dropout),
+                          update=True, scalars_out=self._host_scalars, want_adj=False)
+        else:
+            eng.run(theta, lr=group["lr"], seed=seed, step=step, dropout_p=float(gcn.dropout),
+                    update=True, opt_kind=kind, scalars_out=self._host_scalars, want_adj=False, **extra)
         model.mark_full_updated()
         if self.lr_decayer is not None:
             self.optimizer._opt_called = True             # the update ran in the kernel; keeps StepLR's order check quiet

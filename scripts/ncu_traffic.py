@@ -17,6 +17,7 @@ EPI = {"1": "k2_layer1", "2": "k2_layer2", "3": "k2_bwd2", "4": "k2_bwd1", "0": 
 def bench_name(kname):
     if "k1_sample_kernel" in kname: return "k1_sample_normalize"
     if "k3_tc_kernel" in kname: return "k3k4_theta_update"
+    if "fused_small_kernel" in kname: return "fused_k1_feat_k2x4"
     if "feat_sparse_kernel" in kname or "feat_linear_kernel" in kname: return "feat_linear"
     m = re.search(r"k2_mma_kernel<\(int\)(\d+), \(int\)(\d+)>", kname) or re.search(r"k2_mma_kernel<(\d+), (\d+)>", kname)
     if m: return EPI.get(m.group(2), "k2")

@@ -224,3 +224,54 @@ def test_row_block_sharded_step_matches_single_device(n, f, h, c, p, world):
     new = torch.cat(thetas, dim=0)
     assert (new - ref_theta).abs().max().item() < 5e-6       # fp32 summation order of the split propagations differs
     assert torch.equal(new[:, :n], new[:, :n].t())            # shards stay mutually consistent (exact symmetry)
+
+
+# ------------------------------------------------------------------------------------------------
+# Multi-sample straight-through estimator (BASELINE.json config 3: S Bernoulli samples per outer step)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,f,h,c,S,sparse,p", [(300, 40, 16, 7, 3, True, 0.5), (300, 40, 16, 7, 3, False, 0.0), (530, 64, 32, 5, 4, True, 0.5),
+                                               (1100, 50, 16, 6, 16, True, 0.5)],
+                         ids=["fused-kernel-S3", "dense-x-S3", "h32-S4", "S16"])
+def test_multi_sample_step_is_the_mean_of_the_single_sample_gradients(n, f, h, c, S, sparse, p):
+    """theta <- clamp(theta - lr * mean_s g_s): the S samples' rank-2d gradients are concatenated along K of ONE update pass.
+    Expected value: the per-sample factor matrices of single-sample calls with the same (seed, step, sample) — themselves
+    checked against the oracle above — combined in fp64."""
+    from lds_gnn_b200 import kernels as K
+    rng = np.random.default_rng(n + S)
+    x = (rng.random((n, f)) < 0.1).astype(np.float32) * rng.random((n, f)).astype(np.float32)
+    y = rng.integers(0, c, n)
+    mask = rng.random(n) < 0.3
+    w = [dev((rng.standard_normal(s_) * 0.3).astype(np.float32)) for s_ in ((h, f), (h,), (c, h), (c,))]
+    a = (rng.random((n, n)) < 0.05)
+    th = np.triu(a, 1); th = (th + th.T).astype(np.float32) * 0.9 + 0.05 * np.eye(n, dtype=np.float32)
+    th[5, 7] = th[7, 5] = 1.3; th[9, 11] = th[11, 9] = -0.2                       # outside [0, 1]: clamp backward masks them
+    theta0 = K.theta_triu_to_full(dev(th[np.triu_indices(n)]))
+    eng = K.OuterStep(n, dev(x), dev(y), dev(mask), hidden=h, classes=c, sparse_features=sparse)
+    eng.set_weights(*w)
+    seed, step, lr = 99, 3, 0.6
+    g = np.zeros((n, n)); losses, accs, adjs = [], [], []
+    for s in range(S):
+        t = theta0.clone()
+        sc = eng.run(t, lr=lr, seed=seed, step=step, dropout_p=p, update=False, sample=s).clone()
+        assert torch.equal(t, theta0)
+        fa, fb, cv = (eng.buffer(k).double().cpu().numpy() for k in ("fa", "fb", "cvec"))
+        gs = fa @ fb.T + fb @ fa.T + cv[:, None] + cv[None, :]
+        np.fill_diagonal(gs, 0.0)
+        g += gs
+        losses.append(sc[0].item()); accs.append(sc[1].item())
+        adjs.append(eng.buffer("adj")[:, :n].float().cpu().numpy().copy())
+    assert any(not np.array_equal(adjs[0], adjs[s]) for s in range(1, S)), "samples must differ"
+    th64 = theta0[:, :n].double().cpu().numpy()
+    g *= ((th64 >= 0) & (th64 <= 1))
+    ref = np.clip(th64 - lr * g / S, 0, 1)
+    theta = theta0.clone()
+    sc = eng.run_multi(theta, S, lr=lr, seed=seed, step=step, dropout_p=p, update=True)
+    out = theta[:, :n].cpu().numpy()
+    assert np.array_equal(out, out.T)
+    assert np.abs(out - ref).max() < 3e-6 + 2e-5 * lr * np.abs(g).max() / S
+    assert abs(sc[0].item() - np.mean(losses)) < 1e-5 and abs(sc[1].item() - np.mean(accs)) < 1e-6
+    # S = 1 through run_multi is the plain step
+    t1, t2 = theta0.clone(), theta0.clone()
+    eng.run_multi(t1, 1, lr=lr, seed=seed, step=step, dropout_p=p, update=True)
+    eng.run(t2, lr=lr, seed=seed, step=step, dropout_p=p, update=True)
+    assert torch.equal(t1, t2)
