@@ -194,6 +194,14 @@ typedef struct lds_outer_step_args {
    * (the S rank-2d gradients are concatenated along K of the update GEMM). Tensor-core SGD update, unsharded only. */
   int32_t  num_samples, sample_index;
   void*    fpack_multi;
+  /* ---- sharded step, operand exchange in its final layout (optional; opnd_send == NULL keeps the fp32 row exchange).
+   * Each phase leaves the NEXT propagation's operand rows of this rank in opnd_send as bf16 [hi: hp x opnd_rank_rows]
+   * [lo: hp x opnd_rank_rows] (K-major, hp = padded operand width of the next propagation: 16/32/64/128; rows beyond this
+   * rank's row count stay as the caller zero-filled them). The caller all-gathers the first 2 * hp * opnd_rank_rows
+   * elements of every rank into opnd_full = [rank][hi, lo][hp][opnd_rank_rows]; the propagation reads it through a 3-D
+   * tensor map, so no re-layout kernel runs. opnd_rank_rows = rows per rank (a multiple of 64, the same on every rank). */
+  void*    opnd_send;
+  int32_t  opnd_rank_rows, reserved3;
 } lds_outer_step_args;
 
 #define LDS_PHASE_SAMPLE   1u
@@ -216,6 +224,7 @@ int32_t lds_outer_step(const lds_outer_step_args* args, void* stream);
 void*   lds_outer_step_buffer(void* workspace, int32_t n, int32_t f, int32_t h, int32_t c, int32_t which);
 void*   lds_outer_step_shard_buffer(void* workspace, int32_t n, int32_t rows, int32_t f, int32_t h, int32_t c, int32_t which);
 int64_t lds_outer_step_factor_ld(int32_t h, int32_t c);
+int32_t lds_outer_step_operand_hp(int32_t h, int32_t c, uint32_t phase);   /* padded operand width (16/32/64/128) of a propagation phase */
 int64_t lds_outer_step_packed_k(int32_t h, int32_t c);   /* columns of a packed bf16 factor row            */
 int64_t lds_outer_step_state_ld(int32_t rows);           /* row stride of the transposed row-local state    */
 

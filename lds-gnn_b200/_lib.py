@@ -47,6 +47,7 @@ SIGNATURES = {
     "lds_outer_step_buffer": (c_void_p, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32]),
     "lds_outer_step_factor_ld": (c_int64, [c_int32, c_int32]),
     "lds_outer_step_packed_k": (c_int64, [c_int32, c_int32]),
+    "lds_outer_step_operand_hp": (c_int32, [c_int32, c_int32, c_uint32]),
     "lds_outer_step_state_ld": (c_int64, [c_int32]),
     "lds_profile_begin": (c_int32, []),
     "lds_profile_end": (c_int32, [c_void_p, c_void_p, c_int32]),
@@ -79,6 +80,7 @@ class OuterStepArgs(Structure):
         ("opnd_full", c_void_p), ("fa_full", c_void_p), ("fb_full", c_void_p), ("c_full", c_void_p),
         ("f_full", c_void_p), ("k2_timeline", c_void_p),
         ("num_samples", c_int32), ("sample_index", c_int32), ("fpack_multi", c_void_p),
+        ("opnd_send", c_void_p), ("opnd_rank_rows", c_int32), ("reserved3", c_int32),
     ]
 
 

@@ -41,7 +41,7 @@ template <int HP, int EPI>
 __global__ void __launch_bounds__(K2_THREADS, 1)
 k2_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_bhi,
               const __grid_constant__ CUtensorMap tm_blo, float* __restrict__ partial, int* __restrict__ counters,
-              const K2Sched s, const int use_lo, const __grid_constant__ EpiArgs ea) {
+              const K2Sched s, const int use_lo, const __grid_constant__ EpiArgs ea, const int b_rank_rows) {
   __shared__ K2EpiShared sh_epi;
   using Cfg = K2Cfg<HP>;
   constexpr int STAGES = Cfg::STAGES;
@@ -88,8 +88,14 @@ k2_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
           uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], tx_bytes);
           tma_load_2d(st, &tm_a, &full_bar[stage], kb * K2_BLOCK_K, p * K2_BLOCK_M);
-          tma_load_2d(st + Cfg::A_BYTES, &tm_bhi, &full_bar[stage], kb * K2_BLOCK_K, 0);
-          if (use_lo) tma_load_2d(st + Cfg::A_BYTES + Cfg::B_BYTES, &tm_blo, &full_bar[stage], kb * K2_BLOCK_K, 0);
+          if (b_rank_rows > 0) {                             // operand as gathered: [rank][HP][rows of that rank] (sharded step)
+            const int rk = (kb * K2_BLOCK_K) / b_rank_rows, i0 = kb * K2_BLOCK_K - rk * b_rank_rows;
+            tma_load_3d(st + Cfg::A_BYTES, &tm_bhi, &full_bar[stage], i0, 0, rk);
+            if (use_lo) tma_load_3d(st + Cfg::A_BYTES + Cfg::B_BYTES, &tm_blo, &full_bar[stage], i0, 0, rk);
+          } else {
+            tma_load_2d(st + Cfg::A_BYTES, &tm_bhi, &full_bar[stage], kb * K2_BLOCK_K, 0);
+            if (use_lo) tma_load_2d(st + Cfg::A_BYTES + Cfg::B_BYTES, &tm_blo, &full_bar[stage], kb * K2_BLOCK_K, 0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         pos += cnt;
@@ -275,49 +281,71 @@ int32_t make_tmap_2d(CUtensorMap* out, CUtensorMapDataType dtype, int elem_bytes
   return LDS_OK;
 }
 
+int32_t make_tmap_3d_bf16(CUtensorMap* out, const void* base, int64_t cols, int64_t rows, int64_t blocks, int64_t row_stride_elems,
+                          int64_t block_stride_elems, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return LDS_ERR_CUDA; }
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)blocks};
+  cuuint64_t gstr[2] = {(cuuint64_t)row_stride_elems * 2, (cuuint64_t)block_stride_elems * 2};
+  cuuint32_t box[3] = {(cuuint32_t)K2_BLOCK_K, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (3-D) failed with CUresult %d (cols=%lld rows=%lld blocks=%lld)", (int)r, (long long)cols, (long long)rows, (long long)blocks); return LDS_ERR_CUDA; }
+  return LDS_OK;
+}
+
 static int32_t make_tmap_bf16(CUtensorMap* out, const void* base, int64_t cols, int64_t rows, int64_t ld, int box_rows) {
   return make_tmap_2d(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, cols, rows, ld, K2_BLOCK_K, box_rows);
 }
 
 template <int HP, int EPI>
 static int32_t launch_mma_t(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tbl, float* partial, int* counters,
-                            const K2Sched& s, bool use_lo, const EpiArgs& ea, cudaStream_t stream) {
+                            const K2Sched& s, bool use_lo, const EpiArgs& ea, int b_rank_rows, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     LDS_CHECK_CUDA(cudaFuncSetAttribute(k2_mma_kernel<HP, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2Cfg<HP>::SMEM_BYTES));
     attr_set = true;
   }
-  k2_mma_kernel<HP, EPI><<<s.grid, K2_THREADS, K2Cfg<HP>::SMEM_BYTES, stream>>>(ta, tbh, tbl, partial, counters, s, use_lo ? 1 : 0, ea);
+  k2_mma_kernel<HP, EPI><<<s.grid, K2_THREADS, K2Cfg<HP>::SMEM_BYTES, stream>>>(ta, tbh, tbl, partial, counters, s, use_lo ? 1 : 0, ea, b_rank_rows);
   LDS_CHECK_LAUNCH("k2_mma_kernel");
   return LDS_OK;
 }
 
 template <int HP>
 static int32_t launch_mma_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tbl, float* partial, int* counters,
-                              const K2Sched& s, bool use_lo, const EpiArgs& ea, cudaStream_t stream) {
+                              const K2Sched& s, bool use_lo, const EpiArgs& ea, int b_rank_rows, cudaStream_t stream) {
   switch (epi) {
-    case K2_EPI_PLAIN:  return launch_mma_t<HP, K2_EPI_PLAIN>(ta, tbh, tbl, partial, counters, s, use_lo, ea, stream);
-    case K2_EPI_LAYER1: return launch_mma_t<HP, K2_EPI_LAYER1>(ta, tbh, tbl, partial, counters, s, use_lo, ea, stream);
-    case K2_EPI_LAYER2: return launch_mma_t<HP, K2_EPI_LAYER2>(ta, tbh, tbl, partial, counters, s, use_lo, ea, stream);
-    case K2_EPI_BWD2:   return launch_mma_t<HP, K2_EPI_BWD2>(ta, tbh, tbl, partial, counters, s, use_lo, ea, stream);
-    case K2_EPI_BWD1:   return launch_mma_t<HP, K2_EPI_BWD1>(ta, tbh, tbl, partial, counters, s, use_lo, ea, stream);
+    case K2_EPI_PLAIN:  return launch_mma_t<HP, K2_EPI_PLAIN>(ta, tbh, tbl, partial, counters, s, use_lo, ea, b_rank_rows, stream);
+    case K2_EPI_LAYER1: return launch_mma_t<HP, K2_EPI_LAYER1>(ta, tbh, tbl, partial, counters, s, use_lo, ea, b_rank_rows, stream);
+    case K2_EPI_LAYER2: return launch_mma_t<HP, K2_EPI_LAYER2>(ta, tbh, tbl, partial, counters, s, use_lo, ea, b_rank_rows, stream);
+    case K2_EPI_BWD2:   return launch_mma_t<HP, K2_EPI_BWD2>(ta, tbh, tbl, partial, counters, s, use_lo, ea, b_rank_rows, stream);
+    case K2_EPI_BWD1:   return launch_mma_t<HP, K2_EPI_BWD1>(ta, tbh, tbl, partial, counters, s, use_lo, ea, b_rank_rows, stream);
   }
   set_error("k2: unknown epilogue %d", epi);
   return LDS_ERR_ARG;
 }
 
 int32_t k2_launch_mma(const void* a, int64_t ld_a, int n, int rows, const void* bt_hi, const void* bt_lo, int64_t ldb,
-                      float* partial, int* counters, const K2Sched& s, bool use_lo, int epi, const EpiArgs& ea, cudaStream_t stream) {
+                      float* partial, int* counters, const K2Sched& s, bool use_lo, int epi, const EpiArgs& ea, cudaStream_t stream,
+                      int b_rank_rows) {
   CUtensorMap ta, tbh, tbl;
   int32_t rc;
   if ((rc = make_tmap_bf16(&ta, a, n, rows, ld_a, K2_BLOCK_M)) != LDS_OK) return rc;
+  if (b_rank_rows > 0) {      // rank-blocked gathered operand: block r = [hi: hp x b_rank_rows][lo: hp x b_rank_rows], bt_hi / bt_lo point into block 0
+    const int64_t blocks = ceil_div(n, b_rank_rows), bstride = 2 * (int64_t)s.hp * b_rank_rows;
+    if ((rc = make_tmap_3d_bf16(&tbh, bt_hi, b_rank_rows, s.hp, blocks, b_rank_rows, bstride, s.hp)) != LDS_OK) return rc;
+    if ((rc = make_tmap_3d_bf16(&tbl, bt_lo, b_rank_rows, s.hp, blocks, b_rank_rows, bstride, s.hp)) != LDS_OK) return rc;
+  } else {
   if ((rc = make_tmap_bf16(&tbh, bt_hi, n, s.hp, ldb, s.hp)) != LDS_OK) return rc;
   if ((rc = make_tmap_bf16(&tbl, bt_lo, n, s.hp, ldb, s.hp)) != LDS_OK) return rc;
+  }
   switch (s.hp) {
-    case 16: return launch_mma_epi<16>(epi, ta, tbh, tbl, partial, counters, s, use_lo, ea, stream);
-    case 32: return launch_mma_epi<32>(epi, ta, tbh, tbl, partial, counters, s, use_lo, ea, stream);
-    case 64: return launch_mma_epi<64>(epi, ta, tbh, tbl, partial, counters, s, use_lo, ea, stream);
-    case 128: return launch_mma_epi<128>(epi, ta, tbh, tbl, partial, counters, s, use_lo, ea, stream);
+    case 16: return launch_mma_epi<16>(epi, ta, tbh, tbl, partial, counters, s, use_lo, ea, b_rank_rows, stream);
+    case 32: return launch_mma_epi<32>(epi, ta, tbh, tbl, partial, counters, s, use_lo, ea, b_rank_rows, stream);
+    case 64: return launch_mma_epi<64>(epi, ta, tbh, tbl, partial, counters, s, use_lo, ea, b_rank_rows, stream);
+    case 128: return launch_mma_epi<128>(epi, ta, tbh, tbl, partial, counters, s, use_lo, ea, b_rank_rows, stream);
   }
   set_error("k2: unsupported padded width %d", s.hp);
   return LDS_ERR_UNSUPPORTED;

@@ -296,6 +296,10 @@ extern "C" int64_t lds_outer_step_shard_workspace_bytes(int32_t n, int32_t rows,
 }
 
 extern "C" int64_t lds_outer_step_factor_ld(int32_t h, int32_t c) { return round_up(h + c, 4); }
+// padded width of the operand that propagation phase `phase` (LDS_PHASE_LAYER1 .. LDS_PHASE_BWD1) multiplies
+extern "C" int32_t lds_outer_step_operand_hp(int32_t h, int32_t c, uint32_t phase) {
+  return k2_padded_width((phase == LDS_PHASE_LAYER1 || phase == LDS_PHASE_BWD1) ? h : c);
+}
 extern "C" int64_t lds_outer_step_packed_k(int32_t h, int32_t c) { return k3_packed_k(h, c); }
 extern "C" int64_t lds_outer_step_state_ld(int32_t rows) { return round_up(rows, 32); }
 
@@ -349,11 +353,22 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   uint8_t* ws = reinterpret_cast<uint8_t*>(A.workspace);
   auto buf = [&](int b) { return ws + L.off[b]; };
   auto fbuf = [&](int b) { return reinterpret_cast<float*>(ws + L.off[b]); };
-  float* opnd = sharded ? fbuf(B_OPND) : nullptr;            // sharded: operand rows go out as fp32 for the all-gather
+  // sharded: the next operand's rows leave either as fp32 rows (re-laid out by a prep kernel after the all-gather) or,
+  // with opnd_send, directly as the K-major bf16 hi/lo block the propagation's 3-D tensor map reads after the gather
+  const bool packed_xchg = sharded && A.opnd_send != nullptr;
+  if (packed_xchg) LDS_CHECK_ARG(A.opnd_rank_rows >= rows && A.opnd_rank_rows % 64 == 0 && (reinterpret_cast<uintptr_t>(A.opnd_send) & 1023) == 0,
+                                 "lds_outer_step: opnd_send needs opnd_rank_rows >= rows, a multiple of 64, and a 1024-byte aligned buffer");
+  float* opnd = (sharded && !packed_xchg) ? fbuf(B_OPND) : nullptr;
   const int64_t ld_opnd = A.h > A.c ? A.h : A.c;
   int* counters = reinterpret_cast<int*>(buf(B_CNT));
   auto* bt_hi = reinterpret_cast<__nv_bfloat16*>(buf(B_BTHI));
   auto* bt_lo = reinterpret_cast<__nv_bfloat16*>(buf(B_BTLO));
+  const int64_t per = A.opnd_rank_rows;
+  auto* snd = reinterpret_cast<__nv_bfloat16*>(A.opnd_send);
+  // where an epilogue / the feature kernel writes the next operand (padded width hp_next), and with which row stride
+  auto out_hi = [&](int hp_next) { (void)hp_next; return packed_xchg ? snd : bt_hi; };
+  auto out_lo = [&](int hp_next) { return packed_xchg ? snd + (int64_t)hp_next * per : bt_lo; };
+  const int64_t out_ld = packed_xchg ? per : L.ldb;
   const bool use_lo = !(A.k2_flags & LDS_K2_SINGLE_BF16);
 
   DropCfg dx, dh;
@@ -426,11 +441,11 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
     const dim3 egrid((unsigned)L.nblk);
     if (sparse_x) {
       feat_sparse_kernel<<<egrid, EPI_THREADS, 0, stream>>>(A.x_crow, A.x_col, A.x_val, rows, A.f, fbuf(B_W0S), A.b0, A.h, dx, fbuf(B_RS), fbuf(B_P1), L.ldr,
-                                                            bt_hi, bt_lo, L.ldb, L.hp1, row0, opnd, ld_opnd);
+                                                            out_hi(L.hp1), out_lo(L.hp1), out_ld, L.hp1, row0, opnd, ld_opnd);
       LDS_CHECK_LAUNCH("feat_sparse_kernel");
     } else {
       feat_linear_kernel<<<egrid, FEAT_THREADS, 0, stream>>>(A.x, A.ld_x, rows, A.f, fbuf(B_W0S), round_up(A.f, 4), A.b0, A.h, dx, fbuf(B_RS), fbuf(B_P1), L.ldr,
-                                                             bt_hi, bt_lo, L.ldb, L.hp1, row0, opnd, ld_opnd);
+                                                             out_hi(L.hp1), out_lo(L.hp1), out_ld, L.hp1, row0, opnd, ld_opnd);
       LDS_CHECK_LAUNCH("feat_linear_kernel");
     }
     profile_mark(stream, 1);
@@ -457,21 +472,29 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   if ((A.k2_flags & LDS_K2_SIMT) && (phases & (LDS_PHASE_LAYER1 | LDS_PHASE_LAYER2 | LDS_PHASE_BWD2 | LDS_PHASE_BWD1))) {
     set_error("lds_outer_step: LDS_K2_SIMT is only available through lds_k2_propagate"); return LDS_ERR_ARG;
   }
-  auto propagate = [&](uint32_t phase, const K2Sched& s, int width, int epi, int mark) -> int32_t {
+  auto propagate = [&](uint32_t phase, const K2Sched& s, int width, int epi, int mark, int hp_next) -> int32_t {
     if (fused_done || !(phases & phase)) return LDS_OK;
-    if (sharded) {   // the gathered operand [n][width] fp32 -> K-major bf16 hi/lo terms
+    const __nv_bfloat16* in_hi = bt_hi;
+    const __nv_bfloat16* in_lo = bt_lo;
+    int rank_rows = 0;
+    if (packed_xchg) {                                        // gathered [rank][hi, lo][hp][per] bf16
+      in_hi = reinterpret_cast<const __nv_bfloat16*>(A.opnd_full);
+      in_lo = in_hi + (int64_t)s.hp * per;
+      rank_rows = (int)per;
+    } else if (sharded) {   // the gathered operand [n][width] fp32 -> K-major bf16 hi/lo terms
       const int32_t r0 = k2_launch_prep(A.opnd_full, ld_opnd, A.n, width, s.hp, nullptr, bt_hi, bt_lo, L.ldb, counters, 0, stream);
       if (r0 != LDS_OK) return r0;
     }
+    E.bt_hi = out_hi(hp_next); E.bt_lo = out_lo(hp_next); E.ldb = out_ld;
     E.timeline = A.k2_timeline ? A.k2_timeline + (size_t)(mark - 3) * 512 * 8 : nullptr;
-    const int32_t r = k2_launch_mma(buf(B_A), L.lda, A.n, rows, bt_hi, bt_lo, L.ldb, fbuf(B_PARTIAL), counters, s, use_lo, epi, E, stream);
+    const int32_t r = k2_launch_mma(buf(B_A), L.lda, A.n, rows, in_hi, in_lo, L.ldb, fbuf(B_PARTIAL), counters, s, use_lo, epi, E, stream, rank_rows);
     profile_mark(stream, mark);
     return r;
   };
-  if ((rc = propagate(LDS_PHASE_LAYER1, L.s1, A.h, K2_EPI_LAYER1, 3)) != LDS_OK) return rc;   // Z1, H1, P2, operand (r P2)^T
-  if ((rc = propagate(LDS_PHASE_LAYER2, L.s2, A.c, K2_EPI_LAYER2, 4)) != LDS_OK) return rc;   // Z2, log-softmax, loss, dZ2, operand (r dZ2)^T
-  if ((rc = propagate(LDS_PHASE_BWD2, L.s2, A.c, K2_EPI_BWD2, 5)) != LDS_OK) return rc;       // dP2, dZ1, operand (r dZ1)^T; loss/acc finalised
-  if ((rc = propagate(LDS_PHASE_BWD1, L.s1, A.h, K2_EPI_BWD1, 6)) != LDS_OK) return rc;       // dP1, c, factor matrices
+  if ((rc = propagate(LDS_PHASE_LAYER1, L.s1, A.h, K2_EPI_LAYER1, 3, L.hp2)) != LDS_OK) return rc;   // Z1, H1, P2, operand (r P2)^T
+  if ((rc = propagate(LDS_PHASE_LAYER2, L.s2, A.c, K2_EPI_LAYER2, 4, L.hp2)) != LDS_OK) return rc;   // Z2, log-softmax, loss, dZ2, operand (r dZ2)^T
+  if ((rc = propagate(LDS_PHASE_BWD2, L.s2, A.c, K2_EPI_BWD2, 5, L.hp1)) != LDS_OK) return rc;       // dP2, dZ1, operand (r dZ1)^T; loss/acc finalised
+  if ((rc = propagate(LDS_PHASE_BWD1, L.s1, A.h, K2_EPI_BWD1, 6, L.hp1)) != LDS_OK) return rc;       // dP1, c, factor matrices
 
   if ((phases & LDS_PHASE_UPDATE) && A.update && (S == 1 || (int)smp == S - 1)) {
     const float* cv = sharded ? A.c_full : fbuf(B_C);

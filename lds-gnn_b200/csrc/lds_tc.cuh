@@ -46,6 +46,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int x, int y, int z) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const void* smem_src, const CUtensorMap* m, int x, int y) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(x), "r"(y) : "memory");
@@ -101,5 +106,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
 // (box_cols * elem_bytes must be 128). Defined in lds_k2_propagate.cu.
 int32_t make_tmap_2d(CUtensorMap* out, CUtensorMapDataType dtype, int elem_bytes, const void* base, int64_t cols, int64_t rows,
                      int64_t ld, int box_cols, int box_rows);
+
+// Host: 3-D bf16 tensor map over a rank-blocked operand [blocks][rows][cols] (cols contiguous), box = 1 x box_rows x 64 cols,
+// 128-byte swizzle. Defined in lds_k2_propagate.cu.
+int32_t make_tmap_3d_bf16(CUtensorMap* out, const void* base, int64_t cols, int64_t rows, int64_t blocks, int64_t row_stride_elems,
+                          int64_t block_stride_elems, int box_rows);
 
 }  // namespace lds

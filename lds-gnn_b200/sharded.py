@@ -4,7 +4,10 @@ by contiguous row blocks over the ranks of one box. theta / A_tilde never move:
   * sampling needs no exchange — the Philox draw of edge (i, j) is keyed on (min, max), so the owners of row i and of
     row j regenerate the same bit, and the K3 update is symmetric bit for bit (csrc/lds_k3_theta_update.cu);
   * each of the four propagations Z_rows = r_rows * (A_tilde_rows @ (r * P)) needs the scaled N x w operand of ALL
-    rows: one all-gather of [rows, w] fp32 blocks (16.8 MB at N = 65 536, w = 64) — the only data-path collective;
+    rows: one all-gather per propagation — the only data-path collective. Every rank leaves its rows already in the
+    layout the tensor cores read (K-major bf16 hi/lo block [2][hp][rows per rank]); the gathered array
+    [rank][2][hp][rows per rank] is read through a 3-D TMA tensor map, so nothing is re-laid out after the gather
+    (16.8 MB at N = 65 536 for the two h = 64 wide operands, 4.2 MB for the two class-wide ones);
   * the closed-form theta update needs the factor rows of ALL nodes and c [N]: for the tensor-core SGD update these
     are the packed bf16 rows the BWD1 epilogue writes (8 B per factor element, lds_k3.cuh), gathered as they are;
     for the CUDA-core update (Adam) the fp32 rows fa, fb [N, d];
@@ -55,6 +58,11 @@ class DistComm:
             out[lo:lo + cnt] = gathered[r * per:r * per + cnt]
         return out
 
+    def all_gather_flat(self, local, out):
+        """Equal-size contiguous chunks: out = concat over ranks of `local`."""
+        self.dist.all_gather_into_tensor(out, local, group=self.group)
+        return out
+
     def all_reduce_sum(self, t):
         self.dist.all_reduce(t, group=self.group)
         return t
@@ -69,7 +77,9 @@ class ShardedOuterStep:
         dev = x_local.device
         w = max(self.h, self.c)
         self.ldf = int(_lib.load().lds_outer_step_factor_ld(self.h, self.c))
-        self.opnd_full = torch.empty((self.n, w), dtype=torch.float32, device=dev)
+        self.opnd_full = torch.empty((self.n, w), dtype=torch.float32, device=dev)          # legacy fp32 row exchange (packed=False)
+        self.packed = True
+        self.world_rows = None                                 # rows per rank (multiple of 128), set by the driver / comm
         self.fa_full = self.fb_full = None                   # fp32 factor rows: only for the CUDA-core update (allocated on first use)
         self.kf = int(_lib.load().lds_outer_step_packed_k(self.h, self.c))
         self.f_full = torch.empty((self.n, self.kf), dtype=K.BF16, device=dev)
@@ -78,9 +88,36 @@ class ShardedOuterStep:
     def set_weights(self, *w):
         self.eng.set_weights(*w)
 
+    def _setup_packed(self, per):
+        """Buffers of the packed operand exchange: send block [2][hp][per] bf16 and the gathered [R][2][hp][per]."""
+        if self.world_rows == per:
+            return
+        self.world_rows = int(per)
+        lib = _lib.load()
+        self.hp = {ph: int(lib.lds_outer_step_operand_hp(self.h, self.c, ph)) for ph in PHASES}
+        hpmax = max(self.hp.values())
+        nblk = -(-self.n // per)
+        dev = self.opnd_full.device
+        raw = torch.zeros(2 * hpmax * per + 512, dtype=K.BF16, device=dev)       # rows beyond this rank's count stay zero
+        off = ((-raw.data_ptr()) % 1024) // 2
+        self.send = raw[off:off + 2 * hpmax * per]
+        self._send_raw = raw
+        self.recv = torch.zeros(nblk * 2 * hpmax * per, dtype=K.BF16, device=dev)
+
     def phase(self, theta_local, phases, **kw):
+        if self.packed and self.world_rows:
+            return self.eng.run(theta_local, phases=phases, opnd_full=self.recv, opnd_send=self.send, opnd_rank_rows=self.world_rows,
+                                fa_full=self.fa_full, fb_full=self.fb_full, c_full=self.c_full, f_full=self.f_full, **kw)
         return self.eng.run(theta_local, phases=phases, opnd_full=self.opnd_full, fa_full=self.fa_full, fb_full=self.fb_full,
                             c_full=self.c_full, f_full=self.f_full, **kw)
+
+    def exchange_operand(self, ph, gather_flat, gather_rows):
+        """All-gather the operand of propagation `ph` (written by the previous phase)."""
+        if self.packed and self.world_rows:
+            cnt = 2 * self.hp[ph] * self.world_rows
+            gather_flat(self.send[:cnt], self.recv[:(-(-self.n // self.world_rows)) * cnt])
+        else:
+            gather_rows(self.eng.buffer("operand"), self.opnd_full)
 
     @staticmethod
     def tensor_core_update(kw):
@@ -99,9 +136,11 @@ class ShardedOuterStep:
     def run(self, theta_local, comm, lr, seed, step, dropout_p=0.0, update=True, **kw):
         """One sharded outer step on this rank. Returns a device tensor (loss, acc) of the WHOLE graph."""
         kw = dict(lr=lr, seed=seed, step=step, dropout_p=dropout_p, update=update, **kw)
+        if self.packed:
+            self._setup_packed(comm.bounds[0][1])
         self.phase(theta_local, _lib.PHASE_SAMPLE, **kw)
         for ph in PHASES:
-            comm.all_gather_rows(self.eng.buffer("operand"), self.opnd_full)
+            self.exchange_operand(ph, comm.all_gather_flat, comm.all_gather_rows)
             self.phase(theta_local, ph, **kw)
         scalars = comm.all_reduce_sum(self.eng.scalars[:2].clone())
         for name, full in self.factor_buffers(kw):
@@ -125,10 +164,21 @@ def run_local_group(shards, thetas, lr, seed, step, dropout_p=0.0, update=True, 
     for s in shards:
         s.factor_buffers(kw)                                 # allocate the fp32 factor buffers if this step needs them
 
+    per = max(s.rows for s in shards)
+    per = -(-per // 128) * 128
+    for s in shards:
+        if s.packed:
+            s._setup_packed(per)
     for s, t in zip(shards, thetas):
         s.phase(t, _lib.PHASE_SAMPLE, **kw)
     for ph in PHASES:
-        gather("operand", "opnd_full")
+        if shards[0].packed:
+            cnt = 2 * shards[0].hp[ph] * per
+            full = torch.cat([s.send[:cnt] for s in shards])
+            for s in shards:
+                s.recv[:full.numel()].copy_(full)
+        else:
+            gather("operand", "opnd_full")
         for s, t in zip(shards, thetas):
             s.phase(t, ph, **kw)
     scalars = sum(s.eng.scalars[:2].clone() for s in shards)

@@ -183,9 +183,9 @@ def test_error_paths_do_not_abort():
     assert "struct_bytes" in _lib.last_error()
 
 
-@pytest.mark.parametrize("n,f,h,c,p,world", [(700, 64, 16, 7, 0.5, 3), (1500, 200, 32, 10, 0.0, 4), (2708, 1433, 16, 7, 0.5, 2),
-                                             (600, 40, 64, 7, 0.5, 5)])
-def test_row_block_sharded_step_matches_single_device(n, f, h, c, p, world):
+@pytest.mark.parametrize("n,f,h,c,p,world,packed", [(700, 64, 16, 7, 0.5, 3, True), (1500, 200, 32, 10, 0.0, 4, True), (2708, 1433, 16, 7, 0.5, 2, True),
+                                                    (600, 40, 64, 7, 0.5, 5, True), (700, 64, 16, 7, 0.5, 3, False), (600, 40, 64, 7, 0.5, 5, False)])
+def test_row_block_sharded_step_matches_single_device(n, f, h, c, p, world, packed):
     """the oracle of the sharded run is the single-device result. All `world` ranks are emulated on one GPU
     (same kernels, same phases, exchange = concatenation); the sampled mask must be identical bit for bit (no exchange
     of random bits), the rest equal up to fp32 summation order."""
@@ -209,6 +209,7 @@ def test_row_block_sharded_step_matches_single_device(n, f, h, c, p, world):
     for lo, cnt in bounds:
         sh = S.ShardedOuterStep(n, lo, cnt, x[lo:lo + cnt], y[lo:lo + cnt], mask[lo:lo + cnt], int(mask.sum().item()), h, c)
         sh.set_weights(*w)
+        sh.packed = packed            # operand exchange in its final bf16 layout (3-D tensor map) / legacy fp32 rows + re-layout kernel
         shards.append(sh)
         thetas.append(full[lo:lo + cnt].clone())
     sc = S.run_local_group(shards, thetas, lr=lr, seed=seed, step=step, dropout_p=p, update=True)
