@@ -408,7 +408,19 @@ def run_large(args, rank, world, device, workload):
     lib = _lib.load()
     if world > 1:
         eng = S.ShardedOuterStep(n, lo, cnt, d["x"], d["y"], d["mask"], d["mask_count"], h, c)
-        comm = S.DistComm(n)
+        exchange = "nccl all-gather"
+        comm = None
+        if os.environ.get("LDS_EXCHANGE", "peer") == "peer":      # NVLink peer-memory push (symmetric memory); NCCL if it cannot be set up
+            try:
+                comm = S.SymmComm(n)
+                eng._setup_comm(comm)
+                exchange = "NVLink peer-memory push (one 128-bit store kernel per exchange + signal-pad barrier)"
+            except Exception as exc:                              # noqa: BLE001  (report, then use NCCL)
+                print(f"[bench] symmetric-memory exchange unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
+                comm = None
+                eng._comm = None
+        if comm is None:
+            comm = S.DistComm(n)
         eng.set_weights(*views)
         step_fn = lambda k, lr_now: eng.run(theta, comm, lr=lr_now, seed=1234, step=k, dropout_p=HYPER["dropout"], update=True)
         scal = lambda: None
@@ -507,7 +519,8 @@ def run_large(args, rank, world, device, workload):
         "vs_baseline": None, "dtype": "bf16 adjacency x (bf16 hi+lo) operands, fp32 accumulate; fp32 theta", "data": "synthetic",
         "config": {"workload": f"LDS-GCN direct outer step, synthetic N={n} dense theta ~ U(0,1), F={f}, hidden={h}, C={c}, SGD lr 0.1 decay 0.99, "
                                f"dropout 0.5, 1 sample/step", "parallelism": "single GPU" if world == 1 else
-                               f"theta / A_tilde row-block sharded over {world} GPUs, NCCL all-gather of the N x h operand (4 per step) + factors",
+                               f"theta / A_tilde row-block sharded over {world} GPUs; per step 4 all-gathers of the N x h operand + packed factor rows + c "
+                               f"over {exchange}",
                    "l2": "not flushed: per-GPU theta rows are %.1f GB, far larger than the 126 MB L2" % (rows_local * n * 4 / 1e9)},
         "clocks": clock_info,
         "e2e": {"value": round(args.steps / (e2e_ms / 1e3), 3), "unit": UNIT, "h2d_bytes_per_step": total * 4, "d2h_bytes_per_step": 8,

@@ -228,6 +228,11 @@ int32_t lds_outer_step_operand_hp(int32_t h, int32_t c, uint32_t phase);   /* pa
 int64_t lds_outer_step_packed_k(int32_t h, int32_t c);   /* columns of a packed bf16 factor row            */
 int64_t lds_outer_step_state_ld(int32_t rows);           /* row stride of the transposed row-local state    */
 
+/* ---- sharded step over NVLink peer memory: all-gather by direct stores. Copies `bytes` from src into
+ * dst_bases[p] + dst_offset_bytes for every peer p in [0, world) (device array of `world` P2P-mapped base pointers, this
+ * rank included) with 128-bit stores in one kernel; the caller then runs a cross-GPU barrier. 16-byte alignment. */
+int32_t lds_peer_push(const void* src, void* const* dst_bases, int32_t world, int64_t dst_offset_bytes, int64_t bytes, void* stream);
+
 /* ---- measurement hook for bench.py (not part of the reference-facing surface). Between begin and end,
  * lds_outer_step records a CUDA event on its stream after every kernel launch. lds_profile_end synchronises on
  * the last event and returns the number of intervals written: ms_out[i] = device time of the launch whose id is

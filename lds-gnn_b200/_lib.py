@@ -46,6 +46,7 @@ SIGNATURES = {
     "lds_outer_step_shard_buffer": (c_void_p, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32]),
     "lds_outer_step_buffer": (c_void_p, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32]),
     "lds_outer_step_factor_ld": (c_int64, [c_int32, c_int32]),
+    "lds_peer_push": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_void_p]),
     "lds_outer_step_packed_k": (c_int64, [c_int32, c_int32]),
     "lds_outer_step_operand_hp": (c_int32, [c_int32, c_int32, c_uint32]),
     "lds_outer_step_state_ld": (c_int64, [c_int32]),

@@ -67,6 +67,56 @@ class DistComm:
         self.dist.all_reduce(t, group=self.group)
         return t
 
+    # ---- gather buffers: `gather_into` fills gb.t[offset + r * chunk : offset + (r + 1) * chunk] with rank r's `local`
+    def gather_buffer(self, numel, dtype, device):
+        return GatherBuffer(torch.zeros(numel, dtype=dtype, device=device))
+
+    def gather_into(self, local, gb, offset, chunk, count=None):
+        """`local` holds `count` (default `chunk`) valid elements; equal `chunk` strides between ranks."""
+        if count is not None and count != chunk:
+            padded = local.new_zeros(chunk)
+            padded[:count] = local[:count]
+            local = padded
+        self.dist.all_gather_into_tensor(gb.t[offset:offset + self.world * chunk], local[:chunk], group=self.group)
+
+
+class GatherBuffer:
+    def __init__(self, tensor, ctx=None):
+        self.t, self.ctx = tensor, ctx
+
+
+class SymmComm(DistComm):
+    """Exchange over NVLink peer memory instead of NCCL: the gather buffers are torch symmetric memory (every rank maps
+    every peer's buffer), `gather_into` is ONE kernel of ours that stores this rank's block into all peers' buffers with
+    128-bit stores (csrc/lds_common.cu: peer_push_kernel) followed by the signal-pad barrier of the symmetric-memory
+    handle. At the sizes of this path (0.5 - 5 MB per rank) an NCCL all-gather is dominated by its launch and protocol
+    latency (~35-130 us measured, 7 per step); the push runs at NVLink store bandwidth."""
+
+    def __init__(self, n, group=None):
+        super().__init__(n, group)
+        import torch.distributed._symmetric_memory as symm_mem
+        self.symm_mem = symm_mem
+        pg = group if group is not None else self.dist.group.WORLD
+        self.group_name = pg.group_name
+        self.lib = _lib.load()
+
+    def gather_buffer(self, numel, dtype, device):
+        t = self.symm_mem.empty(int(numel), dtype=dtype, device=device)
+        t.zero_()
+        hdl = self.symm_mem.rendezvous(t, self.group_name)
+        ptrs = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64, device=device)
+        torch.cuda.synchronize()
+        hdl.barrier(channel=0)                              # everybody's buffer is zeroed before anybody pushes
+        return GatherBuffer(t, (hdl, ptrs))
+
+    def gather_into(self, local, gb, offset, chunk, count=None):
+        hdl, ptrs = gb.ctx
+        esz = local.element_size()
+        nbytes = -(-(chunk if count is None else count) * esz // 16) * 16
+        _lib.check(self.lib.lds_peer_push(local.data_ptr(), ptrs.data_ptr(), self.world, (offset + self.rank * chunk) * esz, nbytes,
+                                          K._stream()), "lds_peer_push")
+        hdl.barrier(channel=0)
+
 
 class ShardedOuterStep:
     def __init__(self, n, row0, rows, x_local, y_local, mask_local, mask_count, hidden, classes, sparse_features=None):
@@ -111,14 +161,6 @@ class ShardedOuterStep:
         return self.eng.run(theta_local, phases=phases, opnd_full=self.opnd_full, fa_full=self.fa_full, fb_full=self.fb_full,
                             c_full=self.c_full, f_full=self.f_full, **kw)
 
-    def exchange_operand(self, ph, gather_flat, gather_rows):
-        """All-gather the operand of propagation `ph` (written by the previous phase)."""
-        if self.packed and self.world_rows:
-            cnt = 2 * self.hp[ph] * self.world_rows
-            gather_flat(self.send[:cnt], self.recv[:(-(-self.n // self.world_rows)) * cnt])
-        else:
-            gather_rows(self.eng.buffer("operand"), self.opnd_full)
-
     @staticmethod
     def tensor_core_update(kw):
         return kw.get("opt_kind", _lib.OPT_SGD) == _lib.OPT_SGD and not (kw.get("k3_flags", 0) & _lib.K3_SIMT)
@@ -133,14 +175,51 @@ class ShardedOuterStep:
             self.fb_full = torch.empty((self.n, self.ldf), dtype=torch.float32, device=dev)
         return [("fa", self.fa_full), ("fb", self.fb_full)]
 
+    def _setup_comm(self, comm):
+        """Gather buffers owned by the exchange object (plain tensors for NCCL / gloo, symmetric memory for SymmComm)."""
+        if getattr(self, "_comm", None) is comm:
+            return
+        per = comm.bounds[0][1]
+        self._setup_packed(per)
+        dev = self.opnd_full.device
+        hpmax = max(self.hp.values())
+        self._half = comm.world * 2 * hpmax * per
+        self.g_opnd = comm.gather_buffer(2 * self._half, K.BF16, dev)        # double-buffered: exchange e fills half e & 1
+        self.g_f = comm.gather_buffer(comm.world * per * self.kf, K.BF16, dev)
+        self.g_c = comm.gather_buffer(comm.world * per + 4, torch.float32, dev)
+        self.f_full = self.g_f.t.view(-1, self.kf)
+        self.c_full = self.g_c.t
+        self._xchg = 0
+        self._comm = comm
+
     def run(self, theta_local, comm, lr, seed, step, dropout_p=0.0, update=True, **kw):
         """One sharded outer step on this rank. Returns a device tensor (loss, acc) of the WHOLE graph."""
         kw = dict(lr=lr, seed=seed, step=step, dropout_p=dropout_p, update=update, **kw)
-        if self.packed:
-            self._setup_packed(comm.bounds[0][1])
+        if not self.packed:
+            return self._run_legacy(theta_local, comm, kw)
+        self._setup_comm(comm)
+        per = self.world_rows
         self.phase(theta_local, _lib.PHASE_SAMPLE, **kw)
         for ph in PHASES:
-            self.exchange_operand(ph, comm.all_gather_flat, comm.all_gather_rows)
+            off = (self._xchg & 1) * self._half
+            comm.gather_into(self.send, self.g_opnd, off, 2 * self.hp[ph] * per)
+            self.recv = self.g_opnd.t[off:off + self._half]
+            self._xchg += 1
+            self.phase(theta_local, ph, **kw)
+        if self.tensor_core_update(kw):
+            comm.gather_into(self.eng.buffer("fpack").reshape(-1), self.g_f, 0, per * self.kf, count=self.rows * self.kf)
+        else:
+            for name, full in self.factor_buffers(kw):
+                comm.all_gather_rows(self.eng.buffer(name), full)
+        comm.gather_into(self.eng.buffer("cvec"), self.g_c, 0, per, count=self.rows)
+        self.phase(theta_local, _lib.PHASE_UPDATE, **kw)
+        return comm.all_reduce_sum(self.eng.scalars[:2].clone())      # after the update: not on theta's critical path
+
+    def _run_legacy(self, theta_local, comm, kw):
+        """fp32 row exchange + re-layout kernel per propagation (kept for comparison / tests)."""
+        self.phase(theta_local, _lib.PHASE_SAMPLE, **kw)
+        for ph in PHASES:
+            comm.all_gather_rows(self.eng.buffer("operand"), self.opnd_full)
             self.phase(theta_local, ph, **kw)
         scalars = comm.all_reduce_sum(self.eng.scalars[:2].clone())
         for name, full in self.factor_buffers(kw):

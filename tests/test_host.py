@@ -345,6 +345,10 @@ lo, cnt = shard_bounds(n2, 2, dist.get_rank())
 out2 = torch.empty(n2, 2)
 comm2.all_gather_rows(torch.full((cnt, 2), float(dist.get_rank())), out2)
 assert comm2.equal and out2[:256].sum() == 0 and out2[256:].sum() == 512
+# gather buffers of the packed exchange: equal chunk strides, ragged valid counts, offsets (double buffering)
+gb = comm.gather_buffer(2 * 2 * 256 + 4, torch.float32, torch.device("cpu"))
+comm.gather_into(torch.arange(lo, lo + cnt, dtype=torch.float32), gb, 512, 256, count=cnt if cnt < 256 else None)
+assert torch.equal(gb.t[512:512 + n], torch.arange(n, dtype=torch.float32)) and gb.t[:512].abs().sum() == 0
 dist.barrier()
 dist.destroy_process_group()
 print("ok")
