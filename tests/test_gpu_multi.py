@@ -1,0 +1,69 @@
+"""-m gpu tests that need TWO GPUs on the box (skipped otherwise): the sharded outer step over NCCL and over NVLink
+peer memory (torch symmetric memory + lds_peer_push) must give the same theta, bit for bit between the two exchanges
+and within fp32 summation order of the single-GPU step (the oracle of the sharded run is the unsharded one)."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dev = torch.device("cuda", rank)
+dist.init_process_group("nccl", device_id=dev)
+from lds_gnn_b200 import kernels as K, sharded as S
+n, f, h, c, p = 1500, 96, 64, 7, 0.5
+rng = np.random.default_rng(0)                                   # identical data on both ranks
+x = ((rng.random((n, f)) < 0.1) * rng.random((n, f))).astype(np.float32)
+y = rng.integers(0, c, n); mask = rng.random(n) < 0.3
+w = [torch.as_tensor((rng.standard_normal(s_) * 0.3).astype(np.float32), device=dev) for s_ in ((h, f), (h,), (c, h), (c,))]
+a = rng.random((n, n)); th = np.triu(a, 1); th = (th + th.T + np.diag(rng.random(n))).astype(np.float32)
+full0 = K.theta_triu_to_full(torch.as_tensor(th[np.triu_indices(n)], device=dev))
+xt, yt, mt = (torch.as_tensor(v, device=dev) for v in (x, y, mask))
+lo, cnt = S.shard_bounds(n, world, rank)
+results = {{}}
+for name in ("nccl", "peer"):
+    sh = S.ShardedOuterStep(n, lo, cnt, xt[lo:lo + cnt], yt[lo:lo + cnt], mt[lo:lo + cnt], int(mask.sum()), h, c)
+    sh.set_weights(*w)
+    comm = S.DistComm(n) if name == "nccl" else S.SymmComm(n)
+    theta = full0[lo:lo + cnt].clone()
+    for step in range(3):
+        sc = sh.run(theta, comm, lr=0.3, seed=7, step=step, dropout_p=p, update=True)
+    torch.cuda.synchronize()
+    results[name] = (theta, sc.clone())
+assert torch.equal(results["nccl"][0], results["peer"][0]), "the two exchanges must be bitwise identical"
+assert torch.equal(results["nccl"][1], results["peer"][1])
+# single-GPU oracle of the same three steps
+eng = K.OuterStep(n, xt, yt, mt, hidden=h, classes=c)
+eng.set_weights(*w)
+ref = full0.clone()
+for step in range(3):
+    rs = eng.run(ref, lr=0.3, seed=7, step=step, dropout_p=p, update=True)
+torch.cuda.synchronize()
+assert (results["peer"][0] - ref[lo:lo + cnt]).abs().max().item() < 2e-5
+assert abs(results["peer"][1][0].item() - rs[0].item()) < 1e-5
+dist.barrier(); dist.destroy_process_group()
+print("ok")
+"""
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs on the box")
+def test_sharded_step_nccl_and_peer_memory_exchange_agree(tmp_path):
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "multi_worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=600) for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(o[1][-3000:] for o in outs)
