@@ -43,6 +43,8 @@ extern "C" {
 #define LDS_K2_FORCE_STREAMK 4u  /* split panels across CTAs (stream-K) even when every panel could own a CTA   */
 #define LDS_K2_NO_FUSE       8u  /* lds_outer_step: never take the fused small-graph kernel (one launch per stage)   */
 #define LDS_K2_DUMP_ADJ     16u  /* lds_outer_step: the fused small-graph kernel also writes A_tilde to the workspace */
+#define LDS_K2_FORWARD_ONLY 32u  /* lds_outer_step: sample + GCN forward + loss/accuracy (+ out_logp) only: no backward,
+                                    no update — the evaluation pass of empirical_mean_loss (src/utils/evaluation.py:51-84)  */
 /* K3 flags */
 #define LDS_K3_DENSE_GRAD    1u  /* write dL/dA_tilde (dense, not symmetrised) instead of updating theta      */
 #define LDS_K3_ACCUMULATE    2u  /* with DENSE_GRAD: add into grad_out instead of overwriting                  */

@@ -11,7 +11,7 @@ from . import _build
 
 LDS_OK = 0
 K1_EXPLICIT_U = 1
-K2_SIMT, K2_SINGLE_BF16, K2_FORCE_STREAMK, K2_NO_FUSE, K2_DUMP_ADJ = 1, 2, 4, 8, 16
+K2_SIMT, K2_SINGLE_BF16, K2_FORCE_STREAMK, K2_NO_FUSE, K2_DUMP_ADJ, K2_FORWARD_ONLY = 1, 2, 4, 8, 16, 32
 K3_DENSE_GRAD, K3_ACCUMULATE, K3_SIMT = 1, 2, 4
 OPT_SGD, OPT_ADAM = 0, 1
 STREAM_EDGES, STREAM_DROP_X, STREAM_DROP_H = 0, 1, 2

@@ -269,7 +269,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
   // ================= P2: the four propagations from the resident tiles =================
   int acc_m = 0; uint32_t acc_phase_m = 0;                   // accumulator ring state of the MMA issuer
   int acc_e = 0; uint32_t acc_phase_e = 0;                   // ... and of the epilogue warps
-  for (int ph = 0; ph < 4; ++ph) {
+  for (int ph = 0; ph < fa.num_phases; ++ph) {
     if (warp == 0) {
       if (lane == 0) {                                       // the operand k-blocks of this CTA's range (all fit: no ring)
         asm volatile("fence.proxy.async;" ::: "memory");     // the operand was written with generic stores before the grid barrier
@@ -307,10 +307,20 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
       unsigned long long t;
       if (fa.timeline != nullptr) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); fa.timeline[(size_t)cta * 16 + 5 + 2 * ph] = t; }
     }
-    if (ph < 3) grid_barrier(fa.gridbar, gbase, gk, gridDim.x);
+    if (ph + 1 < fa.num_phases) grid_barrier(fa.gridbar, gbase, gk, gridDim.x);
     stamp(6 + 2 * ph);
   }
 
+  if (fa.num_phases == 2) {                                  // forward only: nobody runs the BWD2 prologue that finalises (loss, acc)
+    grid_barrier(fa.gridbar, gbase, gk, gridDim.x);
+    if (cta == 0 && tid == 0) {
+      float l = 0.f, c = 0.f;
+      for (int k = 0; k < ea.nblk; ++k) { l += ea.loss_part[k]; c += ea.corr_part[k]; }
+      const float ls = l * ea.inv_m * ea.scal_scale, cs = c * ea.inv_m * ea.scal_scale;
+      ea.out_scalars[0] = ea.scal_accumulate ? ea.out_scalars[0] + ls : ls;
+      ea.out_scalars[1] = ea.scal_accumulate ? ea.out_scalars[1] + cs : cs;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }

@@ -20,6 +20,7 @@ struct FusedSmallArgs {
   const float* w0; int64_t ldw; float* w0t; const float* b0; DropCfg dx;
   int rows_per_cta;
   // propagations
+  int num_phases;                              // 4: forward + backward; 2: forward only (layer 1, layer 2 + loss)
   K2Sched s;                                   // panel-aligned: s.kblocks is the PADDED k-range (parts * per_cta), max_seg = 1
   int kb_real;                                 // ceil(n / 64): k-blocks that exist
   float* partial; int* counters; int use_lo;

@@ -279,6 +279,17 @@ feat_sparse_kernel(const int32_t* __restrict__ crow, const int32_t* __restrict__
   store_operand_tile(tile, hp, i0, ldb, bt_hi, bt_lo);
 }
 
+// forward-only steps: sum the per-panel partials in a fixed order (what the BWD2 launch does in a training step)
+__global__ void finalize_scalars_kernel(const float* __restrict__ loss_part, const float* __restrict__ corr_part, int nblk, float inv_m,
+                                        float* __restrict__ out_scalars) {
+  if (threadIdx.x == 0) {
+    float l = 0.f, c = 0.f;
+    for (int k = 0; k < nblk; ++k) { l += loss_part[k]; c += corr_part[k]; }
+    out_scalars[0] = l * inv_m;
+    out_scalars[1] = c * inv_m;
+  }
+}
+
 }  // namespace lds
 
 using namespace lds;
@@ -380,6 +391,7 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   const uint32_t smp = S > 1 ? (uint32_t)A.sample_index : (uint32_t)(A.sample_index > 0 ? A.sample_index : 0);
   if (S > 1) {
     LDS_CHECK_ARG(A.sample_index >= 0 && A.sample_index < S, "lds_outer_step: sample_index %d outside [0, %d)", A.sample_index, S);
+    LDS_CHECK_ARG(!(A.k2_flags & LDS_K2_FORWARD_ONLY), "lds_outer_step: LDS_K2_FORWARD_ONLY is a single-sample call");
     LDS_CHECK_ARG(A.fpack_multi != nullptr && (reinterpret_cast<uintptr_t>(A.fpack_multi) & 15) == 0, "lds_outer_step: num_samples > 1 needs a 16-byte aligned fpack_multi");
     if (sharded || A.opt_kind != LDS_OPT_SGD || (A.k3_flags & LDS_K3_SIMT)) { set_error("lds_outer_step: the multi-sample estimator runs unsharded with the tensor-core SGD update"); return LDS_ERR_UNSUPPORTED; }
   }
@@ -403,6 +415,7 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
     F.deg_part = fbuf(B_DEGP); F.deg = fbuf(B_DEG); F.rs = fbuf(B_RS);
     F.crow = A.x_crow; F.xcol = A.x_col; F.xval = A.x_val; F.f = A.f;
     F.w0 = A.w0; F.ldw = A.ld_w0; F.w0t = fbuf(B_W0S); F.b0 = A.b0; F.dx = dx;
+    F.num_phases = (A.k2_flags & LDS_K2_FORWARD_ONLY) ? 2 : 4;
     F.rows_per_cta = (int)ceil_div(A.n, L.sf.grid);
     F.s = L.sf; F.kb_real = L.kb_real; F.partial = fbuf(B_PARTIAL); F.counters = counters; F.use_lo = use_lo ? 1 : 0;
     F.gridbar = reinterpret_cast<unsigned*>(buf(B_GBAR));
@@ -493,6 +506,15 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   };
   if ((rc = propagate(LDS_PHASE_LAYER1, L.s1, A.h, K2_EPI_LAYER1, 3, L.hp2)) != LDS_OK) return rc;   // Z1, H1, P2, operand (r P2)^T
   if ((rc = propagate(LDS_PHASE_LAYER2, L.s2, A.c, K2_EPI_LAYER2, 4, L.hp2)) != LDS_OK) return rc;   // Z2, log-softmax, loss, dZ2, operand (r dZ2)^T
+  const bool fwd_only = (A.k2_flags & LDS_K2_FORWARD_ONLY) != 0;
+  if (fwd_only && sharded) { set_error("lds_outer_step: LDS_K2_FORWARD_ONLY is not available for row-block shards"); return LDS_ERR_UNSUPPORTED; }
+  if (fwd_only) {
+    if (!fused_done && !sharded) {                            // (loss, acc) are normally finalised by the BWD2 launch
+      finalize_scalars_kernel<<<1, 32, 0, stream>>>(fbuf(B_LOSSP), fbuf(B_CORRP), L.panels, 1.0f / (float)A.mask_count, A.out_scalars);
+      LDS_CHECK_LAUNCH("finalize_scalars_kernel");
+    }
+    return LDS_OK;
+  }
   if ((rc = propagate(LDS_PHASE_BWD2, L.s2, A.c, K2_EPI_BWD2, 5, L.hp1)) != LDS_OK) return rc;       // dP2, dZ1, operand (r dZ1)^T; loss/acc finalised
   if ((rc = propagate(LDS_PHASE_BWD1, L.s1, A.h, K2_EPI_BWD1, 6, L.hp1)) != LDS_OK) return rc;       // dP1, c, factor matrices
 

@@ -26,21 +26,70 @@ def evaluate(model: torch.nn.Module, data, adj_matrix: torch.Tensor = None) -> D
     return result
 
 
+def _fused_eval_engine(gcn, graph_model, data):
+    """The fused forward-only route applies to the plain LDS configuration (same conditions as the trainer's fused step)."""
+    from ..models.gcn import MetaDenseGCN
+    from ..models.graph import BernoulliGraphModel
+    from ..models.sampling import Sampler
+    if type(graph_model) is not BernoulliGraphModel or graph_model.directed or not graph_model._probs_param().is_cuda:
+        return None
+    if not isinstance(gcn, MetaDenseGCN) or not getattr(gcn, "normalize_adj", False) or not data.x.is_cuda:
+        return None
+    cfg = Sampler._ingredient.values
+    if not cfg["undirected"] or cfg["sparsification"] != "NONE" or cfg["dense"]:
+        return None
+    from .. import kernels
+    h, c = gcn.layer_in.fc.out_features, gcn.layer_out.fc.out_features
+    key = (data.x.data_ptr(), tuple(data.x.shape), h, c)
+    cached = getattr(graph_model, "_eval_engine", None)
+    if cached is None or cached[0] != key:
+        eng = kernels.OuterStep(graph_model._n, data.x, data.y, data.val_mask, hidden=h, classes=c)
+        cached = (key, eng)
+        graph_model._eval_engine = cached
+    return cached[1]
+
+
 def empirical_mean_loss(gcn, graph_model, n_samples: int, data, model_parameters: OrderedDict = None) -> Tuple[Metrics, Metrics]:
     """Monte-Carlo estimate of validation / test loss and accuracy under the learned graph distribution
-    (src/utils/evaluation.py:51-84). Sampling and propagation run on the CUDA kernels (K1 + K2, forward only);
-    the 4 x n_samples scalars are reduced on the device and read back with ONE host sync instead of 64."""
+    (src/utils/evaluation.py:51-84): n_samples x {sample a graph, GCN forward in eval mode, NLL + accuracy on val and test}.
+
+    Plain LDS configuration: every sample is ONE forward-only call of the fused step (`lds_outer_step` with
+    LDS_K2_FORWARD_ONLY: sample, normalise, both propagations, log-softmax) writing its log-probabilities into one
+    [S, N, C] buffer; the 4 x S scalars are then reduced on the device in a handful of batched ops and read back with ONE
+    host sync (the reference does 64 `.item()` calls). Anything else: the reference's loop on the composable kernels."""
     gcn.eval()
     graph_model.eval()
-    rows = []
+    eng = _fused_eval_engine(gcn, graph_model, data) if n_samples > 0 else None
     with torch.no_grad():
-        for _ in range(n_samples):
-            graph = graph_model.sample()
-            predictions = gcn(data.x, graph, params=model_parameters)
-            row = []
+        if eng is not None:
+            from ..models.sampling import PHILOX
+            names = ("layer_in.fc.weight", "layer_in.fc.bias", "layer_out.fc.weight", "layer_out.fc.bias")
+            params = model_parameters if model_parameters is not None else OrderedDict(gcn.named_parameters())
+            eng.set_weights(*(params[k] for k in names))
+            theta = graph_model.theta_full()
+            n, c = graph_model._n, eng.c
+            logp = torch.empty((n_samples, n, c), dtype=torch.float32, device=theta.device)
+            for s in range(n_samples):
+                seed, step = PHILOX.next_step()
+                eng.run(theta, lr=0.0, seed=seed, step=step, dropout_p=0.0, update=False, out_logp=logp[s], want_adj=False,
+                        forward_only=True)
+            cols = []
             for mask in (data.val_mask, data.test_mask):
-                row.append(F.nll_loss(predictions[mask], data.y[mask]))
-                row.append((torch.argmax(predictions[mask], dim=-1) == data.y[mask]).float().mean())
-            rows.append(torch.stack(row))
-        table = torch.stack(rows).double().mean(dim=0).tolist()       # single device->host transfer
+                idx = mask.nonzero().flatten()
+                lp = logp[:, idx]                                                    # [S, M, C]
+                yy = data.y[idx]
+                cols.append(-lp.gather(2, yy.view(1, -1, 1).expand(n_samples, -1, 1)).squeeze(2).mean(dim=1))
+                cols.append((lp.argmax(dim=2) == yy.view(1, -1)).float().mean(dim=1))
+            table = torch.stack(cols, dim=1).double().mean(dim=0).tolist()            # single device->host transfer
+        else:
+            rows = []
+            for _ in range(n_samples):
+                graph = graph_model.sample()
+                predictions = gcn(data.x, graph, params=model_parameters)
+                row = []
+                for mask in (data.val_mask, data.test_mask):
+                    row.append(F.nll_loss(predictions[mask], data.y[mask]))
+                    row.append((torch.argmax(predictions[mask], dim=-1) == data.y[mask]).float().mean())
+                rows.append(torch.stack(row))
+            table = torch.stack(rows).double().mean(dim=0).tolist()       # single device->host transfer
     return Metrics(loss=table[0], acc=table[1]), Metrics(loss=table[2], acc=table[3])

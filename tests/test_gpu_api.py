@@ -333,3 +333,28 @@ def test_empirical_mean_loss_and_bilevel_runner_smoke():
     runner.train(patience=1, hyper_gradient_interval=2, inner_loop_max_epochs=3, outer_loop_max_epochs=1)
     out = runner.evaluate()
     assert set(out) == {"loss.val.final", "acc.val.final", "loss.test.final", "acc.test.final"}
+
+
+@pytest.mark.parametrize("case", ["n130_sparse", "n257_h64", "n96_binary"])
+def test_empirical_mean_loss_fused_forward_only_matches_the_sample_by_sample_loop(case):
+    """src/utils/evaluation.py:51-84. The fused route (one forward-only lds_outer_step per sample, batched reduction) must
+    reproduce the reference's loop run on the composable kernels with the same Philox draws."""
+    import lds_gnn_b200.utils.evaluation as E
+    from lds_gnn_b200.models.sampling import PHILOX
+    g = load_golden(case)
+    data, gcn, inner, model, outer = _setup(g, lr=0.1, lr_decay=0.99, dropout=0.5)
+    assert E._fused_eval_engine(gcn, model, data) is not None
+    PHILOX.seed, PHILOX.step = 1234, 50
+    fused = E.empirical_mean_loss(gcn, model, n_samples=5, data=data, model_parameters=inner.model_params)
+    assert PHILOX.step == 55
+    PHILOX.seed, PHILOX.step = 1234, 50
+    orig = E._fused_eval_engine
+    E._fused_eval_engine = lambda *a, **k: None            # force the reference's loop
+    try:
+        loop = E.empirical_mean_loss(gcn, model, n_samples=5, data=data, model_parameters=inner.model_params)
+    finally:
+        E._fused_eval_engine = orig
+    for a, b in zip(fused, loop):
+        assert abs(a.loss - b.loss) < 2e-5 * max(1.0, abs(b.loss)), (a, b)
+        assert abs(a.acc - b.acc) < 1e-6, (a, b)
+    assert gcn.training is False
