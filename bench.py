@@ -272,18 +272,32 @@ def run_ours(args, rank, world, device):
     # slices ARE the fast-weight tensors handed to the trainer, one host->device copy per step.
     total = sum(v.numel() for v in weights.values())
     host_flat = torch.empty(total, dtype=torch.float32).pin_memory()
-    dev_flat = torch.empty(total, dtype=torch.float32, device=device)
+    # Two device copies of the weights, alternated: train_step returns as soon as (loss, acc) exist, i.e. while the backward
+    # half of the step (which still reads layer_out's weights) and the theta update are running; the next step's upload is
+    # ordered behind them by the stream, and writes the OTHER buffer so that user code touching the weights stays simple.
+    dev_flats = [torch.empty(total, dtype=torch.float32, device=device) for _ in range(2)]
+    param_sets = []
     off = 0
     for k, pname in names.items():
         cnt = weights[k].numel()
         host_flat[off:off + cnt].copy_(weights[k].reshape(-1))
-        inner.model_params[pname] = dev_flat[off:off + cnt].view(weights[k].shape)
         off += cnt
+    for buf in dev_flats:
+        views, off = {}, 0
+        for k, pname in names.items():
+            cnt = weights[k].numel()
+            views[pname] = buf[off:off + cnt].view(weights[k].shape)
+            off += cnt
+        param_sets.append(views)
     h2d_bytes = total * 4
+    state = {"i": 0}
 
     def api_step():
-        dev_flat.copy_(host_flat, non_blocking=True)       # this step's fast weights: pinned host -> device
-        return outer.train_step(inner.model_forward)       # returns host floats (device -> host read inside)
+        i = state["i"] & 1
+        state["i"] += 1
+        dev_flats[i].copy_(host_flat, non_blocking=True)       # this step's fast weights: pinned host -> device
+        inner.model_params.update(param_sets[i])
+        return outer.train_step(inner.model_forward)           # returns host floats (device -> host read inside)
 
     for _ in range(args.warmup):
         api_step()

@@ -163,7 +163,7 @@ typedef struct lds_outer_step_args {
   int32_t  opt_kind;          /* LDS_OPT_*                                                              */
   float*   adam_m; float* adam_v; float beta1, beta2, eps; int32_t adam_t;
   int32_t  update;            /* 1: apply K3+K4; 0: forward + backward factors only                     */
-  float*   out_scalars;       /* [4] fp32: loss, accuracy, reserved, reserved                            */
+  float*   out_scalars;       /* [4] fp32: loss, accuracy, scalars_tag (see below), reserved             */
   float*   out_logp;          /* optional [n][c] log-probabilities, else NULL                           */
   void*    workspace; int64_t workspace_bytes;
   uint32_t k2_flags;          /* LDS_K2_* for the four propagations                                      */
@@ -204,6 +204,11 @@ typedef struct lds_outer_step_args {
    * tensor map, so no re-layout kernel runs. opnd_rank_rows = rows per rank (a multiple of 64, the same on every rank). */
   void*    opnd_send;
   int32_t  opnd_rank_rows, reserved3;
+  /* ---- early result. scalars_tag != 0 (unsharded calls): once (loss, acc) are final — after the second propagation, i.e.
+   * before the backward half and the update have run — the kernel writes them, a system-scope fence, then the tag into
+   * out_scalars[2]. With out_scalars in pinned host memory the host can poll for the tag and return the step's metrics while
+   * the rest of the step is still executing; everything later stays ordered by the stream. */
+  float    scalars_tag; float reserved4;
 } lds_outer_step_args;
 
 #define LDS_PHASE_SAMPLE   1u

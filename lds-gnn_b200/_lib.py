@@ -82,6 +82,7 @@ class OuterStepArgs(Structure):
         ("f_full", c_void_p), ("k2_timeline", c_void_p),
         ("num_samples", c_int32), ("sample_index", c_int32), ("fpack_multi", c_void_p),
         ("opnd_send", c_void_p), ("opnd_rank_rows", c_int32), ("reserved3", c_int32),
+        ("scalars_tag", c_float), ("reserved4", c_float),
     ]
 
 

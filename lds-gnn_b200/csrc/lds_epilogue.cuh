@@ -63,6 +63,8 @@ struct EpiArgs {
   int64_t ld_fpack;                    // row i at fpack + i * ld_fpack, kf columns (multi-sample: column block s of [n][S * kf])
   int c_accumulate;                    // multi-sample: cvec += instead of =
   float scal_scale; int scal_accumulate;   // (loss, acc) *= scal_scale, added to out_scalars instead of stored (multi-sample mean)
+  float scal_tag;                          // != 0: written to out_scalars[2] AFTER (loss, acc) with a system-scope fence, so a host that
+                                           // polls pinned out_scalars sees the step's result as soon as it exists (lds_outer_step_args)
   float* cvec;
   const float* w1; const float* b1;
   const int64_t* y; const uint8_t* mask; float inv_m;
@@ -74,6 +76,16 @@ struct EpiArgs {
   // K2_EPI_PLAIN (standalone lds_k2_propagate)
   float* z_out; int64_t ld_z; const float* scale_out; int rows; int width;
 };
+
+// (loss, acc) of the step from the per-panel partials, fixed order. One thread.
+__device__ __forceinline__ void finalize_scalars(const EpiArgs& ea) {
+  float l = 0.f, c = 0.f;
+  for (int k = 0; k < ea.nblk; ++k) { l += ea.loss_part[k]; c += ea.corr_part[k]; }
+  const float ls = l * ea.inv_m * ea.scal_scale, cs = c * ea.inv_m * ea.scal_scale;
+  ea.out_scalars[0] = ea.scal_accumulate ? ea.out_scalars[0] + ls : ls;
+  ea.out_scalars[1] = ea.scal_accumulate ? ea.out_scalars[1] + cs : cs;
+  if (ea.scal_tag != 0.f) { __threadfence_system(); ea.out_scalars[2] = ea.scal_tag; }
+}
 
 __device__ __forceinline__ float quad_sum(float v) {           // fixed order: (x0 + x1) + (x2 + x3) seen from every lane
   v += __shfl_xor_sync(0xffffffffu, v, 1);

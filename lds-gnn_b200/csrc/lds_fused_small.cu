@@ -313,13 +313,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
 
   if (fa.num_phases == 2) {                                  // forward only: nobody runs the BWD2 prologue that finalises (loss, acc)
     grid_barrier(fa.gridbar, gbase, gk, gridDim.x);
-    if (cta == 0 && tid == 0) {
-      float l = 0.f, c = 0.f;
-      for (int k = 0; k < ea.nblk; ++k) { l += ea.loss_part[k]; c += ea.corr_part[k]; }
-      const float ls = l * ea.inv_m * ea.scal_scale, cs = c * ea.inv_m * ea.scal_scale;
-      ea.out_scalars[0] = ea.scal_accumulate ? ea.out_scalars[0] + ls : ls;
-      ea.out_scalars[1] = ea.scal_accumulate ? ea.out_scalars[1] + cs : cs;
-    }
+    if (cta == 0 && tid == 0) finalize_scalars(ea);
   }
   tc_fence_before();
   __syncthreads();

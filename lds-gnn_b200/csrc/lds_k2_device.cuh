@@ -38,13 +38,7 @@ __device__ __forceinline__ void k2_epilogue_loop(const K2Sched& s, const EpiArgs
       }
     };
     stamp(0);                                                // epilogue warps past the setup barrier
-    if (EPI == K2_EPI_BWD2 && cta == 0 && etid == 0) {       // the layer-2 launch is complete: finalise loss / accuracy
-      float l = 0.f, c = 0.f;
-      for (int k = 0; k < ea.nblk; ++k) { l += ea.loss_part[k]; c += ea.corr_part[k]; }
-      const float ls = l * ea.inv_m * ea.scal_scale, cs = c * ea.inv_m * ea.scal_scale;
-      ea.out_scalars[0] = ea.scal_accumulate ? ea.out_scalars[0] + ls : ls;
-      ea.out_scalars[1] = ea.scal_accumulate ? ea.out_scalars[1] + cs : cs;
-    }
+    if (EPI == K2_EPI_BWD2 && cta == 0 && etid == 0) finalize_scalars(ea);   // the layer-2 launch / phase is complete
     int seg = 0;
     for (int pos = lo; pos < hi; ++seg) {
       const int p = pos / s.kblocks, kb0 = pos - p * s.kblocks;

@@ -280,14 +280,8 @@ feat_sparse_kernel(const int32_t* __restrict__ crow, const int32_t* __restrict__
 }
 
 // forward-only steps: sum the per-panel partials in a fixed order (what the BWD2 launch does in a training step)
-__global__ void finalize_scalars_kernel(const float* __restrict__ loss_part, const float* __restrict__ corr_part, int nblk, float inv_m,
-                                        float* __restrict__ out_scalars) {
-  if (threadIdx.x == 0) {
-    float l = 0.f, c = 0.f;
-    for (int k = 0; k < nblk; ++k) { l += loss_part[k]; c += corr_part[k]; }
-    out_scalars[0] = l * inv_m;
-    out_scalars[1] = c * inv_m;
-  }
+__global__ void finalize_scalars_kernel(const __grid_constant__ EpiArgs ea) {
+  if (threadIdx.x == 0) finalize_scalars(ea);
 }
 
 }  // namespace lds
@@ -430,6 +424,7 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
     else { E.fa = fbuf(B_FA); E.fb = fbuf(B_FB); }
     if (S > 1) { E.fpack = reinterpret_cast<__nv_bfloat16*>(A.fpack_multi) + (int64_t)smp * L.kf; E.ld_fpack = (int64_t)S * L.kf; }
     E.c_accumulate = (S > 1 && smp > 0) ? 1 : 0; E.scal_scale = 1.0f / (float)S; E.scal_accumulate = E.c_accumulate;
+    E.scal_tag = ((int)smp == S - 1) ? A.scalars_tag : 0.f;
     E.w1 = A.w1; E.b1 = A.b1; E.y = A.y; E.mask = A.mask; E.inv_m = 1.0f / (float)A.mask_count;
     E.drop_h = dh; E.bt_hi = bt_hi; E.bt_lo = bt_lo; E.ldb = L.ldb;
     E.loss_part = fbuf(B_LOSSP); E.corr_part = fbuf(B_CORRP); E.nblk = L.panels;
@@ -477,6 +472,7 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   else { E.fa = fbuf(B_FA); E.fb = fbuf(B_FB); }
   if (S > 1) { E.fpack = reinterpret_cast<__nv_bfloat16*>(A.fpack_multi) + (int64_t)smp * L.kf; E.ld_fpack = (int64_t)S * L.kf; }
   E.c_accumulate = (S > 1 && smp > 0) ? 1 : 0; E.scal_scale = 1.0f / (float)S; E.scal_accumulate = E.c_accumulate;
+  E.scal_tag = (!sharded && (int)smp == S - 1) ? A.scalars_tag : 0.f;
   E.w1 = A.w1; E.b1 = A.b1; E.y = A.y; E.mask = A.mask; E.inv_m = 1.0f / (float)A.mask_count;
   E.drop_h = dh; E.bt_hi = bt_hi; E.bt_lo = bt_lo; E.ldb = L.ldb;
   E.loss_part = fbuf(B_LOSSP); E.corr_part = fbuf(B_CORRP); E.nblk = L.panels;
@@ -510,7 +506,7 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   if (fwd_only && sharded) { set_error("lds_outer_step: LDS_K2_FORWARD_ONLY is not available for row-block shards"); return LDS_ERR_UNSUPPORTED; }
   if (fwd_only) {
     if (!fused_done && !sharded) {                            // (loss, acc) are normally finalised by the BWD2 launch
-      finalize_scalars_kernel<<<1, 32, 0, stream>>>(fbuf(B_LOSSP), fbuf(B_CORRP), L.panels, 1.0f / (float)A.mask_count, A.out_scalars);
+      finalize_scalars_kernel<<<1, 32, 0, stream>>>(E);
       LDS_CHECK_LAUNCH("finalize_scalars_kernel");
     }
     return LDS_OK;

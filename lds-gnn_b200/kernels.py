@@ -325,7 +325,7 @@ class OuterStep:
     def run(self, theta_full, lr, seed, step, dropout_p=0.0, update=True, u=None, keep_x=None, keep_h=None,
             opt_kind=_lib.OPT_SGD, adam_m=None, adam_v=None, betas=(0.9, 0.999), eps=1e-8, adam_t=1,
             out_logp=None, k2_flags=0, k3_flags=0, phases=None, opnd_full=None, fa_full=None, fb_full=None, c_full=None,
-            f_full=None, k2_timeline=None, scalars_out=None, want_adj=True, sample=0, num_samples=1, fpack_multi=None, opnd_send=None, opnd_rank_rows=0, forward_only=False):
+            f_full=None, k2_timeline=None, scalars_out=None, want_adj=True, sample=0, num_samples=1, fpack_multi=None, opnd_send=None, opnd_rank_rows=0, forward_only=False, scalars_tag=0.0):
         """Enqueue one fused outer step on the current stream. Results: (loss, acc) in `scalars_out[0:2]` (any fp32
         buffer the device can write, e.g. pinned host memory) or, by default, in self.scalars.
         `want_adj`: keep the sampled A_tilde readable through buffer("adj") — small graphs run a fused kernel whose A_tilde
@@ -345,6 +345,7 @@ class OuterStep:
         a.fpack_multi = None if fpack_multi is None else fpack_multi.data_ptr()
         a.opnd_send = None if opnd_send is None else opnd_send.data_ptr()
         a.opnd_rank_rows = int(opnd_rank_rows)
+        a.scalars_tag = float(scalars_tag)
         plain = (u is None and keep_x is None and keep_h is None and adam_m is None and out_logp is None and not k2_flags
                  and not k3_flags and opnd_full is None and fa_full is None and c_full is None and f_full is None
                  and k2_timeline is None and scalars_out is None)

@@ -192,24 +192,37 @@ class OuterProblemTrainer:
             st["t"] += 1
             extra = dict(adam_m=st["m"], adam_v=st["v"], betas=group["betas"], eps=group["eps"], adam_t=st["t"])
         seed, step = PHILOX.next_step()
-        # (loss, acc) land in pinned host memory, written by the step's own kernel: the step's one device->host
-        # transfer is those 8 bytes, and the host only waits for the stream.
+        # (loss, acc) land in pinned host memory, written by the step's own kernel as soon as they are final (after the
+        # second propagation), followed by a tag; the host polls for the tag and returns the metrics while the backward
+        # half and the theta update are still running. Everything later is ordered by the stream.
         if self._host_scalars is None:
             self._host_scalars = torch.zeros(4, dtype=torch.float32).pin_memory()
+            self._host_view = self._host_scalars.numpy()      # shares the pinned memory
+            self._tag = 0
+        self._tag = self._tag % 1000000 + 1                   # exactly representable in fp32, never 0
+        tag = float(self._tag)
         if self.n_samples > 1:
             if kind != _lib.OPT_SGD:
                 raise NotImplementedError("n_samples > 1 is implemented for the SGD outer optimiser (models/factory.py:66-69)")
             eng.run_multi(theta, self.n_samples, lr=group["lr"], seed=seed, step=step, dropout_p=float(gcn.dropout),
-                          update=True, scalars_out=self._host_scalars, want_adj=False)
+                          update=True, scalars_out=self._host_scalars, want_adj=False, scalars_tag=tag)
         else:
             eng.run(theta, lr=group["lr"], seed=seed, step=step, dropout_p=float(gcn.dropout),
-                    update=True, opt_kind=kind, scalars_out=self._host_scalars, want_adj=False, **extra)
+                    update=True, opt_kind=kind, scalars_out=self._host_scalars, want_adj=False, scalars_tag=tag, **extra)
         model.mark_full_updated()
         if self.lr_decayer is not None:
             self.optimizer._opt_called = True             # the update ran in the kernel; keeps StepLR's order check quiet
             self.lr_decayer.step()
-        torch.cuda.current_stream().synchronize()
-        loss, acc = self._host_scalars[:2].tolist()
+        hv = self._host_view
+        spins = 0
+        while hv[2] != tag:
+            spins += 1
+            if spins > 200000:                            # ~50 ms of polling: let the stream report what happened
+                torch.cuda.current_stream().synchronize()
+                if hv[2] != tag:
+                    raise RuntimeError("lds_outer_step finished without publishing its metrics")
+                break
+        loss, acc = float(hv[0]), float(hv[1])
         return Metrics(loss=loss, acc=acc)
 
     # ------------------------------------------------------------------------------------------ rest of the API
