@@ -17,6 +17,7 @@
 //
 // The theta update (K3+K4) stays its own launch. Reference semantics: see lds_k1_sample.cu, lds_outer_step.cu and
 // lds_epilogue.cuh (src/models/sampling.py:47-85, src/utils/graph.py:123-153, src/models/gcn.py:23-34).
+#include <stdlib.h>
 #include <string.h>
 #include "lds_fused_small.cuh"
 #include "lds_k2_device.cuh"
@@ -61,6 +62,25 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned base, unsig
   ++k;
 }
 
+// ---- thread-block cluster helpers (CLUSTER variant: the CTAs of one 128-row panel form a cluster) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {          // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(cta_rank));
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote) : "memory");
+  return v;
+}
+
+// CLUSTER = true: launched with cluster dimension = CTAs per panel. The split-K partial tiles of a panel stay in the
+// shared memory of the CTAs that produced them (in the operand buffer, idle once the MMAs have retired); after a
+// cluster barrier the cluster's rank-0 CTA sums them over DISTRIBUTED shared memory in rank order (deterministic) and
+// runs the row epilogue. No partial tile, fence or arrival counter goes through L2: that chain was ~40 % of a phase.
+template <bool CLUSTER>
 __global__ void __launch_bounds__(K2_THREADS, 1)
 fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo,
                    const __grid_constant__ FusedSmallArgs fa) {
@@ -297,11 +317,63 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
         tc_commit(&tfull_bar[acc_m]);
         if (++acc_m == 2) { acc_m = 0; acc_phase_m ^= 1; }
       }
-    } else {
+    } else if (!CLUSTER) {
       if (ph == 0) k2_epilogue_loop<FS_HP, K2_EPI_LAYER1, true>(s, ea, fa.partial, fa.counters, cta, lo, hi, tmem_base, tfull_bar, tempty_bar, acc_e, acc_phase_e, sh_epi, fa.use_lo != 0);
       else if (ph == 1) k2_epilogue_loop<FS_HP, K2_EPI_LAYER2, true>(s, ea, fa.partial, fa.counters, cta, lo, hi, tmem_base, tfull_bar, tempty_bar, acc_e, acc_phase_e, sh_epi, fa.use_lo != 0);
       else if (ph == 2) k2_epilogue_loop<FS_HP, K2_EPI_BWD2, true>(s, ea, fa.partial, fa.counters, cta, lo, hi, tmem_base, tfull_bar, tempty_bar, acc_e, acc_phase_e, sh_epi, fa.use_lo != 0);
       else k2_epilogue_loop<FS_HP, K2_EPI_BWD1, true>(s, ea, fa.partial, fa.counters, cta, lo, hi, tmem_base, tfull_bar, tempty_bar, acc_e, acc_phase_e, sh_epi, fa.use_lo != 0);
+    } else if (warp < 6) {
+      // CLUSTER: drain this CTA's accumulator into its own shared memory (the operand buffer is idle: the MMAs have retired)
+      if (ph == 2 && cta == 0 && tid == 64) finalize_scalars(ea);   // the layer-2 phase is complete: (loss, acc)
+      mbar_wait(&tfull_bar[acc_e], acc_phase_e);
+      tc_fence_after();
+      const int quarter = warp & 3, row = quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc_e * 2 * FS_HP);
+      uint32_t t16[16], u16[16];
+      tc_ld16(taddr, t16);
+      tc_ld16(taddr + FS_HP, u16);
+      tc_wait_ld();
+      if (fa.use_lo) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) t16[q] = __float_as_uint(__uint_as_float(t16[q]) + __uint_as_float(u16[q]));
+      }
+      uint4* dst = reinterpret_cast<uint4*>(sb + row * (FS_HP * 4));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dst[q] = make_uint4(t16[4 * q], t16[4 * q + 1], t16[4 * q + 2], t16[4 * q + 3]);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc_e]);
+      if (++acc_e == 2) { acc_e = 0; acc_phase_e ^= 1; }
+    }
+    if (CLUSTER) {
+      cluster_sync_all();                                      // every CTA's partial tile is in its shared memory
+      if (cluster_ctarank() == 0 && warp >= 2) {
+        const int etid = tid - 64, row = etid >> 2, g = etid & 3;    // four threads per row, a quarter of the columns each
+        const uint32_t mine = smem_u32(sb) + (uint32_t)(row * FS_HP + g * 4) * 4u;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        float4 t[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) if (r < fa.parts) t[r] = ld_dsmem_f4(mine, (uint32_t)r);       // all in flight, then a fixed-order sum
+#pragma unroll
+        for (int r = 0; r < 8; ++r) if (r < fa.parts) { v[0] += t[r].x; v[1] += t[r].y; v[2] += t[r].z; v[3] += t[r].w; }
+        const int i = my_p * K2_BLOCK_M + row;
+        if (ph == 0) epi_layer1<FS_HP>(ea, i, g, v);
+        else if (ph == 2) epi_bwd2<FS_HP>(ea, i, g, v);
+        else if (ph == 3) epi_bwd1<FS_HP>(ea, i, g, v);
+        else {
+          float li, ci;
+          epi_layer2<FS_HP>(ea, i, g, v, li, ci);
+          li = warp_sum(li); ci = warp_sum(ci);
+          if (lane == 0) { sh_epi.red[warp - 2][0] = li; sh_epi.red[warp - 2][1] = ci; }
+          named_bar_sync(2, 512);
+          if (etid == 0) {
+            float l = 0.f, c = 0.f;
+            for (int w = 0; w < 16; ++w) { l += sh_epi.red[w][0]; c += sh_epi.red[w][1]; }   // fixed order
+            ea.loss_part[my_p] = l;
+            ea.corr_part[my_p] = c;
+          }
+        }
+      }
     }
     if (tid == 64) {                                           // first epilogue thread: its loop is done
       unsigned long long t;
@@ -311,6 +383,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
     stamp(6 + 2 * ph);
   }
 
+  if (CLUSTER) cluster_sync_all();                           // nobody exits while the cluster leader still reads its shared memory
   if (fa.num_phases == 2) {                                  // forward only: nobody runs the BWD2 prologue that finalises (loss, acc)
     grid_barrier(fa.gridbar, gbase, gk, gridDim.x);
     if (cta == 0 && tid == 0) finalize_scalars(ea);
@@ -335,25 +408,58 @@ bool fused_small_schedule(int n, int hp1, int hp2, K2Sched& s, int& kb_real) {
   return true;
 }
 
-int32_t fused_small_launch(const FusedSmallArgs& fa, cudaStream_t stream) {
+// How many clusters of `cs` CTAs of the CLUSTER kernel can be resident at once (cached per cluster size; 0 = cannot).
+static int max_active_clusters(int cs) {
+  static int cache[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
+  if (cs < 1 || cs > 8) return 0;
+  if (cache[cs] >= 0) return cache[cs];
+  int n = 0;
+  if (cudaFuncSetAttribute(fused_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM) == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(cs * 32)); cfg.blockDim = dim3(K2_THREADS); cfg.dynamicSmemBytes = FS_SMEM;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, fused_small_kernel<true>, &cfg) != cudaSuccess) n = 0;
+  }
+  (void)cudaGetLastError();
+  cache[cs] = n;
+  return n;
+}
+
+int32_t fused_small_launch(const FusedSmallArgs& fa_in, cudaStream_t stream, bool allow_cluster) {
   static int coop = -1;
   if (coop < 0) {
     int dev = 0, v = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess) v = 0;
-    if (v && num_sms() < fa.s.grid) v = 0;
+    if (v && num_sms() < fa_in.s.grid) v = 0;
     if (v) {
-      if (cudaFuncSetAttribute(fused_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM) != cudaSuccess) v = 0;
+      if (cudaFuncSetAttribute(fused_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM) != cudaSuccess) v = 0;
     }
     (void)cudaGetLastError();
     coop = v;
   }
-  if (!coop) return LDS_ERR_UNSUPPORTED;                     // the caller falls back to the multi-kernel path
+  if (!coop || num_sms() < fa_in.s.grid) return LDS_ERR_UNSUPPORTED;   // the caller falls back to the multi-kernel path
+  FusedSmallArgs fa = fa_in;
+  fa.parts = fa.s.grid / fa.s.panels;
   CUtensorMap tbh, tbl;
   int32_t rc;
   if ((rc = make_tmap_2d(&tbh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, fa.ea.bt_hi, fa.n, FS_HP, fa.ea.ldb, K2_BLOCK_K, FS_HP)) != LDS_OK) return rc;
   if ((rc = make_tmap_2d(&tbl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, fa.ea.bt_lo, fa.n, FS_HP, fa.ea.ldb, K2_BLOCK_K, FS_HP)) != LDS_OK) return rc;
   void* params[] = {(void*)&tbh, (void*)&tbl, (void*)&fa};
-  LDS_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)fused_small_kernel, dim3((unsigned)fa.s.grid), dim3(K2_THREADS), params, FS_SMEM, stream));
+  static const bool env_no_cluster = getenv("LDS_FUSED_NO_CLUSTER") != nullptr;      // A/B switch for measurements
+  const bool cluster = allow_cluster && !env_no_cluster && fa.parts >= 2 && fa.parts <= 8 && max_active_clusters(fa.parts) >= fa.s.panels;
+  if (cluster) {                                             // one cluster per panel: reduction over distributed shared memory
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)fa.s.grid); cfg.blockDim = dim3(K2_THREADS); cfg.dynamicSmemBytes = FS_SMEM; cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)fa.parts; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 2;
+    LDS_CHECK_CUDA(cudaLaunchKernelExC(&cfg, (const void*)fused_small_kernel<true>, params));
+    return LDS_OK;
+  }
+  LDS_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)fused_small_kernel<false>, dim3((unsigned)fa.s.grid), dim3(K2_THREADS), params, FS_SMEM, stream));
   return LDS_OK;
 }
 

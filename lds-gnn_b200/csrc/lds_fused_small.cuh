@@ -23,6 +23,7 @@ struct FusedSmallArgs {
   int num_phases;                              // 4: forward + backward; 2: forward only (layer 1, layer 2 + loss)
   K2Sched s;                                   // panel-aligned: s.kblocks is the PADDED k-range (parts * per_cta), max_seg = 1
   int kb_real;                                 // ceil(n / 64): k-blocks that exist
+  int parts;                                   // CTAs per panel (= cluster size of the CLUSTER variant); set by the launcher
   float* partial; int* counters; int use_lo;
   unsigned* gridbar;                           // {arrival count (zero between launches), generation}
   unsigned long long* timeline;                // optional debug: [grid][16] %globaltimer stamps per CTA, else NULL
@@ -33,6 +34,8 @@ struct FusedSmallArgs {
 // Returns false when the graph does not fit (more than FS_MAX_TILES tiles per CTA on 148 SMs) or h, c > 16.
 bool fused_small_schedule(int n, int hp1, int hp2, K2Sched& s, int& kb_real);
 // LDS_ERR_UNSUPPORTED when the device cannot run the cooperative launch: the caller uses the multi-kernel path.
-int32_t fused_small_launch(const FusedSmallArgs& fa, cudaStream_t stream);
+// allow_cluster: use the thread-block-cluster variant (split-K reduction over distributed shared memory) when the device can
+// keep one cluster per panel resident.
+int32_t fused_small_launch(const FusedSmallArgs& fa, cudaStream_t stream, bool allow_cluster = true);
 
 }  // namespace lds
