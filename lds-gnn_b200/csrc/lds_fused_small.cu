@@ -448,7 +448,8 @@ int32_t fused_small_launch(const FusedSmallArgs& fa_in, cudaStream_t stream, boo
   if ((rc = make_tmap_2d(&tbl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, fa.ea.bt_lo, fa.n, FS_HP, fa.ea.ldb, K2_BLOCK_K, FS_HP)) != LDS_OK) return rc;
   void* params[] = {(void*)&tbh, (void*)&tbl, (void*)&fa};
   static const bool env_no_cluster = getenv("LDS_FUSED_NO_CLUSTER") != nullptr;      // A/B switch for measurements
-  const bool cluster = allow_cluster && !env_no_cluster && fa.parts >= 2 && fa.parts <= 8 && max_active_clusters(fa.parts) >= fa.s.panels;
+  static bool cluster_broken = false;
+  const bool cluster = allow_cluster && !env_no_cluster && !cluster_broken && fa.parts >= 2 && fa.parts <= 8 && max_active_clusters(fa.parts) >= fa.s.panels;
   if (cluster) {                                             // one cluster per panel: reduction over distributed shared memory
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)fa.s.grid); cfg.blockDim = dim3(K2_THREADS); cfg.dynamicSmemBytes = FS_SMEM; cfg.stream = stream;
@@ -456,8 +457,9 @@ int32_t fused_small_launch(const FusedSmallArgs& fa_in, cudaStream_t stream, boo
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)fa.parts; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 2;
-    LDS_CHECK_CUDA(cudaLaunchKernelExC(&cfg, (const void*)fused_small_kernel<true>, params));
-    return LDS_OK;
+    if (cudaLaunchKernelExC(&cfg, (const void*)fused_small_kernel<true>, params) == cudaSuccess) return LDS_OK;
+    (void)cudaGetLastError();                                // e.g. the device cannot co-schedule the clusters after all:
+    cluster_broken = true;                                   // use the variant without clusters from now on
   }
   LDS_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)fused_small_kernel<false>, dim3((unsigned)fa.s.grid), dim3(K2_THREADS), params, FS_SMEM, stream));
   return LDS_OK;
