@@ -1,22 +1,27 @@
 #!/usr/bin/env python
 """bench.py — LDS outer steps/s on B200 (BASELINE.json metric), one JSON line on stdout.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload citeseer|cora|tiny] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload citeseer|cora|cora_knn16|tiny|n20k|n65k] [--impl ours|reference]
 
 A "step" is one direct outer step (OuterProblemTrainer.train_step with model_forward at fixed GCN weights,
-SGD, one sample, dropout 0.5; reference src/trainers/outer.py:57-87) on synthetic data of the named shape.
+SGD, dropout 0.5; reference src/trainers/outer.py:57-87) on synthetic data of the named shape. Default workload:
+Citeseer shape (BASELINE.json configs[1]); cora_knn16 = config 3 (kNN theta_0, 16 samples per step), n20k = config 4.
   value     device-resident throughput: K calls of the fused C entry point `lds_outer_step`, theta / X / weights
             already in HBM, each step timed with CUDA events on the launching stream, L2 flushed between steps.
   e2e       the same metric through the reference-facing API `OuterProblemTrainer.train_step(inner.model_forward)`:
             every step copies that step's GCN weights from pinned host memory to the device and reads Metrics
-            (loss, acc) back to the host; wall clock between two device synchronisations.
+            (loss, acc) back to the host (written by the kernel into pinned memory); wall clock between two device
+            synchronisations.
   roofline  the dominant kernel of the step (by device time, per-kernel CUDA events recorded inside the library
-            on the launching stream): algorithmic bytes per launch / its mean duration vs the measured HBM peak.
+            on the launching stream): algorithmic bytes per launch / its mean duration vs the measured HBM peak;
+            `traffic` = DRAM bytes of that kernel from the committed ncu capture (profiles/ncu_traffic.json).
   cpu_baseline  the oracle's torch/CPU port of the reference's own op sequence, timed on this box's host cores
             (rank 0, N=1 only), a bounded sample of the same workload.
 --impl reference times that CPU port for K steps and prints the same line with "impl": "reference".
-N > 1 (torchrun): replicas only this round — every rank runs the same single-GPU workload on its own theta
-(no data-path collective), value = sum of units / max-over-ranks time, "scaling": "weak".
+N > 1 (torchrun): BASELINE.json config 5 — N = 65 536 with theta / A_tilde row-block sharded over the ranks ("scaling":
+"strong"; the operand / factor exchange runs over NVLink peer memory, NCCL as fallback; LDS_EXCHANGE=nccl forces NCCL).
+Each line carries `scaling_reference`: the same step on one GPU measured in the same run. `--replicas` runs N independent
+single-GPU replicas of the default workload instead (weak scaling, no data-path collective).
 """
 import argparse
 import ctypes
