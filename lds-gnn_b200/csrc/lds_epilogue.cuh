@@ -69,7 +69,8 @@ struct EpiArgs {
   const float* w1; const float* b1;
   const int64_t* y; const uint8_t* mask; float inv_m;
   DropCfg drop_h;
-  __nv_bfloat16* bt_hi; __nv_bfloat16* bt_lo; int64_t ldb;
+  __nv_bfloat16* bt_hi; __nv_bfloat16* bt_lo; int64_t ldb;       // where the NEXT propagation's operand is written: never the
+  __nv_bfloat16* bt_hi_alt; __nv_bfloat16* bt_lo_alt;            // buffer the current one is still reading (ping-pong; `alt` selects)
   float* loss_part; float* corr_part; int nblk;       // one partial per 128-row panel
   float* out_scalars; float* out_logp;
   unsigned long long* timeline;   // optional debug: [grid][8] globaltimer stamps per CTA (scripts/k2_timeline.py), else NULL
@@ -93,12 +94,12 @@ __device__ __forceinline__ float quad_sum(float v) {           // fixed order: (
   return v;
 }
 
-__device__ __forceinline__ void store_operand(const EpiArgs& a, int c, int i, float v) {
+__device__ __forceinline__ void store_operand(const EpiArgs& a, bool alt, int c, int i, float v) {
   if (a.opnd) { a.opnd[(int64_t)i * a.ld_opnd + c] = v; return; }
   __nv_bfloat16 hi, lo;
   split_bf16(v, hi, lo);
-  a.bt_hi[(int64_t)c * a.ldb + i] = hi;
-  a.bt_lo[(int64_t)c * a.ldb + i] = lo;
+  (alt ? a.bt_hi_alt : a.bt_hi)[(int64_t)c * a.ldb + i] = hi;
+  (alt ? a.bt_lo_alt : a.bt_lo)[(int64_t)c * a.ldb + i] = lo;
 }
 
 // In every function: i = row (may be >= a.n in the last panel: `live` guards the memory traffic, the shuffles are
@@ -116,7 +117,7 @@ __device__ __forceinline__ void epi_plain(const EpiArgs& a, int i, int g, const 
 
 // ---- layer 1: Z1 = r * sum, H1 = relu, dropout, P2 = H1' W1^T + b1, operand (r * P2)^T      (gcn.py:28-30, layers.py:43)
 template <int HP>
-__device__ __forceinline__ void epi_layer1(const EpiArgs& a, int i, int g, float (&v)[HP / 4]) {
+__device__ __forceinline__ void epi_layer1(const EpiArgs& a, int i, int g, float (&v)[HP / 4], bool alt = false) {
   constexpr int Q = HP / 4;
   const bool live = i < a.n;
   const int il = live ? i : a.n - 1;
@@ -152,7 +153,7 @@ __device__ __forceinline__ void epi_layer1(const EpiArgs& a, int i, int g, float
     if (live && o < a.c) {
       const float acc = mine + a.b1[o];
       a.p2[(int64_t)o * a.ldr + i] = acc;
-      store_operand(a, o, i, ri * acc);
+      store_operand(a, alt, o, i, ri * acc);
     }
   }
   // operand rows >= C are left as they are: column c of the product depends on operand row c only, and no epilogue
@@ -162,7 +163,7 @@ __device__ __forceinline__ void epi_layer1(const EpiArgs& a, int i, int g, float
 // ---- layer 2: Z2 = r * sum, log_softmax, masked NLL + accuracy, dZ2, operand (r * dZ2)^T     (gcn.py:34, outer.py:65-67)
 // Returns this thread's (loss, correct) contribution (non-zero on one lane of the quad); the caller reduces over the panel.
 template <int HP>
-__device__ __forceinline__ void epi_layer2(const EpiArgs& a, int i, int g, float (&v)[HP / 4], float& loss_i, float& corr_i) {
+__device__ __forceinline__ void epi_layer2(const EpiArgs& a, int i, int g, float (&v)[HP / 4], float& loss_i, float& corr_i, bool alt = false) {
   constexpr int Q = HP / 4;
   loss_i = 0.f; corr_i = 0.f;
   const bool live = i < a.n;
@@ -200,7 +201,7 @@ __device__ __forceinline__ void epi_layer2(const EpiArgs& a, int i, int g, float
       if (mk && o == yi) loss_i = -lp;
       const float dz = mk ? (expf(lp) - (o == yi ? 1.f : 0.f)) * a.inv_m : 0.f;
       a.dz2[(int64_t)o * a.ldr + i] = dz;
-      store_operand(a, o, i, ri * dz);
+      store_operand(a, alt, o, i, ri * dz);
     }
   }
   corr_i = (live && g == 0 && mk && best == yi) ? 1.f : 0.f;
@@ -209,7 +210,7 @@ __device__ __forceinline__ void epi_layer2(const EpiArgs& a, int i, int g, float
 // ---- backward 2: dP2 = r * sum, dH1' = dP2 W1, dZ1 = dropout' relu', operand (r * dZ1)^T
 // The quad first shares the whole dP2 row (C values), then lane g produces the hidden quads q = g, g + 4, ...
 template <int HP>
-__device__ __forceinline__ void epi_bwd2(const EpiArgs& a, int i, int g, float (&v)[HP / 4]) {
+__device__ __forceinline__ void epi_bwd2(const EpiArgs& a, int i, int g, float (&v)[HP / 4], bool alt = false) {
   constexpr int Q = HP / 4;
   const bool live = i < a.n;
   const int il = live ? i : a.n - 1;
@@ -243,7 +244,7 @@ __device__ __forceinline__ void epi_bwd2(const EpiArgs& a, int i, int g, float (
       if (live && c < a.h) {
         const float dz = (z1[e] > 0.f) ? acc[e] * k[e] : 0.f;
         a.dz1[(int64_t)c * a.ldr + i] = dz;
-        store_operand(a, c, i, ri * dz);
+        store_operand(a, alt, c, i, ri * dz);
       }
     }
   }

@@ -83,6 +83,7 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_smem_addr, uint32_t
 template <bool CLUSTER>
 __global__ void __launch_bounds__(K2_THREADS, 1)
 fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant__ CUtensorMap tm_blo,
+                   const __grid_constant__ CUtensorMap tm_bhi_alt, const __grid_constant__ CUtensorMap tm_blo_alt,
                    const __grid_constant__ FusedSmallArgs fa) {
   __shared__ K2EpiShared sh_epi;
   __shared__ unsigned sh_base;
@@ -106,7 +107,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
   const int nt = min(s.per_cta, fa.kb_real - my_kb0);         // real tiles of this CTA (>= 1)
 
   if (tid == 0) sh_base = ld_acquire_u32(&fa.gridbar[1]);
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_bhi); tma_prefetch_desc(&tm_blo); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_bhi); tma_prefetch_desc(&tm_blo); tma_prefetch_desc(&tm_bhi_alt); tma_prefetch_desc(&tm_blo_alt); }
   if (warp == 1) {
     if (lane == 0) {
       mbar_init(bfull, 1);
@@ -294,9 +295,13 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
       if (lane == 0) {                                       // the operand k-blocks of this CTA's range (all fit: no ring)
         asm volatile("fence.proxy.async;" ::: "memory");     // the operand was written with generic stores before the grid barrier
         mbar_expect_tx(bfull, (uint32_t)(nt * FS_B_BYTES * (fa.use_lo ? 2 : 1)));
+        // Operand ping-pong: phase ph reads buffer ph & 1 and its epilogues write the other one — a leader that finishes
+        // early must never overwrite operand rows another CTA has not loaded yet.
+        const CUtensorMap* mh = (ph & 1) ? &tm_bhi_alt : &tm_bhi;
+        const CUtensorMap* ml = (ph & 1) ? &tm_blo_alt : &tm_blo;
         for (int j = 0; j < nt; ++j) {
-          tma_load_2d(sb + j * 2 * FS_B_BYTES, &tm_bhi, bfull, (my_kb0 + j) * K2_BLOCK_K, 0);
-          if (fa.use_lo) tma_load_2d(sb + j * 2 * FS_B_BYTES + FS_B_BYTES, &tm_blo, bfull, (my_kb0 + j) * K2_BLOCK_K, 0);
+          tma_load_2d(sb + j * 2 * FS_B_BYTES, mh, bfull, (my_kb0 + j) * K2_BLOCK_K, 0);
+          if (fa.use_lo) tma_load_2d(sb + j * 2 * FS_B_BYTES + FS_B_BYTES, ml, bfull, (my_kb0 + j) * K2_BLOCK_K, 0);
         }
       }
     } else if (warp == 1) {
@@ -318,10 +323,10 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
         if (++acc_m == 2) { acc_m = 0; acc_phase_m ^= 1; }
       }
     } else if (!CLUSTER) {
-      if (ph == 0) k2_epilogue_loop<FS_HP, K2_EPI_LAYER1, true>(s, ea, fa.partial, fa.counters, cta, lo, hi, tmem_base, tfull_bar, tempty_bar, acc_e, acc_phase_e, sh_epi, fa.use_lo != 0);
-      else if (ph == 1) k2_epilogue_loop<FS_HP, K2_EPI_LAYER2, true>(s, ea, fa.partial, fa.counters, cta, lo, hi, tmem_base, tfull_bar, tempty_bar, acc_e, acc_phase_e, sh_epi, fa.use_lo != 0);
-      else if (ph == 2) k2_epilogue_loop<FS_HP, K2_EPI_BWD2, true>(s, ea, fa.partial, fa.counters, cta, lo, hi, tmem_base, tfull_bar, tempty_bar, acc_e, acc_phase_e, sh_epi, fa.use_lo != 0);
-      else k2_epilogue_loop<FS_HP, K2_EPI_BWD1, true>(s, ea, fa.partial, fa.counters, cta, lo, hi, tmem_base, tfull_bar, tempty_bar, acc_e, acc_phase_e, sh_epi, fa.use_lo != 0);
+      if (ph == 0) k2_epilogue_loop<FS_HP, K2_EPI_LAYER1, true>(s, ea, fa.partial, fa.counters, cta, lo, hi, tmem_base, tfull_bar, tempty_bar, acc_e, acc_phase_e, sh_epi, fa.use_lo != 0, ((ph + 1) & 1) != 0);
+      else if (ph == 1) k2_epilogue_loop<FS_HP, K2_EPI_LAYER2, true>(s, ea, fa.partial, fa.counters, cta, lo, hi, tmem_base, tfull_bar, tempty_bar, acc_e, acc_phase_e, sh_epi, fa.use_lo != 0, ((ph + 1) & 1) != 0);
+      else if (ph == 2) k2_epilogue_loop<FS_HP, K2_EPI_BWD2, true>(s, ea, fa.partial, fa.counters, cta, lo, hi, tmem_base, tfull_bar, tempty_bar, acc_e, acc_phase_e, sh_epi, fa.use_lo != 0, ((ph + 1) & 1) != 0);
+      else k2_epilogue_loop<FS_HP, K2_EPI_BWD1, true>(s, ea, fa.partial, fa.counters, cta, lo, hi, tmem_base, tfull_bar, tempty_bar, acc_e, acc_phase_e, sh_epi, fa.use_lo != 0, ((ph + 1) & 1) != 0);
     } else if (warp < 6) {
       // CLUSTER: drain this CTA's accumulator into its own shared memory (the operand buffer is idle: the MMAs have retired)
       if (ph == 2 && cta == 0 && tid == 64) finalize_scalars(ea);   // the layer-2 phase is complete: (loss, acc)
@@ -357,12 +362,13 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
 #pragma unroll
         for (int r = 0; r < 8; ++r) if (r < fa.parts) { v[0] += t[r].x; v[1] += t[r].y; v[2] += t[r].z; v[3] += t[r].w; }
         const int i = my_p * K2_BLOCK_M + row;
-        if (ph == 0) epi_layer1<FS_HP>(ea, i, g, v);
-        else if (ph == 2) epi_bwd2<FS_HP>(ea, i, g, v);
+        const bool alt = ((ph + 1) & 1) != 0;
+        if (ph == 0) epi_layer1<FS_HP>(ea, i, g, v, alt);
+        else if (ph == 2) epi_bwd2<FS_HP>(ea, i, g, v, alt);
         else if (ph == 3) epi_bwd1<FS_HP>(ea, i, g, v);
         else {
           float li, ci;
-          epi_layer2<FS_HP>(ea, i, g, v, li, ci);
+          epi_layer2<FS_HP>(ea, i, g, v, li, ci, alt);
           li = warp_sum(li); ci = warp_sum(ci);
           if (lane == 0) { sh_epi.red[warp - 2][0] = li; sh_epi.red[warp - 2][1] = ci; }
           named_bar_sync(2, 512);
@@ -442,11 +448,13 @@ int32_t fused_small_launch(const FusedSmallArgs& fa_in, cudaStream_t stream, boo
   if (!coop || num_sms() < fa_in.s.grid) return LDS_ERR_UNSUPPORTED;   // the caller falls back to the multi-kernel path
   FusedSmallArgs fa = fa_in;
   fa.parts = fa.s.grid / fa.s.panels;
-  CUtensorMap tbh, tbl;
+  CUtensorMap tbh, tbl, tbh2, tbl2;
   int32_t rc;
   if ((rc = make_tmap_2d(&tbh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, fa.ea.bt_hi, fa.n, FS_HP, fa.ea.ldb, K2_BLOCK_K, FS_HP)) != LDS_OK) return rc;
   if ((rc = make_tmap_2d(&tbl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, fa.ea.bt_lo, fa.n, FS_HP, fa.ea.ldb, K2_BLOCK_K, FS_HP)) != LDS_OK) return rc;
-  void* params[] = {(void*)&tbh, (void*)&tbl, (void*)&fa};
+  if ((rc = make_tmap_2d(&tbh2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, fa.ea.bt_hi_alt, fa.n, FS_HP, fa.ea.ldb, K2_BLOCK_K, FS_HP)) != LDS_OK) return rc;
+  if ((rc = make_tmap_2d(&tbl2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, fa.ea.bt_lo_alt, fa.n, FS_HP, fa.ea.ldb, K2_BLOCK_K, FS_HP)) != LDS_OK) return rc;
+  void* params[] = {(void*)&tbh, (void*)&tbl, (void*)&tbh2, (void*)&tbl2, (void*)&fa};
   static const bool env_no_cluster = getenv("LDS_FUSED_NO_CLUSTER") != nullptr;      // A/B switch for measurements
   static bool cluster_broken = false;
   const bool cluster = allow_cluster && !env_no_cluster && !cluster_broken && fa.parts >= 2 && fa.parts <= 8 && max_active_clusters(fa.parts) >= fa.s.panels;

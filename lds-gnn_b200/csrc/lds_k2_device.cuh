@@ -23,7 +23,7 @@ struct K2EpiShared {           // static shared memory of the epilogue loop
 template <int HP, int EPI, bool STACKED = false>
 __device__ __forceinline__ void k2_epilogue_loop(const K2Sched& s, const EpiArgs& ea, float* __restrict__ partial, int* __restrict__ counters,
                                                  int cta, int lo, int hi, uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
-                                                 int& acc, uint32_t& acc_phase, K2EpiShared& sh, bool add_lo = false) {
+                                                 int& acc, uint32_t& acc_phase, K2EpiShared& sh, bool add_lo = false, bool alt = false) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   {
     constexpr int Q = HP / 4;
@@ -77,10 +77,10 @@ __device__ __forceinline__ void k2_epilogue_loop(const K2Sched& s, const EpiArgs
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);        // accumulator drained: the next segment's MMAs may start
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         stamp(2);                                            // partial tile written
-        named_bar_sync(1, 128);                              // the four drain warps' stores happen-before the release below
+        __threadfence();                                     // every writer publishes its part of the tile before the CTA is counted in
+        named_bar_sync(1, 128);
         if (etid == 0) {
-          int old;                                           // release: publishes the CTA's partial tile; acquire: the last
-          asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(old) : "l"(counters + p) : "memory");   // arriver sees all of them
+          const int old = atomicAdd(&counters[p], 1);
           const int last = (old == c_last - c_first) ? 1 : 0;
           if (last) counters[p] = 0;                         // everyone has arrived: re-arm for the next launch
           sh.last[seg & 1] = last;
@@ -88,7 +88,8 @@ __device__ __forceinline__ void k2_epilogue_loop(const K2Sched& s, const EpiArgs
       }
       named_bar_sync(2, 512);                                // the drain warps' verdict reaches all 16 warps
       stamp(3);                                              // fence + counter round trip done
-      if (sh.last[seg & 1] != 0) {                           // uniform over the 512 epilogue threads (partials are read with ld.cg: L2)
+      if (sh.last[seg & 1] != 0) {                           // uniform over the 512 epilogue threads
+        __threadfence();
         const int row = etid >> 2, g = etid & 3;             // four threads per row, a quarter of the columns each
         float v[Q];
 #pragma unroll
@@ -120,12 +121,12 @@ __device__ __forceinline__ void k2_epilogue_loop(const K2Sched& s, const EpiArgs
         stamp(4);                                            // partial tiles reduced
         const int i = p * K2_BLOCK_M + row;
         if (EPI == K2_EPI_PLAIN) epi_plain<HP>(ea, i, g, v);
-        else if (EPI == K2_EPI_LAYER1) epi_layer1<HP>(ea, i, g, v);
-        else if (EPI == K2_EPI_BWD2) epi_bwd2<HP>(ea, i, g, v);
+        else if (EPI == K2_EPI_LAYER1) epi_layer1<HP>(ea, i, g, v, alt);
+        else if (EPI == K2_EPI_BWD2) epi_bwd2<HP>(ea, i, g, v, alt);
         else if (EPI == K2_EPI_BWD1) epi_bwd1<HP>(ea, i, g, v);
         else if (EPI == K2_EPI_LAYER2) {
           float li, ci;
-          epi_layer2<HP>(ea, i, g, v, li, ci);
+          epi_layer2<HP>(ea, i, g, v, li, ci, alt);
           li = warp_sum(li); ci = warp_sum(ci);
           if (lane == 0) { sh.red[warp - 2][0] = li; sh.red[warp - 2][1] = ci; }
           named_bar_sync(2, 512);

@@ -26,7 +26,7 @@ constexpr int EPI_THREADS = 1024;   // 32 warps, one row each: the epilogues are
 constexpr int FEAT_THREADS = 256;   // dense feature GEMM: 8 warps x 4 rows
 constexpr int EPI_MAXW = 128;       // widest operand
 
-enum { B_A = 0, B_DEG, B_RS, B_P1, B_Z1, B_P2, B_Z2, B_DZ2, B_DP2, B_DZ1, B_DP1, B_FA, B_FB, B_C, B_BTHI, B_BTLO, B_PARTIAL, B_LOSSP, B_CORRP, B_F, B_W0S, B_CNT, B_OPND, B_DEGP, B_GBAR, B_END };
+enum { B_A = 0, B_DEG, B_RS, B_P1, B_Z1, B_P2, B_Z2, B_DZ2, B_DP2, B_DZ1, B_DP1, B_FA, B_FB, B_C, B_BTHI, B_BTLO, B_BT2HI, B_BT2LO, B_PARTIAL, B_LOSSP, B_CORRP, B_F, B_W0S, B_CNT, B_OPND, B_DEGP, B_GBAR, B_END };
 struct OuterLayout {
   int n, rows, f, h, c, hp1, hp2, hpmax, nblk, panels;
   int64_t lda, ldb, ldf, ldr;
@@ -55,7 +55,7 @@ static bool make_layout(int n, int rows, int f, int h, int c, OuterLayout& L, bo
   bytes[B_P2] = bytes[B_Z2] = bytes[B_DZ2] = bytes[B_DP2] = L.ldr * c * 4;
   bytes[B_FA] = bytes[B_FB] = (int64_t)rows * L.ldf * 4;
   bytes[B_OPND] = (rows < n) ? (int64_t)rows * (h > c ? h : c) * 4 : 0;        // sharded: operand rows for the all-gather
-  bytes[B_BTHI] = bytes[B_BTLO] = k2_operand_bytes(n, L.hpmax);
+  bytes[B_BTHI] = bytes[B_BTLO] = bytes[B_BT2HI] = bytes[B_BT2LO] = k2_operand_bytes(n, L.hpmax);   // operand ping-pong (see propagate)
   // partial tiles are sized for the stream-K schedule whichever schedule runs (workspace size must not depend on flags)
   const int64_t p1 = k2_partial_bytes(k2_make_schedule(n, rows, L.hp1, true)), p2 = k2_partial_bytes(k2_make_schedule(n, rows, L.hp2, true));
   bytes[B_PARTIAL] = p1 > p2 ? p1 : p2;
@@ -371,8 +371,15 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   const int64_t per = A.opnd_rank_rows;
   auto* snd = reinterpret_cast<__nv_bfloat16*>(A.opnd_send);
   // where an epilogue / the feature kernel writes the next operand (padded width hp_next), and with which row stride
-  auto out_hi = [&](int hp_next) { (void)hp_next; return packed_xchg ? snd : bt_hi; };
-  auto out_lo = [&](int hp_next) { return packed_xchg ? snd + (int64_t)hp_next * per : bt_lo; };
+  // Operand ping-pong: a propagation reads operand buffer `cur` while its epilogues write the NEXT operand into the other
+  // one. With a single buffer, a panel that completes early overwrote operand rows that other CTAs were still streaming
+  // (found by the full-size reproducibility test at N = 20 000; at Cora / Citeseer size every MMA retires before the
+  // first epilogue starts, which hid it).
+  __nv_bfloat16* pp_hi[2] = {bt_hi, reinterpret_cast<__nv_bfloat16*>(buf(B_BT2HI))};
+  __nv_bfloat16* pp_lo[2] = {bt_lo, reinterpret_cast<__nv_bfloat16*>(buf(B_BT2LO))};
+  // which buffer holds the operand of each propagation: SAMPLE -> 0, LAYER1 writes 1, LAYER2 writes 0, BWD2 writes 1
+  auto out_hi = [&](int hp_next, int which) { (void)hp_next; return packed_xchg ? snd : pp_hi[which]; };
+  auto out_lo = [&](int hp_next, int which) { return packed_xchg ? snd + (int64_t)hp_next * per : pp_lo[which]; };
   const int64_t out_ld = packed_xchg ? per : L.ldb;
   const bool use_lo = !(A.k2_flags & LDS_K2_SINGLE_BF16);
 
@@ -427,6 +434,7 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
     E.scal_tag = ((int)smp == S - 1) ? A.scalars_tag : 0.f;
     E.w1 = A.w1; E.b1 = A.b1; E.y = A.y; E.mask = A.mask; E.inv_m = 1.0f / (float)A.mask_count;
     E.drop_h = dh; E.bt_hi = bt_hi; E.bt_lo = bt_lo; E.ldb = L.ldb;
+    E.bt_hi_alt = reinterpret_cast<__nv_bfloat16*>(buf(B_BT2HI)); E.bt_lo_alt = reinterpret_cast<__nv_bfloat16*>(buf(B_BT2LO));
     E.loss_part = fbuf(B_LOSSP); E.corr_part = fbuf(B_CORRP); E.nblk = L.panels;
     E.out_scalars = A.out_scalars; E.out_logp = A.out_logp;
     rc = fused_small_launch(F, stream);
@@ -449,11 +457,11 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
     const dim3 egrid((unsigned)L.nblk);
     if (sparse_x) {
       feat_sparse_kernel<<<egrid, EPI_THREADS, 0, stream>>>(A.x_crow, A.x_col, A.x_val, rows, A.f, fbuf(B_W0S), A.b0, A.h, dx, fbuf(B_RS), fbuf(B_P1), L.ldr,
-                                                            out_hi(L.hp1), out_lo(L.hp1), out_ld, L.hp1, row0, opnd, ld_opnd);
+                                                            out_hi(L.hp1, 0), out_lo(L.hp1, 0), out_ld, L.hp1, row0, opnd, ld_opnd);
       LDS_CHECK_LAUNCH("feat_sparse_kernel");
     } else {
       feat_linear_kernel<<<egrid, FEAT_THREADS, 0, stream>>>(A.x, A.ld_x, rows, A.f, fbuf(B_W0S), round_up(A.f, 4), A.b0, A.h, dx, fbuf(B_RS), fbuf(B_P1), L.ldr,
-                                                             out_hi(L.hp1), out_lo(L.hp1), out_ld, L.hp1, row0, opnd, ld_opnd);
+                                                             out_hi(L.hp1, 0), out_lo(L.hp1, 0), out_ld, L.hp1, row0, opnd, ld_opnd);
       LDS_CHECK_LAUNCH("feat_linear_kernel");
     }
     profile_mark(stream, 1);
@@ -481,27 +489,27 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   if ((A.k2_flags & LDS_K2_SIMT) && (phases & (LDS_PHASE_LAYER1 | LDS_PHASE_LAYER2 | LDS_PHASE_BWD2 | LDS_PHASE_BWD1))) {
     set_error("lds_outer_step: LDS_K2_SIMT is only available through lds_k2_propagate"); return LDS_ERR_ARG;
   }
-  auto propagate = [&](uint32_t phase, const K2Sched& s, int width, int epi, int mark, int hp_next) -> int32_t {
+  auto propagate = [&](uint32_t phase, const K2Sched& s, int width, int epi, int mark, int hp_next, int cur) -> int32_t {
     if (fused_done || !(phases & phase)) return LDS_OK;
-    const __nv_bfloat16* in_hi = bt_hi;
-    const __nv_bfloat16* in_lo = bt_lo;
+    const __nv_bfloat16* in_hi = pp_hi[cur];
+    const __nv_bfloat16* in_lo = pp_lo[cur];
     int rank_rows = 0;
     if (packed_xchg) {                                        // gathered [rank][hi, lo][hp][per] bf16
       in_hi = reinterpret_cast<const __nv_bfloat16*>(A.opnd_full);
       in_lo = in_hi + (int64_t)s.hp * per;
       rank_rows = (int)per;
     } else if (sharded) {   // the gathered operand [n][width] fp32 -> K-major bf16 hi/lo terms
-      const int32_t r0 = k2_launch_prep(A.opnd_full, ld_opnd, A.n, width, s.hp, nullptr, bt_hi, bt_lo, L.ldb, counters, 0, stream);
+      const int32_t r0 = k2_launch_prep(A.opnd_full, ld_opnd, A.n, width, s.hp, nullptr, pp_hi[cur], pp_lo[cur], L.ldb, counters, 0, stream);
       if (r0 != LDS_OK) return r0;
     }
-    E.bt_hi = out_hi(hp_next); E.bt_lo = out_lo(hp_next); E.ldb = out_ld;
+    E.bt_hi = out_hi(hp_next, cur ^ 1); E.bt_lo = out_lo(hp_next, cur ^ 1); E.ldb = out_ld;
     E.timeline = A.k2_timeline ? A.k2_timeline + (size_t)(mark - 3) * 512 * 8 : nullptr;
     const int32_t r = k2_launch_mma(buf(B_A), L.lda, A.n, rows, in_hi, in_lo, L.ldb, fbuf(B_PARTIAL), counters, s, use_lo, epi, E, stream, rank_rows);
     profile_mark(stream, mark);
     return r;
   };
-  if ((rc = propagate(LDS_PHASE_LAYER1, L.s1, A.h, K2_EPI_LAYER1, 3, L.hp2)) != LDS_OK) return rc;   // Z1, H1, P2, operand (r P2)^T
-  if ((rc = propagate(LDS_PHASE_LAYER2, L.s2, A.c, K2_EPI_LAYER2, 4, L.hp2)) != LDS_OK) return rc;   // Z2, log-softmax, loss, dZ2, operand (r dZ2)^T
+  if ((rc = propagate(LDS_PHASE_LAYER1, L.s1, A.h, K2_EPI_LAYER1, 3, L.hp2, 0)) != LDS_OK) return rc;   // Z1, H1, P2, operand (r P2)^T
+  if ((rc = propagate(LDS_PHASE_LAYER2, L.s2, A.c, K2_EPI_LAYER2, 4, L.hp2, 1)) != LDS_OK) return rc;   // Z2, log-softmax, loss, dZ2, operand (r dZ2)^T
   const bool fwd_only = (A.k2_flags & LDS_K2_FORWARD_ONLY) != 0;
   if (fwd_only && sharded) { set_error("lds_outer_step: LDS_K2_FORWARD_ONLY is not available for row-block shards"); return LDS_ERR_UNSUPPORTED; }
   if (fwd_only) {
@@ -511,8 +519,8 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
     }
     return LDS_OK;
   }
-  if ((rc = propagate(LDS_PHASE_BWD2, L.s2, A.c, K2_EPI_BWD2, 5, L.hp1)) != LDS_OK) return rc;       // dP2, dZ1, operand (r dZ1)^T; loss/acc finalised
-  if ((rc = propagate(LDS_PHASE_BWD1, L.s1, A.h, K2_EPI_BWD1, 6, L.hp1)) != LDS_OK) return rc;       // dP1, c, factor matrices
+  if ((rc = propagate(LDS_PHASE_BWD2, L.s2, A.c, K2_EPI_BWD2, 5, L.hp1, 0)) != LDS_OK) return rc;       // dP2, dZ1, operand (r dZ1)^T; loss/acc finalised
+  if ((rc = propagate(LDS_PHASE_BWD1, L.s1, A.h, K2_EPI_BWD1, 6, L.hp1, 1)) != LDS_OK) return rc;       // dP1, c, factor matrices
 
   if ((phases & LDS_PHASE_UPDATE) && A.update && (S == 1 || (int)smp == S - 1)) {
     const float* cv = sharded ? A.c_full : fbuf(B_C);

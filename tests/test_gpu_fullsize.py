@@ -1,0 +1,138 @@
+"""-m gpu tests at BASELINE.json's full single-GPU size (config 4: N = 20 000, F = 512, hidden 64, C = 7), where the oracle
+cannot run (25 dense N x N fp32 temporaries, N^3 products). Size-independent properties of the path instead:
+
+  * the sampled A_tilde is a symmetric {0,1} matrix with unit diagonal; deg = its row sums EXACTLY; r = deg^-1/2;
+    its edge density matches theta's mean (5 sigma);
+  * checksum through the tensor cores: A_tilde @ 1 reproduces deg bit for bit (sums of ones are exact in fp32);
+  * linearity of the propagation;
+  * a row-block shard regenerates exactly the rows of the full graph (no exchange of random bits);
+  * the update keeps theta symmetric bit for bit, inside [0, 1], leaves the padding alone, is idempotent at lr = 0,
+    and the whole step is bitwise reproducible.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+pytestmark = pytest.mark.gpu
+N = 20000
+
+
+@pytest.fixture(scope="module")
+def big():
+    import bench
+    from lds_gnn_b200 import kernels as K
+    dev = torch.device("cuda")
+    d = bench.make_large_rows("n20k", dev, 0, N, seed=3)
+    rng = np.random.default_rng(0)
+    f, h, c = d["f"], d["h"], d["c"]
+    w = [torch.as_tensor((rng.standard_normal(s) * 0.2).astype(np.float32), device=dev) for s in ((h, f), (h,), (c, h), (c,))]
+    return K, d, w
+
+
+def test_full_size_sample_degree_and_tensor_core_checksum(big):
+    K, d, _ = big
+    theta = d["theta"]
+    adj, _, deg, rs = K.k1_sample_normalize(theta, N, seed=11, step=5)
+    a = adj[:, :N]
+    assert torch.equal(a, a.t()), "A_tilde must be symmetric"
+    assert bool(((a == 0) | (a == 1)).all()) and bool((torch.diagonal(a) == 1).all())
+    assert bool((adj[:, N:] == 0).all())
+    rowsum = a.float().sum(dim=1)
+    assert torch.equal(rowsum, deg), "deg must be the exact row sums"
+    assert torch.allclose(rs, deg.rsqrt(), rtol=2e-7, atol=0)
+    # density: E[A_ij] = theta_ij (i != j); both triangles carry the same draws -> N(N-1)/2 independent Bernoullis
+    p = theta[:, :N].clamp(0, 1)
+    mean_theta = (p.sum().item() - torch.diagonal(p).sum().item()) / (N * (N - 1))
+    mean_adj = (a.float().sum().item() - N) / (N * (N - 1))
+    sigma = (0.25 / (N * (N - 1) / 2)) ** 0.5
+    assert abs(mean_adj - mean_theta) < 5 * sigma
+    # checksum through TMA + tcgen05: A_tilde @ ones == deg exactly, every column
+    ones = torch.ones((N, 16), device="cuda")
+    z = K.k2_propagate(adj, N, ones)
+    assert torch.equal(z, deg[:, None].expand(-1, 16).contiguous())
+    # a row-block shard regenerates the same rows without any exchange
+    r0, rows = 8192, 4096
+    sh_adj, _, sh_deg, _ = K.k1_sample_normalize(theta[r0:r0 + rows], N, seed=11, step=5, row0=r0, rows=rows)
+    assert torch.equal(sh_adj, adj[r0:r0 + rows]) and torch.equal(sh_deg, deg[r0:r0 + rows])
+
+
+def test_full_size_propagation_is_linear(big):
+    K, d, _ = big
+    adj = K.k1_sample_normalize(d["theta"], N, seed=2, step=1)[0]
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    p = torch.randn((N, 64), device="cuda", generator=g)
+    q = torch.randn((N, 64), device="cuda", generator=g)
+    zp, zq = K.k2_propagate(adj, N, p), K.k2_propagate(adj, N, q)
+    zl = K.k2_propagate(adj, N, 0.5 * p - 2.0 * q)
+    ref = 0.5 * zp - 2.0 * zq
+    assert (zl - ref).abs().max().item() < 2e-5 * ref.abs().max().item()     # hi/lo split: ~2^-17 relative per term
+
+
+def test_full_size_step_symmetry_projection_idempotence_determinism(big):
+    K, d, w = big
+    eng = K.OuterStep(N, d["x"], d["y"], d["mask"], hidden=d["h"], classes=d["c"])
+    eng.set_weights(*w)
+    theta0 = d["theta"].clone()
+    theta0[3, 5] = theta0[5, 3] = 1.4                   # outside [0, 1]: projected by the step
+    theta0[7, 9] = theta0[9, 7] = -0.3
+    pad = theta0[:, N:].clone()
+    # lr = 0: the step is the projection, and applying it twice changes nothing
+    t = theta0.clone()
+    eng.run(t, lr=0.0, seed=5, step=0, dropout_p=0.5, update=True)
+    assert torch.equal(t[:, :N], theta0[:, :N].clamp(0, 1))
+    t2 = t.clone()
+    eng.run(t2, lr=0.0, seed=5, step=1, dropout_p=0.5, update=True)
+    assert torch.equal(t2, t)
+    # a real step: symmetric bit for bit, inside [0, 1], padding untouched, finite loss, and reproducible
+    a, b = theta0.clone(), theta0.clone()
+    sa = eng.run(a, lr=50.0, seed=5, step=2, dropout_p=0.5, update=True).clone()
+    sb = eng.run(b, lr=50.0, seed=5, step=2, dropout_p=0.5, update=True).clone()
+    assert torch.equal(a, b) and torch.equal(sa, sb), "the step must be bitwise reproducible"
+    v = a[:, :N]
+    assert torch.equal(v, v.t()) and float(v.min()) >= 0.0 and float(v.max()) <= 1.0
+    assert torch.equal(a[:, N:], pad)
+    assert not torch.equal(v, theta0[:, :N].clamp(0, 1)), "lr = 50 must move theta"
+    assert np.isfinite(sa[0].item()) and 0.0 <= sa[1].item() <= 1.0
+    # degrees of the step's graph are consistent with its own A_tilde
+    assert torch.equal(eng.buffer("adj")[:, :N].float().sum(1), eng.buffer("deg"))
+
+
+def test_full_size_propagations_and_update_against_plain_fp32_products(big):
+    """Independent check at N = 20 000 (no oracle exists at this size): every propagation of the step against a plain
+    torch fp32 product on the same sampled graph, and the theta update against the closed form in fp64 on random rows.
+    Tolerance 1e-4 (inf-norm relative; bar of the north star: 1e-3)."""
+    K, d, w = big
+    torch.backends.cuda.matmul.allow_tf32 = False
+    eng = K.OuterStep(N, d["x"], d["y"], d["mask"], hidden=d["h"], classes=d["c"])
+    eng.set_weights(*w)
+    theta0 = d["theta"].clone()
+    t = theta0.clone()
+    lr = 30.0
+    eng.run(t, lr=lr, seed=21, step=4, dropout_p=0.5, update=True)
+    a = eng.buffer("adj")[:, :N].float()
+    rs = eng.buffer("rsqrt")[:, None]
+
+    def rel(x, ref):
+        return float((x - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+
+    for src, dst in (("p1", "z1"), ("p2", "z2"), ("dz2", "dp2"), ("dz1", "dp1")):
+        ref = rs * (a @ (rs * eng.buffer(src)))
+        assert rel(eng.buffer(dst), ref) < 1e-4, (src, dst)
+    del a
+    # theta update on 96 random rows (all columns), closed form of SURVEY.md App. A.2 in fp64
+    g = torch.Generator(device="cpu"); g.manual_seed(1)
+    rows = torch.randperm(N, generator=g)[:96].cuda()
+    fa, fb, cv = eng.buffer("fa").double(), eng.buffer("fb").double(), eng.buffer("cvec").double()
+    grad = fa[rows] @ fb.t() + fb[rows] @ fa.t() + cv[rows][:, None] + cv[None, :]
+    grad[torch.arange(96, device="cuda"), rows] = 0.0
+    th = theta0[rows, :N].double()
+    grad = grad * ((th >= 0) & (th <= 1))
+    ref = (th - lr * grad).clamp(0, 1)
+    assert float((t[rows, :N].double() - ref).abs().max()) < 2e-6 + 1e-5 * lr * float(grad.abs().max())
