@@ -136,3 +136,34 @@ def test_full_size_propagations_and_update_against_plain_fp32_products(big):
     grad = grad * ((th >= 0) & (th <= 1))
     ref = (th - lr * grad).clamp(0, 1)
     assert float((t[rows, :N].double() - ref).abs().max()) < 2e-6 + 1e-5 * lr * float(grad.abs().max())
+
+
+def test_full_size_row_block_shards_match_the_single_device_step(big):
+    """SURVEY.md 8e at N = 20 000: three row-block shards (emulated on one GPU: same kernels, same phases, exchange =
+    concatenation of the packed operand blocks) against the unsharded step — same graph bit for bit, theta equal up to
+    fp32 summation order, shards mutually consistent (exact symmetry)."""
+    K, d, w = big
+    from lds_gnn_b200 import sharded as S
+    eng = K.OuterStep(N, d["x"], d["y"], d["mask"], hidden=d["h"], classes=d["c"])
+    eng.set_weights(*w)
+    ref = d["theta"].clone()
+    lr = 30.0
+    sc_ref = eng.run(ref, lr=lr, seed=9, step=3, dropout_p=0.5, update=True).clone()
+    deg_ref = eng.buffer("deg").clone()
+    del eng
+    world = 3
+    bounds = [S.shard_bounds(N, world, r) for r in range(world)]
+    shards, thetas = [], []
+    for lo, cnt in bounds:
+        sh = S.ShardedOuterStep(N, lo, cnt, d["x"][lo:lo + cnt], d["y"][lo:lo + cnt], d["mask"][lo:lo + cnt], int(d["mask"].sum().item()),
+                                d["h"], d["c"])
+        sh.set_weights(*w)
+        shards.append(sh)
+        thetas.append(d["theta"][lo:lo + cnt].clone())
+    sc = S.run_local_group(shards, thetas, lr=lr, seed=9, step=3, dropout_p=0.5, update=True)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat([s.eng.buffer("deg") for s in shards]), deg_ref), "shards must sample the same graph"
+    new = torch.cat(thetas, dim=0)
+    assert (new - ref).abs().max().item() < 2e-5
+    assert torch.equal(new[:, :N], new[:, :N].t())
+    assert abs(sc[0].item() - sc_ref[0].item()) < 1e-5 and abs(sc[1].item() - sc_ref[1].item()) < 1e-6
