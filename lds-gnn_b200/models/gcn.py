@@ -3,6 +3,7 @@ import torch
 import torch.nn.functional as F
 
 from ..utils.graph import normalize_adjacency_matrix
+from .sampling import FactoredGraph
 from .layers import MetaDenseGraphConvolution, MetaModule, get_subdict
 
 # When true, a sampled graph is propagated through plain differentiable torch ops instead of the custom
@@ -34,7 +35,11 @@ class MetaDenseGCN(MetaModule):
         self.layer_out.reset_weights()
 
     def forward_to_last_layer(self, node_features, dense_adj, params=None):
-        if self.normalize_adj:
+        if isinstance(dense_adj, FactoredGraph):
+            if not self.normalize_adj:
+                raise NotImplementedError("a FactoredGraph carries the self-looped sample; it is propagated in normalised form only")
+            dense_adj = dense_adj.normalized()
+        elif self.normalize_adj:
             factored_ok = not (_DOUBLE_BACKWARD[0] and torch.is_grad_enabled())
             dense_adj = normalize_adjacency_matrix(dense_adj, materialize=not factored_ok)
         hidden = F.dropout(node_features, self.dropout, training=self.training)

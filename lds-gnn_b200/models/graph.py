@@ -21,7 +21,7 @@ from torch.nn import Parameter
 
 from ..utils.graph import get_triu_values, is_square_matrix, triu_values_to_symmetric_matrix
 from ..utils.tracking import setup_basic_logger
-from .sampling import Sampler
+from .sampling import FactoredGraph, FactorSink, Sampler, sample_factored
 
 logger = setup_basic_logger()
 
@@ -66,6 +66,7 @@ class BernoulliGraphModel(GraphGenerativeModel):
         self._full = None            # [n, ld] fp32 device copy (unclamped, symmetric)
         self._full_key = None        # (data_ptr, version) of `probs` when `_full` was built from it
         self._probs_stale = False    # `_full` is newer than `probs` (after fused steps)
+        self.factor_sink = FactorSink()   # hypergradient deposits of factored graphs (unrolled bilevel loop)
         values = init_matrix if directed else get_triu_values(init_matrix)
         self.probs = Parameter(values, requires_grad=True)
 
@@ -121,6 +122,12 @@ class BernoulliGraphModel(GraphGenerativeModel):
     def mark_full_updated(self):
         """Called by the fused outer step after it updated `theta_full()` in place."""
         self._probs_stale = True
+
+    def sample_factored(self) -> FactoredGraph:
+        """`sample()` for callers that understand factored graphs (the trainers of this package): K1 straight from the
+        resident full matrix — no (T,) -> N x N rebuild, no dense fp32 sample, no N x N autograd node. Same Philox draw
+        as `sample()` would make at this step."""
+        return sample_factored(self.theta_full(), self._n, self._probs_param(), self.factor_sink)
 
     # ---- reference API ---------------------------------------------------------------------------
     def project_parameters(self):

@@ -16,6 +16,7 @@ from torch.nn import Parameter
 from torch.nn.init import xavier_uniform_
 
 from ..utils.graph import FactoredAdjacency
+from .sampling import FactoredGraph, FactoredNormalizedAdjacency
 
 
 def get_subdict(dictionary, key=None):
@@ -72,6 +73,10 @@ class _Propagate(torch.autograd.Function):
 
 
 def propagate(dense_adj, embeddings):
+    if isinstance(dense_adj, FactoredNormalizedAdjacency):       # unrolled bilevel loop: differentiable to any order
+        return dense_adj.propagate(embeddings)
+    if isinstance(dense_adj, FactoredGraph):
+        raise NotImplementedError("a FactoredGraph is propagated in normalised form (MetaDenseGCN(normalize_adj=True))")
     if isinstance(dense_adj, FactoredAdjacency):
         return _Propagate.apply(embeddings, dense_adj.graph, dense_adj.handle)
     return torch.mm(dense_adj, embeddings)

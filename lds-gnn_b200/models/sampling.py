@@ -83,6 +83,135 @@ class _SampleSTE(torch.autograd.Function):
         return grad, None, None, None, None
 
 
+class FactorSink:
+    """Where the hypergradient on theta of FACTORED graphs is collected. With the straight-through estimator every sampled
+    graph has d(sample)/d(theta_full) = I, so the contributions of all graphs of an unroll simply add up:
+        dL/dtheta_full[i][j] = sum_k a_k[i] . b_k[j]  +  c[i]        (i != j; symmetrised by the update kernel)
+    Each differentiable product with a sampled graph deposits one factor pair (a_k, b_k) = (dY, Q) of width <= hidden, each
+    differentiable degree one row-constant term — O(N h) per deposit instead of an N x N autograd temporary. The update
+    kernel (K3+K4) consumes the K-concatenation of all pairs in ONE pass over theta."""
+
+    def __init__(self):
+        self.fa, self.fb, self.c = [], [], None
+
+    def clear(self):
+        self.fa, self.fb, self.c = [], [], None
+
+    def add_outer(self, a: Tensor, b: Tensor):
+        self.fa.append(a)
+        self.fb.append(b)
+
+    def add_row_constant(self, c: Tensor):
+        self.c = c if self.c is None else self.c + c
+
+    def empty(self) -> bool:
+        return not self.fa and self.c is None
+
+    def collect(self, n: int, device):
+        """(fa [n, d], fb [n, d], c [n]) fp32, contiguous; d >= 1."""
+        if self.fa:
+            fa = torch.cat(self.fa, dim=1).contiguous()
+            fb = torch.cat(self.fb, dim=1).contiguous()
+        else:
+            fa = torch.zeros((n, 1), dtype=torch.float32, device=device)
+            fb = torch.zeros((n, 1), dtype=torch.float32, device=device)
+        c = self.c.contiguous() if self.c is not None else torch.zeros(n, dtype=torch.float32, device=device)
+        return fa, fb, c
+
+
+class _FactoredMatmul(torch.autograd.Function):
+    """Y = A_tilde Q for a factored sampled graph (K2 on the tensor cores), differentiable to ANY order: the backward is
+    the same product (A_tilde is symmetric) applied through this Function again, so a later backward can differentiate
+    through it (the unrolled inner steps, src/trainers/inner.py:71). The gradient on the graph, dY Q^T, is never formed:
+    when the backward runs as a plain (non-create_graph) pass — the hypergradient pass of outer.py:77 — the factor pair is
+    deposited in the graph's FactorSink. A create_graph backward is the inner optimiser differentiating w.r.t. the GCN
+    weights only (inner.py:71 -> autograd.grad(loss, params)), which sends nothing to theta, so nothing is deposited."""
+
+    @staticmethod
+    def forward(ctx, q, link, fg):
+        from .. import kernels
+        q = q.contiguous()
+        y = kernels.k2_propagate(fg.handle.adj, fg.handle.n, q)
+        ctx.save_for_backward(q)
+        ctx.fg = fg
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (q,) = ctx.saved_tensors
+        fg = ctx.fg
+        if not torch.is_grad_enabled():
+            fg.sink.add_outer(dy.detach(), q.detach())
+        dq = _FactoredMatmul.apply(dy, fg.link, fg) if ctx.needs_input_grad[0] else None
+        return dq, None, None
+
+
+class _FactoredDegree(torch.autograd.Function):
+    """deg_i = sum_j A_tilde_ij (K1's row sums). d deg_i / d sample_ij = 1 for j != i: a row-constant deposit."""
+
+    @staticmethod
+    def forward(ctx, link, fg):
+        ctx.fg = fg
+        return fg.handle.deg.clone()
+
+    @staticmethod
+    def backward(ctx, ddeg):
+        if not torch.is_grad_enabled():
+            ctx.fg.sink.add_row_constant(ddeg.detach())
+        return None, None
+
+
+class FactoredGraph:
+    """A sampled graph for the unrolled bilevel loop that never becomes an N x N autograd tensor: bf16 A_tilde (self
+    loops included) + degrees from K1, a `link` tensor (the model's `probs`) that ties it into autograd, and the
+    FactorSink its straight-through gradient is deposited in. Quacks like a square matrix for the reference's asserts."""
+
+    def __init__(self, handle: SampleHandle, link: Tensor, sink: FactorSink):
+        self.handle, self.link, self.sink = handle, link, sink
+
+    def dim(self):
+        return 2
+
+    def size(self, dim=None):
+        shape = torch.Size((self.handle.n, self.handle.n))
+        return shape if dim is None else shape[dim]
+
+    @property
+    def shape(self):
+        return self.size()
+
+    @property
+    def device(self):
+        return self.handle.adj.device
+
+    def matmul(self, q: Tensor) -> Tensor:
+        return _FactoredMatmul.apply(q, self.link, self)
+
+    def degree(self) -> Tensor:
+        return _FactoredDegree.apply(self.link, self)
+
+    def normalized(self):
+        """D^-1/2 (A+I) D^-1/2 (src/utils/graph.py:136-153) in factored, differentiable form."""
+        return FactoredNormalizedAdjacency(self, torch.rsqrt(self.degree()))
+
+
+class FactoredNormalizedAdjacency:
+    def __init__(self, fg: FactoredGraph, r: Tensor):
+        self.fg, self.r = fg, r
+
+    def propagate(self, embeddings: Tensor) -> Tensor:
+        r = self.r[:, None]
+        return r * self.fg.matmul(r * embeddings)
+
+
+def sample_factored(theta_full: Tensor, n: int, link: Tensor, sink: FactorSink) -> FactoredGraph:
+    """The LDS sampling path (same Philox draws, same step counter as `sample_graph`) without the dense fp32 sample."""
+    from .. import kernels
+    seed, step = PHILOX.next_step()
+    adj, _, deg, rs = kernels.k1_sample_normalize(theta_full, n, seed, step, want_sample=False)
+    return FactoredGraph(SampleHandle(n, adj, deg, rs, seed, step), link, sink)
+
+
 def straight_through_estimator(sample: Tensor, parameters: Tensor) -> Tensor:
     """(sample - parameters).detach() + parameters (src/models/sampling.py:82-85)."""
     assert sample.size() == parameters.size()

@@ -67,7 +67,8 @@ class BilevelProblemRunner:
 
     def inner_opt_step(self) -> Metrics:
         self.outer_trainer.train()
-        graph = self.outer_trainer.sample()
+        sampler = getattr(self.outer_trainer, "sample_for_unroll", None)       # factored graph when the hyper step can use it
+        graph = sampler(self.inner_trainer) if sampler is not None else self.outer_trainer.sample()
         return self.inner_trainer.train_step(graph)
 
     def hyper_opt_step(self, current_step: int, sacred_runner=None):

@@ -7,6 +7,11 @@ published algorithm — `torch.optim.Adam`'s rule of that era applied out of pla
 differentiate through it: g += wd * p; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
 p' = p - lr * sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps). It is checked against `torch.optim.Adam` on
 detached copies in tests/ (same trajectory to 1e-6 while eps placement is immaterial).
+
+All parameters are updated as ONE flat vector (per-group hyper-parameters become per-element vectors): the
+update is ~10 differentiable ops per step instead of ~14 per parameter tensor, which matters because the
+unrolled loop is bound by the host's op-dispatch rate, not by the GPU. The new parameters are views of the
+flat result, so the next step's concatenation is free.
 """
 import math
 from typing import Iterable, List
@@ -20,43 +25,85 @@ class DifferentiableAdam:
         position = {id(p): i for i, p in enumerate(reference)}
         self.track = track_higher_grads
         self.param_groups = []
-        self.state = []
         self._slots = []
         for group in optimizer.param_groups:
             self.param_groups.append({k: v for k, v in group.items() if k != "params"})
             self._slots.append([position[id(p)] for p in group["params"]])
-            self.state.append({})
+        self._shapes = [p.shape for p in reference]
+        self._numels = [p.numel() for p in reference]
+        self.state = {"step": 0, "exp_avg": None, "exp_avg_sq": None}
+        self._vectors = None          # per-element hyper-parameters, built on the parameters' device at the first step
+        self._flat = None             # (flat tensor, views) of the last result: reused when the caller passes the views back
+
+    # ---- per-element hyper-parameter vectors -----------------------------------------------------------------
+    def _hyper(self, like: torch.Tensor):
+        if self._vectors is None or self._vectors["device"] != like.device or self._vectors["dtype"] != like.dtype:
+            total = sum(self._numels)
+            offsets = [0]
+            for k in self._numels:
+                offsets.append(offsets[-1] + k)
+            cols = {name: torch.zeros(total, dtype=like.dtype) for name in ("lr", "wd", "b1", "b2", "eps", "in_group")}
+            for group, slots in zip(self.param_groups, self._slots):
+                for slot in slots:
+                    sl = slice(offsets[slot], offsets[slot + 1])
+                    cols["lr"][sl], cols["wd"][sl], cols["eps"][sl] = group["lr"], group["weight_decay"], group["eps"]
+                    cols["b1"][sl], cols["b2"][sl] = group["betas"]
+                    cols["in_group"][sl] = 1.0
+            vec = {"device": like.device, "dtype": like.dtype, "offsets": offsets}
+            for name, col in cols.items():
+                lo, hi = col.min().item(), col.max().item()
+                vec[name] = lo if lo == hi else col.to(like.device)            # uniform -> python scalar (no extra op)
+            self._vectors = vec
+        return self._vectors
 
     def step(self, loss: torch.Tensor, params: Iterable[torch.Tensor]) -> List[torch.Tensor]:
         params = list(params)
         grads = torch.autograd.grad(loss, params, create_graph=self.track, allow_unused=True)
-        updated = list(params)
-        for gi, (group, slots) in enumerate(zip(self.param_groups, self._slots)):
-            beta1, beta2 = group["betas"]
-            for slot in slots:
-                p, g = params[slot], grads[slot]
-                if g is None:
-                    continue
-                st = self.state[gi].setdefault(slot, {})
-                if not st:
-                    st["step"] = 0
-                    st["exp_avg"] = torch.zeros_like(p)
-                    st["exp_avg_sq"] = torch.zeros_like(p)
-                st["step"] += 1
-                if group["weight_decay"] != 0:
-                    g = g + group["weight_decay"] * p
-                st["exp_avg"] = m = st["exp_avg"] * beta1 + (1 - beta1) * g
-                st["exp_avg_sq"] = v = st["exp_avg_sq"] * beta2 + (1 - beta2) * g * g
-                # sqrt has an infinite derivative at 0: floor exact zeros (higher masks that gradient instead)
-                root = torch.where(v > 0, v, torch.full_like(v, 1e-30)).sqrt()
-                step_size = group["lr"] * math.sqrt(1 - beta2 ** st["step"]) / (1 - beta1 ** st["step"])
-                updated[slot] = p - step_size * m / (root + group["eps"])
-        return updated
+        hp = self._hyper(params[0])
+        if self._flat is not None and len(params) == len(self._flat[1]) and all(a is b for a, b in zip(params, self._flat[1])):
+            p = self._flat[0]
+        else:
+            p = torch.cat([q.reshape(-1) for q in params])
+        unused = [g is None for g in grads]
+        g = torch.cat([torch.zeros_like(q).reshape(-1) if miss else gr.reshape(-1) for q, gr, miss in zip(params, grads, unused)])
+        st = self.state
+        if st["exp_avg"] is None:
+            st["exp_avg"] = torch.zeros_like(p)
+            st["exp_avg_sq"] = torch.zeros_like(p)
+        st["step"] += 1
+        t = st["step"]
+        if not (isinstance(hp["wd"], float) and hp["wd"] == 0.0):
+            g = g + hp["wd"] * p
+        b1, b2 = hp["b1"], hp["b2"]
+        m = st["exp_avg"] * b1 + (1 - b1) * g
+        v = st["exp_avg_sq"] * b2 + (1 - b2) * (g * g)
+        # sqrt has an infinite derivative at 0: floor exact zeros (higher masks that gradient instead)
+        root = v.clamp_min(1e-30).sqrt()
+        if isinstance(b1, float) and isinstance(b2, float):
+            correction = math.sqrt(1 - b2 ** t) / (1 - b1 ** t)
+        else:
+            correction = torch.sqrt(1 - torch.as_tensor(b2) ** t) / (1 - torch.as_tensor(b1) ** t)
+        new_p = p - (hp["lr"] * correction) * (m / (root + hp["eps"]))
+        frozen = None
+        if any(unused) or not isinstance(hp["in_group"], float):
+            # parameters without a gradient (or outside every group) keep value and state, like torch.optim.Adam
+            keep = torch.cat([torch.full((k,), 0.0 if miss else 1.0, dtype=p.dtype, device=p.device)
+                              for k, miss in zip(self._numels, unused)])
+            if not isinstance(hp["in_group"], float):
+                keep = keep * hp["in_group"]
+            frozen = keep == 0
+            new_p = torch.where(frozen, p, new_p)
+            m = torch.where(frozen, st["exp_avg"], m)
+            v = torch.where(frozen, st["exp_avg_sq"], v)
+        st["exp_avg"], st["exp_avg_sq"] = m, v
+        offsets = hp["offsets"]
+        views = [new_p[offsets[i]:offsets[i + 1]].view(shape) for i, shape in enumerate(self._shapes)]
+        self._flat = (new_p, views)
+        return views
 
     def detach_(self):
         """Cut the optimiser state from the autograd graph (truncated back-propagation, inner.py:110-125)."""
-        for group_state in self.state:
-            for st in group_state.values():
-                for key, value in st.items():
-                    if torch.is_tensor(value):
-                        st[key] = value.detach()
+        for key in ("exp_avg", "exp_avg_sq"):
+            if self.state[key] is not None:
+                self.state[key] = self.state[key].detach()
+        self._flat = None

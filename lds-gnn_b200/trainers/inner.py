@@ -33,6 +33,7 @@ class InnerProblemTrainer:
         self.model_params: OrderedDict = OrderedDict(model.named_parameters())
         self.optimizer: DifferentiableAdam = None
         self.data = data
+        self._rows_cache = {}
         self.reset_optimizer()
 
     def reset_weights(self):
@@ -48,17 +49,30 @@ class InnerProblemTrainer:
     def copy_model_params(self) -> Dict:
         return copy_detach_parameter_dict(self.model_params)
 
+    def _masked_rows(self, mask: torch.Tensor):
+        """(row indices, labels) of a boolean node mask, cached: `tensor[bool_mask]` costs a device->host sync per use."""
+        key = (mask.data_ptr(), mask._version, self.data.y.data_ptr())
+        hit = self._rows_cache.get(key)
+        if hit is None:
+            rows = mask.nonzero().flatten()
+            hit = self._rows_cache[key] = (rows, self.data.y[rows], mask)       # the mask is kept alive with its key
+            if len(self._rows_cache) > 8:
+                self._rows_cache.pop(next(iter(self._rows_cache)))
+        return hit[0], hit[1]
+
     def train_step(self, graph: torch.Tensor, mask: torch.Tensor = None) -> Metrics:
-        """One differentiable optimiser step on the training nodes (inner.py:55-74)."""
+        """One differentiable optimiser step on the training nodes (inner.py:55-74). One host sync: (loss, acc) together."""
         assert is_square_matrix(graph)
         with double_backward_path():
             predictions = self.model_forward(graph, is_train=True)
-        mask = mask or self.data.train_mask
-        loss = F.nll_loss(predictions[mask], self.data.y[mask])
-        acc = accuracy(predictions[mask], self.data.y[mask])
+        rows, labels = self._masked_rows(mask or self.data.train_mask)
+        selected = predictions.index_select(0, rows)
+        loss = F.nll_loss(selected, labels)
+        correct = (torch.argmax(selected.detach(), dim=-1) == labels).float().mean()
         new_params = self.optimizer.step(loss, params=self.model_params.values())
         self._update_model_params(list(new_params))
-        return Metrics(loss=loss.item(), acc=acc)
+        loss_value, acc = torch.stack((loss.detach(), correct)).tolist()
+        return Metrics(loss=loss_value, acc=acc)
 
     def model_forward(self, graph, is_train: bool = True) -> torch.Tensor:
         """The `gcn_predict_fct` of the outer step (inner.py:76-78): sets train/eval mode, runs the GCN at the

@@ -13,6 +13,12 @@
   Differences a caller can observe: `model.probs.grad` is not materialised (the gradient is consumed inside
   the update kernel) and dropout masks come from the device Philox stream instead of torch's generator.
 
+* FACTORED — the same plain LDS configuration when the fast weights DO carry unrolled history (every hyper step of
+  the real bilevel loop, src/trainers/bilevel.py:53-73): the graphs of the inner steps were sampled as
+  `FactoredGraph`s (`sample_for_unroll`), autograd runs over O(N h) tensors only — every product with a sampled
+  graph is K2 on the tensor cores, differentiable to any order — and the straight-through hypergradient of ALL
+  graphs of the unroll arrives as low-rank factor pairs that ONE K3+K4 pass folds into theta.
+
 * COMPOSABLE — everything else (custom predict functions, regularisers, other optimisers): the reference's
   own sequence `zero_grad / sample / predict / nll / backward / step / decay / project`, with sampling and
   propagation running on the same kernels through autograd Functions.
@@ -72,12 +78,14 @@ class OuterProblemTrainer:
                                  gamma=self.lr_decay) if self.lr_decay is not None else None
         self.refine_embeddings = refine_embeddings
         self.fused_enabled = True          # set False to force the composable route
+        self.factored_enabled = True       # set False to run unrolled hyper steps on the dense composable route
         self.first_order = False           # True: drop the hypergradient terms through unrolled inner steps (always fused)
         self.n_samples = 1                 # fused route: Bernoulli samples per outer step (mean of the straight-through gradients)
         self.last_route = None             # "fused" | "composable" (observability / tests)
         self._engine = None
         self._adam_state = None
         self._host_scalars = None
+        self._opt_rows = None
         if pretrain:
             self.pretrain_model()
 
@@ -88,7 +96,10 @@ class OuterProblemTrainer:
                    retain_graph: bool = True) -> Metrics:
         plan = self._fused_plan(gcn_predict_fct, mask)
         if plan is not None:
-            return self._train_step_fused(*plan)
+            route, inner, opt = plan
+            if route == "fused":
+                return self._train_step_fused(inner, opt)
+            return self._train_step_factored(inner, opt, retain_graph)
         return self._train_step_composable(gcn_predict_fct, mask, retain_graph)
 
     def _train_step_composable(self, gcn_predict_fct, mask, retain_graph) -> Metrics:
@@ -113,6 +124,69 @@ class OuterProblemTrainer:
         if self.refine_embeddings:
             self.model.refine()
         return Metrics(loss=loss.item(), acc=acc)
+
+    # ---- factored route (unrolled hypergradient) ---------------------------------------------------
+    def unroll_plan(self, inner) -> bool:
+        """True when the inner steps of `inner` may train on FactoredGraphs: the conditions of the fused step."""
+        return self.factored_enabled and not self.first_order and self._fused_plan(inner.model_forward, None) is not None
+
+    def sample_for_unroll(self, inner):
+        """The graph of one unrolled inner step (src/trainers/bilevel.py:103-107): factored when the hyper step that
+        will differentiate through it takes the factored route, else `sample()`."""
+        if self.unroll_plan(inner):
+            return self.model.sample_factored()
+        return self.model.sample()
+
+    def _train_step_factored(self, inner, opt, retain_graph) -> Metrics:
+        from .. import kernels
+        self.last_route = "factored"
+        model = self.model
+        model.train()
+        self.optimizer.zero_grad()
+        sink = model.factor_sink
+        sink.clear()
+        graph = model.sample_factored()
+        predictions = inner.model_forward(graph)
+        key = (self.opt_mask.data_ptr(), self.opt_mask._version)
+        if self._opt_rows is None or self._opt_rows[0] != key:          # `tensor[bool_mask]` would sync the host every step
+            rows = self.opt_mask.nonzero().flatten()
+            self._opt_rows = (key, rows, self.dataset.y[rows])
+        _, rows, labels = self._opt_rows
+        selected = predictions.index_select(0, rows)
+        loss = F.nll_loss(selected, labels)
+        correct = (torch.argmax(selected.detach(), dim=-1) == labels).float().mean()
+        loss.backward(retain_graph=retain_graph)
+        n = model._n
+        fa, fb, cvec = sink.collect(n, predictions.device)
+        sink.clear()
+        kind, group = opt
+        probs = model._probs_param()
+        if probs.grad is not None:
+            # part of the history was built on dense graphs (`sample()`): their share arrived in probs.grad through autograd.
+            # Add the factored share as a dense gradient and finish like the composable route.
+            dense = kernels.k3_dense_grad(n, fa, fb, cvec)
+            g = kernels.theta_full_to_triu(dense, n, sym_sum=True)
+            inside = (probs.detach() >= 0.0) & (probs.detach() <= 1.0)
+            probs.grad.add_(g * inside)
+            self.optimizer.step()
+            model.project_parameters()
+        else:
+            theta = model.theta_full()
+            if kind == _lib.OPT_SGD:
+                kernels.k3k4_theta_update_tc_(theta, n, fa, fb, cvec, group["lr"])
+            else:
+                st = self._adam_state
+                if st is None or st["m"].shape != theta.shape:
+                    st = self._adam_state = {"m": torch.zeros_like(theta), "v": torch.zeros_like(theta), "t": 0}
+                st["t"] += 1
+                kernels.k3k4_theta_update_(theta, n, fa, fb, cvec, group["lr"], opt_kind=kind, adam_m=st["m"], adam_v=st["v"],
+                                           betas=group["betas"], eps=group["eps"], t=st["t"])
+            model.mark_full_updated()
+            self.optimizer._opt_called = True
+        if self.lr_decayer is not None:
+            self.lr_decayer.step()
+        loss_value, acc = torch.stack((loss.detach(), correct)).tolist()          # one device->host transfer
+        return Metrics(loss=loss_value, acc=acc)
 
     # ---- fused route -----------------------------------------------------------------------------
     def _optimizer_kind(self):
@@ -154,12 +228,12 @@ class OuterProblemTrainer:
         # The fused step differentiates the DIRECT term only. If the fast weights still carry the unrolled inner
         # steps' history (src/trainers/inner.py:71-72), the reference's backward also flows through those steps into
         # the graphs they sampled; that needs autograd, so stay composable unless the caller opted for first order.
-        if not self.first_order and any(p.grad_fn is not None for p in owner.model_params.values()):
-            return None
         opt = self._optimizer_kind()
         if opt is None:
             return None
-        return owner, opt
+        if not self.first_order and any(p.grad_fn is not None for p in owner.model_params.values()):
+            return ("factored", owner, opt) if self.factored_enabled else None
+        return "fused", owner, opt
 
     def _get_engine(self, gcn):
         from .. import kernels

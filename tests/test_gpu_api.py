@@ -293,12 +293,19 @@ def test_train_step_contract():                                          # test_
     # a custom predict function cannot be fused: same API, composable route
     m2 = outer.train_step(lambda graph: gcn(data.x, graph))
     assert outer.last_route == "composable" and np.isfinite(m2.loss)
-    # fast weights with unrolled history keep the exact (autograd) route unless first_order is requested
+    # fast weights with unrolled history keep an exact (autograd) route unless first_order is requested: the factored
+    # route (here with a dense-graph history: that share arrives through probs.grad), or the composable one when disabled
     graph = outer.sample()
     inner.train_step(graph)
     assert any(p.grad_fn is not None for p in inner.model_params.values())
     outer.train_step(inner.model_forward)
+    assert outer.last_route == "factored"
+    inner.detach()                                                        # theta changed in place: drop the old history
+    inner.train_step(outer.sample())
+    outer.factored_enabled = False
+    outer.train_step(inner.model_forward)
     assert outer.last_route == "composable"
+    outer.factored_enabled = True
     inner.detach()
     outer.train_step(inner.model_forward)
     assert outer.last_route == "fused"
@@ -320,6 +327,53 @@ def test_hypergradient_reaches_first_graph_through_unrolled_inner_steps():   # t
     pred = inner.model_forward(outer.sample())
     F.nll_loss(pred[data.val_mask], data.y[data.val_mask]).backward()
     assert first.grad is None
+
+
+@pytest.mark.parametrize("name,optimizer,dropout,history", [
+    ("n33_twostep", "SGD", 0.0, "factored"), ("n257_h64", "SGD", 0.5, "factored"), ("n130_sparse", "Adam", 0.5, "factored"),
+    ("n130_sparse", "SGD", 0.5, "dense")])
+def test_factored_unrolled_hyper_step_matches_composable_route(name, optimizer, dropout, history):
+    """One bilevel block (src/trainers/bilevel.py:53-73): tau inner steps with the differentiable Adam, then the hyper step
+    whose backward flows through all of them into every sampled graph. The factored route (O(N h) autograd tensors, K2 for
+    every product, one K3+K4 pass over the concatenated factor pairs) must give the composable route's theta — dense
+    N x N autograd through the same unroll with the same Philox graphs and the same dropout masks. Two blocks in a row, so
+    the second starts from the first one's update; `history = dense` mixes dense inner graphs into a factored hyper step."""
+    from lds_gnn_b200.models.sampling import PHILOX
+    from lds_gnn_b200.trainers.bilevel import BilevelProblemRunner
+    g = load_golden(name)
+    results = {}
+    for route in ("factored", "composable"):
+        kw = dict(eps=1e-3) if optimizer == "Adam" else {}
+        data, gcn, inner, model, outer = _setup(g, lr=0.05 if optimizer == "Adam" else 0.5, lr_decay=0.9, dropout=dropout,
+                                                optimizer=optimizer, **kw)
+        with torch.no_grad():                                   # interior probabilities: every graph of the unroll is random
+            model.probs.mul_(0.6).add_(0.2)
+        outer.factored_enabled = route == "factored"
+        runner = BilevelProblemRunner(inner, outer, data)
+        PHILOX.manual_seed(7)
+        torch.manual_seed(21)                                   # dropout masks of the inner steps and the hyper forward
+        metrics = []
+        for block in range(2):
+            for _ in range(3):
+                if route == "factored" and history == "dense":
+                    inner.train_step(outer.sample())
+                else:
+                    runner.inner_opt_step()
+            before = model.probs.detach().clone()
+            metrics.append(outer.train_step(inner.model_forward))
+            assert outer.last_route == route
+            inner.detach(); outer.detach()
+            step = (model.probs.detach() - before).abs().max().item()
+            assert step > 0
+        results[route] = (metrics, model.probs.detach().clone(), outer.get_learning_rates(), step)
+    mf, pf, lf, _ = results["factored"]
+    mc, pc, lc, step = results["composable"]
+    assert lf == lc
+    for a, b in zip(mf, mc):
+        assert abs(a.loss - b.loss) < 1e-4 and abs(a.acc - b.acc) < 1e-6
+    assert pf.min() >= 0 and pf.max() <= 1
+    tol = 1e-3 * step + 1e-6 if optimizer == "SGD" else 2e-3 * step + 1e-5
+    assert (pf - pc).abs().max().item() <= tol, ((pf - pc).abs().max().item(), step)
 
 
 def test_empirical_mean_loss_and_bilevel_runner_smoke():

@@ -232,7 +232,7 @@ def test_differentiable_adam_tracks_torch_adam_and_is_differentiable():
     (cur[0].sum()).backward()
     assert scale.grad is not None and scale.grad.abs() > 0   # hypergradient flows through the unrolled updates
     dopt.detach_()
-    assert all(not v.requires_grad for st in dopt.state for s in st.values() for v in s.values() if torch.is_tensor(v))
+    assert all(not v.requires_grad for v in dopt.state.values() if torch.is_tensor(v))
 
 
 def test_directed_model_and_state_dict_on_cpu():         # tst/models/test_bernoulli_model.py:113-128
@@ -387,3 +387,69 @@ def test_knn_graph_matches_sklearn(metric, loop):
     assert np.array_equal(sym, np.maximum(ref, ref.T))
     with pytest.raises(ValueError):
         knn_graph_dense(torch.as_tensor(x), 10, metric="manhattan")
+
+
+def test_factored_unroll_hypergradient_equals_dense_autograd(monkeypatch):
+    """Host logic of the factored unrolled hypergradient (src/trainers/bilevel.py:103-113, inner.py:55-74, outer.py:57-87):
+    with the two kernels it calls replaced by torch stand-ins IN THIS TEST (fp64, CPU), the factor pairs deposited by the
+    any-order-differentiable Functions must reproduce the dense autograd gradient on every sampled graph of the unroll —
+    second-order terms through the differentiable Adam included."""
+    import torch.nn.functional as F
+    from lds_gnn_b200 import kernels
+    from lds_gnn_b200.models.gcn import MetaDenseGCN
+    from lds_gnn_b200.models.sampling import FactoredGraph, FactorSink, SampleHandle
+    from lds_gnn_b200.trainers.inner import InnerProblemTrainer
+    from lds_gnn_b200.utils.graph import DenseData
+    monkeypatch.setattr(kernels, "k2_propagate", lambda adj, n, q, *a, **k: adj @ q)
+    torch.manual_seed(3)
+    dt = torch.float64
+    n, f, h, c, steps = 30, 11, 8, 3, 3
+    x = torch.rand(n, f, dtype=dt)
+    y = torch.randint(0, c, (n,))
+    train_mask = torch.zeros(n, dtype=torch.bool); train_mask[:12] = True
+    val_mask = torch.zeros(n, dtype=torch.bool); val_mask[12:22] = True
+    data = DenseData(x=x, y=y, train_mask=train_mask, val_mask=val_mask, test_mask=val_mask, num_classes=c)
+    samples = []
+    for _ in range(steps + 1):
+        s = (torch.rand(n, n) < 0.2).to(dt).triu(1)
+        samples.append(s + s.t() + torch.diag((torch.rand(n) < 0.5).to(dt)))
+
+    def run(factored):
+        torch.manual_seed(11)
+        gcn = MetaDenseGCN(f, h, c, dropout=0.5).to(dt)
+        inner = InnerProblemTrainer(gcn, data, lr=0.05, weight_decay=5e-3)
+        link = torch.zeros(1, dtype=dt, requires_grad=True)
+        sink = FactorSink()
+        graphs = []
+        for s in samples:
+            if factored:
+                looped = s.clone(); looped.fill_diagonal_(1.0)
+                graphs.append(FactoredGraph(SampleHandle(n, looped, looped.sum(1), None, 0, 0), link, sink))
+            else:
+                graphs.append(s.clone().requires_grad_(True))
+        torch.manual_seed(5)                                   # same dropout masks in both runs
+        for g in graphs[:-1]:
+            inner.train_step(g)
+        assert sink.empty()                                    # inner steps (create_graph backward) send nothing to theta
+        pred = inner.model_forward(graphs[-1])
+        loss = F.nll_loss(pred[val_mask], y[val_mask])
+        loss.backward()
+        if factored:
+            fa, fb, cvec = sink.collect(n, "cpu")
+            assert fa.shape[1] == fb.shape[1] and fa.shape[1] >= 2 * (h + c)
+            dense = fa @ fb.t() + cvec[:, None]
+        else:
+            dense = sum(g.grad for g in graphs)
+        # what theta_triu receives is the mirror backward g_ij + g_ji (src/utils/graph.py:35-37); the factored backward uses
+        # A_tilde = A_tilde^T, so single entries of its second-order deposits sit at the transposed position
+        dense = dense + dense.t()
+        dense.fill_diagonal_(0.0)
+        return loss.item(), dense, [p.detach() for p in inner.model_params.values()]
+
+    loss_d, grad_d, w_d = run(False)
+    loss_f, grad_f, w_f = run(True)
+    assert abs(loss_d - loss_f) < 1e-12
+    for a, b in zip(w_d, w_f):
+        assert torch.allclose(a, b, atol=1e-12)
+    assert grad_d.abs().max() > 0
+    assert (grad_d - grad_f).abs().max() <= 1e-10 * grad_d.abs().max()
