@@ -94,6 +94,13 @@ int32_t lds_k1_sample_normalize(const float* theta_full, int64_t ld_theta, int32
                                 void* a_out, int64_t ld_a, float* sample_out, int64_t ld_s,
                                 float* deg_out, float* rsqrt_out, uint32_t flags, void* stream);
 
+/* Same pass with the Philox step taken from DEVICE memory: step = *step_base + step_offset, read by the kernel. A CUDA graph
+ * captured over a whole bilevel block (tau inner steps + the hyper step, src/trainers/bilevel.py:53-73) then draws fresh
+ * graphs on every replay; the block bumps the counter itself. Same draws as lds_k1_sample_normalize at that step. */
+int32_t lds_k1_sample_normalize_dstep(const float* theta_full, int64_t ld_theta, int32_t n, int32_t row0, int32_t rows,
+                                      uint64_t seed, const uint64_t* step_base, uint64_t step_offset, uint32_t sample,
+                                      void* a_out, int64_t ld_a, float* deg_out, float* rsqrt_out, void* stream);
+
 /* ---- K2 (a8's torch.mm(dense_adj, .), src/models/layers.py:44, and its transposes in backward):
  *   z_out[rows][width] = scale_out * ( A[rows][n] @ (scale_in * p[n][width]) )
  * A bf16 (TMA -> tcgen05.mma, fp32 accumulation in TMEM), p split into bf16 hi+lo terms.
@@ -104,6 +111,15 @@ int32_t lds_k2_propagate(const void* a, int64_t ld_a, int32_t n, int32_t rows,
                          const float* scale_in, const float* scale_out,
                          float* z_out, int64_t ld_z,
                          void* workspace, int64_t workspace_bytes, uint32_t flags, void* stream);
+
+/* ---- sparse feature products of the unrolled inner steps: MetaLinear's F.linear(dropout(X), W0) and its autograd transposes
+ * (src/models/layers.py:43, src/models/gcn.py:27-28) for bag-of-words X kept in CSR.
+ *   y[i][c] = sum_{k in [ptr[i], ptr[i+1])} val[perm ? perm[k] : k] * b[idx[k] * ldb_row + c * ldb_col],  i < rows, c < w
+ * (ptr, idx) = CSR of S; for S = X^T pass the CSC arrays of X and `perm` = position of each entry in X's CSR value order, so
+ * one (dropout-scaled) value array serves both directions. b may be a strided view (e.g. W0^T: ldb_row = 1, ldb_col = F). */
+int32_t lds_spmm_csr(const int32_t* ptr, const int32_t* idx, const float* val, const int32_t* perm, int32_t rows,
+                     const float* b, int64_t ldb_row, int64_t ldb_col, int32_t w,
+                     float* y, int64_t ldy, void* stream);
 
 /* ---- K3+K4 (a10's theta part, a11): closed-form straight-through gradient + optimiser step + projection
  * for rows [row0, row0+rows):   g_ij = fa_i.fb_j + fb_i.fa_j + c_i + c_j  (i != j),  0 on the diagonal,

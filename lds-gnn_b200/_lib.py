@@ -31,6 +31,10 @@ SIGNATURES = {
     "lds_k1_sample_normalize": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_uint64, c_uint64, c_uint32,
                                           c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
                                           c_uint32, c_void_p]),
+    "lds_k1_sample_normalize_dstep": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_uint64, c_void_p, c_uint64, c_uint32,
+                                                c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "lds_spmm_csr": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int32,
+                               c_void_p, c_int64, c_void_p]),
     "lds_k2_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32]),
     "lds_k2_propagate": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_void_p,
                                    c_void_p, c_int64, c_void_p, c_int64, c_uint32, c_void_p]),

@@ -106,7 +106,7 @@ constexpr int K1_UNROLL = 4;      // column quads per thread per trip: 8 x 16-by
 // `u < clamp(theta, 0, 1)` with u = (w >> 8) * 2^-24 is evaluated exactly in integers: (w >> 8) < ceil(theta * 2^24)
 // (the saturating round-up conversion gives 0 for theta <= 0 or NaN and > 2^24 for theta > 1, which is the clamp).
 __device__ __forceinline__ void k1_quad_fast(int j0, const float (&th0)[4], const float (&th1)[4], int p, const PhiloxRounds& R,
-                                             __nv_bfloat16* __restrict__ a0, __nv_bfloat16* __restrict__ a1,
+                                             uint32_t c2, uint32_t c3, __nv_bfloat16* __restrict__ a0, __nv_bfloat16* __restrict__ a1,
                                              uint32_t& cnt0, uint32_t& cnt1) {
   uint32_t b0[4], b1[4];
 #pragma unroll
@@ -114,7 +114,7 @@ __device__ __forceinline__ void k1_quad_fast(int j0, const float (&th0)[4], cons
     const int q = (j0 >> 1) + b;
     const bool upper = p < q;                       // p == q cannot happen here (no diagonal element in the quad)
     uint32_t w[4];
-    philox4x32_10_rk((uint32_t)(upper ? q : p), (uint32_t)(upper ? p : q), R, w);
+    philox4x32_10_rk((uint32_t)(upper ? q : p), (uint32_t)(upper ? p : q), R, c2, c3, w);
     const uint32_t w01 = upper ? w[1] : w[2], w10 = upper ? w[2] : w[1];
     b0[2 * b]     = ((w[0] >> 8) < __float2uint_ru(th0[2 * b] * 16777216.f)) ? 1u : 0u;
     b0[2 * b + 1] = ((w01 >> 8)  < __float2uint_ru(th0[2 * b + 1] * 16777216.f)) ? 1u : 0u;
@@ -196,12 +196,23 @@ __device__ __forceinline__ void k1_quad(int j0, const float (&th0)[4], const flo
 // One CTA per global row pair (2p, 2p+1). A thread owns column quads; each quad = two 2x2 Philox blocks.
 // All of a trip's 128-bit loads are issued before the first is consumed: the kernel is bound by memory-level
 // parallelism (each quad costs ~200 ALU instructions after its load), not by issue slots.
-template <bool EXPLICIT_U>
+// STEP_DEV: the Philox step is *step_base + step_offset, read here from device memory (a captured CUDA graph then draws a
+// fresh graph on every replay); otherwise the host-prepared counter words are used and the code is unchanged.
+template <bool EXPLICIT_U, bool STEP_DEV>
 __global__ void __launch_bounds__(K1_THREADS, 3)
 k1_sample_kernel(const float* __restrict__ theta, int64_t ldt, int n, int row0, int rows,
-                 const PhiloxKey key, const __grid_constant__ PhiloxRounds rounds, const float* __restrict__ U, int64_t ldu,
+                 const PhiloxKey key_in, const __grid_constant__ PhiloxRounds rounds, const float* __restrict__ U, int64_t ldu,
                  __nv_bfloat16* __restrict__ A, int64_t lda, float* __restrict__ S, int64_t lds_,
-                 float* __restrict__ deg, float* __restrict__ rs) {
+                 float* __restrict__ deg, float* __restrict__ rs,
+                 const unsigned long long* __restrict__ step_base, unsigned long long step_offset) {
+  PhiloxKey key = key_in;
+  uint32_t c2 = rounds.c2, c3 = rounds.c3;
+  if (STEP_DEV) {
+    const unsigned long long step = *step_base + step_offset;
+    c2 = (uint32_t)(step & 0xffffffffull);
+    c3 = (c3 & 0xffffu) | (uint32_t)(((step >> 32) & 0xffffull) << 16);
+    key.c2 = c2; key.c3 = c3;
+  }
   const int p = (row0 >> 1) + blockIdx.x;             // global row-pair index
   const int gi0 = 2 * p, gi1 = 2 * p + 1;             // global rows
   const int li0 = gi0 - row0, li1 = gi1 - row0;       // local rows in this shard
@@ -234,7 +245,7 @@ k1_sample_kernel(const float* __restrict__ theta, int64_t ldt, int n, int row0, 
       const int j0 = base + u * 4 * K1_THREADS;
       if (j0 >= ncols) continue;
       const bool fast = !EXPLICIT_U && has1 && S == nullptr && A != nullptr && (j0 + 3 < n) && (gi1 < j0 || gi0 > j0 + 3);
-      if (fast) k1_quad_fast(j0, th0[u], th1[u], p, rounds, A + (int64_t)li0 * lda + j0, A + (int64_t)li1 * lda + j0, cnt0, cnt1);
+      if (fast) k1_quad_fast(j0, th0[u], th1[u], p, rounds, c2, c3, A + (int64_t)li0 * lda + j0, A + (int64_t)li1 * lda + j0, cnt0, cnt1);
       else k1_quad<EXPLICIT_U>(j0, th0[u], th1[u], p, gi0, gi1, li0, li1, has1, n, key, U, ldu, A, lda, S, lds_, sum0, sum1);
     }
   }
@@ -294,11 +305,12 @@ extern "C" int32_t lds_theta_stats(const float* theta_full, int64_t ld, int32_t 
   return LDS_OK;
 }
 
-extern "C" int32_t lds_k1_sample_normalize(const float* theta_full, int64_t ld_theta, int32_t n, int32_t row0, int32_t rows,
-                                           uint64_t seed, uint64_t step, uint32_t sample,
-                                           const float* u_explicit, int64_t ld_u,
-                                           void* a_out, int64_t ld_a, float* sample_out, int64_t ld_s,
-                                           float* deg_out, float* rsqrt_out, uint32_t flags, void* stream) {
+static int32_t k1_launch(const float* theta_full, int64_t ld_theta, int32_t n, int32_t row0, int32_t rows,
+                         uint64_t seed, uint64_t step, const uint64_t* step_base, uint32_t sample,
+                         const float* u_explicit, int64_t ld_u,
+                         void* a_out, int64_t ld_a, float* sample_out, int64_t ld_s,
+                         float* deg_out, float* rsqrt_out, uint32_t flags, void* stream) {
+  using namespace lds;
   LDS_CHECK_ARG(theta_full && deg_out && rsqrt_out, "lds_k1_sample_normalize: null pointer");
   LDS_CHECK_ARG(n > 0 && rows > 0 && row0 >= 0 && row0 + rows <= n, "lds_k1_sample_normalize: rows [%d, %d) outside [0, %d)", row0, row0 + rows, n);
   LDS_CHECK_ARG((row0 & 1) == 0, "lds_k1_sample_normalize: row0 must be even (got %d)", row0);
@@ -311,14 +323,34 @@ extern "C" int32_t lds_k1_sample_normalize(const float* theta_full, int64_t ld_t
   if (sample_out) LDS_CHECK_ARG(ld_s >= n, "lds_k1_sample_normalize: ld_s must be >= n");
   const bool explicit_u = (flags & LDS_K1_EXPLICIT_U) != 0;
   if (explicit_u) LDS_CHECK_ARG(u_explicit && ld_u >= n, "lds_k1_sample_normalize: LDS_K1_EXPLICIT_U needs u_explicit with ld_u >= n");
-  const PhiloxKey key = philox_key(seed, step, LDS_STREAM_EDGES, sample);
+  const PhiloxKey key = philox_key(seed, step_base ? 0 : step, LDS_STREAM_EDGES, sample);
   const PhiloxRounds rounds = philox_rounds(key);
   const int pairs = (rows + 1) / 2;
   auto* A = reinterpret_cast<__nv_bfloat16*>(a_out);
+  auto* sb = reinterpret_cast<const unsigned long long*>(step_base);
   if (explicit_u)
-    k1_sample_kernel<true><<<pairs, K1_THREADS, 0, (cudaStream_t)stream>>>(theta_full, ld_theta, n, row0, rows, key, rounds, u_explicit, ld_u, A, ld_a, sample_out, ld_s, deg_out, rsqrt_out);
+    k1_sample_kernel<true, false><<<pairs, K1_THREADS, 0, (cudaStream_t)stream>>>(theta_full, ld_theta, n, row0, rows, key, rounds, u_explicit, ld_u, A, ld_a, sample_out, ld_s, deg_out, rsqrt_out, nullptr, 0ull);
+  else if (step_base)
+    k1_sample_kernel<false, true><<<pairs, K1_THREADS, 0, (cudaStream_t)stream>>>(theta_full, ld_theta, n, row0, rows, key, rounds, nullptr, 0, A, ld_a, sample_out, ld_s, deg_out, rsqrt_out, sb, (unsigned long long)step);
   else
-    k1_sample_kernel<false><<<pairs, K1_THREADS, 0, (cudaStream_t)stream>>>(theta_full, ld_theta, n, row0, rows, key, rounds, nullptr, 0, A, ld_a, sample_out, ld_s, deg_out, rsqrt_out);
+    k1_sample_kernel<false, false><<<pairs, K1_THREADS, 0, (cudaStream_t)stream>>>(theta_full, ld_theta, n, row0, rows, key, rounds, nullptr, 0, A, ld_a, sample_out, ld_s, deg_out, rsqrt_out, nullptr, 0ull);
   LDS_CHECK_LAUNCH("k1_sample_kernel");
   return LDS_OK;
+}
+
+extern "C" int32_t lds_k1_sample_normalize(const float* theta_full, int64_t ld_theta, int32_t n, int32_t row0, int32_t rows,
+                                           uint64_t seed, uint64_t step, uint32_t sample,
+                                           const float* u_explicit, int64_t ld_u,
+                                           void* a_out, int64_t ld_a, float* sample_out, int64_t ld_s,
+                                           float* deg_out, float* rsqrt_out, uint32_t flags, void* stream) {
+  return k1_launch(theta_full, ld_theta, n, row0, rows, seed, step, nullptr, sample, u_explicit, ld_u, a_out, ld_a, sample_out, ld_s,
+                   deg_out, rsqrt_out, flags, stream);
+}
+
+extern "C" int32_t lds_k1_sample_normalize_dstep(const float* theta_full, int64_t ld_theta, int32_t n, int32_t row0, int32_t rows,
+                                                 uint64_t seed, const uint64_t* step_base, uint64_t step_offset, uint32_t sample,
+                                                 void* a_out, int64_t ld_a, float* deg_out, float* rsqrt_out, void* stream) {
+  LDS_CHECK_ARG(step_base, "lds_k1_sample_normalize_dstep: null step_base");
+  return k1_launch(theta_full, ld_theta, n, row0, rows, seed, step_offset, step_base, sample, nullptr, 0, a_out, ld_a, nullptr, 0,
+                   deg_out, rsqrt_out, 0u, stream);
 }

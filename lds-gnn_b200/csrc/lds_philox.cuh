@@ -52,9 +52,10 @@ inline PhiloxRounds philox_rounds(const PhiloxKey& key) {
   return r;
 }
 
-__device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c1, const PhiloxRounds& R, uint32_t out[4]) {
+// c2 / c3 (the step / stream / sample words of the counter) are passed explicitly so a kernel can take the step from
+// device memory (lds_k1_sample_normalize_dstep); the plain overload below uses the host-prepared ones.
+__device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c1, const PhiloxRounds& R, uint32_t c2, uint32_t c3, uint32_t out[4]) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
-  uint32_t c2 = R.c2, c3 = R.c3;
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
     const uint64_t p0 = (uint64_t)M0 * c0;
@@ -67,6 +68,9 @@ __device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c1, const
     c2 = n2;
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c1, const PhiloxRounds& R, uint32_t out[4]) {
+  philox4x32_10_rk(c0, c1, R, R.c2, R.c3, out);
 }
 
 // Rolled variant for code that runs once per launch on a few warps (row epilogues): 10x less instruction fetch.

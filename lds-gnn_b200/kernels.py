@@ -78,9 +78,10 @@ def theta_stats(full, n):
 
 # ----------------------------------------------------------------------------- K1
 def k1_sample_normalize(theta_full, n, seed, step, sample=0, u=None, want_adj=True, want_sample=False,
-                        row0=0, rows=None):
+                        row0=0, rows=None, step_base=None):
     """Fused sample / mirror / self-loop / degree / rsqrt pass. Returns (A_tilde bf16 [rows, ld] or None,
-    raw sample fp32 [rows, n] or None, deg [rows], rsqrt [rows])."""
+    raw sample fp32 [rows, n] or None, deg [rows], rsqrt [rows]). With `step_base` (int64 device tensor [1]) the kernel
+    reads the Philox step from device memory as step_base[0] + step (CUDA-graph replays draw fresh graphs)."""
     _lib.require_device()
     _f32(theta_full, "theta_full")
     rows = n - row0 if rows is None else rows
@@ -91,6 +92,13 @@ def k1_sample_normalize(theta_full, n, seed, step, sample=0, u=None, want_adj=Tr
     deg = torch.empty(rows, dtype=torch.float32, device=dev)
     rs = torch.empty(rows, dtype=torch.float32, device=dev)
     flags = 0
+    if step_base is not None:
+        if u is not None or want_sample or step_base.dtype != torch.int64 or not step_base.is_cuda:
+            raise TypeError("step_base: int64 CUDA tensor, without explicit uniforms / dense sample output")
+        _lib.check(_lib.load().lds_k1_sample_normalize_dstep(
+            _ptr(theta_full), theta_full.stride(0), n, row0, rows, int(seed), _ptr(step_base), int(step), int(sample),
+            _ptr(adj), ld, _ptr(deg), _ptr(rs), _stream()), "lds_k1_sample_normalize_dstep")
+        return adj, smp, deg, rs
     if u is not None:
         _f32(u, "u")
         flags |= _lib.K1_EXPLICIT_U
@@ -134,6 +142,21 @@ def k2_propagate(adj, n, p, scale_in=None, scale_out=None, flags=0, out=None):
         _ptr(adj), adj.stride(0), n, rows, _ptr(p), p.stride(0), width, _ptr(scale_in), _ptr(scale_out),
         _ptr(z), z.stride(0), _ptr(ws), need, int(flags), _stream()), "lds_k2_propagate")
     return z
+
+
+# ----------------------------------------------------------------------------- sparse feature products
+def spmm_csr(ptr, idx, val, perm, rows, b):
+    """y[rows, w] = S @ b for S in CSR (ptr, idx, val[perm]); b [cols, w] fp32, any strides (src/models/layers.py:43)."""
+    _lib.require_device()
+    _f32(b, "b")
+    _f32(val, "val")
+    if ptr.dtype != torch.int32 or idx.dtype != torch.int32 or (perm is not None and perm.dtype != torch.int32):
+        raise TypeError("CSR index arrays must be int32")
+    w = b.shape[1]
+    y = torch.empty((rows, w), dtype=torch.float32, device=b.device)
+    _lib.check(_lib.load().lds_spmm_csr(_ptr(ptr), _ptr(idx), _ptr(val), _ptr(perm), int(rows), _ptr(b), b.stride(0), b.stride(1),
+                                        int(w), _ptr(y), y.stride(0), _stream()), "lds_spmm_csr")
+    return y
 
 
 # ----------------------------------------------------------------------------- K3 + K4

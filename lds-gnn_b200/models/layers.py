@@ -33,11 +33,93 @@ class MetaModule(nn.Module):
     """Marker base class: modules whose forward accepts `params=` overrides."""
 
 
+class SparseFeatureMatrix:
+    """CSR + CSC index structure of a static, mostly-zero feature matrix (bag of words, ~1 % dense), built once per tensor.
+    The CSC side stores, for every entry, its position in the CSR value order (`perm`), so one per-step value array — the
+    dropout-scaled values — serves X' B and X'^T B alike."""
+
+    def __init__(self, x: torch.Tensor):
+        csr = x.detach().to(torch.float32).to_sparse_csr()
+        self.rows, self.cols = int(x.shape[0]), int(x.shape[1])
+        crow, col = csr.crow_indices(), csr.col_indices()
+        self.crow, self.col = crow.to(torch.int32).contiguous(), col.to(torch.int32).contiguous()
+        self.val = csr.values().to(torch.float32).contiguous()
+        row_of = torch.repeat_interleave(torch.arange(self.rows, device=x.device), crow[1:] - crow[:-1])
+        order = torch.argsort(col.to(torch.int64) * self.rows + row_of)           # column-major order of the entries
+        self.perm = order.to(torch.int32).contiguous()
+        self.csc_row = row_of[order].to(torch.int32).contiguous()
+        counts = torch.bincount(col.to(torch.int64), minlength=self.cols)
+        self.csc_ptr = torch.cat([counts.new_zeros(1), counts.cumsum(0)]).to(torch.int32).contiguous()
+
+    def with_values(self, values: torch.Tensor) -> "SparseFeatures":
+        return SparseFeatures(self, values)
+
+
+class SparseFeatures:
+    """X' = the static structure + this step's (dropout-scaled) values."""
+
+    def __init__(self, matrix: SparseFeatureMatrix, values: torch.Tensor):
+        self.matrix, self.values = matrix, values.contiguous()
+
+    def size(self, dim=None):
+        shape = torch.Size((self.matrix.rows, self.matrix.cols))
+        return shape if dim is None else shape[dim]
+
+    def product(self, b: torch.Tensor, transposed: bool) -> torch.Tensor:
+        from .. import kernels
+        m = self.matrix
+        if transposed:
+            return kernels.spmm_csr(m.csc_ptr, m.csc_row, self.values, m.perm, m.cols, b)
+        return kernels.spmm_csr(m.crow, m.col, self.values, None, m.rows, b)
+
+
+class _SparseProduct(torch.autograd.Function):
+    """Y = S B with S = X' (or X'^T) constant: linear in B, so the backward is the transposed product through this same
+    Function — differentiable to any order, which the unrolled hypergradient needs (src/trainers/inner.py:71)."""
+
+    @staticmethod
+    def forward(ctx, b, feats, transposed):
+        ctx.feats, ctx.transposed = feats, transposed
+        return feats.product(b, transposed)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return _SparseProduct.apply(dy, ctx.feats, not ctx.transposed), None, None
+
+
+SMALL_LINEAR_ELEMENTS = 1 << 20      # N * out * in below which MetaLinear runs as broadcast-multiply-reduce (CUDA only)
+SPARSE_DENSITY = 0.25          # same rule as the fused outer step (kernels.OuterStep.SPARSE_DENSITY)
+
+
+def sparse_companion(x: torch.Tensor):
+    """The SparseFeatureMatrix of a static CUDA feature tensor (cached on the tensor), or None when it is too dense."""
+    cached = getattr(x, "_lds_sparse", None)
+    if cached is None:
+        cached = False
+        if x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and not x.requires_grad:
+            if int((x != 0).sum().item()) < SPARSE_DENSITY * x.numel():
+                cached = SparseFeatureMatrix(x)
+        x._lds_sparse = cached
+    return cached or None
+
+
 class MetaLinear(nn.Linear, MetaModule):
     def forward(self, input, params=None):
         if params is None:
             params = OrderedDict(self.named_parameters())
-        return F.linear(input, params["weight"], params.get("bias", None))
+        if isinstance(input, SparseFeatures):
+            out = _SparseProduct.apply(params["weight"].t(), input, False)
+            bias = params.get("bias", None)
+            return out if bias is None else out + bias
+        weight = params["weight"]
+        if input.is_cuda and input.dim() == 2 and input.shape[0] * weight.shape[0] * weight.shape[1] <= SMALL_LINEAR_ELEMENTS:
+            # a skinny layer (hidden x classes): as a matmul its weight gradient is a [C x N] x [N x h] product that cuBLAS
+            # runs as a 30 us "large-K" SGEMM for a 6 x 16 result, 16 times per bilevel block. As broadcast-multiply-reduce
+            # every order of its backward is a ~2 us elementwise + reduction pair.
+            out = (input.unsqueeze(1) * weight.unsqueeze(0)).sum(dim=2)
+            bias = params.get("bias", None)
+            return out if bias is None else out + bias
+        return F.linear(input, weight, params.get("bias", None))
 
 
 class _Propagate(torch.autograd.Function):

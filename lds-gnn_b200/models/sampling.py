@@ -29,22 +29,44 @@ class SPARSIFICATION(Enum):
 
 class PhiloxState:
     """Seed + step counter of the device RNG. The seed is drawn from torch's global generator on first use,
-    so `torch.manual_seed` (what sacred's seeding does) makes runs reproducible."""
+    so `torch.manual_seed` (what sacred's seeding does) makes runs reproducible.
+
+    While a bilevel block is being captured into a CUDA graph (`begin_capture`), `next_step` hands out OFFSETS relative to
+    a device-resident counter instead of absolute steps: the sampling kernel reads the counter itself, so every replay of
+    the graph draws fresh graphs (the host sets the counter to `step` before a replay and advances `step` after it)."""
 
     def __init__(self):
         self.seed = None
         self.step = 0
+        self.capture_base = None         # int64 device tensor [1] while capturing, else None
+        self.capture_draws = 0
 
     def manual_seed(self, seed: int):
         self.seed = int(seed) & ((1 << 64) - 1)
         self.step = 0
 
-    def next_step(self):
+    def _ensure_seed(self):
         if self.seed is None:
             self.seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+
+    def next_step(self):
+        self._ensure_seed()
+        if self.capture_base is not None:
+            offset = self.capture_draws
+            self.capture_draws += 1
+            return self.seed, offset
         step = self.step
         self.step += 1
         return self.seed, step
+
+    def begin_capture(self, base: Tensor):
+        self._ensure_seed()
+        self.capture_base, self.capture_draws = base, 0
+
+    def end_capture(self) -> int:
+        draws = self.capture_draws
+        self.capture_base, self.capture_draws = None, 0
+        return draws
 
 
 PHILOX = PhiloxState()
@@ -208,7 +230,7 @@ def sample_factored(theta_full: Tensor, n: int, link: Tensor, sink: FactorSink) 
     """The LDS sampling path (same Philox draws, same step counter as `sample_graph`) without the dense fp32 sample."""
     from .. import kernels
     seed, step = PHILOX.next_step()
-    adj, _, deg, rs = kernels.k1_sample_normalize(theta_full, n, seed, step, want_sample=False)
+    adj, _, deg, rs = kernels.k1_sample_normalize(theta_full, n, seed, step, want_sample=False, step_base=PHILOX.capture_base)
     return FactoredGraph(SampleHandle(n, adj, deg, rs, seed, step), link, sink)
 
 

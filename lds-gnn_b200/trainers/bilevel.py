@@ -26,6 +26,10 @@ class BilevelProblemRunner:
         self.graph_state_dict = None
         self.n_samples_empirical_mean = n_samples_empirical_mean
         self.logger = setup_basic_logger()
+        # Replay aligned blocks (tau inner steps + the hyper step) from one captured CUDA graph when the plain LDS configuration
+        # allows it (trainers/graph_block.py); LDS_GRAPH_BLOCKS=0 or `graph_blocks = False` keeps the step-by-step loop.
+        self.graph_blocks = os.environ.get("LDS_GRAPH_BLOCKS", "1") != "0"
+        self._blocks = {}
 
     def train(self, patience: int, hyper_gradient_interval: int, inner_loop_max_epochs: int = 400,
               outer_loop_max_epochs: int = 400, sacred_runner=None):
@@ -37,7 +41,11 @@ class BilevelProblemRunner:
             self.inner_trainer.reset_weights()
             self.inner_trainer.reset_optimizer()
             self.logger.info("Starting new outer loop...")
+            tau = max(1, hyper_gradient_interval)
             while not inner_stopper.abort:                     # judged on the training loss
+                if self.graph_blocks and current_step % tau == 1 % tau and self._block_eligible():
+                    current_step = self._run_block(tau, current_step, inner_stopper, sacred_runner)
+                    continue
                 train_metrics = self.inner_opt_step()
                 inner_stopper.update(train_metrics.loss, model_params=self.inner_trainer.copy_model_params())
                 if sacred_runner is not None:
@@ -65,6 +73,48 @@ class BilevelProblemRunner:
         self.logger.info(f"Ended training after {outer_step} steps...")
         self.gcn_params, self.graph_state_dict = outer_stopper.model_params
 
+    # ---- captured blocks ---------------------------------------------------------------------------
+    def _block_eligible(self) -> bool:
+        from .graph_block import CapturedBilevelBlock
+        return CapturedBilevelBlock.eligible(self)
+
+    def _run_block(self, tau: int, current_step: int, inner_stopper: EarlyStopping, sacred_runner) -> int:
+        """Steps current_step .. current_step + tau - 1 of the reference loop (the last one triggers the hyper step) from ONE
+        graph replay; the per-step early stopping is applied afterwards, and if the reference would have stopped before the
+        block's hyper step, that step is undone. Returns the new current_step."""
+        from .graph_block import CapturedBilevelBlock
+        block = self._blocks.get(tau)
+        if block is None:
+            block = self._blocks[tau] = CapturedBilevelBlock(self, tau)
+        metrics = block.replay()
+        steps_done, last_kept = 0, None
+        for k in range(tau):
+            train_metrics = metrics[k]
+            token = ("weights after step", k)                  # resolved to real tensors once, after the loop
+            inner_stopper.update(train_metrics.loss, model_params=token)
+            if inner_stopper.model_params is token:            # the stopper kept this step's weights (early_stopping.py:26-30)
+                last_kept = k
+            if sacred_runner is not None:
+                sacred_runner.log_scalar("loss.train", train_metrics.loss, step=current_step)
+                sacred_runner.log_scalar("acc.train", train_metrics.acc, step=current_step)
+                sacred_runner.log_scalar("Memory Usage (%)", _memory_percent())
+            self.logger.info(f"Model Optimization Step {current_step}: loss={train_metrics.loss}, accuracy={train_metrics.acc}")
+            current_step += 1
+            steps_done = k + 1
+            if inner_stopper.abort:
+                break
+        if last_kept is not None:
+            inner_stopper.model_params = block.params_after(last_kept)
+        elif isinstance(inner_stopper.model_params, tuple):
+            inner_stopper.model_params = None
+        if steps_done == tau:                                  # the block's last step is the one that triggers the hyper step
+            self._log_hyper_step(metrics[tau], current_step - 1, sacred_runner)
+        else:
+            block.undo_hyper_step(steps_done)
+        if inner_stopper.abort:
+            block.store_state(steps_done)
+        return current_step
+
     def inner_opt_step(self) -> Metrics:
         self.outer_trainer.train()
         sampler = getattr(self.outer_trainer, "sample_for_unroll", None)       # factored graph when the hyper step can use it
@@ -76,6 +126,9 @@ class BilevelProblemRunner:
         metrics = self.outer_trainer.train_step(self.inner_trainer.model_forward)
         self.inner_trainer.detach()
         self.outer_trainer.detach()
+        self._log_hyper_step(metrics, current_step, sacred_runner)
+
+    def _log_hyper_step(self, metrics: Metrics, current_step: int, sacred_runner=None):
         if sacred_runner is not None:
             sacred_runner.log_scalar("loss.outer", metrics.loss, step=current_step)
             sacred_runner.log_scalar("acc.outer", metrics.acc, step=current_step)

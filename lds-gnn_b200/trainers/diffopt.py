@@ -34,6 +34,10 @@ class DifferentiableAdam:
         self.state = {"step": 0, "exp_avg": None, "exp_avg_sq": None}
         self._vectors = None          # per-element hyper-parameters, built on the parameters' device at the first step
         self._flat = None             # (flat tensor, views) of the last result: reused when the caller passes the views back
+        # CUDA-graph capture of a bilevel block: float64 device tensor [1] = number of steps taken BEFORE the block; the bias
+        # correction is then computed on the device from it (a replayed graph must not bake the step count in)
+        self.device_step = None
+        self.device_offset = 0
 
     # ---- per-element hyper-parameter vectors -----------------------------------------------------------------
     def _hyper(self, like: torch.Tensor):
@@ -79,7 +83,13 @@ class DifferentiableAdam:
         v = st["exp_avg_sq"] * b2 + (1 - b2) * (g * g)
         # sqrt has an infinite derivative at 0: floor exact zeros (higher masks that gradient instead)
         root = v.clamp_min(1e-30).sqrt()
-        if isinstance(b1, float) and isinstance(b2, float):
+        if self.device_step is not None:
+            self.device_offset += 1
+            if not (isinstance(b1, float) and isinstance(b2, float)):
+                raise NotImplementedError("device-side step count needs the same betas in every parameter group")
+            td = self.device_step + float(self.device_offset)                  # float64: 1 - b2^t keeps its digits
+            correction = (torch.sqrt(1 - b2 ** td) / (1 - b1 ** td)).to(p.dtype)
+        elif isinstance(b1, float) and isinstance(b2, float):
             correction = math.sqrt(1 - b2 ** t) / (1 - b1 ** t)
         else:
             correction = torch.sqrt(1 - torch.as_tensor(b2) ** t) / (1 - torch.as_tensor(b1) ** t)

@@ -34,6 +34,7 @@ class InnerProblemTrainer:
         self.optimizer: DifferentiableAdam = None
         self.data = data
         self._rows_cache = {}
+        self.deferred = None            # a list while a bilevel block is captured: train_step appends its device [loss, acc] and returns None
         self.reset_optimizer()
 
     def reset_weights(self):
@@ -71,6 +72,9 @@ class InnerProblemTrainer:
         correct = (torch.argmax(selected.detach(), dim=-1) == labels).float().mean()
         new_params = self.optimizer.step(loss, params=self.model_params.values())
         self._update_model_params(list(new_params))
+        if self.deferred is not None:
+            self.deferred.append(torch.stack((loss.detach(), correct)))
+            return None
         loss_value, acc = torch.stack((loss.detach(), correct)).tolist()
         return Metrics(loss=loss_value, acc=acc)
 

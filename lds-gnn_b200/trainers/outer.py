@@ -86,6 +86,7 @@ class OuterProblemTrainer:
         self._adam_state = None
         self._host_scalars = None
         self._opt_rows = None
+        self.deferred = None               # while a bilevel block is captured: (list for the device [loss, acc], device lr scalar)
         if pretrain:
             self.pretrain_model()
 
@@ -172,6 +173,15 @@ class OuterProblemTrainer:
             model.project_parameters()
         else:
             theta = model.theta_full()
+            if self.deferred is not None:
+                # captured block: the learning rate lives in device memory (it decays between replays) and is folded into the
+                # factors — the gradient is linear in (fa, c) — so the kernel's by-value lr stays 1
+                if kind != _lib.OPT_SGD:
+                    raise NotImplementedError("captured bilevel blocks support the SGD outer optimiser")
+                lr_dev = self.deferred[1]
+                kernels.k3k4_theta_update_tc_(theta, n, fa * lr_dev, fb, cvec * lr_dev, 1.0)
+                self.deferred[0].append(torch.stack((loss.detach(), correct)))
+                return None
             if kind == _lib.OPT_SGD:
                 kernels.k3k4_theta_update_tc_(theta, n, fa, fb, cvec, group["lr"])
             else:

@@ -1,4 +1,5 @@
-"""Time one bilevel block (tau = 5 `inner_opt_step` + 1 `hyper_opt_step`, src/trainers/bilevel.py:53-73) on the
+"""Time one bilevel block (captured CUDA-graph replay, eager factored route, dense composable route)
+ (tau = 5 `inner_opt_step` + 1 `hyper_opt_step`, src/trainers/bilevel.py:53-73) on the
 factored route (FactoredGraph unroll, K2 for every product, one K3+K4 pass) and on the dense composable route.
 usage: python scripts/time_bilevel_block.py [cora|citeseer] [blocks]"""
 import json, os, sys, time
@@ -19,7 +20,7 @@ dev = torch.device("cuda")
 data, weights, opt_mask, shape = bench.make_workload(workload, 0)
 data, opt_mask = data.to(dev), opt_mask.to(dev)
 out = {"workload": workload, "shape": shape, "tau": TAU, "blocks": blocks}
-for route in ("factored", "composable"):
+for route in ("graph", "factored", "composable"):
     torch.manual_seed(0)
     PHILOX.manual_seed(0)
     gcn = MetaDenseGCN(shape["f"], shape["h"], shape["c"], dropout=0.5).to(dev)
@@ -28,19 +29,26 @@ for route in ("factored", "composable"):
     opt = torch.optim.SGD(model.parameters(), lr=0.1)
     outer = OuterProblemTrainer(optimizer=opt, data=data, opt_mask=opt_mask, model=model, smoothness_factor=0.0, disconnection_factor=0.0,
                                 sparsity_factor=0.0, regularize=False, lr_decay=0.99, pretrain=False)
-    outer.factored_enabled = route == "factored"
+    outer.factored_enabled = route != "composable"
     runner = BilevelProblemRunner(inner, outer, data)
     runner.logger.disabled = True
 
+    captured = None
+    if route == "graph":
+        from lds_gnn_b200.trainers.graph_block import CapturedBilevelBlock
+        captured = CapturedBilevelBlock(runner, TAU)
+
     def block():
+        if captured is not None:
+            return captured.replay()
         for _ in range(TAU):
             runner.inner_opt_step()
         runner.hyper_opt_step(0)
 
-    n_blocks = blocks if route == "factored" else max(3, blocks // 4)
+    n_blocks = {"graph": 5 * blocks, "factored": blocks}.get(route, max(3, blocks // 4))
     for _ in range(3):
         block()
-    assert outer.last_route == route, outer.last_route
+    assert outer.last_route == {"graph": "factored-graph"}.get(route, route), outer.last_route
     torch.cuda.synchronize(); torch.cuda.reset_peak_memory_stats()
     t0 = time.perf_counter()
     for _ in range(n_blocks):
@@ -52,5 +60,5 @@ for route in ("factored", "composable"):
     print(f"{workload} {route:10s}: {ms:8.3f} ms per block ({TAU} inner steps + 1 hyper step), peak {out[route]['peak_mem_gb']} GB", flush=True)
     del runner, outer, inner, model, gcn, opt
     torch.cuda.empty_cache()
-out["speedup"] = round(out["composable"]["ms_per_block"] / out["factored"]["ms_per_block"], 2)
+out["speedup_graph_vs_composable"] = round(out["composable"]["ms_per_block"] / out["graph"]["ms_per_block"], 2)
 print(json.dumps(out))

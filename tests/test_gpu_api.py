@@ -331,21 +331,28 @@ def test_hypergradient_reaches_first_graph_through_unrolled_inner_steps():   # t
 
 @pytest.mark.parametrize("name,optimizer,dropout,history", [
     ("n33_twostep", "SGD", 0.0, "factored"), ("n257_h64", "SGD", 0.5, "factored"), ("n130_sparse", "Adam", 0.5, "factored"),
-    ("n130_sparse", "SGD", 0.5, "dense")])
-def test_factored_unrolled_hyper_step_matches_composable_route(name, optimizer, dropout, history):
+    ("n130_sparse", "SGD", 0.5, "dense"), ("n130_sparse", "SGD", 0.0, "factored-sparse-x")])
+def test_factored_unrolled_hyper_step_matches_composable_route(name, optimizer, dropout, history, monkeypatch):
     """One bilevel block (src/trainers/bilevel.py:53-73): tau inner steps with the differentiable Adam, then the hyper step
     whose backward flows through all of them into every sampled graph. The factored route (O(N h) autograd tensors, K2 for
     every product, one K3+K4 pass over the concatenated factor pairs) must give the composable route's theta — dense
     N x N autograd through the same unroll with the same Philox graphs and the same dropout masks. Two blocks in a row, so
     the second starts from the first one's update; `history = dense` mixes dense inner graphs into a factored hyper step."""
+    import lds_gnn_b200.models.gcn as gcn_mod
+    from lds_gnn_b200.models.layers import sparse_companion
     from lds_gnn_b200.models.sampling import PHILOX
     from lds_gnn_b200.trainers.bilevel import BilevelProblemRunner
     g = load_golden(name)
+    # the CSR feature path draws its dropout mask over the non-zeros only: exact mask parity with the dense composable route
+    # needs the dense features (dropout > 0) or no dropout (the "factored-sparse-x" case)
+    monkeypatch.setattr(gcn_mod, "SPARSE_FEATURES", [history == "factored-sparse-x"])
     results = {}
     for route in ("factored", "composable"):
         kw = dict(eps=1e-3) if optimizer == "Adam" else {}
         data, gcn, inner, model, outer = _setup(g, lr=0.05 if optimizer == "Adam" else 0.5, lr_decay=0.9, dropout=dropout,
                                                 optimizer=optimizer, **kw)
+        if history == "factored-sparse-x":
+            assert sparse_companion(data.x) is not None
         with torch.no_grad():                                   # interior probabilities: every graph of the unroll is random
             model.probs.mul_(0.6).add_(0.2)
         outer.factored_enabled = route == "factored"

@@ -1,0 +1,126 @@
+"""-m gpu tests of the captured bilevel block (lds_gnn_b200/trainers/graph_block.py): tau inner steps + the hyper step
+(src/trainers/bilevel.py:53-73) replayed from one CUDA graph must reproduce the step-by-step loop."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from test_gpu_api import _setup, t  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+CUDA = "cuda"
+
+
+@pytest.fixture(autouse=True)
+def _fresh_config():
+    from lds_gnn_b200.models.sampling import PHILOX, Sampler
+    saved = dict(Sampler._ingredient.values)
+    PHILOX.manual_seed(1234)
+    yield
+    Sampler._ingredient.values.update(saved)
+
+
+@pytest.mark.parametrize("n,step0", [(130, 5), (257, (1 << 32) - 2), (64, (7 << 32) + 11)])
+def test_k1_with_device_step_counter_draws_the_same_graph(n, step0):
+    """lds_k1_sample_normalize_dstep: step = *step_base + offset read on the device == the by-value step (bit-exact mask)."""
+    from lds_gnn_b200 import kernels
+    torch.manual_seed(n)
+    ld = kernels.padded_ld(n)
+    theta = torch.zeros((n, ld), device=CUDA)
+    sym = torch.rand(n, n, device=CUDA)
+    theta[:, :n] = (sym + sym.t()) / 2
+    base = torch.tensor([step0], dtype=torch.int64, device=CUDA)
+    for offset in (0, 1, 3):
+        a_ref, _, deg_ref, rs_ref = kernels.k1_sample_normalize(theta, n, 99, step0 + offset)
+        a_dev, _, deg_dev, rs_dev = kernels.k1_sample_normalize(theta, n, 99, offset, step_base=base)
+        assert torch.equal(a_ref, a_dev) and torch.equal(deg_ref, deg_dev) and torch.equal(rs_ref, rs_dev)
+    other, _, _, _ = kernels.k1_sample_normalize(theta, n, 99, 0, step_base=base + 1)
+    assert not torch.equal(other, a_ref[..., :])                              # the counter is really read
+
+
+def _runner(g, dropout=0.0, lr=0.5, lr_decay=0.9):
+    from lds_gnn_b200.trainers.bilevel import BilevelProblemRunner
+    data, gcn, inner, model, outer = _setup(g, lr=lr, lr_decay=lr_decay, dropout=dropout)
+    with torch.no_grad():
+        model.probs.mul_(0.6).add_(0.2)
+    runner = BilevelProblemRunner(inner, outer, data, n_samples_empirical_mean=2)
+    return runner, inner, outer, model
+
+
+@pytest.mark.parametrize("name,tau", [("n130_sparse", 3), ("n257_h64", 5), ("n33_twostep", 1)])
+def test_captured_block_replays_match_the_eager_loop(name, tau):
+    from lds_gnn_b200.models.sampling import PHILOX
+    from lds_gnn_b200.trainers.graph_block import CapturedBilevelBlock
+    g = load_golden(name)
+    out = {}
+    for mode in ("graph", "eager"):
+        runner, inner, outer, model = _runner(g)
+        PHILOX.manual_seed(77)
+        assert CapturedBilevelBlock.eligible(runner)
+        metrics = []
+        if mode == "graph":
+            block = CapturedBilevelBlock(runner, tau)
+            for _ in range(3):
+                metrics += block.replay()
+            assert outer.last_route == "factored-graph"
+            block.store_state(tau)
+        else:
+            for _ in range(3):
+                for _ in range(tau):
+                    metrics.append(runner.inner_opt_step())
+                metrics.append(outer.train_step(inner.model_forward))
+                assert outer.last_route == "factored"
+                inner.detach()
+        out[mode] = (metrics, model.probs.detach().clone(), [p.detach().clone() for p in inner.model_params.values()],
+                     outer.get_learning_rates(), PHILOX.step, inner.optimizer.state["step"])
+    mg, pg, wg, lg, sg, tg = out["graph"]
+    me, pe, we, le, se, te = out["eager"]
+    assert (sg, tg) == (se, te) == (3 * (tau + 1), 3 * tau) and lg == pytest.approx(le)
+    for a, b in zip(mg, me):
+        assert abs(a.loss - b.loss) < 2e-5 * max(1.0, abs(b.loss)) and abs(a.acc - b.acc) < 1e-6
+    for a, b in zip(wg, we):
+        assert (a - b).abs().max().item() < 1e-5
+    assert (pg - pe).abs().max().item() < 1e-5
+    assert (pg - (0.6 * t(g["theta_triu"]) + 0.2)).abs().max().item() > 1e-5          # theta really moved
+
+
+def test_captured_block_draws_fresh_dropout_masks_and_graphs_per_replay():
+    from lds_gnn_b200.trainers.graph_block import CapturedBilevelBlock
+    runner, inner, outer, model = _runner(load_golden("n130_sparse"), dropout=0.5)
+    block = CapturedBilevelBlock(runner, 2)
+    first = block.replay()
+    losses = [first[0].loss]
+    for _ in range(3):
+        inner.reset_weights(); inner.reset_optimizer()                          # same weights-independent randomness check:
+        block.resident = False                                                   # every replay starts from fresh weights
+        losses.append(block.replay()[0].loss)
+    assert len({round(v, 6) for v in losses[1:]}) > 1                            # different graphs / masks every replay
+    assert all(np.isfinite(v) for v in losses)
+
+
+def test_runner_with_captured_blocks_follows_the_step_by_step_loop_incl_early_stop_rollback():
+    """Whole `BilevelProblemRunner.train` (src/trainers/bilevel.py:34-101) with dropout 0 (all randomness from the Philox
+    counter): blocks + post-hoc early stopping + undo of a hyper step the reference would not have taken == eager loop.
+    inner_loop_max_epochs = 7 with tau = 3 stops at step 7, the first step of a block."""
+    from lds_gnn_b200.models.sampling import PHILOX
+    g = load_golden("n130_sparse")
+    out = {}
+    for mode in (True, False):
+        runner, inner, outer, model = _runner(g)
+        runner.graph_blocks = mode
+        PHILOX.manual_seed(5)
+        np.random.seed(0)
+        torch.manual_seed(9)                                                     # reset_weights draws from torch's generator
+        runner.train(patience=2, hyper_gradient_interval=3, inner_loop_max_epochs=7, outer_loop_max_epochs=1)
+        res = runner.evaluate()
+        out[mode] = (model.probs.detach().clone(), outer.get_learning_rates(), PHILOX.step, res,
+                     [v.detach().clone() for v in runner.gcn_params.values()])
+        if mode:
+            assert runner._blocks and outer.last_route == "factored-graph"
+    (pg, lg, sg, rg, wg), (pe, le, se, re_, we) = out[True], out[False]
+    assert sg == se and lg == pytest.approx(le)
+    assert (pg - pe).abs().max().item() < 1e-5
+    for a, b in zip(wg, we):
+        assert (a - b).abs().max().item() < 1e-5
+    for key in rg:
+        assert abs(rg[key] - re_[key]) < 1e-4

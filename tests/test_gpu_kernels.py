@@ -295,3 +295,48 @@ def test_k3k4_adam(K):
         opt.step()
         ref_p.data.clamp_(0, 1)
     assert (full[:, :n].double() - ref_p.data).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("rows,cols,w,density", [(130, 77, 16, 0.05), (333, 1000, 6, 0.01), (64, 50, 64, 0.3), (17, 9, 1, 0.5)])
+def test_spmm_csr_both_directions_match_dense_products(rows, cols, w, density):
+    """lds_spmm_csr + the SparseFeatureMatrix index structure: X' B and X'^T B (src/models/layers.py:43 and its autograd
+    transposes) against fp64 dense products, with contiguous and transposed-view operands, an empty row and an empty column."""
+    from lds_gnn_b200.models.layers import SparseFeatureMatrix
+    torch.manual_seed(rows + w)
+    x = torch.rand(rows, cols, device="cuda") * (torch.rand(rows, cols, device="cuda") < density)
+    x[rows // 2, :] = 0
+    x[:, cols // 3] = 0
+    m = SparseFeatureMatrix(x)
+    vals = m.val * (torch.rand_like(m.val) < 0.5) * 2.0                      # a dropout of the non-zeros
+    feats = m.with_values(vals)
+    xd = torch.zeros_like(x)
+    crow = m.crow.long()
+    row_of = torch.repeat_interleave(torch.arange(rows, device="cuda"), crow[1:] - crow[:-1])
+    xd[row_of, m.col.long()] = vals
+    wmat = torch.randn(w, cols, device="cuda")                               # layer weight [w, cols]: b = wmat.t() is a strided view
+    y = feats.product(wmat.t(), False)
+    ref = xd.double() @ wmat.double().t()
+    assert (y.double() - ref).abs().max() <= 1e-5 * max(1.0, ref.abs().max().item())
+    dy = torch.randn(rows, w, device="cuda")
+    gt = feats.product(dy, True)
+    ref_t = xd.double().t() @ dy.double()
+    assert gt.shape == (cols, w) and (gt.double() - ref_t).abs().max() <= 1e-5 * max(1.0, ref_t.abs().max().item())
+    assert torch.equal(feats.product(dy, True), gt)                          # fixed summation order: bitwise reproducible
+
+
+def test_sparse_linear_is_differentiable_to_second_order():
+    from collections import OrderedDict
+    from lds_gnn_b200.models.layers import MetaLinear, SparseFeatureMatrix
+    torch.manual_seed(0)
+    x = torch.rand(40, 30, device="cuda") * (torch.rand(40, 30, device="cuda") < 0.1)
+    feats = SparseFeatureMatrix(x).with_values(SparseFeatureMatrix(x).val)
+    lin = MetaLinear(30, 5).cuda()
+    results = []
+    for inp in (feats, x):
+        wgt = lin.weight.detach().clone().requires_grad_(True)
+        out = lin(inp, params=OrderedDict(weight=wgt, bias=lin.bias))
+        (g,) = torch.autograd.grad((out ** 3).sum(), wgt, create_graph=True)
+        (gg,) = torch.autograd.grad((g ** 2).sum(), wgt)
+        results.append((out.detach(), g.detach(), gg))
+    for a, b in zip(*results):
+        assert (a - b).abs().max() <= 1e-4 * max(1.0, b.abs().max().item())
