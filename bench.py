@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--workload", default="citeseer")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bilevel-block", action="store_true", help="skip the extra bilevel-block timing (tau inner steps + hyper step)")
     ap.add_argument("--no-scale-ref", action="store_true", help="N > 1: skip the single-GPU run of the same workload on rank 0")
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent single-GPU replicas instead of the sharded N=65536 config")
     ap.add_argument("--cpu-steps", type=int, default=3)
@@ -373,6 +374,59 @@ def run_ours(args, rank, world, device):
     return line
 
 
+# ------------------------------------------------------------------------------------------------ bilevel block
+def time_bilevel_block(workload, device, tau=5, replays=40, eager_blocks=4):
+    """The reference's real training loop never runs an outer step in isolation: it alternates tau = 5 inner steps with one
+    hyper step whose backward flows through all of them (src/trainers/bilevel.py:53-73). This times that block through the
+    package's own BilevelProblemRunner machinery: one captured CUDA graph per block (trainers/graph_block.py) and, for
+    reference, the same block run step by step on the eager factored route. Wall clock around synchronised loops."""
+    from lds_gnn_b200.models.gcn import MetaDenseGCN
+    from lds_gnn_b200.models.graph import BernoulliGraphModel
+    from lds_gnn_b200.trainers.bilevel import BilevelProblemRunner
+    from lds_gnn_b200.trainers.graph_block import CapturedBilevelBlock
+    from lds_gnn_b200.trainers.inner import InnerProblemTrainer
+    from lds_gnn_b200.trainers.outer import OuterProblemTrainer
+    data, _, opt_mask, shape = make_workload(workload, seed=0)
+    data, opt_mask = data.to(device), opt_mask.to(device)
+    gcn = MetaDenseGCN(shape["f"], shape["h"], shape["c"], dropout=0.5).to(device)
+    inner = InnerProblemTrainer(gcn, data, lr=0.01, weight_decay=5e-4)
+    model = BernoulliGraphModel(data.dense_adj).to(device)
+    outer = OuterProblemTrainer(optimizer=torch.optim.SGD(model.parameters(), lr=0.1), data=data, opt_mask=opt_mask, model=model,
+                                smoothness_factor=0.0, disconnection_factor=0.0, sparsity_factor=0.0, regularize=False, lr_decay=0.99)
+    runner = BilevelProblemRunner(inner, outer, data)
+    runner.logger.disabled = True
+    if not CapturedBilevelBlock.eligible(runner):
+        return {"error": "configuration not eligible for captured blocks"}
+    block = CapturedBilevelBlock(runner, tau)
+    for _ in range(3):
+        block.replay()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(replays):
+        metrics = block.replay()                                     # includes the block's device->host read of its 6 (loss, acc)
+    torch.cuda.synchronize()
+    graph_ms = (time.perf_counter() - t0) / replays * 1e3
+    block.store_state(tau)
+
+    def eager_block():
+        for _ in range(tau):
+            runner.inner_opt_step()
+        runner.hyper_opt_step(0)
+
+    eager_block()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(eager_blocks):
+        eager_block()
+    torch.cuda.synchronize()
+    eager_ms = (time.perf_counter() - t0) / eager_blocks * 1e3
+    return {"unit": f"one block = {tau} inner_opt_step + 1 hyper_opt_step (hypergradient through the {tau} unrolled steps)",
+            "ms_per_block": round(graph_ms, 3), "theta_updates_per_s": round(1e3 / graph_ms, 1),
+            "inner_steps_per_s": round(tau * 1e3 / graph_ms, 1), "route": "factored-graph",
+            "eager_factored_ms_per_block": round(eager_ms, 3), "replays": replays,
+            "last_outer_metrics": {"loss": metrics[-1].loss, "acc": metrics[-1].acc}}
+
+
 # ------------------------------------------------------------------------------------------------ large-N / sharded arm
 def hashed_theta(n, ld, row0, rows, device, seed):
     """Dense symmetric theta ~ U[0,1), generated row block by row block on the device from a
@@ -665,6 +719,11 @@ def main():
             line["cpu_baseline"] = {"value": round(rate, 4), "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{args.cpu_steps} full outer steps of the same workload after 1 warm-up "
                                               f"(oracle/reference_port.py: the reference's torch op sequence on CPU){note}"}
+        if world == 1 and not args.no_bilevel_block and workload in ("citeseer", "cora", "tiny"):
+            try:
+                line["bilevel_block"] = time_bilevel_block(workload, device)
+            except Exception as exc:                     # an extra, never the headline: report instead of failing the line
+                line["bilevel_block"] = {"error": f"{type(exc).__name__}: {exc}"}
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist

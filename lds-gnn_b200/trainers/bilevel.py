@@ -105,8 +105,6 @@ class BilevelProblemRunner:
                 break
         if last_kept is not None:
             inner_stopper.model_params = block.params_after(last_kept)
-        elif isinstance(inner_stopper.model_params, tuple):
-            inner_stopper.model_params = None
         if steps_done == tau:                                  # the block's last step is the one that triggers the hyper step
             self._log_hyper_step(metrics[tau], current_step - 1, sacred_runner)
         else:

@@ -453,3 +453,77 @@ def test_factored_unroll_hypergradient_equals_dense_autograd(monkeypatch):
         assert torch.allclose(a, b, atol=1e-12)
     assert grad_d.abs().max() > 0
     assert (grad_d - grad_f).abs().max() <= 1e-10 * grad_d.abs().max()
+
+
+@pytest.mark.parametrize("tau,patience,inner_max,script_seed", [(5, 3, 40, 0), (3, 2, 7, 1), (1, 2, 12, 2), (5, 20, 23, 3), (4, 1, 30, 4)])
+def test_runner_block_bookkeeping_matches_the_step_by_step_loop(monkeypatch, tau, patience, inner_max, script_seed):
+    """Host logic of `BilevelProblemRunner._run_block` (src/trainers/bilevel.py:45-99 re-expressed over whole blocks): with
+    scripted losses and stand-in trainers / block, the block loop must take the same inner steps, the same hyper steps (after
+    undoing the ones the reference would not have taken) and keep the same early-stopping weights as the step-by-step loop."""
+    import lds_gnn_b200.trainers.bilevel as B
+    import lds_gnn_b200.trainers.graph_block as GB
+    from lds_gnn_b200.trainers import Metrics
+    rng = np.random.default_rng(script_seed)
+    script = list(np.abs(1.0 + 0.3 * rng.standard_normal(400)) * np.linspace(1.0, 0.6, 400))
+
+    class World:                      # shared ground truth both stand-ins act on
+        def __init__(self):
+            self.cursor, self.hyper, self.log = 0, 0, []
+
+    class Inner:
+        def __init__(self, w):
+            self.w, self.model = w, None
+        def reset_weights(self): self.w.log.append("reset")
+        def reset_optimizer(self): pass
+        def copy_model_params(self): return ("weights after global step", self.w.cursor - 1)
+        def train_step(self, graph):
+            self.w.cursor += 1
+            return Metrics(loss=script[self.w.cursor - 1], acc=0.5)
+        def model_forward(self, graph): return None
+        def detach(self): pass
+
+    class Outer:
+        def __init__(self, w):
+            self.w = w
+            self.model = type("M", (), {"state_dict": lambda s: {"hyper": w.hyper}, "load_state_dict": lambda s, d: None,
+                                        "statistics": lambda s: {}})()
+        def sample_for_unroll(self, inner): return None
+        def train_step(self, fct):
+            self.w.hyper += 1
+            self.w.log.append(("hyper after", self.w.cursor))
+            return Metrics(loss=0.0, acc=0.0)
+        def detach(self): pass
+        def train(self, mode=True): pass
+        def get_learning_rates(self): return [0.1]
+
+    class FakeBlock:
+        def __init__(self, runner, t):
+            self.w, self.tau = runner.inner_trainer.w, t
+        @staticmethod
+        def eligible(runner): return True
+        def replay(self):
+            self.start = self.w.cursor
+            out = [Metrics(loss=script[self.start + k], acc=0.5) for k in range(self.tau)]
+            self.w.cursor += self.tau
+            self.w.hyper += 1
+            self.w.log.append(("hyper after", self.w.cursor))
+            return out + [Metrics(loss=0.0, acc=0.0)]
+        def params_after(self, k): return ("weights after global step", self.start + k)
+        def undo_hyper_step(self, steps_done):
+            self.w.cursor = self.start + steps_done
+            self.w.hyper -= 1
+            self.w.log.pop()
+        def store_state(self, steps_done): pass
+
+    monkeypatch.setattr(GB, "CapturedBilevelBlock", FakeBlock)
+    monkeypatch.setattr(B, "empirical_mean_loss", lambda *a, **k: (Metrics(loss=1.0, acc=0.5), Metrics(loss=1.0, acc=0.5)))
+    results = []
+    for graph_blocks in (False, True):
+        w = World()
+        runner = B.BilevelProblemRunner(Inner(w), Outer(w), data=None)
+        runner.graph_blocks = graph_blocks
+        runner.logger.disabled = True
+        runner.train(patience=patience, hyper_gradient_interval=tau, inner_loop_max_epochs=inner_max, outer_loop_max_epochs=2)
+        results.append((w.cursor, w.hyper, w.log, runner.gcn_params))
+    assert results[0] == results[1]
+    assert results[0][1] > 0 and results[0][0] > tau
