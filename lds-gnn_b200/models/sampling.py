@@ -114,14 +114,16 @@ class FactorSink:
     kernel (K3+K4) consumes the K-concatenation of all pairs in ONE pass over theta."""
 
     def __init__(self):
-        self.fa, self.fb, self.c = [], [], None
+        self.fa, self.fb, self.scale, self.c = [], [], [], None
 
     def clear(self):
-        self.fa, self.fb, self.c = [], [], None
+        self.fa, self.fb, self.scale, self.c = [], [], [], None
 
-    def add_outer(self, a: Tensor, b: Tensor):
+    def add_outer(self, a: Tensor, b: Tensor, row_scale: Tensor = None):
+        """Deposit the pair (s * a, s * b), s = row_scale[:, None] (or 1): the scaling is applied once, at collect time."""
         self.fa.append(a)
         self.fb.append(b)
+        self.scale.append(row_scale)
 
     def add_row_constant(self, c: Tensor):
         self.c = c if self.c is None else self.c + c
@@ -132,8 +134,13 @@ class FactorSink:
     def collect(self, n: int, device):
         """(fa [n, d], fb [n, d], c [n]) fp32, contiguous; d >= 1."""
         if self.fa:
-            fa = torch.cat(self.fa, dim=1).contiguous()
-            fb = torch.cat(self.fb, dim=1).contiguous()
+            fa = torch.cat(self.fa, dim=1)
+            fb = torch.cat(self.fb, dim=1)
+            if any(s is not None for s in self.scale):
+                cols = torch.cat([(torch.ones(n, dtype=a.dtype, device=a.device) if s is None else s)[:, None].expand(n, a.shape[1])
+                                  for a, s in zip(self.fa, self.scale)], dim=1)
+                fa, fb = fa * cols, fb * cols
+            fa, fb = fa.contiguous(), fb.contiguous()
         else:
             fa = torch.zeros((n, 1), dtype=torch.float32, device=device)
             fb = torch.zeros((n, 1), dtype=torch.float32, device=device)
@@ -166,6 +173,34 @@ class _FactoredMatmul(torch.autograd.Function):
             fg.sink.add_outer(dy.detach(), q.detach())
         dq = _FactoredMatmul.apply(dy, fg.link, fg) if ctx.needs_input_grad[0] else None
         return dq, None, None
+
+
+class _FactoredPropagate(torch.autograd.Function):
+    """Z = r * (A_tilde (r * Q)) — the normalised propagation (src/utils/graph.py:148-152 + src/models/layers.py:44) as ONE K2
+    launch: r rides in the operand pack and in the epilogue. Differentiable to any order in Q and r:
+        dQ = r * (A_tilde (r * dZ))            (this Function again; A_tilde is symmetric)
+        dr = (sum_c dZ*Z + sum_c dQ*Q) / r     (ordinary differentiable ops; Z is this node's own output)
+    and the gradient on the graph is the pair (r*dZ, r*Q), deposited unscaled together with r (FactorSink scales once)."""
+
+    @staticmethod
+    def forward(ctx, q, r, link, fg):
+        from .. import kernels
+        q, r = q.contiguous(), r.contiguous()
+        z = kernels.k2_propagate(fg.handle.adj, fg.handle.n, q, r, r)
+        ctx.save_for_backward(q, r, z)
+        ctx.fg = fg
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        q, r, z = ctx.saved_tensors
+        fg = ctx.fg
+        need_q, need_r = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not torch.is_grad_enabled():
+            fg.sink.add_outer(dz.detach(), q.detach(), r.detach())
+        dq = _FactoredPropagate.apply(dz, r, fg.link, fg) if (need_q or need_r) else None
+        dr = torch.addcmul(dz * z, dq, q).sum(dim=1) / r if need_r else None
+        return (dq if need_q else None), dr, None, None
 
 
 class _FactoredDegree(torch.autograd.Function):
@@ -222,8 +257,7 @@ class FactoredNormalizedAdjacency:
         self.fg, self.r = fg, r
 
     def propagate(self, embeddings: Tensor) -> Tensor:
-        r = self.r[:, None]
-        return r * self.fg.matmul(r * embeddings)
+        return _FactoredPropagate.apply(embeddings, self.r, self.fg.link, self.fg)
 
 
 def sample_factored(theta_full: Tensor, n: int, link: Tensor, sink: FactorSink) -> FactoredGraph:

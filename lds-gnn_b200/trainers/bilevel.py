@@ -44,8 +44,10 @@ class BilevelProblemRunner:
             tau = max(1, hyper_gradient_interval)
             while not inner_stopper.abort:                     # judged on the training loss
                 if self.graph_blocks and current_step % tau == 1 % tau and self._block_eligible():
-                    current_step = self._run_block(tau, current_step, inner_stopper, sacred_runner)
-                    continue
+                    advanced = self._run_block(tau, current_step, inner_stopper, sacred_runner)
+                    if advanced is not None:
+                        current_step = advanced
+                        continue
                 train_metrics = self.inner_opt_step()
                 inner_stopper.update(train_metrics.loss, model_params=self.inner_trainer.copy_model_params())
                 if sacred_runner is not None:
@@ -81,12 +83,18 @@ class BilevelProblemRunner:
     def _run_block(self, tau: int, current_step: int, inner_stopper: EarlyStopping, sacred_runner) -> int:
         """Steps current_step .. current_step + tau - 1 of the reference loop (the last one triggers the hyper step) from ONE
         graph replay; the per-step early stopping is applied afterwards, and if the reference would have stopped before the
-        block's hyper step, that step is undone. Returns the new current_step."""
+        block's hyper step, that step is undone. Returns the new current_step (None: capture failed, nothing was run)."""
         from .graph_block import CapturedBilevelBlock
+        from .graph_block import BlockCaptureError
         block = self._blocks.get(tau)
         if block is None:
             block = self._blocks[tau] = CapturedBilevelBlock(self, tau)
-        metrics = block.replay()
+        try:
+            metrics = block.replay()
+        except BlockCaptureError as exc:                       # state is back at block entry: carry on step by step
+            self.logger.warning(f"bilevel block could not be captured into a CUDA graph ({exc}); continuing step by step")
+            self.graph_blocks = False
+            return None
         steps_done, last_kept = 0, None
         for k in range(tau):
             train_metrics = metrics[k]

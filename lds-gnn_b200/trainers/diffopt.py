@@ -76,11 +76,19 @@ class DifferentiableAdam:
             st["exp_avg_sq"] = torch.zeros_like(p)
         st["step"] += 1
         t = st["step"]
-        if not (isinstance(hp["wd"], float) and hp["wd"] == 0.0):
-            g = g + hp["wd"] * p
+        # fused forms (add / addcmul / lerp): a third of the launches of the textbook expressions, same derivatives
+        if isinstance(hp["wd"], float):
+            if hp["wd"] != 0.0:
+                g = torch.add(g, p, alpha=hp["wd"])
+        else:
+            g = torch.addcmul(g, hp["wd"], p)
         b1, b2 = hp["b1"], hp["b2"]
-        m = st["exp_avg"] * b1 + (1 - b1) * g
-        v = st["exp_avg_sq"] * b2 + (1 - b2) * (g * g)
+        if isinstance(b1, float) and isinstance(b2, float):
+            m = torch.lerp(st["exp_avg"], g, 1 - b1)
+            v = torch.addcmul(st["exp_avg_sq"] * b2, g, g, value=1 - b2)
+        else:
+            m = st["exp_avg"] * b1 + (1 - b1) * g
+            v = st["exp_avg_sq"] * b2 + (1 - b2) * (g * g)
         # sqrt has an infinite derivative at 0: floor exact zeros (higher masks that gradient instead)
         root = v.clamp_min(1e-30).sqrt()
         if self.device_step is not None:

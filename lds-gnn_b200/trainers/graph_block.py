@@ -25,6 +25,10 @@ from . import Metrics
 NAMES = ("layer_in.fc.weight", "layer_in.fc.bias", "layer_out.fc.weight", "layer_out.fc.bias")
 
 
+class BlockCaptureError(RuntimeError):
+    """The block could not be captured; the trainers' state is back to what it was at block entry."""
+
+
 class CapturedBilevelBlock:
 
     def __init__(self, runner, tau: int):
@@ -145,23 +149,31 @@ class CapturedBilevelBlock:
         # one eager pass on a side stream first (library handles, workspaces, index caches), then the capture itself; both leave
         # the Python-side counters advanced and (the eager one) the state changed: restore everything afterwards
         self._set_dynamic(host[0], host[1], outer.get_learning_rates()[0])
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                PHILOX.begin_capture(self.step_dev)
+                try:
+                    self._body()
+                finally:
+                    self.draws = PHILOX.end_capture()
+            torch.cuda.current_stream().wait_stream(side)
+            self._restore(saved, theta)
+            graph = torch.cuda.CUDAGraph()
             PHILOX.begin_capture(self.step_dev)
             try:
-                self._body()
+                with torch.cuda.graph(graph):
+                    self._body()
             finally:
-                self.draws = PHILOX.end_capture()
-        torch.cuda.current_stream().wait_stream(side)
-        self._restore(saved, theta)
-        graph = torch.cuda.CUDAGraph()
-        PHILOX.begin_capture(self.step_dev)
-        try:
-            with torch.cuda.graph(graph):
-                self._body()
-        finally:
-            PHILOX.end_capture()
+                PHILOX.end_capture()
+        except Exception as exc:
+            torch.cuda.synchronize()
+            self._restore(saved, theta)
+            PHILOX.step = host[0]
+            inner.optimizer.state["step"] = host[1]
+            self.store_state(self.tau)                             # eager state := the (restored) state at block entry
+            raise BlockCaptureError(f"{type(exc).__name__}: {exc}") from exc
         self._restore(saved, theta)
         PHILOX.step = host[0]
         inner.optimizer.state["step"] = host[1]

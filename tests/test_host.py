@@ -400,7 +400,10 @@ def test_factored_unroll_hypergradient_equals_dense_autograd(monkeypatch):
     from lds_gnn_b200.models.sampling import FactoredGraph, FactorSink, SampleHandle
     from lds_gnn_b200.trainers.inner import InnerProblemTrainer
     from lds_gnn_b200.utils.graph import DenseData
-    monkeypatch.setattr(kernels, "k2_propagate", lambda adj, n, q, *a, **k: adj @ q)
+    def k2_stub(adj, n, q, scale_in=None, scale_out=None, **kw):
+        y = adj @ (q if scale_in is None else scale_in[:, None] * q)
+        return y if scale_out is None else scale_out[:, None] * y
+    monkeypatch.setattr(kernels, "k2_propagate", k2_stub)
     torch.manual_seed(3)
     dt = torch.float64
     n, f, h, c, steps = 30, 11, 8, 3, 3
