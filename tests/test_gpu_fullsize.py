@@ -167,3 +167,55 @@ def test_full_size_row_block_shards_match_the_single_device_step(big):
     assert (new - ref).abs().max().item() < 2e-5
     assert torch.equal(new[:, :N], new[:, :N].t())
     assert abs(sc[0].item() - sc_ref[0].item()) < 1e-5 and abs(sc[1].item() - sc_ref[1].item()) < 1e-6
+
+
+def test_full_size_unrolled_block_factored_route_matches_dense_autograd(big):
+    """The unrolled bilevel block (two inner steps with the differentiable Adam, then the hyper step through them,
+    src/trainers/bilevel.py:53-73) at N = 20 000: the factored route (K2 for every product with a graph, factor pairs of all
+    three graphs folded into theta by one K3+K4 pass, d ~ 430 columns) against dense N x N autograd through the same unroll
+    (the composable route, ~20 GB of temporaries) on the same Philox graphs. Also pins the hi/lo-split K3 at large d and N."""
+    import lds_gnn_b200.models.gcn as gcn_mod
+    from lds_gnn_b200.models.gcn import MetaDenseGCN
+    from lds_gnn_b200.models.graph import BernoulliGraphModel
+    from lds_gnn_b200.models.sampling import PHILOX
+    from lds_gnn_b200.trainers.bilevel import BilevelProblemRunner
+    from lds_gnn_b200.trainers.inner import InnerProblemTrainer
+    from lds_gnn_b200.trainers.outer import OuterProblemTrainer
+    from lds_gnn_b200.utils.graph import DenseData
+    K, d, w = big
+    dev = torch.device("cuda")
+    train_mask = torch.zeros(N, dtype=torch.bool, device=dev)
+    train_mask[torch.arange(0, N, 143, device=dev)] = True
+    data = DenseData(x=d["x"], y=d["y"], train_mask=train_mask, val_mask=d["mask"], test_mask=d["mask"], num_classes=d["c"])
+    theta0 = d["theta"][:, :N].contiguous()
+    results = {}
+    for route in ("factored", "composable"):
+        torch.manual_seed(4)
+        gcn = MetaDenseGCN(d["f"], d["h"], d["c"], dropout=0.0).to(dev)
+        with torch.no_grad():
+            for p, v in zip((gcn.layer_in.fc.weight, gcn.layer_in.fc.bias, gcn.layer_out.fc.weight, gcn.layer_out.fc.bias), w):
+                p.copy_(v)
+        inner = InnerProblemTrainer(gcn, data, lr=0.01, weight_decay=5e-4)
+        model = BernoulliGraphModel(theta0).to(dev)
+        outer = OuterProblemTrainer(optimizer=torch.optim.SGD(model.parameters(), lr=2.0e4), data=data,   # lr: gradients are ~1e-7 at degree ~10 000
+                                     opt_mask=d["mask"], model=model,
+                                    smoothness_factor=0.0, disconnection_factor=0.0, sparsity_factor=0.0, regularize=False, lr_decay=None)
+        outer.factored_enabled = route == "factored"
+        runner = BilevelProblemRunner(inner, outer, data)
+        PHILOX.manual_seed(31)
+        for _ in range(2):
+            runner.inner_opt_step()
+        before = model.theta_full().clone()
+        m = outer.train_step(inner.model_forward, retain_graph=False)
+        assert outer.last_route == route
+        inner.detach()
+        after = model.theta_full()
+        step = (after - before).abs().max().item()
+        results[route] = (m, after[:, :N].clone(), step)
+        del runner, outer, model, inner, gcn, before, after
+        torch.cuda.empty_cache()
+    (mf, tf, sf), (mc, tc, sc) = results["factored"], results["composable"]
+    assert abs(mf.loss - mc.loss) < 1e-4 and abs(mf.acc - mc.acc) < 1e-6
+    assert sc > 1e-4, "the hyper step must move theta for the comparison to mean anything"
+    assert torch.equal(tf, tf.t()), "theta must stay exactly symmetric"
+    assert (tf - tc).abs().max().item() <= 2e-3 * sc + 1e-6, ((tf - tc).abs().max().item(), sc)

@@ -222,7 +222,10 @@ def test_k3k4_sgd_update_matches_closed_form_and_stays_symmetric(K, n, d):
                                        # compact-operand kernel: 1..5 boxes of packed factors, ring wrap-around over many tiles
                                        # per CTA, row-block changes inside a CTA's tile range; d > 80 = the k-block kernel
                                        (300, 12, None), (520, 40, None), (520, 60, None), (900, 80, None), (4100, 71, None),
-                                       (520, 100, None), (4100, 71, (1024, 1000)), (900, 80, (128, 300))])
+                                       (520, 100, None), (4100, 71, (1024, 1000)), (900, 80, (128, 300)),
+                                       # widths of the unrolled bilevel block: ~22 factor pairs concatenated along K
+                                       # (d ~ 250 at hidden 16, ~ 800 at hidden 64), DESIGN.md 5c
+                                       (300, 250, None), (520, 800, None), (1300, 1210, None)])
 def test_k3k4_tensor_core_update_matches_closed_form_and_is_exactly_symmetric(K, n, d, rows0):
     rng = np.random.default_rng(n * 13 + d)
     th = random_theta(rng, n, "outside" if n == 130 else "mixed")
