@@ -121,6 +121,18 @@ int32_t lds_spmm_csr(const int32_t* ptr, const int32_t* idx, const float* val, c
                      const float* b, int64_t ldb_row, int64_t ldb_col, int32_t w,
                      float* y, int64_t ldy, void* stream);
 
+/* ---- skinny dense products around the second GCN layer in the unrolled inner steps (MetaLinear of layer_out,
+ * src/models/layers.py:43, src/models/gcn.py:29-30, and what autograd derives from it). Closed under differentiation:
+ *   lds_row_linear : y[n][j] = sum_k x[n][k] * w[j*sw0 + k*sw1] (+ bias[j]),   k, m <= 128   (X W^T with a tiny, strided W)
+ *   lds_gram_tn    : out[i][j] = sum_n a[n][i] * b[n][j],                       a, b <= 128   (weight / bias gradients)
+ * lds_gram_tn reduces deterministically (fixed partial-tile order). Its workspace must be zero-filled before the FIRST use
+ * (the kernel leaves its arrival counter re-armed) and be 256-byte aligned. */
+int32_t lds_row_linear(const float* x, int64_t ldx, int32_t k, const float* w, int64_t sw0, int64_t sw1, int32_t m,
+                       const float* bias, float* y, int64_t ldy, int64_t n_rows, void* stream);
+int64_t lds_gram_tn_workspace_bytes(int32_t a, int32_t b);
+int32_t lds_gram_tn(const float* a_mat, int64_t lda, int32_t a, const float* b_mat, int64_t ldb, int32_t b, int64_t n_rows,
+                    float* out, int64_t ldo, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- K3+K4 (a10's theta part, a11): closed-form straight-through gradient + optimiser step + projection
  * for rows [row0, row0+rows):   g_ij = fa_i.fb_j + fb_i.fa_j + c_i + c_j  (i != j),  0 on the diagonal,
  * masked where theta is outside [0,1] (clamp backward), then

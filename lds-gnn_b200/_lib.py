@@ -35,6 +35,9 @@ SIGNATURES = {
                                                 c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "lds_spmm_csr": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int32,
                                c_void_p, c_int64, c_void_p]),
+    "lds_row_linear": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "lds_gram_tn_workspace_bytes": (c_int64, [c_int32, c_int32]),
+    "lds_gram_tn": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "lds_k2_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32]),
     "lds_k2_propagate": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_void_p,
                                    c_void_p, c_int64, c_void_p, c_int64, c_uint32, c_void_p]),

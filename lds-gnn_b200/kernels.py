@@ -113,11 +113,11 @@ def k1_sample_normalize(theta_full, n, seed, step, sample=0, u=None, want_adj=Tr
 _ws_cache = {}
 
 
-def _workspace(nbytes, device, tag):
+def _workspace(nbytes, device, tag, zero=False):
     key = (tag, str(device))
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+        buf = (torch.zeros if zero else torch.empty)(nbytes + 1024, dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     off = (-buf.data_ptr()) % 1024
     return buf[off:off + nbytes]
@@ -157,6 +157,45 @@ def spmm_csr(ptr, idx, val, perm, rows, b):
     _lib.check(_lib.load().lds_spmm_csr(_ptr(ptr), _ptr(idx), _ptr(val), _ptr(perm), int(rows), _ptr(b), b.stride(0), b.stride(1),
                                         int(w), _ptr(y), y.stride(0), _stream()), "lds_spmm_csr")
     return y
+
+
+# ----------------------------------------------------------------------------- skinny dense products
+def row_linear(x, w, bias=None):
+    """y[n, m] = x[n, k] @ w[m, k]^T (+ bias); w may be any strided view (e.g. a transpose). k, m <= 128."""
+    _lib.require_device()
+    _f32(x, "x")
+    _f32(w, "w")
+    x = x if x.stride(1) == 1 else x.contiguous()
+    n, k = x.shape
+    m = w.shape[0]
+    if w.shape[1] != k:
+        raise ValueError(f"row_linear: x is {tuple(x.shape)}, w is {tuple(w.shape)}")
+    y = torch.empty((n, m), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().lds_row_linear(_ptr(x), x.stride(0), int(k), _ptr(w), w.stride(0), w.stride(1), int(m),
+                                          _ptr(None if bias is None else _f32(bias, "bias").contiguous()), _ptr(y), y.stride(0), int(n), _stream()),
+               "lds_row_linear")
+    return y
+
+
+def gram_tn(a, b):
+    """out[i, j] = sum_n a[n, i] * b[n, j] (deterministic). a [n, p], b [n, q], p, q <= 128."""
+    _lib.require_device()
+    _f32(a, "a")
+    _f32(b, "b")
+    a = a if a.stride(1) == 1 else a.contiguous()
+    b = b if b.stride(1) == 1 else b.contiguous()
+    n, p = a.shape
+    q = b.shape[1]
+    if b.shape[0] != n:
+        raise ValueError(f"gram_tn: a is {tuple(a.shape)}, b is {tuple(b.shape)}")
+    out = torch.empty((p, q), dtype=torch.float32, device=a.device)
+    need = int(_lib.load().lds_gram_tn_workspace_bytes(int(p), int(q)))
+    if need < 0:
+        raise ValueError(f"gram_tn: widths {p}, {q} outside 1..128")
+    ws = _workspace(max(need, 1 << 20), a.device, "gram", zero=True)[:need]      # one zero-initialised arena for every width
+    _lib.check(_lib.load().lds_gram_tn(_ptr(a), a.stride(0), int(p), _ptr(b), b.stride(0), int(q), int(n), _ptr(out), out.stride(0),
+                                       _ptr(ws), need, _stream()), "lds_gram_tn")
+    return out
 
 
 # ----------------------------------------------------------------------------- K3 + K4

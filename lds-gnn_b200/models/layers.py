@@ -87,7 +87,71 @@ class _SparseProduct(torch.autograd.Function):
         return _SparseProduct.apply(dy, ctx.feats, not ctx.transposed), None, None
 
 
-SMALL_LINEAR_ELEMENTS = 1 << 20      # N * out * in below which MetaLinear runs as broadcast-multiply-reduce (CUDA only)
+class _RowLinear(torch.autograd.Function):
+    """Y = X W^T (+ b) for a skinny W (hidden x classes) as one launch (lds_row_linear); closed under differentiation together
+    with _GramTN: dX = dY W, dW = dY^T X, db = dY^T 1 — so a double backward (src/trainers/inner.py:71) stays on these two."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        from .. import kernels
+        ctx.save_for_backward(x, w)
+        return kernels.row_linear(x, w, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx = _RowLinear.apply(dy, w.t(), None) if ctx.needs_input_grad[0] else None
+        dw = _GramTN.apply(dy, x) if ctx.needs_input_grad[1] else None
+        db = _column_sum(dy) if ctx.needs_input_grad[2] else None
+        return dx, dw, db
+
+
+class _GramTN(torch.autograd.Function):
+    """G = A^T B, a deterministic reduction over all rows to a few dozen numbers (lds_gram_tn). dA = B dG^T, dB = A dG."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        from .. import kernels
+        ctx.save_for_backward(a, b)
+        return kernels.gram_tn(a, b)
+
+    @staticmethod
+    def backward(ctx, dg):
+        a, b = ctx.saved_tensors
+        da = _RowLinear.apply(b, dg, None) if ctx.needs_input_grad[0] else None
+        db = _RowLinear.apply(a, dg.t(), None) if ctx.needs_input_grad[1] else None
+        return da, db
+
+
+_ONES = {}
+
+
+def _column_sum(y: torch.Tensor) -> torch.Tensor:
+    """y.sum(0) as 1^T y through _GramTN (torch's column reduction of an [N, 16] tensor is a 20 us single-block kernel)."""
+    key = (y.shape[0], y.device)
+    ones = _ONES.get(key)
+    if ones is None:
+        ones = _ONES[key] = torch.ones((y.shape[0], 1), dtype=torch.float32, device=y.device)
+    return _GramTN.apply(ones, y).reshape(-1)
+
+
+class _BiasAdd(torch.autograd.Function):
+    """x + bias with the bias gradient as a _GramTN column sum (any-order differentiable: both directions are linear)."""
+
+    @staticmethod
+    def forward(ctx, x, bias):
+        return x + bias
+
+    @staticmethod
+    def backward(ctx, dy):
+        return (dy if ctx.needs_input_grad[0] else None), (_column_sum(dy) if ctx.needs_input_grad[1] else None)
+
+
+def _skinny_ok(t: torch.Tensor, *widths) -> bool:
+    return t.is_cuda and t.dim() == 2 and t.dtype == torch.float32 and all(0 < w <= 128 for w in widths)
+
+
+SKINNY_LINEAR = [True]         # MetaLinear with in/out features <= 128 on CUDA runs on lds_row_linear / lds_gram_tn
 SPARSE_DENSITY = 0.25          # same rule as the fused outer step (kernels.OuterStep.SPARSE_DENSITY)
 
 
@@ -110,15 +174,15 @@ class MetaLinear(nn.Linear, MetaModule):
         if isinstance(input, SparseFeatures):
             out = _SparseProduct.apply(params["weight"].t(), input, False)
             bias = params.get("bias", None)
-            return out if bias is None else out + bias
+            if bias is None:
+                return out
+            return _BiasAdd.apply(out, bias) if _skinny_ok(out, out.shape[1]) else out + bias
         weight = params["weight"]
-        if input.is_cuda and input.dim() == 2 and input.shape[0] * weight.shape[0] * weight.shape[1] <= SMALL_LINEAR_ELEMENTS:
+        if SKINNY_LINEAR[0] and _skinny_ok(input, weight.shape[0], weight.shape[1]) and weight.dtype == torch.float32:
             # a skinny layer (hidden x classes): as a matmul its weight gradient is a [C x N] x [N x h] product that cuBLAS
-            # runs as a 30 us "large-K" SGEMM for a 6 x 16 result, 16 times per bilevel block. As broadcast-multiply-reduce
-            # every order of its backward is a ~2 us elementwise + reduction pair.
-            out = (input.unsqueeze(1) * weight.unsqueeze(0)).sum(dim=2)
-            bias = params.get("bias", None)
-            return out if bias is None else out + bias
+            # runs as a 30 us "large-K" SGEMM for a 6 x 16 result, 16 times per bilevel block; here every order of its backward
+            # is one ~3 us launch of lds_row_linear / lds_gram_tn.
+            return _RowLinear.apply(input, weight, params.get("bias", None))
         return F.linear(input, weight, params.get("bias", None))
 
 

@@ -195,7 +195,10 @@ class _FactoredPropagate(torch.autograd.Function):
     def backward(ctx, dz):
         q, r, z = ctx.saved_tensors
         fg = ctx.fg
-        need_q, need_r = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        # r = deg^-1/2 leads to theta only (deg is a function of the sample). A create_graph backward is the inner optimiser's
+        # gradient w.r.t. the GCN weights, which sends nothing to theta (see _FactoredMatmul): skip dr there; the nodes recorded
+        # for dq still carry the dependence on r that the hypergradient pass differentiates.
+        need_q, need_r = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and not torch.is_grad_enabled()
         if not torch.is_grad_enabled():
             fg.sink.add_outer(dz.detach(), q.detach(), r.detach())
         dq = _FactoredPropagate.apply(dz, r, fg.link, fg) if (need_q or need_r) else None

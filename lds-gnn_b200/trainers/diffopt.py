@@ -16,6 +16,7 @@ flat result, so the next step's concatenation is free.
 import math
 from typing import Iterable, List
 
+import numpy as np
 import torch
 
 
@@ -34,10 +35,13 @@ class DifferentiableAdam:
         self.state = {"step": 0, "exp_avg": None, "exp_avg_sq": None}
         self._vectors = None          # per-element hyper-parameters, built on the parameters' device at the first step
         self._flat = None             # (flat tensor, views) of the last result: reused when the caller passes the views back
-        # CUDA-graph capture of a bilevel block: float64 device tensor [1] = number of steps taken BEFORE the block; the bias
-        # correction is then computed on the device from it (a replayed graph must not bake the step count in)
+        # CUDA-graph capture of a bilevel block: int64 device tensor [1] = number of steps taken BEFORE the block. The bias
+        # correction is then looked up on the device (a replayed graph must not bake the step count in): one gather from a
+        # table of sqrt(1 - b2^t) / (1 - b1^t), t = 0 .. TABLE-1, computed once in fp64 (the factor is 1.0f well before the end).
         self.device_step = None
         self.device_offset = 0
+        self._correction_table = None
+        self._host_correction = None
 
     # ---- per-element hyper-parameter vectors -----------------------------------------------------------------
     def _hyper(self, like: torch.Tensor):
@@ -95,13 +99,18 @@ class DifferentiableAdam:
             self.device_offset += 1
             if not (isinstance(b1, float) and isinstance(b2, float)):
                 raise NotImplementedError("device-side step count needs the same betas in every parameter group")
-            td = self.device_step + float(self.device_offset)                  # float64: 1 - b2^t keeps its digits
-            correction = (torch.sqrt(1 - b2 ** td) / (1 - b1 ** td)).to(p.dtype)
+            correction = self.correction_table(p).index_select(0, (self.device_step + self.device_offset).clamp_max(self.TABLE - 1))
+            step_size = correction * hp["lr"]                       # fp32 table entry x fp32(lr), rounded to fp32
         elif isinstance(b1, float) and isinstance(b2, float):
             correction = math.sqrt(1 - b2 ** t) / (1 - b1 ** t)
+            if isinstance(hp["lr"], float) and p.dtype == torch.float32:
+                # the same fp32 arithmetic as the device-side path above: a step-by-step run and a replayed block agree bitwise
+                step_size = float(np.float32(self._host_table()[min(t, self.TABLE - 1)]) * np.float32(hp["lr"]))
+            else:
+                step_size = hp["lr"] * correction
         else:
-            correction = torch.sqrt(1 - torch.as_tensor(b2) ** t) / (1 - torch.as_tensor(b1) ** t)
-        new_p = p - (hp["lr"] * correction) * (m / (root + hp["eps"]))
+            step_size = hp["lr"] * (torch.sqrt(1 - torch.as_tensor(b2) ** t) / (1 - torch.as_tensor(b1) ** t))
+        new_p = p - step_size * (m / (root + hp["eps"]))
         frozen = None
         if any(unused) or not isinstance(hp["in_group"], float):
             # parameters without a gradient (or outside every group) keep value and state, like torch.optim.Adam
@@ -118,6 +127,22 @@ class DifferentiableAdam:
         views = [new_p[offsets[i]:offsets[i + 1]].view(shape) for i, shape in enumerate(self._shapes)]
         self._flat = (new_p, views)
         return views
+
+    TABLE = 1 << 16
+
+    def _host_table(self):
+        """fp32 bias-correction factors sqrt(1 - b2^t) / (1 - b1^t) for t = 0 .. TABLE-1 (numpy; entry 0 unused)."""
+        if self._host_correction is None:
+            b1, b2 = self.param_groups[0]["betas"]
+            t = np.maximum(np.arange(self.TABLE, dtype=np.float64), 1.0)
+            self._host_correction = (np.sqrt(1 - b2 ** t) / (1 - b1 ** t)).astype(np.float32)
+        return self._host_correction
+
+    def correction_table(self, like: torch.Tensor) -> torch.Tensor:
+        """The same table on `like`'s device."""
+        if self._correction_table is None or self._correction_table.device != like.device:
+            self._correction_table = torch.from_numpy(self._host_table()).to(like.dtype).to(like.device)
+        return self._correction_table
 
     def detach_(self):
         """Cut the optimiser state from the autograd graph (truncated back-propagation, inner.py:110-125)."""

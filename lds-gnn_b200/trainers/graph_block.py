@@ -6,7 +6,7 @@ O(N h) elementwise kernels) but ~15 ms of host work (Python autograd over the un
 varies between blocks is therefore read from device memory, so one captured graph serves every block:
   * the Philox step of each sampled graph  -> lds_k1_sample_normalize_dstep reads a device counter (+ its offset in the block)
   * torch's dropout masks                  -> torch's own graph-safe generator offsets
-  * the inner Adam's step count            -> `DifferentiableAdam.device_step` (bias correction computed on the device)
+  * the inner Adam's step count            -> `DifferentiableAdam.device_step` (bias correction gathered from a device table)
   * the outer learning rate (StepLR decay) -> a device scalar folded into the gradient factors (the update is linear in them)
   * fast weights / Adam moments            -> static buffers, written back by the block's last nodes
 and everything the host needs afterwards comes back in one transfer: the tau+1 (loss, acc) pairs. The weights after every
@@ -49,7 +49,7 @@ class CapturedBilevelBlock:
         self.m = torch.zeros(total, **f32)                          # Adam moments at block entry / exit
         self.v = torch.zeros(total, **f32)
         self.snap = torch.zeros((self.tau, total), **f32)           # fast weights after inner step k
-        self.t_dev = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.t_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.lr_dev = torch.zeros(1, **f32)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.metrics = torch.zeros((self.tau + 1, 2), **f32)
@@ -58,6 +58,7 @@ class CapturedBilevelBlock:
         self.draws = self.tau + 1
         self.resident = False                                       # True: the static buffers hold the current inner state
         self._lr_saved = None
+        self._table = None
         self._keepalive = None
         self._theta_ptr = None
 
@@ -119,6 +120,7 @@ class CapturedBilevelBlock:
         opt.state["exp_avg"], opt.state["exp_avg_sq"] = self.m, self.v
         opt._flat = None
         opt.device_step, opt.device_offset = self.t_dev, 0
+        opt._correction_table = self._table                        # the runner replaces the optimiser object; the table is ours
         results = []
         inner.deferred = results
         outer.deferred = (results, self.lr_dev)
@@ -149,6 +151,7 @@ class CapturedBilevelBlock:
         # one eager pass on a side stream first (library handles, workspaces, index caches), then the capture itself; both leave
         # the Python-side counters advanced and (the eager one) the state changed: restore everything afterwards
         self._set_dynamic(host[0], host[1], outer.get_learning_rates()[0])
+        self._table = inner.optimizer.correction_table(self.w)      # built (host -> device copy) BEFORE the capture
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -196,7 +199,7 @@ class CapturedBilevelBlock:
 
     def _set_dynamic(self, philox_step: int, adam_steps: int, lr: float):
         self.step_dev.fill_(int(philox_step))
-        self.t_dev.fill_(float(adam_steps))
+        self.t_dev.fill_(int(adam_steps))
         self.lr_dev.fill_(float(lr))
 
     # ------------------------------------------------------------------------------------------ replay

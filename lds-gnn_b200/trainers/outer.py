@@ -183,7 +183,10 @@ class OuterProblemTrainer:
                 self.deferred[0].append(torch.stack((loss.detach(), correct)))
                 return None
             if kind == _lib.OPT_SGD:
-                kernels.k3k4_theta_update_tc_(theta, n, fa, fb, cvec, group["lr"])
+                # lr folded into the factors exactly as the captured block does (where it must live in device memory), so a
+                # step-by-step run and a replayed block produce the same bits
+                lr = float(group["lr"])
+                kernels.k3k4_theta_update_tc_(theta, n, fa * lr, fb, cvec * lr, 1.0)
             else:
                 st = self._adam_state
                 if st is None or st["m"].shape != theta.shape:

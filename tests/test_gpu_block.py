@@ -76,11 +76,13 @@ def test_captured_block_replays_match_the_eager_loop(name, tau):
     mg, pg, wg, lg, sg, tg = out["graph"]
     me, pe, we, le, se, te = out["eager"]
     assert (sg, tg) == (se, te) == (3 * (tau + 1), 3 * tau) and lg == pytest.approx(le)
+    # the replayed block executes the same kernels on the same numbers as the eager loop (learning rate and Adam step size
+    # are rounded the same way in both), so the comparison is tight: a looser bound would hide a flipped Bernoulli draw
     for a, b in zip(mg, me):
-        assert abs(a.loss - b.loss) < 2e-5 * max(1.0, abs(b.loss)) and abs(a.acc - b.acc) < 1e-6
+        assert abs(a.loss - b.loss) < 1e-6 * max(1.0, abs(b.loss)) and abs(a.acc - b.acc) < 1e-6
     for a, b in zip(wg, we):
-        assert (a - b).abs().max().item() < 1e-5
-    assert (pg - pe).abs().max().item() < 1e-5
+        assert (a - b).abs().max().item() < 1e-6
+    assert (pg - pe).abs().max().item() < 1e-6
     assert (pg - (0.6 * t(g["theta_triu"]) + 0.2)).abs().max().item() > 1e-5          # theta really moved
 
 

@@ -343,3 +343,54 @@ def test_sparse_linear_is_differentiable_to_second_order():
         results.append((out.detach(), g.detach(), gg))
     for a, b in zip(*results):
         assert (a - b).abs().max() <= 1e-4 * max(1.0, b.abs().max().item())
+
+
+@pytest.mark.parametrize("n,k,m", [(1, 1, 1), (130, 16, 6), (3327, 6, 16), (3327, 16, 16), (20000, 64, 7), (257, 128, 128), (1000, 3, 100)])
+def test_row_linear_and_gram_tn_match_fp64_products(n, k, m):
+    """lds_row_linear / lds_gram_tn (MetaLinear of layer_out and its autograd products, src/models/layers.py:43): against fp64
+    torch products; strided (transposed) weights; the Gram reduction is bitwise reproducible and re-arms its own counter."""
+    from lds_gnn_b200 import kernels
+    torch.manual_seed(n + k + m)
+    x = torch.randn(n, k, device="cuda")
+    w = torch.randn(m, k, device="cuda")
+    b = torch.randn(m, device="cuda")
+    ref = x.double() @ w.double().t() + b.double()
+    y = kernels.row_linear(x, w, b)
+    assert (y.double() - ref).abs().max() <= 2e-6 * max(1.0, ref.abs().max().item()) * k ** 0.5
+    wt = torch.randn(k, m, device="cuda")                                    # the same product through a transposed view
+    y2 = kernels.row_linear(x, wt.t())
+    ref2 = x.double() @ wt.double()
+    assert (y2.double() - ref2).abs().max() <= 2e-6 * max(1.0, ref2.abs().max().item()) * k ** 0.5
+    a = torch.randn(n, m, device="cuda")
+    g = kernels.gram_tn(a, x)
+    refg = a.double().t() @ x.double()
+    assert g.shape == (m, k) and (g.double() - refg).abs().max() <= 1e-6 * max(1.0, refg.abs().max().item()) * n ** 0.5
+    for _ in range(3):
+        assert torch.equal(kernels.gram_tn(a, x), g)
+    ones = torch.ones(n, 1, device="cuda")
+    assert (kernels.gram_tn(ones, x).reshape(-1).double() - x.double().sum(0)).abs().max() <= 1e-6 * n ** 0.5 * max(1.0, x.abs().max().item())
+
+
+def test_skinny_linear_is_differentiable_to_second_order_like_f_linear():
+    from collections import OrderedDict
+    import lds_gnn_b200.models.layers as L
+    torch.manual_seed(1)
+    x = torch.randn(500, 16, device="cuda")
+    lin = L.MetaLinear(16, 6).cuda()
+    with torch.no_grad():
+        lin.bias.normal_()
+    results = []
+    for skinny in (True, False):
+        L.SKINNY_LINEAR[0] = skinny
+        try:
+            xin = x.clone().requires_grad_(True)
+            wgt = lin.weight.detach().clone().requires_grad_(True)
+            bias = lin.bias.detach().clone().requires_grad_(True)
+            out = lin(xin, params=OrderedDict(weight=wgt, bias=bias))
+            gx, gw, gb = torch.autograd.grad((out ** 3).sum(), (xin, wgt, bias), create_graph=True)
+            second = torch.autograd.grad((gx ** 2).sum() + (gw ** 2).sum() + (gb ** 2).sum(), (xin, wgt, bias))
+            results.append((out.detach(), gx.detach(), gw.detach(), gb.detach()) + tuple(second))
+        finally:
+            L.SKINNY_LINEAR[0] = True
+    for a, b in zip(*results):
+        assert (a - b).abs().max() <= 2e-4 * max(1.0, b.abs().max().item())
