@@ -12,6 +12,8 @@ FAMILIES = [("lds::k2_mma_kernel", "K2 `k2_mma_kernel` (tcgen05 propagate, every
             ("lds::k3_tc_kernel", "K3+K4 `k3_tc_kernel` (all factor pairs of the block, one pass over theta)"),
             ("lds::k3_pack_kernel", "K3 factor pack `k3_pack_kernel`"),
             ("lds::spmm_csr_kernel", "CSR feature products `spmm_csr_kernel`"),
+            ("lds::row_linear_kernel", "skinny X W^T `row_linear_kernel`"),
+            ("lds::gram_tn_kernel", "skinny A^T B / column sums `gram_tn_kernel`"),
             ("gemm", "cuBLAS / CUTLASS GEMMs (skinny dense products left in torch)"),
             ("reduce_kernel", "torch reductions"), ("elementwise", "torch elementwise"), ("", "other torch kernels (softmax, nll, index, cat, copy, dropout)")]
 agg = collections.OrderedDict((label, []) for _, label in FAMILIES)
