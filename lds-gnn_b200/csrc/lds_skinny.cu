@@ -80,15 +80,21 @@ gram_tn_kernel(const float* __restrict__ A, int64_t lda, int a, const float* __r
   if (!last) return;
   __threadfence();
   for (int p = threadIdx.x; p < pairs; p += SK_THREADS) {
-    float s = 0.f;
-    for (unsigned c = 0; c < gridDim.x; ++c) s += __ldcg(partial + (int64_t)c * pairs + p);
-    out[(int64_t)(p / b) * ldo + p % b] = s;
+    // four independent chains so the L2 loads overlap; the association ((c0 + c4 + ..) + (c1 + c5 + ..)) + .. is fixed
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    unsigned c = 0;
+    for (; c + 3 < gridDim.x; c += 4) {
+      s0 += __ldcg(partial + (int64_t)c * pairs + p);       s1 += __ldcg(partial + (int64_t)(c + 1) * pairs + p);
+      s2 += __ldcg(partial + (int64_t)(c + 2) * pairs + p); s3 += __ldcg(partial + (int64_t)(c + 3) * pairs + p);
+    }
+    for (; c < gridDim.x; ++c) s0 += __ldcg(partial + (int64_t)c * pairs + p);
+    out[(int64_t)(p / b) * ldo + p % b] = (s0 + s1) + (s2 + s3);
   }
   if (threadIdx.x == 0) *counter = 0u;                               // re-armed for the next call
 }
 
 static int gram_ctas(int64_t n_rows) {
-  int64_t g = ceil_div(n_rows, 32);
+  int64_t g = ceil_div(n_rows, 128);                // few, fatter CTAs: the last CTA's pass over the partial tiles is the serial part
   if (g > num_sms()) g = num_sms();
   return (int)(g < 1 ? 1 : g);
 }

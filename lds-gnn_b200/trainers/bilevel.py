@@ -43,7 +43,7 @@ class BilevelProblemRunner:
             self.logger.info("Starting new outer loop...")
             tau = max(1, hyper_gradient_interval)
             while not inner_stopper.abort:                     # judged on the training loss
-                if self.graph_blocks and current_step % tau == 1 % tau and self._block_eligible():
+                if self.graph_blocks and tau <= 64 and current_step % tau == 1 % tau and self._block_eligible():
                     advanced = self._run_block(tau, current_step, inner_stopper, sacred_runner)
                     if advanced is not None:
                         current_step = advanced

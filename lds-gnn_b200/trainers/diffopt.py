@@ -42,6 +42,8 @@ class DifferentiableAdam:
         self.device_offset = 0
         self._correction_table = None
         self._host_correction = None
+        self._block_steps = None
+        self._block_first = 1
 
     # ---- per-element hyper-parameter vectors -----------------------------------------------------------------
     def _hyper(self, like: torch.Tensor):
@@ -99,8 +101,15 @@ class DifferentiableAdam:
             self.device_offset += 1
             if not (isinstance(b1, float) and isinstance(b2, float)):
                 raise NotImplementedError("device-side step count needs the same betas in every parameter group")
-            correction = self.correction_table(p).index_select(0, (self.device_step + self.device_offset).clamp_max(self.TABLE - 1))
-            step_size = correction * hp["lr"]                       # fp32 table entry x fp32(lr), rounded to fp32
+            if self.device_offset == 1 or self._block_steps is None:
+                # step sizes of the next BLOCK_MAX steps in one gather (fp32 table entry x fp32(lr), rounded to fp32)
+                idx = (self.device_step + torch.arange(1, self.BLOCK_MAX + 1, device=p.device)).clamp_max(self.TABLE - 1)
+                self._block_steps = self.correction_table(p).index_select(0, idx) * hp["lr"]
+                self._block_first = self.device_offset
+            k = self.device_offset - self._block_first
+            if k >= self.BLOCK_MAX:
+                raise NotImplementedError(f"more than {self.BLOCK_MAX} unrolled steps per captured block")
+            step_size = self._block_steps[k:k + 1]
         elif isinstance(b1, float) and isinstance(b2, float):
             correction = math.sqrt(1 - b2 ** t) / (1 - b1 ** t)
             if isinstance(hp["lr"], float) and p.dtype == torch.float32:
@@ -129,6 +138,7 @@ class DifferentiableAdam:
         return views
 
     TABLE = 1 << 16
+    BLOCK_MAX = 64
 
     def _host_table(self):
         """fp32 bias-correction factors sqrt(1 - b2^t) / (1 - b1^t) for t = 0 .. TABLE-1 (numpy; entry 0 unused)."""

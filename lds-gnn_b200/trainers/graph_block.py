@@ -119,7 +119,7 @@ class CapturedBilevelBlock:
         opt = inner.optimizer
         opt.state["exp_avg"], opt.state["exp_avg_sq"] = self.m, self.v
         opt._flat = None
-        opt.device_step, opt.device_offset = self.t_dev, 0
+        opt.device_step, opt.device_offset, opt._block_steps = self.t_dev, 0, None
         opt._correction_table = self._table                        # the runner replaces the optimiser object; the table is ours
         results = []
         inner.deferred = results
@@ -138,7 +138,7 @@ class CapturedBilevelBlock:
         finally:
             inner.deferred = None
             outer.deferred = None
-            opt.device_step, opt.device_offset = None, 0
+            opt.device_step, opt.device_offset, opt._block_steps = None, 0, None
 
     def capture(self):
         inner, outer = self.inner, self.outer

@@ -11,7 +11,10 @@ src/trainers/bilevel.py:34-145) on the same synthetic dataset, splits, hyper-par
              full N x N matrix from torch's generator, triu mirror, straight-through estimator, dense normalisation,
              torch.mm propagation, autograd for everything — i.e. what the reference executes, on the same device
 
-Writes profiles/accuracy_parity_<shape>.json and prints a markdown table.
+Lives under tests/ because it runs the oracle's port of the reference as its second arm (the oracle is test infrastructure:
+only tests/, smoke() and bench.py's cpu_baseline leg may execute it). Not collected by pytest; run it by hand on a B200:
+    python tests/accuracy_parity.py --shape cora --seeds 5
+Writes gpurun_out/accuracy_parity_<shape>.json and prints a markdown table.
 """
 import argparse
 import json
