@@ -75,6 +75,25 @@ class CapturedBilevelBlock:
         return names == list(NAMES) and all(p.is_cuda and p.dtype == torch.float32 for p in inner.model_params.values())
 
     # ------------------------------------------------------------------------------------------ state hand-over
+    def _is_resident(self) -> bool:
+        """True when the trainers' Python-side state IS the static buffers (what `replay` leaves behind). Anything else — fresh
+        weights / optimiser after `reset_weights` / `reset_optimizer`, eager steps in between, `store_state` — is detected by
+        identity, so a stale buffer can never be replayed."""
+        params, state = self.inner.model_params, self.inner.optimizer.state
+        first = params.get(NAMES[0]) if hasattr(params, "get") else None
+        return (self.resident and first is not None and first.data_ptr() == self.w.data_ptr() and first.grad_fn is None
+                and state["exp_avg"] is self.m and state["exp_avg_sq"] is self.v)
+
+    def _publish_state(self):
+        """The trainers' Python-side state := the static buffers (views, no history): what a replay leaves behind, and what the
+        capture must leave behind too (its own bodies left references to tensors of the graph's pool)."""
+        inner = self.inner
+        inner.model_params = OrderedDict((name, self.w[self.offsets[i]:self.offsets[i + 1]].view(self.shapes[i]).requires_grad_(True))
+                                         for i, name in enumerate(NAMES))          # leaves: an eager step may follow
+        inner.optimizer.state["exp_avg"], inner.optimizer.state["exp_avg_sq"] = self.m, self.v
+        inner.optimizer._flat = None
+        self.resident = True
+
     def load_state(self):
         """Eager inner state (fast weights, Adam moments, step count) -> static buffers."""
         inner = self.inner
@@ -182,6 +201,7 @@ class CapturedBilevelBlock:
         inner.optimizer.state["step"] = host[1]
         model.zero_grad(set_to_none=True)
         self.graph = graph
+        self._publish_state()
         # The graph holds raw addresses. Everything it reads that was allocated OUTSIDE its private pool must outlive it: the
         # optimiser whose per-element hyper-parameter vectors were baked in (the runner replaces the optimiser object at every
         # outer iteration), the kernels' cached workspaces (a later, larger request would replace and free them), theta.
@@ -208,13 +228,13 @@ class CapturedBilevelBlock:
         count, StepLR, the lazily synchronised `probs`) is advanced as the eager loop would have."""
         inner, outer = self.inner, self.outer
         if self.graph is None:
-            if not self.resident:
+            if not self._is_resident():
                 self.load_state()
             self.capture()
         if outer.model.theta_full().data_ptr() != self._theta_ptr:       # the model was moved / rebuilt: addresses changed
             self.graph = None
             return self.replay()
-        if not self.resident:
+        if not self._is_resident():
             self.load_state()
         outer.model.train()
         inner.model.train(True)
@@ -229,10 +249,7 @@ class CapturedBilevelBlock:
             self._lr_saved = (sched.last_epoch, [g["lr"] for g in outer.optimizer.param_groups], list(sched._last_lr), sched._step_count)
             outer.optimizer._opt_called = True
             sched.step()
-        # the trainers' Python-side state now describes the block's result (views of the static buffers, no history)
-        inner.model_params = OrderedDict((name, self.w[self.offsets[i]:self.offsets[i + 1]].view(self.shapes[i])) for i, name in enumerate(NAMES))
-        inner.optimizer.state["exp_avg"], inner.optimizer.state["exp_avg_sq"] = self.m, self.v
-        inner.optimizer._flat = None
+        self._publish_state()
         rows = self.metrics.tolist()                                # the block's only device->host transfer
         return [Metrics(loss=r[0], acc=r[1]) for r in rows]
 
