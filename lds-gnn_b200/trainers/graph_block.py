@@ -182,13 +182,28 @@ class CapturedBilevelBlock:
                     self.draws = PHILOX.end_capture()
             torch.cuda.current_stream().wait_stream(side)
             self._restore(saved, theta)
+            # capture_begin / capture_end directly: the `torch.cuda.graph` context manager first runs gc.collect() and
+            # torch.cuda.empty_cache(), which costs seconds when a previous phase left tens of GB cached, and this graph's pool
+            # is a fraction of a GB
             graph = torch.cuda.CUDAGraph()
+            capture_stream = torch.cuda.Stream()
+            capture_stream.wait_stream(torch.cuda.current_stream())
             PHILOX.begin_capture(self.step_dev)
             try:
-                with torch.cuda.graph(graph):
-                    self._body()
+                with torch.cuda.stream(capture_stream):
+                    graph.capture_begin()
+                    try:
+                        self._body()
+                    except BaseException:
+                        try:
+                            graph.capture_end()
+                        except Exception:
+                            pass
+                        raise
+                    graph.capture_end()
             finally:
                 PHILOX.end_capture()
+            torch.cuda.current_stream().wait_stream(capture_stream)
         except Exception as exc:
             torch.cuda.synchronize()
             self._restore(saved, theta)
