@@ -126,3 +126,40 @@ def test_runner_with_captured_blocks_follows_the_step_by_step_loop_incl_early_st
         assert (a - b).abs().max().item() < 1e-5
     for key in rg:
         assert abs(rg[key] - re_[key]) < 1e-4
+
+
+def test_capture_failure_falls_back_to_the_step_by_step_loop_with_state_intact(monkeypatch):
+    """If the block cannot be captured (here: its body raises while the stream is capturing), the runner must carry on step by
+    step from exactly the state at block entry — the eager warm-up pass and the aborted capture leave no trace in theta, the fast
+    weights, the optimiser, the Philox counter or the LR schedule."""
+    import lds_gnn_b200.trainers.graph_block as GB
+    from lds_gnn_b200.models.sampling import PHILOX
+    g = load_golden("n130_sparse")
+    real_body = GB.CapturedBilevelBlock._body
+
+    def failing_body(self):
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("simulated capture failure")
+        return real_body(self)
+
+    out = {}
+    for mode in ("broken-capture", "eager"):
+        runner, inner, outer, model = _runner(g)
+        runner.graph_blocks = mode == "broken-capture"
+        if mode == "broken-capture":
+            monkeypatch.setattr(GB.CapturedBilevelBlock, "_body", failing_body)
+        else:
+            monkeypatch.setattr(GB.CapturedBilevelBlock, "_body", real_body)
+        PHILOX.manual_seed(5)
+        np.random.seed(0)
+        torch.manual_seed(9)
+        runner.train(patience=2, hyper_gradient_interval=3, inner_loop_max_epochs=7, outer_loop_max_epochs=1)
+        res = runner.evaluate()
+        out[mode] = (model.probs.detach().clone(), outer.get_learning_rates(), PHILOX.step, res)
+        if mode == "broken-capture":
+            assert runner.graph_blocks is False and outer.last_route == "factored"      # it did fall back
+    (pb, lb, sb, rb), (pe, le, se, re_) = out["broken-capture"], out["eager"]
+    assert sb == se and lb == pytest.approx(le)
+    assert (pb - pe).abs().max().item() < 1e-6
+    for key in rb:
+        assert abs(rb[key] - re_[key]) < 1e-5
