@@ -10,7 +10,10 @@ triangles and a natural row-block sharding. The two views are kept consistent la
     optimizers holding the Parameter) sees fresh values — a fused step only marks `probs` stale and the
     conversion kernel runs on the next access;
   * `theta_full()` re-expands `probs` when the Parameter was modified since the last sync (tensor version
-    counter / storage pointer).
+    counter / storage pointer) OR was handed out since (`model.probs`, `parameters()`, `state_dict()`): writes
+    through `.data` (`model.probs.data.fill_(..)`, the reference's `ParameterClamper`) do not bump the version
+    counter, so a hand-out is treated as a possible write. Code that keeps a long-lived reference to the
+    Parameter and writes through `.data` later must call `model.invalidate()`.
 """
 from abc import ABC, abstractmethod
 from typing import Dict
@@ -66,6 +69,7 @@ class BernoulliGraphModel(GraphGenerativeModel):
         self._full = None            # [n, ld] fp32 device copy (unclamped, symmetric)
         self._full_key = None        # (data_ptr, version) of `probs` when `_full` was built from it
         self._probs_stale = False    # `_full` is newer than `probs` (after fused steps)
+        self._handed_out = False     # `probs` left the module since the last expansion: `.data` writes are invisible to `_version`
         self.factor_sink = FactorSink()   # hypergradient deposits of factored graphs (unrolled bilevel loop)
         values = init_matrix if directed else get_triu_values(init_matrix)
         self.probs = Parameter(values, requires_grad=True)
@@ -86,18 +90,33 @@ class BernoulliGraphModel(GraphGenerativeModel):
     def __getattr__(self, name):
         if name == "probs" and "_parameters" in self.__dict__:
             self._sync_probs()
+            self.__dict__["_handed_out"] = True
         return super().__getattr__(name)
 
     def named_parameters(self, *args, **kwargs):
         self._sync_probs()
+        self._handed_out = True
         return super().named_parameters(*args, **kwargs)
 
     def state_dict(self, *args, **kwargs):
         self._sync_probs()
+        self._handed_out = True
         return super().state_dict(*args, **kwargs)
 
+    def invalidate(self):
+        """`probs` was written behind the module's back (through `.data` on a reference obtained earlier): the next
+        `theta_full()` re-expands it. A device copy that is NEWER than `probs` (after fused steps) is flushed first."""
+        self._sync_probs()
+        self._full_key = None
+
     def load_state_dict(self, state_dict, *args, **kwargs):
-        self._probs_stale = False    # the loaded values win over a newer device copy
+        src = state_dict.get("probs") if hasattr(state_dict, "get") else None
+        if torch.is_tensor(src) and src.data_ptr() == self._probs_param().data_ptr():
+            # the dict aliases the live Parameter — the reference's in-memory "checkpoint" (src/trainers/bilevel.py:96-98 keeps
+            # `state_dict()` without a copy): loading it is a no-op there, so the newest values (the device copy) must survive
+            self._sync_probs()
+        else:
+            self._probs_stale = False    # the loaded values win over a newer device copy
         return super().load_state_dict(state_dict, *args, **kwargs)
 
     def _apply(self, fn, *args, **kwargs):
@@ -113,10 +132,11 @@ class BernoulliGraphModel(GraphGenerativeModel):
         if not p.is_cuda:
             raise RuntimeError("BernoulliGraphModel: the B200 path needs the model on a CUDA device (model.to('cuda')); no CPU fallback")
         key = (p.data_ptr(), p._version)
-        if self._full is None or (not self._probs_stale and key != self._full_key):
+        if self._full is None or (not self._probs_stale and (key != self._full_key or self._handed_out)):
             from .. import kernels
             self._full = kernels.theta_triu_to_full(p.detach(), clamp=False, out=self._full)
             self._full_key = key
+            self._handed_out = False
         return self._full
 
     def mark_full_updated(self):
@@ -131,7 +151,14 @@ class BernoulliGraphModel(GraphGenerativeModel):
 
     # ---- reference API ---------------------------------------------------------------------------
     def project_parameters(self):
+        """clamp(probs, 0, 1) in place (src/models/graph.py:16-20, 63-64). When the device matrix is the newer copy (after
+        fused steps) it is the one that gets clamped — `probs` receives the result at its next access."""
+        if self._probs_stale and self._full is not None and not self.directed:
+            from .. import kernels
+            kernels.theta_clamp_(self._full, self._n)
+            return
         self.apply(ParameterClamper())
+        self._full_key = None
 
     def forward(self, *args, **kwargs) -> Tensor:
         return self.probs if self.directed else triu_values_to_symmetric_matrix(self.probs)  # type: ignore

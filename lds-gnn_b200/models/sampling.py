@@ -40,14 +40,24 @@ class PhiloxState:
         self.step = 0
         self.capture_base = None         # int64 device tensor [1] while capturing, else None
         self.capture_draws = 0
+        self._derived_from = None        # torch.initial_seed() the current seed was derived from (None: set explicitly)
 
     def manual_seed(self, seed: int):
         self.seed = int(seed) & ((1 << 64) - 1)
         self.step = 0
+        self._derived_from = None
 
     def _ensure_seed(self):
+        """A seed derived from torch's generator follows it: after a later `torch.manual_seed(s)` (sacred seeds every run
+        that way) the next draw re-derives the seed and restarts the step counter, so a second run in the same process is
+        reproducible too. A seed set with `manual_seed` (or assigned) stays."""
+        if self.seed is not None and self._derived_from is not None and self.capture_base is None \
+                and torch.initial_seed() != self._derived_from:
+            self.seed = None
         if self.seed is None:
+            self._derived_from = torch.initial_seed()
             self.seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            self.step = 0
 
     def next_step(self):
         self._ensure_seed()

@@ -29,6 +29,10 @@ class BilevelProblemRunner:
         # Replay aligned blocks (tau inner steps + the hyper step) from one captured CUDA graph when the plain LDS configuration
         # allows it (trainers/graph_block.py); LDS_GRAPH_BLOCKS=0 or `graph_blocks = False` keeps the step-by-step loop.
         self.graph_blocks = os.environ.get("LDS_GRAPH_BLOCKS", "1") != "0"
+        # The reference keeps `graph_model.state_dict()` WITHOUT a copy in its early stopper (src/trainers/bilevel.py:96-98): the
+        # dict aliases the live `probs`, so `evaluate()` reloads the LAST theta next to the best GCN weights. False (default)
+        # reproduces that; True snapshots theta of the best outer iteration instead (a deliberate deviation).
+        self.snapshot_best_graph = False
         self._blocks = {}
 
     def train(self, patience: int, hyper_gradient_interval: int, inner_loop_max_epochs: int = 400,
@@ -70,7 +74,8 @@ class BilevelProblemRunner:
                 sacred_runner.log_scalar("loss.test.empirical", test_results.loss)
                 sacred_runner.log_scalar("acc.test.empirical", test_results.acc)
             self.logger.info(f"Empirical Validation Set Results: loss={val_results.loss}, accuracy={val_results.acc}")
-            outer_stopper.update(val_results.loss, model_params=[deepcopy(gcn_params), deepcopy(self.outer_trainer.model.state_dict())])
+            graph_state = self.outer_trainer.model.state_dict()
+            outer_stopper.update(val_results.loss, model_params=[deepcopy(gcn_params), deepcopy(graph_state) if self.snapshot_best_graph else graph_state])
             outer_step += 1
         self.logger.info(f"Ended training after {outer_step} steps...")
         self.gcn_params, self.graph_state_dict = outer_stopper.model_params

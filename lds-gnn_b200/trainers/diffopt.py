@@ -3,10 +3,11 @@
 
 `higher` (git master, unpinned, scripts/install.sh:3-4) is not vendored with the reference and cannot be
 installed offline, so NUMERIC PARITY OF THIS UPDATE IS UNPINNED: this file follows the
-published algorithm — `torch.optim.Adam`'s rule of that era applied out of place so later losses can
+published algorithm of higher's master — `torch.optim.Adam`'s rule applied out of place so later losses can
 differentiate through it: g += wd * p; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
-p' = p - lr * sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps). It is checked against `torch.optim.Adam` on
-detached copies in tests/ (same trajectory to 1e-6 while eps placement is immaterial).
+p' = p - lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)  (bias correction on sqrt(v) BEFORE eps is added, exactly
+torch.optim.Adam's current form). It is checked against `torch.optim.Adam` on detached copies and against the
+live reference's inner steps run over the `higher` stand-in (tests/golden/blk_*.npz).
 
 All parameters are updated as ONE flat vector (per-group hyper-parameters become per-element vectors): the
 update is ~10 differentiable ops per step instead of ~14 per parameter tensor, which matters because the
@@ -37,7 +38,7 @@ class DifferentiableAdam:
         self._flat = None             # (flat tensor, views) of the last result: reused when the caller passes the views back
         # CUDA-graph capture of a bilevel block: int64 device tensor [1] = number of steps taken BEFORE the block. The bias
         # correction is then looked up on the device (a replayed graph must not bake the step count in): one gather from a
-        # table of sqrt(1 - b2^t) / (1 - b1^t), t = 0 .. TABLE-1, computed once in fp64 (the factor is 1.0f well before the end).
+        # table of (1 / (1 - b1^t), 1 / sqrt(1 - b2^t)), t = 0 .. TABLE-1, computed once in fp64 (both are 1.0f well before the end).
         self.device_step = None
         self.device_offset = 0
         self._correction_table = None
@@ -104,22 +105,25 @@ class DifferentiableAdam:
             if self.device_offset == 1 or self._block_steps is None:
                 # step sizes of the next BLOCK_MAX steps in one gather (fp32 table entry x fp32(lr), rounded to fp32)
                 idx = (self.device_step + torch.arange(1, self.BLOCK_MAX + 1, device=p.device)).clamp_max(self.TABLE - 1)
-                self._block_steps = self.correction_table(p).index_select(0, idx) * hp["lr"]
+                rows = self.correction_table(p).index_select(0, idx)
+                self._block_steps = (rows[:, 0] * hp["lr"], rows[:, 1])
                 self._block_first = self.device_offset
             k = self.device_offset - self._block_first
             if k >= self.BLOCK_MAX:
                 raise NotImplementedError(f"more than {self.BLOCK_MAX} unrolled steps per captured block")
-            step_size = self._block_steps[k:k + 1]
+            step_size, root_scale = self._block_steps[0][k:k + 1], self._block_steps[1][k:k + 1]
         elif isinstance(b1, float) and isinstance(b2, float):
-            correction = math.sqrt(1 - b2 ** t) / (1 - b1 ** t)
             if isinstance(hp["lr"], float) and p.dtype == torch.float32:
                 # the same fp32 arithmetic as the device-side path above: a step-by-step run and a replayed block agree bitwise
-                step_size = float(np.float32(self._host_table()[min(t, self.TABLE - 1)]) * np.float32(hp["lr"]))
+                row = self._host_table()[min(t, self.TABLE - 1)]
+                step_size, root_scale = float(np.float32(row[0]) * np.float32(hp["lr"])), float(row[1])
             else:
-                step_size = hp["lr"] * correction
+                step_size, root_scale = hp["lr"] / (1 - b1 ** t), 1.0 / math.sqrt(1 - b2 ** t)
         else:
-            step_size = hp["lr"] * (torch.sqrt(1 - torch.as_tensor(b2) ** t) / (1 - torch.as_tensor(b1) ** t))
-        new_p = p - step_size * (m / (root + hp["eps"]))
+            step_size = hp["lr"] / (1 - torch.as_tensor(b1) ** t)
+            root_scale = 1.0 / torch.sqrt(1 - torch.as_tensor(b2) ** t)
+        # higher master / torch.optim.Adam: the bias correction scales sqrt(v) BEFORE eps is added
+        new_p = p - step_size * (m / (root * root_scale + hp["eps"]))
         frozen = None
         if any(unused) or not isinstance(hp["in_group"], float):
             # parameters without a gradient (or outside every group) keep value and state, like torch.optim.Adam
@@ -141,11 +145,11 @@ class DifferentiableAdam:
     BLOCK_MAX = 64
 
     def _host_table(self):
-        """fp32 bias-correction factors sqrt(1 - b2^t) / (1 - b1^t) for t = 0 .. TABLE-1 (numpy; entry 0 unused)."""
+        """fp32 bias-correction factors [1 / (1 - b1^t), 1 / sqrt(1 - b2^t)] for t = 0 .. TABLE-1 (numpy; entry 0 unused)."""
         if self._host_correction is None:
             b1, b2 = self.param_groups[0]["betas"]
             t = np.maximum(np.arange(self.TABLE, dtype=np.float64), 1.0)
-            self._host_correction = (np.sqrt(1 - b2 ** t) / (1 - b1 ** t)).astype(np.float32)
+            self._host_correction = np.stack((1.0 / (1 - b1 ** t), 1.0 / np.sqrt(1 - b2 ** t)), axis=1).astype(np.float32)
         return self._host_correction
 
     def correction_table(self, like: torch.Tensor) -> torch.Tensor:

@@ -136,3 +136,100 @@ def _outer_steps(theta_triu, uniforms, x, w0, b0, w1, b1, y, mask, lr, lr_decay,
             ))
     stats = model.statistics()
     return results, stats
+
+
+# ------------------------------------------------------------------------------------------------
+# Rows (f)1, (f)2 and BASELINE config 3 of SURVEY.md §8: evaluation, unrolled bilevel block, S-sample step
+# ------------------------------------------------------------------------------------------------
+def _with_dtype(dtype, fn):
+    old_default = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)
+    try:
+        return fn()
+    finally:
+        torch.set_default_dtype(old_default)
+
+
+def empirical_mean(theta_triu, uniforms, x, w0, b0, w1, b1, y, val_mask, test_mask, dtype=torch.float32):
+    """The reference's `empirical_mean_loss` (src/utils/evaluation.py:51-84) with one explicit uniform matrix per sample.
+    Returns (val loss, val acc, test loss, test acc)."""
+    def run():
+        model, gcn, _, data = build(theta_triu, x, w0, b0, w1, b1, y, val_mask, lr=1.0, p=0.5, dtype=dtype)
+        from src.utils.evaluation import empirical_mean_loss
+        data.val_mask = torch.as_tensor(np.asarray(val_mask)).bool()
+        data.test_mask = torch.as_tensor(np.asarray(test_mask)).bool()
+        with explicit_draws(uniforms, ()):
+            val, test = empirical_mean_loss(gcn, graph_model=model, n_samples=len(uniforms), data=data,
+                                            model_parameters=None)
+        return np.array([val.loss, val.acc, test.loss, test.acc], dtype=np.float64)
+    return _with_dtype(dtype, run)
+
+
+def multi_sample_step(theta_triu, uniforms, x, w0, b0, w1, b1, y, mask, lr, p=0.0, keep_masks=(), dtype=torch.float32):
+    """BASELINE config 3: S Bernoulli samples per outer step. The reference has no such trainer method; this composes ITS
+    objects the way its train_step does (src/trainers/outer.py:57-87): zero_grad; S x {model.sample(); gcn forward; nll / S;
+    backward -> probs.grad accumulates}; optimizer.step(); project_parameters()."""
+    def run():
+        import torch.nn.functional as F
+        model, gcn, trainer, data = build(theta_triu, x, w0, b0, w1, b1, y, mask, lr=lr, p=p, dtype=dtype)
+        from src.utils.evaluation import accuracy
+        s_total = len(uniforms)
+        m = trainer.opt_mask
+        losses, accs = [], []
+        with explicit_draws(uniforms, keep_masks):
+            trainer.model.train()
+            trainer.optimizer.zero_grad()
+            for _ in range(s_total):
+                graph = trainer.model.sample()
+                gcn.train(p > 0.0)
+                pred = gcn(data.x, graph, params=None)
+                loss = F.nll_loss(pred[m], data.y[m])
+                losses.append(loss.item()); accs.append(accuracy(pred[m], data.y[m]))
+                (loss / s_total).backward()
+            grad = model.probs.grad.detach().numpy().copy()
+            trainer.optimizer.step()
+            trainer.model.project_parameters()
+        return dict(loss=np.float64(np.mean(losses)), acc=np.float64(np.mean(accs)), grad_triu=grad,
+                    theta_new=model.probs.detach().numpy().copy())
+    return _with_dtype(dtype, run)
+
+
+def bilevel_blocks(theta_triu, uniforms, x, w0, b0, w1, b1, y, train_mask, opt_mask, tau, blocks, outer_lr, lr_decay,
+                   inner_lr, weight_decay, dtype=torch.float32):
+    """`blocks` x {tau x BilevelProblemRunner.inner_opt_step; hyper_opt_step} of the unmodified reference
+    (src/trainers/bilevel.py:103-113, src/trainers/inner.py:55-74, src/trainers/outer.py:57-87) over the `higher` stand-in
+    (oracle/shims/higher/optim.py), dropout 0, one explicit uniform matrix per `sample()` call (tau + 1 per block).
+    Returns per block: inner (loss, acc) per step, the fast weights after every inner step, the hyper step's (loss, acc),
+    probs.grad and the updated probs."""
+    def run():
+        model, gcn, outer, data = build(theta_triu, x, w0, b0, w1, b1, y, opt_mask, lr=outer_lr, lr_decay=lr_decay, p=0.0, dtype=dtype)
+        from src.trainers.bilevel import BilevelProblemRunner
+        from src.trainers.inner import InnerProblemTrainer
+        data.train_mask = torch.as_tensor(np.asarray(train_mask)).bool()
+        data.val_mask = torch.as_tensor(np.asarray(opt_mask)).bool()
+        data.test_mask = data.val_mask
+        inner = InnerProblemTrainer(gcn, data, lr=inner_lr, weight_decay=weight_decay)
+        runner = BilevelProblemRunner(inner, outer, data)
+        out = []
+        with explicit_draws(uniforms, ()):
+            for _ in range(blocks):
+                rec = dict(inner_loss=[], inner_acc=[], weights=[])
+                for _ in range(tau):
+                    m = runner.inner_opt_step()
+                    rec["inner_loss"].append(m.loss); rec["inner_acc"].append(m.acc)
+                    rec["weights"].append([v.detach().numpy().copy() for v in inner.model_params.values()])
+                captured = {}
+                real = outer.train_step
+
+                def spy(fct, *a, **k):
+                    captured["m"] = real(fct, *a, **k)
+                    captured["grad"] = model.probs.grad.detach().numpy().copy()
+                    return captured["m"]
+                outer.train_step = spy
+                runner.hyper_opt_step(0)
+                outer.train_step = real
+                rec.update(hyper_loss=captured["m"].loss, hyper_acc=captured["m"].acc, grad_triu=captured["grad"],
+                           theta_new=model.probs.detach().numpy().copy(), lr_after=outer.get_learning_rates()[0])
+                out.append(rec)
+        return out
+    return _with_dtype(dtype, run)

@@ -58,8 +58,120 @@ CASES = [
 ]
 
 
+def split_masks(seed, n):
+    """Disjoint train / opt (the half of the validation nodes the outer objective uses, scripts/bilevel.py:77) / val / test masks."""
+    rng = np.random.default_rng(1000 + seed)
+    perm = rng.permutation(n)
+    k = max(4, n // 6)
+    masks = []
+    for b in range(4):
+        m = np.zeros(n, dtype=bool)
+        m[perm[b * k:(b + 1) * k]] = True
+        masks.append(m)
+    return masks
+
+
+# ---- rows (f)1, (f)2 and config 3 of SURVEY.md §8 (VERDICT r1 item 1): goldens from the LIVE reference for
+#      empirical_mean_loss, the S-sample step and the unrolled bilevel block. Uniforms are not stored: they are
+#      PH.edge_uniforms(n, philox_seed, step[, sample]) — the generator is pinned by the Random123 vectors (tests/test_oracle.py).
+EVAL_CASES = [
+    # name,          seed, n,   f,  h,  c, S, step0
+    ("eval_n130_s4",   11, 130, 64, 16, 7, 4, 50),
+    ("eval_n257_s16",  12, 257, 50, 64, 7, 16, 7),
+]
+MULTI_CASES = [
+    # name,           seed, n,   f,  h,  c, S,  p,   lr,  step
+    ("multi_n130_s4",   21, 130, 64, 16, 7, 4,  0.5, 0.6, 3),
+    ("multi_n300_s16",  22, 300, 40, 16, 6, 16, 0.0, 0.8, 9),
+]
+BLOCK_CASES = [
+    # name,           seed, n,   f,  h,  c, tau, blocks, outer_lr, decay, inner_lr, wd,   step0
+    ("blk_n130_tau3",   31, 130, 64, 16, 7, 3,   2,      0.5,      0.9,   0.01,     5e-4, 100),
+    ("blk_n257_tau5",   32, 257, 50, 64, 7, 5,   1,      0.3,      0.99,  0.02,     1e-4, 0),
+    ("blk_n96_tau1",    33, 96,  30, 16, 6, 1,   3,      1.0,      1.0,   0.01,     0.0,  5),
+]
+
+
+def interior(theta):
+    """Every probability strictly inside (0, 1): every graph of the case is random."""
+    return (0.6 * theta + 0.2).astype(np.float32)
+
+
+def next_rows():
+    for name, seed, n, f, h, c, S, step0 in EVAL_CASES:
+        inp = make_inputs(seed, n, f, h, c, "mixed", 0.0)
+        inp["theta_triu"] = interior(inp["theta_triu"])
+        _, _, val_mask, test_mask = split_masks(seed, n)
+        philox_seed = 0x5EED0000 + seed
+        uniforms = [PH.edge_uniforms(n, philox_seed, step0 + s) for s in range(S)]
+        out = dict(inp)
+        out.pop("mask")
+        out.update(n=n, f=f, h=h, c=c, S=S, step0=np.int64(step0), philox_seed=np.int64(philox_seed), val_mask=val_mask, test_mask=test_mask)
+        for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+            out[f"metrics_{tag}"] = L.empirical_mean(inp["theta_triu"], uniforms, inp["x"], inp["w0"], inp["b0"], inp["w1"], inp["b1"],
+                                                     inp["y"], val_mask, test_mask, dtype=dt)
+        yield name, out
+    for name, seed, n, f, h, c, S, p, lr, step in MULTI_CASES:
+        inp = make_inputs(seed, n, f, h, c, "mixed", p)
+        inp["theta_triu"] = interior(inp["theta_triu"])
+        inp["theta_triu"][3] = 1.25; inp["theta_triu"][n + 5] = -0.1          # outside [0, 1]: the clamp backward masks them
+        philox_seed = 0x5EED0000 + seed
+        uniforms = [PH.edge_uniforms(n, philox_seed, step, sample=s) for s in range(S)]
+        keeps = []
+        if p > 0:
+            for s in range(S):
+                keeps += [PH.dropout_keep_mask(n, f, p, philox_seed, step, PH.STREAM_DROP_X, sample=s),
+                          PH.dropout_keep_mask(n, h, p, philox_seed, step, PH.STREAM_DROP_H, sample=s)]
+        out = dict(inp)
+        out.update(n=n, f=f, h=h, c=c, S=S, p=np.float64(p), lr=np.float64(lr), step=np.int64(step), philox_seed=np.int64(philox_seed))
+        for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+            r = L.multi_sample_step(inp["theta_triu"], uniforms, inp["x"], inp["w0"], inp["b0"], inp["w1"], inp["b1"], inp["y"],
+                                    inp["mask"], lr=lr, p=p, keep_masks=keeps, dtype=dt)
+            for k, v in r.items():
+                out[f"{k}_{tag}"] = v
+        yield name, out
+    for name, seed, n, f, h, c, tau, blocks, outer_lr, decay, inner_lr, wd, step0 in BLOCK_CASES:
+        inp = make_inputs(seed, n, f, h, c, "mixed", 0.0)
+        inp["theta_triu"] = interior(inp["theta_triu"])
+        train_mask, opt_mask, _, _ = split_masks(seed, n)
+        philox_seed = 0x5EED0000 + seed
+        uniforms = [PH.edge_uniforms(n, philox_seed, step0 + k) for k in range(blocks * (tau + 1))]
+        out = dict(inp)
+        out.pop("mask")
+        out.update(n=n, f=f, h=h, c=c, tau=tau, blocks=blocks, outer_lr=np.float64(outer_lr), lr_decay=np.float64(decay),
+                   inner_lr=np.float64(inner_lr), weight_decay=np.float64(wd), step0=np.int64(step0),
+                   philox_seed=np.int64(philox_seed), train_mask=train_mask, opt_mask=opt_mask)
+        for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+            res = L.bilevel_blocks(inp["theta_triu"], uniforms, inp["x"], inp["w0"], inp["b0"], inp["w1"], inp["b1"], inp["y"],
+                                   train_mask, opt_mask, tau=tau, blocks=blocks, outer_lr=outer_lr, lr_decay=decay,
+                                   inner_lr=inner_lr, weight_decay=wd, dtype=dt)
+            for b, rec in enumerate(res):
+                out[f"inner_loss{b}_{tag}"] = np.asarray(rec["inner_loss"], dtype=np.float64)
+                out[f"inner_acc{b}_{tag}"] = np.asarray(rec["inner_acc"], dtype=np.float64)
+                for k, ws in enumerate(rec["weights"]):
+                    for wname, w in zip(("w0", "b0", "w1", "b1"), ws):
+                        out[f"{wname}_after{b}_{k}_{tag}"] = w
+                out[f"hyper_loss{b}_{tag}"] = np.float64(rec["hyper_loss"])
+                out[f"hyper_acc{b}_{tag}"] = np.float64(rec["hyper_acc"])
+                out[f"lr_after{b}_{tag}"] = np.float64(rec["lr_after"])
+                out[f"theta_new{b}_{tag}"] = rec["theta_new"]
+                if tag == "f64":
+                    out[f"grad_triu{b}_{tag}"] = rec["grad_triu"]
+        yield name, out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    import sys
+    if "--next-only" not in sys.argv:
+        outer_cases()
+    for name, out in next_rows():
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def outer_cases():
     for name, seed, n, f, h, c, kind, p, steps, lr, decay in CASES:
         inp = make_inputs(seed, n, f, h, c, kind, p)
         philox_seed = 0x5EED0000 + seed

@@ -55,8 +55,8 @@ def to_uniform(words):
     return ((words >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)).astype(np.float32)
 
 
-def edge_uniforms(n, seed, step, sample=0):
-    """U[i, j] for the full n x n matrix, symmetric by construction (U[i,j] == U[j,i])."""
+def edge_uniforms_elementwise(n, seed, step, sample=0):
+    """U[i, j] for the full n x n matrix, one Philox call per ELEMENT — the literal statement of the mapping above."""
     i = np.arange(n, dtype=np.int64)[:, None]
     j = np.arange(n, dtype=np.int64)[None, :]
     a = np.minimum(i, j)
@@ -68,6 +68,23 @@ def edge_uniforms(n, seed, step, sample=0):
     return to_uniform(words)
 
 
+def edge_uniforms(n, seed, step, sample=0):
+    """U[i, j] for the full n x n matrix, symmetric by construction (U[i,j] == U[j,i]). One Philox call per 2x2 BLOCK
+    (a quarter of the work of `edge_uniforms_elementwise`, same values — tests/test_oracle.py checks the equality)."""
+    nb = (n + 1) // 2
+    P = np.arange(nb, dtype=np.int64)[:, None]
+    Q = np.arange(nb, dtype=np.int64)[None, :]
+    c2, c3 = _c23(step, STREAM_EDGES, sample)
+    w = philox4x32_10(np.maximum(P, Q), np.minimum(P, Q), c2, c3, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    upper, lower = P < Q, P > Q
+    words = np.empty((2 * nb, 2 * nb), dtype=np.uint32)
+    for di in range(2):
+        for dj in range(2):
+            diag = w[2 * min(di, dj) + max(di, dj)]          # canonical pair (min, max) inside a diagonal block
+            words[di::2, dj::2] = np.where(upper, w[2 * di + dj], np.where(lower, w[2 * dj + di], diag))
+    return to_uniform(words[:n, :n])
+
+
 def edge_uniform(seed, step, sample, i, j):
     a, b = (i, j) if i <= j else (j, i)
     c2, c3 = _c23(step, STREAM_EDGES, sample)
@@ -76,11 +93,12 @@ def edge_uniform(seed, step, sample, i, j):
 
 
 def dropout_uniforms(rows, cols, seed, step, stream, sample=0):
+    """One Philox call per (row, 4-column group); word = col % 4."""
     r = np.arange(rows, dtype=np.int64)[:, None]
-    c = np.arange(cols, dtype=np.int64)[None, :]
+    q = np.arange((cols + 3) // 4, dtype=np.int64)[None, :]
     c2, c3 = _c23(step, stream, sample)
-    w = philox4x32_10(c // 4, r, c2, c3, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    words = np.choose((c % 4) + 0 * r, w)
+    w = philox4x32_10(q + 0 * r, r + 0 * q, c2, c3, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    words = np.stack(w, axis=2).reshape(rows, -1)[:, :cols]
     return to_uniform(words)
 
 

@@ -1,9 +1,13 @@
-"""DifferentiableAdam restated from higher's published algorithm: torch.optim.Adam's update
-applied out of place with create_graph=True so later losses can differentiate through it
-(call sites: src/trainers/inner.py:48-50, 71). Weight decay is added to the gradient;
-denom = sqrt(v) + eps and step_size = lr * sqrt(1-beta2^t) / (1-beta1^t) (the torch-1.3-era Adam
-form that higher's DifferentiableAdam follows). Numeric parity with the real `higher` is
-UNPINNED: the package is absent and the reference's tests at this boundary are behavioural only."""
+"""DifferentiableAdam restated from higher's published algorithm (facebookresearch/higher, git master — what the
+reference installs, scripts/install.sh:3-4; call sites: src/trainers/inner.py:48-50, 71): torch.optim.Adam's update
+applied out of place with create_graph=True so later losses can differentiate through it.
+
+    g += wd * p;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2        (v == 0 entries get their sqrt-gradient masked)
+    denom = sqrt(v) / sqrt(1 - b2^t) + eps;  step_size = lr / (1 - b1^t);  p' = p - step_size * m / denom
+
+i.e. the bias correction is applied to sqrt(v) BEFORE eps is added (the form torch.optim.Adam uses since 1.6 and
+higher's master follows). Numeric parity with the real `higher` is UNPINNED: the package is absent and the reference's
+tests at this boundary are behavioural only."""
 import math
 
 import torch
@@ -42,15 +46,15 @@ class DifferentiableAdam(DifferentiableOptimizer):
                     st["exp_avg"] = torch.zeros_like(p.data)
                     st["exp_avg_sq"] = torch.zeros_like(p.data)
                 st["step"] += 1
+                bc1 = 1 - beta1 ** st["step"]
+                bc2 = 1 - beta2 ** st["step"]
                 if group["weight_decay"] != 0:
                     g = g + group["weight_decay"] * p
                 st["exp_avg"] = exp_avg = st["exp_avg"] * beta1 + (1 - beta1) * g
                 st["exp_avg_sq"] = exp_avg_sq = st["exp_avg_sq"] * beta2 + (1 - beta2) * g * g
-                bc1 = 1 - beta1 ** st["step"]
-                bc2 = 1 - beta2 ** st["step"]
-                # higher masks the sqrt's infinite gradient where v == 0; a 1e-30 floor does the same job
+                # higher masks the sqrt's infinite gradient where v == 0 (_maybe_mask); a 1e-30 floor does the same job
                 safe = exp_avg_sq + (exp_avg_sq == 0).to(exp_avg_sq.dtype) * 1e-30
-                denom = safe.sqrt() + group["eps"]
-                step_size = group["lr"] * math.sqrt(bc2) / bc1
-                new_params[pidx] = p - step_size * exp_avg / denom
+                denom = safe.sqrt() / math.sqrt(bc2) + group["eps"]
+                step_size = group["lr"] / bc1
+                new_params[pidx] = p - step_size * (exp_avg / denom)
         return new_params

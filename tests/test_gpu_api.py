@@ -121,6 +121,16 @@ def test_sampling_is_reproducible_under_manual_seed():
     torch.manual_seed(7); PHILOX.seed = None; PHILOX.step = 0
     b = [Sampler.sample(probs).clone() for _ in range(2)]
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and not torch.equal(a[0], a[1])
+    # a later torch.manual_seed alone (what sacred does at the start of every run) reseeds graph sampling too
+    torch.manual_seed(7)
+    c = [Sampler.sample(probs).clone() for _ in range(2)]
+    assert torch.equal(a[0], c[0]) and torch.equal(a[1], c[1])
+    torch.manual_seed(8)
+    assert not torch.equal(Sampler.sample(probs), a[0])
+    PHILOX.manual_seed(5)                                                   # an explicit seed is not overridden by torch's
+    d = Sampler.sample(probs).clone()
+    torch.manual_seed(7); PHILOX.step = 0
+    assert torch.equal(Sampler.sample(probs), d)
 
 
 # ------------------------------------------------------------------ graph utils (test_graph.py, test_gradients.py)
@@ -419,3 +429,33 @@ def test_empirical_mean_loss_fused_forward_only_matches_the_sample_by_sample_loo
         assert abs(a.loss - b.loss) < 2e-5 * max(1.0, abs(b.loss)), (a, b)
         assert abs(a.acc - b.acc) < 1e-6, (a, b)
     assert gcn.training is False
+
+
+def test_writes_through_probs_data_reach_the_device_matrix():
+    """`.data` writes do not bump the Parameter's version counter (the reference reads `probs` afresh on every forward, so the
+    idiom works there): a hand-out of `probs` is treated as a possible write, `project_parameters()` clamps whichever copy
+    is the newer one, and `invalidate()` covers references obtained earlier."""
+    g = load_golden("n64_dropout")
+    data, gcn, inner, model, outer = _setup(g, lr=0.1, lr_decay=None)
+    n = model._n
+    outer.train_step(inner.model_forward)                                  # device matrix resident, probs stale
+    model.probs.data.fill_(0.3)
+    full = model.theta_full()
+    assert torch.all(full[:, :n] == 0.3)
+    s = model.statistics()
+    assert abs(s["mean_prob"] - 0.3) < 1e-6 and abs(s["expected_num_edges"] - 0.3 * n * n) < 1e-2
+    outer.train_step(inner.model_forward)                                  # runs on the new values, and is not overwritten afterwards
+    after = model.probs.detach().clone()
+    assert 0.2 < after.mean().item() < 0.4 and not torch.all(after == 0.3)
+    # project_parameters right after a fused step (device copy newer than probs) clamps the device copy, not stale values
+    model.probs.data.fill_(1.7)
+    model.theta_full()
+    model.mark_full_updated()                                              # as a fused step would
+    model.project_parameters()
+    assert model.probs.max().item() == 1.0 and model.theta_full()[:, :n].max().item() == 1.0
+    # a reference obtained earlier + invalidate()
+    ref = model.probs
+    model.theta_full()
+    ref.data.fill_(0.25)
+    model.invalidate()
+    assert torch.all(model.theta_full()[:, :n] == 0.25)

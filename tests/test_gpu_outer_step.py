@@ -91,7 +91,8 @@ def test_golden_outer_step(golden, sparse):
 
 @pytest.mark.parametrize("sparse", [False, True], ids=["dense_x", "csr_x"])
 @pytest.mark.parametrize("n,f,h,c,p", [(50, 30, 16, 7, 0.0), (301, 120, 16, 7, 0.5), (700, 64, 64, 7, 0.5),
-                                       (1200, 200, 32, 10, 0.0), (2708, 1433, 16, 7, 0.5)])
+                                       (1200, 200, 32, 10, 0.0), (2708, 1433, 16, 7, 0.5), (3327, 3703, 16, 6, 0.5)],
+                         ids=["n50", "n301", "n700_h64", "n1200_h32", "cora_shape", "citeseer_shape_as_benchmarked"])
 def test_philox_outer_step_matches_oracle(n, f, h, c, p, sparse):
     """Philox mode end to end: the oracle regenerates the edge uniforms and both dropout masks on the CPU."""
     from oracle.make_golden import make_inputs
@@ -276,3 +277,50 @@ def test_multi_sample_step_is_the_mean_of_the_single_sample_gradients(n, f, h, c
     eng.run_multi(t1, 1, lr=lr, seed=seed, step=step, dropout_p=p, update=True)
     eng.run(t2, lr=lr, seed=seed, step=step, dropout_p=p, update=True)
     assert torch.equal(t1, t2)
+
+
+def test_cora_shape_knn_theta_16_samples_matches_oracle():
+    """BASELINE config 3 at its exact geometry: Cora shape (N = 2708, F = 1433, C = 7, h = 16), theta_0 from a cosine kNN graph
+    (k = 10, max-symmetrised; src/data/utils.py:165-175, transforms.py:15-37), S = 16 Bernoulli samples per outer step with
+    dropout 0.5. Oracle: the fp64 restatement run once per sample with that sample's regenerated uniforms and dropout masks;
+    expected update = clamp(theta - lr * mean_s g_s)."""
+    from sklearn.neighbors import kneighbors_graph
+    from lds_gnn_b200 import kernels as K
+    n, f, h, c, S, p = 2708, 1433, 16, 7, 16, 0.5
+    rng = np.random.default_rng(3)
+    x = (rng.random((n, f)) < 0.0127).astype(np.float32)
+    x[np.arange(n), rng.integers(0, f, n)] = 1.0
+    x /= x.sum(1, keepdims=True)
+    knn = kneighbors_graph(x, 10, metric="cosine", mode="connectivity", include_self=False).toarray().astype(np.float32)
+    adj = np.maximum(knn, knn.T)
+    full0 = 0.7 * adj + 0.3 * adj * rng.random((n, n)).astype(np.float32)             # edges in (0.7, 1.0]: the 16 graphs differ
+    full0 = np.triu(full0, 1); full0 = full0 + full0.T
+    theta_triu = full0[np.triu_indices(n)].astype(np.float32)
+    lim0, lim1 = np.sqrt(6.0 / (f + h)), np.sqrt(6.0 / (h + c))
+    w = [rng.uniform(-lim0, lim0, (h, f)).astype(np.float32), (rng.standard_normal(h) * 0.05).astype(np.float32),
+         rng.uniform(-lim1, lim1, (c, h)).astype(np.float32), (rng.standard_normal(c) * 0.05).astype(np.float32)]
+    y = rng.integers(0, c, n).astype(np.int64)
+    mask = np.zeros(n, dtype=bool); mask[rng.permutation(n)[:250]] = True
+    seed, step, lr = 0xC0FFEE, 4, 1.0
+    eng = K.OuterStep(n, dev(x), dev(y), dev(mask), hidden=h, classes=c)
+    eng.set_weights(*(dev(a) for a in w))
+    theta = K.theta_triu_to_full(dev(theta_triu))
+    sc = eng.run_multi(theta, S, lr=lr, seed=seed, step=step, dropout_p=p, update=True)
+    torch.cuda.synchronize()
+    grad, losses, accs, degs = 0.0, [], [], []
+    for s in range(S):
+        u = PH.edge_uniforms(n, seed, step, sample=s)
+        kx = PH.dropout_keep_mask(n, f, p, seed, step, PH.STREAM_DROP_X, sample=s)
+        kh = PH.dropout_keep_mask(n, h, p, seed, step, PH.STREAM_DROP_H, sample=s)
+        o = R.outer_step(theta_triu, u, x, *w, y, mask, lr=lr, p=p, keep_x=kx, keep_h=kh)
+        grad = grad + o["d_theta_triu"] / S
+        losses.append(o["loss"]); accs.append(o["acc"]); degs.append(o["deg"].sum())
+    assert len(set(degs)) > 1, "the 16 sampled graphs must differ"
+    assert abs(sc[0].item() - np.mean(losses)) < 1e-4 * max(1.0, np.mean(losses)) and abs(sc[1].item() - np.mean(accs)) < 1e-6
+    ref_new = np.clip(theta_triu.astype(np.float64) - lr * grad, 0.0, 1.0)
+    new = K.theta_full_to_triu(theta, n).cpu().numpy()
+    tol = 1e-3 * lr * np.abs(grad).max() + 2e-7
+    assert np.abs(new - ref_new).max() <= tol, (np.abs(new - ref_new).max(), tol)
+    assert np.abs(ref_new - np.clip(theta_triu, 0, 1)).max() > 50 * tol                  # the step taken dwarfs the tolerance
+    sym = theta[:, :n].cpu().numpy()
+    assert np.array_equal(sym, sym.T)

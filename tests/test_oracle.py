@@ -131,6 +131,19 @@ def test_philox_uniform_mapping_properties():
     assert not np.array_equal(keep[:, :16], PH.dropout_keep_mask(200, 16, 0.5, 5, 2, PH.STREAM_DROP_H))
 
 
+def test_blockwise_philox_generators_equal_the_elementwise_definition():
+    """edge_uniforms / dropout_uniforms draw one Philox call per 2x2 block / per 4-column group; the element-by-element
+    statement of the mapping (one call per element, the header's definition) must give the same words."""
+    for n in (1, 2, 5, 33, 130):
+        for sample in (0, 3):
+            assert np.array_equal(PH.edge_uniforms(n, 77, 5, sample=sample), PH.edge_uniforms_elementwise(n, 77, 5, sample=sample))
+    for rows, cols in ((7, 1), (5, 4), (9, 13), (64, 50)):
+        r = np.arange(rows, dtype=np.int64)[:, None]; c = np.arange(cols, dtype=np.int64)[None, :]
+        c2, c3 = PH._c23(2, PH.STREAM_DROP_X, 2)
+        w = PH.philox4x32_10(c // 4, r, c2, c3, 9, 0)
+        assert np.array_equal(PH.dropout_uniforms(rows, cols, 9, 2, PH.STREAM_DROP_X, sample=2), PH.to_uniform(np.choose((c % 4) + 0 * r, w)))
+
+
 # ------------------------------------------------------------------ live reference (build container only)
 @needs_reference
 def test_port_is_bit_identical_to_live_reference_under_shared_rng():
