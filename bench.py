@@ -143,7 +143,9 @@ class ClockSampler:
 KNN_WORKLOADS = {"cora_knn16": ("cora", 10, 16)}      # BASELINE.json config 3: kNN theta_0 (k = 10, cosine), 16 samples per outer step
 
 
-def make_workload(name, seed=0):
+def make_workload(name, seed=0, knn_on_device=None):
+    """knn_on_device: CUDA device for the kNN theta_0 of config 3 on OUR kernels (data/utils.py); None = the reference's own
+    host path (sklearn kneighbors_graph, src/data/utils.py:165-175) for the CPU arm."""
     from lds_gnn_b200.data import SHAPES, make_dataset
     knn = KNN_WORKLOADS.get(name)
     if knn is not None:
@@ -151,8 +153,13 @@ def make_workload(name, seed=0):
     n, f, c, h, _, _ = SHAPES[name]
     data = make_dataset(name, seed=seed)
     if knn is not None:                                  # theta_0 = symmetrised kNN graph of the features (data/transforms.py:15-37)
-        from lds_gnn_b200.data.knn import knn_init_adjacency
-        data.dense_adj = knn_init_adjacency(data.x, k=knn[1], metric="cosine", loop=False)
+        if knn_on_device is not None:
+            from lds_gnn_b200.data.utils import knn_init_adjacency
+            data.dense_adj = knn_init_adjacency(data.x.to(knn_on_device), k=knn[1], metric="cosine", loop=False).cpu()
+        else:
+            from oracle.theta0 import knn_connectivity
+            a = knn_connectivity(data.x.numpy(), knn[1], "cosine", False)
+            data.dense_adj = torch.as_tensor(np.maximum(a, a.T))
     rng = np.random.default_rng(seed + 1)
     lim0, lim1 = np.sqrt(6.0 / (f + h)), np.sqrt(6.0 / (h + c))          # xavier-uniform, zero bias (layers.py:38-40)
     weights = dict(w0=torch.as_tensor(rng.uniform(-lim0, lim0, (h, f)).astype(np.float32)), b0=torch.zeros(h),
@@ -192,7 +199,7 @@ def run_ours(args, rank, world, device):
     from lds_gnn_b200.trainers.outer import OuterProblemTrainer
 
     clocks = ClockSampler(torch.cuda.current_device())
-    data, weights, opt_mask, shape = make_workload(args.workload, seed=rank)
+    data, weights, opt_mask, shape = make_workload(args.workload, seed=rank, knn_on_device=device)
     n, f, h, c = shape["n"], shape["f"], shape["h"], shape["c"]
     data = data.to(device)
     opt_mask = opt_mask.to(device)
@@ -386,7 +393,7 @@ def time_bilevel_block(workload, device, tau=5, replays=40, eager_blocks=4):
     from lds_gnn_b200.trainers.graph_block import CapturedBilevelBlock
     from lds_gnn_b200.trainers.inner import InnerProblemTrainer
     from lds_gnn_b200.trainers.outer import OuterProblemTrainer
-    data, _, opt_mask, shape = make_workload(workload, seed=0)
+    data, _, opt_mask, shape = make_workload(workload, seed=0, knn_on_device=device)
     data, opt_mask = data.to(device), opt_mask.to(device)
     gcn = MetaDenseGCN(shape["f"], shape["h"], shape["c"], dropout=0.5).to(device)
     inner = InnerProblemTrainer(gcn, data, lr=0.01, weight_decay=5e-4)

@@ -268,6 +268,34 @@ int64_t lds_outer_step_state_ld(int32_t rows);           /* row stride of the tr
  * rank included) with 128-bit stores in one kernel; the caller then runs a cross-GPU barrier. 16-byte alignment. */
 int32_t lds_peer_push(const void* src, void* const* dst_bases, int32_t world, int64_t dst_offset_bytes, int64_t bytes, void* stream);
 
+/* ---- theta_0 construction on the device (one-off per run in the reference, on the host).
+ * lds_knn_graph: sklearn.neighbors.kneighbors_graph(x, k, mode="connectivity", metric, include_self=loop) as the reference
+ * calls it (src/data/utils.py:165-183, KNNGraph src/data/transforms.py:15-28): adj_out[i][j] = 1 iff j is one of the k nearest
+ * points of i. metric 0 = cosine, 1 = euclidean (= minkowski p = 2). Ties between equidistant neighbours go to the smaller
+ * column index (sklearn leaves them unspecified). symmetrize != 0 additionally applies MakeUndirected on the 0/1 matrix:
+ * max(A, A^T) (src/data/transforms.py:31-38). x fp32 [n][ld_x]; adj_out fp32 [n][ld_adj], ld_adj >= n (padding columns zeroed);
+ * workspace: lds_knn_workspace_bytes(n). k <= 64. */
+int64_t lds_knn_workspace_bytes(int32_t n);
+int32_t lds_knn_graph(const float* x, int64_t ld_x, int32_t n, int32_t f, int32_t k, int32_t metric, int32_t loop,
+                      int32_t symmetrize, float* adj_out, int64_t ld_adj, void* workspace, int64_t workspace_bytes, void* stream);
+/* In place A <- max(A, A^T): to_undirected(adj) (src/utils/graph.py:27-34) / MakeUndirected on a dense matrix. */
+int32_t lds_symmetrize_max(float* adj, int64_t ld, int32_t n, void* stream);
+/* to_dense_adj (src/utils/graph.py:80-116, single graph): adj_out (zero-filled here) [src][dst] = 1 for every edge of
+ * edge_index int64 [2][num_edges]; symmetric != 0 also sets [dst][src] (to_undirected on the edge list). *bad_count (device
+ * int32) receives the number of edges with an endpoint outside [0, n) — the reference raises an IndexError for those. */
+int32_t lds_edges_to_dense(const int64_t* edge_index, int64_t num_edges, int32_t n, int32_t symmetric,
+                           float* adj_out, int64_t ld_adj, int32_t* bad_count, void* stream);
+/* remove_edges_from_directed_graph / remove_edges_from_undirected_graph (src/data/utils.py:197-227) in two calls:
+ * lds_edge_offsets: offsets[i] (device int64 [n+1]) = number of non-zeros in rows < i (of the upper triangle incl. diagonal
+ * when triu != 0), offsets[n] = nnz — the position of an edge in Tensor.nonzero() order is offsets[row] + its rank in the row.
+ * lds_remove_edges_apply: out (zero-filled here) keeps edge e iff e is among perm[0 .. num_keep) — `perm` is the SAME
+ * torch.randperm(nnz) the reference draws, so the retained set is identical; with triu != 0 kept entries are mirrored
+ * (to_undirected(from_triu_only=True)). keep_flags: nnz bytes of scratch. out must not alias adj. */
+int32_t lds_edge_offsets(const float* adj, int64_t ld, int32_t n, int32_t triu, int64_t* offsets, void* stream);
+int32_t lds_remove_edges_apply(const float* adj, int64_t ld, int32_t n, int32_t triu, const int64_t* offsets,
+                               const int64_t* perm, int64_t nnz, int64_t num_keep,
+                               float* out, int64_t ld_out, uint8_t* keep_flags, void* stream);
+
 /* ---- measurement hook for bench.py (not part of the reference-facing surface). Between begin and end,
  * lds_outer_step records a CUDA event on its stream after every kernel launch. lds_profile_end synchronises on
  * the last event and returns the number of intervals written: ms_out[i] = device time of the launch whose id is

@@ -57,6 +57,12 @@ SIGNATURES = {
     "lds_outer_step_packed_k": (c_int64, [c_int32, c_int32]),
     "lds_outer_step_operand_hp": (c_int32, [c_int32, c_int32, c_uint32]),
     "lds_outer_step_state_ld": (c_int64, [c_int32]),
+    "lds_knn_workspace_bytes": (c_int64, [c_int32]),
+    "lds_knn_graph": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "lds_symmetrize_max": (c_int32, [c_void_p, c_int64, c_int32, c_void_p]),
+    "lds_edges_to_dense": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
+    "lds_edge_offsets": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
+    "lds_remove_edges_apply": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "lds_profile_begin": (c_int32, []),
     "lds_profile_end": (c_int32, [c_void_p, c_void_p, c_int32]),
 }

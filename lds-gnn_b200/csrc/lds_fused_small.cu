@@ -455,7 +455,9 @@ int32_t fused_small_launch(const FusedSmallArgs& fa_in, cudaStream_t stream, boo
   if ((rc = make_tmap_2d(&tbh2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, fa.ea.bt_hi_alt, fa.n, FS_HP, fa.ea.ldb, K2_BLOCK_K, FS_HP)) != LDS_OK) return rc;
   if ((rc = make_tmap_2d(&tbl2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, fa.ea.bt_lo_alt, fa.n, FS_HP, fa.ea.ldb, K2_BLOCK_K, FS_HP)) != LDS_OK) return rc;
   void* params[] = {(void*)&tbh, (void*)&tbl, (void*)&tbh2, (void*)&tbl2, (void*)&fa};
-  static const bool env_no_cluster = getenv("LDS_FUSED_NO_CLUSTER") != nullptr;      // A/B switch for measurements
+  // LDS_FUSED_NO_CLUSTER: A/B switch for measurements. Nsight Compute (2025.2) dies on a launch that is both cooperative and
+  // clustered (it reports grid (0,0,0) and exits with code 9), so under its injection library the L2 variant runs instead.
+  static const bool env_no_cluster = getenv("LDS_FUSED_NO_CLUSTER") != nullptr || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr;
   static bool cluster_broken = false;
   const bool cluster = allow_cluster && !env_no_cluster && !cluster_broken && fa.parts >= 2 && fa.parts <= 8 && max_active_clusters(fa.parts) >= fa.s.panels;
   if (cluster) {                                             // one cluster per panel: reduction over distributed shared memory

@@ -81,8 +81,9 @@ EVAL_CASES = [
 ]
 MULTI_CASES = [
     # name,           seed, n,   f,  h,  c, S,  p,   lr,  step
-    ("multi_n130_s4",   21, 130, 64, 16, 7, 4,  0.5, 0.6, 3),
-    ("multi_n300_s16",  22, 300, 40, 16, 6, 16, 0.0, 0.8, 9),
+    # (lr sized so that the largest step is a few 1e-2: the gradients of these small problems are ~1e-5)
+    ("multi_n130_s4",   21, 130, 64, 16, 7, 4,  0.5, 600.0, 3),
+    ("multi_n300_s16",  22, 300, 40, 16, 6, 16, 0.0, 8000.0, 9),
 ]
 BLOCK_CASES = [
     # name,           seed, n,   f,  h,  c, tau, blocks, outer_lr, decay, inner_lr, wd,   step0

@@ -372,21 +372,14 @@ def test_sharded_exchange_world_size_2_gloo(tmp_path):
 
 
 # ------------------------------------------------------------------------------------------------ kNN theta_0
-@pytest.mark.parametrize("metric,loop", [("cosine", False), ("cosine", True), ("minkowski", False)])
-def test_knn_graph_matches_sklearn(metric, loop):
-    """src/data/utils.py:165-175 uses sklearn's kneighbors_graph; the torch construction must give the same graph."""
-    from sklearn.neighbors import kneighbors_graph
-    from lds_gnn_b200.data.knn import knn_graph_dense, knn_init_adjacency
-    rng = np.random.default_rng(5)
-    x = rng.random((257, 31)).astype(np.float32) + 0.01
-    ref = kneighbors_graph(x, n_neighbors=10, mode="connectivity", metric=metric, include_self=loop).toarray().astype(np.float32)
-    got = knn_graph_dense(torch.as_tensor(x), 10, loop=loop, metric=metric).numpy()
-    assert np.array_equal(got, ref)
-    assert got.sum(1).min() == 10 and got.sum(1).max() == 10
-    sym = knn_init_adjacency(torch.as_tensor(x), 10, metric=metric, loop=loop).numpy()
-    assert np.array_equal(sym, np.maximum(ref, ref.T))
-    with pytest.raises(ValueError):
-        knn_graph_dense(torch.as_tensor(x), 10, metric="manhattan")
+def test_theta0_construction_has_no_cpu_fallback():
+    from lds_gnn_b200.data.utils import knn_graph_dense, remove_edges, to_dense_adj
+    with pytest.raises(RuntimeError, match="CUDA"):
+        knn_graph_dense(torch.rand(10, 4), 3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        to_dense_adj(torch.zeros((2, 3), dtype=torch.int64), num_max_nodes=4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        remove_edges(torch.eye(4), False, 0.5, seed=0)
 
 
 def test_factored_unroll_hypergradient_equals_dense_autograd(monkeypatch):

@@ -185,3 +185,28 @@ def test_restatement_matches_live_reference_fp64():
     o = R.outer_step(theta, u, x, w0, b0, w1, b1, y, mask, lr=0.7, p=0.5, keep_x=kx, keep_h=kh)
     assert np.array_equal(res[0]["sample"], o["sample"])
     assert rel_inf(o["logp"], res[0]["logp"]) < 1e-12 and rel_inf(o["d_theta_triu"], res[0]["grad_triu"]) < 1e-10
+
+
+# ------------------------------------------------------------------ theta_0 construction
+@needs_reference
+def test_theta0_restatement_matches_live_reference_functions():
+    from oracle import theta0 as T0
+    L.enable()
+    from src.data import utils as RU
+    from src.utils.graph import to_dense_adj as ref_to_dense
+    rng = np.random.default_rng(0)
+    n = 60
+    a = (rng.random((n, n)) < 0.1).astype(np.float32) * rng.random((n, n)).astype(np.float32)
+    sym = np.maximum(a, a.T)
+    np.fill_diagonal(sym, (rng.random(n) < 0.3) * 0.5)
+    for pct in (0.0, 0.25, 0.9, 1.0):
+        for seed in (0, 7):
+            ref = RU.remove_edges_from_undirected_graph(torch.as_tensor(sym), pct, seed=seed)
+            assert torch.equal(T0.remove_edges_from_undirected_graph(sym, pct, seed=seed), ref)
+            refd = RU.remove_edges_from_directed_graph(torch.as_tensor(a), pct, seed=seed)
+            assert torch.equal(T0.remove_edges_from_directed_graph(a, pct, seed=seed), refd)
+    x = rng.random((n, 9)).astype(np.float32)
+    for metric, loop in (("cosine", True), ("cosine", False), ("minkowski", False)):
+        assert np.array_equal(T0.knn_connectivity(x, 5, metric, loop), RU.knn_graph_dense(torch.as_tensor(x), 5, loop=loop, metric=metric).numpy())
+    ei = torch.as_tensor(np.stack([rng.integers(0, n, 200), rng.integers(0, n, 200)]))
+    assert np.array_equal(T0.to_dense_adj(ei.numpy(), n), ref_to_dense(ei, num_max_nodes=n).numpy())
