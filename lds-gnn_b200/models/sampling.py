@@ -41,6 +41,7 @@ class PhiloxState:
         self.capture_base = None         # int64 device tensor [1] while capturing, else None
         self.capture_draws = 0
         self._derived_from = None        # torch.initial_seed() the current seed was derived from (None: set explicitly)
+        self._torch_reseeded = False     # torch.manual_seed ran since the seed was derived (see _watch_torch_seed below)
 
     def manual_seed(self, seed: int):
         self.seed = int(seed) & ((1 << 64) - 1)
@@ -52,10 +53,11 @@ class PhiloxState:
         that way) the next draw re-derives the seed and restarts the step counter, so a second run in the same process is
         reproducible too. A seed set with `manual_seed` (or assigned) stays."""
         if self.seed is not None and self._derived_from is not None and self.capture_base is None \
-                and torch.initial_seed() != self._derived_from:
+                and (self._torch_reseeded or torch.initial_seed() != self._derived_from):
             self.seed = None
         if self.seed is None:
             self._derived_from = torch.initial_seed()
+            self._torch_reseeded = False
             self.seed = int(torch.randint(0, 2 ** 62, (1,)).item())
             self.step = 0
 
@@ -80,6 +82,27 @@ class PhiloxState:
 
 
 PHILOX = PhiloxState()
+
+
+def _watch_torch_seed():
+    """`torch.manual_seed(s)` with the SAME s as before leaves `torch.initial_seed()` unchanged, so a second sacred run with the
+    same seed in one process could not be told from a continuation. The global seeding entry points are wrapped once to leave
+    a note for PHILOX (nothing else changes: the wrappers call straight through)."""
+    if getattr(torch.manual_seed, "_lds_watched", False):
+        return
+    original = torch.manual_seed
+
+    def manual_seed(seed):
+        PHILOX._torch_reseeded = True
+        return original(seed)
+    manual_seed._lds_watched = True
+    manual_seed.__doc__ = original.__doc__
+    torch.manual_seed = manual_seed
+    if getattr(torch.random, "manual_seed", None) is original:
+        torch.random.manual_seed = manual_seed
+
+
+_watch_torch_seed()
 
 
 class SampleHandle:

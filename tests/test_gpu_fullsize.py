@@ -196,6 +196,13 @@ def test_full_size_unrolled_block_factored_route_matches_dense_autograd(big):
             for p, v in zip((gcn.layer_in.fc.weight, gcn.layer_in.fc.bias, gcn.layer_out.fc.weight, gcn.layer_out.fc.bias), w):
                 p.copy_(v)
         inner = InnerProblemTrainer(gcn, data, lr=0.01, weight_decay=5e-4)
+        # Adam's update lr m / (sqrt(v_hat) + eps) is sign-like where |g| ~ eps, and its derivative (which the hypergradient
+        # flows through) is a difference of terms ~ 1 / |g|: with the default eps = 1e-8 and weight gradients of ~1e-6 at this
+        # size, two equally valid fp32 evaluations of the same unroll differ by percents. A larger eps keeps the comparison of
+        # the two ROUTES well conditioned (what is tested here is the factored machinery, not Adam's conditioning).
+        for group in inner.optimizer.param_groups:
+            group["eps"] = 1e-4
+        inner.optimizer._vectors = None
         model = BernoulliGraphModel(theta0).to(dev)
         outer = OuterProblemTrainer(optimizer=torch.optim.SGD(model.parameters(), lr=2.0e4), data=data,   # lr: gradients are ~1e-7 at degree ~10 000
                                      opt_mask=d["mask"], model=model,
