@@ -43,6 +43,7 @@ extern "C" {
 #define LDS_K2_FORCE_STREAMK 4u  /* split panels across CTAs (stream-K) even when every panel could own a CTA   */
 #define LDS_K2_NO_FUSE       8u  /* lds_outer_step: never take the fused small-graph kernel (one launch per stage)   */
 #define LDS_K2_DUMP_ADJ     16u  /* lds_outer_step: the fused small-graph kernel also writes A_tilde to the workspace */
+#define LDS_K2_BF16_ADJ     64u  /* lds_outer_step: keep A_tilde as bf16 in HBM (the pre-packed launch plan; n <= 8192) instead of bits */
 #define LDS_K2_FORWARD_ONLY 32u  /* lds_outer_step: sample + GCN forward + loss/accuracy (+ out_logp) only: no backward,
                                     no update — the evaluation pass of empirical_mean_loss (src/utils/evaluation.py:51-84)  */
 /* K3 flags */
@@ -100,6 +101,25 @@ int32_t lds_k1_sample_normalize(const float* theta_full, int64_t ld_theta, int32
 int32_t lds_k1_sample_normalize_dstep(const float* theta_full, int64_t ld_theta, int32_t n, int32_t row0, int32_t rows,
                                       uint64_t seed, const uint64_t* step_base, uint64_t step_offset, uint32_t sample,
                                       void* a_out, int64_t ld_a, float* deg_out, float* rsqrt_out, void* stream);
+
+/* ---- K1 on the bit-packed A_tilde (same reference rows and the same draws as lds_k1_sample_normalize): every Philox block and
+ * every theta element of the shard's diagonal block is touched once per UNORDERED 64 x 64 tile pair — tile (I, J) is sampled
+ * once and stored with its transpose — and A_tilde leaves as bits: 2 N^2 + N^2 / 8 bytes instead of 6 N^2 (unsharded).
+ * Layout of bits_out (lds_packed_adj_bytes(n, rows) bytes, 16-byte aligned, ZERO-FILLED before its first use):
+ *   unit (sp, kb) = local rows [256 sp, 256 sp + 256) x columns [64 kb, 64 kb + 64): 2 KB = [256 rows][2 x uint32],
+ *   word 0 = the 32 even columns of the block (bit q <-> column 64 kb + 2 q), word 1 = the odd columns; units stored [sp][kb].
+ * count_scratch: int32 [rows + 1], zero on entry, zero again on return. row0 must be a multiple of 64. */
+int64_t lds_packed_adj_bytes(int32_t n, int32_t rows);
+int32_t lds_k1_sample_packed(const float* theta_full, int64_t ld_theta, int32_t n, int32_t row0, int32_t rows,
+                             uint64_t seed, uint64_t step, uint32_t sample, const float* u_explicit, int64_t ld_u,
+                             void* bits_out, int32_t* count_scratch, float* deg_out, float* rsqrt_out, void* stream);
+/* K2 on the packed A_tilde: z_out = scale_out * (A_tilde[rows][n] @ (scale_in * p[n][width])). The bits are expanded to the
+ * bf16 {0,1} tiles tcgen05.mma reads inside the kernel, so the product is the one lds_k2_propagate computes while A_tilde
+ * costs N^2 / 8 bytes per pass instead of 2 N^2 (tensor-bound at width 64, not HBM-bound). */
+int64_t lds_k2_packed_workspace_bytes(int32_t n, int32_t rows, int32_t width);
+int32_t lds_k2_propagate_packed(const void* bits, int32_t n, int32_t rows, const float* p, int64_t ld_p, int32_t width,
+                                const float* scale_in, const float* scale_out, float* z_out, int64_t ld_z,
+                                void* workspace, int64_t workspace_bytes, uint32_t flags, void* stream);
 
 /* ---- K2 (a8's torch.mm(dense_adj, .), src/models/layers.py:44, and its transposes in backward):
  *   z_out[rows][width] = scale_out * ( A[rows][n] @ (scale_in * p[n][width]) )
@@ -250,9 +270,12 @@ typedef struct lds_outer_step_args {
 int64_t lds_outer_step_workspace_bytes(int32_t n, int32_t f, int32_t h, int32_t c);
 int64_t lds_outer_step_shard_workspace_bytes(int32_t n, int32_t rows, int32_t f, int32_t h, int32_t c);
 int32_t lds_outer_step(const lds_outer_step_args* args, void* stream);
+/* Launch plan lds_outer_step takes for these arguments: bit 0 = fused small-graph kernel eligible, bit 1 = bit-packed A_tilde
+ * (buffer 16, layout above) instead of the bf16 copy (buffer 0). -1: invalid arguments. Host only. */
+int32_t lds_outer_step_plan(const lds_outer_step_args* args);
 /* Device pointers into a workspace laid out by lds_outer_step (for tests / the composable path / the sharded exchange):
  * which: 0 A_tilde(bf16) 1 deg 2 rsqrt 3 P1 4 Z1 5 P2 6 Z2 7 dZ2 8 dP2 9 dZ1 10 dP1 11 fa 12 fb 13 cvec 14 operand rows
- * 15 packed factor rows (bf16 [n][lds_outer_step_packed_k], this rank's rows at row0).
+ * 15 packed factor rows (bf16 [n][lds_outer_step_packed_k], this rank's rows at row0). 16 bit-packed A_tilde (lds_k1_sample_packed).
  * The row-local state 3..10 is stored TRANSPOSED, [width][lds_outer_step_state_ld(rows)] fp32 (coalesced for the
  * thread-per-row epilogues); 11/12 are written only when the CUDA-core update runs (Adam or LDS_K3_SIMT).
  * `rows` = n for the unsharded layout. */

@@ -11,7 +11,7 @@ from . import _build
 
 LDS_OK = 0
 K1_EXPLICIT_U = 1
-K2_SIMT, K2_SINGLE_BF16, K2_FORCE_STREAMK, K2_NO_FUSE, K2_DUMP_ADJ, K2_FORWARD_ONLY = 1, 2, 4, 8, 16, 32
+K2_SIMT, K2_SINGLE_BF16, K2_FORCE_STREAMK, K2_NO_FUSE, K2_DUMP_ADJ, K2_FORWARD_ONLY, K2_BF16_ADJ = 1, 2, 4, 8, 16, 32, 64
 K3_DENSE_GRAD, K3_ACCUMULATE, K3_SIMT = 1, 2, 4
 OPT_SGD, OPT_ADAM = 0, 1
 STREAM_EDGES, STREAM_DROP_X, STREAM_DROP_H = 0, 1, 2
@@ -38,6 +38,13 @@ SIGNATURES = {
     "lds_row_linear": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "lds_gram_tn_workspace_bytes": (c_int64, [c_int32, c_int32]),
     "lds_gram_tn": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "lds_packed_adj_bytes": (c_int64, [c_int32, c_int32]),
+    "lds_k1_sample_packed": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_uint64, c_uint64, c_uint32, c_void_p, c_int64,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lds_k2_packed_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32]),
+    "lds_k2_propagate_packed": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int64,
+                                          c_void_p, c_int64, c_uint32, c_void_p]),
+    "lds_outer_step_plan": (c_int32, [c_void_p]),
     "lds_k2_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32]),
     "lds_k2_propagate": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_void_p,
                                    c_void_p, c_int64, c_void_p, c_int64, c_uint32, c_void_p]),

@@ -18,6 +18,7 @@
 #include <string.h>
 #include "lds_epilogue.cuh"
 #include "lds_fused_small.cuh"
+#include "lds_k2_packed.cuh"
 
 namespace lds {
 
@@ -26,13 +27,18 @@ constexpr int EPI_THREADS = 1024;   // 32 warps, one row each: the epilogues are
 constexpr int FEAT_THREADS = 256;   // dense feature GEMM: 8 warps x 4 rows
 constexpr int EPI_MAXW = 128;       // widest operand
 
-enum { B_A = 0, B_DEG, B_RS, B_P1, B_Z1, B_P2, B_Z2, B_DZ2, B_DP2, B_DZ1, B_DP1, B_FA, B_FB, B_C, B_BTHI, B_BTLO, B_BT2HI, B_BT2LO, B_PARTIAL, B_LOSSP, B_CORRP, B_F, B_W0S, B_CNT, B_OPND, B_DEGP, B_GBAR, B_END };
+enum { B_A = 0, B_DEG, B_RS, B_P1, B_Z1, B_P2, B_Z2, B_DZ2, B_DP2, B_DZ1, B_DP1, B_FA, B_FB, B_C, B_BTHI, B_BTLO, B_BT2HI, B_BT2LO, B_PARTIAL, B_LOSSP, B_CORRP, B_F, B_W0S, B_CNT, B_OPND, B_DEGP, B_GBAR, B_BITS, B_ROWCNT, B_END };
+// The bf16 copy of A_tilde (2 N^2 bytes: the pre-packed launch plan, kept for the stream-K / A-B flags and the tests that
+// compare the two plans) is only provisioned up to this many nodes; larger problems run on the bit-packed plan alone.
+constexpr int kBf16AdjMaxN = 8192;
 struct OuterLayout {
   int n, rows, f, h, c, hp1, hp2, hpmax, nblk, panels;
   int64_t lda, ldb, ldf, ldr;
   int kf;
   K2Sched s1, s2, sf;       // sf: panel-aligned schedule of the fused small-graph kernel
+  K2PSched p1, p2;          // schedules of the packed propagation (lds_k2_packed.cu)
   bool fused; int kb_real;
+  bool has_bf16_adj;
   int64_t off[B_END];
   int64_t total;
 };
@@ -49,7 +55,11 @@ static bool make_layout(int n, int rows, int f, int h, int c, OuterLayout& L, bo
   L.nblk = (int)ceil_div(rows, EPI_ROWS);
   L.panels = (int)ceil_div(rows, K2_BLOCK_M);
   int64_t bytes[B_END];
-  bytes[B_A] = (int64_t)rows * L.lda * 2;
+  L.has_bf16_adj = n <= kBf16AdjMaxN;
+  bytes[B_A] = L.has_bf16_adj ? (int64_t)rows * L.lda * 2 : 0;
+  bytes[B_BITS] = pk_bytes(n, rows);                          // bit-packed A_tilde (lds_packed.cuh)
+  bytes[B_ROWCNT] = (int64_t)(rows + 1) * 4;                        // integer row sums of the packed sampling pass (zero between calls)
+  L.p1 = k2p_make_schedule(n, rows, L.hp1); L.p2 = k2p_make_schedule(n, rows, L.hp2);
   bytes[B_DEG] = bytes[B_RS] = bytes[B_C] = (int64_t)rows * 4;
   bytes[B_P1] = bytes[B_Z1] = bytes[B_DZ1] = bytes[B_DP1] = L.ldr * h * 4;
   bytes[B_P2] = bytes[B_Z2] = bytes[B_DZ2] = bytes[B_DP2] = L.ldr * c * 4;
@@ -59,6 +69,8 @@ static bool make_layout(int n, int rows, int f, int h, int c, OuterLayout& L, bo
   // partial tiles are sized for the stream-K schedule whichever schedule runs (workspace size must not depend on flags)
   const int64_t p1 = k2_partial_bytes(k2_make_schedule(n, rows, L.hp1, true)), p2 = k2_partial_bytes(k2_make_schedule(n, rows, L.hp2, true));
   bytes[B_PARTIAL] = p1 > p2 ? p1 : p2;
+  if (k2p_partial_bytes(L.p1) > bytes[B_PARTIAL]) bytes[B_PARTIAL] = k2p_partial_bytes(L.p1);
+  if (k2p_partial_bytes(L.p2) > bytes[B_PARTIAL]) bytes[B_PARTIAL] = k2p_partial_bytes(L.p2);
   L.fused = (rows == n) && fused_small_schedule(n, L.hp1, L.hp2, L.sf, L.kb_real);
   if (L.fused && k2_partial_bytes(L.sf) > bytes[B_PARTIAL]) bytes[B_PARTIAL] = k2_partial_bytes(L.sf);
   bytes[B_LOSSP] = bytes[B_CORRP] = (int64_t)ceil_div(rows, K2_BLOCK_M) * 4;
@@ -310,13 +322,27 @@ extern "C" int64_t lds_outer_step_state_ld(int32_t rows) { return round_up(rows,
 
 extern "C" void* lds_outer_step_shard_buffer(void* workspace, int32_t n, int32_t rows, int32_t f, int32_t h, int32_t c, int32_t which) {
   OuterLayout L;
-  if (!workspace || !make_layout(n, rows, f, h, c, L) || which < 0 || which > 15) return nullptr;
-  const int b = (which == 14) ? B_OPND : (which == 15) ? B_F : which;
+  if (!workspace || !make_layout(n, rows, f, h, c, L) || which < 0 || which > 16) return nullptr;
+  const int b = (which == 14) ? B_OPND : (which == 15) ? B_F : (which == 16) ? B_BITS : which;
   return reinterpret_cast<uint8_t*>(workspace) + L.off[b];
 }
 
 extern "C" void* lds_outer_step_buffer(void* workspace, int32_t n, int32_t f, int32_t h, int32_t c, int32_t which) {
   return lds_outer_step_shard_buffer(workspace, n, n, f, h, c, which);
+}
+
+// Which launch plan lds_outer_step takes for these arguments: bit 0 = the fused small-graph kernel is eligible (the device may
+// still refuse the cooperative launch), bit 1 = bit-packed A_tilde (else the bf16 plan).
+extern "C" int32_t lds_outer_step_plan(const lds_outer_step_args* args) {
+  if (!args || args->struct_bytes != sizeof(lds_outer_step_args)) return -1;
+  const lds_outer_step_args& A = *args;
+  const bool sharded = A.rows > 0 && A.rows < A.n;
+  OuterLayout L;
+  if (!make_layout(A.n, sharded ? A.rows : A.n, A.f, A.h, A.c, L)) return -1;
+  int plan = 0;
+  if (!sharded && A.x_crow != nullptr && !(A.k2_flags & (LDS_K2_NO_FUSE | LDS_K2_FORCE_STREAMK | LDS_K2_SIMT)) && L.fused) plan |= 1;
+  if (!(A.k2_flags & (LDS_K2_FORCE_STREAMK | LDS_K2_SIMT | LDS_K2_BF16_ADJ)) && ((sharded ? A.row0 : 0) % 64 == 0)) plan |= 2;
+  return plan;
 }
 
 extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_) {
@@ -442,6 +468,13 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
     else if (rc != LDS_ERR_UNSUPPORTED) return rc;
   }
 
+  // Launch plan of everything that is not the fused small-graph kernel: the bit-packed A_tilde (tile-symmetric sampling,
+  // on-chip expansion in the propagation) unless a flag asks for the bf16 plan (stream-K / validation switches).
+  const bool packed = !(A.k2_flags & (LDS_K2_FORCE_STREAMK | LDS_K2_SIMT | LDS_K2_BF16_ADJ)) && (row0 % 64 == 0);
+  if (!fused_done && !packed && !L.has_bf16_adj) {
+    set_error("lds_outer_step: the bf16 A_tilde plan is provisioned up to n = %d (n = %d runs the bit-packed plan; row0 must be a multiple of 64)", kBf16AdjMaxN, A.n);
+    return LDS_ERR_UNSUPPORTED;
+  }
   if (!fused_done && (phases & LDS_PHASE_SAMPLE)) {
     {   // stage the layer_in weight (tiny; independent of K1) and re-arm the stream-K counters
       const int64_t ldp = round_up(A.f, 4);
@@ -450,8 +483,12 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
       LDS_CHECK_LAUNCH("stage_w0_kernel");
       profile_mark(stream, 8);
     }
-    rc = lds_k1_sample_normalize(A.theta_full, A.ld_theta, A.n, row0, rows, A.seed, A.step, smp, A.u_explicit, A.ld_u,
-                                 buf(B_A), L.lda, nullptr, 0, fbuf(B_DEG), fbuf(B_RS), A.u_explicit ? LDS_K1_EXPLICIT_U : 0u, stream_);
+    if (packed)
+      rc = k1p_launch(A.theta_full, A.ld_theta, A.n, row0, rows, A.seed, A.step, smp, A.u_explicit, A.ld_u,
+                      reinterpret_cast<uint32_t*>(buf(B_BITS)), reinterpret_cast<int*>(buf(B_ROWCNT)), fbuf(B_DEG), fbuf(B_RS), stream);
+    else
+      rc = lds_k1_sample_normalize(A.theta_full, A.ld_theta, A.n, row0, rows, A.seed, A.step, smp, A.u_explicit, A.ld_u,
+                                   buf(B_A), L.lda, nullptr, 0, fbuf(B_DEG), fbuf(B_RS), A.u_explicit ? LDS_K1_EXPLICIT_U : 0u, stream_);
     if (rc != LDS_OK) return rc;
     profile_mark(stream, 0);
     const dim3 egrid((unsigned)L.nblk);
@@ -489,7 +526,7 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   if ((A.k2_flags & LDS_K2_SIMT) && (phases & (LDS_PHASE_LAYER1 | LDS_PHASE_LAYER2 | LDS_PHASE_BWD2 | LDS_PHASE_BWD1))) {
     set_error("lds_outer_step: LDS_K2_SIMT is only available through lds_k2_propagate"); return LDS_ERR_ARG;
   }
-  auto propagate = [&](uint32_t phase, const K2Sched& s, int width, int epi, int mark, int hp_next, int cur) -> int32_t {
+  auto propagate = [&](uint32_t phase, const K2Sched& s, const K2PSched& sp, int width, int epi, int mark, int hp_next, int cur) -> int32_t {
     if (fused_done || !(phases & phase)) return LDS_OK;
     const __nv_bfloat16* in_hi = pp_hi[cur];
     const __nv_bfloat16* in_lo = pp_lo[cur];
@@ -504,12 +541,14 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
     }
     E.bt_hi = out_hi(hp_next, cur ^ 1); E.bt_lo = out_lo(hp_next, cur ^ 1); E.ldb = out_ld;
     E.timeline = A.k2_timeline ? A.k2_timeline + (size_t)(mark - 3) * 512 * 8 : nullptr;
-    const int32_t r = k2_launch_mma(buf(B_A), L.lda, A.n, rows, in_hi, in_lo, L.ldb, fbuf(B_PARTIAL), counters, s, use_lo, epi, E, stream, rank_rows);
+    const int32_t r = packed
+        ? k2p_launch(buf(B_BITS), A.n, rows, in_hi, in_lo, L.ldb, fbuf(B_PARTIAL), sp, use_lo, epi, E, false, stream, rank_rows)
+        : k2_launch_mma(buf(B_A), L.lda, A.n, rows, in_hi, in_lo, L.ldb, fbuf(B_PARTIAL), counters, s, use_lo, epi, E, stream, rank_rows);
     profile_mark(stream, mark);
     return r;
   };
-  if ((rc = propagate(LDS_PHASE_LAYER1, L.s1, A.h, K2_EPI_LAYER1, 3, L.hp2, 0)) != LDS_OK) return rc;   // Z1, H1, P2, operand (r P2)^T
-  if ((rc = propagate(LDS_PHASE_LAYER2, L.s2, A.c, K2_EPI_LAYER2, 4, L.hp2, 1)) != LDS_OK) return rc;   // Z2, log-softmax, loss, dZ2, operand (r dZ2)^T
+  if ((rc = propagate(LDS_PHASE_LAYER1, L.s1, L.p1, A.h, K2_EPI_LAYER1, 3, L.hp2, 0)) != LDS_OK) return rc;   // Z1, H1, P2, operand (r P2)^T
+  if ((rc = propagate(LDS_PHASE_LAYER2, L.s2, L.p2, A.c, K2_EPI_LAYER2, 4, L.hp2, 1)) != LDS_OK) return rc;   // Z2, log-softmax, loss, dZ2, operand (r dZ2)^T
   const bool fwd_only = (A.k2_flags & LDS_K2_FORWARD_ONLY) != 0;
   if (fwd_only && sharded) { set_error("lds_outer_step: LDS_K2_FORWARD_ONLY is not available for row-block shards"); return LDS_ERR_UNSUPPORTED; }
   if (fwd_only) {
@@ -519,8 +558,8 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
     }
     return LDS_OK;
   }
-  if ((rc = propagate(LDS_PHASE_BWD2, L.s2, A.c, K2_EPI_BWD2, 5, L.hp1, 0)) != LDS_OK) return rc;       // dP2, dZ1, operand (r dZ1)^T; loss/acc finalised
-  if ((rc = propagate(LDS_PHASE_BWD1, L.s1, A.h, K2_EPI_BWD1, 6, L.hp1, 1)) != LDS_OK) return rc;       // dP1, c, factor matrices
+  if ((rc = propagate(LDS_PHASE_BWD2, L.s2, L.p2, A.c, K2_EPI_BWD2, 5, L.hp1, 0)) != LDS_OK) return rc;       // dP2, dZ1, operand (r dZ1)^T; loss/acc finalised
+  if ((rc = propagate(LDS_PHASE_BWD1, L.s1, L.p1, A.h, K2_EPI_BWD1, 6, L.hp1, 1)) != LDS_OK) return rc;       // dP1, c, factor matrices
 
   if ((phases & LDS_PHASE_UPDATE) && A.update && (S == 1 || (int)smp == S - 1)) {
     const float* cv = sharded ? A.c_full : fbuf(B_C);

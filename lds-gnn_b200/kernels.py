@@ -109,6 +109,43 @@ def k1_sample_normalize(theta_full, n, seed, step, sample=0, u=None, want_adj=Tr
     return adj, smp, deg, rs
 
 
+def packed_adj_bytes(n, rows=None):
+    return int(_lib.load().lds_packed_adj_bytes(int(n), int(n if rows is None else rows)))
+
+
+def k1_sample_packed(theta_full, n, seed, step, sample=0, u=None, row0=0, rows=None, bits=None):
+    """K1 on the bit-packed A_tilde (tile-symmetric: one Philox block / theta read per unordered tile pair of the shard).
+    Returns (bits uint8 [packed_adj_bytes], deg [rows], rsqrt [rows]); `unpack_adj` gives the {0,1} matrix."""
+    _lib.require_device()
+    _f32(theta_full, "theta_full")
+    rows = n - row0 if rows is None else rows
+    dev = theta_full.device
+    nbytes = packed_adj_bytes(n, rows)
+    if bits is None:
+        bits = torch.zeros(nbytes, dtype=torch.uint8, device=dev)          # zero-filled once: rows / columns beyond the matrix stay zero
+    cnt = torch.zeros(rows + 1, dtype=torch.int32, device=dev)
+    deg = torch.empty(rows, dtype=torch.float32, device=dev)
+    rs = torch.empty(rows, dtype=torch.float32, device=dev)
+    if u is not None:
+        _f32(u, "u")
+    _lib.check(_lib.load().lds_k1_sample_packed(
+        _ptr(theta_full), theta_full.stride(0), n, row0, rows, int(seed), int(step), int(sample), _ptr(u), 0 if u is None else u.stride(0),
+        _ptr(bits), _ptr(cnt), _ptr(deg), _ptr(rs), _stream()), "lds_k1_sample_packed")
+    return bits, deg, rs
+
+
+def unpack_adj(bits, n, rows=None, dtype=BF16):
+    """Bit-packed A_tilde (layout: include/lds_b200.h, lds_k1_sample_packed) -> dense [rows, ld] matrix of 0/1. Tests and
+    debugging only: plain torch ops."""
+    rows = n if rows is None else rows
+    sp, kb = (rows + 255) // 256, (n + 63) // 64
+    words = bits[:sp * kb * 2048].view(torch.int32).view(sp, kb, 256, 2)
+    q = torch.arange(32, device=bits.device, dtype=torch.int32)
+    cells = ((words.unsqueeze(-1) >> q) & 1)                               # [sp, kb, 256, 2 (even / odd), 32 (pair)]
+    cells = cells.permute(0, 2, 1, 4, 3).reshape(sp * 256, kb * 64)        # column = 64 kb + 2 pair + parity
+    return cells[:rows].to(dtype)
+
+
 # ----------------------------------------------------------------------------- K2
 _ws_cache = {}
 
@@ -141,6 +178,25 @@ def k2_propagate(adj, n, p, scale_in=None, scale_out=None, flags=0, out=None):
     _lib.check(_lib.load().lds_k2_propagate(
         _ptr(adj), adj.stride(0), n, rows, _ptr(p), p.stride(0), width, _ptr(scale_in), _ptr(scale_out),
         _ptr(z), z.stride(0), _ptr(ws), need, int(flags), _stream()), "lds_k2_propagate")
+    return z
+
+
+def k2_propagate_packed(bits, n, rows, p, scale_in=None, scale_out=None, flags=0, out=None):
+    """z = scale_out * (A_tilde @ (scale_in * p)) with A_tilde given as bits: expanded on chip, tensor-bound instead of HBM-bound."""
+    _lib.require_device()
+    _f32(p, "p")
+    width = p.shape[1]
+    if p.shape[0] != n:
+        raise ValueError(f"p has {p.shape[0]} rows, expected {n}")
+    p = p if p.stride(1) == 1 else p.contiguous()
+    z = out if out is not None else torch.empty((rows, width), dtype=torch.float32, device=p.device)
+    need = int(_lib.load().lds_k2_packed_workspace_bytes(n, rows, width))
+    if need < 0:
+        raise ValueError(f"unsupported propagate shape n={n} rows={rows} width={width}")
+    ws = _workspace(need, p.device, "k2p")
+    _lib.check(_lib.load().lds_k2_propagate_packed(
+        _ptr(bits), n, rows, _ptr(p), p.stride(0), width, _ptr(scale_in), _ptr(scale_out), _ptr(z), z.stride(0), _ptr(ws), need,
+        int(flags), _stream()), "lds_k2_propagate_packed")
     return z
 
 
@@ -287,6 +343,7 @@ class OuterStep:
         self._args_ref = ctypes.byref(self.args)
         self._f32_factors = False
         self._fpack_multi = None
+        self._plan = -1                                      # launch plan of the last step (lds_outer_step_plan)
         self._init_static_args()
 
     def set_mask(self, mask):
@@ -326,6 +383,10 @@ class OuterStep:
         off = ptr - self.ws.data_ptr()
         if name == "adj":
             shape = (n, padded_ld(self.n))
+            if self._plan >= 0 and not (self._plan & 1) and (self._plan & 2):      # bit-packed plan: expand the bits (tests / debugging)
+                bptr = self.lib.lds_outer_step_shard_buffer(_ptr(self.ws), self.n, self.rows, self.f, self.h, self.c, 16)
+                boff = bptr - self.ws.data_ptr()
+                return unpack_adj(self.ws[boff:boff + packed_adj_bytes(self.n, n)], self.n, n)[:, :shape[1]].contiguous()
             return self.ws[off:off + 2 * shape[0] * shape[1]].view(BF16).view(shape)
         if name == "fpack":                                  # this rank's rows of the packed bf16 factor matrix
             kf = int(self.lib.lds_outer_step_packed_k(h, c))
@@ -437,4 +498,6 @@ class OuterStep:
             a.phases = int(phases)
         self._f32_factors = not (opt_kind == _lib.OPT_SGD and not (k3_flags & _lib.K3_SIMT))
         _lib.check(self.lib.lds_outer_step(self._args_ref, _stream()), "lds_outer_step")
+        if want_adj:
+            self._plan = int(self.lib.lds_outer_step_plan(self._args_ref))
         return self.scalars if scalars_out is None else scalars_out
