@@ -45,7 +45,10 @@ extern "C" {
 #define LDS_K2_DUMP_ADJ     16u  /* lds_outer_step: the fused small-graph kernel also writes A_tilde to the workspace */
 #define LDS_K2_BF16_ADJ     64u  /* lds_outer_step: keep A_tilde as bf16 in HBM (the pre-packed launch plan; n <= 8192) instead of bits */
 #define LDS_K2_FORWARD_ONLY 32u  /* lds_outer_step: sample + GCN forward + loss/accuracy (+ out_logp) only: no backward,
-                                    no update — the evaluation pass of empirical_mean_loss (src/utils/evaluation.py:51-84)  */
+                                    no update — the evaluation pass of empirical_mean_loss (src/utils/evaluation.py:51-84).
+                                    With num_samples = S > 1 (sample_index 0, dropout 0): S graphs in ONE call, drawn at Philox
+                                    steps step .. step + S - 1; out_logp is [S][n][c], out_scalars the mean (loss, acc). Small
+                                    graphs run all S in one launch and compute the sample-invariant X W0^T + b0 once.      */
 /* K3 flags */
 #define LDS_K3_DENSE_GRAD    1u  /* write dL/dA_tilde (dense, not symmetrised) instead of updating theta      */
 #define LDS_K3_ACCUMULATE    2u  /* with DENSE_GRAD: add into grad_out instead of overwriting                  */
@@ -318,6 +321,16 @@ int32_t lds_edge_offsets(const float* adj, int64_t ld, int32_t n, int32_t triu, 
 int32_t lds_remove_edges_apply(const float* adj, int64_t ld, int32_t n, int32_t triu, const int64_t* offsets,
                                const int64_t* perm, int64_t nnz, int64_t num_keep,
                                float* out, int64_t ld_out, uint8_t* keep_flags, void* stream);
+
+/* ---- empirical_mean_loss (src/utils/evaluation.py:51-84): from the [samples][n][c] log-probabilities of a batched
+ * evaluation (lds_outer_step with LDS_K2_FORWARD_ONLY), out4 (device) = { mean NLL on mask_a, accuracy on mask_a, mean NLL on
+ * mask_b, accuracy on mask_b } — each the mean over the samples of the per-sample masked mean (F.nll_loss / accuracy on
+ * predictions[mask], evaluation.py:76-80), arg-max ties to the smaller class like torch.argmax. Deterministic (fixed-order sums).
+ * count_a / count_b = number of ones in the masks. workspace: lds_eval_metrics_workspace_bytes(n, samples). */
+int64_t lds_eval_metrics_workspace_bytes(int32_t n, int32_t samples);
+int32_t lds_eval_metrics(const float* logp, int32_t samples, int32_t n, int32_t c, const int64_t* y,
+                         const uint8_t* mask_a, int32_t count_a, const uint8_t* mask_b, int32_t count_b,
+                         float* out4, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- measurement hook for bench.py (not part of the reference-facing surface). Between begin and end,
  * lds_outer_step records a CUDA event on its stream after every kernel launch. lds_profile_end synchronises on

@@ -64,6 +64,8 @@ SIGNATURES = {
     "lds_outer_step_packed_k": (c_int64, [c_int32, c_int32]),
     "lds_outer_step_operand_hp": (c_int32, [c_int32, c_int32, c_uint32]),
     "lds_outer_step_state_ld": (c_int64, [c_int32]),
+    "lds_eval_metrics_workspace_bytes": (c_int64, [c_int32, c_int32]),
+    "lds_eval_metrics": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
     "lds_knn_workspace_bytes": (c_int64, [c_int32]),
     "lds_knn_graph": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "lds_symmetrize_max": (c_int32, [c_void_p, c_int64, c_int32, c_void_p]),

@@ -163,7 +163,8 @@ __device__ __forceinline__ void epi_layer1(const EpiArgs& a, int i, int g, float
 // ---- layer 2: Z2 = r * sum, log_softmax, masked NLL + accuracy, dZ2, operand (r * dZ2)^T     (gcn.py:34, outer.py:65-67)
 // Returns this thread's (loss, correct) contribution (non-zero on one lane of the quad); the caller reduces over the panel.
 template <int HP>
-__device__ __forceinline__ void epi_layer2(const EpiArgs& a, int i, int g, float (&v)[HP / 4], float& loss_i, float& corr_i, bool alt = false) {
+__device__ __forceinline__ void epi_layer2(const EpiArgs& a, int i, int g, float (&v)[HP / 4], float& loss_i, float& corr_i, bool alt = false,
+                                           int64_t logp_offset = 0) {
   constexpr int Q = HP / 4;
   loss_i = 0.f; corr_i = 0.f;
   const bool live = i < a.n;
@@ -197,7 +198,7 @@ __device__ __forceinline__ void epi_layer2(const EpiArgs& a, int i, int g, float
     const int o = g * Q + k;
     if (live && o < a.c) {
       const float lp = v[k] - lse;
-      if (a.out_logp) a.out_logp[(int64_t)i * a.c + o] = lp;
+      if (a.out_logp) a.out_logp[logp_offset + (int64_t)i * a.c + o] = lp;
       if (mk && o == yi) loss_i = -lp;
       const float dz = mk ? (expf(lp) - (o == yi ? 1.f : 0.f)) * a.inv_m : 0.f;
       a.dz2[(int64_t)o * a.ldr + i] = dz;

@@ -132,12 +132,27 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
   };
   stamp(0);
 
-  // ================= P0: weight staging, panel counters, sampling into shared memory =================
-  for (int idx = cta * K2_THREADS + tid; idx < fa.f * ea.h; idx += gridDim.x * K2_THREADS) {
-    const int ff = idx / ea.h, o = idx - ff * ea.h;
-    fa.w0t[idx] = fa.w0[(int64_t)o * fa.ldw + ff];
+  int acc_m = 0; uint32_t acc_phase_m = 0;                   // accumulator ring state of the MMA issuer
+  int acc_e = 0; uint32_t acc_phase_e = 0;                   // ... and of the epilogue warps
+  uint32_t bfull_uses = 0;                                   // completed uses of the operand barrier (its phase parity)
+  // Batched evaluation (src/utils/evaluation.py:51-84): S graphs in ONE launch. The feature rows X W0^T + b0 are sample-
+  // invariant in eval mode (no dropout), so they are computed for the first graph only; theta stays in L2 across samples.
+  const int n_samples = fa.eval_samples > 1 ? fa.eval_samples : 1;
+  for (int smp = 0; smp < n_samples; ++smp) {
+  uint32_t c2s = fa.rounds.c2, c3s = fa.rounds.c3;
+  if (n_samples > 1) {                                       // Philox step of this graph: step0 + smp, sample 0
+    const unsigned long long st = fa.step0 + (unsigned long long)smp;
+    c2s = (uint32_t)(st & 0xffffffffull);
+    c3s = (c3s & 0xffffu) | (uint32_t)(((st >> 32) & 0xffffull) << 16);
   }
-  if (cta == 0) for (int k = tid; k < s.panels; k += K2_THREADS) fa.counters[k] = 0;
+  // ================= P0: weight staging, panel counters, sampling into shared memory =================
+  if (smp == 0) {
+    for (int idx = cta * K2_THREADS + tid; idx < fa.f * ea.h; idx += gridDim.x * K2_THREADS) {
+      const int ff = idx / ea.h, o = idx - ff * ea.h;
+      fa.w0t[idx] = fa.w0[(int64_t)o * fa.ldw + ff];
+    }
+    if (cta == 0) for (int k = tid; k < s.panels; k += K2_THREADS) fa.counters[k] = 0;
+  }
   if (warp < 16) {
     const int rp = tid >> 3, c8 = tid & 7;                   // item = (row pair, 8-column chunk) of a 128 x 64 tile
     const int gi0 = my_p * K2_BLOCK_M + 2 * rp, gi1 = gi0 + 1;
@@ -184,7 +199,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
           const int q = (gj0 >> 1) + b;
           const bool upper = pblk < q;
           uint32_t w[4];
-          philox4x32_10_rk((uint32_t)(upper ? q : pblk), (uint32_t)(upper ? pblk : q), fa.rounds, w);
+          philox4x32_10_rk((uint32_t)(upper ? q : pblk), (uint32_t)(upper ? pblk : q), fa.rounds, c2s, c3s, w);
           // word = 2*(a%2) + (b%2) of the canonical pair (a, b) = (min, max); the diagonal block uses w[1] for both off-diagonal cells
           const uint32_t w01 = (pblk <= q) ? w[1] : w[2], w10 = upper ? w[2] : w[1];
           b0[2 * b]     = ((w[0] >> 8) < __float2uint_ru(th0[2 * b] * 16777216.f)) ? 1u : 0u;
@@ -249,9 +264,9 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
       for (int sh = 8; sh > 0; sh >>= 1) d += __shfl_xor_sync(0xffffffffu, d, sh);      // integer-valued: exact in any order
       const float ri = 1.0f / sqrtf(d);
       if (live && lane16 == 0) { fa.deg[i] = d; fa.rs[i] = ri; }
-      const int beg = fa.crow[il], end = live ? fa.crow[il + 1] : beg;
-      const int trips = (max(__shfl_sync(0xffffffffu, end - beg, 0), __shfl_sync(0xffffffffu, end - beg, 16)) + 15) >> 4;
       float acc = 0.f;
+      const int beg = fa.crow[il], end = (live && smp == 0) ? fa.crow[il + 1] : beg;     // later graphs of a batched evaluation reuse P1
+      const int trips = (max(__shfl_sync(0xffffffffu, end - beg, 0), __shfl_sync(0xffffffffu, end - beg, 16)) + 15) >> 4;
       for (int tr = 0; tr < trips; ++tr) {                     // both halves run the same number of trips (shuffles are warp-wide)
         const int base = beg + 16 * tr;
         const int idx = base + lane16;
@@ -274,8 +289,8 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
         }
       }
       if (live && lane16 < ea.h) {
-        const float pv = acc + fa.b0[lane16];
-        ea.p1[(int64_t)lane16 * ea.ldr + i] = pv;
+        const float pv = (smp == 0) ? acc + fa.b0[lane16] : ea.p1[(int64_t)lane16 * ea.ldr + i];
+        if (smp == 0) ea.p1[(int64_t)lane16 * ea.ldr + i] = pv;
         __nv_bfloat16 bh, bl;
         split_bf16(ri * pv, bh, bl);
         ea.bt_hi[(int64_t)lane16 * ea.ldb + i] = bh;
@@ -288,9 +303,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
   stamp(4);
 
   // ================= P2: the four propagations from the resident tiles =================
-  int acc_m = 0; uint32_t acc_phase_m = 0;                   // accumulator ring state of the MMA issuer
-  int acc_e = 0; uint32_t acc_phase_e = 0;                   // ... and of the epilogue warps
-  for (int ph = 0; ph < fa.num_phases; ++ph) {
+  for (int ph = 0; ph < fa.num_phases; ++ph, ++bfull_uses) {
     if (warp == 0) {
       if (lane == 0) {                                       // the operand k-blocks of this CTA's range (all fit: no ring)
         asm volatile("fence.proxy.async;" ::: "memory");     // the operand was written with generic stores before the grid barrier
@@ -309,7 +322,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
         // one MMA of width 32 against the stacked operand [hi(16 rows); lo(16 rows)] (contiguous in smem): the hi and lo
         // products land in columns 0-15 / 16-31 of the accumulator and are added by the drain
         const uint32_t idesc = fa.use_lo ? umma_idesc_bf16(K2_BLOCK_M, 2 * FS_HP) : umma_idesc_bf16(K2_BLOCK_M, FS_HP);
-        mbar_wait(bfull, (uint32_t)(ph & 1));
+        mbar_wait(bfull, bfull_uses & 1u);
         mbar_wait(&tempty_bar[acc_m], acc_phase_m ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc_m * 2 * FS_HP);
@@ -368,15 +381,15 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
         else if (ph == 3) epi_bwd1<FS_HP>(ea, i, g, v);
         else {
           float li, ci;
-          epi_layer2<FS_HP>(ea, i, g, v, li, ci, alt);
+          epi_layer2<FS_HP>(ea, i, g, v, li, ci, alt, (int64_t)smp * n * ea.c);
           li = warp_sum(li); ci = warp_sum(ci);
           if (lane == 0) { sh_epi.red[warp - 2][0] = li; sh_epi.red[warp - 2][1] = ci; }
           named_bar_sync(2, 512);
           if (etid == 0) {
             float l = 0.f, c = 0.f;
             for (int w = 0; w < 16; ++w) { l += sh_epi.red[w][0]; c += sh_epi.red[w][1]; }   // fixed order
-            ea.loss_part[my_p] = l;
-            ea.corr_part[my_p] = c;
+            ea.loss_part[my_p] = (smp ? ea.loss_part[my_p] : 0.f) + l;      // batched evaluation: sum over the graphs (this CTA is
+            ea.corr_part[my_p] = (smp ? ea.corr_part[my_p] : 0.f) + c;      // the only writer of its panel's partial: fixed order)
           }
         }
       }
@@ -385,9 +398,10 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
       unsigned long long t;
       if (fa.timeline != nullptr) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); fa.timeline[(size_t)cta * 16 + 5 + 2 * ph] = t; }
     }
-    if (ph + 1 < fa.num_phases) grid_barrier(fa.gridbar, gbase, gk, gridDim.x);
+    if (ph + 1 < fa.num_phases || smp + 1 < n_samples) grid_barrier(fa.gridbar, gbase, gk, gridDim.x);
     stamp(6 + 2 * ph);
   }
+  }   // graphs of a batched evaluation
 
   if (CLUSTER) cluster_sync_all();                           // nobody exits while the cluster leader still reads its shared memory
   if (fa.num_phases == 2) {                                  // forward only: nobody runs the BWD2 prologue that finalises (loss, acc)
@@ -471,6 +485,7 @@ int32_t fused_small_launch(const FusedSmallArgs& fa_in, cudaStream_t stream, boo
     (void)cudaGetLastError();                                // e.g. the device cannot co-schedule the clusters after all:
     cluster_broken = true;                                   // use the variant without clusters from now on
   }
+  if (fa.eval_samples > 1) return LDS_ERR_UNSUPPORTED;       // batched evaluation exists in the cluster variant only: the caller loops
   LDS_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)fused_small_kernel<false>, dim3((unsigned)fa.s.grid), dim3(K2_THREADS), params, FS_SMEM, stream));
   return LDS_OK;
 }

@@ -21,6 +21,8 @@ struct FusedSmallArgs {
   int rows_per_cta;
   // propagations
   int num_phases;                              // 4: forward + backward; 2: forward only (layer 1, layer 2 + loss)
+  int eval_samples;                            // forward only: graphs evaluated in THIS launch (Philox steps step0 .. step0 + S - 1, sample 0);
+  unsigned long long step0;                    // the feature rows are computed once, log-probs go to out_logp[s][n][c] (cluster variant only)
   K2Sched s;                                   // panel-aligned: s.kblocks is the PADDED k-range (parts * per_cta), max_seg = 1
   int kb_real;                                 // ceil(n / 64): k-blocks that exist
   int parts;                                   // CTAs per panel (= cluster size of the CLUSTER variant); set by the launcher

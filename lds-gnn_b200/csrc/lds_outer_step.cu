@@ -27,7 +27,7 @@ constexpr int EPI_THREADS = 1024;   // 32 warps, one row each: the epilogues are
 constexpr int FEAT_THREADS = 256;   // dense feature GEMM: 8 warps x 4 rows
 constexpr int EPI_MAXW = 128;       // widest operand
 
-enum { B_A = 0, B_DEG, B_RS, B_P1, B_Z1, B_P2, B_Z2, B_DZ2, B_DP2, B_DZ1, B_DP1, B_FA, B_FB, B_C, B_BTHI, B_BTLO, B_BT2HI, B_BT2LO, B_PARTIAL, B_LOSSP, B_CORRP, B_F, B_W0S, B_CNT, B_OPND, B_DEGP, B_GBAR, B_BITS, B_ROWCNT, B_END };
+enum { B_A = 0, B_DEG, B_RS, B_P1, B_Z1, B_P2, B_Z2, B_DZ2, B_DP2, B_DZ1, B_DP1, B_FA, B_FB, B_C, B_BTHI, B_BTLO, B_BT2HI, B_BT2LO, B_PARTIAL, B_LOSSP, B_CORRP, B_F, B_W0S, B_CNT, B_OPND, B_DEGP, B_GBAR, B_BITS, B_ROWCNT, B_EVALTMP, B_END };
 // The bf16 copy of A_tilde (2 N^2 bytes: the pre-packed launch plan, kept for the stream-K / A-B flags and the tests that
 // compare the two plans) is only provisioned up to this many nodes; larger problems run on the bit-packed plan alone.
 constexpr int kBf16AdjMaxN = 8192;
@@ -58,6 +58,7 @@ static bool make_layout(int n, int rows, int f, int h, int c, OuterLayout& L, bo
   L.has_bf16_adj = n <= kBf16AdjMaxN;
   bytes[B_A] = L.has_bf16_adj ? (int64_t)rows * L.lda * 2 : 0;
   bytes[B_BITS] = pk_bytes(n, rows);                          // bit-packed A_tilde (lds_packed.cuh)
+  bytes[B_EVALTMP] = 16;
   bytes[B_ROWCNT] = (int64_t)(rows + 1) * 4;                        // integer row sums of the packed sampling pass (zero between calls)
   L.p1 = k2p_make_schedule(n, rows, L.hp1); L.p2 = k2p_make_schedule(n, rows, L.hp2);
   bytes[B_DEG] = bytes[B_RS] = bytes[B_C] = (int64_t)rows * 4;
@@ -291,6 +292,12 @@ feat_sparse_kernel(const int32_t* __restrict__ crow, const int32_t* __restrict__
   store_operand_tile(tile, hp, i0, ldb, bt_hi, bt_lo);
 }
 
+// batched evaluation on the multi-launch plans: out[0:2] = mean over the graphs of tmp[0:2]
+__global__ void eval_accumulate_kernel(float* out, const float* tmp, int s, int total, float tag) {
+  if (threadIdx.x < 2) out[threadIdx.x] = (s ? out[threadIdx.x] : 0.f) + tmp[threadIdx.x] / (float)total;
+  if (threadIdx.x == 0 && tag != 0.f) { __threadfence_system(); out[2] = tag; }
+}
+
 // forward-only steps: sum the per-panel partials in a fixed order (what the BWD2 launch does in a training step)
 __global__ void finalize_scalars_kernel(const __grid_constant__ EpiArgs ea) {
   if (threadIdx.x == 0) finalize_scalars(ea);
@@ -414,11 +421,14 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   dx.keep_thresh = dh.keep_thresh = (float)(1.0 - (double)A.dropout_p);
   dx.scale = dh.scale = 1.0f / dx.keep_thresh;
   dx.explicit_keep = A.keep_x; dh.explicit_keep = A.keep_h;
-  const int S = A.num_samples > 1 ? A.num_samples : 1;
+  // Batched evaluation (LDS_K2_FORWARD_ONLY with num_samples = S > 1): S graphs drawn at Philox steps step .. step + S - 1
+  // (sample 0), log-probabilities to out_logp[s][n][c], out_scalars = mean (loss, acc) over the graphs.
+  const bool eval_batch = (A.k2_flags & LDS_K2_FORWARD_ONLY) && A.num_samples > 1;
+  if (eval_batch) LDS_CHECK_ARG(!sharded && A.dropout_p == 0.f && A.sample_index == 0, "lds_outer_step: a batched evaluation is unsharded, without dropout, sample_index 0");
+  const int S = (A.num_samples > 1 && !eval_batch) ? A.num_samples : 1;
   const uint32_t smp = S > 1 ? (uint32_t)A.sample_index : (uint32_t)(A.sample_index > 0 ? A.sample_index : 0);
   if (S > 1) {
     LDS_CHECK_ARG(A.sample_index >= 0 && A.sample_index < S, "lds_outer_step: sample_index %d outside [0, %d)", A.sample_index, S);
-    LDS_CHECK_ARG(!(A.k2_flags & LDS_K2_FORWARD_ONLY), "lds_outer_step: LDS_K2_FORWARD_ONLY is a single-sample call");
     LDS_CHECK_ARG(A.fpack_multi != nullptr && (reinterpret_cast<uintptr_t>(A.fpack_multi) & 15) == 0, "lds_outer_step: num_samples > 1 needs a 16-byte aligned fpack_multi");
     if (sharded || A.opt_kind != LDS_OPT_SGD || (A.k3_flags & LDS_K3_SIMT)) { set_error("lds_outer_step: the multi-sample estimator runs unsharded with the tensor-core SGD update"); return LDS_ERR_UNSUPPORTED; }
   }
@@ -443,6 +453,7 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
     F.crow = A.x_crow; F.xcol = A.x_col; F.xval = A.x_val; F.f = A.f;
     F.w0 = A.w0; F.ldw = A.ld_w0; F.w0t = fbuf(B_W0S); F.b0 = A.b0; F.dx = dx;
     F.num_phases = (A.k2_flags & LDS_K2_FORWARD_ONLY) ? 2 : 4;
+    F.eval_samples = eval_batch ? A.num_samples : 1; F.step0 = A.step;
     F.rows_per_cta = (int)ceil_div(A.n, L.sf.grid);
     F.s = L.sf; F.kb_real = L.kb_real; F.partial = fbuf(B_PARTIAL); F.counters = counters; F.use_lo = use_lo ? 1 : 0;
     F.gridbar = reinterpret_cast<unsigned*>(buf(B_GBAR));
@@ -456,7 +467,7 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
     if (tc_update) { E.fpack = reinterpret_cast<__nv_bfloat16*>(buf(B_F)); E.ld_fpack = L.kf; }
     else { E.fa = fbuf(B_FA); E.fb = fbuf(B_FB); }
     if (S > 1) { E.fpack = reinterpret_cast<__nv_bfloat16*>(A.fpack_multi) + (int64_t)smp * L.kf; E.ld_fpack = (int64_t)S * L.kf; }
-    E.c_accumulate = (S > 1 && smp > 0) ? 1 : 0; E.scal_scale = 1.0f / (float)S; E.scal_accumulate = E.c_accumulate;
+    E.c_accumulate = (S > 1 && smp > 0) ? 1 : 0; E.scal_scale = 1.0f / (float)(eval_batch ? A.num_samples : S); E.scal_accumulate = E.c_accumulate;
     E.scal_tag = ((int)smp == S - 1) ? A.scalars_tag : 0.f;
     E.w1 = A.w1; E.b1 = A.b1; E.y = A.y; E.mask = A.mask; E.inv_m = 1.0f / (float)A.mask_count;
     E.drop_h = dh; E.bt_hi = bt_hi; E.bt_lo = bt_lo; E.ldb = L.ldb;
@@ -466,6 +477,19 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
     rc = fused_small_launch(F, stream);
     if (rc == LDS_OK) { fused_done = true; profile_mark(stream, 10); }
     else if (rc != LDS_ERR_UNSUPPORTED) return rc;
+  }
+  if (eval_batch && !fused_done) {
+    // any other launch plan: one forward-only pass per graph, the mean of the scalars accumulated on the device
+    float* tmp = fbuf(B_EVALTMP);
+    for (int s = 0; s < A.num_samples; ++s) {
+      lds_outer_step_args one = A;
+      one.num_samples = 1; one.step = A.step + (uint64_t)s; one.out_scalars = tmp; one.scalars_tag = 0.f;
+      if (A.out_logp) one.out_logp = A.out_logp + (int64_t)s * A.n * A.c;
+      if ((rc = lds_outer_step(&one, stream_)) != LDS_OK) return rc;
+      eval_accumulate_kernel<<<1, 32, 0, stream>>>(A.out_scalars, tmp, s, A.num_samples, s == A.num_samples - 1 ? A.scalars_tag : 0.f);
+      LDS_CHECK_LAUNCH("eval_accumulate_kernel");
+    }
+    return LDS_OK;
   }
 
   // Launch plan of everything that is not the fused small-graph kernel: the bit-packed A_tilde (tile-symmetric sampling,

@@ -223,9 +223,69 @@ __global__ void remove_edges_apply_kernel(const float* __restrict__ adj, int64_t
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// empirical_mean_loss (src/utils/evaluation.py:51-84): masked NLL and accuracy of S x N x C log-probabilities for TWO
+// node masks (validation, test) in one pass. Deterministic: per-block partials, summed in a fixed order by the finisher.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+eval_metrics_kernel(const float* __restrict__ logp, int n, int c, const int64_t* __restrict__ y, const uint8_t* __restrict__ mask_a,
+                    const uint8_t* __restrict__ mask_b, float* __restrict__ partial) {
+  __shared__ float red[8][4];
+  const int i = blockIdx.x * 256 + threadIdx.x, s = blockIdx.y;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};                          // loss a, correct a, loss b, correct b
+  if (i < n) {
+    const bool ma = mask_a[i] != 0, mb = mask_b[i] != 0;
+    if (ma || mb) {
+      const float* row = logp + ((int64_t)s * n + i) * c;
+      const int yi = (int)y[i];
+      float best = row[0]; int arg = 0;
+      for (int o = 1; o < c; ++o) { const float t = row[o]; if (t > best) { best = t; arg = o; } }    // first maximum wins (torch.argmax)
+      const float nll = -row[yi], hit = (arg == yi) ? 1.f : 0.f;
+      if (ma) { v[0] = nll; v[1] = hit; }
+      if (mb) { v[2] = nll; v[3] = hit; }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = warp_sum(v[k]);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red[w][0] = v[0]; red[w][1] = v[1]; red[w][2] = v[2]; red[w][3] = v[3]; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    partial[((int64_t)s * gridDim.x + blockIdx.x) * 4 + threadIdx.x] = t;
+  }
+}
+
+__global__ void eval_metrics_finish_kernel(const float* __restrict__ partial, int blocks, int samples, float inv_a, float inv_b, float* __restrict__ out4) {
+  if (threadIdx.x >= 4) return;
+  double t = 0.0;                                             // mean over samples of the per-sample masked means
+  for (int k = 0; k < blocks * samples; ++k) t += (double)partial[(int64_t)k * 4 + threadIdx.x];
+  out4[threadIdx.x] = (float)(t * (double)((threadIdx.x < 2) ? inv_a : inv_b) / (double)samples);
+}
+
 }  // namespace lds
 
 using namespace lds;
+
+extern "C" int64_t lds_eval_metrics_workspace_bytes(int32_t n, int32_t samples) {
+  return (n > 0 && samples > 0) ? (int64_t)samples * ceil_div(n, 256) * 16 : -1;
+}
+
+extern "C" int32_t lds_eval_metrics(const float* logp, int32_t samples, int32_t n, int32_t c, const int64_t* y,
+                                    const uint8_t* mask_a, int32_t count_a, const uint8_t* mask_b, int32_t count_b,
+                                    float* out4, void* workspace, int64_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LDS_CHECK_ARG(logp && y && mask_a && mask_b && out4 && workspace, "lds_eval_metrics: null pointer");
+  LDS_CHECK_ARG(samples > 0 && n > 0 && c > 0 && count_a > 0 && count_b > 0, "lds_eval_metrics: need positive sizes and mask counts");
+  if (workspace_bytes < lds_eval_metrics_workspace_bytes(n, samples)) { set_error("lds_eval_metrics: workspace too small"); return LDS_ERR_WORKSPACE; }
+  const int blocks = (int)ceil_div(n, 256);
+  eval_metrics_kernel<<<dim3((unsigned)blocks, (unsigned)samples), 256, 0, stream>>>(logp, n, c, y, mask_a, mask_b, reinterpret_cast<float*>(workspace));
+  LDS_CHECK_LAUNCH("eval_metrics_kernel");
+  eval_metrics_finish_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<const float*>(workspace), blocks, samples, 1.0f / (float)count_a, 1.0f / (float)count_b, out4);
+  LDS_CHECK_LAUNCH("eval_metrics_finish_kernel");
+  return LDS_OK;
+}
 
 extern "C" int64_t lds_knn_workspace_bytes(int32_t n) { return n > 0 ? round_up((int64_t)n * 8, 256) : -1; }
 
