@@ -539,15 +539,35 @@ def run_large(args, rank, world, device, workload):
         cntm = lib.lds_profile_end(ms_buf, id_buf, 64)
         for i in range(max(cntm, 0)):
             per_kernel.setdefault(int(id_buf[i]), []).append(float(ms_buf[i]))
-    # e2e: the step's weights from pinned host memory, (loss, acc) back to the host, every step
+    # e2e: through the reference-facing API — a row-block BernoulliGraphModel behind OuterProblemTrainer.train_step(model_forward)
+    # (src/trainers/outer.py:57-87) — with the step's weights from pinned host memory and Metrics back on the host, every step
+    from lds_gnn_b200.models.gcn import MetaDenseGCN
+    from lds_gnn_b200.models.graph import BernoulliGraphModel
+    from lds_gnn_b200.models.sampling import PHILOX
+    from lds_gnn_b200.trainers.inner import InnerProblemTrainer
+    from lds_gnn_b200.trainers.outer import OuterProblemTrainer
+    from lds_gnn_b200.utils.graph import DenseData
+    api_data = DenseData(x=d["x"], y=d["y"], train_mask=d["mask"], val_mask=d["mask"], test_mask=d["mask"], num_classes=c)
+    api_gcn = MetaDenseGCN(f, h, c, dropout=HYPER["dropout"]).to(device)
+    api_inner = InnerProblemTrainer(api_gcn, api_data)
+    api_inner.model_params = type(api_inner.model_params)(zip(api_inner.model_params.keys(), views))      # the step's weights: views of dev_flat
+    api_model = BernoulliGraphModel.from_row_block(theta, n, lo)
+    api_outer = OuterProblemTrainer(optimizer=torch.optim.SGD(api_model.parameters(), lr=lr), data=api_data, opt_mask=d["mask"], model=api_model,
+                                    smoothness_factor=0.0, disconnection_factor=0.0, sparsity_factor=0.0, regularize=False,
+                                    lr_decay=HYPER["lr_decay"], pretrain=False)
+    if world > 1:
+        api_outer._engine = ((d["x"].data_ptr(), d["mask"].data_ptr(), h, c, lo, cnt), eng, comm)           # reuse the buffers of the timed engine
+    PHILOX.manual_seed(1234)
+    PHILOX.step = 30_000
+    api_outer.train_step(api_inner.model_forward)                # builds the trainer's engine (untimed)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     ts = time.perf_counter()
     for k in range(args.steps):
         dev_flat.copy_(host_flat, non_blocking=True)
-        out = step_fn(30_000 + k, lr)
-        loss_acc = (out if world > 1 else eng.scalars)[:2].tolist()
+        metrics = api_outer.train_step(api_inner.model_forward)
+        loss_acc = [metrics.loss, metrics.acc]
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - ts) * 1e3
     clock_info = clocks.stop(wall0, time.time())
@@ -608,7 +628,7 @@ def run_large(args, rank, world, device, workload):
                    "l2": "not flushed: per-GPU theta rows are %.1f GB, far larger than the 126 MB L2" % (rows_local * n * 4 / 1e9)},
         "clocks": clock_info,
         "e2e": {"value": round(args.steps / (e2e_ms / 1e3), 3), "unit": UNIT, "h2d_bytes_per_step": total * 4, "d2h_bytes_per_step": 8,
-                "api": "lds_gnn_b200.sharded.ShardedOuterStep.run" if world > 1 else "lds_gnn_b200.kernels.OuterStep.run"},
+                "api": "OuterProblemTrainer.train_step(InnerProblemTrainer.model_forward) on BernoulliGraphModel.from_row_block"},
         "gpu_launches": (LAUNCHES_PER_STEP + (4 if world > 1 else 0)) * args.steps,
         "roofline": {"kernel": KERNEL_NAMES[dom], "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
                      "frac": round(achieved / hbm_peak, 4), "traffic": ncu_traffic(workload if world == 1 else None, KERNEL_NAMES[dom])[0],

@@ -71,15 +71,42 @@ class BernoulliGraphModel(GraphGenerativeModel):
         self._probs_stale = False    # `_full` is newer than `probs` (after fused steps)
         self._handed_out = False     # `probs` left the module since the last expansion: `.data` writes are invisible to `_version`
         self.factor_sink = FactorSink()   # hypergradient deposits of factored graphs (unrolled bilevel loop)
+        self.row_block = None        # (row0, rows) when the model owns a row block of theta (`from_row_block`)
         values = init_matrix if directed else get_triu_values(init_matrix)
         self.probs = Parameter(values, requires_grad=True)
+
+    @classmethod
+    def from_row_block(cls, theta_rows: Tensor, n: int, row0: int = 0) -> "BernoulliGraphModel":
+        """Large graphs (BASELINE.json configs 4 and 5): the model owns rows [row0, row0 + rows) of the symmetric N x N
+        probability matrix as ONE device tensor [rows, ld] (ld = round_up(n, 64), padding columns zero) and never builds the
+        (T,) upper-triangle vector, an N x N host tensor or the 2 x T index of the reference's forward
+        (src/utils/graph.py:166-181) — at N = 65 536 those are 8.6 GB, 17 GB and 34 GB. `probs` IS that tensor (a
+        deliberate deviation from the reference's (T,) shape, only for this constructor); with rows < n the outer trainer
+        steps it as one rank of the row-block sharded step, the other ranks own the other blocks and stay
+        consistent without exchanging theta: the update is symmetric bit for bit."""
+        from .. import kernels
+        if not theta_rows.is_cuda or theta_rows.dtype != torch.float32 or theta_rows.dim() != 2:
+            raise TypeError("from_row_block: theta_rows must be a CUDA float32 matrix [rows, ld]")
+        rows, ld = theta_rows.shape
+        if ld != kernels.padded_ld(n) or row0 < 0 or row0 + rows > n or row0 % 128:
+            raise ValueError(f"from_row_block: need ld == {kernels.padded_ld(n)}, 0 <= row0, row0 + rows <= n and row0 a multiple of 128")
+        self = cls.__new__(cls)
+        GraphGenerativeModel.__init__(self)
+        self.directed = False
+        self.orig_matrix = None
+        self._n = int(n)
+        self._full, self._full_key, self._probs_stale, self._handed_out = None, None, False, False
+        self.factor_sink = FactorSink()
+        self.row_block = (int(row0), int(rows))
+        self.probs = Parameter(theta_rows, requires_grad=True)
+        return self
 
     # ---- lazy consistency between the (T,) Parameter and the full device matrix ------------------
     def _probs_param(self) -> Parameter:
         return self._parameters["probs"]
 
     def _sync_probs(self):
-        if self._probs_stale:
+        if self._probs_stale and self.row_block is None:
             from .. import kernels
             p = self._probs_param()
             with torch.no_grad():
@@ -129,6 +156,8 @@ class BernoulliGraphModel(GraphGenerativeModel):
         if self.directed:
             raise NotImplementedError("theta_full() is defined for the undirected LDS model")
         p = self._probs_param()
+        if self.row_block is not None:
+            return p.data                                   # the parameter IS the device matrix (rows of this block)
         if not p.is_cuda:
             raise RuntimeError("BernoulliGraphModel: the B200 path needs the model on a CUDA device (model.to('cuda')); no CPU fallback")
         key = (p.data_ptr(), p._version)
@@ -141,7 +170,7 @@ class BernoulliGraphModel(GraphGenerativeModel):
 
     def mark_full_updated(self):
         """Called by the fused outer step after it updated `theta_full()` in place."""
-        self._probs_stale = True
+        self._probs_stale = self.row_block is None
 
     def sample_factored(self) -> FactoredGraph:
         """`sample()` for callers that understand factored graphs (the trainers of this package): K1 straight from the
@@ -161,11 +190,17 @@ class BernoulliGraphModel(GraphGenerativeModel):
         self._full_key = None
 
     def forward(self, *args, **kwargs) -> Tensor:
+        if self.row_block is not None:
+            if self.row_block[1] != self._n:
+                raise NotImplementedError("forward() of a row-block model needs every row: only the sharded outer step is defined for it")
+            return self.probs[:, :self._n].clamp(0.0, 1.0)
         return self.probs if self.directed else triu_values_to_symmetric_matrix(self.probs)  # type: ignore
 
     def statistics(self) -> Dict[str, float]:
         """Same keys and definitions as the reference (src/models/graph.py:69-78); one reduction kernel and
         a single device->host copy instead of a rebuild of the N x N matrix plus five `.item()` syncs."""
+        if self.row_block is not None:
+            return self._row_block_statistics()
         if self.directed or not self._probs_param().is_cuda:
             sample = self.forward()
             probs = self.probs
@@ -178,3 +213,24 @@ class BernoulliGraphModel(GraphGenerativeModel):
         t = self._n * (self._n + 1) // 2
         return {"expected_num_edges": s[0], "percentage_edges_expected": s[0] / (self._n ** 2),
                 "mean_prob": s[1] / t, "min_prob": s[2], "max_prob": s[3]}
+
+    def _row_block_statistics(self) -> Dict[str, float]:
+        """statistics() of a row-block model: local sums over this block (upper-triangle terms: columns >= global row),
+        all-reduced over the ranks when torch.distributed is initialised. One device->host transfer."""
+        import torch.distributed as dist
+        row0, rows = self.row_block
+        n = self._n
+        th = self.probs.detach()[:, :n]
+        gi = torch.arange(row0, row0 + rows, device=th.device)[:, None]
+        upper = torch.arange(n, device=th.device)[None, :] >= gi
+        big = torch.finfo(torch.float64).max
+        vals = th.double()
+        acc = torch.stack([vals.clamp(0.0, 1.0).sum(), (vals * upper).sum(),
+                           torch.where(upper, vals, torch.full_like(vals, big)).min(), torch.where(upper, vals, torch.full_like(vals, -big)).max()])
+        if dist.is_available() and dist.is_initialized() and rows < n:
+            sums, mn, mx = acc[:2].clone(), acc[2:3].clone(), acc[3:4].clone()
+            dist.all_reduce(sums); dist.all_reduce(mn, op=dist.ReduceOp.MIN); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            acc = torch.cat([sums, mn, mx])
+        s = acc.tolist()
+        t = n * (n + 1) // 2
+        return {"expected_num_edges": s[0], "percentage_edges_expected": s[0] / (n ** 2), "mean_prob": s[1] / t, "min_prob": s[2], "max_prob": s[3]}

@@ -85,6 +85,44 @@ class GatherBuffer:
         self.t, self.ctx = tensor, ctx
 
 
+class LocalComm:
+    """The exchange of a single rank that owns every row (world size 1, no process group): gathers are copies."""
+
+    def __init__(self, n):
+        self.world, self.rank = 1, 0
+        self.bounds = [shard_bounds(n, 1, 0)]
+        self.equal = True
+
+    def all_gather_rows(self, local, out):
+        out[:local.shape[0]].copy_(local)
+        return out
+
+    def all_reduce_sum(self, t):
+        return t
+
+    def gather_buffer(self, numel, dtype, device):
+        return GatherBuffer(torch.zeros(numel, dtype=dtype, device=device))
+
+    def gather_into(self, local, gb, offset, chunk, count=None):
+        k = chunk if count is None else count
+        gb.t[offset:offset + k].copy_(local.reshape(-1)[:k])
+
+
+def make_comm(n, device):
+    """The exchange object of this process: NVLink peer-memory push over symmetric memory when torch.distributed runs NCCL on
+    CUDA devices (falls back to NCCL all-gathers), gloo / other backends through torch.distributed, a plain copy without a
+    process group."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return LocalComm(n)
+    if device.type == "cuda" and dist.get_backend() == "nccl":
+        try:
+            return SymmComm(n)
+        except Exception:                                       # noqa: BLE001  (symmetric memory unavailable: NCCL all-gathers)
+            pass
+    return DistComm(n)
+
+
 class SymmComm(DistComm):
     """Exchange over NVLink peer memory instead of NCCL: the gather buffers are torch symmetric memory (every rank maps
     every peer's buffer), `gather_into` is ONE kernel of ours that stores this rank's block into all peers' buffers with

@@ -100,6 +100,8 @@ class OuterProblemTrainer:
             route, inner, opt = plan
             if route == "fused":
                 return self._train_step_fused(inner, opt)
+            if route == "sharded":
+                return self._train_step_sharded(inner, opt)
             return self._train_step_factored(inner, opt, retain_graph)
         return self._train_step_composable(gcn_predict_fct, mask, retain_graph)
 
@@ -244,6 +246,12 @@ class OuterProblemTrainer:
         opt = self._optimizer_kind()
         if opt is None:
             return None
+        if model.row_block is not None:
+            # a model that owns a row block of theta (large graphs): the direct step only — its weights must not carry an
+            # unrolled history (the unrolled hypergradient of sharded graphs is not implemented)
+            if any(p.grad_fn is not None for p in owner.model_params.values()) and not self.first_order:
+                raise NotImplementedError("row-block models support the direct outer step (detach the inner trainer or set first_order)")
+            return "sharded", owner, opt
         if not self.first_order and any(p.grad_fn is not None for p in owner.model_params.values()):
             return ("factored", owner, opt) if self.factored_enabled else None
         return "fused", owner, opt
@@ -310,6 +318,49 @@ class OuterProblemTrainer:
                     raise RuntimeError("lds_outer_step finished without publishing its metrics")
                 break
         loss, acc = float(hv[0]), float(hv[1])
+        return Metrics(loss=loss, acc=acc)
+
+    # ---- row-block route (BASELINE.json configs 4 and 5 behind the same call) ---------------------
+    def _train_step_sharded(self, inner, opt) -> Metrics:
+        """`model` owns rows [row0, row0 + rows) of theta (`BernoulliGraphModel.from_row_block`) and `dataset.x / y`, `opt_mask`
+        hold the same rows. rows == n: the whole step on this GPU (bit-packed plan); rows < n: this process is one rank of the
+        row-block sharded step (lds_gnn_b200/sharded.py) — every rank calls train_step, the exchange runs over
+        torch.distributed (NVLink peer-memory push under NCCL). The Philox seed must agree on all ranks (PHILOX.manual_seed)."""
+        from .. import kernels, sharded
+        self.last_route = "sharded"
+        model, gcn = self.model, inner.model
+        model.train(); gcn.train(True)
+        kind, group = opt
+        if kind != _lib.OPT_SGD:
+            raise NotImplementedError("row-block models are stepped with the SGD outer optimiser (models/factory.py:66-69)")
+        row0, rows = model.row_block
+        n = model._n
+        h, c = gcn.layer_in.fc.out_features, gcn.layer_out.fc.out_features
+        x = self.dataset.x
+        key = (x.data_ptr(), self.opt_mask.data_ptr(), h, c, row0, rows)
+        if self._engine is None or self._engine[0] != key:
+            if x.shape[0] != rows:
+                raise ValueError(f"the dataset of a row-block model holds the block's {rows} rows (got {x.shape[0]})")
+            if rows == n:
+                eng, comm = kernels.OuterStep(n, x, self.dataset.y, self.opt_mask, hidden=h, classes=c), None
+            else:
+                comm = sharded.make_comm(n, x.device)
+                count = comm.all_reduce_sum(self.opt_mask.sum().to(torch.float32).reshape(1).clone())
+                eng = sharded.ShardedOuterStep(n, row0, rows, x, self.dataset.y, self.opt_mask, int(count.item()), h, c)
+            self._engine = (key, eng, comm)
+        _, eng, comm = self._engine
+        params = inner.model_params
+        eng.set_weights(params["layer_in.fc.weight"], params["layer_in.fc.bias"], params["layer_out.fc.weight"], params["layer_out.fc.bias"])
+        seed, step = PHILOX.next_step()
+        theta = model.theta_full()
+        if comm is None:
+            out = eng.run(theta, lr=group["lr"], seed=seed, step=step, dropout_p=float(gcn.dropout), update=True, want_adj=False)
+        else:
+            out = eng.run(theta, comm, lr=group["lr"], seed=seed, step=step, dropout_p=float(gcn.dropout), update=True, want_adj=False)
+        if self.lr_decayer is not None:
+            self.optimizer._opt_called = True
+            self.lr_decayer.step()
+        loss, acc = out[:2].tolist()                          # one device->host transfer
         return Metrics(loss=loss, acc=acc)
 
     # ------------------------------------------------------------------------------------------ rest of the API

@@ -14,6 +14,9 @@ iu = torch.triu_indices(n, n)
 theta = K.theta_triu_to_full(data.dense_adj[iu[0], iu[1]].contiguous().to(dev))
 for i in range(5): eng.run(theta, lr=0.1, seed=1, step=i, dropout_p=0.5, want_adj=False)
 tl = torch.zeros((4, 512, 8), dtype=torch.int64, device=dev)
+if os.environ.get("COLD"):
+    torch.empty(256 << 20, dtype=torch.uint8, device=dev).zero_()          # flush the 126 MB L2
+    torch.cuda.synchronize()
 eng.run(theta, lr=0.1, seed=1, step=99, dropout_p=0.5, k2_timeline=tl, want_adj=False)
 torch.cuda.synchronize()
 t = tl.cpu().numpy().astype(np.float64).reshape(-1)[:148 * 16].reshape(148, 16)

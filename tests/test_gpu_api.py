@@ -459,3 +459,38 @@ def test_writes_through_probs_data_reach_the_device_matrix():
     ref.data.fill_(0.25)
     model.invalidate()
     assert torch.all(model.theta_full()[:, :n] == 0.25)
+
+
+def test_row_block_model_steps_through_the_same_train_step():
+    """BASELINE.json configs 4 / 5 behind the reference API: a model that owns a row block of theta as one device matrix
+    (`BernoulliGraphModel.from_row_block`, no (T,) vector, no N x N host tensor). With the block = all rows, `train_step`
+    must reproduce the regular model's step: same Philox graph, same theta."""
+    from lds_gnn_b200 import kernels
+    from lds_gnn_b200.models.graph import BernoulliGraphModel
+    from lds_gnn_b200.models.sampling import PHILOX
+    from lds_gnn_b200.trainers.outer import OuterProblemTrainer
+    g = load_golden("n257_h64")
+    data, gcn, inner, model, outer = _setup(g, lr=0.5, lr_decay=0.9, dropout=0.5)
+    with torch.no_grad():
+        model.probs.mul_(0.6).add_(0.2)
+    n = model._n
+    block = BernoulliGraphModel.from_row_block(model.theta_full().clone(), n, 0)
+    assert block.probs.shape == (n, kernels.padded_ld(n)) and block.row_block == (0, n)
+    outer_b = OuterProblemTrainer(optimizer=torch.optim.SGD(block.parameters(), lr=0.5), data=data, opt_mask=outer.opt_mask, model=block,
+                                  smoothness_factor=0.0, disconnection_factor=0.0, sparsity_factor=0.0, regularize=False, lr_decay=0.9, pretrain=False)
+    res = []
+    for trainer in (outer, outer_b):
+        PHILOX.manual_seed(11)
+        res.append([trainer.train_step(inner.model_forward) for _ in range(2)])
+    assert outer.last_route == "fused" and outer_b.last_route == "sharded"
+    for a, b in zip(*res):
+        assert abs(a.loss - b.loss) < 1e-5 and abs(a.acc - b.acc) < 1e-6
+    full = model.theta_full()[:, :n]
+    assert (block.probs.detach()[:, :n] - full).abs().max().item() < 2e-6          # fused small-graph kernel vs bit-packed plan: summation order
+    assert torch.equal(block.probs.detach()[:, :n], block.probs.detach()[:, :n].t())
+    assert outer_b.get_learning_rates() == outer.get_learning_rates()
+    sa, sb = model.statistics(), block.statistics()
+    for k in sa:
+        assert abs(sa[k] - sb[k]) <= 1e-5 * max(1.0, abs(sa[k])), k
+    block.project_parameters()
+    assert float(block.probs.min()) >= 0.0 and float(block.probs.max()) <= 1.0

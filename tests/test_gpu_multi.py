@@ -51,6 +51,30 @@ for step in range(3):
 torch.cuda.synchronize()
 assert (results["peer"][0] - ref[lo:lo + cnt]).abs().max().item() < 2e-5
 assert abs(results["peer"][1][0].item() - rs[0].item()) < 1e-5
+# the same three steps through the reference-facing API: a row-block model per rank behind OuterProblemTrainer.train_step
+from lds_gnn_b200.models.gcn import MetaDenseGCN
+from lds_gnn_b200.models.graph import BernoulliGraphModel
+from lds_gnn_b200.models.sampling import PHILOX
+from lds_gnn_b200.trainers.inner import InnerProblemTrainer
+from lds_gnn_b200.trainers.outer import OuterProblemTrainer
+from lds_gnn_b200.utils.graph import DenseData
+data = DenseData(x=xt[lo:lo + cnt], y=yt[lo:lo + cnt], train_mask=mt[lo:lo + cnt], val_mask=mt[lo:lo + cnt], test_mask=mt[lo:lo + cnt], num_classes=c)
+gcn = MetaDenseGCN(f, h, c, dropout=p).to(dev)
+with torch.no_grad():
+    for prm, v in zip(gcn.parameters(), w):
+        prm.copy_(v)
+inner = InnerProblemTrainer(gcn, data)
+model = BernoulliGraphModel.from_row_block(full0[lo:lo + cnt].clone(), n, lo)
+outer = OuterProblemTrainer(optimizer=torch.optim.SGD(model.parameters(), lr=0.3), data=data, opt_mask=mt[lo:lo + cnt], model=model,
+                            smoothness_factor=0.0, disconnection_factor=0.0, sparsity_factor=0.0, regularize=False, lr_decay=None, pretrain=False)
+PHILOX.seed, PHILOX.step = 7, 0
+for step in range(3):
+    m = outer.train_step(inner.model_forward)
+assert outer.last_route == "sharded"
+assert torch.equal(model.probs.detach(), results["peer"][0]), "the API route must run the same sharded step"
+assert abs(m.loss - results["peer"][1][0].item()) < 1e-6
+st = model.statistics()
+assert abs(st["expected_num_edges"] - float(ref[:, :n].clamp(0, 1).double().sum())) < 1e-3 * n
 dist.barrier(); dist.destroy_process_group()
 print("ok")
 """
