@@ -16,6 +16,8 @@ EPI = {"1": "k2_layer1", "2": "k2_layer2", "3": "k2_bwd2", "4": "k2_bwd1", "0": 
 
 def bench_name(kname):
     if "k1_sample_kernel" in kname: return "k1_sample_normalize"
+    if "k1p_sample_kernel" in kname: return "k1p_sample_normalize_packed"
+    if "k2p_mma_kernel" in kname: return "k2p_propagate_packed"
     if "k3_tc_kernel" in kname: return "k3k4_theta_update"
     if "fused_small_kernel" in kname: return "fused_k1_feat_k2x4"
     if "feat_sparse_kernel" in kname or "feat_linear_kernel" in kname: return "feat_linear"
