@@ -34,27 +34,38 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const unsigned* p) {
   return v;
 }
 
-// Sense-reversing grid barrier over `bar` = {arrival count, generation}. All CTAs are co-resident (cooperative launch).
-// The count returns to zero after every barrier; the generation only grows, and every CTA reads its value at kernel
-// start (`base`) before it can change, so nothing has to be reset between launches. Bounded spin: a protocol bug traps.
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned base, unsigned& k, unsigned nctas) {
+__device__ __forceinline__ uint32_t fs_prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Grid barrier over ONE monotonic 64-bit arrival counter (all CTAs are co-resident: cooperative launch). Every CTA of every
+// launch on this workspace passes the same number of barriers, so the counter is a multiple of the grid size between launches
+// and `base` = the value at kernel start rounded down to one (a CTA that starts late sees at most grid - 1 arrivals of
+// barrier 0 on top of it). Barrier k is complete when the counter reaches base + (k + 1) * grid: one release-add, then
+// acquire-polls of the same word — a separate generation word written by the last arriver costs one more L2 round trip per
+// barrier, six times per step. Nothing to re-arm; 64 bits never wrap. Bounded spin: a protocol bug traps.
+__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long base, unsigned& k, unsigned nctas) {
   __syncthreads();                                           // the CTA's writes happen-before thread 0's cumulative release below
   if (threadIdx.x == 0) {
-    const unsigned want = base + k + 1;
-    unsigned old;
+    const unsigned long long want = base + (unsigned long long)(k + 1) * nctas;
     asm volatile("fence.proxy.async;" ::: "memory");         // generic-proxy writes -> TMA (async proxy) reads of other CTAs
-    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(bar) : "memory");
-    if (old == nctas - 1) {                                  // last to arrive: re-arm the count, then release the generation
-      asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(bar), "r"(0u) : "memory");
-      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(want) : "memory");
-    } else {
-      long long t0 = 0;
-      for (unsigned spins = 0; ld_acquire_u32(&bar[1]) != want; ++spins) {
-        if (spins == 64) t0 = clock64();
-        if (spins > 64 && (spins & 255) == 0 && clock64() - t0 > 4000000000ll) {
-          printf("liblds_b200: grid barrier timed out (block %d, barrier %u)\n", blockIdx.x, k);
-          __trap();
-        }
+    asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(bar) : "memory");
+    long long t0 = 0;
+    for (unsigned spins = 0; ld_acquire_u64(bar) < want; ++spins) {
+      if (spins == 64) t0 = clock64();
+      if (spins > 64 && (spins & 255) == 0 && clock64() - t0 > 4000000000ll) {
+        printf("liblds_b200: grid barrier timed out (block %d, barrier %u)\n", blockIdx.x, k);
+        __trap();
       }
     }
   }
@@ -86,7 +97,8 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
                    const __grid_constant__ CUtensorMap tm_bhi_alt, const __grid_constant__ CUtensorMap tm_blo_alt,
                    const __grid_constant__ FusedSmallArgs fa) {
   __shared__ K2EpiShared sh_epi;
-  __shared__ unsigned sh_base;
+  __shared__ unsigned long long sh_base;
+  __shared__ int sh_rowpair;                                 // ticket of the feature-row pairs of this CTA
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sa = smem;                                        // resident A tiles
@@ -106,7 +118,8 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
   const int my_p = lo / s.kblocks, my_kb0 = lo - my_p * s.kblocks;
   const int nt = min(s.per_cta, fa.kb_real - my_kb0);         // real tiles of this CTA (>= 1)
 
-  if (tid == 0) sh_base = ld_acquire_u32(&fa.gridbar[1]);
+  unsigned long long* const gbar = reinterpret_cast<unsigned long long*>(fa.gridbar);
+  if (tid == 0) { const unsigned long long cur = ld_acquire_u64(gbar); sh_base = cur - cur % gridDim.x; sh_rowpair = 0; }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_bhi); tma_prefetch_desc(&tm_blo); tma_prefetch_desc(&tm_bhi_alt); tma_prefetch_desc(&tm_blo_alt); }
   if (warp == 1) {
     if (lane == 0) {
@@ -121,7 +134,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const unsigned gbase = sh_base;
+  const unsigned long long gbase = sh_base;
   unsigned gk = 0;
   auto stamp = [&](int k) {
     if (fa.timeline != nullptr && tid == 0) {
@@ -145,127 +158,58 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
     c2s = (uint32_t)(st & 0xffffffffull);
     c3s = (c3s & 0xffffu) | (uint32_t)(((st >> 32) & 0xffffull) << 16);
   }
-  // ================= P0: weight staging, panel counters, sampling into shared memory =================
-  if (smp == 0) {
-    for (int idx = cta * K2_THREADS + tid; idx < fa.f * ea.h; idx += gridDim.x * K2_THREADS) {
+  // ================= P0: weight staging, tile-symmetric sampling to bits, feature rows =================
+  const int r_lo = cta * fa.rows_per_cta, r_hi = min(n, r_lo + fa.rows_per_cta);
+  if (smp == 0 && warp >= 16) {
+    // Two warps stage this CTA's slice of layer_in.weight (transposed: one contiguous row per non-zero of X) before they start
+    // sampling; the other sixteen start at once. Split barrier: arrive here, wait right before the feature rows, when every
+    // CTA has long arrived. The count is re-armed by CTA 0 behind the next grid barrier.
+    const int st = tid - 512;
+#pragma unroll 4
+    for (int idx = cta * 64 + st; idx < fa.f * ea.h; idx += gridDim.x * 64) {
       const int ff = idx / ea.h, o = idx - ff * ea.h;
       fa.w0t[idx] = fa.w0[(int64_t)o * fa.ldw + ff];
     }
-    if (cta == 0) for (int k = tid; k < s.panels; k += K2_THREADS) fa.counters[k] = 0;
+    if (cta == 0) for (int k = st; k < s.panels; k += 64) fa.counters[k] = 0;
+    named_bar_sync(4, 64);
+    if (st == 0) { __threadfence(); atomicAdd(&fa.gridbar[2], 1u); }
+    // Cold start (between two outer steps the inner problem trains: this step's inputs are not in L2): pull what the feature
+    // rows of this CTA and the row epilogues will read towards L2 now, under the sampling.
+    const int beg = fa.crow[r_lo], end = fa.crow[r_hi];
+    for (int k = beg + st * 32; k < end; k += 64 * 32) { prefetch_l2(fa.xcol + k); prefetch_l2(fa.xval + k); }
+    if (st < 4) prefetch_l2(ea.y + min(r_lo + st * 16, r_hi - 1));
+    if (st == 4) { prefetch_l2(ea.mask + r_lo); prefetch_l2(ea.mask + r_hi - 1); }
+    if (st >= 8 && st < 8 + 8 && (st - 8) * 32 < ea.c * ea.h) prefetch_l2(ea.w1 + (st - 8) * 32);
+    if (st == 16) { prefetch_l2(ea.b1); prefetch_l2(fa.b0); }
   }
-  if (warp < 16) {
-    const int rp = tid >> 3, c8 = tid & 7;                   // item = (row pair, 8-column chunk) of a 128 x 64 tile
-    const int gi0 = my_p * K2_BLOCK_M + 2 * rp, gi1 = gi0 + 1;
-    const int pblk = gi0 >> 1;
-    const float* row0p = fa.theta + (int64_t)gi0 * fa.ldt + 8 * c8;
-    const float* row1p = fa.theta + (int64_t)gi1 * fa.ldt + 8 * c8;
-    // theta rows are padded to ld >= round_up(n, 64): the 8 columns are always inside the row. The NEXT tile's theta is
-    // in flight while this tile's draws are computed (one item per thread per tile: the loop is latency-bound otherwise).
-    float4 nx[4];
-    auto load_theta = [&](int kb) {
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      nx[0] = nx[1] = nx[2] = nx[3] = z;
-      if (gi0 < n) { const float4* r = reinterpret_cast<const float4*>(row0p + kb * K2_BLOCK_K); nx[0] = r[0]; nx[1] = r[1]; }
-      if (gi1 < n) { const float4* r = reinterpret_cast<const float4*>(row1p + kb * K2_BLOCK_K); nx[2] = r[0]; nx[3] = r[1]; }
-    };
-    // pull every theta tile of this CTA towards L2 right away (no registers needed): the loop below then runs at L2 latency
-    for (int j = 1; j < nt; ++j) {
-      if (gi0 < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(row0p + (my_kb0 + j) * K2_BLOCK_K));
-      if (gi1 < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(row1p + (my_kb0 + j) * K2_BLOCK_K));
-    }
-    load_theta(my_kb0);
-    for (int j = 0; j < nt; ++j) {
-      const int kb = my_kb0 + j;
-      const int gj0 = kb * K2_BLOCK_K + 8 * c8;
-      const float th0[8] = {nx[0].x, nx[0].y, nx[0].z, nx[0].w, nx[1].x, nx[1].y, nx[1].z, nx[1].w};
-      const float th1[8] = {nx[2].x, nx[2].y, nx[2].z, nx[2].w, nx[3].x, nx[3].y, nx[3].z, nx[3].w};
-      if (j + 1 < nt) load_theta(kb + 1);
-      uint32_t b0[8], b1[8];
-      if (fa.u_explicit != nullptr) {                        // parity mode: element (i,j) uses U[min][max] (src/models/sampling.py:76)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int gj = gj0 + e;
-          b0[e] = 0u; b1[e] = 0u;
-          if (gj < n) {
-            if (gi0 < n) { const float u = (gi0 <= gj) ? fa.u_explicit[(int64_t)gi0 * fa.ldu + gj] : fa.u_explicit[(int64_t)gj * fa.ldu + gi0];
-                           b0[e] = (u < fminf(fmaxf(th0[e], 0.f), 1.f)) ? 1u : 0u; }
-            if (gi1 < n) { const float u = (gi1 <= gj) ? fa.u_explicit[(int64_t)gi1 * fa.ldu + gj] : fa.u_explicit[(int64_t)gj * fa.ldu + gi1];
-                           b1[e] = (u < fminf(fmaxf(th1[e], 0.f), 1.f)) ? 1u : 0u; }
-          }
-        }
-      } else {
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {                        // four 2x2 Philox blocks: column blocks q
-          const int q = (gj0 >> 1) + b;
-          const bool upper = pblk < q;
-          uint32_t w[4];
-          philox4x32_10_rk((uint32_t)(upper ? q : pblk), (uint32_t)(upper ? pblk : q), fa.rounds, c2s, c3s, w);
-          // word = 2*(a%2) + (b%2) of the canonical pair (a, b) = (min, max); the diagonal block uses w[1] for both off-diagonal cells
-          const uint32_t w01 = (pblk <= q) ? w[1] : w[2], w10 = upper ? w[2] : w[1];
-          b0[2 * b]     = ((w[0] >> 8) < __float2uint_ru(th0[2 * b] * 16777216.f)) ? 1u : 0u;
-          b0[2 * b + 1] = ((w01 >> 8)  < __float2uint_ru(th0[2 * b + 1] * 16777216.f)) ? 1u : 0u;
-          b1[2 * b]     = ((w10 >> 8)  < __float2uint_ru(th1[2 * b] * 16777216.f)) ? 1u : 0u;
-          b1[2 * b + 1] = ((w[3] >> 8) < __float2uint_ru(th1[2 * b + 1] * 16777216.f)) ? 1u : 0u;
-        }
-      }
-      uint32_t s0 = 0, s1 = 0;
-      // only the two k-blocks that cross the panel's diagonal and the last k-block / last panel need the per-cell checks
-      const bool edge = (kb >> 1) == my_p || (kb + 1) * K2_BLOCK_K > n || (my_p + 1) * K2_BLOCK_M > n;
-      if (edge) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int gj = gj0 + e;
-          if (gj == gi0) b0[e] = 1u;                         // self loops: diag := 1 (src/utils/graph.py:131-132)
-          if (gj == gi1) b1[e] = 1u;
-          if (gj >= n || gi0 >= n) b0[e] = 0u;
-          if (gj >= n || gi1 >= n) b1[e] = 0u;
-        }
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) { s0 += b0[e]; s1 += b1[e]; }
-      uint4 v0, v1;                                          // bf16 1.0 = 0x3F80
-      v0.x = b0[0] * 0x3F80u + b0[1] * 0x3F800000u; v0.y = b0[2] * 0x3F80u + b0[3] * 0x3F800000u;
-      v0.z = b0[4] * 0x3F80u + b0[5] * 0x3F800000u; v0.w = b0[6] * 0x3F80u + b0[7] * 0x3F800000u;
-      v1.x = b1[0] * 0x3F80u + b1[1] * 0x3F800000u; v1.y = b1[2] * 0x3F80u + b1[3] * 0x3F800000u;
-      v1.z = b1[4] * 0x3F80u + b1[5] * 0x3F800000u; v1.w = b1[6] * 0x3F80u + b1[7] * 0x3F800000u;
-      uint8_t* tile = sa + j * FS_A_BYTES;                   // K-major SWIZZLE_128B: 16-byte chunk c of row r sits at chunk c ^ (r & 7)
-      const int ra = 2 * rp, rb = 2 * rp + 1;
-      *reinterpret_cast<uint4*>(tile + ra * 128 + ((c8 ^ (ra & 7)) << 4)) = v0;
-      *reinterpret_cast<uint4*>(tile + rb * 128 + ((c8 ^ (rb & 7)) << 4)) = v1;
-      if (fa.a_dump != nullptr) {                            // tests: the sampled A_tilde as the multi-kernel path stores it
-        if (gi0 < n) *reinterpret_cast<uint4*>(fa.a_dump + (int64_t)gi0 * fa.lda + gj0) = v0;
-        if (gi1 < n) *reinterpret_cast<uint4*>(fa.a_dump + (int64_t)gi1 * fa.lda + gj0) = v1;
-      }
-#pragma unroll
-      for (int sh = 1; sh <= 4; sh <<= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, sh); s1 += __shfl_xor_sync(0xffffffffu, s1, sh); }
-      if (c8 == 0) {                                         // row sums of this tile (integers in fp32: exact)
-        if (gi0 < n) fa.deg_part[(int64_t)kb * ea.ldr + gi0] = (float)s0;
-        if (gi1 < n) fa.deg_part[(int64_t)kb * ea.ldr + gi1] = (float)s1;
-      }
-    }
-  }
-  fence_proxy_async_smem();                                  // generic-proxy smem writes -> visible to tcgen05.mma
-  stamp(1);
-  grid_barrier(fa.gridbar, gbase, gk, gridDim.x);
-  stamp(2);
-
-  // ================= P1: degrees, r, feature rows, first operand =================
-  // Two rows per warp: h <= 16, so a half-warp owns a row (lane16 = output column; 16 non-zeros per trip).
+  // Every warp takes quarter tiles of the upper triangle (lds_k1_tile.cuh: the same draws and integer compare as the stand-
+  // alone packed kernel): one Philox call and one theta read per UNORDERED 2 x 2 block, the tile and its transpose leave as
+  // bits (L2), the row sums as integer atomics. Static assignment, interleaved over the CTAs: a global ticket would be a few
+  // thousand same-address atomics in one burst, which alone took longer than the sampling.
   {
+    const int first = warp * (int)gridDim.x + cta, stride = (K2_THREADS / 32) * (int)gridDim.x;
+    if (fa.k1.u != nullptr) k1q_warp_loop<true>(fa.k1, fa.rounds, c2s, c3s, lane, first, stride);
+    else k1q_warp_loop<false>(fa.k1, fa.rounds, c2s, c3s, lane, first, stride);
+  }
+  stamp(13);
+  if (smp == 0) {
+    // P1 = dropout(X) W0^T + b0 for this CTA's rows: independent of the sample, so the warps that are done sampling (a
+    // warp gets at most about one tile) run it under the tail of the slow (diagonal / ragged) tiles. Two rows per warp:
+    // h <= 16, so a half-warp owns a row (lane16 = output column; 16 non-zeros per trip); row pairs from a CTA-local ticket.
+    if (lane == 0) while (ld_acquire_u32(&fa.gridbar[2]) < gridDim.x) { }
+    __syncwarp();
     const int lane16 = lane & 15, half = lane >> 4;
-    const int r_lo = cta * fa.rows_per_cta, r_hi = min(n, r_lo + fa.rows_per_cta);
-    for (int ib = r_lo + 2 * warp; ib < r_hi; ib += 2 * (K2_THREADS / 32)) {
+    for (;;) {
+      int pr = 0;
+      if (lane == 0) pr = atomicAdd(&sh_rowpair, 1);
+      pr = __shfl_sync(0xffffffffu, pr, 0);
+      const int ib = r_lo + 2 * pr;
+      if (ib >= r_hi) break;
       const int i = ib + half;
       const bool live = i < r_hi;
       const int il = live ? i : r_hi - 1;
-      float d = 0.f;
-      for (int kb = lane16; kb < fa.kb_real; kb += 16) d += fa.deg_part[(int64_t)kb * ea.ldr + il];
-#pragma unroll
-      for (int sh = 8; sh > 0; sh >>= 1) d += __shfl_xor_sync(0xffffffffu, d, sh);      // integer-valued: exact in any order
-      const float ri = 1.0f / sqrtf(d);
-      if (live && lane16 == 0) { fa.deg[i] = d; fa.rs[i] = ri; }
       float acc = 0.f;
-      const int beg = fa.crow[il], end = (live && smp == 0) ? fa.crow[il + 1] : beg;     // later graphs of a batched evaluation reuse P1
+      const int beg = fa.crow[il], end = live ? fa.crow[il + 1] : beg;
       const int trips = (max(__shfl_sync(0xffffffffu, end - beg, 0), __shfl_sync(0xffffffffu, end - beg, 16)) + 15) >> 4;
       for (int tr = 0; tr < trips; ++tr) {                     // both halves run the same number of trips (shuffles are warp-wide)
         const int base = beg + 16 * tr;
@@ -288,18 +232,64 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
           for (int u = 0; u < 8; ++u) if (j + u < cnt) acc = fmaf(vj[u], wv[u], acc);
         }
       }
-      if (live && lane16 < ea.h) {
-        const float pv = (smp == 0) ? acc + fa.b0[lane16] : ea.p1[(int64_t)lane16 * ea.ldr + i];
-        if (smp == 0) ea.p1[(int64_t)lane16 * ea.ldr + i] = pv;
-        __nv_bfloat16 bh, bl;
-        split_bf16(ri * pv, bh, bl);
-        ea.bt_hi[(int64_t)lane16 * ea.ldb + i] = bh;
-        ea.bt_lo[(int64_t)lane16 * ea.ldb + i] = bl;
+      if (live && lane16 < ea.h) ea.p1[(int64_t)lane16 * ea.ldr + i] = acc + fa.b0[lane16];
+    }
+  }
+  stamp(1);
+  grid_barrier(gbar, gbase, gk, gridDim.x);
+  stamp(2);
+
+  // ================= P1: expand this CTA's tiles into shared memory; degrees, r, first operand =================
+  if (cta == 0 && tid == 0) fa.gridbar[2] = 0u;              // every CTA is past the split barrier: re-arm it for the next launch
+  if (tid < 512) {
+    // row r of tile j: 64 bits (even / odd column words, lds_packed.cuh) -> 64 bf16 {0, 1} in the UMMA K-major SWIZZLE_128B
+    // layout (16-byte chunk c of row r sits at chunk c ^ (r & 7)). The bits were written by other SMs: read them through L2.
+    const int r = tid & 127, gi = my_p * K2_BLOCK_M + r;
+    for (int j = tid >> 7; j < nt; j += 4) {
+      const int kb = my_kb0 + j;
+      uint2 w = make_uint2(0u, 0u);
+      if (gi < n) w = __ldcg(reinterpret_cast<const uint2*>(fa.k1.bits + pk_word(gi, kb, fa.k1.kblocks, 0)));
+      uint32_t pw[32];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {                            // bit deposit as in lds_k2_packed.cu (expand_row), then 0x4000 -> 0x3F80 = bf16 1.0
+        const uint32_t a = ((q < 7) ? (w.x << (6 - q)) : (w.x >> 1)) & 0x40404040u;
+        const uint32_t b = ((q < 7) ? (w.y << (6 - q)) : (w.y >> 1)) & 0x40404040u;
+        const uint32_t x0 = fs_prmt(a, b, 0x4808u), x1 = fs_prmt(a, b, 0x5818u), x2 = fs_prmt(a, b, 0x6828u), x3 = fs_prmt(a, b, 0x7838u);
+        pw[q] = x0 - (x0 >> 7); pw[q + 8] = x1 - (x1 >> 7); pw[q + 16] = x2 - (x2 >> 7); pw[q + 24] = x3 - (x3 >> 7);
+      }
+      uint8_t* row = sa + j * FS_A_BYTES + r * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(row + ((c ^ (r & 7)) << 4)) = make_uint4(pw[4 * c], pw[4 * c + 1], pw[4 * c + 2], pw[4 * c + 3]);
+      if (fa.a_dump != nullptr && gi < n) {                    // tests: the sampled A_tilde as the multi-kernel bf16 plan stores it
+        uint4* d = reinterpret_cast<uint4*>(fa.a_dump + (int64_t)gi * fa.lda + kb * K2_BLOCK_K);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) d[c] = make_uint4(pw[4 * c], pw[4 * c + 1], pw[4 * c + 2], pw[4 * c + 3]);
       }
     }
   }
+  {
+    // deg = integer row count (exact), r = deg^-1/2 with IEEE sqrt / divide like the reference; operand (r P1)^T as bf16 hi/lo
+    const int nr = r_hi - r_lo;
+    for (int idx = tid; idx < nr * FS_HP; idx += K2_THREADS) {
+      const int c = idx / nr, i = r_lo + (idx - c * nr);
+      const float d = (float)__ldcg(fa.k1.cnt + i);
+      const float ri = 1.0f / sqrtf(d);
+      if (c == 0) { fa.deg[i] = d; fa.rs[i] = ri; }
+      if (c < ea.h) {
+        __nv_bfloat16 bh, bl;
+        split_bf16(ri * ea.p1[(int64_t)c * ea.ldr + i], bh, bl);
+        ea.bt_hi[(int64_t)c * ea.ldb + i] = bh;
+        ea.bt_lo[(int64_t)c * ea.ldb + i] = bl;
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nr; idx += K2_THREADS) fa.k1.cnt[r_lo + idx] = 0;      // re-arm the row counters (this CTA is their only reader)
+    if (tid == 0) sh_rowpair = 0;
+  }
+  fence_proxy_async_smem();                                  // generic-proxy smem writes -> visible to tcgen05.mma
   stamp(3);
-  grid_barrier(fa.gridbar, gbase, gk, gridDim.x);
+  grid_barrier(gbar, gbase, gk, gridDim.x);
   stamp(4);
 
   // ================= P2: the four propagations from the resident tiles =================
@@ -398,14 +388,14 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
       unsigned long long t;
       if (fa.timeline != nullptr) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); fa.timeline[(size_t)cta * 16 + 5 + 2 * ph] = t; }
     }
-    if (ph + 1 < fa.num_phases || smp + 1 < n_samples) grid_barrier(fa.gridbar, gbase, gk, gridDim.x);
+    if (ph + 1 < fa.num_phases || smp + 1 < n_samples) grid_barrier(gbar, gbase, gk, gridDim.x);
     stamp(6 + 2 * ph);
   }
   }   // graphs of a batched evaluation
 
   if (CLUSTER) cluster_sync_all();                           // nobody exits while the cluster leader still reads its shared memory
   if (fa.num_phases == 2) {                                  // forward only: nobody runs the BWD2 prologue that finalises (loss, acc)
-    grid_barrier(fa.gridbar, gbase, gk, gridDim.x);
+    grid_barrier(gbar, gbase, gk, gridDim.x);
     if (cta == 0 && tid == 0) finalize_scalars(ea);
   }
   tc_fence_before();

@@ -1,6 +1,7 @@
 // lds_fused_small.cuh — interface of the small-graph fused kernel (lds_fused_small.cu), used by lds_outer_step.cu.
 #pragma once
 #include "lds_epilogue.cuh"
+#include "lds_k1_tile.cuh"
 
 namespace lds {
 
@@ -8,12 +9,11 @@ constexpr int FS_MAX_TILES = 11;     // resident 128 x 64 A tiles per CTA (176 K
 constexpr int FS_HP = 16;            // padded operand width of all four propagations (h <= 16 and C <= 16)
 
 struct FusedSmallArgs {
-  // sampling (K1)
-  const float* theta; int64_t ldt; int n;
+  // sampling (K1): tile-symmetric, to bits (lds_k1_tile.cuh) — theta, explicit uniforms (parity mode), bits, row counters
+  // (int32 [n + 1]: zero on entry, zero again on return; the ticket lives behind them), chunk = 1
+  K1PArgs k1; int n;
   PhiloxRounds rounds;                         // edge stream of this (seed, step)
-  const float* u_explicit; int64_t ldu;        // parity mode, else NULL
   __nv_bfloat16* a_dump; int64_t lda;          // optional copy of A_tilde in global memory (tests), else NULL
-  float* deg_part;                             // [kblocks][ldr] per-tile row sums
   float* deg; float* rs;
   // feature GEMM
   const int32_t* crow; const int32_t* xcol; const float* xval; int f;
@@ -27,7 +27,7 @@ struct FusedSmallArgs {
   int kb_real;                                 // ceil(n / 64): k-blocks that exist
   int parts;                                   // CTAs per panel (= cluster size of the CLUSTER variant); set by the launcher
   float* partial; int* counters; int use_lo;
-  unsigned* gridbar;                           // {arrival count (zero between launches), generation}
+  unsigned* gridbar;                           // 16 bytes: {monotonic 64-bit arrival counter of the grid barrier, arrivals of the staged-weight split barrier (zero between launches), spare}
   unsigned long long* timeline;                // optional debug: [grid][16] %globaltimer stamps per CTA, else NULL
   EpiArgs ea;
 };

@@ -47,7 +47,7 @@ int32_t k1p_launch(const float* theta, int64_t ldt, int n, int row0, int rows, u
   a.u = u_explicit; a.ldu = ldu; a.bits = bits; a.kblocks = pk_kblocks(n); a.cnt = cnt;
   a.ticket = reinterpret_cast<unsigned*>(cnt + rows);
   static const int dbg = getenv("LDS_K1P_DEBUG") ? atoi(getenv("LDS_K1P_DEBUG")) : 0;
-  a.dbg = dbg; a.chunk = K1P_CHUNK;
+  a.dbg = dbg; a.chunk = K1P_CHUNK; a.prefetch = 0;
   const PhiloxRounds R = philox_rounds(philox_key(seed, step, LDS_STREAM_EDGES, sample));
   const int64_t total = (int64_t)a.my_tiles * a.nt - (int64_t)a.my_tiles * (a.my_tiles - 1) / 2;
   const int64_t want = ceil_div(total, (int64_t)K1P_CHUNK * (K1P_THREADS / 32));

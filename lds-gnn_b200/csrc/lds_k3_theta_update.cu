@@ -14,6 +14,7 @@
 // with sequential FMAs in k order; element (j,i) computes the same two chains swapped, and fp32 add/mul/fma are
 // commutative in their multiplicands, so theta_ij == theta_ji bit for bit (the row-block shards of a multi-GPU
 // run therefore stay consistent without any exchange).
+#include <stdlib.h>
 #include "lds_k3.cuh"
 #include "lds_tc.cuh"
 
@@ -174,8 +175,13 @@ constexpr int K3T_SMEM = K3T_OSTAGES * K3T_STAGE_BYTES + K3T_RING * K3T_SLAB_BYT
 // src/trainers/outer.py:78-83, src/models/graph.py:16-20).
 // `cj` = c_j of the slab's 32 columns (zero past n), staged through shared memory once per tile: the 224 KB carve-out
 // leaves almost no L1, and a cvec load issued per cell cost an L2 round trip each (45 % of the stall samples at N = 20 000).
+// MIRROR (tile-symmetric launch, tile strictly above the diagonal): the new values also go to the transposed tile,
+// theta[jb + c][gi] — for a fixed column c the 32 lanes of a warp hold 32 consecutive rows gi, i.e. one full 128-byte
+// line of the mirrored row: plain coalesced stores, no staging buffer (tdst = &theta[jb][gi], row stride ldt).
+template <bool MIRROR>
 __device__ __forceinline__ void k3_update_slab_row(uint8_t* slab, int row, const uint32_t (&d1)[32], const uint32_t (&d2)[32],
-                                                   const float* cj_s, bool interior, float ci, int gi, int jb, int n, float lr) {
+                                                   const float* cj_s, bool interior, float ci, int gi, int jb, int n, float lr,
+                                                   float* __restrict__ tdst = nullptr, int64_t ldt = 0) {
   if (interior) {
 #pragma unroll
     for (int c4 = 0; c4 < 8; ++c4) {
@@ -189,6 +195,7 @@ __device__ __forceinline__ void k3_update_slab_row(uint8_t* slab, int row, const
         float g = (__uint_as_float(d1[4 * c4 + b]) + __uint_as_float(d2[4 * c4 + b])) + (ci + cj[b]);
         if (tv[b] < 0.f || tv[b] > 1.f) g = 0.f;                 // clamp backward
         nv[b] = fminf(fmaxf(fmaf(-lr, g, tv[b]), 0.f), 1.f);
+        if (MIRROR) __stcs(tdst + (int64_t)(4 * c4 + b) * ldt, nv[b]);
       }
       *cell = make_float4(nv[0], nv[1], nv[2], nv[3]);
     }
@@ -208,15 +215,33 @@ __device__ __forceinline__ void k3_update_slab_row(uint8_t* slab, int row, const
         if (tv[b] < 0.f || tv[b] > 1.f) g = 0.f;
         const float nv = fminf(fmaxf(fmaf(-lr, g, tv[b]), 0.f), 1.f);
         if (gj + b < n) tv[b] = nv;               // the TMA store clips at 16-byte granularity: leave padding as loaded
+        if (MIRROR && gj + b < n) __stcs(tdst + (int64_t)(4 * c4 + b) * ldt, nv);
       }
       *cell = make_float4(tv[0], tv[1], tv[2], tv[3]);
     }
   }
 }
 
+// Tile (bi, bj) of linear index t. SYM: the upper triangle incl. the diagonal, row by row (bj >= bi).
+template <bool SYM>
+__device__ __forceinline__ void k3_tile_of(int t, int tiles_j, int& bi, int& bj) {
+  if (!SYM) { bi = t / tiles_j; bj = t - bi * tiles_j; return; }
+  const float bb = 2.0f * tiles_j + 1.0f;
+  bi = (int)((bb - sqrtf(bb * bb - 8.0f * (float)t)) * 0.5f);              // float estimate, then exact correction
+  bi = max(0, min(bi, tiles_j - 1));
+  while (bi > 0 && bi * tiles_j - bi * (bi - 1) / 2 > t) --bi;
+  while (bi + 1 < tiles_j && (bi + 1) * tiles_j - (bi + 1) * bi / 2 <= t) ++bi;
+  bj = bi + (t - (bi * tiles_j - bi * (bi - 1) / 2));
+}
+
+// SYM (unsharded update of a SYMMETRIC theta — the expansion of the reference's (T,) `probs`): only the tiles on and above
+// the diagonal are read and computed; a tile strictly above it is stored twice, as it is and transposed (k3_update_slab_row),
+// so the launch moves 6 N^2 bytes (2 read + 4 written) instead of 8 N^2. theta_ji is then a copy of theta_ij — the same bits
+// the full launch computes for it (D1(i,j) and D2(j,i) are the same products in the same order).
+template <bool SYM>
 __global__ void __launch_bounds__(K3T_THREADS, 1)
 k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant__ CUtensorMap tm_f,
-             const float* __restrict__ cvec, int n, int row0, int rows, int ksteps, float lr) {
+             const float* __restrict__ cvec, int n, int row0, int rows, int ksteps, float lr, float* __restrict__ theta, int64_t ldt) {
   __shared__ __align__(16) float cj_stage[2][64];            // c_j of the tile's columns, one half per epilogue warp group
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -234,7 +259,7 @@ k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_j = (n + K3T_TILE - 1) / K3T_TILE;
   const int tiles_i = (rows + K3T_TILE - 1) / K3T_TILE;
-  const int num_tiles = tiles_i * tiles_j;
+  const int num_tiles = SYM ? tiles_j * (tiles_j + 1) / 2 : tiles_i * tiles_j;
   const int t_lo = (int)(((int64_t)blockIdx.x * num_tiles) / gridDim.x);          // contiguous range: F_i stays hot in L2/L1
   const int t_hi = (int)(((int64_t)(blockIdx.x + 1) * num_tiles) / gridDim.x);
 
@@ -259,7 +284,8 @@ k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant
     if (lane == 0) {
       int oq = 0;
       for (int t = t_lo; t < t_hi; ++t) {
-        const int bi = t / tiles_j, bj = t - bi * tiles_j;
+        int bi, bj;
+        k3_tile_of<SYM>(t, tiles_j, bi, bj);
         for (int q = 0; q < ksteps; ++q, ++oq) {
           const int os = oq % K3T_OSTAGES;
           uint8_t* st = ops + os * K3T_STAGE_BYTES;
@@ -275,7 +301,8 @@ k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant
     if (lane == 0) {
       int q = 0;
       for (int t = t_lo; t < t_hi; ++t) {
-        const int bi = t / tiles_j, bj = t - bi * tiles_j;
+        int bi, bj;
+        k3_tile_of<SYM>(t, tiles_j, bi, bj);
         for (int s = 0; s < 4; ++s, ++q) {
           const int slot = q % K3T_RING;
           mbar_wait(&thempty[slot], (uint32_t)(((q / K3T_RING) & 1) ^ 1));
@@ -325,7 +352,8 @@ k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant
     int pending = -1;
     int tt = 0;
     for (int t = t_lo; t < t_hi; ++t, ++tt) {
-      const int bi = t / tiles_j, bj = t - bi * tiles_j;
+      int bi, bj;
+        k3_tile_of<SYM>(t, tiles_j, bi, bj);
       const int li0 = bi * K3T_TILE, gi0 = row0 + li0, j0 = bj * K3T_TILE;
       const int acc = tt & 1;
       const int gi = gi0 + row;
@@ -354,7 +382,11 @@ k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant
         const int jb = j0 + s * K3T_SLAB_COLS;
         mbar_wait(&thfull[slot], (uint32_t)((q / K3T_RING) & 1));
         tc_wait_ld();
-        k3_update_slab_row(slabs + slot * K3T_SLAB_BYTES + row * 128, row, d1, d2, &cj_stage[hf][32 * sl], interior, ci, gi, jb, n, lr);
+        if (SYM && bj > bi)
+          k3_update_slab_row<true>(slabs + slot * K3T_SLAB_BYTES + row * 128, row, d1, d2, &cj_stage[hf][32 * sl], interior, ci, gi, jb, n, lr,
+                                   theta + (int64_t)jb * ldt + gi, ldt);
+        else
+          k3_update_slab_row<false>(slabs + slot * K3T_SLAB_BYTES + row * 128, row, d1, d2, &cj_stage[hf][32 * sl], interior, ci, gi, jb, n, lr);
         fence_proxy_async_smem();                      // generic-proxy writes -> visible to the TMA store
         named_bar_sync(1 + hf, 128);                   // the four warps that own this slab
         if (storer) {
@@ -403,12 +435,18 @@ int32_t k3_launch_tc(float* theta, int64_t ldt, int n, int row0, int rows, const
   if ((rc = make_tmap_2d(&tf, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, f, kf, n, kf, K3T_KB, K3T_TILE)) != LDS_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    LDS_CHECK_CUDA(cudaFuncSetAttribute(k3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K3T_SMEM));
+    LDS_CHECK_CUDA(cudaFuncSetAttribute(k3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K3T_SMEM));
+    LDS_CHECK_CUDA(cudaFuncSetAttribute(k3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K3T_SMEM));
     attr_set = true;
   }
-  const int tiles = (int)(ceil_div(rows, K3T_TILE) * ceil_div(n, K3T_TILE));
+  // Unsharded: the tile-symmetric launch (theta is symmetric). LDS_K3_FULL=1: A/B switch, every tile computed and stored on its own.
+  static const bool force_full = getenv("LDS_K3_FULL") != nullptr;
+  const bool sym = !force_full && row0 == 0 && rows == n;
+  const int tj = (int)ceil_div(n, K3T_TILE);
+  const int tiles = sym ? tj * (tj + 1) / 2 : (int)(ceil_div(rows, K3T_TILE) * tj);
   const int grid = tiles < kNumSMsB200 ? tiles : kNumSMsB200;
-  k3_tc_kernel<<<grid, K3T_THREADS, K3T_SMEM, stream>>>(tth, tf, cvec, n, row0, rows, kf / K3T_KB, lr);
+  if (sym) k3_tc_kernel<true><<<grid, K3T_THREADS, K3T_SMEM, stream>>>(tth, tf, cvec, n, row0, rows, kf / K3T_KB, lr, theta, ldt);
+  else k3_tc_kernel<false><<<grid, K3T_THREADS, K3T_SMEM, stream>>>(tth, tf, cvec, n, row0, rows, kf / K3T_KB, lr, theta, ldt);
   LDS_CHECK_LAUNCH("k3_tc_kernel");
   return LDS_OK;
 }

@@ -15,6 +15,7 @@
 //   epi_bwd1      dP1 = r*., rho, kappa, c = -(rho+kappa)/(2 deg); factors fa = r(dZ1|dZ2), fb = r(P1|P2); loss/acc finalised
 //   K3+K4         theta <- clamp(theta - lr * g(fa, fb, c))                         lds_k3_theta_update.cu
 // The outer step needs no weight gradients (the reference computes and discards them), so X is read once.
+#include <stdlib.h>
 #include <string.h>
 #include "lds_epilogue.cuh"
 #include "lds_fused_small.cuh"
@@ -77,7 +78,7 @@ static bool make_layout(int n, int rows, int f, int h, int c, OuterLayout& L, bo
   bytes[B_LOSSP] = bytes[B_CORRP] = (int64_t)ceil_div(rows, K2_BLOCK_M) * 4;
   bytes[B_F] = (int64_t)n * L.kf * 2;                       // packed bf16 factor rows of the tensor-core update (all n rows: K3 needs F_j of every column)
   bytes[B_CNT] = (int64_t)ceil_div(rows, K2_BLOCK_M) * 4;     // per-panel arrival counters of the stream-K reduction
-  bytes[B_DEGP] = L.fused ? (int64_t)L.kb_real * L.ldr * 4 : 0;   // fused small-graph path: per-tile row sums
+  bytes[B_DEGP] = 0;                                        // (was: per-tile row sums of the fused small-graph path)
   bytes[B_GBAR] = 16;                                       // grid barrier of the fused small-graph kernel {count, generation}
   bytes[B_W0S] = (int64_t)h * round_up(f, 4) * 4;          // staged layer_in weight: transposed [f][h] (CSR path) or padded [h][ldx]
   int64_t o = 0;
@@ -442,14 +443,20 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   bool fused_done = false;
   const bool tc_update = A.opt_kind == LDS_OPT_SGD && !(A.k3_flags & LDS_K3_SIMT);
   if (!sharded && sparse_x && !(A.k2_flags & (LDS_K2_NO_FUSE | LDS_K2_FORCE_STREAMK | LDS_K2_SIMT)) &&
-      L.fused) {
+      L.fused && A.ld_theta >= round_up(A.n, 64)) {
     FusedSmallArgs F;
     memset(&F, 0, sizeof(F));
-    F.theta = A.theta_full; F.ldt = A.ld_theta; F.n = A.n;
+    F.n = A.n;
+    F.k1.theta = A.theta_full; F.k1.ldt = A.ld_theta; F.k1.n = A.n; F.k1.row0 = 0; F.k1.rows = A.n;
+    F.k1.nt = (int)ceil_div(A.n, 64); F.k1.lo_t = 0; F.k1.my_tiles = F.k1.nt;
+    F.k1.u = A.u_explicit; F.k1.ldu = A.ld_u;
+    F.k1.bits = reinterpret_cast<uint32_t*>(buf(B_BITS)); F.k1.kblocks = pk_kblocks(A.n);
+    F.k1.cnt = reinterpret_cast<int*>(buf(B_ROWCNT)); F.k1.ticket = nullptr;
+    static const int k1dbg = getenv("LDS_K1P_DEBUG") ? atoi(getenv("LDS_K1P_DEBUG")) : 0;   // measurement switches of lds_k1_tile.cuh
+    F.k1.chunk = 1; F.k1.dbg = k1dbg; F.k1.prefetch = 1;
     F.rounds = philox_rounds(philox_key(A.seed, A.step, LDS_STREAM_EDGES, smp));
-    F.u_explicit = A.u_explicit; F.ldu = A.ld_u;
     F.a_dump = (A.k2_flags & LDS_K2_DUMP_ADJ) ? reinterpret_cast<__nv_bfloat16*>(buf(B_A)) : nullptr; F.lda = L.lda;
-    F.deg_part = fbuf(B_DEGP); F.deg = fbuf(B_DEG); F.rs = fbuf(B_RS);
+    F.deg = fbuf(B_DEG); F.rs = fbuf(B_RS);
     F.crow = A.x_crow; F.xcol = A.x_col; F.xval = A.x_val; F.f = A.f;
     F.w0 = A.w0; F.ldw = A.ld_w0; F.w0t = fbuf(B_W0S); F.b0 = A.b0; F.dx = dx;
     F.num_phases = (A.k2_flags & LDS_K2_FORWARD_ONLY) ? 2 : 4;
