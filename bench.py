@@ -77,6 +77,15 @@ def load_peaks_json():
     return peaks()
 
 
+def bf16_peak_tflops():
+    """Dense bf16 tensor peak for a kernel timed inside a long step: the SUSTAINED cuBLAS figure of MEASURED_PEAKS.json."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh).get("bf16_tflops_sustained", 1397.8))
+    return 1397.8
+
+
 def ncu_traffic(workload, kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture of
     this workload (profiles/ncu_traffic.json, written by scripts/ncu_traffic.py from the .ncu-rep), or (None, None)."""
@@ -169,6 +178,26 @@ def make_workload(name, seed=0, knn_on_device=None):
     opt_mask = torch.zeros_like(data.val_mask)
     opt_mask[val_idx[len(val_idx) // 2:]] = True
     return data, weights, opt_mask, dict(n=n, f=f, c=c, h=h)
+
+
+def small_config(workload, shape, samples, world=1, replicas=False):
+    """`config` of a Citeseer / Cora shape line. Built by ONE function and worded arm-neutrally so that the repo arm and the
+    `--impl reference` arm print the same dict (the driver compares them)."""
+    n, f, c, h = shape["n"], shape["f"], shape["c"], shape["h"]
+    return {"workload": f"LDS-GCN direct outer step, {workload} shape (N={n}, F={f}, C={c}, hidden={h}), SGD lr 0.1 decay 0.99, "
+                        f"dropout 0.5, {samples} sample(s)/step" + (", theta_0 = kNN graph (k=10, cosine)" if samples > 1 else ""),
+            "parallelism": "one device per replica" + (f", {world} independent replicas" if (world > 1 and replicas) else ""),
+            "l2": "GPU arm: flushed between timed steps (256 MiB write); CPU reference arm: host caches as they are",
+            "theta_init": "kNN graph of the synthetic features" if samples > 1 else "synthetic SBM adjacency"}
+
+
+def large_config(n, f, h, c, world):
+    """`config` of an N = 20 000 / 65 536 line (same dict in both arms, see small_config)."""
+    return {"workload": f"LDS-GCN direct outer step, synthetic N={n} dense theta ~ U(0,1), F={f}, hidden={h}, C={c}, SGD lr 0.1 decay 0.99, "
+                        f"dropout 0.5, 1 sample/step",
+            "parallelism": "single GPU" if world == 1 else
+                           f"theta / A_tilde row-block sharded over {world} GPUs; per step 4 all-gathers of the N x h operand + packed factor rows + c",
+            "l2": "not flushed: per-GPU theta rows are %.1f GB, far larger than the 126 MB L2" % (n // world * n * 4 / 1e9)}
 
 
 def algorithmic_bytes(shape):
@@ -362,11 +391,9 @@ def run_ours(args, rank, world, device):
         "ms_per_step": round(dev_ms / args.steps, 5), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16 adjacency x (bf16 hi+lo) operands, fp32 accumulate; fp32 theta",
         "data": "synthetic",
-        "config": {"workload": f"LDS-GCN direct outer step, {args.workload} shape (N={n}, F={f}, C={c}, hidden={h}), SGD lr 0.1 decay 0.99, "
-                               f"dropout 0.5, {samples} sample(s)/step" + (", theta_0 = kNN graph (k=10, cosine)" if samples > 1 else ""),
-                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas",
-                   "l2": "flushed between timed steps (256 MiB write)",
-                   "theta_init": "kNN graph of the synthetic features" if samples > 1 else "synthetic SBM adjacency"},
+        "config": small_config(args.workload, shape, samples, world, args.replicas),
+        "scaling_note": "N > 1 lines (torchrun) run BASELINE config 5 (N=65536 row-block sharded, strong scaling): their like-for-like "
+                        "single-GPU figure is each line's scaling_reference, not this line",
         "clocks": clock_info,
         "e2e": {"value": round(total_steps / (e2e_ms / 1e3), 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
                 "api": "OuterProblemTrainer.train_step(InnerProblemTrainer.model_forward)", "l2": "not flushed"},
@@ -599,33 +626,48 @@ def run_large(args, rank, world, device, workload):
             torch.cuda.empty_cache()
         dist.barrier()
     hbm_peak, peak_src = peaks()
+    bf16_peak = bf16_peak_tflops()
     rows_local = cnt
-    alg = {0: 6 * rows_local * n, 3: 2 * rows_local * n, 4: 2 * rows_local * n, 5: 2 * rows_local * n, 6: 2 * rows_local * n,
-           7: 8 * rows_local * n}
+    packed = not os.environ.get("LDS_BF16_PLAN")               # the bit-packed plan is the default of every step this function times
+    hp1, hp2 = int(lib.lds_outer_step_operand_hp(h, c, _lib.PHASE_LAYER1)), int(lib.lds_outer_step_operand_hp(h, c, _lib.PHASE_LAYER2))
+    # Bytes each kernel of THIS launch plan has to move per launch on this rank. Bit-packed plan: sampling reads the
+    # rank's theta rows once per unordered tile pair (the rank's own diagonal block only once) and writes bits; a propagation
+    # reads the bits (it is tensor-bound: reported as TFLOP/s, hi + lo MMAs counted); the update is 6 N^2 unsharded
+    # (tile-symmetric: upper tiles read, both triangles written), 8 rows n for a row-block shard. SURVEY 8(d)'s bf16 figures
+    # (6 / 2 / 8 N^2) are kept next to them as `survey_bytes`.
+    k1_bytes = (4 * (rows_local * n - rows_local * rows_local // 2) + rows_local * n // 8) if packed else 6 * rows_local * n
+    k2_bytes = (rows_local * n // 8) if packed else 2 * rows_local * n
+    k3_bytes = 6 * n * n if world == 1 else 8 * rows_local * n
+    alg = {0: k1_bytes, 3: k2_bytes, 4: k2_bytes, 5: k2_bytes, 6: k2_bytes, 7: k3_bytes}
+    survey = {0: 6 * rows_local * n, 3: 2 * rows_local * n, 4: 2 * rows_local * n, 5: 2 * rows_local * n, 6: 2 * rows_local * n, 7: 8 * rows_local * n}
+    k2_flops = {3: 4 * rows_local * n * hp1, 6: 4 * rows_local * n * hp1, 4: 4 * rows_local * n * hp2, 5: 4 * rows_local * n * hp2}
     kernel_summary = {}
     for kid, vals in per_kernel.items():
         if kid < 0:
             kernel_summary["exchange_and_host_gaps"] = {"step_share_us": 1e3 * sum(vals) / reps}
             continue
-        entry = {"mean_us": 1e3 * sum(vals) / len(vals), "step_share_us": 1e3 * sum(vals) / reps}
+        mean_ms = sum(vals) / len(vals)
+        entry = {"mean_us": 1e3 * mean_ms, "step_share_us": 1e3 * sum(vals) / reps}
         if kid in alg:
-            entry["algorithmic_GBps"] = round(alg[kid] / (sum(vals) / len(vals) / 1e3) / 1e9, 1)
-            entry["frac_of_hbm_peak"] = round(entry["algorithmic_GBps"] / hbm_peak, 4)
+            entry["bytes"] = alg[kid]
+            entry["survey_bytes"] = survey[kid]
+            entry["GBps"] = round(alg[kid] / (mean_ms / 1e3) / 1e9, 1)
+            entry["frac_of_hbm_peak"] = round(entry["GBps"] / hbm_peak, 4)
+        if kid in k2_flops:
+            entry["tflops"] = round(k2_flops[kid] / (mean_ms / 1e3) / 1e12, 1)
+            entry["frac_of_bf16_peak"] = round(entry["tflops"] / bf16_peak, 4)
         kernel_summary[KERNEL_NAMES.get(kid, str(kid))] = entry
     cand = {k: v for k, v in per_kernel.items() if k in alg}
     dom = max(cand, key=lambda k: sum(cand[k]))
     mean_s = sum(cand[dom]) / len(cand[dom]) / 1e3
     achieved = alg[dom] / mean_s / 1e9
-    step_bytes = 22 * rows_local * n
+    step_bytes = sum(alg.values())
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
         "vs_baseline": None, "dtype": "bf16 adjacency x (bf16 hi+lo) operands, fp32 accumulate; fp32 theta", "data": "synthetic",
-        "config": {"workload": f"LDS-GCN direct outer step, synthetic N={n} dense theta ~ U(0,1), F={f}, hidden={h}, C={c}, SGD lr 0.1 decay 0.99, "
-                               f"dropout 0.5, 1 sample/step", "parallelism": "single GPU" if world == 1 else
-                               f"theta / A_tilde row-block sharded over {world} GPUs; per step 4 all-gathers of the N x h operand + packed factor rows + c "
-                               f"over {exchange}",
-                   "l2": "not flushed: per-GPU theta rows are %.1f GB, far larger than the 126 MB L2" % (rows_local * n * 4 / 1e9)},
+        "config": large_config(n, f, h, c, world),
+        "exchange": exchange if world > 1 else None,
         "clocks": clock_info,
         "e2e": {"value": round(args.steps / (e2e_ms / 1e3), 3), "unit": UNIT, "h2d_bytes_per_step": total * 4, "d2h_bytes_per_step": 8,
                 "api": "OuterProblemTrainer.train_step(InnerProblemTrainer.model_forward) on BernoulliGraphModel.from_row_block"},
@@ -640,7 +682,7 @@ def run_large(args, rank, world, device, workload):
         "scaling_reference": scaling_reference,
         "cpu_baseline": {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                          "sample": f"not runnable: the reference keeps ~25 dense N x N fp32 tensors ({25 * n * n * 4 / 1e9:.0f} GB) and does "
-                                   f"6 N^3 SGEMMs per step at N={n}; see --impl reference for the extrapolated figure"},
+                                   f"6 N^3 SGEMMs per step at N={n}"},
     }
     return line
 
@@ -667,23 +709,17 @@ def time_cpu_port(workload, steps, warmup):
 
 
 def run_reference_large(args, workload):
-    """The reference cannot run N >= 20 000 (25 dense N x N fp32 temporaries, 6 N^3 SGEMMs per step). Bounded sample: the
-    port's step on a Cora-shape sub-problem, extrapolated with its measured O(N^3) normalisation cost."""
+    """The reference cannot run N >= 20 000 (25 dense N x N fp32 temporaries, 6 N^3 SGEMMs per step): no value, and no
+    extrapolation either — a made-up denominator would only produce a made-up ratio."""
     from lds_gnn_b200.data import SHAPES
-    n = SHAPES[workload][0]
-    steps = max(2, min(args.steps, 3))
-    rate, ms, threads, shape, loss = time_cpu_port("cora", steps, 1)
-    scale = (shape["n"] / n) ** 3
-    value = rate * scale
-    cpu = {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-           "sample": f"{steps} outer steps of the port at Cora shape (N={shape['n']}: {ms:.0f} ms/step) x (N_s/N)^3 — EXTRAPOLATED, "
-                     f"the reference cannot hold N={n} in memory"}
-    return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": 1,
-            "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": f"LDS-GCN direct outer step, synthetic N={n} (extrapolated from N={shape['n']})",
-                                            "parallelism": "host CPU"},
-            "cpu_baseline": cpu, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "extrapolated": True}
+    n, f, c, h, _, _ = SHAPES[workload]
+    why = (f"the reference cannot run this config: ~25 dense N x N fp32 tensors ({25 * n * n * 4 / 1e9:.0f} GB) and 6 N^3 SGEMMs per "
+           f"step at N={n} on the host")
+    return {"impl": "reference", "metric": METRIC, "value": None, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": None, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": large_config(n, f, h, c, args.gpus), "unavailable": why,
+            "cpu_baseline": {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": why},
+            "e2e": {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
 
 
 def run_reference(args):
@@ -692,17 +728,16 @@ def run_reference(args):
         workload = "n65k"
     if workload in ("n20k", "n65k"):
         return run_reference_large(args, workload)
-    rate, ms, threads, shape, loss = time_cpu_port(args.workload, args.steps, max(1, min(args.warmup, 2)))
+    rate, ms, threads, shape, loss = time_cpu_port(args.workload, args.steps, args.warmup)
     samples = KNN_WORKLOADS[args.workload][2] if args.workload in KNN_WORKLOADS else 1
     rate, ms = rate / samples, ms * samples                  # the port runs single-sample steps: an S-sample step is S of them
     cpu = {"value": round(rate, 4), "unit": UNIT, "cores": threads, "kind": "port",
            "sample": f"{args.steps} full single-sample outer steps of the same workload (oracle/reference_port.py, torch CPU, {threads} threads)"
                      + (f", rate divided by {samples} samples per outer step" if samples > 1 else "")}
     return {"impl": "reference", "metric": METRIC, "value": round(rate, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": max(1, min(args.warmup, 2)), "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"LDS-GCN direct outer step, {args.workload} shape (N={shape['n']}, F={shape['f']}, C={shape['c']}, "
-                                   f"hidden={shape['h']}), SGD lr 0.1 decay 0.99, dropout 0.5, {samples} sample(s)/step", "parallelism": "host CPU"},
+            "config": small_config(args.workload, shape, samples, args.gpus, args.replicas),
             "cpu_baseline": cpu, "e2e": {"value": round(rate, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "final_loss": loss}
 

@@ -140,7 +140,14 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
     if (fa.timeline != nullptr && tid == 0) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      fa.timeline[(size_t)cta * 16 + k] = t;
+      fa.timeline[(size_t)cta * 32 + k] = t;
+    }
+  };
+  auto stamp_any = [&](int k) {                               // the calling thread stamps (finer phase breakdown)
+    if (fa.timeline != nullptr) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      fa.timeline[(size_t)cta * 32 + k] = t;
     }
   };
   stamp(0);
@@ -313,6 +320,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
         // products land in columns 0-15 / 16-31 of the accumulator and are added by the drain
         const uint32_t idesc = fa.use_lo ? umma_idesc_bf16(K2_BLOCK_M, 2 * FS_HP) : umma_idesc_bf16(K2_BLOCK_M, FS_HP);
         mbar_wait(bfull, bfull_uses & 1u);
+        stamp_any(16 + 4 * ph);                              // operand k-blocks landed
         mbar_wait(&tempty_bar[acc_m], acc_phase_m ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc_m * 2 * FS_HP);
@@ -335,6 +343,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
       if (ph == 2 && cta == 0 && tid == 64) finalize_scalars(ea);   // the layer-2 phase is complete: (loss, acc)
       mbar_wait(&tfull_bar[acc_e], acc_phase_e);
       tc_fence_after();
+      if (tid == 64) stamp_any(17 + 4 * ph);                 // accumulator complete
       const int quarter = warp & 3, row = quarter * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc_e * 2 * FS_HP);
       uint32_t t16[16], u16[16];
@@ -355,6 +364,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
     }
     if (CLUSTER) {
       cluster_sync_all();                                      // every CTA's partial tile is in its shared memory
+      if (tid == 64) stamp_any(18 + 4 * ph);
       if (cluster_ctarank() == 0 && warp >= 2) {
         const int etid = tid - 64, row = etid >> 2, g = etid & 3;    // four threads per row, a quarter of the columns each
         const uint32_t mine = smem_u32(sb) + (uint32_t)(row * FS_HP + g * 4) * 4u;
@@ -366,6 +376,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
         for (int r = 0; r < 8; ++r) if (r < fa.parts) { v[0] += t[r].x; v[1] += t[r].y; v[2] += t[r].z; v[3] += t[r].w; }
         const int i = my_p * K2_BLOCK_M + row;
         const bool alt = ((ph + 1) & 1) != 0;
+        if (tid == 64) stamp_any(19 + 4 * ph);               // partial tiles summed over distributed shared memory
         if (ph == 0) epi_layer1<FS_HP>(ea, i, g, v, alt);
         else if (ph == 2) epi_bwd2<FS_HP>(ea, i, g, v, alt);
         else if (ph == 3) epi_bwd1<FS_HP>(ea, i, g, v);
@@ -386,7 +397,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
     }
     if (tid == 64) {                                           // first epilogue thread: its loop is done
       unsigned long long t;
-      if (fa.timeline != nullptr) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); fa.timeline[(size_t)cta * 16 + 5 + 2 * ph] = t; }
+      if (fa.timeline != nullptr) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); fa.timeline[(size_t)cta * 32 + 5 + 2 * ph] = t; }
     }
     if (ph + 1 < fa.num_phases || smp + 1 < n_samples) grid_barrier(gbar, gbase, gk, gridDim.x);
     stamp(6 + 2 * ph);

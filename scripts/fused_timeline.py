@@ -32,12 +32,12 @@ if cold:
     torch.cuda.synchronize()
 eng.run(theta, lr=0.1, seed=1, step=99, dropout_p=0.5, k2_timeline=tl, want_adj=False)
 torch.cuda.synchronize()
-t = tl.cpu().numpy().astype(np.float64).reshape(-1)[:148 * 16].reshape(148, 16)
+t = tl.cpu().numpy().astype(np.float64).reshape(-1)[:148 * 32].reshape(148, 32)
 act = t[:, 0] > 0
 t = t[act]
 t0 = t[:, 0].min()
-names = ["start", "sampled", "barrier1", "feat_done", "barrier2", "epi0_done", "after0", "epi1_done", "after1", "epi2_done", "after2", "epi3_done", "end", "tiles_done(warp0)"]
+names = ["start", "sampled", "barrier1", "feat_done", "barrier2", "epi0_done", "after0", "epi1_done", "after1", "epi2_done", "after2", "epi3_done", "end", "tiles_done(warp0)", "", ""] + [f"ph{p}_{w}" for p in range(4) for w in ("operand_landed", "acc_ready", "cluster_synced", "dsmem_summed")]
 print(f"{act.sum()} CTAs")
 for j, nm in enumerate(names):
     col = t[:, j]; col = col[col > 0]
-    if len(col): print(f"   {nm:12s} n={len(col):4d}  min {(col.min()-t0)/1e3:7.2f} us  median {(np.median(col)-t0)/1e3:7.2f}  max {(col.max()-t0)/1e3:7.2f}")
+    if len(col) and nm: print(f"   {nm:12s} n={len(col):4d}  min {(col.min()-t0)/1e3:7.2f} us  median {(np.median(col)-t0)/1e3:7.2f}  max {(col.max()-t0)/1e3:7.2f}")
