@@ -156,6 +156,25 @@ int64_t lds_gram_tn_workspace_bytes(int32_t a, int32_t b);
 int32_t lds_gram_tn(const float* a_mat, int64_t lda, int32_t a, const float* b_mat, int64_t ldb, int32_t b, int64_t n_rows,
                     float* out, int64_t ldo, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- differentiable Adam of the unrolled inner problem (higher.optim.DifferentiableAdam as the reference drives it,
+ * src/trainers/inner.py:6, 42-50, 71; src/trainers/bilevel.py:53-73), over the flat parameter vector, ONE launch per step:
+ *   g2 = g + wd p;  m' = m + (1 - b1)(g2 - m);  v' = b2 v + (1 - b2) g2^2;
+ *   p' = p - step_size m' / (sqrt(max(v', 1e-30)) root_scale + eps)      step_size = lr / (1 - b1^t), root_scale = 1 / sqrt(1 - b2^t)
+ * and the vector-Jacobian product of that elementwise map as one launch (what the hyper step's backward needs of it; the
+ * second-order terms of the hypergradient live in g's own graph). step_size / root_scale are taken from device memory when
+ * step_size_dev / root_scale_dev are non-NULL (a captured CUDA graph must not bake the step count in), else by value.
+ * weight_decay_vec (per-element weight decay: the reference decays layer_in only, inner.py:42-46) overrides weight_decay when non-NULL.
+ * Backward: grad_m_out / grad_v_out may be NULL (= 0); any of dp, dm, dv, dg may be NULL (not needed). No aliasing. */
+int32_t lds_adam_step(const float* p, const float* m, const float* v, const float* g, int64_t n,
+                      float weight_decay, const float* weight_decay_vec, float beta1, float beta2, float eps,
+                      float step_size, float root_scale, const float* step_size_dev, const float* root_scale_dev,
+                      float* p_out, float* m_out, float* v_out, void* stream);
+int32_t lds_adam_step_backward(const float* grad_p_out, const float* grad_m_out, const float* grad_v_out,
+                               const float* p, const float* m, const float* v, const float* g, int64_t n,
+                               float weight_decay, const float* weight_decay_vec, float beta1, float beta2, float eps,
+                               float step_size, float root_scale, const float* step_size_dev, const float* root_scale_dev,
+                               float* dp, float* dm, float* dv, float* dg, void* stream);
+
 /* ---- K3+K4 (a10's theta part, a11): closed-form straight-through gradient + optimiser step + projection
  * for rows [row0, row0+rows):   g_ij = fa_i.fb_j + fb_i.fa_j + c_i + c_j  (i != j),  0 on the diagonal,
  * masked where theta is outside [0,1] (clamp backward), then

@@ -37,6 +37,11 @@ SIGNATURES = {
                                c_void_p, c_int64, c_void_p]),
     "lds_row_linear": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "lds_gram_tn_workspace_bytes": (c_int64, [c_int32, c_int32]),
+    "lds_adam_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_float, c_float, c_float, c_float, c_float,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lds_adam_step_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                         c_float, c_void_p, c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lds_gram_tn": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "lds_packed_adj_bytes": (c_int64, [c_int32, c_int32]),
     "lds_k1_sample_packed": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_uint64, c_uint64, c_uint32, c_void_p, c_int64,

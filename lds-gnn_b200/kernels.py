@@ -254,6 +254,40 @@ def gram_tn(a, b):
     return out
 
 
+def _scalar_or_ptr(x):
+    """(by-value float, device pointer or None) of a hyper-parameter given as a python float or a 1-element device tensor."""
+    if isinstance(x, torch.Tensor):
+        return 0.0, x.data_ptr()
+    return float(x), None
+
+
+def adam_step(p, m, v, g, wd, b1, b2, eps, step_size, root_scale):
+    """One out-of-place Adam step over flat fp32 vectors (csrc/lds_adam.cu). step_size / root_scale: floats or 1-element
+    device tensors (both of the same kind); wd: a float or a per-element fp32 vector. Returns (p', m', v')."""
+    _lib.require_device()
+    outs = [torch.empty_like(p) for _ in range(3)]
+    ss, ssp = _scalar_or_ptr(step_size)
+    rs, rsp = _scalar_or_ptr(root_scale)
+    wdv, wdp = _scalar_or_ptr(wd)                             # a per-element vector (parameter groups) or one float
+    _lib.check(_lib.load().lds_adam_step(_ptr(p), _ptr(m), _ptr(v), _ptr(g), p.numel(), wdv, wdp, float(b1), float(b2), float(eps),
+                                         ss, rs, ssp, rsp, _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _stream()), "lds_adam_step")
+    return outs
+
+
+def adam_step_backward(gp, gm, gv, p, m, v, g, wd, b1, b2, eps, step_size, root_scale, need):
+    """Vector-Jacobian product of adam_step: upstream (gp, gm, gv) (gm / gv may be None) -> (dp, dm, dv, dg), None where `need` is False."""
+    _lib.require_device()
+    outs = [torch.empty_like(p) if flag else None for flag in need]
+    ss, ssp = _scalar_or_ptr(step_size)
+    rs, rsp = _scalar_or_ptr(root_scale)
+    wdv, wdp = _scalar_or_ptr(wd)
+    opt = lambda t: None if t is None else _ptr(t)
+    _lib.check(_lib.load().lds_adam_step_backward(opt(gp), opt(gm), opt(gv), _ptr(p), _ptr(m), _ptr(v), _ptr(g), p.numel(),
+                                                  wdv, wdp, float(b1), float(b2), float(eps), ss, rs, ssp, rsp,
+                                                  opt(outs[0]), opt(outs[1]), opt(outs[2]), opt(outs[3]), _stream()), "lds_adam_step_backward")
+    return outs
+
+
 # ----------------------------------------------------------------------------- K3 + K4
 def k3k4_theta_update_(theta_full, n, fa, fb, cvec, lr, d=None, opt_kind=_lib.OPT_SGD, adam_m=None, adam_v=None,
                        betas=(0.9, 0.999), eps=1e-8, t=1, row0=0, rows=None):

@@ -21,6 +21,34 @@ import numpy as np
 import torch
 
 
+class _FusedAdamStep(torch.autograd.Function):
+    """(p, m, v, g) -> (p', m', v') as one launch (csrc/lds_adam.cu) instead of ~12 elementwise kernels, and its backward as one
+    instead of ~22. The map is elementwise, so the hyper step needs only its first-order vector-Jacobian product here: the
+    second-order terms of the hypergradient come from g's own graph (autograd.grad(..., create_graph=True))."""
+
+    @staticmethod
+    def forward(ctx, p, m, v, g, wd, b1, b2, eps, step_size, root_scale):
+        from .. import kernels
+        p, m, v, g = (t.contiguous() for t in (p, m, v, g))
+        ctx.set_materialize_grads(False)                       # an unused output (the last step's state) arrives as None, not as zeros
+        ctx.save_for_backward(p, m, v, g)
+        ctx.hyper = (wd, b1, b2, eps, step_size, root_scale)
+        new_p, new_m, new_v = kernels.adam_step(p, m, v, g, wd, b1, b2, eps, step_size, root_scale)
+        return new_p, new_m, new_v
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gp, gm, gv):
+        from .. import kernels
+        p, m, v, g = ctx.saved_tensors
+        as_c = lambda t: None if t is None else t.contiguous()
+        dp, dm, dv, dg = kernels.adam_step_backward(as_c(gp), as_c(gm), as_c(gv), p, m, v, g, *ctx.hyper, need=ctx.needs_input_grad[:4])
+        return dp, dm, dv, dg, None, None, None, None, None, None
+
+
+FUSED_STEP = [True]            # CUDA fp32, one parameter group's hyper-parameters, every parameter has a gradient: one launch per step
+
+
 class DifferentiableAdam:
     def __init__(self, optimizer: torch.optim.Adam, reference_params: Iterable[torch.Tensor], track_higher_grads: bool = True):
         reference = list(reference_params)
@@ -83,21 +111,29 @@ class DifferentiableAdam:
             st["exp_avg_sq"] = torch.zeros_like(p)
         st["step"] += 1
         t = st["step"]
+        fused = (FUSED_STEP[0] and p.is_cuda and p.dtype == torch.float32 and not any(unused) and isinstance(hp["in_group"], float)
+                 and all(isinstance(hp[k], float) for k in ("b1", "b2", "eps", "lr")))       # weight decay may differ per group (a vector)
+        g_raw = g
         # fused forms (add / addcmul / lerp): a third of the launches of the textbook expressions, same derivatives
-        if isinstance(hp["wd"], float):
+        if fused:
+            pass
+        elif isinstance(hp["wd"], float):
             if hp["wd"] != 0.0:
                 g = torch.add(g, p, alpha=hp["wd"])
         else:
             g = torch.addcmul(g, hp["wd"], p)
         b1, b2 = hp["b1"], hp["b2"]
-        if isinstance(b1, float) and isinstance(b2, float):
+        if fused:
+            m = v = root = None
+        elif isinstance(b1, float) and isinstance(b2, float):
             m = torch.lerp(st["exp_avg"], g, 1 - b1)
             v = torch.addcmul(st["exp_avg_sq"] * b2, g, g, value=1 - b2)
         else:
             m = st["exp_avg"] * b1 + (1 - b1) * g
             v = st["exp_avg_sq"] * b2 + (1 - b2) * (g * g)
         # sqrt has an infinite derivative at 0: floor exact zeros (higher masks that gradient instead)
-        root = v.clamp_min(1e-30).sqrt()
+        if not fused:
+            root = v.clamp_min(1e-30).sqrt()
         if self.device_step is not None:
             self.device_offset += 1
             if not (isinstance(b1, float) and isinstance(b2, float)):
@@ -123,7 +159,10 @@ class DifferentiableAdam:
             step_size = hp["lr"] / (1 - torch.as_tensor(b1) ** t)
             root_scale = 1.0 / torch.sqrt(1 - torch.as_tensor(b2) ** t)
         # higher master / torch.optim.Adam: the bias correction scales sqrt(v) BEFORE eps is added
-        new_p = p - step_size * (m / (root * root_scale + hp["eps"]))
+        if fused:
+            new_p, m, v = _FusedAdamStep.apply(p, st["exp_avg"], st["exp_avg_sq"], g_raw, hp["wd"], b1, b2, hp["eps"], step_size, root_scale)
+        else:
+            new_p = p - step_size * (m / (root * root_scale + hp["eps"]))
         frozen = None
         if any(unused) or not isinstance(hp["in_group"], float):
             # parameters without a gradient (or outside every group) keep value and state, like torch.optim.Adam

@@ -163,3 +163,51 @@ def test_capture_failure_falls_back_to_the_step_by_step_loop_with_state_intact(m
     assert (pb - pe).abs().max().item() < 1e-6
     for key in rb:
         assert abs(rb[key] - re_[key]) < 1e-5
+
+
+@pytest.mark.parametrize("wd,on_device", [(5e-4, False), (0.0, True), ("vector", True)])
+def test_fused_adam_step_matches_the_elementwise_form_and_its_autograd(wd, on_device):
+    """lds_adam_step / lds_adam_step_backward (one launch each) against the same update written as differentiable fp64 torch
+    ops — values and the vector-Jacobian product the hyper step takes through it (src/trainers/inner.py:42-50 over higher's
+    Adam), incl. entries whose second moment is floored, hyper-parameters by value and from device memory."""
+    from lds_gnn_b200.trainers.diffopt import _FusedAdamStep
+    torch.manual_seed(7)
+    n = 70_001
+    b1, b2, eps, step_size, root_scale = 0.9, 0.999, 1e-8, 0.0123, 3.7
+    p = torch.randn(n, device=CUDA)
+    m = torch.randn(n, device=CUDA) * 0.1
+    v = torch.rand(n, device=CUDA) * 1e-2 + 1e-3                              # (a vanishing second moment makes the map ill-conditioned in fp32)
+    g = torch.randn(n, device=CUDA) * 0.3
+    if isinstance(wd, float) and wd == 0.0:
+        v[:64] = 0.0; g[:64] = 0.0                                            # v' == 0: the floored branch (no gradient through sqrt)
+    ups = [torch.randn(n, device=CUDA) for _ in range(3)]
+    if wd == "vector":                                                        # weight decay on the first "layer" only (parameter groups)
+        wd = torch.zeros(n, device=CUDA); wd[: n // 2] = 5e-3
+    wd64 = wd.double() if isinstance(wd, torch.Tensor) else wd
+
+    def reference(p, m, v, g):
+        g2 = g + wd64 * p
+        mn = m + (1 - b1) * (g2 - m)
+        vn = b2 * v + (1 - b2) * g2 * g2
+        root = vn.clamp_min(1e-30).sqrt()
+        return p - step_size * mn / (root * root_scale + eps), mn, vn
+
+    ins64 = [x.double().requires_grad_(True) for x in (p, m, v, g)]
+    outs64 = reference(*ins64)
+    grads64 = torch.autograd.grad(outs64, ins64, [u.double() for u in ups])
+    ins = [x.clone().requires_grad_(True) for x in (p, m, v, g)]
+    ss = torch.tensor([step_size], device=CUDA) if on_device else step_size
+    rs = torch.tensor([root_scale], device=CUDA) if on_device else root_scale
+    outs = _FusedAdamStep.apply(*ins, wd, b1, b2, eps, ss, rs)
+    for a, b in zip(outs, outs64):
+        assert (a.double() - b).abs().max().item() <= 2e-6 * max(1.0, b.abs().max().item())
+    grads = torch.autograd.grad(outs, ins, ups)
+    for a, b in zip(grads, grads64):
+        assert torch.isfinite(a).all()
+        # fp32 against fp64: relative to the entry (tiny second moments give gradients ~ 1e4) plus an absolute term for entries whose
+        # two contributions (through m' and through v') cancel
+        assert ((a.double() - b).abs() <= 3e-5 * b.abs() + 1e-4 * b.abs().mean()).all()
+    # only p' used downstream (the last step of an unroll): the state gradients arrive as None
+    (gp_only,) = torch.autograd.grad(_FusedAdamStep.apply(*ins, wd, b1, b2, eps, ss, rs)[0], ins[3], ups[0])
+    (ref_only,) = torch.autograd.grad(reference(*ins64)[0], ins64[3], ups[0].double())
+    assert ((gp_only.double() - ref_only).abs() <= 3e-5 * ref_only.abs() + 1e-4 * ref_only.abs().mean()).all()
