@@ -156,6 +156,24 @@ int64_t lds_gram_tn_workspace_bytes(int32_t a, int32_t b);
 int32_t lds_gram_tn(const float* a_mat, int64_t lda, int32_t a, const float* b_mat, int64_t ldb, int32_t b, int64_t n_rows,
                     float* out, int64_t ldo, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- row-local pieces of the unrolled inner steps (csrc/lds_rowops.cu).
+ * Masked NLL of log-softmax ON THE LOGITS z [n][ld_z] (c classes): F.nll_loss(log_softmax(z)[mask], y[mask]) and the accuracy
+ * (src/models/gcn.py:34, src/trainers/inner.py:63-66, src/trainers/outer.py:65-67) -> out_loss_acc[2]; its gradient w.r.t. z
+ * (dense [n][c], zero outside the mask, scaled by the device scalar *grad_loss); and the backward of that gradient given u =
+ * upstream of dz: out_z (may be NULL) and the per-row terms of the gradient w.r.t. *grad_loss (out_g_rows [n], may be NULL; the
+ * caller sums them). rows [m] = global rows of the mask (int64), slot [n] = position among them or -1, y [n] labels (int64).
+ * lds_row_dot2: out[i] = (<a1_i, b1_i> + <a2_i, b2_i>) / r[i] — the gradient of the normalised propagation w.r.t.
+ * r = deg^-1/2 (src/utils/graph.py:148-152), all four [n][ld] with w used columns. */
+int32_t lds_masked_nll_forward(const float* z, int64_t ld_z, int32_t c, const int64_t* rows, const int64_t* y, int32_t m,
+                               float* out_loss_acc, void* stream);
+int32_t lds_masked_nll_grad(const float* z, int64_t ld_z, int32_t c, const int32_t* slot, const int64_t* y, int32_t n, int32_t m,
+                            const float* grad_loss, float* dz, int64_t ld_dz, void* stream);
+int32_t lds_masked_nll_grad_grad(const float* u, int64_t ld_u, const float* z, int64_t ld_z, int32_t c, const int32_t* slot,
+                                 const int64_t* y, int32_t n, int32_t m, const float* grad_loss,
+                                 float* out_z, int64_t ld_out, float* out_g_rows, void* stream);
+int32_t lds_row_dot2(const float* a1, const float* b1, const float* a2, const float* b2, int64_t ld, int32_t w,
+                     const float* r, int32_t n, float* out, void* stream);
+
 /* ---- differentiable Adam of the unrolled inner problem (higher.optim.DifferentiableAdam as the reference drives it,
  * src/trainers/inner.py:6, 42-50, 71; src/trainers/bilevel.py:53-73), over the flat parameter vector, ONE launch per step:
  *   g2 = g + wd p;  m' = m + (1 - b1)(g2 - m);  v' = b2 v + (1 - b2) g2^2;

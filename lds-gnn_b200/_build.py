@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "liblds_b200.so")
-SOURCES = ["lds_common.cu", "lds_k1_sample.cu", "lds_k2_propagate.cu", "lds_k3_theta_update.cu", "lds_fused_small.cu", "lds_outer_step.cu", "lds_spmm.cu", "lds_skinny.cu", "lds_theta0.cu", "lds_k1_packed.cu", "lds_k2_packed.cu", "lds_adam.cu"]
+SOURCES = ["lds_common.cu", "lds_k1_sample.cu", "lds_k2_propagate.cu", "lds_k3_theta_update.cu", "lds_fused_small.cu", "lds_outer_step.cu", "lds_spmm.cu", "lds_skinny.cu", "lds_theta0.cu", "lds_k1_packed.cu", "lds_k2_packed.cu", "lds_adam.cu", "lds_rowops.cu"]
 
 
 def nvcc_path():

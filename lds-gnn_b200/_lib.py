@@ -37,6 +37,11 @@ SIGNATURES = {
                                c_void_p, c_int64, c_void_p]),
     "lds_row_linear": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "lds_gram_tn_workspace_bytes": (c_int64, [c_int32, c_int32]),
+    "lds_masked_nll_forward": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
+    "lds_masked_nll_grad": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
+    "lds_masked_nll_grad_grad": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_void_p,
+                                           c_void_p, c_int64, c_void_p, c_void_p]),
+    "lds_row_dot2": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
     "lds_adam_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_float, c_float, c_float, c_float, c_float,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lds_adam_step_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,

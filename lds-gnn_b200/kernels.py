@@ -254,6 +254,47 @@ def gram_tn(a, b):
     return out
 
 
+def masked_nll_forward(z, rows, y):
+    """(loss, acc) device tensor [2] of F.nll_loss(log_softmax(z)[rows], y[rows]) on the logits z [n, c] (csrc/lds_rowops.cu)."""
+    _lib.require_device()
+    z = _f32(z, "z")
+    out = torch.empty(2, dtype=torch.float32, device=z.device)
+    _lib.check(_lib.load().lds_masked_nll_forward(_ptr(z), z.stride(0), int(z.shape[1]), _ptr(rows), _ptr(y), int(rows.numel()), _ptr(out), _stream()),
+               "lds_masked_nll_forward")
+    return out
+
+
+def masked_nll_grad(z, slot, y, m, grad_loss):
+    """d loss / d z, dense [n, c] (zero rows outside the mask), scaled by the device scalar grad_loss."""
+    _lib.require_device()
+    dz = torch.empty((z.shape[0], z.shape[1]), dtype=torch.float32, device=z.device)
+    _lib.check(_lib.load().lds_masked_nll_grad(_ptr(z), z.stride(0), int(z.shape[1]), _ptr(slot), _ptr(y), int(z.shape[0]), int(m),
+                                               _ptr(grad_loss), _ptr(dz), dz.stride(0), _stream()), "lds_masked_nll_grad")
+    return dz
+
+
+def masked_nll_grad_grad(u, z, slot, y, m, grad_loss, want_z=True, want_g=False):
+    """Backward of masked_nll_grad given u = upstream of dz: (gradient w.r.t. z or None, per-row terms of the gradient w.r.t. grad_loss or None)."""
+    _lib.require_device()
+    n, c = z.shape
+    out_z = torch.empty((n, c), dtype=torch.float32, device=z.device) if want_z else None
+    out_g = torch.empty(n, dtype=torch.float32, device=z.device) if want_g else None
+    _lib.check(_lib.load().lds_masked_nll_grad_grad(_ptr(u), u.stride(0), _ptr(z), z.stride(0), int(c), _ptr(slot), _ptr(y), int(n), int(m),
+                                                    _ptr(grad_loss), None if out_z is None else _ptr(out_z), c,
+                                                    None if out_g is None else _ptr(out_g), _stream()), "lds_masked_nll_grad_grad")
+    return out_z, out_g
+
+
+def row_dot2(a1, b1, a2, b2, r):
+    """out[i] = (<a1_i, b1_i> + <a2_i, b2_i>) / r[i] for contiguous fp32 [n, w] operands."""
+    _lib.require_device()
+    n, w = a1.shape
+    out = torch.empty(n, dtype=torch.float32, device=a1.device)
+    _lib.check(_lib.load().lds_row_dot2(_ptr(a1), _ptr(b1), _ptr(a2), _ptr(b2), a1.stride(0), int(w), _ptr(r), int(n), _ptr(out), _stream()),
+               "lds_row_dot2")
+    return out
+
+
 def _scalar_or_ptr(x):
     """(by-value float, device pointer or None) of a hyper-parameter given as a python float or a 1-element device tensor."""
     if isinstance(x, torch.Tensor):

@@ -235,7 +235,13 @@ class _FactoredPropagate(torch.autograd.Function):
         if not torch.is_grad_enabled():
             fg.sink.add_outer(dz.detach(), q.detach(), r.detach())
         dq = _FactoredPropagate.apply(dz, r, fg.link, fg) if (need_q or need_r) else None
-        dr = torch.addcmul(dz * z, dq, q).sum(dim=1) / r if need_r else None
+        dr = None
+        if need_r:
+            if dz.is_cuda and dz.dtype == torch.float32 and dz.dim() == 2:
+                from .. import kernels                       # one launch instead of mul, addcmul, sum, div (need_r only holds in the
+                dr = kernels.row_dot2(dz.contiguous(), z, dq.contiguous(), q, r)      # plain hypergradient pass: nothing differentiates this)
+            else:
+                dr = torch.addcmul(dz * z, dq, q).sum(dim=1) / r
         return (dq if need_q else None), dr, None, None
 
 

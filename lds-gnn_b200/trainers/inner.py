@@ -17,6 +17,7 @@ from torch.optim import Adam
 from ..models.gcn import MetaDenseGCN, double_backward_path
 from ..utils.evaluation import accuracy
 from ..utils.graph import DenseData, is_square_matrix
+from ..utils.rowops import MaskInfo, fused_nll_ok, masked_nll
 from . import Metrics
 from .diffopt import DifferentiableAdam
 
@@ -51,25 +52,20 @@ class InnerProblemTrainer:
         return copy_detach_parameter_dict(self.model_params)
 
     def _masked_rows(self, mask: torch.Tensor):
-        """(row indices, labels) of a boolean node mask, cached: `tensor[bool_mask]` costs a device->host sync per use."""
+        """(row indices, their labels, MaskInfo) of a boolean node mask, cached: `tensor[bool_mask]` costs a device->host sync per use."""
         key = (mask.data_ptr(), mask._version, self.data.y.data_ptr())
         hit = self._rows_cache.get(key)
         if hit is None:
-            rows = mask.nonzero().flatten()
-            hit = self._rows_cache[key] = (rows, self.data.y[rows], mask)       # the mask is kept alive with its key
+            info = MaskInfo(mask, self.data.y)
+            hit = self._rows_cache[key] = (info.rows, info.selected_labels, mask, info)       # the mask is kept alive with its key
             if len(self._rows_cache) > 8:
                 self._rows_cache.pop(next(iter(self._rows_cache)))
-        return hit[0], hit[1]
+        return hit[0], hit[1], hit[3]
 
     def train_step(self, graph: torch.Tensor, mask: torch.Tensor = None) -> Metrics:
         """One differentiable optimiser step on the training nodes (inner.py:55-74). One host sync: (loss, acc) together."""
         assert is_square_matrix(graph)
-        with double_backward_path():
-            predictions = self.model_forward(graph, is_train=True)
-        rows, labels = self._masked_rows(mask or self.data.train_mask)
-        selected = predictions.index_select(0, rows)
-        loss = F.nll_loss(selected, labels)
-        correct = (torch.argmax(selected.detach(), dim=-1) == labels).float().mean()
+        loss, correct = self.loss_and_accuracy(graph, mask or self.data.train_mask, is_train=True)
         new_params = self.optimizer.step(loss, params=self.model_params.values())
         self._update_model_params(list(new_params))
         if self.deferred is not None:
@@ -77,6 +73,23 @@ class InnerProblemTrainer:
             return None
         loss_value, acc = torch.stack((loss.detach(), correct)).tolist()
         return Metrics(loss=loss_value, acc=acc)
+
+    def loss_and_accuracy(self, graph, mask: torch.Tensor, is_train: bool = True):
+        """(NLL, accuracy) of the GCN at the current fast weights on the rows of `mask`, as 0-dim device tensors; the loss is
+        differentiable to second order. On CUDA the log-softmax, the row selection, the NLL and the accuracy are one launch on
+        the logits (utils/rowops.py) instead of ~7 (and ~21 more in the two backward orders)."""
+        rows, labels, info = self._masked_rows(mask)
+        with double_backward_path():
+            logits = self.logits_forward(graph, is_train=is_train)
+        if fused_nll_ok(logits):
+            return masked_nll(logits, info)
+        selected = F.log_softmax(logits, dim=1).index_select(0, rows)
+        return F.nll_loss(selected, labels), (torch.argmax(selected.detach(), dim=-1) == labels).float().mean()
+
+    def logits_forward(self, graph, is_train: bool = True) -> torch.Tensor:
+        """model_forward without the final log-softmax (the fused loss works on the logits)."""
+        self.model.train(mode=is_train)
+        return self.model.forward_to_last_layer(self.data.x, graph, params=self.model_params)
 
     def model_forward(self, graph, is_train: bool = True) -> torch.Tensor:
         """The `gcn_predict_fct` of the outer step (inner.py:76-78): sets train/eval mode, runs the GCN at the

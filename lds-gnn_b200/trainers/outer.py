@@ -36,6 +36,7 @@ from ..config import Ingredient
 from ..models.graph import BernoulliGraphModel, GraphGenerativeModel
 from ..models.sampling import PHILOX, Sampler
 from ..utils.evaluation import accuracy
+from ..utils.rowops import MaskInfo, fused_nll_ok, masked_nll
 from ..utils.graph import DenseData
 from ..utils.tracking import get_lr, setup_basic_logger
 from . import Metrics
@@ -149,18 +150,20 @@ class OuterProblemTrainer:
         sink = model.factor_sink
         sink.clear()
         graph = model.sample_factored()
-        predictions = inner.model_forward(graph)
         key = (self.opt_mask.data_ptr(), self.opt_mask._version)
         if self._opt_rows is None or self._opt_rows[0] != key:          # `tensor[bool_mask]` would sync the host every step
-            rows = self.opt_mask.nonzero().flatten()
-            self._opt_rows = (key, rows, self.dataset.y[rows])
-        _, rows, labels = self._opt_rows
-        selected = predictions.index_select(0, rows)
-        loss = F.nll_loss(selected, labels)
-        correct = (torch.argmax(selected.detach(), dim=-1) == labels).float().mean()
+            self._opt_rows = (key, MaskInfo(self.opt_mask, self.dataset.y))
+        info = self._opt_rows[1]
+        logits = inner.logits_forward(graph)
+        if fused_nll_ok(logits):                                        # log-softmax + row selection + NLL + accuracy: one launch
+            loss, correct = masked_nll(logits, info)
+        else:
+            selected = F.log_softmax(logits, dim=1).index_select(0, info.rows)
+            loss = F.nll_loss(selected, info.selected_labels)
+            correct = (torch.argmax(selected.detach(), dim=-1) == info.selected_labels).float().mean()
         loss.backward(retain_graph=retain_graph)
         n = model._n
-        fa, fb, cvec = sink.collect(n, predictions.device)
+        fa, fb, cvec = sink.collect(n, logits.device)
         sink.clear()
         kind, group = opt
         probs = model._probs_param()

@@ -211,3 +211,46 @@ def test_fused_adam_step_matches_the_elementwise_form_and_its_autograd(wd, on_de
     (gp_only,) = torch.autograd.grad(_FusedAdamStep.apply(*ins, wd, b1, b2, eps, ss, rs)[0], ins[3], ups[0])
     (ref_only,) = torch.autograd.grad(reference(*ins64)[0], ins64[3], ups[0].double())
     assert ((gp_only.double() - ref_only).abs() <= 3e-5 * ref_only.abs() + 1e-4 * ref_only.abs().mean()).all()
+
+
+@pytest.mark.parametrize("n,c,m", [(300, 6, 40), (1000, 7, 1000), (257, 16, 1), (3327, 6, 120)])
+def test_fused_masked_nll_matches_torch_to_second_order(n, c, m):
+    """lds_masked_nll_{forward,grad,grad_grad} against F.nll_loss(F.log_softmax(z)[mask], y[mask]) in fp64: loss, accuracy, the
+    gradient w.r.t. the logits, and the gradient of a functional of that gradient (the double backward of the hyper step,
+    src/trainers/inner.py:63-71)."""
+    import torch.nn.functional as F
+    from lds_gnn_b200.utils.rowops import MaskInfo, masked_nll
+    torch.manual_seed(n + c)
+    z = (torch.randn(n, c, device=CUDA) * 2).requires_grad_(True)
+    y = torch.randint(0, c, (n,), device=CUDA)
+    mask = torch.zeros(n, dtype=torch.bool, device=CUDA)
+    mask[torch.randperm(n, device=CUDA)[:m]] = True
+    info = MaskInfo(mask, y)
+    probe = torch.randn(n, c, device=CUDA)
+
+    loss, acc = masked_nll(z, info)
+    (dz,) = torch.autograd.grad(loss, z, create_graph=True)
+    (ddz,) = torch.autograd.grad((dz * probe).sum(), z)
+
+    z64 = z.detach().double().requires_grad_(True)
+    logp = F.log_softmax(z64, dim=1)
+    loss64 = F.nll_loss(logp[mask], y[mask])
+    acc64 = (logp[mask].argmax(1) == y[mask]).double().mean()
+    (dz64,) = torch.autograd.grad(loss64, z64, create_graph=True)
+    (ddz64,) = torch.autograd.grad((dz64 * probe.double()).sum(), z64)
+    assert abs(loss.item() - loss64.item()) <= 1e-6 * max(1.0, abs(loss64.item()))
+    assert abs(acc.item() - acc64.item()) <= 1e-6
+    assert (dz.double() - dz64).abs().max().item() <= 1e-6 * max(1e-3, dz64.abs().max().item())
+    assert (ddz.double() - ddz64).abs().max().item() <= 2e-6 * max(1e-3, ddz64.abs().max().item())
+    assert dz[~mask].abs().max().item() == 0.0 if m < n else True
+
+
+def test_row_dot2_matches_torch():
+    from lds_gnn_b200 import kernels
+    torch.manual_seed(1)
+    n, w = 3327, 16
+    a1, b1, a2, b2 = (torch.randn(n, w, device=CUDA) for _ in range(4))
+    r = torch.rand(n, device=CUDA) + 0.1
+    out = kernels.row_dot2(a1, b1, a2, b2, r)
+    ref = ((a1.double() * b1.double()).sum(1) + (a2.double() * b2.double()).sum(1)) / r.double()
+    assert (out.double() - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
