@@ -159,7 +159,11 @@ class FactorSink:
         self.scale.append(row_scale)
 
     def add_row_constant(self, c: Tensor):
-        self.c = c if self.c is None else self.c + c
+        """Row-constant terms are summed once, at collect time (one stacked reduction instead of one add per deposit)."""
+        if self.c is None:
+            self.c = [c]
+        else:
+            self.c.append(c)
 
     def empty(self) -> bool:
         return not self.fa and self.c is None
@@ -177,7 +181,12 @@ class FactorSink:
         else:
             fa = torch.zeros((n, 1), dtype=torch.float32, device=device)
             fb = torch.zeros((n, 1), dtype=torch.float32, device=device)
-        c = self.c.contiguous() if self.c is not None else torch.zeros(n, dtype=torch.float32, device=device)
+        if self.c is None:
+            c = torch.zeros(n, dtype=torch.float32, device=device)
+        elif len(self.c) == 1:
+            c = self.c[0].contiguous()
+        else:
+            c = torch.stack(self.c).sum(dim=0)
         return fa, fb, c
 
 
@@ -216,8 +225,9 @@ class _FactoredPropagate(torch.autograd.Function):
     and the gradient on the graph is the pair (r*dZ, r*Q), deposited unscaled together with r (FactorSink scales once)."""
 
     @staticmethod
-    def forward(ctx, q, r, link, fg):
+    def forward(ctx, q, r, link, fg, own_r=False):
         from .. import kernels
+        ctx.own_r = bool(own_r)                              # r is this graph's own deg^-1/2 (FactoredGraph.normalized)
         q, r = q.contiguous(), r.contiguous()
         z = kernels.k2_propagate(fg.handle.adj, fg.handle.n, q, r, r)
         ctx.save_for_backward(q, r, z)
@@ -234,15 +244,21 @@ class _FactoredPropagate(torch.autograd.Function):
         need_q, need_r = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and not torch.is_grad_enabled()
         if not torch.is_grad_enabled():
             fg.sink.add_outer(dz.detach(), q.detach(), r.detach())
-        dq = _FactoredPropagate.apply(dz, r, fg.link, fg) if (need_q or need_r) else None
+        dq = _FactoredPropagate.apply(dz, r, fg.link, fg, ctx.own_r) if (need_q or need_r) else None
         dr = None
         if need_r:
             if dz.is_cuda and dz.dtype == torch.float32 and dz.dim() == 2:
                 from .. import kernels                       # one launch instead of mul, addcmul, sum, div (need_r only holds in the
-                dr = kernels.row_dot2(dz.contiguous(), z, dq.contiguous(), q, r)      # plain hypergradient pass: nothing differentiates this)
+                if ctx.own_r:                                # plain hypergradient pass: nothing differentiates this)
+                    # r IS this graph's deg^-1/2: it reaches theta only through deg, a row sum of the sample, so the chain
+                    # dr -> d deg = -r^3 dr / 2 -> row-constant deposit is closed here: S / (-2 deg) with S = sum dZ Z + dQ Q.
+                    # (Saves the rsqrt backward and the gradient accumulation on r and deg: ~5 launches per use.)
+                    fg.sink.add_row_constant(kernels.row_dot2(dz.contiguous(), z, dq.contiguous(), q, fg.neg_two_deg()))
+                else:
+                    dr = kernels.row_dot2(dz.contiguous(), z, dq.contiguous(), q, r)
             else:
                 dr = torch.addcmul(dz * z, dq, q).sum(dim=1) / r
-        return (dq if need_q else None), dr, None, None
+        return (dq if need_q else None), dr, None, None, None
 
 
 class _FactoredDegree(torch.autograd.Function):
@@ -291,15 +307,20 @@ class FactoredGraph:
 
     def normalized(self):
         """D^-1/2 (A+I) D^-1/2 (src/utils/graph.py:136-153) in factored, differentiable form."""
-        return FactoredNormalizedAdjacency(self, torch.rsqrt(self.degree()))
+        return FactoredNormalizedAdjacency(self, torch.rsqrt(self.degree()), own_r=True)
+
+    def neg_two_deg(self) -> Tensor:
+        if getattr(self, "_neg2deg", None) is None:
+            self._neg2deg = self.handle.deg * -2.0
+        return self._neg2deg
 
 
 class FactoredNormalizedAdjacency:
-    def __init__(self, fg: FactoredGraph, r: Tensor):
-        self.fg, self.r = fg, r
+    def __init__(self, fg: FactoredGraph, r: Tensor, own_r: bool = False):
+        self.fg, self.r, self.own_r = fg, r, own_r            # own_r: r is fg's deg^-1/2 (lets the backward close the chain to deg)
 
     def propagate(self, embeddings: Tensor) -> Tensor:
-        return _FactoredPropagate.apply(embeddings, self.r, self.fg.link, self.fg)
+        return _FactoredPropagate.apply(embeddings, self.r, self.fg.link, self.fg, self.own_r)
 
 
 def sample_factored(theta_full: Tensor, n: int, link: Tensor, sink: FactorSink) -> FactoredGraph:
