@@ -324,3 +324,52 @@ def test_cora_shape_knn_theta_16_samples_matches_oracle():
     assert np.abs(ref_new - np.clip(theta_triu, 0, 1)).max() > 50 * tol                  # the step taken dwarfs the tolerance
     sym = theta[:, :n].cpu().numpy()
     assert np.array_equal(sym, sym.T)
+
+
+@pytest.mark.parametrize("n,f,h,c,flags", [(301, 120, 16, 7, "fused"), (301, 120, 16, 7, "packed"), (301, 120, 16, 7, "bf16"),
+                                           (1000, 64, 64, 7, "packed"), (2708, 300, 16, 7, "fused"), (130, 40, 16, 3, "fused")])
+def test_outer_step_writes_stay_inside_their_buffers(n, f, h, c, flags):
+    """Guard bands instead of compute-sanitizer (closed on this GPU pool): theta and the step's workspace sit inside larger
+    allocations filled with a sentinel; after several steps on each launch plan the bands, theta's padding columns and the
+    rows past n are untouched, and the step still agrees with an engine that ran on plain allocations."""
+    from lds_gnn_b200 import _lib, kernels as K
+    rng = np.random.default_rng(n + f)
+    x = (rng.random((n, f)) < 0.05).astype(np.float32) * rng.random((n, f)).astype(np.float32)
+    y = rng.integers(0, c, n)
+    mask = np.zeros(n, dtype=bool); mask[rng.permutation(n)[: max(4, n // 5)]] = True
+    w = [rng.standard_normal((h, f)).astype(np.float32) * 0.1, np.zeros(h, np.float32),
+         rng.standard_normal((c, h)).astype(np.float32) * 0.1, np.zeros(c, np.float32)]
+    sym = rng.random((n, n)).astype(np.float32); sym = (sym + sym.T) / 2
+    k2 = {"fused": 0, "packed": _lib.K2_NO_FUSE, "bf16": _lib.K2_NO_FUSE | _lib.K2_BF16_ADJ}[flags]
+
+    def engine():
+        eng = K.OuterStep(n, dev(x), dev(y), dev(mask), hidden=h, classes=c, sparse_features=True)
+        eng.set_weights(*(dev(a) for a in w))
+        return eng
+
+    ld = K.padded_ld(n)
+    band = 64
+    SENT = 7.25
+    big = torch.full((n + 2 * band, ld), SENT, device="cuda")
+    theta = big[band:band + n]
+    theta.zero_(); theta[:, :n] = dev(sym)
+    plain_theta = torch.zeros((n, ld), device="cuda"); plain_theta[:, :n] = dev(sym)
+
+    eng = engine()
+    nbytes = eng.ws_bytes
+    guard = 1 << 16
+    raw = torch.full((nbytes + 2 * guard + 1024,), 0xA5, dtype=torch.uint8, device="cuda")
+    off = guard + ((-(raw.data_ptr() + guard)) % 1024)
+    raw[off:off + nbytes] = 0
+    eng._ws_raw, eng.ws = raw, raw[off:off + nbytes]
+    eng._init_static_args()                                              # the argument block caches the workspace pointer
+    ref = engine()
+    for step in range(3):
+        eng.run(theta, lr=0.5, seed=11, step=step, dropout_p=0.5, k2_flags=k2, want_adj=False)
+        ref.run(plain_theta, lr=0.5, seed=11, step=step, dropout_p=0.5, k2_flags=k2, want_adj=False)
+    torch.cuda.synchronize()
+    assert bool((raw[:off] == 0xA5).all()) and bool((raw[off + nbytes:] == 0xA5).all()), "write outside the workspace"
+    assert bool((big[:band] == SENT).all()) and bool((big[band + n:] == SENT).all()), "write outside theta's rows"
+    assert bool((theta[:, n:] == 0).all()), "theta's padding columns were written"
+    assert torch.equal(theta, plain_theta)
+    assert torch.equal(eng.scalars[:2], ref.scalars[:2])
