@@ -333,6 +333,8 @@ def run_ours(args, rank, world, device):
         param_sets.append(views)
     h2d_bytes = total * 4
     state = {"i": 0}
+    # (Tried: the upload on its own stream with an event, so that it overlaps the previous step's backward half — e2e 8.9 k vs
+    # 9.2 k steps/s: the extra stream switch / event calls cost the host more than the 10 us copy costs the GPU.)
 
     def api_step():
         i = state["i"] & 1
@@ -680,6 +682,18 @@ def run_large(args, rank, world, device, workload):
                           "frac_of_hbm_peak": round(step_bytes / (dev_ms / 1e3 / args.steps) / 1e9 / hbm_peak, 4)},
         "kernels": kernel_summary, "last_metrics": {"loss": loss_acc[0], "acc": loss_acc[1]},
         "scaling_reference": scaling_reference,
+        "sharding": None if world == 1 else {
+            # what row-block sharding costs by construction and what the exchange costs on top, separated: the unsharded plan uses
+            # theta's symmetry (sampling: one draw / one theta read per unordered tile pair; update: 6 N^2 instead of 8 N^2); a
+            # row-block shard can do that only inside its own diagonal block — the mirrored tiles live on other ranks, and moving
+            # theta over NVLink would cost more than it saves — so the ranks together move more bytes than one GPU does
+            "bytes_all_ranks_over_unsharded": round(world * step_bytes / (2.125 * n * n + 4 * n * n / 8 + 6 * n * n), 3),
+            "compute_us_per_step": round(sum(v["step_share_us"] for k, v in kernel_summary.items() if k != "exchange_and_host_gaps"), 1),
+            "exchange_and_gaps_us_per_step": round(kernel_summary.get("exchange_and_host_gaps", {}).get("step_share_us", 0.0), 1),
+            "parallel_efficiency": round(sum(v["step_share_us"] for k, v in kernel_summary.items() if k != "exchange_and_host_gaps")
+                                         / max(1e-9, sum(v["step_share_us"] for v in kernel_summary.values())), 4),
+            "note": "parallel_efficiency = rank-0 kernel time / (kernel time + exchange + launch gaps); scaling_reference.efficiency also "
+                    "contains bytes_all_ranks_over_unsharded (the symmetric single-GPU plan does less work than the shards together)"},
         "cpu_baseline": {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                          "sample": f"not runnable: the reference keeps ~25 dense N x N fp32 tensors ({25 * n * n * 4 / 1e9:.0f} GB) and does "
                                    f"6 N^3 SGEMMs per step at N={n}"},

@@ -225,7 +225,9 @@ __device__ __forceinline__ void k3_update_slab_row(uint8_t* slab, int row, const
 // Tile (bi, bj) of linear index t, row by row. SYM: the upper triangle incl. the diagonal (bj >= bi).
 // (Tried: bands of 32 tile rows walked column by column, so that every CTA re-reads a few MB of F_i and uses each F_j block
 // 32 times in a row — ncu at N = 65 536 shows 20.5 GB of DRAM reads for 17.2 GB of theta, i.e. factor rows missing L2.
-// Measured: 5.84 -> 5.76 ms tile-symmetric, 7.39 -> 7.62 ms full at N = 65 536, no change at N = 20 000: not kept.)
+// Measured: 5.84 -> 5.76 ms tile-symmetric, 7.39 -> 7.62 ms full at N = 65 536, no change at N = 20 000: not kept.
+// Also tried for the same reason: F pinned in the persisting part of L2 through an access-policy window on the stream
+// (hitProp persisting, missProp streaming) for the duration of the launch — 5.8 -> 12.4 ms and 7.5 -> 17.1 ms: not kept.)
 template <bool SYM>
 __device__ __forceinline__ void k3_tile_of(int t, int tiles_j, int& bi, int& bj) {
   if (!SYM) { bi = t / tiles_j; bj = t - bi * tiles_j; return; }
