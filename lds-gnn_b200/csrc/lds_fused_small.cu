@@ -303,15 +303,15 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
   for (int ph = 0; ph < fa.num_phases; ++ph, ++bfull_uses) {
     if (warp == 0) {
       if (lane == 0) {                                       // the operand k-blocks of this CTA's range (all fit: no ring)
-        asm volatile("fence.proxy.async;" ::: "memory");     // the operand was written with generic stores before the grid barrier
+        asm volatile("fence.proxy.async;" ::: "memory");     // the operand was written with generic stores by other CTAs
         mbar_expect_tx(bfull, (uint32_t)(nt * FS_B_BYTES * (fa.use_lo ? 2 : 1)));
         // Operand ping-pong: phase ph reads buffer ph & 1 and its epilogues write the other one — a leader that finishes
         // early must never overwrite operand rows another CTA has not loaded yet.
         const CUtensorMap* mh = (ph & 1) ? &tm_bhi_alt : &tm_bhi;
         const CUtensorMap* ml = (ph & 1) ? &tm_blo_alt : &tm_blo;
-        for (int j = 0; j < nt; ++j) {
+        for (int j = 0; j < nt; ++j) {                       // merged: hi and lo rows are one 32-row box (the two terms are adjacent)
           tma_load_2d(sb + j * 2 * FS_B_BYTES, mh, bfull, (my_kb0 + j) * K2_BLOCK_K, 0);
-          if (fa.use_lo) tma_load_2d(sb + j * 2 * FS_B_BYTES + FS_B_BYTES, ml, bfull, (my_kb0 + j) * K2_BLOCK_K, 0);
+          if (fa.use_lo && !fa.merged_lo) tma_load_2d(sb + j * 2 * FS_B_BYTES + FS_B_BYTES, ml, bfull, (my_kb0 + j) * K2_BLOCK_K, 0);
         }
       }
     } else if (warp == 1) {
@@ -340,7 +340,6 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
       else k2_epilogue_loop<FS_HP, K2_EPI_BWD1, true>(s, ea, fa.partial, fa.counters, cta, lo, hi, tmem_base, tfull_bar, tempty_bar, acc_e, acc_phase_e, sh_epi, fa.use_lo != 0, ((ph + 1) & 1) != 0);
     } else if (warp < 6) {
       // CLUSTER: drain this CTA's accumulator into its own shared memory (the operand buffer is idle: the MMAs have retired)
-      if (ph == 2 && cta == 0 && tid == 64) finalize_scalars(ea);   // the layer-2 phase is complete: (loss, acc)
       mbar_wait(&tfull_bar[acc_e], acc_phase_e);
       tc_fence_after();
       if (tid == 64) stamp_any(17 + 4 * ph);                 // accumulator complete
@@ -377,6 +376,9 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
         const int i = my_p * K2_BLOCK_M + row;
         const bool alt = ((ph + 1) & 1) != 0;
         if (tid == 64) stamp_any(19 + 4 * ph);               // partial tiles summed over distributed shared memory
+        // (loss, acc): the layer-2 phase of EVERY panel is complete here — cluster 0 covers all k-blocks, so its CTAs have
+        // consumed every panel's phase-1 flag, and each leader wrote its loss partial before its flag
+        if (ph == 2 && my_p == 0 && etid == 0) finalize_scalars(ea);
         if (ph == 0) epi_layer1<FS_HP>(ea, i, g, v, alt);
         else if (ph == 2) epi_bwd2<FS_HP>(ea, i, g, v, alt);
         else if (ph == 3) epi_bwd1<FS_HP>(ea, i, g, v);
@@ -399,6 +401,9 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
       unsigned long long t;
       if (fa.timeline != nullptr) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); fa.timeline[(size_t)cta * 32 + 5 + 2 * ph] = t; }
     }
+    // (Tried: per-panel ready flags instead of this barrier for phases 1-3 — a CTA only needs the operand rows of <= 7 panels — with
+    // acquire-polling lanes in warp 0 and a release store by each panel's leader: 64.8 vs 61.7 us per launch, i.e. SLOWER than
+    // the one-word barrier; reverted.)
     if (ph + 1 < fa.num_phases || smp + 1 < n_samples) grid_barrier(gbar, gbase, gk, gridDim.x);
     stamp(6 + 2 * ph);
   }
@@ -465,9 +470,12 @@ int32_t fused_small_launch(const FusedSmallArgs& fa_in, cudaStream_t stream, boo
   fa.parts = fa.s.grid / fa.s.panels;
   CUtensorMap tbh, tbl, tbh2, tbl2;
   int32_t rc;
-  if ((rc = make_tmap_2d(&tbh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, fa.ea.bt_hi, fa.n, FS_HP, fa.ea.ldb, K2_BLOCK_K, FS_HP)) != LDS_OK) return rc;
+  // the hi and lo terms of an operand buffer are adjacent ([16][ldb] each): one 32-row box fetches both
+  fa.merged_lo = (fa.use_lo && fa.ea.bt_lo == fa.ea.bt_hi + (int64_t)FS_HP * fa.ea.ldb && fa.ea.bt_lo_alt == fa.ea.bt_hi_alt + (int64_t)FS_HP * fa.ea.ldb) ? 1 : 0;
+  const int brows = fa.merged_lo ? 2 * FS_HP : FS_HP;
+  if ((rc = make_tmap_2d(&tbh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, fa.ea.bt_hi, fa.n, brows, fa.ea.ldb, K2_BLOCK_K, brows)) != LDS_OK) return rc;
   if ((rc = make_tmap_2d(&tbl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, fa.ea.bt_lo, fa.n, FS_HP, fa.ea.ldb, K2_BLOCK_K, FS_HP)) != LDS_OK) return rc;
-  if ((rc = make_tmap_2d(&tbh2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, fa.ea.bt_hi_alt, fa.n, FS_HP, fa.ea.ldb, K2_BLOCK_K, FS_HP)) != LDS_OK) return rc;
+  if ((rc = make_tmap_2d(&tbh2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, fa.ea.bt_hi_alt, fa.n, brows, fa.ea.ldb, K2_BLOCK_K, brows)) != LDS_OK) return rc;
   if ((rc = make_tmap_2d(&tbl2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, fa.ea.bt_lo_alt, fa.n, FS_HP, fa.ea.ldb, K2_BLOCK_K, FS_HP)) != LDS_OK) return rc;
   void* params[] = {(void*)&tbh, (void*)&tbl, (void*)&tbh2, (void*)&tbl2, (void*)&fa};
   // LDS_FUSED_NO_CLUSTER: A/B switch for measurements. Nsight Compute (2025.2) dies on a launch that is both cooperative and

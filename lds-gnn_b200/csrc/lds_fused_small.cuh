@@ -27,6 +27,7 @@ struct FusedSmallArgs {
   int kb_real;                                 // ceil(n / 64): k-blocks that exist
   int parts;                                   // CTAs per panel (= cluster size of the CLUSTER variant); set by the launcher
   float* partial; int* counters; int use_lo;
+  int merged_lo;                               // set by the launcher: the lo term follows the hi term in memory, one TMA box fetches both
   unsigned* gridbar;                           // 16 bytes: {monotonic 64-bit arrival counter of the grid barrier, arrivals of the staged-weight split barrier (zero between launches), spare}
   unsigned long long* timeline;                // optional debug: [grid][16] %globaltimer stamps per CTA, else NULL
   EpiArgs ea;
