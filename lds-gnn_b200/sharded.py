@@ -71,8 +71,9 @@ class DistComm:
     def gather_buffer(self, numel, dtype, device):
         return GatherBuffer(torch.zeros(numel, dtype=dtype, device=device))
 
-    def gather_into(self, local, gb, offset, chunk, count=None):
-        """`local` holds `count` (default `chunk`) valid elements; equal `chunk` strides between ranks."""
+    def gather_into(self, local, gb, offset, chunk, count=None, barrier=True):
+        """`local` holds `count` (default `chunk`) valid elements; equal `chunk` strides between ranks. `barrier` only matters for
+        the peer-memory exchange (several pushes may share the barrier of the last one)."""
         if count is not None and count != chunk:
             padded = local.new_zeros(chunk)
             padded[:count] = local[:count]
@@ -103,7 +104,7 @@ class LocalComm:
     def gather_buffer(self, numel, dtype, device):
         return GatherBuffer(torch.zeros(numel, dtype=dtype, device=device))
 
-    def gather_into(self, local, gb, offset, chunk, count=None):
+    def gather_into(self, local, gb, offset, chunk, count=None, barrier=True):
         k = chunk if count is None else count
         gb.t[offset:offset + k].copy_(local.reshape(-1)[:k])
 
@@ -147,13 +148,14 @@ class SymmComm(DistComm):
         hdl.barrier(channel=0)                              # everybody's buffer is zeroed before anybody pushes
         return GatherBuffer(t, (hdl, ptrs))
 
-    def gather_into(self, local, gb, offset, chunk, count=None):
+    def gather_into(self, local, gb, offset, chunk, count=None, barrier=True):
         hdl, ptrs = gb.ctx
         esz = local.element_size()
         nbytes = -(-(chunk if count is None else count) * esz // 16) * 16
         _lib.check(self.lib.lds_peer_push(local.data_ptr(), ptrs.data_ptr(), self.world, (offset + self.rank * chunk) * esz, nbytes,
                                           K._stream()), "lds_peer_push")
-        hdl.barrier(channel=0)
+        if barrier:                                          # pushes issued before this one on the same stream are covered too
+            hdl.barrier(channel=0)
 
 
 class ShardedOuterStep:
@@ -225,6 +227,7 @@ class ShardedOuterStep:
         self.g_opnd = comm.gather_buffer(2 * self._half, K.BF16, dev)        # double-buffered: exchange e fills half e & 1
         self.g_f = comm.gather_buffer(comm.world * per * self.kf, K.BF16, dev)
         self.g_c = comm.gather_buffer(comm.world * per + 4, torch.float32, dev)
+        self.g_s = comm.gather_buffer(comm.world * 4, torch.float32, dev)     # per-rank (loss, acc) partial sums: they ride with the update's exchange
         self.f_full = self.g_f.t.view(-1, self.kf)
         self.c_full = self.g_c.t
         self._xchg = 0
@@ -244,14 +247,17 @@ class ShardedOuterStep:
             self.recv = self.g_opnd.t[off:off + self._half]
             self._xchg += 1
             self.phase(theta_local, ph, **kw)
+        # factor rows, the ranks' (loss, acc) partial sums and c leave back to back and share ONE barrier (three pushes, no
+        # all-reduce: a 2-float NCCL all-reduce costs more than the whole exchange of c)
         if self.tensor_core_update(kw):
-            comm.gather_into(self.eng.buffer("fpack").reshape(-1), self.g_f, 0, per * self.kf, count=self.rows * self.kf)
+            comm.gather_into(self.eng.buffer("fpack").reshape(-1), self.g_f, 0, per * self.kf, count=self.rows * self.kf, barrier=False)
         else:
             for name, full in self.factor_buffers(kw):
                 comm.all_gather_rows(self.eng.buffer(name), full)
+        comm.gather_into(self.eng.scalars, self.g_s, 0, 4, barrier=False)
         comm.gather_into(self.eng.buffer("cvec"), self.g_c, 0, per, count=self.rows)
         self.phase(theta_local, _lib.PHASE_UPDATE, **kw)
-        return comm.all_reduce_sum(self.eng.scalars[:2].clone())      # after the update: not on theta's critical path
+        return self.g_s.t.view(-1, 4)[:, :2].sum(dim=0)
 
     def _run_legacy(self, theta_local, comm, kw):
         """fp32 row exchange + re-layout kernel per propagation (kept for comparison / tests)."""
