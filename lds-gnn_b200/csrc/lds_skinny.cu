@@ -6,6 +6,7 @@
 // As library calls these were a 30 us "large-K" SGEMM or 8-20 us single-block column reductions each, ~50 times per bilevel
 // block (profiles/r01m_launches_graph_block.md); here each is one ~3 us launch. Both are closed under differentiation
 // (d(XW^T) needs dY W and dY^T X; d(A^T B) needs B dG^T and A dG), which is what makes them usable under a double backward.
+#include <stdlib.h>
 #include "lds_common.cuh"
 
 namespace lds {
@@ -93,6 +94,63 @@ gram_tn_kernel(const float* __restrict__ A, int64_t lda, int a, const float* __r
   if (threadIdx.x == 0) *counter = 0u;                               // re-armed for the next call
 }
 
+// Small problems (the unrolled inner steps at Cora / Citeseer shape: N ~ 3000 rows, <= 512 outputs): ONE thread-block cluster.
+// The kernel above is bound by its arrival protocol — partial tiles through L2, fence, atomic counter, last-arriver pass: 7.5 us
+// per call, 38 calls per bilevel block — not by arithmetic. Here every CTA of the cluster stages its row range in shared memory
+// once, thread = (output pair, row slice), the slices are summed in shared memory and the CTAs' partial tiles by the rank-0 CTA
+// over distributed shared memory, both in a fixed order: deterministic, no global scratch, no atomics.
+constexpr int GC_THREADS = 512;
+__global__ void __launch_bounds__(GC_THREADS)
+gram_tn_cluster_kernel(const float* __restrict__ A, int64_t lda, int a, const float* __restrict__ B, int64_t ldb, int b, int n_rows,
+                       int per, float* __restrict__ out, int64_t ldo) {
+  extern __shared__ float gsm[];
+  uint32_t rank, csize;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+  const int pairs = a * b, nsl = GC_THREADS / pairs;
+  float* a_s = gsm;                         // [per][a]
+  float* b_s = a_s + (size_t)per * a;       // [per][b]
+  float* sl_s = b_s + (size_t)per * b;      // [nsl][pairs]
+  float* part = sl_s + (size_t)nsl * pairs; // [pairs]: this CTA's partial tile, read by rank 0
+  const int r0 = (int)rank * per, rows = max(0, min(n_rows, r0 + per) - r0);
+  for (int e = threadIdx.x; e < rows * a; e += GC_THREADS) a_s[e] = A[(int64_t)(r0 + e / a) * lda + e % a];
+  for (int e = threadIdx.x; e < rows * b; e += GC_THREADS) b_s[e] = B[(int64_t)(r0 + e / b) * ldb + e % b];
+  __syncthreads();
+  const int p = threadIdx.x % pairs, sl = threadIdx.x / pairs;
+  if (sl < nsl) {
+    const int i = p / b, j = p - i * b;
+    float s0 = 0.f, s1 = 0.f;
+    int r = sl;
+    for (; r + nsl < rows; r += 2 * nsl) {
+      s0 = fmaf(a_s[r * a + i], b_s[r * b + j], s0);
+      s1 = fmaf(a_s[(r + nsl) * a + i], b_s[(r + nsl) * b + j], s1);
+    }
+    if (r < rows) s0 = fmaf(a_s[r * a + i], b_s[r * b + j], s0);
+    sl_s[sl * pairs + p] = s0 + s1;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < pairs) {
+    float s = 0.f;
+    for (int k = 0; k < nsl; ++k) s += sl_s[k * pairs + threadIdx.x];
+    part[threadIdx.x] = s;
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (rank == 0 && (int)threadIdx.x < pairs) {
+    const uint32_t mine = (uint32_t)__cvta_generic_to_shared(part + threadIdx.x);
+    float s = 0.f;
+    for (uint32_t k = 0; k < csize; ++k) {
+      uint32_t remote; float v;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(mine), "r"(k));
+      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+      s += v;
+    }
+    out[(int64_t)(threadIdx.x / b) * ldo + threadIdx.x % b] = s;
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // nobody exits while rank 0 still reads its shared memory
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 static int gram_ctas(int64_t n_rows) {
   int64_t g = ceil_div(n_rows, 128);                // few, fatter CTAs: the last CTA's pass over the partial tiles is the serial part
   if (g > num_sms()) g = num_sms();
@@ -125,6 +183,27 @@ extern "C" int32_t lds_gram_tn(const float* a_mat, int64_t lda, int32_t a, const
   using namespace lds;
   LDS_CHECK_ARG(a_mat && b_mat && out && workspace, "lds_gram_tn: null pointer");
   LDS_CHECK_ARG(n_rows > 0 && a > 0 && a <= 128 && b > 0 && b <= 128 && lda >= a && ldb >= b && ldo >= b, "lds_gram_tn: need n_rows > 0, 0 < a, b <= 128, lda >= a, ldb >= b, ldo >= b");
+  static const bool no_cluster = getenv("LDS_GRAM_NO_CLUSTER") != nullptr;      // A/B switch
+  if (!no_cluster && a * b <= GC_THREADS && n_rows <= 8 * 1024) {
+    constexpr int CS = 8;                                      // portable cluster size
+    const int per = (int)ceil_div(n_rows, CS);
+    const size_t smem = ((size_t)per * (a + b) + (size_t)(GC_THREADS / (a * b)) * a * b + (size_t)a * b) * sizeof(float);
+    if (smem <= 200 * 1024) {
+      static size_t smem_set = 0;
+      if (smem > 48 * 1024 && smem > smem_set) {
+        LDS_CHECK_CUDA(cudaFuncSetAttribute(gram_tn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        smem_set = 200 * 1024;
+      }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(CS); cfg.blockDim = dim3(GC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      const int n32 = (int)n_rows;
+      LDS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gram_tn_cluster_kernel, a_mat, lda, (int)a, b_mat, ldb, (int)b, n32, per, out, ldo));
+      return LDS_OK;
+    }
+  }
   const int ctas = gram_ctas(n_rows);
   const int64_t need = (int64_t)ctas * a * b * sizeof(float) + 256;
   if (workspace_bytes < need) { set_error("lds_gram_tn: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need); return LDS_ERR_WORKSPACE; }

@@ -224,6 +224,20 @@ class CapturedBilevelBlock:
         self._keepalive = (inner.optimizer, dict(kernels._ws_cache), theta, inner.data, outer.dataset, outer.opt_mask,
                            dict(inner._rows_cache), outer._opt_rows)
         self._theta_ptr = theta.data_ptr()
+        self._captured_signature = self._signature()
+        if self.draws != self.tau + 1:                              # undo_hyper_step rewinds the Philox counter on this assumption
+            raise BlockCaptureError(f"a block of tau = {self.tau} drew {self.draws} graphs (expected tau + 1)")
+
+    def _signature(self):
+        """Everything a captured block bakes in besides theta's address: the masks' row lists, the features, the inner
+        optimiser's hyper-parameters (per-element vectors of the capturing optimiser), dropout and the GCN shapes. The eager
+        loop would pick a change of any of these up at the next step; a replay must too, so a mismatch recaptures."""
+        inner, outer = self.inner, self.outer
+        data = inner.data
+        groups = tuple((float(g["lr"]), float(g["weight_decay"]), tuple(g["betas"]), float(g["eps"])) for g in inner.optimizer.param_groups)
+        return (data.x.data_ptr(), data.y.data_ptr(), data.train_mask.data_ptr(), data.train_mask._version,
+                outer.opt_mask.data_ptr(), outer.opt_mask._version, groups, float(inner.model.dropout),
+                tuple(tuple(p.shape) for p in inner.model_params.values()))
 
     def _restore(self, saved, theta):
         with torch.no_grad():
@@ -246,8 +260,8 @@ class CapturedBilevelBlock:
             if not self._is_resident():
                 self.load_state()
             self.capture()
-        if outer.model.theta_full().data_ptr() != self._theta_ptr:       # the model was moved / rebuilt: addresses changed
-            self.graph = None
+        if outer.model.theta_full().data_ptr() != self._theta_ptr or self._signature() != self._captured_signature:
+            self.graph = None                                       # the model was moved / rebuilt, or something the graph baked in changed
             return self.replay()
         if not self._is_resident():
             self.load_state()
@@ -270,7 +284,8 @@ class CapturedBilevelBlock:
 
     def undo_hyper_step(self, steps_done: int):
         """The reference stopped after `steps_done` < tau inner steps of this block: its hyper step never happened. Restore theta,
-        the learning-rate schedule and the counters to that point."""
+        the learning-rate schedule and the counters to that point. (torch's own dropout generator is NOT rewound: with dropout
+        > 0 the masks drawn after a rollback differ from the step-by-step loop's, like after any extra draw; the graphs do not.)"""
         outer = self.outer
         with torch.no_grad():
             outer.model.theta_full().copy_(self.theta_backup)
