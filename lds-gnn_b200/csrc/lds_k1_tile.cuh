@@ -236,8 +236,9 @@ __device__ __forceinline__ void k1q_unit(const K1PArgs& a, const PhiloxRounds& R
   for (int u = 0; u < 8; ++u) {
     const int l0 = EDGE ? min(2 * (t0 + u), r_last) : 2 * (t0 + u), l1 = EDGE ? min(2 * (t0 + u) + 1, r_last) : 2 * (t0 + u) + 1;
     if (a.dbg & 1) { th[u][0] = make_float2(0.3f, 0.6f); th[u][1] = make_float2(0.2f, 0.9f); continue; }
-    th[u][0] = __ldcs(reinterpret_cast<const float2*>(tp + (int64_t)l0 * a.ldt));
-    th[u][1] = __ldcs(reinterpret_cast<const float2*>(tp + (int64_t)l1 * a.ldt));
+    // plain loads (not streaming): the update kernel that follows re-reads exactly these tiles, and at this size they fit in L2
+    th[u][0] = __ldg(reinterpret_cast<const float2*>(tp + (int64_t)l0 * a.ldt));
+    th[u][1] = __ldg(reinterpret_cast<const float2*>(tp + (int64_t)l1 * a.ldt));
   }
   uint32_t* row_dst = a.bits + pk_word(r_base, jg, a.kblocks, 0);         // the tile's 64 rows x 2 words are contiguous
   uint32_t c[4] = {0u, 0u, 0u, 0u};
