@@ -405,6 +405,9 @@ def run_ours(args, rank, world, device):
         "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "frac_of_hbm_peak": round(step_frac, 4)},
         "warm_l2": {"value": round(total_steps / (warm_ms / 1e3), 2), "unit": UNIT, "ms_per_step": round(warm_ms / args.steps, 5)},
         "kernels": kernel_summary,
+        "kernels_note": "per-kernel times come from a separate pass with an event recorded between the launches, which disables the "
+                        "programmatic dependent launch of the update kernel (its prologue otherwise overlaps the fused kernel's last "
+                        "phase): their sum exceeds ms_per_step by that overlap",
         "final_loss": loss_after, "e2e_last_metrics": {"loss": m.loss, "acc": m.acc},
     }
     return line

@@ -37,6 +37,8 @@ static cudaEvent_t g_events[kMaxMarks];
 static int g_ids[kMaxMarks];
 static bool g_events_created = false;
 
+bool profile_active() { return g_profiling; }
+
 void profile_mark(cudaStream_t stream, int id) {
   if (!g_profiling || g_marks >= kMaxMarks) return;
   cudaEventRecord(g_events[g_marks], stream);

@@ -29,6 +29,7 @@ int num_sms();                        // cached cudaDevAttrMultiProcessorCount o
 
 // Per-kernel timing of lds_outer_step for bench.py (lds_profile_begin/end): records a CUDA event after each launch.
 void profile_mark(cudaStream_t stream, int id);
+bool profile_active();               // between lds_profile_begin / _end (an event is recorded between the launches: no dependent launch)
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -301,6 +301,9 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
 
   // ================= P2: the four propagations from the resident tiles =================
   for (int ph = 0; ph < fa.num_phases; ++ph, ++bfull_uses) {
+    // last phase of the launch: the update kernel that follows on the stream may be scheduled now (programmatic dependent
+    // launch): its prologue and first instruction fetches overlap this phase; it waits for this grid's completion before it reads
+    if (ph + 1 == fa.num_phases && smp + 1 == n_samples && tid == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (warp == 0) {
       if (lane == 0) {                                       // the operand k-blocks of this CTA's range (all fit: no ring)
         asm volatile("fence.proxy.async;" ::: "memory");     // the operand was written with generic stores by other CTAs

@@ -29,7 +29,8 @@ __device__ __forceinline__ __nv_bfloat16 k3_pack_element(FloatPtr fa_row, FloatP
 int32_t k3_launch_pack(const float* fa, const float* fb, int64_t ldf, int n, int h, int c, void* f, cudaStream_t stream);
 
 // Tensor-core SGD update of rows [row0, row0+rows): theta <- clamp(theta - lr g), g from the packed rows F [n][kf].
+// dependent_launch: the previous kernel on `stream` issues griddepcontrol.launch_dependents (programmatic dependent launch).
 int32_t k3_launch_tc(float* theta, int64_t ldt, int n, int row0, int rows, const void* f, int kf,
-                     const float* cvec, float lr, cudaStream_t stream);
+                     const float* cvec, float lr, cudaStream_t stream, bool dependent_launch = false);
 
 }  // namespace lds

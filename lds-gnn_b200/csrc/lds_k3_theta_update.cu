@@ -283,6 +283,10 @@ k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch (lds_outer_step after the fused small-graph kernel): everything above — and this kernel's first
+  // instruction fetches — may run while the producer of F / c / theta is still in its last phase; nothing below may. Without
+  // the launch attribute this returns at once.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ===== TMA producer: operand boxes =====
@@ -433,7 +437,7 @@ int32_t k3_launch_pack(const float* fa, const float* fb, int64_t ldf, int n, int
 }
 
 int32_t k3_launch_tc(float* theta, int64_t ldt, int n, int row0, int rows, const void* f, int kf,
-                     const float* cvec, float lr, cudaStream_t stream) {
+                     const float* cvec, float lr, cudaStream_t stream, bool dependent_launch) {
   CUtensorMap tth, tf;
   int32_t rc;
   if ((rc = make_tmap_2d(&tth, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, theta, n, rows, ldt, K3T_SLAB_COLS, K3T_TILE)) != LDS_OK) return rc;
@@ -450,6 +454,21 @@ int32_t k3_launch_tc(float* theta, int64_t ldt, int n, int row0, int rows, const
   const int tj = (int)ceil_div(n, K3T_TILE);
   const int tiles = sym ? tj * (tj + 1) / 2 : (int)(ceil_div(rows, K3T_TILE) * tj);
   const int grid = tiles < kNumSMsB200 ? tiles : kNumSMsB200;
+  static const bool no_pdl = getenv("LDS_NO_PDL") != nullptr;        // A/B switch
+  if (dependent_launch && !no_pdl) {
+    // the previous kernel on this stream triggers its dependents early (griddepcontrol.launch_dependents): this launch may start
+    // its prologue before that kernel has finished; the kernel waits (griddepcontrol.wait) before it touches memory
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(K3T_THREADS); cfg.dynamicSmemBytes = K3T_SMEM; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    const int ks = kf / K3T_KB;
+    cudaError_t e = sym ? cudaLaunchKernelEx(&cfg, k3_tc_kernel<true>, tth, tf, cvec, n, row0, rows, ks, lr, theta, ldt)
+                        : cudaLaunchKernelEx(&cfg, k3_tc_kernel<false>, tth, tf, cvec, n, row0, rows, ks, lr, theta, ldt);
+    if (e == cudaSuccess) return LDS_OK;
+    (void)cudaGetLastError();                                  // fall through to the plain launch
+  }
   if (sym) k3_tc_kernel<true><<<grid, K3T_THREADS, K3T_SMEM, stream>>>(tth, tf, cvec, n, row0, rows, kf / K3T_KB, lr, theta, ldt);
   else k3_tc_kernel<false><<<grid, K3T_THREADS, K3T_SMEM, stream>>>(tth, tf, cvec, n, row0, rows, kf / K3T_KB, lr, theta, ldt);
   LDS_CHECK_LAUNCH("k3_tc_kernel");

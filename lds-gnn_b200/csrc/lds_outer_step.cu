@@ -595,11 +595,11 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   if ((phases & LDS_PHASE_UPDATE) && A.update && (S == 1 || (int)smp == S - 1)) {
     const float* cv = sharded ? A.c_full : fbuf(B_C);
     if (S > 1) {                                              // mean of the S single-sample gradients: one pass, K = S * kf
-      rc = k3_launch_tc(A.theta_full, A.ld_theta, A.n, 0, rows, A.fpack_multi, S * L.kf, cv, A.lr / (float)S, stream);
+      rc = k3_launch_tc(A.theta_full, A.ld_theta, A.n, 0, rows, A.fpack_multi, S * L.kf, cv, A.lr / (float)S, stream, fused_done && !profile_active());
     } else if (tc_update) {
       const void* f = sharded ? A.f_full : buf(B_F);
       LDS_CHECK_ARG((reinterpret_cast<uintptr_t>(cv) & 15) == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0, "lds_outer_step: c_full / f_full must be 16-byte aligned");
-      rc = k3_launch_tc(A.theta_full, A.ld_theta, A.n, row0, rows, f, L.kf, cv, A.lr, stream);
+      rc = k3_launch_tc(A.theta_full, A.ld_theta, A.n, row0, rows, f, L.kf, cv, A.lr, stream, fused_done && !profile_active());
     } else {
       const float* fa = sharded ? A.fa_full : fbuf(B_FA);
       const float* fb = sharded ? A.fb_full : fbuf(B_FB);
