@@ -33,7 +33,7 @@ struct EpiArgs;   // lds_epilogue.cuh
 // epilogue `epi` (K2Epi) on every completed 128-row panel. `counters`: one zero-initialised int per panel.
 int32_t k2_launch_mma(const void* a, int64_t ld_a, int n, int rows, const void* bt_hi, const void* bt_lo, int64_t ldb,
                       float* partial, int* counters, const K2Sched& s, bool use_lo, int epi, const EpiArgs& ea, cudaStream_t stream,
-                      int b_rank_rows = 0);   // > 0: the operand is the gathered rank-blocked array [rank][hi, lo][hp][b_rank_rows] (sharded step)
+                      int b_rank_rows = 0, bool dependent = false);   // > 0: the operand is the gathered rank-blocked array [rank][hi, lo][hp][b_rank_rows] (sharded step)
 // Operand preparation: bt_hi/lo[c][i] = bf16 split of scale_in[i] * p[i][c] (transposed, K-major), c < hp; zeroes the counters.
 int32_t k2_launch_prep(const float* p, int64_t ld_p, int n, int width, int hp, const float* scale_in,
                        void* bt_hi, void* bt_lo, int64_t ldb, int* counters, int num_counters, cudaStream_t stream);

@@ -74,6 +74,9 @@ k2_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch (lds_k2_propagate: this kernel follows the operand pack): the setup above overlaps the pack;
+  // nothing below may start before the pack's writes (operand, re-armed counters) are visible. A plain launch returns at once.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -159,6 +162,7 @@ __global__ void k2_prep_kernel(const float* __restrict__ p, int64_t ld_p, int n,
                                __nv_bfloat16* __restrict__ bt_hi, __nv_bfloat16* __restrict__ bt_lo, int64_t ldb,
                                int* __restrict__ counters, int num_counters) {
   __shared__ float tile[32][33];
+  if (threadIdx.x == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the propagation may set itself up now
   if (blockIdx.x == 0 && blockIdx.y == 0)
     for (int k = threadIdx.x; k < num_counters; k += blockDim.x) counters[k] = 0;
   const int i0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -302,11 +306,22 @@ static int32_t make_tmap_bf16(CUtensorMap* out, const void* base, int64_t cols, 
 
 template <int HP, int EPI>
 static int32_t launch_mma_t(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tbl, float* partial, int* counters,
-                            const K2Sched& s, bool use_lo, const EpiArgs& ea, int b_rank_rows, cudaStream_t stream) {
+                            const K2Sched& s, bool use_lo, const EpiArgs& ea, int b_rank_rows, cudaStream_t stream, bool dependent = false) {
   static bool attr_set = false;
   if (!attr_set) {
     LDS_CHECK_CUDA(cudaFuncSetAttribute(k2_mma_kernel<HP, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2Cfg<HP>::SMEM_BYTES));
     attr_set = true;
+  }
+  static const bool no_pdl = getenv("LDS_NO_PDL") != nullptr;
+  if (dependent && !no_pdl) {                                  // the previous kernel on the stream (operand pack) triggers its dependents
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)s.grid); cfg.blockDim = dim3(K2_THREADS); cfg.dynamicSmemBytes = K2Cfg<HP>::SMEM_BYTES; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    const int ul = use_lo ? 1 : 0;
+    if (cudaLaunchKernelEx(&cfg, k2_mma_kernel<HP, EPI>, ta, tbh, tbl, partial, counters, s, ul, ea, b_rank_rows) == cudaSuccess) return LDS_OK;
+    (void)cudaGetLastError();                                  // fall through to the plain launch
   }
   k2_mma_kernel<HP, EPI><<<s.grid, K2_THREADS, K2Cfg<HP>::SMEM_BYTES, stream>>>(ta, tbh, tbl, partial, counters, s, use_lo ? 1 : 0, ea, b_rank_rows);
   LDS_CHECK_LAUNCH("k2_mma_kernel");
@@ -315,9 +330,9 @@ static int32_t launch_mma_t(const CUtensorMap& ta, const CUtensorMap& tbh, const
 
 template <int HP>
 static int32_t launch_mma_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tbl, float* partial, int* counters,
-                              const K2Sched& s, bool use_lo, const EpiArgs& ea, int b_rank_rows, cudaStream_t stream) {
+                              const K2Sched& s, bool use_lo, const EpiArgs& ea, int b_rank_rows, cudaStream_t stream, bool dependent) {
   switch (epi) {
-    case K2_EPI_PLAIN:  return launch_mma_t<HP, K2_EPI_PLAIN>(ta, tbh, tbl, partial, counters, s, use_lo, ea, b_rank_rows, stream);
+    case K2_EPI_PLAIN:  return launch_mma_t<HP, K2_EPI_PLAIN>(ta, tbh, tbl, partial, counters, s, use_lo, ea, b_rank_rows, stream, dependent);
     case K2_EPI_LAYER1: return launch_mma_t<HP, K2_EPI_LAYER1>(ta, tbh, tbl, partial, counters, s, use_lo, ea, b_rank_rows, stream);
     case K2_EPI_LAYER2: return launch_mma_t<HP, K2_EPI_LAYER2>(ta, tbh, tbl, partial, counters, s, use_lo, ea, b_rank_rows, stream);
     case K2_EPI_BWD2:   return launch_mma_t<HP, K2_EPI_BWD2>(ta, tbh, tbl, partial, counters, s, use_lo, ea, b_rank_rows, stream);
@@ -329,7 +344,7 @@ static int32_t launch_mma_epi(int epi, const CUtensorMap& ta, const CUtensorMap&
 
 int32_t k2_launch_mma(const void* a, int64_t ld_a, int n, int rows, const void* bt_hi, const void* bt_lo, int64_t ldb,
                       float* partial, int* counters, const K2Sched& s, bool use_lo, int epi, const EpiArgs& ea, cudaStream_t stream,
-                      int b_rank_rows) {
+                      int b_rank_rows, bool dependent) {
   CUtensorMap ta, tbh, tbl;
   int32_t rc;
   if ((rc = make_tmap_bf16(&ta, a, n, rows, ld_a, K2_BLOCK_M)) != LDS_OK) return rc;
@@ -342,10 +357,10 @@ int32_t k2_launch_mma(const void* a, int64_t ld_a, int n, int rows, const void* 
   if ((rc = make_tmap_bf16(&tbl, bt_lo, n, s.hp, ldb, s.hp)) != LDS_OK) return rc;
   }
   switch (s.hp) {
-    case 16: return launch_mma_epi<16>(epi, ta, tbh, tbl, partial, counters, s, use_lo, ea, b_rank_rows, stream);
-    case 32: return launch_mma_epi<32>(epi, ta, tbh, tbl, partial, counters, s, use_lo, ea, b_rank_rows, stream);
-    case 64: return launch_mma_epi<64>(epi, ta, tbh, tbl, partial, counters, s, use_lo, ea, b_rank_rows, stream);
-    case 128: return launch_mma_epi<128>(epi, ta, tbh, tbl, partial, counters, s, use_lo, ea, b_rank_rows, stream);
+    case 16: return launch_mma_epi<16>(epi, ta, tbh, tbl, partial, counters, s, use_lo, ea, b_rank_rows, stream, dependent);
+    case 32: return launch_mma_epi<32>(epi, ta, tbh, tbl, partial, counters, s, use_lo, ea, b_rank_rows, stream, dependent);
+    case 64: return launch_mma_epi<64>(epi, ta, tbh, tbl, partial, counters, s, use_lo, ea, b_rank_rows, stream, dependent);
+    case 128: return launch_mma_epi<128>(epi, ta, tbh, tbl, partial, counters, s, use_lo, ea, b_rank_rows, stream, dependent);
   }
   set_error("k2: unsupported padded width %d", s.hp);
   return LDS_ERR_UNSUPPORTED;
@@ -407,5 +422,6 @@ extern "C" int32_t lds_k2_propagate(const void* a, int64_t ld_a, int32_t n, int3
   EpiArgs ea;
   memset(&ea, 0, sizeof(ea));
   ea.z_out = z_out; ea.ld_z = ld_z; ea.scale_out = scale_out; ea.rows = rows; ea.width = width;
-  return k2_launch_mma(a, ld_a, n, rows, bt_hi, bt_lo, ldb, partial, counters, s, !(flags & LDS_K2_SINGLE_BF16), K2_EPI_PLAIN, ea, stream);
+  return k2_launch_mma(a, ld_a, n, rows, bt_hi, bt_lo, ldb, partial, counters, s, !(flags & LDS_K2_SINGLE_BF16), K2_EPI_PLAIN, ea, stream, 0,
+                       /*dependent=*/true);
 }

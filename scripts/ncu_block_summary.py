@@ -13,7 +13,10 @@ FAMILIES = [("lds::k2_mma_kernel", "K2 `k2_mma_kernel` (tcgen05 propagate, every
             ("lds::k3_pack_kernel", "K3 factor pack `k3_pack_kernel`"),
             ("lds::spmm_csr_kernel", "CSR feature products `spmm_csr_kernel`"),
             ("lds::row_linear_kernel", "skinny X W^T `row_linear_kernel`"),
-            ("lds::gram_tn_kernel", "skinny A^T B / column sums `gram_tn_kernel`"),
+            ("lds::gram_tn", "skinny A^T B / column sums `gram_tn_cluster_kernel` / `gram_tn_kernel`"),
+            ("lds::adam_step", "differentiable Adam step and its backward `adam_step(_backward)_kernel`"),
+            ("lds::masked_nll", "masked NLL on the logits: forward, gradient, gradient of the gradient `masked_nll_*_kernel`"),
+            ("lds::row_dot2", "r-gradient of the normalised propagation `row_dot2_kernel`"),
             ("gemm", "cuBLAS / CUTLASS GEMMs (skinny dense products left in torch)"),
             ("reduce_kernel", "torch reductions"), ("elementwise", "torch elementwise"), ("", "other torch kernels (softmax, nll, index, cat, copy, dropout)")]
 agg = collections.OrderedDict((label, []) for _, label in FAMILIES)
