@@ -23,6 +23,7 @@ struct AdamHyper { float wd, b1, b2, eps, step_size, root_scale; const float* st
 __global__ void __launch_bounds__(256)
 adam_step_kernel(const float* __restrict__ p, const float* __restrict__ m, const float* __restrict__ v, const float* __restrict__ g, int64_t n,
                  AdamHyper hp, float* __restrict__ p_out, float* __restrict__ m_out, float* __restrict__ v_out) {
+  pdl_prologue();
   const float step = hp.step_size_dev ? *hp.step_size_dev : hp.step_size;
   const float rs = hp.root_scale_dev ? *hp.root_scale_dev : hp.root_scale;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -43,6 +44,7 @@ __global__ void __launch_bounds__(256)
 adam_step_backward_kernel(const float* __restrict__ gp, const float* __restrict__ gm, const float* __restrict__ gv,
                           const float* __restrict__ p, const float* __restrict__ m, const float* __restrict__ v, const float* __restrict__ g,
                           int64_t n, AdamHyper hp, float* __restrict__ dp, float* __restrict__ dm, float* __restrict__ dv, float* __restrict__ dg) {
+  pdl_prologue();
   const float step = hp.step_size_dev ? *hp.step_size_dev : hp.step_size;
   const float rs = hp.root_scale_dev ? *hp.root_scale_dev : hp.root_scale;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -85,8 +87,7 @@ extern "C" int32_t lds_adam_step(const float* p, const float* m, const float* v,
   LDS_CHECK_ARG(n > 0, "lds_adam_step: n must be positive");
   LDS_CHECK_ARG((step_size_dev == nullptr) == (root_scale_dev == nullptr), "lds_adam_step: step_size_dev and root_scale_dev come together");
   AdamHyper hp{weight_decay, beta1, beta2, eps, step_size, root_scale, step_size_dev, root_scale_dev, weight_decay_vec};
-  adam_step_kernel<<<adam_grid(n), 256, 0, (cudaStream_t)stream>>>(p, m, v, g, n, hp, p_out, m_out, v_out);
-  LDS_CHECK_LAUNCH("adam_step_kernel");
+  LDS_CHECK_CUDA(launch_dependent(adam_step_kernel, dim3((unsigned)adam_grid(n)), dim3(256), 0, (cudaStream_t)stream, p, m, v, g, n, hp, p_out, m_out, v_out));
   return LDS_OK;
 }
 
@@ -99,7 +100,6 @@ extern "C" int32_t lds_adam_step_backward(const float* grad_p_out, const float* 
   LDS_CHECK_ARG(n > 0, "lds_adam_step_backward: n must be positive");
   LDS_CHECK_ARG((step_size_dev == nullptr) == (root_scale_dev == nullptr), "lds_adam_step_backward: step_size_dev and root_scale_dev come together");
   AdamHyper hp{weight_decay, beta1, beta2, eps, step_size, root_scale, step_size_dev, root_scale_dev, weight_decay_vec};
-  adam_step_backward_kernel<<<adam_grid(n), 256, 0, (cudaStream_t)stream>>>(grad_p_out, grad_m_out, grad_v_out, p, m, v, g, n, hp, dp, dm, dv, dg);
-  LDS_CHECK_LAUNCH("adam_step_backward_kernel");
+  LDS_CHECK_CUDA(launch_dependent(adam_step_backward_kernel, dim3((unsigned)adam_grid(n)), dim3(256), 0, (cudaStream_t)stream, grad_p_out, grad_m_out, grad_v_out, p, m, v, g, n, hp, dp, dm, dv, dg));
   return LDS_OK;
 }

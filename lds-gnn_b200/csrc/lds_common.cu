@@ -1,3 +1,4 @@
+#include <stdlib.h>
 // lds_common.cu — error slot, version, device check, host Philox restatement.
 #include <stdarg.h>
 #include <string.h>
@@ -38,6 +39,11 @@ static int g_ids[kMaxMarks];
 static bool g_events_created = false;
 
 bool profile_active() { return g_profiling; }
+
+bool pdl_enabled() {
+  static const bool on = getenv("LDS_NO_PDL") == nullptr;
+  return on;
+}
 
 void profile_mark(cudaStream_t stream, int id) {
   if (!g_profiling || g_marks >= kMaxMarks) return;

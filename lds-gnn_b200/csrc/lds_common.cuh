@@ -31,6 +31,28 @@ int num_sms();                        // cached cudaDevAttrMultiProcessorCount o
 void profile_mark(cudaStream_t stream, int id);
 bool profile_active();               // between lds_profile_begin / _end (an event is recorded between the launches: no dependent launch)
 
+// Programmatic dependent launch for the chains of small kernels of the unrolled inner steps (a captured bilevel block is ~450
+// kernels of a few us each, back to back): a kernel launched with `launch_dependent` may be scheduled while its predecessor on
+// the stream is still running, provided that predecessor has issued griddepcontrol.launch_dependents — every kernel launched this
+// way does so in its first statement (`pdl_prologue`) and then waits until the predecessor has completed and its writes are
+// visible. What is hidden is the dependent's launch latency; after a kernel that never triggers (ATen's) the launch is an
+// ordinary one. LDS_NO_PDL=1 disables it (A/B switch).
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

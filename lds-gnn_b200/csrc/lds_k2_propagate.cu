@@ -58,6 +58,7 @@ k2_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
   const int lo = cta * s.per_cta;
   const int hi = min(lo + s.per_cta, s.total);
 
+  if (EPI == K2_EPI_PLAIN && threadIdx.x == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // stand-alone propagate: see pdl_prologue
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_bhi); tma_prefetch_desc(&tm_blo);
   }
@@ -162,7 +163,7 @@ __global__ void k2_prep_kernel(const float* __restrict__ p, int64_t ld_p, int n,
                                __nv_bfloat16* __restrict__ bt_hi, __nv_bfloat16* __restrict__ bt_lo, int64_t ldb,
                                int* __restrict__ counters, int num_counters) {
   __shared__ float tile[32][33];
-  if (threadIdx.x == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the propagation may set itself up now
+  pdl_prologue();                                              // the propagation that follows may set itself up now; wait for our own producer
   if (blockIdx.x == 0 && blockIdx.y == 0)
     for (int k = threadIdx.x; k < num_counters; k += blockDim.x) counters[k] = 0;
   const int i0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -377,8 +378,8 @@ int32_t k2_launch_simt(const void* a, int64_t ld_a, int n, int rows, const float
 int32_t k2_launch_prep(const float* p, int64_t ld_p, int n, int width, int hp, const float* scale_in,
                        void* bt_hi, void* bt_lo, int64_t ldb, int* counters, int num_counters, cudaStream_t stream) {
   dim3 grid((unsigned)ceil_div(ldb, 32), (unsigned)ceil_div(hp, 32));
-  k2_prep_kernel<<<grid, 256, 0, stream>>>(p, ld_p, n, width, hp, scale_in, reinterpret_cast<__nv_bfloat16*>(bt_hi), reinterpret_cast<__nv_bfloat16*>(bt_lo), ldb, counters, num_counters);
-  LDS_CHECK_LAUNCH("k2_prep_kernel");
+  LDS_CHECK_CUDA(launch_dependent(k2_prep_kernel, grid, dim3(256), 0, stream, p, ld_p, n, width, hp, scale_in, reinterpret_cast<__nv_bfloat16*>(bt_hi),
+                                  reinterpret_cast<__nv_bfloat16*>(bt_lo), ldb, counters, num_counters));
   return LDS_OK;
 }
 

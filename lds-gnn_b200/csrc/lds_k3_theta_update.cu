@@ -422,6 +422,7 @@ k3_tc_kernel(const __grid_constant__ CUtensorMap tm_theta, const __grid_constant
 // fa, fb fp32 [n][ldf] -> packed rows F bf16 [n][kf] (layout: lds_k3.cuh)
 __global__ void k3_pack_kernel(const float* __restrict__ fa, const float* __restrict__ fb, int64_t ldf, int n, int h, int c, int kf,
                                __nv_bfloat16* __restrict__ f) {
+  pdl_prologue();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)n * kf) return;
   const int i = (int)(idx / kf), k = (int)(idx - (int64_t)i * kf);
@@ -431,7 +432,7 @@ __global__ void k3_pack_kernel(const float* __restrict__ fa, const float* __rest
 int32_t k3_launch_pack(const float* fa, const float* fb, int64_t ldf, int n, int h, int c, void* f, cudaStream_t stream) {
   const int kf = k3_packed_k(h, c);
   const int64_t total = (int64_t)n * kf;
-  k3_pack_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(fa, fb, ldf, n, h, c, kf, reinterpret_cast<__nv_bfloat16*>(f));
+  LDS_CHECK_CUDA(launch_dependent(k3_pack_kernel, dim3((unsigned)ceil_div(total, 256)), dim3(256), 0, stream, fa, fb, ldf, n, h, c, kf, reinterpret_cast<__nv_bfloat16*>(f)));
   LDS_CHECK_LAUNCH("k3_pack_kernel");
   return LDS_OK;
 }

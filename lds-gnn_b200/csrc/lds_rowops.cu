@@ -33,6 +33,7 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {      // fi
 __global__ void __launch_bounds__(1024)
 masked_nll_forward_kernel(const float* __restrict__ z, int64_t ldz, int c, const int64_t* __restrict__ rows, const int64_t* __restrict__ y,
                           int m, float* __restrict__ out) {
+  pdl_prologue();
   __shared__ float scratch[32];
   float loss = 0.f, correct = 0.f;
   for (int k = threadIdx.x; k < m; k += blockDim.x) {
@@ -55,6 +56,7 @@ masked_nll_forward_kernel(const float* __restrict__ z, int64_t ldz, int c, const
 __global__ void __launch_bounds__(RO_THREADS)
 masked_nll_grad_kernel(const float* __restrict__ z, int64_t ldz, int c, const int32_t* __restrict__ slot, const int64_t* __restrict__ y,
                        int n, int m, const float* __restrict__ g, float* __restrict__ dz, int64_t ldd) {
+  pdl_prologue();
   const float scale = *g / (float)m;
   for (int i = blockIdx.x * RO_THREADS + threadIdx.x; i < n; i += gridDim.x * RO_THREADS) {
     float* di = dz + (int64_t)i * ldd;
@@ -76,6 +78,7 @@ __global__ void __launch_bounds__(RO_THREADS)
 masked_nll_grad_grad_kernel(const float* __restrict__ u, int64_t ldu, const float* __restrict__ z, int64_t ldz, int c,
                             const int32_t* __restrict__ slot, const int64_t* __restrict__ y, int n, int m, const float* __restrict__ g,
                             float* __restrict__ out_z, int64_t ldo, float* __restrict__ out_g_rows) {
+  pdl_prologue();
   const float scale = *g / (float)m;
   for (int i = blockIdx.x * RO_THREADS + threadIdx.x; i < n; i += gridDim.x * RO_THREADS) {
     float* oi = out_z ? out_z + (int64_t)i * ldo : nullptr;
@@ -103,6 +106,7 @@ masked_nll_grad_grad_kernel(const float* __restrict__ u, int64_t ldu, const floa
 __global__ void __launch_bounds__(RO_THREADS)
 row_dot2_kernel(const float* __restrict__ a1, const float* __restrict__ b1, const float* __restrict__ a2, const float* __restrict__ b2,
                 int64_t ld, int w, const float* __restrict__ r, int n, float* __restrict__ out) {
+  pdl_prologue();
   for (int i = blockIdx.x * RO_THREADS + threadIdx.x; i < n; i += gridDim.x * RO_THREADS) {
     const int64_t o = (int64_t)i * ld;
     float s = 0.f;
@@ -127,8 +131,7 @@ extern "C" int32_t lds_masked_nll_forward(const float* z, int64_t ld_z, int32_t 
                                           float* out_loss_acc, void* stream) {
   LDS_CHECK_ARG(z && rows && y && out_loss_acc, "lds_masked_nll_forward: null pointer");
   LDS_CHECK_ARG(c > 0 && c <= RO_MAXC && ld_z >= c && m > 0, "lds_masked_nll_forward: need 0 < c <= 128, ld_z >= c, m > 0");
-  masked_nll_forward_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(z, ld_z, c, rows, y, m, out_loss_acc);
-  LDS_CHECK_LAUNCH("masked_nll_forward_kernel");
+  LDS_CHECK_CUDA(launch_dependent(masked_nll_forward_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, z, ld_z, c, rows, y, m, out_loss_acc));
   return LDS_OK;
 }
 
@@ -136,8 +139,7 @@ extern "C" int32_t lds_masked_nll_grad(const float* z, int64_t ld_z, int32_t c, 
                                        const float* grad_loss, float* dz, int64_t ld_dz, void* stream) {
   LDS_CHECK_ARG(z && slot && y && grad_loss && dz, "lds_masked_nll_grad: null pointer");
   LDS_CHECK_ARG(c > 0 && c <= RO_MAXC && ld_z >= c && ld_dz >= c && n > 0 && m > 0, "lds_masked_nll_grad: need 0 < c <= 128, ld >= c, n, m > 0");
-  masked_nll_grad_kernel<<<ro_grid(n), RO_THREADS, 0, (cudaStream_t)stream>>>(z, ld_z, c, slot, y, n, m, grad_loss, dz, ld_dz);
-  LDS_CHECK_LAUNCH("masked_nll_grad_kernel");
+  LDS_CHECK_CUDA(launch_dependent(masked_nll_grad_kernel, dim3((unsigned)ro_grid(n)), dim3(RO_THREADS), 0, (cudaStream_t)stream, z, ld_z, c, slot, y, n, m, grad_loss, dz, ld_dz));
   return LDS_OK;
 }
 
@@ -147,8 +149,7 @@ extern "C" int32_t lds_masked_nll_grad_grad(const float* u, int64_t ld_u, const 
   LDS_CHECK_ARG(u && z && slot && y && grad_loss && (out_z || out_g_rows), "lds_masked_nll_grad_grad: null pointer");
   LDS_CHECK_ARG(c > 0 && c <= RO_MAXC && ld_z >= c && ld_u >= c && (!out_z || ld_out >= c) && n > 0 && m > 0,
                 "lds_masked_nll_grad_grad: need 0 < c <= 128, ld >= c, n, m > 0");
-  masked_nll_grad_grad_kernel<<<ro_grid(n), RO_THREADS, 0, (cudaStream_t)stream>>>(u, ld_u, z, ld_z, c, slot, y, n, m, grad_loss, out_z, ld_out, out_g_rows);
-  LDS_CHECK_LAUNCH("masked_nll_grad_grad_kernel");
+  LDS_CHECK_CUDA(launch_dependent(masked_nll_grad_grad_kernel, dim3((unsigned)ro_grid(n)), dim3(RO_THREADS), 0, (cudaStream_t)stream, u, ld_u, z, ld_z, c, slot, y, n, m, grad_loss, out_z, ld_out, out_g_rows));
   return LDS_OK;
 }
 
@@ -156,7 +157,6 @@ extern "C" int32_t lds_row_dot2(const float* a1, const float* b1, const float* a
                                 const float* r, int32_t n, float* out, void* stream) {
   LDS_CHECK_ARG(a1 && b1 && a2 && b2 && r && out, "lds_row_dot2: null pointer");
   LDS_CHECK_ARG(w > 0 && ld >= w && n > 0, "lds_row_dot2: need w > 0, ld >= w, n > 0");
-  row_dot2_kernel<<<ro_grid(n), RO_THREADS, 0, (cudaStream_t)stream>>>(a1, b1, a2, b2, ld, w, r, n, out);
-  LDS_CHECK_LAUNCH("row_dot2_kernel");
+  LDS_CHECK_CUDA(launch_dependent(row_dot2_kernel, dim3((unsigned)ro_grid(n)), dim3(RO_THREADS), 0, (cudaStream_t)stream, a1, b1, a2, b2, ld, w, r, n, out));
   return LDS_OK;
 }

@@ -18,6 +18,7 @@ constexpr int SK_CHUNK = 64;          // rows staged per pass of the Gram kernel
 __global__ void __launch_bounds__(SK_THREADS)
 row_linear_kernel(const float* __restrict__ X, int64_t ldx, int kdim, const float* __restrict__ W, int64_t sw0, int64_t sw1, int m,
                   const float* __restrict__ bias, float* __restrict__ Y, int64_t ldy, int64_t n_rows) {
+  pdl_prologue();
   extern __shared__ float w_s[];                                    // [m][kdim + 1]
   const int kp = kdim + 1;
   for (int e = threadIdx.x; e < m * kdim; e += SK_THREADS) { const int j = e / kdim, k = e % kdim; w_s[j * kp + k] = W[(int64_t)j * sw0 + (int64_t)k * sw1]; }
@@ -38,6 +39,7 @@ row_linear_kernel(const float* __restrict__ X, int64_t ldx, int kdim, const floa
 __global__ void __launch_bounds__(SK_THREADS)
 gram_tn_kernel(const float* __restrict__ A, int64_t lda, int a, const float* __restrict__ B, int64_t ldb, int b, int64_t n_rows,
                float* __restrict__ partial, unsigned int* __restrict__ counter, float* __restrict__ out, int64_t ldo) {
+  pdl_prologue();
   extern __shared__ float sm[];                                     // A chunk [SK_CHUNK][a], B chunk [SK_CHUNK][b]
   float* a_s = sm; float* b_s = sm + SK_CHUNK * a;
   __shared__ bool last;
@@ -103,6 +105,7 @@ constexpr int GC_THREADS = 512;
 __global__ void __launch_bounds__(GC_THREADS)
 gram_tn_cluster_kernel(const float* __restrict__ A, int64_t lda, int a, const float* __restrict__ B, int64_t ldb, int b, int n_rows,
                        int per, float* __restrict__ out, int64_t ldo) {
+  pdl_prologue();
   extern __shared__ float gsm[];
   uint32_t rank, csize;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -168,8 +171,7 @@ extern "C" int32_t lds_row_linear(const float* x, int64_t ldx, int32_t k, const 
   if (smem > 48 * 1024) LDS_CHECK_CUDA(cudaFuncSetAttribute(row_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t blocks = ceil_div(n_rows * m, SK_THREADS);
   if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
-  row_linear_kernel<<<(unsigned)blocks, SK_THREADS, smem, (cudaStream_t)stream>>>(x, ldx, k, w, sw0, sw1, m, bias, y, ldy, n_rows);
-  LDS_CHECK_LAUNCH("row_linear_kernel");
+  LDS_CHECK_CUDA(launch_dependent(row_linear_kernel, dim3((unsigned)blocks), dim3(SK_THREADS), smem, (cudaStream_t)stream, x, ldx, k, w, sw0, sw1, m, bias, y, ldy, n_rows));
   return LDS_OK;
 }
 
@@ -196,9 +198,10 @@ extern "C" int32_t lds_gram_tn(const float* a_mat, int64_t lda, int32_t a, const
       }
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(CS); cfg.blockDim = dim3(GC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
-      cudaLaunchAttribute at[1];
+      cudaLaunchAttribute at[2];
       at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
+      at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
       const int n32 = (int)n_rows;
       LDS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gram_tn_cluster_kernel, a_mat, lda, (int)a, b_mat, ldb, (int)b, n32, per, out, ldo));
       return LDS_OK;
@@ -213,7 +216,6 @@ extern "C" int32_t lds_gram_tn(const float* a_mat, int64_t lda, int32_t a, const
   auto* partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + 256);
   const size_t smem = (size_t)SK_CHUNK * (a + b) * sizeof(float);
   if (smem > 48 * 1024) LDS_CHECK_CUDA(cudaFuncSetAttribute(gram_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gram_tn_kernel<<<ctas, SK_THREADS, smem, (cudaStream_t)stream>>>(a_mat, lda, a, b_mat, ldb, b, n_rows, partial, counter, out, ldo);
-  LDS_CHECK_LAUNCH("gram_tn_kernel");
+  LDS_CHECK_CUDA(launch_dependent(gram_tn_kernel, dim3((unsigned)ctas), dim3(SK_THREADS), smem, (cudaStream_t)stream, a_mat, lda, a, b_mat, ldb, b, n_rows, partial, counter, out, ldo));
   return LDS_OK;
 }

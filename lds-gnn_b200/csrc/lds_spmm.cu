@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(256)
 spmm_csr_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, const float* __restrict__ val,
                 const int32_t* __restrict__ perm, int rows, const float* __restrict__ B, int64_t ldb_row, int64_t ldb_col, int w,
                 float* __restrict__ Y, int64_t ldy) {
+  pdl_prologue();
   const int row = blockIdx.x * (256 / WP) + threadIdx.y;
   if (row >= rows) return;
   const int k0 = ptr[row], k1 = ptr[row + 1];
@@ -48,12 +49,11 @@ extern "C" int32_t lds_spmm_csr(const int32_t* ptr, const int32_t* idx, const fl
   LDS_CHECK_ARG(rows > 0 && w > 0 && ldy >= w, "lds_spmm_csr: need rows > 0, w > 0, ldy >= w");
   const cudaStream_t s = (cudaStream_t)stream;
   if (w <= 8) {
-    spmm_csr_kernel<8><<<(unsigned)ceil_div(rows, 32), dim3(8, 32), 0, s>>>(ptr, idx, val, perm, rows, b, ldb_row, ldb_col, w, y, ldy);
+    LDS_CHECK_CUDA(launch_dependent(spmm_csr_kernel<8>, dim3((unsigned)ceil_div(rows, 32)), dim3(8, 32), 0, s, ptr, idx, val, perm, rows, b, ldb_row, ldb_col, w, y, ldy));
   } else if (w <= 16) {
-    spmm_csr_kernel<16><<<(unsigned)ceil_div(rows, 16), dim3(16, 16), 0, s>>>(ptr, idx, val, perm, rows, b, ldb_row, ldb_col, w, y, ldy);
+    LDS_CHECK_CUDA(launch_dependent(spmm_csr_kernel<16>, dim3((unsigned)ceil_div(rows, 16)), dim3(16, 16), 0, s, ptr, idx, val, perm, rows, b, ldb_row, ldb_col, w, y, ldy));
   } else {
-    spmm_csr_kernel<32><<<(unsigned)ceil_div(rows, 8), dim3(32, 8), 0, s>>>(ptr, idx, val, perm, rows, b, ldb_row, ldb_col, w, y, ldy);
+    LDS_CHECK_CUDA(launch_dependent(spmm_csr_kernel<32>, dim3((unsigned)ceil_div(rows, 8)), dim3(32, 8), 0, s, ptr, idx, val, perm, rows, b, ldb_row, ldb_col, w, y, ldy));
   }
-  LDS_CHECK_LAUNCH("spmm_csr_kernel");
   return LDS_OK;
 }
