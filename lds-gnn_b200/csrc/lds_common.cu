@@ -38,6 +38,12 @@ static cudaEvent_t g_events[kMaxMarks];
 static int g_ids[kMaxMarks];
 static bool g_events_created = false;
 
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
 bool profile_active() { return g_profiling; }
 
 bool pdl_enabled() {

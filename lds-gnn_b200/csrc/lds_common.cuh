@@ -26,6 +26,12 @@ constexpr int kLdAlign = 64;          // theta / A_tilde row stride multiple (el
 constexpr int kNumSMsB200 = 148;
 
 int num_sms();                        // cached cudaDevAttrMultiProcessorCount of the current device
+int current_device();                 // cudaGetDevice (0 on failure), < kMaxDevices
+constexpr int kMaxDevices = 64;
+// One-time per-DEVICE initialisation flags (function attributes such as the dynamic shared-memory limit are per device, so a
+// process that drives several GPUs must set them on each): `if (first_use(flags)) { ...set attributes... }`.
+struct PerDeviceOnce { bool done[kMaxDevices] = {}; };
+inline bool first_use(PerDeviceOnce& o) { const int d = current_device(); if (o.done[d]) return false; o.done[d] = true; return true; }
 
 // Per-kernel timing of lds_outer_step for bench.py (lds_profile_begin/end): records a CUDA event after each launch.
 void profile_mark(cudaStream_t stream, int id);

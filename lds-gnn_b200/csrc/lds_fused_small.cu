@@ -439,7 +439,10 @@ bool fused_small_schedule(int n, int hp1, int hp2, K2Sched& s, int& kb_real) {
 
 // How many clusters of `cs` CTAs of the CLUSTER kernel can be resident at once (cached per cluster size; 0 = cannot).
 static int max_active_clusters(int cs) {
-  static int cache[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
+  static int cache_all[kMaxDevices][9];
+  static PerDeviceOnce once;
+  int* cache = cache_all[current_device()];
+  if (first_use(once)) for (int k = 0; k < 9; ++k) cache[k] = -1;
   if (cs < 1 || cs > 8) return 0;
   if (cache[cs] >= 0) return cache[cs];
   int n = 0;
@@ -457,7 +460,10 @@ static int max_active_clusters(int cs) {
 }
 
 int32_t fused_small_launch(const FusedSmallArgs& fa_in, cudaStream_t stream, bool allow_cluster) {
-  static int coop = -1;
+  static int coop_all[kMaxDevices];
+  static PerDeviceOnce once;
+  int& coop = coop_all[current_device()];
+  if (first_use(once)) coop = -1;
   if (coop < 0) {
     int dev = 0, v = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess) v = 0;
@@ -484,7 +490,8 @@ int32_t fused_small_launch(const FusedSmallArgs& fa_in, cudaStream_t stream, boo
   // LDS_FUSED_NO_CLUSTER: A/B switch for measurements. Nsight Compute (2025.2) dies on a launch that is both cooperative and
   // clustered (it reports grid (0,0,0) and exits with code 9), so under its injection library the L2 variant runs instead.
   static const bool env_no_cluster = getenv("LDS_FUSED_NO_CLUSTER") != nullptr || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr;
-  static bool cluster_broken = false;
+  static bool cluster_broken_all[kMaxDevices] = {};
+  bool& cluster_broken = cluster_broken_all[current_device()];
   const bool cluster = allow_cluster && !env_no_cluster && !cluster_broken && fa.parts >= 2 && fa.parts <= 8 && max_active_clusters(fa.parts) >= fa.s.panels;
   if (cluster) {                                             // one cluster per panel: reduction over distributed shared memory
     cudaLaunchConfig_t cfg = {};

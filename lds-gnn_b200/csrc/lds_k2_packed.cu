@@ -334,7 +334,8 @@ K2PSched k2p_make_schedule(int n, int rows, int hp) {
 template <int HP>
 static int32_t launch_mma(const CUtensorMap& tbh, const CUtensorMap& tbl, const uint32_t* bits, float* partial, const K2PSched& s,
                           bool use_lo, int b_rank_rows, cudaStream_t stream) {
-  LDS_CHECK_CUDA(cudaFuncSetAttribute(k2p_mma_kernel<HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2PCfg<HP>::SMEM_BYTES));
+  static PerDeviceOnce once;
+  if (first_use(once)) LDS_CHECK_CUDA(cudaFuncSetAttribute(k2p_mma_kernel<HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2PCfg<HP>::SMEM_BYTES));
   static const int dbg = getenv("LDS_K2P_DEBUG") ? atoi(getenv("LDS_K2P_DEBUG")) : 0;      // measurement switches: 1 no expansion, 2 no MMAs, 4 no bit loads, 8 no operand loads, 16 no drain stores
   k2p_mma_kernel<HP><<<s.grid, K2P_THREADS, K2PCfg<HP>::SMEM_BYTES, stream>>>(tbh, tbl, bits, partial, s, use_lo ? 1 : 0, b_rank_rows, dbg);
   LDS_CHECK_LAUNCH("k2p_mma_kernel");

@@ -308,11 +308,8 @@ static int32_t make_tmap_bf16(CUtensorMap* out, const void* base, int64_t cols, 
 template <int HP, int EPI>
 static int32_t launch_mma_t(const CUtensorMap& ta, const CUtensorMap& tbh, const CUtensorMap& tbl, float* partial, int* counters,
                             const K2Sched& s, bool use_lo, const EpiArgs& ea, int b_rank_rows, cudaStream_t stream, bool dependent = false) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    LDS_CHECK_CUDA(cudaFuncSetAttribute(k2_mma_kernel<HP, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2Cfg<HP>::SMEM_BYTES));
-    attr_set = true;
-  }
+  static PerDeviceOnce once;
+  if (first_use(once)) LDS_CHECK_CUDA(cudaFuncSetAttribute(k2_mma_kernel<HP, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2Cfg<HP>::SMEM_BYTES));
   static const bool no_pdl = getenv("LDS_NO_PDL") != nullptr;
   if (dependent && !no_pdl) {                                  // the previous kernel on the stream (operand pack) triggers its dependents
     cudaLaunchConfig_t cfg = {};

@@ -443,11 +443,10 @@ int32_t k3_launch_tc(float* theta, int64_t ldt, int n, int row0, int rows, const
   int32_t rc;
   if ((rc = make_tmap_2d(&tth, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, theta, n, rows, ldt, K3T_SLAB_COLS, K3T_TILE)) != LDS_OK) return rc;
   if ((rc = make_tmap_2d(&tf, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, f, kf, n, kf, K3T_KB, K3T_TILE)) != LDS_OK) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (first_use(once)) {
     LDS_CHECK_CUDA(cudaFuncSetAttribute(k3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K3T_SMEM));
     LDS_CHECK_CUDA(cudaFuncSetAttribute(k3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K3T_SMEM));
-    attr_set = true;
   }
   // Unsharded: the tile-symmetric launch (theta is symmetric). LDS_K3_FULL=1: A/B switch, every tile computed and stored on its own.
   static const bool force_full = getenv("LDS_K3_FULL") != nullptr;

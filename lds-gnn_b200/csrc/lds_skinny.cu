@@ -191,11 +191,9 @@ extern "C" int32_t lds_gram_tn(const float* a_mat, int64_t lda, int32_t a, const
     const int per = (int)ceil_div(n_rows, CS);
     const size_t smem = ((size_t)per * (a + b) + (size_t)(GC_THREADS / (a * b)) * a * b + (size_t)a * b) * sizeof(float);
     if (smem <= 200 * 1024) {
-      static size_t smem_set = 0;
-      if (smem > 48 * 1024 && smem > smem_set) {
+      static PerDeviceOnce once;
+      if (smem > 48 * 1024 && first_use(once))
         LDS_CHECK_CUDA(cudaFuncSetAttribute(gram_tn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-        smem_set = 200 * 1024;
-      }
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(CS); cfg.blockDim = dim3(GC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
       cudaLaunchAttribute at[2];

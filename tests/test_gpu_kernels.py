@@ -345,7 +345,8 @@ def test_sparse_linear_is_differentiable_to_second_order():
         assert (a - b).abs().max() <= 1e-4 * max(1.0, b.abs().max().item())
 
 
-@pytest.mark.parametrize("n,k,m", [(1, 1, 1), (130, 16, 6), (3327, 6, 16), (3327, 16, 16), (20000, 64, 7), (257, 128, 128), (1000, 3, 100)])
+@pytest.mark.parametrize("n,k,m", [(1, 1, 1), (130, 16, 6), (3327, 6, 16), (3327, 16, 16), (20000, 64, 7), (257, 128, 128), (1000, 3, 100),
+                                   (5, 2, 2), (8192, 16, 32), (8193, 16, 32)])      # cluster Gram: fewer rows than CTAs, its largest problem, the first one past it
 def test_row_linear_and_gram_tn_match_fp64_products(n, k, m):
     """lds_row_linear / lds_gram_tn (MetaLinear of layer_out and its autograd products, src/models/layers.py:43): against fp64
     torch products; strided (transposed) weights; the Gram reduction is bitwise reproducible and re-arms its own counter."""
