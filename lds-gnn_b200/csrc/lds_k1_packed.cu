@@ -20,11 +20,13 @@ namespace lds {
 template <bool EXPLICIT_U>
 __global__ void __launch_bounds__(K1P_THREADS, 4)
 k1p_sample_kernel(const __grid_constant__ K1PArgs a, const __grid_constant__ PhiloxRounds R) {
+  if (threadIdx.x == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the finalize kernel may be scheduled (pdl_prologue)
   k1p_warp_loop<EXPLICIT_U>(a, R, R.c2, R.c3, (int)(threadIdx.x & 31));
 }
 
 // deg = row sum (integer-valued, exact), r = deg^-1/2 with IEEE sqrt / divide like the reference; re-arms the counters.
 __global__ void k1p_finalize_kernel(int* __restrict__ cnt, int rows, float* __restrict__ deg, float* __restrict__ rs) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) cnt[rows] = 0;                                  // the chunk ticket
   if (i >= rows) return;
@@ -56,8 +58,7 @@ int32_t k1p_launch(const float* theta, int64_t ldt, int n, int row0, int rows, u
   if (u_explicit) k1p_sample_kernel<true><<<grid, K1P_THREADS, 0, stream>>>(a, R);
   else k1p_sample_kernel<false><<<grid, K1P_THREADS, 0, stream>>>(a, R);
   LDS_CHECK_LAUNCH("k1p_sample_kernel");
-  k1p_finalize_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, stream>>>(cnt, rows, deg, rs);
-  LDS_CHECK_LAUNCH("k1p_finalize_kernel");
+  LDS_CHECK_CUDA(launch_dependent(k1p_finalize_kernel, dim3((unsigned)ceil_div(rows, 256)), dim3(256), 0, stream, cnt, rows, deg, rs));
   return LDS_OK;
 }
 

@@ -115,6 +115,7 @@ k2p_mma_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant
   const int lo = cta * s.per_cta;
   const int hi = min(lo + s.per_cta, s.total);
 
+  if (threadIdx.x == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the epilogue kernel may be scheduled (see pdl_prologue)
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_bhi); tma_prefetch_desc(&tm_blo); }
   if (warp == 1) {
     if (lane == 0) {
@@ -131,6 +132,7 @@ k2p_mma_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");         // everything above overlaps the previous kernel of the step (dependent launch)
 
   if (warp == 0) {
     // ===== producer of the skinny-operand tiles =====
@@ -268,6 +270,7 @@ template <int HP, int EPI>
 __global__ void __launch_bounds__(512)
 k2p_epilogue_kernel(const float* __restrict__ partial, const K2PSched s, const __grid_constant__ EpiArgs ea, const int alt, const int use_lo) {
   __shared__ float red[16][2];
+  pdl_prologue();
   constexpr int Q = HP / 4;
   const int etid = threadIdx.x, warp = etid >> 5, lane = etid & 31;
   const int p = blockIdx.x, sp = p >> 1, tile = p & 1;
@@ -337,22 +340,23 @@ static int32_t launch_mma(const CUtensorMap& tbh, const CUtensorMap& tbl, const 
   static PerDeviceOnce once;
   if (first_use(once)) LDS_CHECK_CUDA(cudaFuncSetAttribute(k2p_mma_kernel<HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2PCfg<HP>::SMEM_BYTES));
   static const int dbg = getenv("LDS_K2P_DEBUG") ? atoi(getenv("LDS_K2P_DEBUG")) : 0;      // measurement switches: 1 no expansion, 2 no MMAs, 4 no bit loads, 8 no operand loads, 16 no drain stores
-  k2p_mma_kernel<HP><<<s.grid, K2P_THREADS, K2PCfg<HP>::SMEM_BYTES, stream>>>(tbh, tbl, bits, partial, s, use_lo ? 1 : 0, b_rank_rows, dbg);
-  LDS_CHECK_LAUNCH("k2p_mma_kernel");
+  LDS_CHECK_CUDA(launch_dependent(k2p_mma_kernel<HP>, dim3((unsigned)s.grid), dim3(K2P_THREADS), (size_t)K2PCfg<HP>::SMEM_BYTES, stream,
+                                  tbh, tbl, bits, partial, s, use_lo ? 1 : 0, b_rank_rows, dbg));
   return LDS_OK;
 }
 
 template <int HP>
 static int32_t launch_epi(int epi, const float* partial, const K2PSched& s, const EpiArgs& ea, int alt, int use_lo, int panels, cudaStream_t stream) {
+  cudaError_t err = cudaSuccess;
   switch (epi) {
-    case K2_EPI_PLAIN:  k2p_epilogue_kernel<HP, K2_EPI_PLAIN><<<panels, 512, 0, stream>>>(partial, s, ea, alt, use_lo); break;
-    case K2_EPI_LAYER1: k2p_epilogue_kernel<HP, K2_EPI_LAYER1><<<panels, 512, 0, stream>>>(partial, s, ea, alt, use_lo); break;
-    case K2_EPI_LAYER2: k2p_epilogue_kernel<HP, K2_EPI_LAYER2><<<panels, 512, 0, stream>>>(partial, s, ea, alt, use_lo); break;
-    case K2_EPI_BWD2:   k2p_epilogue_kernel<HP, K2_EPI_BWD2><<<panels, 512, 0, stream>>>(partial, s, ea, alt, use_lo); break;
-    case K2_EPI_BWD1:   k2p_epilogue_kernel<HP, K2_EPI_BWD1><<<panels, 512, 0, stream>>>(partial, s, ea, alt, use_lo); break;
+    case K2_EPI_PLAIN:  err = launch_dependent(k2p_epilogue_kernel<HP, K2_EPI_PLAIN>, dim3((unsigned)panels), dim3(512), 0, stream, partial, s, ea, alt, use_lo); break;
+    case K2_EPI_LAYER1: err = launch_dependent(k2p_epilogue_kernel<HP, K2_EPI_LAYER1>, dim3((unsigned)panels), dim3(512), 0, stream, partial, s, ea, alt, use_lo); break;
+    case K2_EPI_LAYER2: err = launch_dependent(k2p_epilogue_kernel<HP, K2_EPI_LAYER2>, dim3((unsigned)panels), dim3(512), 0, stream, partial, s, ea, alt, use_lo); break;
+    case K2_EPI_BWD2:   err = launch_dependent(k2p_epilogue_kernel<HP, K2_EPI_BWD2>, dim3((unsigned)panels), dim3(512), 0, stream, partial, s, ea, alt, use_lo); break;
+    case K2_EPI_BWD1:   err = launch_dependent(k2p_epilogue_kernel<HP, K2_EPI_BWD1>, dim3((unsigned)panels), dim3(512), 0, stream, partial, s, ea, alt, use_lo); break;
     default: set_error("k2 (packed): unknown epilogue %d", epi); return LDS_ERR_ARG;
   }
-  LDS_CHECK_LAUNCH("k2p_epilogue_kernel");
+  if (err != cudaSuccess) return cuda_fail(err, "k2p_epilogue_kernel");
   return LDS_OK;
 }
 

@@ -136,6 +136,7 @@ feat_linear_kernel(const float* __restrict__ x, int64_t ldx, int n, int f, const
                    DropCfg dc, const float* __restrict__ rs, float* __restrict__ p1, int64_t ldr,
                    __nv_bfloat16* __restrict__ bt_hi, __nv_bfloat16* __restrict__ bt_lo, int64_t ldb, int hp,
                    int row0, float* __restrict__ opnd, int64_t ld_opnd) {
+  pdl_prologue();
   __shared__ float tile[EPI_MAXW][EPI_ROWS + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * EPI_ROWS;
@@ -231,6 +232,7 @@ feat_sparse_kernel(const int32_t* __restrict__ crow, const int32_t* __restrict__
                    DropCfg dc, const float* __restrict__ rs, float* __restrict__ p1, int64_t ldr,
                    __nv_bfloat16* __restrict__ bt_hi, __nv_bfloat16* __restrict__ bt_lo, int64_t ldb, int hp,
                    int row0, float* __restrict__ opnd, int64_t ld_opnd) {
+  pdl_prologue();
   __shared__ float tile[EPI_MAXW][EPI_ROWS + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * EPI_ROWS;
@@ -524,13 +526,11 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
     profile_mark(stream, 0);
     const dim3 egrid((unsigned)L.nblk);
     if (sparse_x) {
-      feat_sparse_kernel<<<egrid, EPI_THREADS, 0, stream>>>(A.x_crow, A.x_col, A.x_val, rows, A.f, fbuf(B_W0S), A.b0, A.h, dx, fbuf(B_RS), fbuf(B_P1), L.ldr,
-                                                            out_hi(L.hp1, 0), out_lo(L.hp1, 0), out_ld, L.hp1, row0, opnd, ld_opnd);
-      LDS_CHECK_LAUNCH("feat_sparse_kernel");
+      LDS_CHECK_CUDA(launch_dependent(feat_sparse_kernel, egrid, dim3(EPI_THREADS), 0, stream, A.x_crow, A.x_col, A.x_val, rows, A.f, fbuf(B_W0S), A.b0, A.h, dx,
+                                      fbuf(B_RS), fbuf(B_P1), L.ldr, out_hi(L.hp1, 0), out_lo(L.hp1, 0), out_ld, L.hp1, row0, opnd, ld_opnd));
     } else {
-      feat_linear_kernel<<<egrid, FEAT_THREADS, 0, stream>>>(A.x, A.ld_x, rows, A.f, fbuf(B_W0S), round_up(A.f, 4), A.b0, A.h, dx, fbuf(B_RS), fbuf(B_P1), L.ldr,
-                                                             out_hi(L.hp1, 0), out_lo(L.hp1, 0), out_ld, L.hp1, row0, opnd, ld_opnd);
-      LDS_CHECK_LAUNCH("feat_linear_kernel");
+      LDS_CHECK_CUDA(launch_dependent(feat_linear_kernel, egrid, dim3(FEAT_THREADS), 0, stream, A.x, A.ld_x, rows, A.f, fbuf(B_W0S), round_up(A.f, 4), A.b0, A.h, dx,
+                                      fbuf(B_RS), fbuf(B_P1), L.ldr, out_hi(L.hp1, 0), out_lo(L.hp1, 0), out_ld, L.hp1, row0, opnd, ld_opnd));
     }
     profile_mark(stream, 1);
   }
@@ -595,11 +595,11 @@ extern "C" int32_t lds_outer_step(const lds_outer_step_args* args, void* stream_
   if ((phases & LDS_PHASE_UPDATE) && A.update && (S == 1 || (int)smp == S - 1)) {
     const float* cv = sharded ? A.c_full : fbuf(B_C);
     if (S > 1) {                                              // mean of the S single-sample gradients: one pass, K = S * kf
-      rc = k3_launch_tc(A.theta_full, A.ld_theta, A.n, 0, rows, A.fpack_multi, S * L.kf, cv, A.lr / (float)S, stream, fused_done && !profile_active());
+      rc = k3_launch_tc(A.theta_full, A.ld_theta, A.n, 0, rows, A.fpack_multi, S * L.kf, cv, A.lr / (float)S, stream, (fused_done || packed) && !profile_active());
     } else if (tc_update) {
       const void* f = sharded ? A.f_full : buf(B_F);
       LDS_CHECK_ARG((reinterpret_cast<uintptr_t>(cv) & 15) == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0, "lds_outer_step: c_full / f_full must be 16-byte aligned");
-      rc = k3_launch_tc(A.theta_full, A.ld_theta, A.n, row0, rows, f, L.kf, cv, A.lr, stream, fused_done && !profile_active());
+      rc = k3_launch_tc(A.theta_full, A.ld_theta, A.n, row0, rows, f, L.kf, cv, A.lr, stream, (fused_done || packed) && !profile_active());
     } else {
       const float* fa = sharded ? A.fa_full : fbuf(B_FA);
       const float* fb = sharded ? A.fb_full : fbuf(B_FB);
