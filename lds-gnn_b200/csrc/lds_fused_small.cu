@@ -99,6 +99,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
   __shared__ K2EpiShared sh_epi;
   __shared__ unsigned long long sh_base;
   __shared__ int sh_rowpair;                                 // ticket of the feature-row pairs of this CTA
+  __shared__ float sh_w1[FS_HP * FS_HP], sh_b1[FS_HP];       // layer_out's weights for the leader's row epilogues (CLUSTER)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sa = smem;                                        // resident A tiles
@@ -248,6 +249,10 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
 
   // ================= P1: expand this CTA's tiles into shared memory; degrees, r, first operand =================
   if (cta == 0 && tid == 0) fa.gridbar[2] = 0u;              // every CTA is past the split barrier: re-arm it for the next launch
+  if (CLUSTER && smp == 0 && tid >= 512) {                   // warps 16-17 do not expand tiles: layer_out's weights -> shared memory
+    for (int k = tid - 512; k < ea.c * ea.h; k += 64) sh_w1[k] = ea.w1[k];
+    if (tid - 512 < ea.c) sh_b1[tid - 512] = ea.b1[tid - 512];
+  }
   if (tid < 512) {
     // row r of tile j: 64 bits (even / odd column words, lds_packed.cuh) -> 64 bf16 {0, 1} in the UMMA K-major SWIZZLE_128B
     // layout (16-byte chunk c of row r sits at chunk c ^ (r & 7)). The bits were written by other SMs: read them through L2.
@@ -382,8 +387,12 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
         // (loss, acc): the layer-2 phase of EVERY panel is complete here — cluster 0 covers all k-blocks, so its CTAs have
         // consumed every panel's phase-1 flag, and each leader wrote its loss partial before its flag
         if (ph == 2 && my_p == 0 && etid == 0) finalize_scalars(ea);
-        if (ph == 0) epi_layer1<FS_HP>(ea, i, g, v, alt);
-        else if (ph == 2) epi_bwd2<FS_HP>(ea, i, g, v, alt);
+        // W1 / b1 from shared memory: the cluster barrier's acquire has just invalidated L1, and data-dependent %globaltimer
+        // stamps put 2.0 of the 3.1 us of the layer-1 epilogue on its two trips through rows of W1 in global memory
+        EpiArgs es = ea;
+        es.w1 = sh_w1; es.b1 = sh_b1;
+        if (ph == 0) epi_layer1<FS_HP>(es, i, g, v, alt);
+        else if (ph == 2) epi_bwd2<FS_HP>(es, i, g, v, alt);
         else if (ph == 3) epi_bwd1<FS_HP>(ea, i, g, v);
         else {
           float li, ci;

@@ -41,3 +41,17 @@ print(f"{act.sum()} CTAs")
 for j, nm in enumerate(names):
     col = t[:, j]; col = col[col > 0]
     if len(col) and nm: print(f"   {nm:12s} n={len(col):4d}  min {(col.min()-t0)/1e3:7.2f} us  median {(np.median(col)-t0)/1e3:7.2f}  max {(col.max()-t0)/1e3:7.2f}")
+# per-leader view: (epilogue done - partial tiles summed) of every panel leader and phase
+lead = t[:, 19] > 0
+ids = np.nonzero(act)[0][lead]
+tt = t[lead]
+print("leader CTA : epilogue us (ph0..3) | summed-synced | barrier wait after the epilogue")
+for k in range(len(ids)):
+    row = [f"{(tt[k, 5 + 2 * p] - tt[k, 19 + 4 * p]) / 1e3:5.2f}" for p in range(4)]
+    syn = [f"{(tt[k, 19 + 4 * p] - tt[k, 18 + 4 * p]) / 1e3:5.2f}" for p in range(4)]
+    bar = [f"{(tt[k, 6 + 2 * p] - tt[k, 5 + 2 * p]) / 1e3:5.2f}" for p in range(4)]
+    print(f"  cta {ids[k]:3d}: {' '.join(row)} | {' '.join(syn)} | {' '.join(bar)}")
+if tt[:, 24].max() > 0:
+    print("layer-1 epilogue of the leaders, us after the cluster sync (median): sum ready, r loaded, dropout flags, relu done, linear trip 0, trip 1, end, epi_done stamp")
+    base = tt[:, 18]
+    print("   ", " ".join(f"{np.median(tt[:, s] - base) / 1e3:6.2f}" for s in (19, 24, 25, 26, 27, 28, 29, 30, 5)))
