@@ -87,6 +87,50 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_smem_addr, uint32_t
   return v;
 }
 
+// epi_bwd2 (lds_epilogue.cuh) for the CLUSTER variant at HP = 16: same arithmetic in the same order, but the row's dP2 goes
+// to the other lanes of its quad through shared memory (`rowbuf`: the row's 16 floats of the partial-tile buffer, which this
+// quad has just summed and nobody else reads) and the product with W1 is a rolled loop over the C classes: ~150 instructions
+// instead of ~970 (16 shuffles and 16 predicated 4-wide steps, unrolled for the padded width).
+__device__ __forceinline__ void fs_bwd2(const EpiArgs& a, int i, int g, float (&v)[4], bool alt, float* rowbuf) {
+  const bool live = i < a.n;
+  const int il = live ? i : a.n - 1;
+  const float ri = a.rs[il];
+  float k[4] = {0.f, 0.f, 0.f, 0.f}, z1[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool mine = 4 * g < a.h;
+  if (mine) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const int c = 4 * g + e; z1[e] = (c < a.h) ? a.z1[(int64_t)c * a.ldr + il] : 0.f; }
+    drop_quad(a.drop_h, il, a.row0 + il, g, a.h, k);
+  }
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const int o = g * 4 + kk;
+    v[kk] = (o < a.c) ? ri * v[kk] : 0.f;
+    if (live && o < a.c) a.dp2[(int64_t)o * a.ldr + i] = v[kk];
+  }
+  *reinterpret_cast<float4*>(rowbuf + 4 * g) = make_float4(v[0], v[1], v[2], v[3]);
+  __syncwarp();
+  if (mine) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+    for (int o = 0; o < a.c; ++o) {
+      const float dpo = rowbuf[o];
+      const float* wrow = a.w1 + o * a.h + 4 * g;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) if (4 * g + e < a.h) acc[e] = fmaf(dpo, wrow[e], acc[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = 4 * g + e;
+      if (live && c < a.h) {
+        const float dz = (z1[e] > 0.f) ? acc[e] * k[e] : 0.f;
+        a.dz1[(int64_t)c * a.ldr + i] = dz;
+        store_operand(a, alt, c, i, ri * dz);
+      }
+    }
+  }
+}
+
 // CLUSTER = true: launched with cluster dimension = CTAs per panel. The split-K partial tiles of a panel stay in the
 // shared memory of the CTAs that produced them (in the operand buffer, idle once the MMAs have retired); after a
 // cluster barrier the cluster's rank-0 CTA sums them over DISTRIBUTED shared memory in rank order (deterministic) and
@@ -392,7 +436,7 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
         EpiArgs es = ea;
         es.w1 = sh_w1; es.b1 = sh_b1;
         if (ph == 0) epi_layer1<FS_HP>(es, i, g, v, alt);
-        else if (ph == 2) epi_bwd2<FS_HP>(es, i, g, v, alt);
+        else if (ph == 2) fs_bwd2(es, i, g, v, alt, reinterpret_cast<float*>(sb) + row * FS_HP);
         else if (ph == 3) epi_bwd1<FS_HP>(ea, i, g, v);
         else {
           float li, ci;
