@@ -73,6 +73,31 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned l
   ++k;
 }
 
+// The same barrier in two halves: everything the CTA must publish is written, it arrives, does work that only touches its own
+// shared memory, then waits. Hides the barrier's two L2 round trips (and the other CTAs' skew) behind that work.
+__device__ __forceinline__ void grid_barrier_arrive(unsigned long long* bar) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("fence.proxy.async;" ::: "memory");
+    asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(bar) : "memory");
+  }
+}
+__device__ __forceinline__ void grid_barrier_wait(unsigned long long* bar, unsigned long long base, unsigned& k, unsigned nctas) {
+  if (threadIdx.x == 0) {
+    const unsigned long long want = base + (unsigned long long)(k + 1) * nctas;
+    long long t0 = 0;
+    for (unsigned spins = 0; ld_acquire_u64(bar) < want; ++spins) {
+      if (spins == 64) t0 = clock64();
+      if (spins > 64 && (spins & 255) == 0 && clock64() - t0 > 4000000000ll) {
+        printf("liblds_b200: grid barrier timed out (block %d, barrier %u)\n", blockIdx.x, k);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  ++k;
+}
+
 // ---- thread-block cluster helpers (CLUSTER variant: the CTAs of one 128-row panel form a cluster) ----
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {          // every thread of every CTA of the cluster
@@ -297,6 +322,27 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
     for (int k = tid - 512; k < ea.c * ea.h; k += 64) sh_w1[k] = ea.w1[k];
     if (tid - 512 < ea.c) sh_b1[tid - 512] = ea.b1[tid - 512];
   }
+  {
+    // deg = integer row count (exact), r = deg^-1/2 with IEEE sqrt / divide like the reference; operand (r P1)^T as bf16 hi/lo
+    const int nr = r_hi - r_lo;
+    for (int idx = tid; idx < nr * FS_HP; idx += K2_THREADS) {
+      const int c = idx / nr, i = r_lo + (idx - c * nr);
+      const float d = (float)__ldcg(fa.k1.cnt + i);
+      const float ri = 1.0f / sqrtf(d);
+      if (c == 0) { fa.deg[i] = d; fa.rs[i] = ri; }
+      if (c < ea.h) {
+        __nv_bfloat16 bh, bl;
+        split_bf16(ri * ea.p1[(int64_t)c * ea.ldr + i], bh, bl);
+        ea.bt_hi[(int64_t)c * ea.ldb + i] = bh;
+        ea.bt_lo[(int64_t)c * ea.ldb + i] = bl;
+      }
+    }
+    // Everything other CTAs wait for (r, deg, the first operand) is written: arrive at the grid barrier now and expand the
+    // tiles — work on this CTA's own shared memory — while the arrivals and the barrier's L2 round trips are in flight.
+    grid_barrier_arrive(gbar);
+    for (int idx = tid; idx < nr; idx += K2_THREADS) fa.k1.cnt[r_lo + idx] = 0;      // re-arm the row counters (this CTA is their only reader)
+    if (tid == 0) sh_rowpair = 0;
+  }
   if (tid < 512) {
     // row r of tile j: 64 bits (even / odd column words, lds_packed.cuh) -> 64 bf16 {0, 1} in the UMMA K-major SWIZZLE_128B
     // layout (16-byte chunk c of row r sits at chunk c ^ (r & 7)). The bits were written by other SMs: read them through L2.
@@ -324,28 +370,9 @@ fused_small_kernel(const __grid_constant__ CUtensorMap tm_bhi, const __grid_cons
       }
     }
   }
-  {
-    // deg = integer row count (exact), r = deg^-1/2 with IEEE sqrt / divide like the reference; operand (r P1)^T as bf16 hi/lo
-    const int nr = r_hi - r_lo;
-    for (int idx = tid; idx < nr * FS_HP; idx += K2_THREADS) {
-      const int c = idx / nr, i = r_lo + (idx - c * nr);
-      const float d = (float)__ldcg(fa.k1.cnt + i);
-      const float ri = 1.0f / sqrtf(d);
-      if (c == 0) { fa.deg[i] = d; fa.rs[i] = ri; }
-      if (c < ea.h) {
-        __nv_bfloat16 bh, bl;
-        split_bf16(ri * ea.p1[(int64_t)c * ea.ldr + i], bh, bl);
-        ea.bt_hi[(int64_t)c * ea.ldb + i] = bh;
-        ea.bt_lo[(int64_t)c * ea.ldb + i] = bl;
-      }
-    }
-    __syncthreads();
-    for (int idx = tid; idx < nr; idx += K2_THREADS) fa.k1.cnt[r_lo + idx] = 0;      // re-arm the row counters (this CTA is their only reader)
-    if (tid == 0) sh_rowpair = 0;
-  }
   fence_proxy_async_smem();                                  // generic-proxy smem writes -> visible to tcgen05.mma
   stamp(3);
-  grid_barrier(gbar, gbase, gk, gridDim.x);
+  grid_barrier_wait(gbar, gbase, gk, gridDim.x);
   stamp(4);
 
   // ================= P2: the four propagations from the resident tiles =================
