@@ -365,7 +365,11 @@ def run_ours(args, rank, world, device):
     h2d_bytes = total * 4
     state = {"i": 0}
     # (Tried: the upload on its own stream with an event, so that it overlaps the previous step's backward half — e2e 8.9 k vs
-    # 9.2 k steps/s: the extra stream switch / event calls cost the host more than the 10 us copy costs the GPU.)
+    # 9.2 k steps/s: the extra stream switch / event calls cost the host more than the 10 us copy costs the GPU.
+    # Tried: no copy at all — the trainer is handed PINNED HOST tensors and the fused kernel's weight-staging warps read W0
+    # straight over PCIe (source-order, full 128-byte lines, under the sampling phase; b0 / W1 / b1 to shared memory):
+    # bit-identical results, but SM-initiated reads of host memory reach only ~4 GB/s here — 237 KB took ~55 us, e2e 7.0 k
+    # against 10.3 k steps/s with the copy engine (200-step loops, one box). The copy engine stays.)
 
     def api_step():
         i = state["i"] & 1
@@ -374,7 +378,7 @@ def run_ours(args, rank, world, device):
         inner.model_params.update(param_sets[i])
         return outer.train_step(inner.model_forward)           # returns host floats (device -> host read inside)
 
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 30)):                      # untimed: the host side (allocator, caches, branch history) settles too
         api_step()
     assert outer.last_route == "fused", "bench e2e must exercise the fused CUDA path"
     torch.cuda.synchronize()
