@@ -364,8 +364,9 @@ def run_ours(args, rank, world, device):
         param_sets.append(views)
     h2d_bytes = total * 4
     state = {"i": 0}
-    # (Tried: the upload on its own stream with an event, so that it overlaps the previous step's backward half — e2e 8.9 k vs
-    # 9.2 k steps/s: the extra stream switch / event calls cost the host more than the 10 us copy costs the GPU.
+    same_stream_upload = os.environ.get("LDS_BENCH_E2E_UPLOAD") == "stream"      # A/B switch: torch copy_ on the compute stream
+    # (Round 1: the upload on its own stream with an event through torch's Python stream API cost the host more than the 10 us
+    # copy costs the GPU — e2e 8.9 k vs 9.2 k steps/s; as three driver calls inside one C call (lds_upload_async) it pays.
     # Tried: no copy at all — the trainer is handed PINNED HOST tensors and the fused kernel's weight-staging warps read W0
     # straight over PCIe (source-order, full 128-byte lines, under the sampling phase; b0 / W1 / b1 to shared memory):
     # bit-identical results, but SM-initiated reads of host memory reach only ~4 GB/s here — 237 KB took ~55 us, e2e 7.0 k
@@ -374,7 +375,11 @@ def run_ours(args, rank, world, device):
     def api_step():
         i = state["i"] & 1
         state["i"] += 1
-        dev_flats[i].copy_(host_flat, non_blocking=True)       # this step's fast weights: pinned host -> device
+        if same_stream_upload:
+            dev_flats[i].copy_(host_flat, non_blocking=True)   # this step's fast weights: pinned host -> device
+        else:
+            K.upload_async(dev_flats[i], host_flat)            # ... on the library's copy stream (lds_upload_async): the transfer
+                                                               # overlaps the previous step's backward half and theta update
         inner.model_params.update(param_sets[i])
         return outer.train_step(inner.model_forward)           # returns host floats (device -> host read inside)
 

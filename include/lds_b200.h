@@ -369,6 +369,13 @@ int32_t lds_eval_metrics(const float* logp, int32_t samples, int32_t n, int32_t 
                          const uint8_t* mask_a, int32_t count_a, const uint8_t* mask_b, int32_t count_b,
                          float* out4, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Host -> device upload of a step's inputs on a copy stream owned by the library. The reference keeps its GCN weights on the
+ * device (src/trainers/inner.py:42-50); a caller whose fast weights arrive from the host every step (bench.py's e2e arm) uploads
+ * them with this call instead of a copy on its compute stream: the transfer overlaps the work still executing on `stream`, and
+ * everything enqueued on `stream` afterwards is ordered behind it. `dst_device` must not be read or written by work already
+ * enqueued (alternate two buffers); `src_pinned_host` must stay unchanged until the copy has run. */
+int32_t lds_upload_async(void* dst_device, const void* src_pinned_host, int64_t bytes, void* stream);
+
 /* ---- measurement hook for bench.py (not part of the reference-facing surface). Between begin and end,
  * lds_outer_step records a CUDA event on its stream after every kernel launch. lds_profile_end synchronises on
  * the last event and returns the number of intervals written: ms_out[i] = device time of the launch whose id is

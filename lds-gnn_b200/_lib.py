@@ -82,6 +82,7 @@ SIGNATURES = {
     "lds_edges_to_dense": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
     "lds_edge_offsets": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "lds_remove_edges_apply": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "lds_upload_async": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p]),
     "lds_profile_begin": (c_int32, []),
     "lds_profile_end": (c_int32, [c_void_p, c_void_p, c_int32]),
 }

@@ -127,6 +127,28 @@ peer_push_kernel(const uint4* __restrict__ src, uint8_t* const* __restrict__ dst
 }
 }  // namespace lds
 
+// Upload of a step's inputs (the GCN weights of an outer step that arrive from the host) on a stream of the library's own:
+// the copy overlaps whatever is still executing on `stream` (the backward half and the theta update of the previous step),
+// and work enqueued on `stream` after this call sees the data. Three driver calls, no host synchronisation.
+extern "C" int32_t lds_upload_async(void* dst_device, const void* src_pinned_host, int64_t bytes, void* stream) {
+  LDS_CHECK_ARG(dst_device && src_pinned_host && bytes > 0, "lds_upload_async: bad arguments");
+  static cudaStream_t side[lds::kMaxDevices];
+  static cudaEvent_t ev[lds::kMaxDevices][8];
+  static unsigned turn[lds::kMaxDevices];
+  static lds::PerDeviceOnce once;
+  const int d = lds::current_device();
+  if (lds::first_use(once)) {
+    LDS_CHECK_CUDA(cudaStreamCreateWithFlags(&side[d], cudaStreamNonBlocking));
+    for (int k = 0; k < 8; ++k) LDS_CHECK_CUDA(cudaEventCreateWithFlags(&ev[d][k], cudaEventDisableTiming));
+    turn[d] = 0;
+  }
+  cudaEvent_t e = ev[d][turn[d]++ & 7];
+  LDS_CHECK_CUDA(cudaMemcpyAsync(dst_device, src_pinned_host, (size_t)bytes, cudaMemcpyHostToDevice, side[d]));
+  LDS_CHECK_CUDA(cudaEventRecord(e, side[d]));
+  LDS_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, e, 0));
+  return LDS_OK;
+}
+
 extern "C" int32_t lds_peer_push(const void* src, void* const* dst_bases, int32_t world, int64_t dst_offset_bytes, int64_t bytes, void* stream) {
   LDS_CHECK_ARG(src && dst_bases && world > 0 && world <= 64, "lds_peer_push: bad arguments");
   LDS_CHECK_ARG(bytes > 0 && bytes % 16 == 0 && dst_offset_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0,

@@ -16,6 +16,17 @@ def _stream():
     return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
 
 
+def upload_async(dst, src_pinned):
+    """dst (CUDA tensor) <- src_pinned (pinned host tensor, same dtype / numel) on the library's copy stream; work enqueued on
+    the current stream afterwards is ordered behind the copy (lds_upload_async). `dst` must not be in use by enqueued work."""
+    if not dst.is_cuda or src_pinned.is_cuda or dst.dtype != src_pinned.dtype or dst.numel() != src_pinned.numel() \
+            or not dst.is_contiguous() or not src_pinned.is_contiguous():
+        raise TypeError("upload_async: contiguous CUDA destination and pinned host source of the same dtype and size")
+    lib = _lib.load()
+    _lib.check(lib.lds_upload_async(ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(src_pinned.data_ptr()),
+                                    dst.numel() * dst.element_size(), _stream()), "lds_upload_async")
+
+
 def _ptr(t):
     return ctypes.c_void_p(0 if t is None else t.data_ptr())
 

@@ -494,3 +494,24 @@ def test_row_block_model_steps_through_the_same_train_step():
         assert abs(sa[k] - sb[k]) <= 1e-5 * max(1.0, abs(sa[k])), k
     block.project_parameters()
     assert float(block.probs.min()) >= 0.0 and float(block.probs.max()) <= 1.0
+
+
+def test_upload_async_orders_later_work_behind_the_copy():
+    """kernels.upload_async (lds_upload_async): the copy runs on the library's own stream, and work enqueued on the current
+    stream afterwards reads the uploaded data — also while the current stream is still busy with earlier work."""
+    from lds_gnn_b200 import kernels as K
+    n = 1 << 20
+    src = [torch.full((n,), float(k + 1)).pin_memory() for k in range(2)]
+    dst = [torch.zeros(n, device="cuda") for _ in range(2)]
+    busy = torch.randn(4096, 4096, device="cuda")
+    sums = []
+    for k in range(6):
+        for _ in range(3):
+            busy = (busy @ busy).clamp_(-1, 1)                            # keeps the compute stream occupied
+        src[k & 1].fill_(float(k + 1)) if k < 2 else None
+        K.upload_async(dst[k & 1], src[k & 1])
+        sums.append(dst[k & 1].sum())                                     # enqueued after the upload: must see it
+    torch.cuda.synchronize()
+    assert [float(s) for s in sums] == [float(n * ((k & 1) + 1)) for k in range(6)]
+    with pytest.raises(TypeError):
+        K.upload_async(dst[0], dst[1])
