@@ -438,7 +438,8 @@ def run_ours(args, rank, world, device):
                         "single-GPU figure is each line's scaling_reference, not this line",
         "clocks": clock_info,
         "e2e": {"value": round(total_steps / (e2e_ms / 1e3), 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
-                "api": "OuterProblemTrainer.train_step(InnerProblemTrainer.model_forward)", "l2": "not flushed"},
+                "api": "OuterProblemTrainer.train_step(InnerProblemTrainer.model_forward)", "l2": "not flushed",
+                "warmup_steps": max(args.warmup, 30), "upload": "torch copy_ on the compute stream" if same_stream_upload else "lds_upload_async (copy stream of the library)"},
         # fused small-graph kernel + K3K4 (S samples: S fused launches + one K3K4), else 8 launches per step
         "gpu_launches": ((samples + 1) if 10 in per_kernel else LAUNCHES_PER_STEP * samples) * args.steps,
         "roofline": roofline,
