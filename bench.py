@@ -383,15 +383,15 @@ def run_ours(args, rank, world, device):
         inner.model_params.update(param_sets[i])
         return outer.train_step(inner.model_forward)           # returns host floats (device -> host read inside)
 
+    import gc
+    gc.collect()                                           # before the warm-up: a collection is milliseconds of idle GPU, and the first
+    gc.disable()                                           # steps after an idle gap run slower; no collector pauses in the timed region
     for _ in range(max(args.warmup, 30)):                      # untimed: the host side (allocator, caches, branch history) settles too
         api_step()
     assert outer.last_route == "fused", "bench e2e must exercise the fused CUDA path"
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    import gc
-    gc.collect()
-    gc.disable()                                           # no collector pauses inside the (short) timed region
     t_start = time.perf_counter()
     for _ in range(args.steps):
         m = api_step()
