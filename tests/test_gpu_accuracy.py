@@ -5,8 +5,9 @@ tests/golden/accuracy_live_reference_<shape>.json holds the final validation / t
 container by oracle/accuracy_live_reference.py — no code shared with this package except the synthetic dataset generator.
 The same datasets (same seeds), hyper-parameters and stopping rule run here through the package on the GPU (captured bilevel
 blocks, factored hypergradient, Philox sampling). The two arms draw different random numbers, so runs are not comparable one
-by one; the north star asks for the MEAN final validation accuracy within 0.5 pt over 5 seeds — with the 3 seeds the CPU
-reference could afford the tolerance here is 1.5 pt on the means and 4 pt on any single seed (datasets differ by seed far
+by one; the north star asks for the MEAN final validation accuracy within 0.5 pt over 5 seeds — with the 3 (Cora shape) / 2
+(Citeseer shape) seeds the CPU reference could afford (10 / 25 minutes per seed) the tolerance here is 1.5 pt on the means and
+4 pt on any single seed; measured: +0.10 / -0.21 pt validation, -0.12 / -0.38 pt test (datasets differ by seed far
 more than the arms do: 0.92-0.96 across seeds)."""
 import argparse
 import importlib.util
@@ -28,9 +29,11 @@ def _parity_module():
     return mod
 
 
-@pytest.mark.parametrize("shape", ["cora"])
+@pytest.mark.parametrize("shape", ["cora", "citeseer"])
 def test_final_accuracy_matches_the_live_reference(shape):
     path = os.path.join(HERE, "golden", f"accuracy_live_reference_{shape}.json")
+    if not os.path.exists(path):
+        pytest.skip(f"no live-reference run committed for the {shape} shape (oracle/accuracy_live_reference.py)")
     gold = json.load(open(path))
     a = gold["args"]
     args = argparse.Namespace(hidden=a["hidden"], dropout=a["dropout"], gcn_lr=a["gcn_lr"], gcn_wd=a["gcn_wd"], lds_lr=a["lds_lr"],
